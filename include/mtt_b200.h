@@ -1,0 +1,128 @@
+/*
+ * mtt_b200.h -- C ABI of libmtt_sm100.so: the sm_100a kernels behind the TaskPrompter / InvPT
+ * forward hot path (reference: prismformore/Multi-Task-Transformer).
+ *
+ * The reference has no FFI of its own: its hot path is PyTorch eager ops called from nn.Module
+ * forwards. Each entry point below replaces the eager-op sequence named in its comment
+ * (file:line relative to the reference root; TP = TaskPrompter/, IP = InvPT/). The Python host
+ * (multi-task-transformer_b200/) binds these with ctypes; INTEGRATION.md shows the binding a
+ * reference maintainer would add.
+ *
+ * Conventions
+ *  - Plain C: pointers are DEVICE pointers owned by the caller; the library never allocates,
+ *    frees or synchronises; every call only enqueues work on `stream` (a cudaStream_t).
+ *  - Return value: 0 = OK, negative = mtt_status; text via mtt_last_error() (thread local).
+ *  - "split" tensors: an fp32 value x is carried as two bf16 planes, hi = bf16(x) and
+ *    lo = bf16(x - hi), with identical layout. nsplit = 2 uses both planes (3 tensor-core MMAs per
+ *    product: hi*hi + hi*lo + lo*hi, ~2^-17 relative error, the parity mode); nsplit = 1 uses only
+ *    the hi plane (plain bf16, the speed mode). lo pointers may be NULL when nsplit = 1.
+ *  - All leading dimensions are in ELEMENTS.
+ */
+#ifndef MTT_B200_H_
+#define MTT_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* mtt_stream_t; /* cudaStream_t */
+
+enum mtt_status {
+  MTT_OK = 0,
+  MTT_ERR_BAD_SHAPE = -1,
+  MTT_ERR_UNSUPPORTED_ARCH = -2,
+  MTT_ERR_MISALIGNED = -3,
+  MTT_ERR_LAUNCH = -4,
+  MTT_ERR_DRIVER = -5
+};
+
+enum mtt_act { MTT_ACT_NONE = 0, MTT_ACT_GELU = 1, MTT_ACT_RELU = 2 };
+
+/* ---- library ---------------------------------------------------------------------------- */
+int mtt_version(void);
+const char* mtt_last_error(void);
+/* 0 iff the current device is compute capability 10.x; the kernels are sm_100a only. */
+int mtt_device_check(void);
+/* number of kernel launches issued by this library on the calling thread since the last reset */
+int64_t mtt_launch_count(void);
+void mtt_launch_count_reset(void);
+
+/* ---- fp32 -> split bf16 planes ------------------------------------------------------------
+ * Used for weight pre-packing and for inputs produced outside the library.
+ * rows x cols fp32 (ld_in) -> hi/lo bf16 (ld_out); columns [cols, cols_pad) are written as zero. */
+int mtt_split_f32(const float* in, int64_t ld_in, void* out_hi, void* out_lo, int64_t ld_out,
+                  int64_t rows, int32_t cols, int32_t cols_pad, mtt_stream_t stream);
+
+/* ---- LayerNorm over the last dim ---------------------------------------------------------
+ * Replaces nn.LayerNorm calls: TP/models/transformers/taskprompter.py:272,274,277,413;
+ * IP/models/transformers/vit.py:212-213,349; IP/models/transformers/invpt.py:298,307,526.
+ * in [rows, cols] fp32 -> out_f32 (optional) and/or split bf16 (optional). */
+int mtt_layernorm(const float* in, int64_t ld_in, const float* gamma, const float* beta, float eps,
+                  float* out_f32, int64_t ld_f32, void* out_hi, void* out_lo, int64_t ld_bf,
+                  int64_t rows, int32_t cols, mtt_stream_t stream);
+
+/* ---- GEMM / implicit-GEMM convolution on tcgen05 -----------------------------------------
+ * D[m, n] = act( sum_k A[m, k] * Bw[n, k] + bias[n] ) + residual[m, n]
+ * mode 0 (linear): A is [M, lda] row-major. Replaces nn.Linear / 1x1 Conv2d:
+ *   TP taskprompter.py:201 (qkv), :212 (proj), timm Mlp fc1/fc2 (:274,:277), :447,:468 (1x1
+ *   decode convs), :362 (fea_fuse 1x1), :695 (linear_pred); IP vit.py:186,192, invpt.py:200-202.
+ * mode 1 (conv): A is an NHWC activation [B, H, W, lda]; ksize x ksize taps, stride 1, dilation
+ *   dil, zero padding dil*(ksize-1)/2. Bw is [N, ksize*ksize*cin_pad] with cin_pad = K rounded up
+ *   to 64 (tap-major, zero padded). M = B*H*W. Replaces nn.Conv2d 3x3 (+ folded eval BatchNorm):
+ *   TP taskprompter.py:362 (fea_fuse 3x3), :691 (ConvHead.mt_proj); IP transformer_decoder.py:113,
+ *   invpt.py:33-38 (dilated), :493 (mt_proj).
+ * Output rows can be regrouped: r_out = (r / in_group) * out_group + out_offset + r % in_group
+ * (in_group = 0: identity); used to scatter patch rows into the joint [prompts; patches] stream. */
+typedef struct {
+  const void* a_hi;
+  const void* a_lo;
+  int64_t lda;
+  const void* b_hi;
+  const void* b_lo;
+  int64_t ldb;
+  int32_t M, N, K;
+  int32_t nsplit;
+  int32_t mode;
+  int32_t B, H, W, ksize, dil;
+  const float* bias;
+  int32_t act;
+  const float* residual;
+  int64_t ldr;
+  int32_t res_row_mod; /* >0: residual row = r % res_row_mod (row-broadcast, e.g. pos_embed) */
+  float* out_f32;
+  int64_t ldo_f32;
+  void* out_hi;
+  void* out_lo;
+  int64_t ldo_bf;
+  int32_t in_group, out_group, out_offset;
+} mtt_gemm_desc;
+
+int mtt_gemm(const mtt_gemm_desc* d, mtt_stream_t stream);
+
+/* ---- fused multi-head attention over the joint [prompts; patches] sequence ----------------
+ * Replaces TP taskprompter.py:204-210 (raw = q k^T, softmax(raw*scale), attn @ v) and IP
+ * vit.py:189-193, without materialising the [B,H,N,N] maps. qkv is the split output of the qkv
+ * GEMM, [B*N, 3*H*64] with column order (q|k|v, head, 64) exactly as taskprompter.py:201 reshapes
+ * it. out is [B*N, H*64] split. If prompt_logits != NULL the raw, UN-scaled logits of query rows
+ * [0, T) are written as fp32 [B, H, T, N] (the only part of `raw_spa_attn` the reference consumes:
+ * taskprompter.py:436-437, :482). head_dim must be 64. */
+typedef struct {
+  const void* qkv_hi;
+  const void* qkv_lo;
+  void* out_hi;
+  void* out_lo;
+  float* prompt_logits;
+  int32_t B, N, H, T;
+  int32_t nsplit;
+  float scale;
+} mtt_attn_desc;
+
+int mtt_attention(const mtt_attn_desc* d, mtt_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MTT_B200_H_ */

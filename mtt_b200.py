@@ -1,0 +1,13 @@
+"""Import alias: the package lives in ``multi-task-transformer_b200/`` (a name Python cannot import
+directly because of the hyphens); ``import mtt_b200`` loads it under an importable name."""
+import importlib.util
+import os
+import sys
+
+_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "multi-task-transformer_b200")
+_spec = importlib.util.spec_from_file_location(
+    "mtt_b200", os.path.join(_dir, "__init__.py"), submodule_search_locations=[_dir]
+)
+_mod = importlib.util.module_from_spec(_spec)
+sys.modules["mtt_b200"] = _mod
+_spec.loader.exec_module(_mod)

@@ -1,0 +1,300 @@
+// Fused multi-head attention for the joint [prompts; patches] token sequence (head_dim 64).
+//
+// Replaces, per (batch, head), the eager sequence of TP/models/transformers/taskprompter.py:204-210
+//   raw = q @ k^T ; attn = softmax(raw * scale) ; x = attn @ v
+// (and IP/models/transformers/vit.py:189-193) without materialising the [B,H,N,N] maps, and emits
+// the only part of `raw` the reference ever consumes: the un-scaled logits of the first T (prompt)
+// query rows (taskprompter.py:436-437 spatial gates, :482 cross-task reweighting).
+//
+// One CTA = one 128-row query tile of one (b, h); keys/values stream in blocks of 128 by TMA.
+//   S = Q K^T          tcgen05.mma SS, fp32 accumulator in TMEM (128 columns)
+//   P = exp2(S*c - m)  registers; written back IN PLACE over S as packed bf16 hi/lo planes
+//   O_blk = P V        tcgen05.mma with A = P from TMEM, B = V from smem (MN-major), TMEM 64 columns
+//   O = O*alpha + O_blk  in registers (one query row per thread), online softmax
+// Split-bf16 operands (NSPLIT = 2): every product is 3 MMAs, as in gemm_tc.cu.
+// The CTA is deliberately simple (no warp specialisation): 96 KB smem and 256 TMEM columns let two
+// CTAs share an SM, so one CTA's softmax overlaps the other's MMAs.
+#include <math.h>
+
+#include "host_common.h"
+#include "ptx.cuh"
+
+namespace mtt {
+
+constexpr int kAttnThreads = 128;
+constexpr int kAttnTmemCols = 256;
+constexpr uint32_t kAttnTile = 128 * 64 * 2;  // 16 KB: 128 rows x 64 bf16
+
+struct AttnParams {
+  int B, N, H, T;
+  float scale_log2;  // scale * log2(e)
+  __nv_bfloat16* out_hi;
+  __nv_bfloat16* out_lo;
+  float* prompt_logits;
+};
+
+template <int NSPLIT>
+__global__ void __launch_bounds__(kAttnThreads, 2)
+attention_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
+                 const AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* sQ = smem;                          // [NSPLIT][16 KB]
+  uint8_t* sK = sQ + NSPLIT * kAttnTile;
+  uint8_t* sV = sK + NSPLIT * kAttnTile;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + NSPLIT * kAttnTile);
+  uint64_t* bar_q = bars + 0;
+  uint64_t* bar_k = bars + 1;
+  uint64_t* bar_v = bars + 2;
+  uint64_t* bar_s = bars + 3;
+  uint64_t* bar_o = bars + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int C = p.H * 64;
+  const int q0 = qt * 128;
+  const int nkv = (p.N + 127) / 128;
+
+  if (tid == 0) {
+    tma_prefetch_desc(&tm_hi);
+    if (NSPLIT == 2) tma_prefetch_desc(&tm_lo);
+    mbar_init(bar_q, 1);
+    mbar_init(bar_k, 1);
+    mbar_init(bar_v, 1);
+    mbar_init(bar_s, 1);
+    mbar_init(bar_o, 1);
+    fence_barrier_init();
+  }
+  __syncwarp();
+  if (warp == 0) tmem_alloc<kAttnTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tS = tmem_base;        // S / P: columns [0, 128)
+  const uint32_t tO = tmem_base + 128;  // O_blk:  columns [128, 192)
+  const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+
+  if (tid == 0) {
+    mbar_arrive_expect_tx(bar_q, NSPLIT * kAttnTile);
+    tma_load_3d(sQ, &tm_hi, bar_q, h * 64, q0, b);
+    if (NSPLIT == 2) tma_load_3d(sQ + kAttnTile, &tm_lo, bar_q, h * 64, q0, b);
+    mbar_arrive_expect_tx(bar_k, NSPLIT * kAttnTile);
+    tma_load_3d(sK, &tm_hi, bar_k, C + h * 64, 0, b);
+    if (NSPLIT == 2) tma_load_3d(sK + kAttnTile, &tm_lo, bar_k, C + h * 64, 0, b);
+    mbar_arrive_expect_tx(bar_v, NSPLIT * kAttnTile);
+    tma_load_3d(sV, &tm_hi, bar_v, 2 * C + h * 64, 0, b);
+    if (NSPLIT == 2) tma_load_3d(sV + kAttnTile, &tm_lo, bar_v, 2 * C + h * 64, 0, b);
+  }
+  __syncwarp();
+
+  float o_acc[64];
+#pragma unroll
+  for (int i = 0; i < 64; ++i) o_acc[i] = 0.f;
+  float m_run = -INFINITY, l_run = 0.f;
+  const int q_row = q0 + tid;
+  const bool export_row = (p.prompt_logits != nullptr) && (q_row < p.T);
+  float* export_ptr =
+      export_row ? p.prompt_logits + (((long long)b * p.H + h) * p.T + q_row) * p.N : nullptr;
+
+  for (int j = 0; j < nkv; ++j) {
+    const uint32_t ph = j & 1;
+    const int kn = min(128, p.N - j * 128);  // valid keys in this block
+    const int kn16 = (kn + 15) & ~15;        // MMA N (S) / K extent (PV)
+    if (tid == 0) {
+      if (j == 0) mbar_wait(bar_q, 0);
+      mbar_wait(bar_k, ph);
+      tc_fence_after();
+      const uint32_t idesc_s = umma_idesc_bf16(128, kn16, 0);
+      const uint32_t qh = smem_u32(sQ), kh = smem_u32(sK);
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        const uint64_t qdh = umma_desc_sw128(qh + ks * 32);
+        const uint64_t kdh = umma_desc_sw128(kh + ks * 32);
+        umma_ss(tS, qdh, kdh, idesc_s, ks > 0);
+        if (NSPLIT == 2) {
+          const uint64_t qdl = umma_desc_sw128(qh + kAttnTile + ks * 32);
+          const uint64_t kdl = umma_desc_sw128(kh + kAttnTile + ks * 32);
+          umma_ss(tS, qdh, kdl, idesc_s, 1);
+          umma_ss(tS, qdl, kdh, idesc_s, 1);
+        }
+      }
+      umma_commit(bar_s);
+    }
+    __syncwarp();
+    mbar_wait(bar_s, ph);
+    tc_fence_after();
+    if (tid == 0 && j + 1 < nkv) {  // K buffer is free again: prefetch the next key block
+      mbar_arrive_expect_tx(bar_k, NSPLIT * kAttnTile);
+      tma_load_3d(sK, &tm_hi, bar_k, C + h * 64, (j + 1) * 128, b);
+      if (NSPLIT == 2) tma_load_3d(sK + kAttnTile, &tm_lo, bar_k, C + h * 64, (j + 1) * 128, b);
+    }
+    __syncwarp();
+
+    // ---- pass 1: row maximum over the valid columns (and prompt-row logit export)
+    const int nchunk = (kn16 + 31) >> 5;
+    float mx = -INFINITY;
+    for (int c = 0; c < nchunk; ++c) {
+      uint32_t r[32];
+      tmem_ld32(tS + lane_addr + c * 32, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const float s = __uint_as_float(r[i]);
+        if (c * 32 + i < kn) mx = fmaxf(mx, s);
+      }
+      if (export_row) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (c * 32 + i < kn) export_ptr[j * 128 + c * 32 + i] = __uint_as_float(r[i]);
+      }
+    }
+    const float m_new = fmaxf(m_run, mx);
+    const float alpha = exp2f((m_run - m_new) * p.scale_log2);
+    const float mb = m_new * p.scale_log2;
+    m_run = m_new;
+
+    // ---- pass 2: P = exp2(S*c - m*c), written in place as packed bf16 hi | lo (16 + 16 columns)
+    float l_blk = 0.f;
+    for (int c = 0; c < nchunk; ++c) {
+      uint32_t r[32];
+      tmem_ld32(tS + lane_addr + c * 32, r);
+      tmem_ld_wait();
+      uint32_t ph_[16], pl_[16];
+#pragma unroll
+      for (int i = 0; i < 32; i += 2) {
+        float p0 = exp2f(__uint_as_float(r[i]) * p.scale_log2 - mb);
+        float p1 = exp2f(__uint_as_float(r[i + 1]) * p.scale_log2 - mb);
+        if (c * 32 + i >= kn) p0 = 0.f;
+        if (c * 32 + i + 1 >= kn) p1 = 0.f;
+        l_blk += p0 + p1;
+        split_pack2(p0, p1, ph_[i >> 1], pl_[i >> 1]);
+      }
+      tmem_st16(tS + lane_addr + c * 32, ph_);
+      if (NSPLIT == 2) tmem_st16(tS + lane_addr + c * 32 + 16, pl_);
+    }
+    tmem_st_wait();
+    tc_fence_before();
+    __syncthreads();
+
+    if (tid == 0) {
+      tc_fence_after();
+      mbar_wait(bar_v, ph);
+      tc_fence_after();
+      constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, 1);
+      const uint32_t vh = smem_u32(sV);
+      const int ksteps = kn16 >> 4;
+      for (int ks = 0; ks < ksteps; ++ks) {
+        const uint32_t a_hi = tS + (ks >> 1) * 32 + (ks & 1) * 8;
+        const uint64_t vdh = umma_desc_sw128(vh + ks * 2048);
+        umma_ts(tO, a_hi, vdh, idesc_o, ks > 0);
+        if (NSPLIT == 2) {
+          const uint64_t vdl = umma_desc_sw128(vh + kAttnTile + ks * 2048);
+          umma_ts(tO, a_hi, vdl, idesc_o, 1);
+          umma_ts(tO, a_hi + 16, vdh, idesc_o, 1);
+        }
+      }
+      umma_commit(bar_o);
+    }
+    __syncwarp();
+    mbar_wait(bar_o, ph);
+    tc_fence_after();
+    if (tid == 0 && j + 1 < nkv) {  // V buffer is free again
+      mbar_arrive_expect_tx(bar_v, NSPLIT * kAttnTile);
+      tma_load_3d(sV, &tm_hi, bar_v, 2 * C + h * 64, (j + 1) * 128, b);
+      if (NSPLIT == 2) tma_load_3d(sV + kAttnTile, &tm_lo, bar_v, 2 * C + h * 64, (j + 1) * 128, b);
+    }
+    __syncwarp();
+    l_run = l_run * alpha + l_blk;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t r[32];
+      tmem_ld32(tO + lane_addr + c * 32, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) o_acc[c * 32 + i] = o_acc[c * 32 + i] * alpha + __uint_as_float(r[i]);
+    }
+    tc_fence_before();
+  }
+
+  if (q_row < p.N) {
+    const float inv = 1.0f / l_run;
+    const long long off = ((long long)b * p.N + q_row) * C + h * 64;
+#pragma unroll
+    for (int i = 0; i < 64; i += 8) {
+      uint4 hv, lv;
+      split_pack2(o_acc[i] * inv, o_acc[i + 1] * inv, hv.x, lv.x);
+      split_pack2(o_acc[i + 2] * inv, o_acc[i + 3] * inv, hv.y, lv.y);
+      split_pack2(o_acc[i + 4] * inv, o_acc[i + 5] * inv, hv.z, lv.z);
+      split_pack2(o_acc[i + 6] * inv, o_acc[i + 7] * inv, hv.w, lv.w);
+      *reinterpret_cast<uint4*>(p.out_hi + off + i) = hv;
+      if (NSPLIT == 2) *reinterpret_cast<uint4*>(p.out_lo + off + i) = lv;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc<kAttnTmemCols>(tmem_base);
+  }
+}
+
+template <int NSPLIT>
+static int launch_attn(const CUtensorMap& mh, const CUtensorMap& ml, const AttnParams& p,
+                       cudaStream_t stream) {
+  constexpr uint32_t smem = 3 * NSPLIT * kAttnTile + 1024 + 128;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(attention_kernel<NSPLIT>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess)
+      return set_error(MTT_ERR_LAUNCH, "attention: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  dim3 grid((p.N + 127) / 128, p.H, p.B);
+  attention_kernel<NSPLIT><<<grid, kAttnThreads, smem, stream>>>(mh, ml, p);
+  return check_launch("mtt_attention");
+}
+
+}  // namespace mtt
+
+extern "C" int mtt_attention(const mtt_attn_desc* d, mtt_stream_t stream_) {
+  using namespace mtt;
+  if (!d) return set_error(MTT_ERR_BAD_SHAPE, "mtt_attention: null descriptor");
+  if (d->B <= 0 || d->N <= 0 || d->H <= 0 || d->T < 0 || d->T > d->N)
+    return set_error(MTT_ERR_BAD_SHAPE, "mtt_attention: B=%d N=%d H=%d T=%d", d->B, d->N, d->H, d->T);
+  if (d->nsplit != 1 && d->nsplit != 2)
+    return set_error(MTT_ERR_BAD_SHAPE, "mtt_attention: nsplit=%d", d->nsplit);
+  if (!d->qkv_hi || !d->out_hi || (d->nsplit == 2 && (!d->qkv_lo || !d->out_lo)))
+    return set_error(MTT_ERR_BAD_SHAPE, "mtt_attention: missing plane");
+  if (d->T > 128) return set_error(MTT_ERR_BAD_SHAPE, "mtt_attention: T=%d > 128 unsupported", d->T);
+  if ((reinterpret_cast<uintptr_t>(d->out_hi) & 15) || (d->out_lo && (reinterpret_cast<uintptr_t>(d->out_lo) & 15)))
+    return set_error(MTT_ERR_MISALIGNED, "mtt_attention: output not 16-byte aligned");
+  const int C = d->H * 64;
+  CUtensorMap mh, ml;
+  const uint64_t dims[3] = {(uint64_t)3 * C, (uint64_t)d->N, (uint64_t)d->B};
+  const uint64_t str[2] = {(uint64_t)3 * C * 2, (uint64_t)d->N * 3 * C * 2};
+  const uint32_t box[3] = {64, 128, 1};
+  int rc;
+  if ((rc = make_tmap_bf16(&mh, d->qkv_hi, 3, dims, str, box))) return rc;
+  if (d->nsplit == 2) {
+    if ((rc = make_tmap_bf16(&ml, d->qkv_lo, 3, dims, str, box))) return rc;
+  } else {
+    ml = mh;
+  }
+  AttnParams p;
+  p.B = d->B;
+  p.N = d->N;
+  p.H = d->H;
+  p.T = d->prompt_logits ? d->T : 0;
+  p.scale_log2 = d->scale * 1.4426950408889634f;
+  p.out_hi = static_cast<__nv_bfloat16*>(d->out_hi);
+  p.out_lo = static_cast<__nv_bfloat16*>(d->out_lo);
+  p.prompt_logits = d->prompt_logits;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  return d->nsplit == 2 ? launch_attn<2>(mh, ml, p, stream) : launch_attn<1>(mh, ml, p, stream);
+}

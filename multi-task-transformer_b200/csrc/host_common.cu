@@ -1,0 +1,112 @@
+#include "host_common.h"
+
+#include <cudaTypedefs.h>
+#include <stdarg.h>
+#include <stdio.h>
+
+namespace mtt {
+
+static thread_local char g_err[512] = "";
+static thread_local int64_t g_launches = 0;
+
+int set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+void count_launch() { ++g_launches; }
+
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess)
+    return set_error(MTT_ERR_LAUNCH, "%s: launch failed: %s", what, cudaGetErrorString(e));
+  count_launch();
+  return MTT_OK;
+}
+
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  }
+  return fn;
+}
+
+int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                   const uint64_t* strides_bytes, const uint32_t* box) {
+  auto enc = get_encode();
+  if (!enc) return set_error(MTT_ERR_DRIVER, "cuTensorMapEncodeTiled entry point not found");
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0)
+    return set_error(MTT_ERR_MISALIGNED, "TMA base pointer %p is not 16-byte aligned", base);
+  for (int i = 0; i + 1 < rank; ++i)
+    if (strides_bytes[i] % 16 != 0)
+      return set_error(MTT_ERR_MISALIGNED, "TMA stride %d = %llu bytes is not a multiple of 16", i,
+                       (unsigned long long)strides_bytes[i]);
+  cuuint64_t gdim[5];
+  cuuint64_t gstr[4];
+  cuuint32_t bx[5], estr[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bx[i] = box[i];
+    estr[i] = 1;
+    if (i + 1 < rank) gstr[i] = strides_bytes[i];
+  }
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base),
+                   gdim, gstr, bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    return set_error(MTT_ERR_DRIVER,
+                     "cuTensorMapEncodeTiled failed (%d): rank %d dims [%llu,%llu,%llu,%llu,%llu] box "
+                     "[%u,%u,%u,%u,%u]",
+                     (int)r, rank, (unsigned long long)dims[0],
+                     (unsigned long long)(rank > 1 ? dims[1] : 0),
+                     (unsigned long long)(rank > 2 ? dims[2] : 0),
+                     (unsigned long long)(rank > 3 ? dims[3] : 0),
+                     (unsigned long long)(rank > 4 ? dims[4] : 0), box[0], rank > 1 ? box[1] : 0,
+                     rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0, rank > 4 ? box[4] : 0);
+  }
+  return MTT_OK;
+}
+
+int sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return n;
+}
+
+}  // namespace mtt
+
+extern "C" {
+
+int mtt_version(void) { return 100; }
+
+const char* mtt_last_error(void) { return mtt::g_err; }
+
+int mtt_device_check(void) {
+  int dev = 0, major = 0, minor = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess)
+    return mtt::set_error(MTT_ERR_UNSUPPORTED_ARCH, "no CUDA device");
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
+  if (major != 10)
+    return mtt::set_error(MTT_ERR_UNSUPPORTED_ARCH,
+                          "device compute capability %d.%d; this library is sm_100a only", major,
+                          minor);
+  return MTT_OK;
+}
+
+int64_t mtt_launch_count(void) { return mtt::g_launches; }
+void mtt_launch_count_reset(void) { mtt::g_launches = 0; }
+}

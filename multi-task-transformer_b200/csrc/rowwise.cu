@@ -1,0 +1,131 @@
+// Row-wise HBM-bound kernels: fp32 -> split-bf16 cast and LayerNorm with split output.
+// One warp per row, float4 loads, warp-shuffle reductions.
+#include "host_common.h"
+#include "ptx.cuh"
+
+namespace mtt {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__global__ void __launch_bounds__(256)
+split_kernel(const float* __restrict__ in, long long ld_in, __nv_bfloat16* __restrict__ hi,
+             __nv_bfloat16* __restrict__ lo, long long ld_out, long long rows, int cols, int cols_pad) {
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const float* src = in + row * ld_in;
+  __nv_bfloat16* dh = hi + row * ld_out;
+  __nv_bfloat16* dl = lo ? lo + row * ld_out : nullptr;
+  for (int c = lane; c < cols_pad; c += 32) {
+    const float x = c < cols ? src[c] : 0.f;
+    __nv_bfloat16 h, l;
+    split_bf16(x, h, l);
+    dh[c] = h;
+    if (dl) dl[c] = l;
+  }
+}
+
+// LayerNorm, biased variance, two-pass statistics like ATen's CPU/CUDA kernels
+// (reference: nn.LayerNorm at TP/models/transformers/taskprompter.py:262,266,329).
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const float* __restrict__ in, long long ld_in, const float* __restrict__ gamma,
+                 const float* __restrict__ beta, float eps, float* __restrict__ out_f32,
+                 long long ld_f32, __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo,
+                 long long ld_bf, long long rows, int cols) {
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const float* src = in + row * ld_in;
+  const bool vec = ((cols & 3) == 0) && ((ld_in & 3) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(in) & 15) == 0);
+  float s = 0.f;
+  if (vec) {
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+    for (int c = lane; c < cols / 4; c += 32) {
+      const float4 v = s4[c];
+      s += (v.x + v.y) + (v.z + v.w);
+    }
+  } else {
+    for (int c = lane; c < cols; c += 32) s += src[c];
+  }
+  const float mean = warp_sum(s) / (float)cols;
+  float ss = 0.f;
+  if (vec) {
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+    for (int c = lane; c < cols / 4; c += 32) {
+      const float4 v = s4[c];
+      const float a = v.x - mean, b = v.y - mean, cc = v.z - mean, d = v.w - mean;
+      ss += (a * a + b * b) + (cc * cc + d * d);
+    }
+  } else {
+    for (int c = lane; c < cols; c += 32) {
+      const float a = src[c] - mean;
+      ss += a * a;
+    }
+  }
+  const float var = warp_sum(ss) / (float)cols;
+  const float rstd = 1.0f / sqrtf(var + eps);
+  for (int c = lane * 2; c < cols; c += 64) {
+    const bool two = c + 1 < cols;
+    const float y0 = (src[c] - mean) * rstd * gamma[c] + beta[c];
+    const float y1 = two ? (src[c + 1] - mean) * rstd * gamma[c + 1] + beta[c + 1] : 0.f;
+    if (out_f32) {
+      out_f32[row * ld_f32 + c] = y0;
+      if (two) out_f32[row * ld_f32 + c + 1] = y1;
+    }
+    if (out_hi) {
+      if (two && ((ld_bf & 1) == 0)) {
+        uint32_t h, l;
+        split_pack2(y0, y1, h, l);
+        *reinterpret_cast<uint32_t*>(out_hi + row * ld_bf + c) = h;
+        if (out_lo) *reinterpret_cast<uint32_t*>(out_lo + row * ld_bf + c) = l;
+      } else {
+        __nv_bfloat16 h, l;
+        split_bf16(y0, h, l);
+        out_hi[row * ld_bf + c] = h;
+        if (out_lo) out_lo[row * ld_bf + c] = l;
+        if (two) {
+          split_bf16(y1, h, l);
+          out_hi[row * ld_bf + c + 1] = h;
+          if (out_lo) out_lo[row * ld_bf + c + 1] = l;
+        }
+      }
+    }
+  }
+}
+
+}  // namespace mtt
+
+extern "C" int mtt_split_f32(const float* in, int64_t ld_in, void* out_hi, void* out_lo,
+                             int64_t ld_out, int64_t rows, int32_t cols, int32_t cols_pad,
+                             mtt_stream_t stream) {
+  using namespace mtt;
+  if (!in || !out_hi || rows <= 0 || cols <= 0 || cols_pad < cols || ld_out < cols_pad)
+    return set_error(MTT_ERR_BAD_SHAPE, "mtt_split_f32: bad arguments (rows=%lld cols=%d pad=%d)",
+                     (long long)rows, cols, cols_pad);
+  const int wpb = 8;
+  const long long blocks = (rows + wpb - 1) / wpb;
+  split_kernel<<<(unsigned)blocks, wpb * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+      in, ld_in, static_cast<__nv_bfloat16*>(out_hi), static_cast<__nv_bfloat16*>(out_lo), ld_out, rows,
+      cols, cols_pad);
+  return check_launch("mtt_split_f32");
+}
+
+extern "C" int mtt_layernorm(const float* in, int64_t ld_in, const float* gamma, const float* beta,
+                             float eps, float* out_f32, int64_t ld_f32, void* out_hi, void* out_lo,
+                             int64_t ld_bf, int64_t rows, int32_t cols, mtt_stream_t stream) {
+  using namespace mtt;
+  if (!in || !gamma || !beta || rows <= 0 || cols <= 0 || (!out_f32 && !out_hi))
+    return set_error(MTT_ERR_BAD_SHAPE, "mtt_layernorm: bad arguments (rows=%lld cols=%d)",
+                     (long long)rows, cols);
+  const int wpb = 8;
+  const long long blocks = (rows + wpb - 1) / wpb;
+  layernorm_kernel<<<(unsigned)blocks, wpb * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+      in, ld_in, gamma, beta, eps, out_f32, ld_f32, static_cast<__nv_bfloat16*>(out_hi),
+      static_cast<__nv_bfloat16*>(out_lo), ld_bf, rows, cols);
+  return check_launch("mtt_layernorm");
+}

@@ -1,0 +1,78 @@
+"""ctypes binding of libmtt_sm100.so (the C ABI declared in include/mtt_b200.h).
+
+There is no fallback: if the shared library is missing or a call fails, a RuntimeError is raised.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmtt_sm100.so")
+
+ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2
+
+
+class GemmDesc(C.Structure):
+    _fields_ = [
+        ("a_hi", C.c_void_p), ("a_lo", C.c_void_p), ("lda", C.c_int64),
+        ("b_hi", C.c_void_p), ("b_lo", C.c_void_p), ("ldb", C.c_int64),
+        ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32),
+        ("nsplit", C.c_int32), ("mode", C.c_int32),
+        ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("ksize", C.c_int32), ("dil", C.c_int32),
+        ("bias", C.c_void_p), ("act", C.c_int32),
+        ("residual", C.c_void_p), ("ldr", C.c_int64), ("res_row_mod", C.c_int32),
+        ("out_f32", C.c_void_p), ("ldo_f32", C.c_int64),
+        ("out_hi", C.c_void_p), ("out_lo", C.c_void_p), ("ldo_bf", C.c_int64),
+        ("in_group", C.c_int32), ("out_group", C.c_int32), ("out_offset", C.c_int32),
+    ]
+
+
+class AttnDesc(C.Structure):
+    _fields_ = [
+        ("qkv_hi", C.c_void_p), ("qkv_lo", C.c_void_p),
+        ("out_hi", C.c_void_p), ("out_lo", C.c_void_p),
+        ("prompt_logits", C.c_void_p),
+        ("B", C.c_int32), ("N", C.c_int32), ("H", C.c_int32), ("T", C.c_int32),
+        ("nsplit", C.c_int32), ("scale", C.c_float),
+    ]
+
+
+# name -> (restype, argtypes); every symbol include/mtt_b200.h declares
+_i64, _i32, _f32, _vp = C.c_int64, C.c_int32, C.c_float, C.c_void_p
+SYMBOLS = {
+    "mtt_version": (C.c_int, []),
+    "mtt_last_error": (C.c_char_p, []),
+    "mtt_device_check": (C.c_int, []),
+    "mtt_launch_count": (C.c_int64, []),
+    "mtt_launch_count_reset": (None, []),
+    "mtt_split_f32": (C.c_int, [_vp, _i64, _vp, _vp, _i64, _i64, _i32, _i32, _vp]),
+    "mtt_layernorm": (C.c_int, [_vp, _i64, _vp, _vp, _f32, _vp, _i64, _vp, _vp, _i64, _i64, _i32, _vp]),
+    "mtt_gemm": (C.c_int, [C.POINTER(GemmDesc), _vp]),
+    "mtt_attention": (C.c_int, [C.POINTER(AttnDesc), _vp]),
+}
+
+_lib = None
+
+
+def load():
+    """Load the shared library (once). Raises RuntimeError when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). There is no CPU or eager fallback."
+        )
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().mtt_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"{what} failed ({rc}): {msg}")

@@ -1,0 +1,149 @@
+"""Tensor-level wrappers over the C ABI (include/mtt_b200.h).
+
+PyTorch is used for device memory and streams only: every function here enqueues one library
+kernel on ``torch.cuda.current_stream()`` and returns. Nothing in this module computes with torch
+ops on the hot path.
+"""
+import ctypes as C
+
+import torch
+
+from . import lib as _L
+
+ACT_NONE, ACT_GELU, ACT_RELU = _L.ACT_NONE, _L.ACT_GELU, _L.ACT_RELU
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def round_up(x, m):
+    return (x + m - 1) // m * m
+
+
+class Split:
+    """An fp32-valued [rows, cols] matrix carried as bf16 planes hi (= bf16(x)) and lo (= bf16(x - hi)).
+
+    Storage is one [nsplit, rows, ld] bf16 tensor; ``ld`` (elements) is a multiple of 8 so that TMA
+    row strides are 16-byte aligned."""
+
+    __slots__ = ("buf", "rows", "cols", "ld", "nsplit")
+
+    def __init__(self, rows, cols, device, nsplit=2, ld=None, zero=False):
+        self.rows, self.cols, self.nsplit = int(rows), int(cols), int(nsplit)
+        self.ld = int(ld) if ld is not None else round_up(self.cols, 8)
+        alloc = torch.zeros if zero else torch.empty
+        self.buf = alloc((self.nsplit, self.rows, self.ld), dtype=torch.bfloat16, device=device)
+
+    @property
+    def hi(self):
+        return self.buf[0]
+
+    @property
+    def lo(self):
+        return self.buf[1] if self.nsplit == 2 else None
+
+    def float(self):
+        """Reconstruct the fp32 values (testing / debugging only)."""
+        x = self.buf[0, :, : self.cols].float()
+        if self.nsplit == 2:
+            x = x + self.buf[1, :, : self.cols].float()
+        return x
+
+
+def split_f32(x, nsplit=2, cols_pad=None, out=None):
+    """fp32 [rows, cols] (last dim contiguous) -> Split. Columns [cols, cols_pad) are zero."""
+    assert x.dtype == torch.float32 and x.dim() == 2 and x.stride(1) == 1
+    rows, cols = x.shape
+    cols_pad = cols if cols_pad is None else cols_pad
+    if out is None:
+        out = Split(rows, cols_pad, x.device, nsplit, ld=round_up(cols_pad, 8))
+    lib = _L.load()
+    rc = lib.mtt_split_f32(_ptr(x), x.stride(0), _ptr(out.hi), _ptr(out.lo), out.ld, rows, cols,
+                           cols_pad, _stream())
+    _L.check(rc, "mtt_split_f32")
+    return out
+
+
+def layernorm(x, gamma, beta, eps, out_f32=None, out_split=None):
+    """x fp32 [rows, cols] -> out_f32 (fp32 tensor) and/or out_split (Split)."""
+    assert x.dtype == torch.float32 and x.dim() == 2 and x.stride(1) == 1
+    rows, cols = x.shape
+    lib = _L.load()
+    rc = lib.mtt_layernorm(
+        _ptr(x), x.stride(0), _ptr(gamma), _ptr(beta), float(eps),
+        _ptr(out_f32), out_f32.stride(0) if out_f32 is not None else 0,
+        _ptr(out_split.hi) if out_split is not None else None,
+        _ptr(out_split.lo) if out_split is not None else None,
+        out_split.ld if out_split is not None else 0, rows, cols, _stream())
+    _L.check(rc, "mtt_layernorm")
+
+
+def gemm(a, w, *, M=None, N=None, K=None, bias=None, act=ACT_NONE, residual=None, res_row_mod=0,
+         out_f32=None, out_split=None, regroup=None, conv=None):
+    """D = act(A @ W^T + bias) + residual on the tcgen05 GEMM.
+
+    a: Split [M, K] (or NHWC activation [B*H*W, C] when ``conv=(B, H, W, ksize, dil)``);
+    w: Split [N, K] (conv: [N, ksize*ksize*cin_pad]); outputs: fp32 tensor and/or Split.
+    regroup=(in_group, out_group, out_offset) scatters output rows."""
+    nsplit = min(a.nsplit, w.nsplit)
+    d = _L.GemmDesc()
+    d.a_hi, d.a_lo, d.lda = a.hi.data_ptr(), (a.lo.data_ptr() if nsplit == 2 else 0), a.ld
+    d.b_hi, d.b_lo, d.ldb = w.hi.data_ptr(), (w.lo.data_ptr() if nsplit == 2 else 0), w.ld
+    d.M = a.rows if M is None else M
+    d.N = w.rows if N is None else N
+    d.K = a.cols if K is None else K
+    d.nsplit = nsplit
+    if conv is not None:
+        d.mode = 1
+        d.B, d.H, d.W, d.ksize, d.dil = conv
+    else:
+        d.mode = 0
+    d.bias = bias.data_ptr() if bias is not None else 0
+    d.act = act
+    if residual is not None:
+        assert residual.dtype == torch.float32 and residual.stride(-1) == 1
+        d.residual, d.ldr = residual.data_ptr(), residual.stride(-2)
+    d.res_row_mod = res_row_mod
+    if out_f32 is not None:
+        assert out_f32.dtype == torch.float32 and out_f32.stride(-1) == 1
+        d.out_f32, d.ldo_f32 = out_f32.data_ptr(), out_f32.stride(-2)
+    if out_split is not None:
+        d.out_hi = out_split.hi.data_ptr()
+        d.out_lo = out_split.lo.data_ptr() if out_split.nsplit == 2 else 0
+        d.ldo_bf = out_split.ld
+        if nsplit == 2 and out_split.nsplit != 2:
+            raise ValueError("nsplit=2 GEMM needs a 2-plane split output")
+    if regroup is not None:
+        d.in_group, d.out_group, d.out_offset = regroup
+    rc = _L.load().mtt_gemm(C.byref(d), _stream())
+    _L.check(rc, "mtt_gemm")
+
+
+def attention(qkv, out, *, B, N, H, scale, prompt_logits=None, T=0):
+    """Fused softmax(q k^T * scale) v over [B, N] tokens; qkv Split [B*N, 3*H*64], out Split [B*N, H*64].
+    prompt_logits: optional fp32 [B, H, T, N] receiving raw q.k^T of the first T query rows."""
+    d = _L.AttnDesc()
+    nsplit = min(qkv.nsplit, out.nsplit)
+    assert qkv.ld == 3 * H * 64 and out.ld == H * 64
+    d.qkv_hi, d.qkv_lo = qkv.hi.data_ptr(), (qkv.lo.data_ptr() if nsplit == 2 else 0)
+    d.out_hi, d.out_lo = out.hi.data_ptr(), (out.lo.data_ptr() if nsplit == 2 else 0)
+    if prompt_logits is not None:
+        assert prompt_logits.dtype == torch.float32 and prompt_logits.is_contiguous()
+        assert tuple(prompt_logits.shape) == (B, H, T, N)
+        d.prompt_logits = prompt_logits.data_ptr()
+    d.B, d.N, d.H, d.T, d.nsplit, d.scale = B, N, H, T, nsplit, float(scale)
+    rc = _L.load().mtt_attention(C.byref(d), _stream())
+    _L.check(rc, "mtt_attention")
+
+
+def launch_count(reset=False):
+    lib = _L.load()
+    n = lib.mtt_launch_count()
+    if reset:
+        lib.mtt_launch_count_reset()
+    return n

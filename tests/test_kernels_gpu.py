@@ -1,0 +1,183 @@
+"""-m gpu: each C-ABI kernel against a plain torch restatement of the same op (fp64 on the host).
+
+Tolerances: nsplit=2 (parity mode, 3 MMAs per product) must stay below 3e-5 relative to the largest
+output magnitude; nsplit=1 (plain bf16) below 2e-2. Index/scatter logic must be exact.
+"""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300)]
+
+TOL = {2: 3e-5, 1: 2e-2}
+
+
+def relerr(got, ref):
+    ref = ref.double()
+    return ((got.double().cpu() - ref.cpu()).abs().max() / ref.abs().max().clamp_min(1e-30)).item()
+
+
+def test_split_exact(cuda_dev):
+    from mtt_b200 import ops
+
+    torch.manual_seed(0)
+    x = torch.randn(37, 53, device=cuda_dev) * 3
+    s = ops.split_f32(x, 2, cols_pad=64)
+    torch.cuda.synchronize()
+    hi = x.bfloat16()
+    lo = (x - hi.float()).bfloat16()
+    assert torch.equal(s.hi[:, :53], hi)
+    assert torch.equal(s.lo[:, :53], lo)
+    assert (s.hi[:, 53:64] == 0).all() and (s.lo[:, 53:64] == 0).all()
+    assert (s.float()[:, :53] - x).abs().max() <= 2 ** -16 * x.abs().max()
+
+
+@pytest.mark.parametrize("rows,cols", [(5, 192), (1029, 1024), (77, 350), (13, 2880)])
+def test_layernorm(cuda_dev, rows, cols):
+    from mtt_b200 import ops
+
+    torch.manual_seed(1)
+    x = torch.randn(rows, cols, device=cuda_dev) * 2 + 0.5
+    g = torch.randn(cols, device=cuda_dev)
+    b = torch.randn(cols, device=cuda_dev)
+    ref = F.layer_norm(x.double().cpu(), (cols,), g.double().cpu(), b.double().cpu(), 1e-6)
+    of = torch.empty_like(x)
+    osp = ops.Split(rows, cols, cuda_dev, 2)
+    ops.layernorm(x, g, b, 1e-6, out_f32=of, out_split=osp)
+    torch.cuda.synchronize()
+    assert relerr(of, ref) < 2e-6
+    assert relerr(osp.float(), ref) < 1e-5
+
+
+def _gemm_case(dev, M, N, K, nsplit, bias, act, residual, regroup=None, res_row_mod=0, out_ld=None):
+    from mtt_b200 import ops
+
+    torch.manual_seed(M * 7 + N * 3 + K)
+    a = torch.randn(M, K, device=dev)
+    w = torch.randn(N, K, device=dev) * 0.05
+    bs = torch.randn(N, device=dev) if bias else None
+    A = ops.split_f32(a, nsplit)
+    Wp = ops.split_f32(w, nsplit)
+    rows_out = M
+    if regroup:
+        ig, og, off = regroup
+        rows_out = (M // ig) * og
+    ld = out_ld or N
+    res = None
+    if residual:
+        rr = res_row_mod if res_row_mod else rows_out
+        res = torch.randn(rr, N, device=dev)
+    of = torch.full((rows_out, ld), float("nan"), device=dev)
+    osp = ops.Split(rows_out, N, dev, nsplit)
+    osp.buf.zero_()
+    ops.gemm(A, Wp, bias=bs, act=act, residual=res, res_row_mod=res_row_mod, out_f32=of[:, :N],
+             out_split=osp, regroup=regroup)
+    torch.cuda.synchronize()
+    ref = a.double().cpu() @ w.double().cpu().t()
+    if bias:
+        ref = ref + bs.double().cpu()
+    if act == ops.ACT_GELU:
+        ref = F.gelu(ref)
+    elif act == ops.ACT_RELU:
+        ref = F.relu(ref)
+    idx = torch.arange(M)
+    oidx = idx
+    if regroup:
+        oidx = (idx // ig) * og + off + idx % ig
+    if residual:
+        r = res.double().cpu()
+        ref = ref + (r[idx % res_row_mod] if res_row_mod else r[oidx])
+    got = of[:, :N].cpu()[oidx]
+    e = relerr(got, ref)
+    assert e < TOL[nsplit], f"fp32 out rel err {e}"
+    e2 = relerr(osp.float().cpu()[oidx], ref)
+    assert e2 < TOL[nsplit] + 1e-5, f"split out rel err {e2}"
+    if regroup:  # rows that are not targets must be untouched
+        mask = torch.ones(rows_out, dtype=torch.bool)
+        mask[oidx] = False
+        assert torch.isnan(of.cpu()[mask][:, :N]).all()
+    if ld > N:
+        assert torch.isnan(of[:, N:]).all()
+
+
+@pytest.mark.parametrize("nsplit", [2, 1])
+def test_gemm_small_tails(cuda_dev, nsplit):
+    from mtt_b200 import ops
+
+    _gemm_case(cuda_dev, 300, 200, 136, nsplit, True, ops.ACT_NONE, False)
+    _gemm_case(cuda_dev, 20, 1024, 1024, nsplit, True, ops.ACT_NONE, True)
+    _gemm_case(cuda_dev, 257, 21, 350 + 2, nsplit, True, ops.ACT_NONE, False)  # scalar epilogue path
+    _gemm_case(cuda_dev, 130, 1, 72, nsplit, False, ops.ACT_RELU, False)
+
+
+@pytest.mark.parametrize("nsplit", [2, 1])
+def test_gemm_block_shapes(cuda_dev, nsplit):
+    from mtt_b200 import ops
+
+    # qkv-like (many tiles, persistent loop wraps the pipeline several times)
+    _gemm_case(cuda_dev, 2058, 3072, 1024, nsplit, True, ops.ACT_NONE, False)
+    # fc1-like with GELU
+    _gemm_case(cuda_dev, 1029, 4096, 1024, nsplit, True, ops.ACT_GELU, False)
+    # fc2-like with residual
+    _gemm_case(cuda_dev, 1029, 1024, 4096, nsplit, True, ops.ACT_NONE, True)
+
+
+def test_gemm_regroup_and_rowmod(cuda_dev):
+    from mtt_b200 import ops
+
+    # patch-embed style: rows of each image scattered behind T=5 prompt rows; pos-embed broadcast
+    _gemm_case(cuda_dev, 2 * 64, 256, 768, 2, True, ops.ACT_NONE, True, regroup=(64, 69, 5), res_row_mod=64)
+    _gemm_case(cuda_dev, 3 * 100, 136, 200, 2, False, ops.ACT_NONE, False, regroup=(100, 104, 4), out_ld=144)
+
+
+@pytest.mark.parametrize("ksize,dil", [(3, 1), (3, 2), (1, 1)])
+@pytest.mark.parametrize("nsplit", [2, 1])
+def test_conv(cuda_dev, ksize, dil, nsplit):
+    from mtt_b200 import ops
+    from mtt_b200.pack import pack_conv_weight
+
+    torch.manual_seed(5)
+    for (B, H, W, Cin, Cout) in [(2, 12, 20, 72, 40), (1, 32, 32, 350, 350), (2, 7, 9, 64, 130)]:
+        x = torch.randn(B, Cin, H, W, device=cuda_dev)
+        w = torch.randn(Cout, Cin, ksize, ksize, device=cuda_dev) * 0.05
+        bias = torch.randn(Cout, device=cuda_dev)
+        xn = x.permute(0, 2, 3, 1).reshape(B * H * W, Cin).contiguous()
+        A = ops.split_f32(xn, nsplit)
+        Wp = pack_conv_weight(w, nsplit)
+        out = torch.empty(B * H * W, Cout, device=cuda_dev)
+        ops.gemm(A, Wp, N=Cout, K=Cin, bias=bias, act=ops.ACT_RELU, out_f32=out, conv=(B, H, W, ksize, dil))
+        torch.cuda.synchronize()
+        ref = F.relu(F.conv2d(x.double().cpu(), w.double().cpu(), bias.double().cpu(),
+                              padding=dil * (ksize - 1) // 2, dilation=dil))
+        ref = ref.permute(0, 2, 3, 1).reshape(B * H * W, Cout)
+        e = relerr(out, ref)
+        assert e < TOL[nsplit], f"conv {B,H,W,Cin,Cout} k{ksize} d{dil}: rel err {e}"
+
+
+@pytest.mark.parametrize("nsplit", [2, 1])
+@pytest.mark.parametrize("B,H,N,T", [(2, 3, 300, 4), (1, 2, 1029, 5), (1, 1, 128, 0), (2, 2, 65, 2)])
+def test_attention(cuda_dev, nsplit, B, H, N, T):
+    from mtt_b200 import ops
+
+    torch.manual_seed(11)
+    C = H * 64
+    qkv = torch.randn(B * N, 3 * C, device=cuda_dev)
+    qkv[:, :C] *= 1.5
+    Q = ops.split_f32(qkv, nsplit)
+    out = ops.Split(B * N, C, cuda_dev, nsplit)
+    logits = torch.full((B, H, T, N), float("nan"), device=cuda_dev) if T else None
+    scale = 64 ** -0.5
+    ops.attention(Q, out, B=B, N=N, H=H, scale=scale, prompt_logits=logits, T=T)
+    torch.cuda.synchronize()
+    x = qkv.double().cpu().reshape(B, N, 3, H, 64).permute(2, 0, 3, 1, 4)
+    q, k, v = x[0], x[1], x[2]
+    raw = q @ k.transpose(-2, -1)
+    ref = (raw * scale).softmax(-1) @ v
+    ref = ref.transpose(1, 2).reshape(B * N, C)
+    e = relerr(out.float(), ref)
+    assert e < (1e-4 if nsplit == 2 else 3e-2), f"attention out rel err {e}"
+    if T:
+        e = relerr(logits, raw[:, :, :T, :])
+        assert e < (3e-5 if nsplit == 2 else 2e-2), f"prompt logits rel err {e}"
