@@ -122,6 +122,74 @@ typedef struct {
 
 int mtt_attention(const mtt_attn_desc* d, mtt_stream_t stream);
 
+/* ---- patch embedding im2col ---------------------------------------------------------------
+ * timm PatchEmbed (Conv2d k = s = patch) as a GEMM: img NCHW fp32 -> split [B*P, Cin*patch*patch],
+ * column order (c, ky, kx) = conv.weight.reshape(C_out, -1). Replaces TP taskprompter.py:393,
+ * IP vit.py:333. */
+int mtt_im2col_patch(const float* img, int32_t B, int32_t Cin, int32_t H, int32_t W, int32_t patch,
+                     void* out_hi, void* out_lo, int64_t ld_out, mtt_stream_t stream);
+
+/* dst[(b*group_rows + t)*ld + c] = src[t*C + c]: task prompts / cls token into the joint stream
+ * (TP taskprompter.py:397, IP vit.py:334-336). */
+int mtt_broadcast_rows(const float* src, float* dst, int32_t B, int32_t T, int32_t C,
+                       int64_t group_rows, int64_t ld, mtt_stream_t stream);
+
+/* ---- skinny linear (<= 32 rows, fp32 weights) ----------------------------------------------
+ * out[r, n] (+)= sum_k A[r, k] W[n, k] + bias[n]; A is either split planes (a_hi[, a_lo]) or fp32.
+ * Row r of A lives at (r / a_in_group) * a_out_group + a_offset + r % a_in_group (a_in_group = 0:
+ * identity); same for the output rows. Replaces token_trans / token_trans1 on the B*T prompt rows
+ * (TP taskprompter.py:219, :250). */
+typedef struct {
+  const void* a_hi;
+  const void* a_lo;
+  const float* a_f32;
+  int64_t lda;
+  int32_t a_in_group, a_out_group, a_offset;
+  const float* w;
+  int64_t ldw;
+  const float* bias;
+  int32_t R, N, K;
+  float* out;
+  int64_t ldo;
+  int32_t o_in_group, o_out_group, o_offset;
+  int32_t accumulate;
+} mtt_skinny_desc;
+int mtt_skinny_linear(const mtt_skinny_desc* d, mtt_stream_t stream);
+
+/* Raw channel logits Rc[b,t,c,i,j] = sum_{pixel in window (i,j)} cp[b,t,pixel] * xn[b,pixel,c]
+ * (TP taskprompter.py:236-240,246). cp fp32 [B,T,P]; xn = split LN1 output of the joint stream
+ * [B*N, ldx] (patch rows start at T); out fp32 [B,T,C,nh,nw]. */
+int mtt_chan_logits(const float* cp, const void* xn_hi, const void* xn_lo, int64_t ldx, int32_t B,
+                    int32_t N, int32_t T, int32_t C, int32_t gh, int32_t gw, int32_t nh, int32_t nw,
+                    float* out, mtt_stream_t stream);
+
+/* Spatial + channel gating of the patch feature map for one task (TP taskprompter.py:436-446,
+ * :452-467): Ys = X*(1 + R[b, c/dh, t, T+pix]), Yc = X*(1 + Rc[b,t,c,window(pix)]), both written as
+ * split [B*P, ldy] operands of the 1x1 decode convs. X row (b, pix) is at
+ * x + (b*x_group_rows + x_row_offset + pix)*ldx. */
+int mtt_gate_split(const float* x, int64_t ldx, int64_t x_group_rows, int64_t x_row_offset,
+                   const float* prompt_logits, const float* chan_logits, int32_t task, int32_t B,
+                   int32_t T, int32_t N, int32_t H, int32_t C, int32_t gh, int32_t gw, int32_t nh,
+                   int32_t nw, void* ys_hi, void* ys_lo, void* yc_hi, void* yc_lo, int64_t ldy,
+                   mtt_stream_t stream);
+
+/* Cross-task reweighting (TP taskprompter.py:478-485).
+ * mtt_ctr_weights: w[b,t,j] = W2_t . gelu(W0_t . R[b,:,t,j] + b0_t) + b2_t with W0 [T,H,H], b0 [T,H],
+ *   W2 [T,H], b2 [T] (ctr_attn_conv.{il}.{task}.{0,2}); out fp32 [B,T,T].
+ * mtt_ctr_mix: acc[t][m,:] (+)= sum_j w[b(m),t,j] * F[j][m,:]; F, acc fp32 [T, M, ld]. */
+int mtt_ctr_weights(const float* prompt_logits, int32_t B, int32_t H, int32_t T, int32_t N,
+                    const float* w0, const float* b0, const float* w2, const float* b2, float* out,
+                    mtt_stream_t stream);
+int mtt_ctr_mix(const float* F, const float* w, float* acc, int32_t T, int64_t M, int32_t C, int64_t ld,
+                int32_t rows_per_batch, int32_t accumulate, mtt_stream_t stream);
+
+/* Bilinear resize, align_corners=False (F.interpolate at TP taskprompter.py:420,
+ * taskprompter_wrapper.py:35; IP transformer_net.py:35). in NHWC fp32 [B,h,w,C] (ld_in); outputs:
+ * NHWC fp32 (optionally accumulated into) and/or NHWC split, and/or NCHW fp32 [B,C,H2,W2]. */
+int mtt_bilinear(const float* in, int64_t ld_in, int32_t B, int32_t h, int32_t w, int32_t C, int32_t H2,
+                 int32_t W2, float* out_f32, int64_t ld_f32, void* out_hi, void* out_lo, int64_t ld_bf,
+                 float* out_nchw, int32_t accumulate, mtt_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,471 @@
+// HBM-bound kernels around the GEMMs: patch im2col, prompt broadcast, the channel-prompt path
+// (skinny linears + windowed channel logits), spatial/channel gating, cross-task reweighting and
+// bilinear resampling.  All are coalesced along the channel (innermost NHWC / token-major) axis,
+// float4 / bf16x2 vectorised where the layout allows, with grids sized by the data (>= several
+// waves of 148 SMs at the benchmark shapes).
+#include "host_common.h"
+#include "ptx.cuh"
+
+namespace mtt {
+
+// ------------------------------------------------------------------------------------------------
+// im2col for the stride-16 patch embedding (timm PatchEmbed: Conv2d(k = s = patch)); column order
+// (c, ky, kx) matches conv.weight.reshape(C_out, -1).   reference: taskprompter.py:393
+__global__ void __launch_bounds__(256)
+im2col_patch_kernel(const float* __restrict__ img, int Cin, int H, int W, int patch, int gw, int P,
+                    __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, long long ld) {
+  const long long row = blockIdx.x;  // b * P + p
+  const int b = (int)(row / P), pidx = (int)(row % P);
+  const int py = pidx / gw, px = pidx % gw;
+  const int K = Cin * patch * patch;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    const int c = k / (patch * patch);
+    const int r = k % (patch * patch);
+    const int ky = r / patch, kx = r % patch;
+    const float v = img[(((long long)b * Cin + c) * H + py * patch + ky) * W + px * patch + kx];
+    __nv_bfloat16 h, l;
+    split_bf16(v, h, l);
+    hi[row * ld + k] = h;
+    if (lo) lo[row * ld + k] = l;
+  }
+}
+
+// dst[(b*group + t) * ld + c] = src[t*C + c]     reference: taskprompter.py:397
+__global__ void broadcast_rows_kernel(const float* __restrict__ src, float* __restrict__ dst, int B, int T,
+                                      int C, long long group, long long ld) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)B * T * C;
+  if (i >= total) return;
+  const int c = (int)(i % C);
+  const int t = (int)((i / C) % T);
+  const int b = (int)(i / ((long long)C * T));
+  dst[((long long)b * group + t) * ld + c] = src[(long long)t * C + c];
+}
+
+// ------------------------------------------------------------------------------------------------
+// Skinny linear: out[r, n] (+)= sum_k A[r, k] * W[n, k] + bias[n], R <= 32 rows, fp32 weights read
+// once.  reference: token_trans / token_trans1 at taskprompter.py:219,250 (M = B*T prompt rows).
+struct SkinnyParams {
+  const __nv_bfloat16* a_hi;
+  const __nv_bfloat16* a_lo;
+  const float* a_f32;
+  long long lda;
+  int a_in, a_out, a_off;
+  const float* w;
+  long long ldw;
+  const float* bias;
+  int R, N, K, kc;
+  float* out;
+  long long ldo;
+  int o_in, o_out, o_off, accumulate;
+};
+
+template <int RMAX>
+__global__ void __launch_bounds__(256) skinny_linear_kernel(const SkinnyParams p) {
+  extern __shared__ float sA[];  // [R][kc]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nwarps = blockDim.x >> 5;
+  const int n = blockIdx.x * nwarps + warp;
+  float acc[RMAX];
+#pragma unroll
+  for (int r = 0; r < RMAX; ++r) acc[r] = 0.f;
+  for (int k0 = 0; k0 < p.K; k0 += p.kc) {
+    const int kc = min(p.kc, p.K - k0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < p.R * kc; i += blockDim.x) {
+      const int r = i / kc, k = i % kc;
+      const long long ar = (p.a_in > 0) ? ((long long)(r / p.a_in) * p.a_out + p.a_off + r % p.a_in) : r;
+      float v;
+      if (p.a_f32) {
+        v = p.a_f32[ar * p.lda + k0 + k];
+      } else {
+        v = __bfloat162float(p.a_hi[ar * p.lda + k0 + k]);
+        if (p.a_lo) v += __bfloat162float(p.a_lo[ar * p.lda + k0 + k]);
+      }
+      sA[r * p.kc + k] = v;
+    }
+    __syncthreads();
+    if (n < p.N) {
+      const float* wr = p.w + (long long)n * p.ldw + k0;
+      for (int k = lane; k < kc; k += 32) {
+        const float wv = __ldg(wr + k);
+#pragma unroll
+        for (int r = 0; r < RMAX; ++r)
+          if (r < p.R) acc[r] = fmaf(wv, sA[r * p.kc + k], acc[r]);
+      }
+    }
+  }
+  if (n >= p.N) return;
+#pragma unroll
+  for (int r = 0; r < RMAX; ++r) {
+    if (r >= p.R) break;
+    float v = acc[r];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) {
+      if (p.bias) v += p.bias[n];
+      const long long orow = (p.o_in > 0) ? ((long long)(r / p.o_in) * p.o_out + p.o_off + r % p.o_in) : r;
+      float* dst = p.out + orow * p.ldo + n;
+      *dst = p.accumulate ? (*dst + v) : v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Raw channel logits  Rc[b,t,c,i,j] = sum_{pixel in window (i,j)} cp[b,t,pixel] * xn[b,pixel,c]
+// reference: taskprompter.py:236-240,246 (the softmax.V after it is dead code and not reproduced).
+constexpr int kMaxTasks = 8;
+__global__ void __launch_bounds__(128)
+chan_logits_kernel(const float* __restrict__ cp, const __nv_bfloat16* __restrict__ xh,
+                   const __nv_bfloat16* __restrict__ xl, long long ldx, int N, int T, int C, int gh, int gw,
+                   int nh, int nw, float* __restrict__ out) {
+  extern __shared__ float scp[];  // [T][wh*ww]
+  const int b = blockIdx.z, win = blockIdx.y;
+  const int wi = win / nw, wj = win % nw;
+  const int wh = gh / nh, ww = gw / nw, wp = wh * ww;
+  const int P = gh * gw;
+  for (int i = threadIdx.x; i < T * wp; i += blockDim.x) {
+    const int t = i / wp, q = i % wp;
+    const int pix = (wi * wh + q / ww) * gw + wj * ww + q % ww;
+    scp[i] = cp[((long long)b * T + t) * P + pix];
+  }
+  __syncthreads();
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float acc[kMaxTasks];
+#pragma unroll
+  for (int t = 0; t < kMaxTasks; ++t) acc[t] = 0.f;
+  for (int q = 0; q < wp; ++q) {
+    const int pix = (wi * wh + q / ww) * gw + wj * ww + q % ww;
+    const long long row = (long long)b * N + T + pix;
+    float x = __bfloat162float(xh[row * ldx + c]);
+    if (xl) x += __bfloat162float(xl[row * ldx + c]);
+#pragma unroll
+    for (int t = 0; t < kMaxTasks; ++t)
+      if (t < T) acc[t] = fmaf(scp[t * wp + q], x, acc[t]);
+  }
+#pragma unroll
+  for (int t = 0; t < kMaxTasks; ++t)
+    if (t < T) out[((((long long)b * T + t) * C + c) * nh + wi) * nw + wj] = acc[t];
+}
+
+// ------------------------------------------------------------------------------------------------
+// Spatial and channel gating (taskprompter.py:436-446 and :452-467), both in one pass over X:
+//   Ys[b,pix,c] = X[b,pix,c] * (1 + R[b, c / dh, t, T + pix])
+//   Yc[b,pix,c] = X[b,pix,c] * (1 + Rc[b, t, c, window(pix)])
+// written as split-bf16 A operands of the two 1x1 decode convolutions.
+__global__ void __launch_bounds__(256)
+gate_split_kernel(const float* __restrict__ x, long long ldx, long long x_group, long long x_off,
+                  const float* __restrict__ logits, const float* __restrict__ rc, int t, int T, int N, int H,
+                  int dh, int C, int gh, int gw, int nh, int nw, __nv_bfloat16* __restrict__ ys_hi,
+                  __nv_bfloat16* __restrict__ ys_lo, __nv_bfloat16* __restrict__ yc_hi,
+                  __nv_bfloat16* __restrict__ yc_lo, long long ldy) {
+  const int P = gh * gw;
+  const long long row = blockIdx.x;  // b * P + pix
+  const int b = (int)(row / P), pix = (int)(row % P);
+  const int py = pix / gw, px = pix % gw;
+  const int win = (py / (gh / nh)) * nw + px / (gw / nw);
+  const float* xr = x + ((long long)b * x_group + x_off + pix) * ldx;
+  const float* lg = logits + (((long long)b * H) * T + t) * N + T + pix;  // + head * T * N
+  const float* rcr = rc + (((long long)b * T + t) * C) * (nh * nw) + win;  // + c * nh*nw
+  for (int c = threadIdx.x * 2; c < C; c += blockDim.x * 2) {
+    const float x0 = xr[c], x1 = xr[c + 1];
+    const float g0 = lg[(long long)(c / dh) * T * N], g1 = lg[(long long)((c + 1) / dh) * T * N];
+    const float r0 = rcr[(long long)c * (nh * nw)], r1 = rcr[(long long)(c + 1) * (nh * nw)];
+    uint32_t h, l;
+    split_pack2(x0 * (1.f + g0), x1 * (1.f + g1), h, l);
+    *reinterpret_cast<uint32_t*>(ys_hi + row * ldy + c) = h;
+    if (ys_lo) *reinterpret_cast<uint32_t*>(ys_lo + row * ldy + c) = l;
+    split_pack2(x0 * (1.f + r0), x1 * (1.f + r1), h, l);
+    *reinterpret_cast<uint32_t*>(yc_hi + row * ldy + c) = h;
+    if (yc_lo) *reinterpret_cast<uint32_t*>(yc_lo + row * ldy + c) = l;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Cross-task reweighting weights (taskprompter.py:481-483):
+//   w[b,t,j] = W2_t . gelu(W0_t . R[b, :, t, j] + b0_t) + b2_t       (two 1x1 convs over the head axis)
+__global__ void ctr_weights_kernel(const float* __restrict__ logits, int B, int H, int T, int N,
+                                   const float* __restrict__ w0, const float* __restrict__ b0,
+                                   const float* __restrict__ w2, const float* __restrict__ b2,
+                                   float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * T * T) return;
+  const int j = i % T, t = (i / T) % T, b = i / (T * T);
+  float acc = b2[t];
+  for (int o = 0; o < H; ++o) {
+    float hsum = b0[t * H + o];
+    for (int h = 0; h < H; ++h)
+      hsum = fmaf(w0[((long long)t * H + o) * H + h], logits[(((long long)b * H + h) * T + t) * N + j], hsum);
+    acc = fmaf(w2[t * H + o], gelu_erf(hsum), acc);
+  }
+  out[i] = acc;
+}
+
+// acc[t][m, :] (+)= sum_j w[b(m), t, j] * F[j][m, :]     (taskprompter.py:484 + level sum :411)
+__global__ void __launch_bounds__(256)
+ctr_mix_kernel(const float* __restrict__ F, const float* __restrict__ w, float* __restrict__ acc, int T,
+               long long M, int C, long long ld, int rows_per_batch, int accumulate) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // over M * C/4
+  const int c4 = C >> 2;
+  if (i >= M * c4) return;
+  const long long m = i / c4;
+  const int c = (int)(i % c4) * 4;
+  const int b = (int)(m / rows_per_batch);
+  float4 f[kMaxTasks];
+#pragma unroll
+  for (int j = 0; j < kMaxTasks; ++j)
+    if (j < T) f[j] = *reinterpret_cast<const float4*>(F + ((long long)j * M + m) * ld + c);
+#pragma unroll
+  for (int t = 0; t < kMaxTasks; ++t) {
+    if (t >= T) break;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < kMaxTasks; ++j) {
+      if (j >= T) break;
+      const float wv = w[((long long)b * T + t) * T + j];
+      s.x = fmaf(wv, f[j].x, s.x);
+      s.y = fmaf(wv, f[j].y, s.y);
+      s.z = fmaf(wv, f[j].z, s.z);
+      s.w = fmaf(wv, f[j].w, s.w);
+    }
+    float4* dst = reinterpret_cast<float4*>(acc + ((long long)t * M + m) * ld + c);
+    if (accumulate) {
+      const float4 o = *dst;
+      s.x += o.x; s.y += o.y; s.z += o.z; s.w += o.w;
+    }
+    *dst = s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Bilinear resize, align_corners = False (ATen upsample_bilinear2d semantics; reference calls at
+// taskprompter.py:420, taskprompter_wrapper.py:35).  NHWC fp32 in; NHWC (fp32 and/or split) or NCHW out.
+__device__ __forceinline__ void bilin_coord(int d, float scale, int in_size, int& i0, int& i1, float& l1) {
+  float s = scale * (d + 0.5f) - 0.5f;
+  if (s < 0.f) s = 0.f;
+  i0 = (int)s;
+  if (i0 > in_size - 1) i0 = in_size - 1;
+  i1 = i0 + (i0 < in_size - 1 ? 1 : 0);
+  l1 = s - (float)i0;
+}
+
+__global__ void __launch_bounds__(256)
+bilinear_nhwc_kernel(const float* __restrict__ in, long long ld_in, int B, int h, int w, int C, int H2, int W2,
+                     float sy, float sx, float* __restrict__ out_f32, long long ld_f32,
+                     __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo, long long ld_bf,
+                     int accumulate) {
+  const long long opix = blockIdx.x;  // (b * H2 + y) * W2 + x
+  const int x = (int)(opix % W2), y = (int)((opix / W2) % H2), b = (int)(opix / ((long long)W2 * H2));
+  int y0, y1, x0, x1;
+  float ly, lx;
+  bilin_coord(y, sy, h, y0, y1, ly);
+  bilin_coord(x, sx, w, x0, x1, lx);
+  const float* p00 = in + (((long long)b * h + y0) * w + x0) * ld_in;
+  const float* p01 = in + (((long long)b * h + y0) * w + x1) * ld_in;
+  const float* p10 = in + (((long long)b * h + y1) * w + x0) * ld_in;
+  const float* p11 = in + (((long long)b * h + y1) * w + x1) * ld_in;
+  const float hy = 1.f - ly, hx = 1.f - lx;
+  for (int c = threadIdx.x * 2; c < C; c += blockDim.x * 2) {
+    const bool two = c + 1 < C;
+    float v0 = hy * (hx * p00[c] + lx * p01[c]) + ly * (hx * p10[c] + lx * p11[c]);
+    float v1 = two ? hy * (hx * p00[c + 1] + lx * p01[c + 1]) + ly * (hx * p10[c + 1] + lx * p11[c + 1]) : 0.f;
+    if (out_f32) {
+      float* o = out_f32 + opix * ld_f32 + c;
+      if (accumulate) {
+        v0 += o[0];
+        if (two) v1 += o[1];
+      }
+      o[0] = v0;
+      if (two) o[1] = v1;
+    }
+    if (out_hi) {
+      uint32_t hh, ll;
+      split_pack2(v0, v1, hh, ll);
+      if (two) {
+        *reinterpret_cast<uint32_t*>(out_hi + opix * ld_bf + c) = hh;
+        if (out_lo) *reinterpret_cast<uint32_t*>(out_lo + opix * ld_bf + c) = ll;
+      } else {
+        out_hi[opix * ld_bf + c] = __ushort_as_bfloat16((unsigned short)(hh & 0xFFFF));
+        if (out_lo) out_lo[opix * ld_bf + c] = __ushort_as_bfloat16((unsigned short)(ll & 0xFFFF));
+      }
+    }
+  }
+}
+
+// NHWC fp32 [B,h,w,C] -> NCHW fp32 [B,C,H2,W2]; one thread per output pixel, loop over channels.
+__global__ void __launch_bounds__(256)
+bilinear_to_nchw_kernel(const float* __restrict__ in, long long ld_in, int B, int h, int w, int C, int H2,
+                        int W2, float sy, float sx, float* __restrict__ out) {
+  const long long opix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (opix >= (long long)B * H2 * W2) return;
+  const int x = (int)(opix % W2), y = (int)((opix / W2) % H2), b = (int)(opix / ((long long)W2 * H2));
+  int y0, y1, x0, x1;
+  float ly, lx;
+  bilin_coord(y, sy, h, y0, y1, ly);
+  bilin_coord(x, sx, w, x0, x1, lx);
+  const float* p00 = in + (((long long)b * h + y0) * w + x0) * ld_in;
+  const float* p01 = in + (((long long)b * h + y0) * w + x1) * ld_in;
+  const float* p10 = in + (((long long)b * h + y1) * w + x0) * ld_in;
+  const float* p11 = in + (((long long)b * h + y1) * w + x1) * ld_in;
+  const float hy = 1.f - ly, hx = 1.f - lx;
+  for (int c = 0; c < C; ++c) {
+    const float v = hy * (hx * p00[c] + lx * p01[c]) + ly * (hx * p10[c] + lx * p11[c]);
+    out[(((long long)b * C + c) * H2 + y) * W2 + x] = v;
+  }
+}
+
+}  // namespace mtt
+
+using namespace mtt;
+#define STREAM static_cast<cudaStream_t>(stream)
+
+extern "C" int mtt_im2col_patch(const float* img, int32_t B, int32_t Cin, int32_t H, int32_t W,
+                                int32_t patch, void* out_hi, void* out_lo, int64_t ld_out,
+                                mtt_stream_t stream) {
+  if (!img || !out_hi || B <= 0 || Cin <= 0 || patch <= 0 || H % patch || W % patch ||
+      ld_out < (int64_t)Cin * patch * patch)
+    return set_error(MTT_ERR_BAD_SHAPE, "mtt_im2col_patch: bad arguments");
+  const int gw = W / patch, P = (H / patch) * gw;
+  im2col_patch_kernel<<<B * P, 256, 0, STREAM>>>(img, Cin, H, W, patch, gw, P,
+                                                static_cast<__nv_bfloat16*>(out_hi),
+                                                static_cast<__nv_bfloat16*>(out_lo), ld_out);
+  return check_launch("mtt_im2col_patch");
+}
+
+extern "C" int mtt_broadcast_rows(const float* src, float* dst, int32_t B, int32_t T, int32_t C,
+                                  int64_t group_rows, int64_t ld, mtt_stream_t stream) {
+  if (!src || !dst || B <= 0 || T <= 0 || C <= 0)
+    return set_error(MTT_ERR_BAD_SHAPE, "mtt_broadcast_rows: bad arguments");
+  const long long total = (long long)B * T * C;
+  broadcast_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, STREAM>>>(src, dst, B, T, C, group_rows,
+                                                                            ld);
+  return check_launch("mtt_broadcast_rows");
+}
+
+extern "C" int mtt_skinny_linear(const mtt_skinny_desc* d, mtt_stream_t stream) {
+  if (!d || d->R <= 0 || d->R > 32 || d->N <= 0 || d->K <= 0 || !d->w || !d->out ||
+      (!d->a_hi && !d->a_f32))
+    return set_error(MTT_ERR_BAD_SHAPE, "mtt_skinny_linear: bad arguments (R=%d N=%d K=%d)",
+                     d ? d->R : -1, d ? d->N : -1, d ? d->K : -1);
+  SkinnyParams p;
+  p.a_hi = static_cast<const __nv_bfloat16*>(d->a_hi);
+  p.a_lo = static_cast<const __nv_bfloat16*>(d->a_lo);
+  p.a_f32 = d->a_f32;
+  p.lda = d->lda;
+  p.a_in = d->a_in_group;
+  p.a_out = d->a_out_group;
+  p.a_off = d->a_offset;
+  p.w = d->w;
+  p.ldw = d->ldw;
+  p.bias = d->bias;
+  p.R = d->R;
+  p.N = d->N;
+  p.K = d->K;
+  int kc = (48 * 1024 / 4) / d->R;  // A chunk of <= 48 KB in shared memory
+  kc &= ~31;
+  if (kc > d->K) kc = (d->K + 31) & ~31;
+  p.kc = kc;
+  p.out = d->out;
+  p.ldo = d->ldo;
+  p.o_in = d->o_in_group;
+  p.o_out = d->o_out_group;
+  p.o_off = d->o_offset;
+  p.accumulate = d->accumulate;
+  const int nwarps = 8;
+  const size_t smem = (size_t)d->R * kc * sizeof(float);
+  const unsigned grid = (d->N + nwarps - 1) / nwarps;
+  if (d->R <= 8)
+    skinny_linear_kernel<8><<<grid, nwarps * 32, smem, STREAM>>>(p);
+  else if (d->R <= 16)
+    skinny_linear_kernel<16><<<grid, nwarps * 32, smem, STREAM>>>(p);
+  else
+    skinny_linear_kernel<32><<<grid, nwarps * 32, smem, STREAM>>>(p);
+  return check_launch("mtt_skinny_linear");
+}
+
+extern "C" int mtt_chan_logits(const float* cp, const void* xn_hi, const void* xn_lo, int64_t ldx,
+                               int32_t B, int32_t N, int32_t T, int32_t C, int32_t gh, int32_t gw,
+                               int32_t nh, int32_t nw, float* out, mtt_stream_t stream) {
+  if (!cp || !xn_hi || !out || T <= 0 || T > kMaxTasks || nh <= 0 || nw <= 0 || gh % nh || gw % nw ||
+      N != T + gh * gw)
+    return set_error(MTT_ERR_BAD_SHAPE, "mtt_chan_logits: bad arguments (T=%d grid %dx%d windows %dx%d)",
+                     T, gh, gw, nh, nw);
+  const int wp = (gh / nh) * (gw / nw);
+  const size_t smem = (size_t)T * wp * sizeof(float);
+  if (smem > 200 * 1024) return set_error(MTT_ERR_BAD_SHAPE, "mtt_chan_logits: window too large");
+  static bool attr = false;
+  if (!attr && smem > 48 * 1024) {
+    cudaFuncSetAttribute(chan_logits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr = true;
+  }
+  dim3 grid((C + 127) / 128, nh * nw, B);
+  chan_logits_kernel<<<grid, 128, smem, STREAM>>>(cp, static_cast<const __nv_bfloat16*>(xn_hi),
+                                                 static_cast<const __nv_bfloat16*>(xn_lo), ldx, N, T, C, gh,
+                                                 gw, nh, nw, out);
+  return check_launch("mtt_chan_logits");
+}
+
+extern "C" int mtt_gate_split(const float* x, int64_t ldx, int64_t x_group_rows, int64_t x_row_offset,
+                              const float* prompt_logits, const float* chan_logits, int32_t task,
+                              int32_t B, int32_t T, int32_t N, int32_t H, int32_t C, int32_t gh,
+                              int32_t gw, int32_t nh, int32_t nw, void* ys_hi, void* ys_lo, void* yc_hi,
+                              void* yc_lo, int64_t ldy, mtt_stream_t stream) {
+  if (!x || !prompt_logits || !chan_logits || !ys_hi || !yc_hi || C % 2 || ldy % 2 || C % H ||
+      task < 0 || task >= T || gh % nh || gw % nw)
+    return set_error(MTT_ERR_BAD_SHAPE, "mtt_gate_split: bad arguments");
+  gate_split_kernel<<<B * gh * gw, 256, 0, STREAM>>>(
+      x, ldx, x_group_rows, x_row_offset, prompt_logits, chan_logits, task, T, N, H, C / H, C, gh, gw, nh,
+      nw, static_cast<__nv_bfloat16*>(ys_hi), static_cast<__nv_bfloat16*>(ys_lo),
+      static_cast<__nv_bfloat16*>(yc_hi), static_cast<__nv_bfloat16*>(yc_lo), ldy);
+  return check_launch("mtt_gate_split");
+}
+
+extern "C" int mtt_ctr_weights(const float* prompt_logits, int32_t B, int32_t H, int32_t T, int32_t N,
+                               const float* w0, const float* b0, const float* w2, const float* b2,
+                               float* out, mtt_stream_t stream) {
+  if (!prompt_logits || !w0 || !b0 || !w2 || !b2 || !out || T <= 0)
+    return set_error(MTT_ERR_BAD_SHAPE, "mtt_ctr_weights: bad arguments");
+  const int total = B * T * T;
+  ctr_weights_kernel<<<(total + 127) / 128, 128, 0, STREAM>>>(prompt_logits, B, H, T, N, w0, b0, w2, b2,
+                                                             out);
+  return check_launch("mtt_ctr_weights");
+}
+
+extern "C" int mtt_ctr_mix(const float* F, const float* w, float* acc, int32_t T, int64_t M, int32_t C,
+                           int64_t ld, int32_t rows_per_batch, int32_t accumulate, mtt_stream_t stream) {
+  if (!F || !w || !acc || T <= 0 || T > kMaxTasks || C % 4 || ld % 4 || rows_per_batch <= 0)
+    return set_error(MTT_ERR_BAD_SHAPE, "mtt_ctr_mix: bad arguments (T=%d C=%d ld=%lld)", T, C,
+                     (long long)ld);
+  const long long total = M * (C / 4);
+  ctr_mix_kernel<<<(unsigned)((total + 255) / 256), 256, 0, STREAM>>>(F, w, acc, T, M, C, ld,
+                                                                     rows_per_batch, accumulate);
+  return check_launch("mtt_ctr_mix");
+}
+
+extern "C" int mtt_bilinear(const float* in, int64_t ld_in, int32_t B, int32_t h, int32_t w, int32_t C,
+                            int32_t H2, int32_t W2, float* out_f32, int64_t ld_f32, void* out_hi,
+                            void* out_lo, int64_t ld_bf, float* out_nchw, int32_t accumulate,
+                            mtt_stream_t stream) {
+  if (!in || B <= 0 || h <= 0 || w <= 0 || C <= 0 || H2 <= 0 || W2 <= 0 ||
+      (!out_f32 && !out_hi && !out_nchw))
+    return set_error(MTT_ERR_BAD_SHAPE, "mtt_bilinear: bad arguments");
+  const float sy = (float)h / (float)H2, sx = (float)w / (float)W2;
+  const long long opix = (long long)B * H2 * W2;
+  if (out_nchw) {
+    bilinear_to_nchw_kernel<<<(unsigned)((opix + 255) / 256), 256, 0, STREAM>>>(in, ld_in, B, h, w, C, H2,
+                                                                               W2, sy, sx, out_nchw);
+    int rc = check_launch("mtt_bilinear(nchw)");
+    if (rc) return rc;
+  }
+  if (out_f32 || out_hi) {
+    if (out_hi && (ld_bf % 2))
+      return set_error(MTT_ERR_MISALIGNED, "mtt_bilinear: ld_bf must be even");
+    const int threads = C >= 512 ? 256 : (C >= 128 ? 128 : 64);
+    bilinear_nhwc_kernel<<<(unsigned)opix, threads, 0, STREAM>>>(
+        in, ld_in, B, h, w, C, H2, W2, sy, sx, out_f32, ld_f32, static_cast<__nv_bfloat16*>(out_hi),
+        static_cast<__nv_bfloat16*>(out_lo), ld_bf, accumulate);
+    return check_launch("mtt_bilinear(nhwc)");
+  }
+  return MTT_OK;
+}

@@ -36,6 +36,18 @@ class AttnDesc(C.Structure):
     ]
 
 
+class SkinnyDesc(C.Structure):
+    _fields_ = [
+        ("a_hi", C.c_void_p), ("a_lo", C.c_void_p), ("a_f32", C.c_void_p), ("lda", C.c_int64),
+        ("a_in_group", C.c_int32), ("a_out_group", C.c_int32), ("a_offset", C.c_int32),
+        ("w", C.c_void_p), ("ldw", C.c_int64), ("bias", C.c_void_p),
+        ("R", C.c_int32), ("N", C.c_int32), ("K", C.c_int32),
+        ("out", C.c_void_p), ("ldo", C.c_int64),
+        ("o_in_group", C.c_int32), ("o_out_group", C.c_int32), ("o_offset", C.c_int32),
+        ("accumulate", C.c_int32),
+    ]
+
+
 # name -> (restype, argtypes); every symbol include/mtt_b200.h declares
 _i64, _i32, _f32, _vp = C.c_int64, C.c_int32, C.c_float, C.c_void_p
 SYMBOLS = {
@@ -48,6 +60,16 @@ SYMBOLS = {
     "mtt_layernorm": (C.c_int, [_vp, _i64, _vp, _vp, _f32, _vp, _i64, _vp, _vp, _i64, _i64, _i32, _vp]),
     "mtt_gemm": (C.c_int, [C.POINTER(GemmDesc), _vp]),
     "mtt_attention": (C.c_int, [C.POINTER(AttnDesc), _vp]),
+    "mtt_im2col_patch": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _i64, _vp]),
+    "mtt_broadcast_rows": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i64, _i64, _vp]),
+    "mtt_skinny_linear": (C.c_int, [C.POINTER(SkinnyDesc), _vp]),
+    "mtt_chan_logits": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "mtt_gate_split": (C.c_int, [_vp, _i64, _i64, _i64, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32,
+                                 _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i64, _vp]),
+    "mtt_ctr_weights": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "mtt_ctr_mix": (C.c_int, [_vp, _vp, _vp, _i32, _i64, _i32, _i64, _i32, _i32, _vp]),
+    "mtt_bilinear": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _i64, _vp, _vp, _i64, _vp,
+                               _i32, _vp]),
 }
 
 _lib = None

@@ -84,7 +84,7 @@ def layernorm(x, gamma, beta, eps, out_f32=None, out_split=None):
 
 
 def gemm(a, w, *, M=None, N=None, K=None, bias=None, act=ACT_NONE, residual=None, res_row_mod=0,
-         out_f32=None, out_split=None, regroup=None, conv=None):
+         out_f32=None, out_split=None, out_col_offset=0, regroup=None, conv=None):
     """D = act(A @ W^T + bias) + residual on the tcgen05 GEMM.
 
     a: Split [M, K] (or NHWC activation [B*H*W, C] when ``conv=(B, H, W, ksize, dil)``);
@@ -113,8 +113,8 @@ def gemm(a, w, *, M=None, N=None, K=None, bias=None, act=ACT_NONE, residual=None
         assert out_f32.dtype == torch.float32 and out_f32.stride(-1) == 1
         d.out_f32, d.ldo_f32 = out_f32.data_ptr(), out_f32.stride(-2)
     if out_split is not None:
-        d.out_hi = out_split.hi.data_ptr()
-        d.out_lo = out_split.lo.data_ptr() if out_split.nsplit == 2 else 0
+        d.out_hi = out_split.hi.data_ptr() + 2 * out_col_offset
+        d.out_lo = (out_split.lo.data_ptr() + 2 * out_col_offset) if out_split.nsplit == 2 else 0
         d.ldo_bf = out_split.ld
         if nsplit == 2 and out_split.nsplit != 2:
             raise ValueError("nsplit=2 GEMM needs a 2-plane split output")
@@ -147,3 +147,85 @@ def launch_count(reset=False):
     if reset:
         lib.mtt_launch_count_reset()
     return n
+
+
+def im2col_patch(img, patch, out):
+    """img fp32 NCHW -> out Split [B*P, Cin*patch*patch]."""
+    assert img.dtype == torch.float32 and img.is_contiguous()
+    B, Cin, H, W = img.shape
+    rc = _L.load().mtt_im2col_patch(_ptr(img), B, Cin, H, W, patch, _ptr(out.hi), _ptr(out.lo), out.ld,
+                                    _stream())
+    _L.check(rc, "mtt_im2col_patch")
+
+
+def broadcast_rows(src, dst, B, group_rows):
+    """dst[(b*group_rows + t), :] = src[t, :] for t < T; dst fp32 [B*group_rows, ld]."""
+    T, Cc = src.shape
+    assert src.is_contiguous() and src.dtype == torch.float32 and dst.dtype == torch.float32
+    rc = _L.load().mtt_broadcast_rows(_ptr(src), _ptr(dst), B, T, Cc, group_rows, dst.stride(0), _stream())
+    _L.check(rc, "mtt_broadcast_rows")
+
+
+def skinny_linear(w, bias, out, *, R, a_split=None, a_f32=None, a_map=None, o_map=None, accumulate=False,
+                  K=None, a_row_base=0, o_row_base=0):
+    """out[r, :] (+)= A[r, :] @ w^T + bias for R <= 32 rows; w fp32 [N, K]."""
+    d = _L.SkinnyDesc()
+    if a_split is not None:
+        d.a_hi = a_split.hi.data_ptr() + 2 * a_row_base * a_split.ld
+        d.a_lo = (a_split.lo.data_ptr() + 2 * a_row_base * a_split.ld) if a_split.nsplit == 2 else 0
+        d.lda = a_split.ld
+    else:
+        assert a_f32.dtype == torch.float32 and a_f32.stride(-1) == 1
+        d.a_f32, d.lda = a_f32.data_ptr() + 4 * a_row_base * a_f32.stride(-2), a_f32.stride(-2)
+    if a_map is not None:
+        d.a_in_group, d.a_out_group, d.a_offset = a_map
+    assert w.dtype == torch.float32 and w.stride(1) == 1
+    d.w, d.ldw = w.data_ptr(), w.stride(0)
+    d.bias = bias.data_ptr() if bias is not None else 0
+    d.R, d.N, d.K = R, w.shape[0], (w.shape[1] if K is None else K)
+    assert out.dtype == torch.float32 and out.stride(-1) == 1
+    d.out, d.ldo = out.data_ptr() + 4 * o_row_base * out.stride(-2), out.stride(-2)
+    if o_map is not None:
+        d.o_in_group, d.o_out_group, d.o_offset = o_map
+    d.accumulate = 1 if accumulate else 0
+    rc = _L.load().mtt_skinny_linear(C.byref(d), _stream())
+    _L.check(rc, "mtt_skinny_linear")
+
+
+def chan_logits(cp, xn, out, *, B, N, T, Cdim, gh, gw, nh, nw):
+    rc = _L.load().mtt_chan_logits(_ptr(cp), _ptr(xn.hi), _ptr(xn.lo), xn.ld, B, N, T, Cdim, gh, gw, nh, nw,
+                                   _ptr(out), _stream())
+    _L.check(rc, "mtt_chan_logits")
+
+
+def gate_split(x, x_group_rows, x_row_offset, prompt_logits, chan_lg, task, ys, yc, *, B, T, N, H, Cdim, gh,
+               gw, nh, nw):
+    assert x.dtype == torch.float32 and x.stride(-1) == 1 and ys.ld == yc.ld
+    rc = _L.load().mtt_gate_split(_ptr(x), x.stride(-2), x_group_rows, x_row_offset, _ptr(prompt_logits),
+                                  _ptr(chan_lg), task, B, T, N, H, Cdim, gh, gw, nh, nw, _ptr(ys.hi),
+                                  _ptr(ys.lo), _ptr(yc.hi), _ptr(yc.lo), ys.ld, _stream())
+    _L.check(rc, "mtt_gate_split")
+
+
+def ctr_weights(prompt_logits, w0, b0, w2, b2, out, *, B, H, T, N):
+    rc = _L.load().mtt_ctr_weights(_ptr(prompt_logits), B, H, T, N, _ptr(w0), _ptr(b0), _ptr(w2), _ptr(b2),
+                                   _ptr(out), _stream())
+    _L.check(rc, "mtt_ctr_weights")
+
+
+def ctr_mix(F, w, acc, *, T, M, Cdim, ld, rows_per_batch, accumulate):
+    rc = _L.load().mtt_ctr_mix(_ptr(F), _ptr(w), _ptr(acc), T, M, Cdim, ld, rows_per_batch,
+                               1 if accumulate else 0, _stream())
+    _L.check(rc, "mtt_ctr_mix")
+
+
+def bilinear(x, ld_in, B, h, w, Cdim, H2, W2, *, out_f32=None, out_split=None, out_nchw=None,
+             accumulate=False):
+    """x: NHWC fp32 [B*h*w, ld_in] -> NHWC fp32 / NHWC Split / NCHW fp32 [B,C,H2,W2]."""
+    rc = _L.load().mtt_bilinear(
+        _ptr(x), ld_in, B, h, w, Cdim, H2, W2, _ptr(out_f32),
+        out_f32.stride(-2) if out_f32 is not None else 0,
+        _ptr(out_split.hi) if out_split is not None else None,
+        _ptr(out_split.lo) if out_split is not None else None,
+        out_split.ld if out_split is not None else 0, _ptr(out_nchw), 1 if accumulate else 0, _stream())
+    _L.check(rc, "mtt_bilinear")

@@ -1,0 +1,81 @@
+"""Generates tests/golden/*.pt by running the UNMODIFIED reference (imported from /root/reference through
+oracle/shim) in the build container. TEST INFRASTRUCTURE.
+
+Weights come from the deterministic oracle initialisers (oracle.taskprompter_ref.init_state_dict,
+oracle.invpt_ref.init_state_dict: fixed torch CPU generator seeds) loaded into the reference model
+with strict=True, so a fixture only needs to carry the input, the reference's outputs and a checksum
+of the parameters -- the GPU box regenerates identical weights without /root/reference.
+
+    python -m oracle.make_golden            # rewrites tests/golden/
+"""
+import hashlib
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import configs, ref_loader  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def sd_checksum(sd):
+    h = hashlib.sha256()
+    for k in sorted(sd):
+        h.update(k.encode())
+        h.update(sd[k].detach().cpu().contiguous().numpy().tobytes())
+    return h.hexdigest()
+
+
+def make_taskprompter(name, seed, batch):
+    from oracle import taskprompter_ref as R
+
+    cfg = configs.taskprompter(name)
+    sd = R.init_state_dict(cfg, seed=seed)
+    model = ref_loader.build_taskprompter(cfg).eval()
+    model.load_state_dict(sd, strict=True)
+    g = torch.Generator().manual_seed(seed + 1000)
+    x = torch.randn(batch, 3, *cfg["img_size"], generator=g)
+    with torch.no_grad():
+        y = model(x)
+    return {"family": "taskprompter", "cfg": name, "seed": seed, "x": x, "out": {k: v.clone() for k, v in y.items()},
+            "sd_sha256": sd_checksum(sd), "torch": torch.__version__,
+            "made_by": "oracle/make_golden.py from the unmodified reference forward (eval, fp32, CPU)"}
+
+
+def make_invpt(name, seed, batch):
+    from oracle import invpt_ref as R
+
+    cfg = configs.invpt(name)
+    sd = R.init_state_dict(cfg, seed=seed)
+    model = ref_loader.build_invpt(cfg).eval()
+    model.load_state_dict(sd, strict=True)
+    g = torch.Generator().manual_seed(seed + 1000)
+    x = torch.randn(batch, 3, *cfg["img_size"], generator=g)
+    with torch.no_grad():
+        y = model(x)
+    out = {k: v.clone() for k, v in y.items() if k != "inter_preds"}
+    inter = {k: v.clone() for k, v in y["inter_preds"].items()}
+    return {"family": "invpt", "cfg": name, "seed": seed, "x": x, "out": out, "inter_preds": inter,
+            "sd_sha256": sd_checksum(sd), "torch": torch.__version__,
+            "made_by": "oracle/make_golden.py from the unmodified reference forward (eval, fp32, CPU)"}
+
+
+def main():
+    if not ref_loader.available():
+        raise SystemExit("reference not found (set MTT_REFERENCE or mount /root/reference)")
+    os.makedirs(GOLD, exist_ok=True)
+    jobs = [("taskprompter", "tp_tiny", 3, 2), ("taskprompter", "tp_tiny1", 4, 2)]
+    if os.path.exists(os.path.join(ROOT, "oracle", "invpt_ref.py")):
+        jobs += [("invpt", "ip_tiny", 5, 2), ("invpt", "ip_cfg1", 6, 2)]
+    for fam, name, seed, batch in jobs:
+        fx = make_taskprompter(name, seed, batch) if fam == "taskprompter" else make_invpt(name, seed, batch)
+        path = os.path.join(GOLD, f"{name}.pt")
+        torch.save(fx, path)
+        print(f"wrote {path} ({os.path.getsize(path) / 1024:.0f} KiB)")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,60 @@
+"""Per-kernel timing on one B200 (CUDA events, L2 flushed between iterations). Development aid;
+the judged numbers come from bench.py."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import mtt_b200
+from mtt_b200 import ops
+
+dev = torch.device("cuda:0")
+flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+
+def timeit(fn, iters=10, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        flush.zero_()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record(); fn(); e.record(); torch.cuda.synchronize()
+        ts.append(s.elapsed_time(e))
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def bench_gemm(M, N, K, nsplit, act=ops.ACT_NONE, res=False):
+    a = ops.split_f32(torch.randn(M, K, device=dev), nsplit)
+    w = ops.split_f32(torch.randn(N, K, device=dev) * 0.02, nsplit)
+    bias = torch.randn(N, device=dev)
+    of = torch.zeros(M, N, device=dev) if res else None
+    osp = None if res else ops.Split(M, N, dev, nsplit)
+    fn = lambda: ops.gemm(a, w, bias=bias, act=act, residual=of, out_f32=of, out_split=osp)
+    ms = timeit(fn)
+    fl = 2.0 * M * N * K
+    print(f"gemm M={M} N={N} K={K} nsplit={nsplit} act={act} res={res}: {ms*1e3:.1f} us  "
+          f"{fl/ms/1e9:.1f} TFLOP/s algorithmic, {fl*(3 if nsplit==2 else 1)/ms/1e9:.1f} TFLOP/s bf16-MMA")
+
+
+def bench_attn(B, H, N, nsplit, T=5):
+    C = H * 64
+    qkv = ops.split_f32(torch.randn(B * N, 3 * C, device=dev), nsplit)
+    out = ops.Split(B * N, C, dev, nsplit)
+    lg = torch.empty(B, H, T, N, device=dev)
+    fn = lambda: ops.attention(qkv, out, B=B, N=N, H=H, scale=0.125, prompt_logits=lg, T=T)
+    ms = timeit(fn)
+    fl = 4.0 * B * H * N * N * 64
+    print(f"attn B={B} H={H} N={N} nsplit={nsplit}: {ms*1e3:.1f} us  {fl/ms/1e9:.1f} TFLOP/s algorithmic, "
+          f"{fl*(3 if nsplit==2 else 1)/ms/1e9:.1f} TFLOP/s bf16-MMA")
+
+
+if __name__ == "__main__":
+    M = 4 * 1029
+    for ns in (2, 1):
+        bench_gemm(M, 3072, 1024, ns)
+        bench_gemm(M, 1024, 1024, ns, res=True)
+        bench_gemm(M, 4096, 1024, ns, act=ops.ACT_GELU)
+        bench_gemm(M, 1024, 4096, ns, res=True)
+        bench_attn(4, 16, 1029, ns)
+    bench_attn(1, 16, 8195, 2, T=3)

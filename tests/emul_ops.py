@@ -1,0 +1,183 @@
+"""TEST-ONLY torch emulation of the C-ABI kernels' contracts (include/mtt_b200.h), used to exercise the
+host-side launch sequences (multi-task-transformer_b200/*.py) on a machine without a GPU.
+
+`install(monkeypatch)` replaces the functions of `mtt_b200.ops` with CPU restatements that read and
+write the same buffers (Split planes, fp32 workspaces) with the same indexing rules. The product
+never imports this module; on a GPU the real library is used and these functions are not involved.
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+
+
+def _wsplit(sp, x, col0=0):
+    """write fp32 x [rows, cols] into Split planes at column offset col0."""
+    rows, cols = x.shape
+    hi = x.bfloat16()
+    sp.buf[0, :rows, col0:col0 + cols] = hi
+    if sp.nsplit == 2:
+        sp.buf[1, :rows, col0:col0 + cols] = (x - hi.float()).bfloat16()
+
+
+def _rsplit(sp, cols=None):
+    cols = sp.cols if cols is None else cols
+    x = sp.buf[0, :, :cols].float()
+    if sp.nsplit == 2:
+        x = x + sp.buf[1, :, :cols].float()
+    return x
+
+
+def _map(r, m, base=0):
+    if m is None or m[0] == 0:
+        return r + base
+    return (r // m[0]) * m[1] + m[2] + r % m[0] + base
+
+
+def install(mp):
+    import mtt_b200
+    from mtt_b200 import ops
+
+    def split_f32(x, nsplit=2, cols_pad=None, out=None):
+        rows, cols = x.shape
+        cols_pad = cols if cols_pad is None else cols_pad
+        if out is None:
+            out = ops.Split(rows, cols_pad, x.device, nsplit, ld=ops.round_up(cols_pad, 8), zero=True)
+        xp = torch.zeros(rows, cols_pad)
+        xp[:, :cols] = x
+        _wsplit(out, xp)
+        return out
+
+    def layernorm(x, gamma, beta, eps, out_f32=None, out_split=None):
+        y = F.layer_norm(x, (x.shape[1],), gamma, beta, eps)
+        if out_f32 is not None:
+            out_f32[:, :x.shape[1]] = y
+        if out_split is not None:
+            _wsplit(out_split, y)
+
+    def gemm(a, w, *, M=None, N=None, K=None, bias=None, act=0, residual=None, res_row_mod=0, out_f32=None,
+             out_split=None, out_col_offset=0, regroup=None, conv=None):
+        M = a.rows if M is None else M
+        N = w.rows if N is None else N
+        K = a.cols if K is None else K
+        A = _rsplit(a, K)[:M]
+        if conv is None:
+            Wm = _rsplit(w, K)[:N]
+            y = A @ Wm.t()
+        else:
+            B, H, Wd, ks, dil = conv
+            cin_pad = ops.round_up(K, 64)
+            Wm = _rsplit(w, ks * ks * cin_pad)[:N].reshape(N, ks, ks, cin_pad)[..., :K].permute(0, 3, 1, 2)
+            x = A.reshape(B, H, Wd, K).permute(0, 3, 1, 2)
+            y = F.conv2d(x, Wm, padding=dil * (ks - 1) // 2, dilation=dil).permute(0, 2, 3, 1).reshape(M, N)
+        if bias is not None:
+            y = y + bias[:N]
+        if act == 1:
+            y = F.gelu(y)
+        elif act == 2:
+            y = F.relu(y)
+        r = torch.arange(M)
+        ro = _map(r, regroup)
+        if residual is not None:
+            rr = r % res_row_mod if res_row_mod > 0 else ro
+            y = y + residual[rr, :N]
+        if out_f32 is not None:
+            out_f32[ro, :N] = y
+        if out_split is not None:
+            hi = y.bfloat16()
+            out_split.buf[0, ro, out_col_offset:out_col_offset + N] = hi
+            if out_split.nsplit == 2:
+                out_split.buf[1, ro, out_col_offset:out_col_offset + N] = (y - hi.float()).bfloat16()
+
+    def attention(qkv, out, *, B, N, H, scale, prompt_logits=None, T=0):
+        C = H * 64
+        x = _rsplit(qkv, 3 * C).reshape(B, N, 3, H, 64).permute(2, 0, 3, 1, 4)
+        q, k, v = x[0], x[1], x[2]
+        raw = q @ k.transpose(-2, -1)
+        o = ((raw * scale).softmax(-1) @ v).transpose(1, 2).reshape(B * N, C)
+        _wsplit(out, o)
+        if prompt_logits is not None:
+            prompt_logits.copy_(raw[:, :, :T, :])
+
+    def im2col_patch(img, patch, out):
+        B, Cin, H, W = img.shape
+        cols = F.unfold(img, patch, stride=patch)          # [B, Cin*p*p, P], (c, ky, kx) order
+        _wsplit(out, cols.transpose(1, 2).reshape(-1, Cin * patch * patch))
+
+    def broadcast_rows(src, dst, B, group_rows):
+        T = src.shape[0]
+        for b in range(B):
+            dst[b * group_rows:b * group_rows + T, :src.shape[1]] = src
+
+    def skinny_linear(w, bias, out, *, R, a_split=None, a_f32=None, a_map=None, o_map=None, accumulate=False,
+                      K=None, a_row_base=0, o_row_base=0):
+        K = w.shape[1] if K is None else K
+        r = torch.arange(R)
+        ar = _map(r, a_map, a_row_base)
+        A = _rsplit(a_split, K)[ar] if a_split is not None else a_f32[ar, :K]
+        y = A @ w[:, :K].t()
+        if bias is not None:
+            y = y + bias
+        orow = _map(r, o_map, o_row_base)
+        if accumulate:
+            out[orow, :w.shape[0]] += y
+        else:
+            out[orow, :w.shape[0]] = y
+
+    def chan_logits(cp, xn, out, *, B, N, T, Cdim, gh, gw, nh, nw):
+        x = _rsplit(xn, Cdim).reshape(B, N, Cdim)[:, T:]
+        wh, ww = gh // nh, gw // nw
+        cpw = cp.reshape(B, T, nh, wh, nw, ww)
+        xw = x.reshape(B, nh, wh, nw, ww, Cdim)
+        out.copy_(torch.einsum("btihjw,bihjwc->btcij", cpw, xw))
+
+    def gate_split(x, x_group_rows, x_row_offset, prompt_logits, chan_lg, task, ys, yc, *, B, T, N, H, Cdim, gh,
+                   gw, nh, nw):
+        P = gh * gw
+        X = x.reshape(B, x_group_rows, -1)[:, x_row_offset:x_row_offset + P, :Cdim]
+        g = prompt_logits[:, :, task, T:]                                    # [B,H,P]
+        g = g.permute(0, 2, 1).repeat_interleave(Cdim // H, dim=2)           # [B,P,C]
+        _wsplit(ys, (X * (1 + g)).reshape(B * P, Cdim))
+        gc = chan_lg[:, task]                                                # [B,C,nh,nw]
+        gc = gc.reshape(B, Cdim, nh, 1, nw, 1).expand(B, Cdim, nh, gh // nh, nw, gw // nw).reshape(B, Cdim, P)
+        _wsplit(yc, (X * (1 + gc.permute(0, 2, 1))).reshape(B * P, Cdim))
+
+    def ctr_weights(prompt_logits, w0, b0, w2, b2, out, *, B, H, T, N):
+        a = prompt_logits[:, :, :, :T]                                       # [B,H,T,T]
+        for t in range(T):
+            hdn = F.gelu(torch.einsum("oh,bhj->boj", w0[t], a[:, :, t, :]) + b0[t][None, :, None])
+            out[:, t, :] = torch.einsum("o,boj->bj", w2[t], hdn) + b2[t]
+
+    def ctr_mix(Fm, w, acc, *, T, M, Cdim, ld, rows_per_batch, accumulate):
+        b = torch.arange(M) // rows_per_batch
+        new = torch.einsum("mtj,jmc->tmc", w[b], Fm)
+        if accumulate:
+            acc += new
+        else:
+            acc.copy_(new)
+
+    def bilinear(x, ld_in, B, h, w, Cdim, H2, W2, *, out_f32=None, out_split=None, out_nchw=None,
+                 accumulate=False):
+        img = x.reshape(B, h, w, ld_in)[..., :Cdim].permute(0, 3, 1, 2)
+        y = F.interpolate(img, size=(H2, W2), mode="bilinear", align_corners=False)
+        if out_nchw is not None:
+            out_nchw.copy_(y)
+        yn = y.permute(0, 2, 3, 1).reshape(B * H2 * W2, Cdim)
+        if out_f32 is not None:
+            if accumulate:
+                out_f32[:, :Cdim] += yn
+            else:
+                out_f32[:, :Cdim] = yn
+        if out_split is not None:
+            _wsplit(out_split, yn)
+
+    for name, fn in list(locals().items()):
+        if callable(fn) and hasattr(ops, name) and name not in ("mp",):
+            mp.setattr(ops, name, fn)
+    mp.setattr(ops._L, "check", lambda rc, what: None)
+
+    class _FakeLib:
+        def mtt_device_check(self):
+            return 0
+
+    mp.setattr(ops._L, "load", lambda: _FakeLib())

@@ -1,0 +1,58 @@
+"""CPU: the oracle restatement against (a) the golden vectors produced by the unmodified reference and
+(b) the reference itself when /root/reference is present (build container)."""
+import os
+
+import pytest
+import torch
+
+from oracle import configs, ref_loader
+from oracle import taskprompter_ref as TPR
+from oracle.make_golden import sd_checksum
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.mark.parametrize("name", ["tp_tiny", "tp_tiny1"])
+def test_taskprompter_oracle_vs_golden(name):
+    fx = torch.load(os.path.join(GOLD, f"{name}.pt"), weights_only=False)
+    cfg = configs.taskprompter(fx["cfg"])
+    sd = TPR.init_state_dict(cfg, seed=fx["seed"])
+    assert sd_checksum(sd) == fx["sd_sha256"], "deterministic initialiser drifted from the fixture"
+    with torch.no_grad():
+        out = TPR.forward(sd, cfg, fx["x"])
+    for t, ref in fx["out"].items():
+        # same algorithm, same fp32 library kernels, different op order: rounding-level agreement
+        assert (out[t] - ref).abs().max() <= 2e-6 * ref.abs().max().clamp_min(1.0) + 2e-6, t
+        if t in ("semseg", "human_parts"):
+            assert torch.equal(out[t].argmax(1), ref.argmax(1))
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="reference tree not present")
+@pytest.mark.parametrize("name", ["tp_tiny", "tp_tiny1"])
+def test_taskprompter_oracle_vs_reference(name):
+    cfg = configs.taskprompter(name)
+    torch.manual_seed(0)
+    model = ref_loader.build_taskprompter(cfg).eval()     # the reference's own initialisation
+    for m in model.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.running_mean.normal_(0, 0.1)
+            m.running_var.uniform_(0.8, 1.2)
+    x = torch.randn(2, 3, *cfg["img_size"])
+    with torch.no_grad():
+        ref = model(x)
+        out = TPR.forward(model.state_dict(), cfg, x)
+    for t in cfg["tasks"]:
+        assert (out[t] - ref[t]).abs().max() <= 2e-6, t
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="reference tree not present")
+def test_accelerate_shares_reference_state_dict():
+    import mtt_b200  # noqa: F401
+    from mtt_b200 import taskprompter as TP
+
+    cfg = configs.taskprompter("tp_tiny")
+    ref = ref_loader.build_taskprompter(cfg).eval()
+    mine = TP.accelerate(ref)
+    a, b = ref.state_dict(), mine.state_dict()
+    assert list(a.keys()) == list(b.keys())
+    assert all(torch.equal(a[k], b[k]) for k in a)
