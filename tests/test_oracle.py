@@ -7,6 +7,7 @@ import torch
 
 from oracle import configs, ref_loader
 from oracle import taskprompter_ref as TPR
+from oracle import invpt_ref as IPR
 from oracle.make_golden import sd_checksum
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
@@ -56,3 +57,36 @@ def test_accelerate_shares_reference_state_dict():
     a, b = ref.state_dict(), mine.state_dict()
     assert list(a.keys()) == list(b.keys())
     assert all(torch.equal(a[k], b[k]) for k in a)
+
+
+@pytest.mark.parametrize("name", ["ip_tiny", "ip_cfg1"])
+def test_invpt_oracle_vs_golden(name):
+    fx = torch.load(os.path.join(GOLD, f"{name}.pt"), weights_only=False)
+    cfg = configs.invpt(fx["cfg"])
+    sd = IPR.init_state_dict(cfg, seed=fx["seed"])
+    assert sd_checksum(sd) == fx["sd_sha256"], "deterministic initialiser drifted from the fixture"
+    with torch.no_grad():
+        out = IPR.forward(sd, cfg, fx["x"])
+    for t, ref in fx["out"].items():
+        assert (out[t] - ref).abs().max() <= 5e-6 * ref.abs().max().clamp_min(1.0), t
+        if fx["inter_preds"] is not None:
+            assert (out["inter_preds"][t] - fx["inter_preds"][t]).abs().max() <= 5e-6, t
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="reference tree not present")
+@pytest.mark.parametrize("name", ["ip_tiny", "ip_cfg1"])
+def test_invpt_oracle_vs_reference(name):
+    cfg = configs.invpt(name)
+    torch.manual_seed(0)
+    model = ref_loader.build_invpt(cfg).eval()
+    for m in model.modules():
+        if isinstance(m, (torch.nn.BatchNorm2d, torch.nn.SyncBatchNorm)):
+            m.running_mean.normal_(0, 0.1)
+            m.running_var.uniform_(0.8, 1.2)
+    x = torch.randn(2, 3, *cfg["img_size"])
+    with torch.no_grad():
+        ref = model(x)
+        out = IPR.forward(model.state_dict(), cfg, x)
+    for t in cfg["tasks"]:
+        assert (out[t] - ref[t]).abs().max() <= 5e-6, t
+        assert (out["inter_preds"][t] - ref["inter_preds"][t]).abs().max() <= 5e-6, t
