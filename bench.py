@@ -1,0 +1,366 @@
+#!/usr/bin/env python
+"""bench.py -- images/s of the TaskPrompter ViT-L PASCAL-Context forward (BASELINE.json configs[3],
+512x512, 5 tasks, bs 4 per GPU) on N B200s of one node, one process per GPU.
+
+    python bench.py --gpus 1 --steps 20 --warmup 5
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference --steps K --warmup W      # CPU arm (oracle port of the reference)
+
+A "step" is one forward pass over one synthetic batch (the hot path named by BASELINE.json's
+north_star; the reference publishes no throughput, so vs_baseline is null). Rank 0 prints ONE JSON
+line. `value` = whole-job images/s with inputs resident in HBM; `e2e` = the same through the public
+nn.Module call with pinned-host inputs (H2D) and a D2H read of every task's logits inside the timed
+region. The forward shards over the batch with no collective (weak scaling): NCCL is used only for
+the start/stop barrier and the max-over-ranks time.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+GFLOP_PER_IMAGE = {"tp_cfg4": 993.2, "tp_cfg2": 1163.5, "tp_cfg5": 12842.7}
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f), "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                 "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def dist_setup(n_gpus):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return rank, world, local
+
+
+def barrier(world):
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.barrier()
+
+
+def max_over_ranks(x, world, dev):
+    if world == 1:
+        return x
+    import torch.distributed as dist
+
+    t = torch.tensor([x], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_oracle_rate(cfg_name, steps, warmup, threads):
+    """images/s of the reference algorithm's CPU port (oracle/taskprompter_ref.py, fp32, eval) on a
+    bounded sample: batch 1 of the same workload per step."""
+    from oracle import configs
+    from oracle import taskprompter_ref as TPR
+
+    torch.set_num_threads(threads)
+    cfg = configs.taskprompter(cfg_name)
+    sd = TPR.init_state_dict(cfg, seed=0)
+    x = torch.randn(1, 3, *cfg["img_size"], generator=torch.Generator().manual_seed(1))
+    with torch.no_grad():
+        for _ in range(warmup):
+            TPR.forward(sd, cfg, x)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            TPR.forward(sd, cfg, x)
+        dt = time.perf_counter() - t0
+    return steps / dt, dt / steps
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    rate, sec = cpu_oracle_rate(args.config, args.steps, min(args.warmup, 1), threads)
+    sample = f"batch 1 of {args.config} per step (fp32 eager CPU, eval), {args.steps} steps"
+    line = {
+        "impl": "reference", "metric": "images/sec", "value": rate, "unit": "images/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"TaskPrompter ViT-L PASCAL-Context 512x512 5 tasks ({args.config}), "
+                               "CPU port of the reference forward, batch 1 per step"},
+        "cpu_baseline": {"value": rate, "unit": "images/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": rate, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def gemm_roofline(model, plan, x_dev, peaks, peak_src):
+    """Average duration and algorithmic FLOPs of the dominant kernel (gemm_tc_kernel: every GEMM / conv
+    launch of one forward), measured live with CUDA events on the launching stream."""
+    from mtt_b200 import ops
+
+    recs = []
+    real = ops.gemm
+
+    def timed(a, w, **kw):
+        M = kw.get("M") or a.rows
+        N = kw.get("N") or w.rows
+        K = kw.get("K") or a.cols
+        taps = 1
+        if kw.get("conv") is not None:
+            taps = kw["conv"][3] ** 2
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        real(a, w, **kw)
+        e.record()
+        recs.append((s, e, 2.0 * M * N * K * taps))
+
+    ops.gemm = timed
+    try:
+        plan._launch(x_dev)   # warm
+        recs.clear()
+        plan._launch(x_dev)
+        torch.cuda.synchronize()
+    finally:
+        ops.gemm = real
+    tot_ms = sum(s.elapsed_time(e) for s, e, _ in recs)
+    tot_fl = sum(f for _, _, f in recs)
+    achieved = tot_fl / (tot_ms * 1e-3) / 1e12
+    peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
+    mma_factor = 3 if model.nsplit == 2 else 1
+    return {
+        "bound": "tensor", "kernel": "gemm_tc_kernel (all GEMM + implicit-GEMM conv launches of one forward)",
+        "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+        "peak_source": f"bf16 dense sustained, {peak_src}", "traffic": None,
+        "launches": len(recs), "avg_launch_us": tot_ms * 1e3 / len(recs), "share_of_forward_ms": tot_ms,
+        "note": ("achieved counts the reference's ALGORITHMIC fp32 FLOPs (2*M*N*K); the parity mode issues "
+                 f"{mma_factor} bf16 tcgen05.mma per product, so the tensor pipe runs at "
+                 f"{achieved * mma_factor:.0f} TFLOP/s = {achieved * mma_factor / peak:.2f} of peak"),
+    }
+
+
+def run_ours(args):
+    rank, world, local = dist_setup(args.gpus)
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    import mtt_b200  # noqa: F401
+    from mtt_b200 import ops
+    from mtt_b200 import taskprompter as TP
+    from oracle import configs
+
+    cfg = configs.taskprompter(args.config)
+    nsplit = 2 if args.mode == "parity" else 1
+    torch.manual_seed(0)
+    with torch.device(dev):
+        model = TP.build_from_config(cfg, nsplit=nsplit, use_graph=True).eval()
+    B = args.batch
+    H, W = cfg["img_size"]
+    n_rot = 4
+    g = torch.Generator().manual_seed(1 + rank)
+    host_in = [torch.randn(B, 3, H, W, generator=g).pin_memory() for _ in range(n_rot)]
+    dev_in = [h.to(dev) for h in host_in]
+    plan = model.plan(B, dev)
+    with torch.no_grad():
+        out = model(dev_in[0])
+    torch.cuda.synchronize()
+    launches_per_fwd = plan.launches_per_forward()
+    torch.cuda.synchronize()
+
+    # ---------------- device-resident throughput ("value")
+    with torch.no_grad():
+        for i in range(args.warmup):
+            model(dev_in[i % n_rot])
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier(world)
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    with torch.no_grad():
+        for i in range(args.steps):
+            model(dev_in[i % n_rot])
+    e.record()
+    torch.cuda.synchronize()
+    barrier(world)
+    ms_total = max_over_ranks(s.elapsed_time(e), world, dev)
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * B * args.steps / (ms_total * 1e-3)
+
+    # ---------------- end to end through the public call, host buffers, H2D + D2H inside the timed region
+    out_bytes = sum(v.numel() * 4 for v in out.values())
+    in_bytes = host_in[0].numel() * 4
+    host_out = [{k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in out.items()} for _ in range(2)]
+    stage = [{k: torch.empty_like(v) for k, v in out.items()} for _ in range(2)]
+    copy_stream = torch.cuda.Stream(device=dev)
+    d2h_done = [torch.cuda.Event(), torch.cuda.Event()]
+    staged = [torch.cuda.Event(), torch.cuda.Event()]
+
+    def e2e_steps(n):
+        main = torch.cuda.current_stream()
+        for i in range(n):
+            j = i & 1
+            x = host_in[i % n_rot].to(dev, non_blocking=True)        # H2D from pinned memory
+            with torch.no_grad():
+                o = model(x)                                         # public nn.Module call
+            main.wait_event(d2h_done[j])                             # staging buffer j is free again
+            for k in o:
+                stage[j][k].copy_(o[k], non_blocking=True)
+            staged[j].record(main)
+            with torch.cuda.stream(copy_stream):                     # D2H overlaps the next step
+                copy_stream.wait_event(staged[j])
+                for k in o:
+                    host_out[j][k].copy_(stage[j][k], non_blocking=True)
+                d2h_done[j].record(copy_stream)
+        copy_stream.synchronize()
+
+    e2e_steps(max(2, args.warmup))
+    torch.cuda.synchronize()
+    barrier(world)
+    t0 = time.perf_counter()
+    s2, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s2.record()
+    e2e_steps(args.steps)
+    torch.cuda.current_stream().wait_stream(copy_stream)
+    e2.record()
+    torch.cuda.synchronize()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    barrier(world)
+    e2e_ms = max_over_ranks(max(s2.elapsed_time(e2), 0.0), world, dev)
+    e2e_value = world * B * args.steps / (e2e_ms * 1e-3)
+
+    if rank != 0:
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.destroy_process_group()
+        return
+
+    peaks, peak_src = load_peaks()
+    roof = gemm_roofline(model, plan, dev_in[0], peaks, peak_src)
+    gflop_img = GFLOP_PER_IMAGE.get(args.config)
+    line = {
+        "metric": "images/sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16x3 (split-bf16 operands, fp32 accumulate)" if nsplit == 2 else "bf16",
+        "data": "synthetic",
+        "config": {
+            "workload": f"TaskPrompter ViT-L PASCAL-Context (5 tasks) 512x512 forward, {args.config}, "
+                        f"bs {B}/GPU, random-init weights, eval",
+            "global_batch": world * B, "parallelism": f"dp{world} (batch-sharded forward, no collective)",
+            "precision_mode": args.mode,
+            "l2": "no explicit flush: each step streams 1.6 GB of packed weights plus ~1 GB of activations "
+                  "(>> 126 MB L2) and the input rotates over 4 buffers",
+        },
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": in_bytes,
+                "d2h_bytes_per_step": out_bytes, "ms_per_step": e2e_ms / args.steps, "wall_ms_per_step": wall_ms / args.steps,
+                "note": "pinned-host input -> H2D -> model(x) -> all task logits D2H (overlapped with the next step)"},
+        "gpu_launches": int(launches_per_fwd * args.steps),
+        "launches_per_step": int(launches_per_fwd),
+        "roofline": roof,
+    }
+    if gflop_img:
+        line["model_tflops_algorithmic"] = value * gflop_img / 1e3 / world
+    if world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        rate, sec = cpu_oracle_rate(args.config, 3, 1, threads)
+        line["cpu_baseline"] = {"value": rate, "unit": "images/s", "cores": threads, "kind": "port",
+                                "sample": f"3 forwards of batch 1 of {args.config} (oracle/taskprompter_ref.py, fp32 eager)"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", default="parity", choices=["parity", "speed"])
+    ap.add_argument("--config", default="tp_cfg4")
+    ap.add_argument("--batch", type=int, default=4)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
