@@ -185,10 +185,71 @@ int mtt_ctr_mix(const float* F, const float* w, float* acc, int32_t T, int64_t M
 
 /* Bilinear resize, align_corners=False (F.interpolate at TP taskprompter.py:420,
  * taskprompter_wrapper.py:35; IP transformer_net.py:35). in NHWC fp32 [B,h,w,C] (ld_in); outputs:
- * NHWC fp32 (optionally accumulated into) and/or NHWC split, and/or NCHW fp32 [B,C,H2,W2]. */
+ * NHWC fp32 (optionally accumulated into) and/or NHWC split, and/or NCHW fp32 [B,C,H2,W2].
+ * Image b starts at row b*in_batch_rows + in_row_offset of `in` (0 batch rows = dense h*w), and at row
+ * b*out_batch_rows + out_row_offset of the NHWC outputs: lets per-task slices of InvPT's joint
+ * [B, T*h*w, C] token buffers be resampled in place (IP invpt.py:299-305, :537). */
 int mtt_bilinear(const float* in, int64_t ld_in, int32_t B, int32_t h, int32_t w, int32_t C, int32_t H2,
                  int32_t W2, float* out_f32, int64_t ld_f32, void* out_hi, void* out_lo, int64_t ld_bf,
-                 float* out_nchw, int32_t accumulate, mtt_stream_t stream);
+                 float* out_nchw, int32_t accumulate, int64_t in_batch_rows, int64_t in_row_offset,
+                 int64_t out_batch_rows, int64_t out_row_offset, mtt_stream_t stream);
+
+/* ---- InvPT decoder (IP/models/transformers/invpt.py, transformer_decoder.py) ---------------- */
+/* fp32 rows gathered at (r / in_group) * src_group + src_offset + r % in_group -> dense split rows.
+ * Replaces x[:, 1:] token selection + layout copies (IP vit.py:345-346, transformer_decoder.py:77). */
+int mtt_split_rows(const float* in, int64_t ld_in, int64_t in_group, int64_t src_group, int64_t src_offset,
+                   void* out_hi, void* out_lo, int64_t ld_out, int64_t rows, int32_t cols,
+                   mtt_stream_t stream);
+
+/* LayerNorm over S segments of `cols` channels (segment s of logical row r lives S*... at physical row
+ * map(r) + s*seg_stride); gamma/beta [S*cols]; segment s is written to output row s*out_seg_stride + r.
+ * S = 1: gathered LayerNorm (IP vit.py:348-349). S = T: the joint-channel LayerNorm over all tasks'
+ * tokens, norm_mts (IP invpt.py:524-526). */
+int mtt_layernorm_seg(const float* in, int64_t ld_in, int64_t in_group, int64_t src_group,
+                      int64_t src_offset, int64_t seg_stride, int32_t S, const float* gamma,
+                      const float* beta, float eps, float* out_f32, int64_t ld_f32, void* out_hi,
+                      void* out_lo, int64_t ld_bf, int64_t out_seg_stride, int64_t rows, int32_t cols,
+                      mtt_stream_t stream);
+
+/* Stride-2 zero insertion [B,h,w,C] fp32 -> split [B,2h,2w,C]: ConvTranspose2d(k3,s2,p1,op1) then runs
+ * as a 3x3 convolution with the flipped kernel on mtt_gemm (IP transformer_decoder.py:63). */
+int mtt_zero_insert(const float* in, int64_t ld_in, int64_t src_group, int64_t src_offset, int32_t B,
+                    int32_t h, int32_t w, int32_t C, void* out_hi, void* out_lo, int64_t ld_out,
+                    mtt_stream_t stream);
+
+/* Per-task depthwise 3x3 stride-2 conv with folded eval BatchNorm -> Q tokens (IP invpt.py:125-137).
+ * in fp32 joint tokens [B, T*h*w, C]; weight [T,C,9], bias [T,C]; out split [B, T*(h/2)(w/2), C]. */
+int mtt_dwconv3x3_s2(const float* in, int64_t ld_in, int32_t B, int32_t T, int32_t h, int32_t w, int32_t C,
+                     const float* weight, const float* bias, void* out_hi, void* out_lo, int64_t ld_out,
+                     mtt_stream_t stream);
+
+/* Per-task average pooling kernel = stride = s, ceil_mode (IP invpt.py:139-147): in fp32 [BT, h*w, C]
+ * -> split [BT, ceil(h/s)*ceil(w/s), C]. */
+int mtt_avgpool(const float* in, int64_t ld_in, int32_t BT, int32_t h, int32_t w, int32_t C, int32_t s,
+                void* out_hi, void* out_lo, int64_t ld_out, mtt_stream_t stream);
+
+/* InvPT cross-task attention with cross-scale score fusion (IP invpt.py:204-236), 2 heads.
+ * q fp32 [B,Lq,C] (ldq), k/v fp32 [B,Tk,C] (ldk), scale = C^-1/2. prev_score (optional) fp32
+ * [B,2,T*(qh/2)*(qw/2),Tk] is bilinearly up-sampled x2 per task over the query grid and mixed with the
+ * current scores by the 1x1 conv fuse_w [2,4], fuse_b [2]. score_out (optional) fp32 [B,2,Lq,Tk] gets
+ * the fused pre-softmax scores; out = softmax . v as split [B*Lq, C]. */
+typedef struct {
+  const float* q;
+  const float* k;
+  const float* v;
+  int64_t ldq, ldk;
+  int32_t B, Lq, Tk, C;
+  float scale;
+  const float* prev_score;
+  int32_t T, qh, qw;
+  const float* fuse_w;
+  const float* fuse_b;
+  float* score_out;
+  void* out_hi;
+  void* out_lo;
+  int64_t ldo;
+} mtt_invpt_attn_desc;
+int mtt_invpt_attention(const mtt_invpt_attn_desc* d, mtt_stream_t stream);
 
 #ifdef __cplusplus
 }

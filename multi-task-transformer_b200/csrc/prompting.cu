@@ -251,20 +251,22 @@ __device__ __forceinline__ void bilin_coord(int d, float scale, int in_size, int
 }
 
 __global__ void __launch_bounds__(256)
-bilinear_nhwc_kernel(const float* __restrict__ in, long long ld_in, int B, int h, int w, int C, int H2, int W2,
-                     float sy, float sx, float* __restrict__ out_f32, long long ld_f32,
-                     __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo, long long ld_bf,
-                     int accumulate) {
-  const long long opix = blockIdx.x;  // (b * H2 + y) * W2 + x
-  const int x = (int)(opix % W2), y = (int)((opix / W2) % H2), b = (int)(opix / ((long long)W2 * H2));
+bilinear_nhwc_kernel(const float* __restrict__ in, long long ld_in, long long in_brows, long long in_off, int B,
+                     int h, int w, int C, int H2, int W2, float sy, float sx, float* __restrict__ out_f32,
+                     long long ld_f32, __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo,
+                     long long ld_bf, long long out_brows, long long out_off, int accumulate) {
+  const long long gpix = blockIdx.x;  // (b * H2 + y) * W2 + x
+  const int x = (int)(gpix % W2), y = (int)((gpix / W2) % H2), b = (int)(gpix / ((long long)W2 * H2));
+  const long long opix = (long long)b * out_brows + out_off + (long long)y * W2 + x;
   int y0, y1, x0, x1;
   float ly, lx;
   bilin_coord(y, sy, h, y0, y1, ly);
   bilin_coord(x, sx, w, x0, x1, lx);
-  const float* p00 = in + (((long long)b * h + y0) * w + x0) * ld_in;
-  const float* p01 = in + (((long long)b * h + y0) * w + x1) * ld_in;
-  const float* p10 = in + (((long long)b * h + y1) * w + x0) * ld_in;
-  const float* p11 = in + (((long long)b * h + y1) * w + x1) * ld_in;
+  const float* ib = in + ((long long)b * in_brows + in_off) * ld_in;
+  const float* p00 = ib + ((long long)y0 * w + x0) * ld_in;
+  const float* p01 = ib + ((long long)y0 * w + x1) * ld_in;
+  const float* p10 = ib + ((long long)y1 * w + x0) * ld_in;
+  const float* p11 = ib + ((long long)y1 * w + x1) * ld_in;
   const float hy = 1.f - ly, hx = 1.f - lx;
   for (int c = threadIdx.x * 2; c < C; c += blockDim.x * 2) {
     const bool two = c + 1 < C;
@@ -295,8 +297,8 @@ bilinear_nhwc_kernel(const float* __restrict__ in, long long ld_in, int B, int h
 
 // NHWC fp32 [B,h,w,C] -> NCHW fp32 [B,C,H2,W2]; one thread per output pixel, loop over channels.
 __global__ void __launch_bounds__(256)
-bilinear_to_nchw_kernel(const float* __restrict__ in, long long ld_in, int B, int h, int w, int C, int H2,
-                        int W2, float sy, float sx, float* __restrict__ out) {
+bilinear_to_nchw_kernel(const float* __restrict__ in, long long ld_in, long long in_brows, long long in_off, int B,
+                        int h, int w, int C, int H2, int W2, float sy, float sx, float* __restrict__ out) {
   const long long opix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (opix >= (long long)B * H2 * W2) return;
   const int x = (int)(opix % W2), y = (int)((opix / W2) % H2), b = (int)(opix / ((long long)W2 * H2));
@@ -304,10 +306,11 @@ bilinear_to_nchw_kernel(const float* __restrict__ in, long long ld_in, int B, in
   float ly, lx;
   bilin_coord(y, sy, h, y0, y1, ly);
   bilin_coord(x, sx, w, x0, x1, lx);
-  const float* p00 = in + (((long long)b * h + y0) * w + x0) * ld_in;
-  const float* p01 = in + (((long long)b * h + y0) * w + x1) * ld_in;
-  const float* p10 = in + (((long long)b * h + y1) * w + x0) * ld_in;
-  const float* p11 = in + (((long long)b * h + y1) * w + x1) * ld_in;
+  const float* ib = in + ((long long)b * in_brows + in_off) * ld_in;
+  const float* p00 = ib + ((long long)y0 * w + x0) * ld_in;
+  const float* p01 = ib + ((long long)y0 * w + x1) * ld_in;
+  const float* p10 = ib + ((long long)y1 * w + x0) * ld_in;
+  const float* p11 = ib + ((long long)y1 * w + x1) * ld_in;
   const float hy = 1.f - ly, hx = 1.f - lx;
   for (int c = 0; c < C; ++c) {
     const float v = hy * (hx * p00[c] + lx * p01[c]) + ly * (hx * p10[c] + lx * p11[c]);
@@ -446,15 +449,18 @@ extern "C" int mtt_ctr_mix(const float* F, const float* w, float* acc, int32_t T
 extern "C" int mtt_bilinear(const float* in, int64_t ld_in, int32_t B, int32_t h, int32_t w, int32_t C,
                             int32_t H2, int32_t W2, float* out_f32, int64_t ld_f32, void* out_hi,
                             void* out_lo, int64_t ld_bf, float* out_nchw, int32_t accumulate,
-                            mtt_stream_t stream) {
+                            int64_t in_batch_rows, int64_t in_row_offset, int64_t out_batch_rows,
+                            int64_t out_row_offset, mtt_stream_t stream) {
   if (!in || B <= 0 || h <= 0 || w <= 0 || C <= 0 || H2 <= 0 || W2 <= 0 ||
       (!out_f32 && !out_hi && !out_nchw))
     return set_error(MTT_ERR_BAD_SHAPE, "mtt_bilinear: bad arguments");
   const float sy = (float)h / (float)H2, sx = (float)w / (float)W2;
   const long long opix = (long long)B * H2 * W2;
+  if (in_batch_rows <= 0) in_batch_rows = (long long)h * w;
+  if (out_batch_rows <= 0) out_batch_rows = (long long)H2 * W2;
   if (out_nchw) {
-    bilinear_to_nchw_kernel<<<(unsigned)((opix + 255) / 256), 256, 0, STREAM>>>(in, ld_in, B, h, w, C, H2,
-                                                                               W2, sy, sx, out_nchw);
+    bilinear_to_nchw_kernel<<<(unsigned)((opix + 255) / 256), 256, 0, STREAM>>>(
+        in, ld_in, in_batch_rows, in_row_offset, B, h, w, C, H2, W2, sy, sx, out_nchw);
     int rc = check_launch("mtt_bilinear(nchw)");
     if (rc) return rc;
   }
@@ -463,8 +469,9 @@ extern "C" int mtt_bilinear(const float* in, int64_t ld_in, int32_t B, int32_t h
       return set_error(MTT_ERR_MISALIGNED, "mtt_bilinear: ld_bf must be even");
     const int threads = C >= 512 ? 256 : (C >= 128 ? 128 : 64);
     bilinear_nhwc_kernel<<<(unsigned)opix, threads, 0, STREAM>>>(
-        in, ld_in, B, h, w, C, H2, W2, sy, sx, out_f32, ld_f32, static_cast<__nv_bfloat16*>(out_hi),
-        static_cast<__nv_bfloat16*>(out_lo), ld_bf, accumulate);
+        in, ld_in, in_batch_rows, in_row_offset, B, h, w, C, H2, W2, sy, sx, out_f32, ld_f32,
+        static_cast<__nv_bfloat16*>(out_hi), static_cast<__nv_bfloat16*>(out_lo), ld_bf, out_batch_rows,
+        out_row_offset, accumulate);
     return check_launch("mtt_bilinear(nhwc)");
   }
   return MTT_OK;

@@ -84,7 +84,7 @@ def layernorm(x, gamma, beta, eps, out_f32=None, out_split=None):
 
 
 def gemm(a, w, *, M=None, N=None, K=None, bias=None, act=ACT_NONE, residual=None, res_row_mod=0,
-         out_f32=None, out_split=None, out_col_offset=0, regroup=None, conv=None):
+         out_f32=None, out_split=None, out_col_offset=0, regroup=None, conv=None, a_row_offset=0):
     """D = act(A @ W^T + bias) + residual on the tcgen05 GEMM.
 
     a: Split [M, K] (or NHWC activation [B*H*W, C] when ``conv=(B, H, W, ksize, dil)``);
@@ -92,7 +92,8 @@ def gemm(a, w, *, M=None, N=None, K=None, bias=None, act=ACT_NONE, residual=None
     regroup=(in_group, out_group, out_offset) scatters output rows."""
     nsplit = min(a.nsplit, w.nsplit)
     d = _L.GemmDesc()
-    d.a_hi, d.a_lo, d.lda = a.hi.data_ptr(), (a.lo.data_ptr() if nsplit == 2 else 0), a.ld
+    aoff = 2 * a_row_offset * a.ld
+    d.a_hi, d.a_lo, d.lda = a.hi.data_ptr() + aoff, (a.lo.data_ptr() + aoff if nsplit == 2 else 0), a.ld
     d.b_hi, d.b_lo, d.ldb = w.hi.data_ptr(), (w.lo.data_ptr() if nsplit == 2 else 0), w.ld
     d.M = a.rows if M is None else M
     d.N = w.rows if N is None else N
@@ -220,12 +221,74 @@ def ctr_mix(F, w, acc, *, T, M, Cdim, ld, rows_per_batch, accumulate):
 
 
 def bilinear(x, ld_in, B, h, w, Cdim, H2, W2, *, out_f32=None, out_split=None, out_nchw=None,
-             accumulate=False):
+             accumulate=False, in_batch_rows=0, in_row_offset=0, out_batch_rows=0, out_row_offset=0):
     """x: NHWC fp32 [B*h*w, ld_in] -> NHWC fp32 / NHWC Split / NCHW fp32 [B,C,H2,W2]."""
     rc = _L.load().mtt_bilinear(
         _ptr(x), ld_in, B, h, w, Cdim, H2, W2, _ptr(out_f32),
         out_f32.stride(-2) if out_f32 is not None else 0,
         _ptr(out_split.hi) if out_split is not None else None,
         _ptr(out_split.lo) if out_split is not None else None,
-        out_split.ld if out_split is not None else 0, _ptr(out_nchw), 1 if accumulate else 0, _stream())
+        out_split.ld if out_split is not None else 0, _ptr(out_nchw), 1 if accumulate else 0,
+        in_batch_rows, in_row_offset, out_batch_rows, out_row_offset, _stream())
     _L.check(rc, "mtt_bilinear")
+
+
+def split_rows(x, out, *, rows, cols, in_group=0, src_group=0, src_offset=0):
+    """Gather fp32 rows of x (row r at (r // in_group) * src_group + src_offset + r % in_group) -> Split."""
+    assert x.dtype == torch.float32 and x.stride(-1) == 1
+    rc = _L.load().mtt_split_rows(_ptr(x), x.stride(-2), in_group, src_group, src_offset, _ptr(out.hi),
+                                  _ptr(out.lo), out.ld, rows, cols, _stream())
+    _L.check(rc, "mtt_split_rows")
+
+
+def layernorm_seg(x, gamma, beta, eps, *, rows, cols, S=1, in_group=0, src_group=0, src_offset=0,
+                  seg_stride=0, out_f32=None, out_split=None, out_seg_stride=0):
+    assert x.dtype == torch.float32 and x.stride(-1) == 1
+    rc = _L.load().mtt_layernorm_seg(
+        _ptr(x), x.stride(-2), in_group, src_group, src_offset, seg_stride, S, _ptr(gamma), _ptr(beta),
+        float(eps), _ptr(out_f32), out_f32.stride(-2) if out_f32 is not None else 0,
+        _ptr(out_split.hi) if out_split is not None else None,
+        _ptr(out_split.lo) if out_split is not None else None,
+        out_split.ld if out_split is not None else 0, out_seg_stride, rows, cols, _stream())
+    _L.check(rc, "mtt_layernorm_seg")
+
+
+def zero_insert(x, out, *, B, h, w, Cdim, src_group, src_offset):
+    assert x.dtype == torch.float32 and x.stride(-1) == 1
+    rc = _L.load().mtt_zero_insert(_ptr(x), x.stride(-2), src_group, src_offset, B, h, w, Cdim, _ptr(out.hi),
+                                   _ptr(out.lo), out.ld, _stream())
+    _L.check(rc, "mtt_zero_insert")
+
+
+def dwconv3x3_s2(x, weight, bias, out, *, B, T, h, w, Cdim):
+    assert x.dtype == torch.float32 and x.stride(-1) == 1 and weight.is_contiguous() and bias.is_contiguous()
+    rc = _L.load().mtt_dwconv3x3_s2(_ptr(x), x.stride(-2), B, T, h, w, Cdim, _ptr(weight), _ptr(bias),
+                                    _ptr(out.hi), _ptr(out.lo), out.ld, _stream())
+    _L.check(rc, "mtt_dwconv3x3_s2")
+
+
+def avgpool(x, out, *, BT, h, w, Cdim, s):
+    assert x.dtype == torch.float32 and x.stride(-1) == 1
+    rc = _L.load().mtt_avgpool(_ptr(x), x.stride(-2), BT, h, w, Cdim, s, _ptr(out.hi), _ptr(out.lo), out.ld,
+                               _stream())
+    _L.check(rc, "mtt_avgpool")
+
+
+def invpt_attention(q, k, v, out, *, B, Lq, Tk, Cdim, scale, prev_score=None, T=0, qh=0, qw=0, fuse_w=None,
+                    fuse_b=None, score_out=None):
+    d = _L.InvptAttnDesc()
+    for t in (q, k, v):
+        assert t.dtype == torch.float32 and t.stride(-1) == 1
+    assert k.stride(-2) == v.stride(-2)
+    d.q, d.k, d.v, d.ldq, d.ldk = q.data_ptr(), k.data_ptr(), v.data_ptr(), q.stride(-2), k.stride(-2)
+    d.B, d.Lq, d.Tk, d.C, d.scale = B, Lq, Tk, Cdim, float(scale)
+    if prev_score is not None:
+        assert prev_score.is_contiguous() and fuse_w.is_contiguous()
+        d.prev_score, d.T, d.qh, d.qw = prev_score.data_ptr(), T, qh, qw
+        d.fuse_w, d.fuse_b = fuse_w.data_ptr(), fuse_b.data_ptr()
+    if score_out is not None:
+        assert score_out.is_contiguous()
+        d.score_out = score_out.data_ptr()
+    d.out_hi, d.out_lo, d.ldo = out.hi.data_ptr(), (out.lo.data_ptr() if out.nsplit == 2 else 0), out.ld
+    rc = _L.load().mtt_invpt_attention(C.byref(d), _stream())
+    _L.check(rc, "mtt_invpt_attention")

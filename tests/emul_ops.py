@@ -56,11 +56,11 @@ def install(mp):
             _wsplit(out_split, y)
 
     def gemm(a, w, *, M=None, N=None, K=None, bias=None, act=0, residual=None, res_row_mod=0, out_f32=None,
-             out_split=None, out_col_offset=0, regroup=None, conv=None):
+             out_split=None, out_col_offset=0, regroup=None, conv=None, a_row_offset=0):
         M = a.rows if M is None else M
         N = w.rows if N is None else N
         K = a.cols if K is None else K
-        A = _rsplit(a, K)[:M]
+        A = _rsplit(a, K)[a_row_offset:a_row_offset + M]
         if conv is None:
             Wm = _rsplit(w, K)[:N]
             y = A @ Wm.t()
@@ -157,19 +157,87 @@ def install(mp):
             acc.copy_(new)
 
     def bilinear(x, ld_in, B, h, w, Cdim, H2, W2, *, out_f32=None, out_split=None, out_nchw=None,
-                 accumulate=False):
-        img = x.reshape(B, h, w, ld_in)[..., :Cdim].permute(0, 3, 1, 2)
+                 accumulate=False, in_batch_rows=0, in_row_offset=0, out_batch_rows=0, out_row_offset=0):
+        ibr = in_batch_rows or h * w
+        obr = out_batch_rows or H2 * W2
+        rows_in = (torch.arange(B)[:, None] * ibr + in_row_offset + torch.arange(h * w)[None]).reshape(-1)
+        rows_out = (torch.arange(B)[:, None] * obr + out_row_offset + torch.arange(H2 * W2)[None]).reshape(-1)
+        img = x[rows_in, :Cdim].reshape(B, h, w, Cdim).permute(0, 3, 1, 2)
         y = F.interpolate(img, size=(H2, W2), mode="bilinear", align_corners=False)
         if out_nchw is not None:
             out_nchw.copy_(y)
         yn = y.permute(0, 2, 3, 1).reshape(B * H2 * W2, Cdim)
         if out_f32 is not None:
             if accumulate:
-                out_f32[:, :Cdim] += yn
-            else:
-                out_f32[:, :Cdim] = yn
+                yn = yn + out_f32[rows_out, :Cdim]
+            out_f32[rows_out, :Cdim] = yn
         if out_split is not None:
-            _wsplit(out_split, yn)
+            hi = yn.bfloat16()
+            out_split.buf[0, rows_out, :Cdim] = hi
+            if out_split.nsplit == 2:
+                out_split.buf[1, rows_out, :Cdim] = (yn - hi.float()).bfloat16()
+
+    def _rows(rows, in_group, src_group, src_offset):
+        r = torch.arange(rows)
+        return (r // in_group) * src_group + src_offset + r % in_group if in_group > 0 else r + src_offset
+
+    def split_rows(x, out, *, rows, cols, in_group=0, src_group=0, src_offset=0):
+        _wsplit(out, x[_rows(rows, in_group, src_group, src_offset), :cols])
+
+    def layernorm_seg(x, gamma, beta, eps, *, rows, cols, S=1, in_group=0, src_group=0, src_offset=0,
+                      seg_stride=0, out_f32=None, out_split=None, out_seg_stride=0):
+        base = _rows(rows, in_group, src_group, src_offset)
+        segs = torch.cat([x[base + k * seg_stride, :cols] for k in range(S)], dim=1)     # [rows, S*cols]
+        y = F.layer_norm(segs, (S * cols,), gamma, beta, eps)
+        for k in range(S):
+            yk = y[:, k * cols:(k + 1) * cols]
+            orow = k * out_seg_stride + torch.arange(rows)
+            if out_f32 is not None:
+                out_f32[orow, :cols] = yk
+            if out_split is not None:
+                hi = yk.bfloat16()
+                out_split.buf[0, orow, :cols] = hi
+                if out_split.nsplit == 2:
+                    out_split.buf[1, orow, :cols] = (yk - hi.float()).bfloat16()
+
+    def zero_insert(x, out, *, B, h, w, Cdim, src_group, src_offset):
+        src = x[_rows(B * h * w, h * w, src_group, src_offset), :Cdim].reshape(B, h, w, Cdim)
+        z = torch.zeros(B, 2 * h, 2 * w, Cdim)
+        z[:, ::2, ::2] = src
+        _wsplit(out, z.reshape(-1, Cdim))
+
+    def dwconv3x3_s2(x, weight, bias, out, *, B, T, h, w, Cdim):
+        xm = x[:, :Cdim].reshape(B, T, h, w, Cdim).permute(0, 1, 4, 2, 3)
+        ys = []
+        for k in range(T):
+            y = F.conv2d(xm[:, k], weight[k].reshape(Cdim, 1, 3, 3), bias[k], stride=2, padding=1, groups=Cdim)
+            ys.append(y.flatten(2).transpose(1, 2))                                       # [B, hw/4, C]
+        _wsplit(out, torch.stack(ys, 1).reshape(-1, Cdim))
+
+    def avgpool(x, out, *, BT, h, w, Cdim, s):
+        xm = x[:, :Cdim].reshape(BT, h, w, Cdim).permute(0, 3, 1, 2)
+        y = F.avg_pool2d(xm, s, s, 0, ceil_mode=True)
+        _wsplit(out, y.flatten(2).transpose(1, 2).reshape(-1, Cdim))
+
+    def invpt_attention(q, k, v, out, *, B, Lq, Tk, Cdim, scale, prev_score=None, T=0, qh=0, qw=0, fuse_w=None,
+                        fuse_b=None, score_out=None):
+        d = Cdim // 2
+        sp = lambda t, L: t[:, :Cdim].reshape(B, L, 2, d).transpose(1, 2)
+        Q, K, V = sp(q, Lq), sp(k, Tk), sp(v, Tk)
+        score = (Q @ K.transpose(-2, -1)) * scale
+        if prev_score is not None:
+            sh, sw = qh // 2, qw // 2
+            ups = []
+            for i in range(T):
+                s_ = prev_score[:, :, sh * sw * i: sh * sw * (i + 1), :].permute(0, 1, 3, 2).reshape(B * 2, Tk, sh, sw)
+                s_ = F.interpolate(s_, scale_factor=2, mode="bilinear", align_corners=False)
+                ups.append(s_.reshape(B, 2, Tk, -1).permute(0, 1, 3, 2))
+            both = torch.cat([score, torch.cat(ups, dim=2)], dim=1)
+            score = F.conv2d(both, fuse_w.reshape(2, 4, 1, 1), fuse_b)
+        if score_out is not None:
+            score_out.copy_(score)
+        o = (score.softmax(-1) @ V).transpose(1, 2).reshape(B * Lq, Cdim)
+        _wsplit(out, o)
 
     for name, fn in list(locals().items()):
         if callable(fn) and hasattr(ops, name) and name not in ("mp",):

@@ -52,3 +52,27 @@ def test_state_dict_keys_match_oracle_names():
         mine = model.state_dict()
         assert set(mine) == set(sd)
         assert all(mine[k].shape == sd[k].shape for k in sd)
+
+
+@pytest.mark.parametrize("name,nsplit,tol", [("ip_tiny", 2, 3e-4), ("ip_cfg1", 2, 3e-4)])
+def test_invpt_plan_matches_oracle(monkeypatch, name, nsplit, tol):
+    import mtt_b200  # noqa: F401
+    from mtt_b200 import invpt as IP
+    from oracle import invpt_ref as IPR
+    import emul_ops
+
+    emul_ops.install(monkeypatch)
+    cfg = configs.invpt(name)
+    sd = IPR.init_state_dict(cfg, seed=5)
+    model = IP.build_from_config(cfg, nsplit=nsplit, use_graph=False).eval()
+    model.load_state_dict(sd, strict=True)
+    torch.manual_seed(2)
+    x = torch.randn(2, 3, *cfg["img_size"])
+    with torch.no_grad():
+        ref = IPR.forward(sd, cfg, x)
+        got = model.plan(2, torch.device("cpu")).run(x, graph=False)
+    for t in cfg["tasks"]:
+        err = (got[t] - ref[t]).norm() / ref[t].norm()
+        assert err < tol, f"{name} {t}: rel-L2 {err:.3e}"
+        err = (got["inter_preds"][t] - ref["inter_preds"][t]).norm() / ref["inter_preds"][t].norm()
+        assert err < tol, f"{name} inter {t}: rel-L2 {err:.3e}"
