@@ -98,6 +98,11 @@ typedef struct {
   void* out_lo;
   int64_t ldo_bf;
   int32_t in_group, out_group, out_offset;
+  /* mode 0 only. a_group_rows > 0: A's logical row r = (g, i) lives at physical row
+   * g * a_group_stride + i (i < a_group_rows <= 128, a_group_rows | M): gathers e.g. the T prompt rows
+   * of every image out of the joint [B*N, C] stream for token_trans (TP taskprompter.py:219). */
+  int32_t a_group_rows;
+  int64_t a_group_stride;
 } mtt_gemm_desc;
 
 int mtt_gemm(const mtt_gemm_desc* d, mtt_stream_t stream);

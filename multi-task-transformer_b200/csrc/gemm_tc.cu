@@ -46,6 +46,7 @@ struct GemmParams {
   long long ldo_bf;
   int in_group, out_group, out_offset;
   int vec_ok;
+  int a_groups_per_tile;  // >0: A rows are gathered in groups through a rank-3 tensor map
 };
 
 template <int NSPLIT>
@@ -124,7 +125,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             uint8_t* sa = smem + stage * Cfg::kStageBytes;
             uint8_t* sb = sa + NSPLIT * kTileBytes;
             mbar_arrive_expect_tx(&full_bar[stage], stage_tx);
-            if (p.mode == 0) {
+            if (p.mode == 0 && p.a_groups_per_tile > 0) {
+              tma_load_3d(sa, &tmA_hi, &full_bar[stage], kb * BK, 0, mt * p.a_groups_per_tile);
+              if (NSPLIT == 2)
+                tma_load_3d(sa + kTileBytes, &tmA_lo, &full_bar[stage], kb * BK, 0, mt * p.a_groups_per_tile);
+            } else if (p.mode == 0) {
               tma_load_2d(sa, &tmA_hi, &full_bar[stage], kb * BK, mt * BM);
               if (NSPLIT == 2) tma_load_2d(sa + kTileBytes, &tmA_lo, &full_bar[stage], kb * BK, mt * BM);
             } else {
@@ -392,7 +397,34 @@ extern "C" int mtt_gemm(const mtt_gemm_desc* d, mtt_stream_t stream_) {
   CUtensorMap maps[4];
   int rc;
   const int ksq = (d->mode == 1) ? d->ksize * d->ksize : 1;
-  if (d->mode == 0) {
+  if (d->mode == 0 && d->a_group_rows > 0) {
+    // gathered A: logical row r = (g, i) lives at physical row g * a_group_stride + i, i < a_group_rows
+    const int g = d->a_group_rows;
+    if (g > BM || d->M % g || d->a_group_stride < g)
+      return set_error(MTT_ERR_BAD_SHAPE, "mtt_gemm: a_group_rows=%d must divide M=%d and be <= %d", g, d->M, BM);
+    const int ngroups = d->M / g;
+    const int gpt = BM / g;  // groups per tile
+    if (ngroups > gpt && BM % g)
+      return set_error(MTT_ERR_BAD_SHAPE, "mtt_gemm: %d groups of %d rows need %d %% %d == 0", ngroups, g, BM, g);
+    p.taps = 1;
+    p.ksize = 1;
+    p.dil = 1;
+    p.cin_pad = 0;
+    p.a_groups_per_tile = ngroups < gpt ? ngroups : gpt;
+    p.tiles_m = (ngroups + p.a_groups_per_tile - 1) / p.a_groups_per_tile;
+    if (p.tiles_m > 1 && p.a_groups_per_tile * g != BM)
+      return set_error(MTT_ERR_BAD_SHAPE, "mtt_gemm: gathered A tiles must be full");
+    p.a_box_bytes = (uint32_t)(p.a_groups_per_tile * g) * BK * 2;
+    const uint64_t dims[3] = {(uint64_t)d->K, (uint64_t)g, (uint64_t)ngroups};
+    const uint64_t str[2] = {(uint64_t)d->lda * 2, (uint64_t)d->a_group_stride * d->lda * 2};
+    const uint32_t box[3] = {BK, (uint32_t)g, (uint32_t)p.a_groups_per_tile};
+    if ((rc = make_tmap_bf16(&maps[0], d->a_hi, 3, dims, str, box))) return rc;
+    if (d->nsplit == 2) {
+      if ((rc = make_tmap_bf16(&maps[1], d->a_lo, 3, dims, str, box))) return rc;
+    } else {
+      maps[1] = maps[0];
+    }
+  } else if (d->mode == 0) {
     p.taps = 1;
     p.ksize = 1;
     p.dil = 1;

@@ -115,38 +115,50 @@ __global__ void __launch_bounds__(256) skinny_linear_kernel(const SkinnyParams p
 // Raw channel logits  Rc[b,t,c,i,j] = sum_{pixel in window (i,j)} cp[b,t,pixel] * xn[b,pixel,c]
 // reference: taskprompter.py:236-240,246 (the softmax.V after it is dead code and not reproduced).
 constexpr int kMaxTasks = 8;
-__global__ void __launch_bounds__(128)
+// block = 32 channels x 32 pixel groups; grid = (C/32, windows, B): the pixel reduction is split over
+// the 32 groups and finished through shared memory, so the grid fills the chip even with one window.
+__global__ void __launch_bounds__(1024)
 chan_logits_kernel(const float* __restrict__ cp, const __nv_bfloat16* __restrict__ xh,
                    const __nv_bfloat16* __restrict__ xl, long long ldx, int N, int T, int C, int gh, int gw,
                    int nh, int nw, float* __restrict__ out) {
-  extern __shared__ float scp[];  // [T][wh*ww]
+  extern __shared__ float scp[];  // [T][wh*ww] then [T][32][33] partials
   const int b = blockIdx.z, win = blockIdx.y;
   const int wi = win / nw, wj = win % nw;
   const int wh = gh / nh, ww = gw / nw, wp = wh * ww;
   const int P = gh * gw;
-  for (int i = threadIdx.x; i < T * wp; i += blockDim.x) {
+  float* red = scp + T * wp;
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+  for (int i = tid; i < T * wp; i += 1024) {
     const int t = i / wp, q = i % wp;
     const int pix = (wi * wh + q / ww) * gw + wj * ww + q % ww;
     scp[i] = cp[((long long)b * T + t) * P + pix];
   }
   __syncthreads();
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+  const int c = blockIdx.x * 32 + threadIdx.x;
   float acc[kMaxTasks];
 #pragma unroll
   for (int t = 0; t < kMaxTasks; ++t) acc[t] = 0.f;
-  for (int q = 0; q < wp; ++q) {
-    const int pix = (wi * wh + q / ww) * gw + wj * ww + q % ww;
-    const long long row = (long long)b * N + T + pix;
-    float x = __bfloat162float(xh[row * ldx + c]);
-    if (xl) x += __bfloat162float(xl[row * ldx + c]);
+  if (c < C) {
+    for (int q = threadIdx.y; q < wp; q += 32) {
+      const int pix = (wi * wh + q / ww) * gw + wj * ww + q % ww;
+      const long long row = (long long)b * N + T + pix;
+      float x = __bfloat162float(xh[row * ldx + c]);
+      if (xl) x += __bfloat162float(xl[row * ldx + c]);
 #pragma unroll
-    for (int t = 0; t < kMaxTasks; ++t)
-      if (t < T) acc[t] = fmaf(scp[t * wp + q], x, acc[t]);
+      for (int t = 0; t < kMaxTasks; ++t)
+        if (t < T) acc[t] = fmaf(scp[t * wp + q], x, acc[t]);
+    }
   }
 #pragma unroll
   for (int t = 0; t < kMaxTasks; ++t)
-    if (t < T) out[((((long long)b * T + t) * C + c) * nh + wi) * nw + wj] = acc[t];
+    if (t < T) red[(t * 32 + threadIdx.y) * 33 + threadIdx.x] = acc[t];
+  __syncthreads();
+  if (threadIdx.y < T && c < C) {
+    const int t = threadIdx.y;
+    float s = 0.f;
+    for (int g = 0; g < 32; ++g) s += red[(t * 32 + g) * 33 + threadIdx.x];
+    out[((((long long)b * T + t) * C + c) * nh + wi) * nw + wj] = s;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -255,7 +267,9 @@ bilinear_nhwc_kernel(const float* __restrict__ in, long long ld_in, long long in
                      int h, int w, int C, int H2, int W2, float sy, float sx, float* __restrict__ out_f32,
                      long long ld_f32, __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo,
                      long long ld_bf, long long out_brows, long long out_off, int accumulate) {
-  const long long gpix = blockIdx.x;  // (b * H2 + y) * W2 + x
+  const long long gpix = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);  // (b*H2 + y)*W2 + x
+  if (gpix >= (long long)B * H2 * W2) return;
+  const int lane = threadIdx.x & 31;
   const int x = (int)(gpix % W2), y = (int)((gpix / W2) % H2), b = (int)(gpix / ((long long)W2 * H2));
   const long long opix = (long long)b * out_brows + out_off + (long long)y * W2 + x;
   int y0, y1, x0, x1;
@@ -268,7 +282,7 @@ bilinear_nhwc_kernel(const float* __restrict__ in, long long ld_in, long long in
   const float* p10 = ib + ((long long)y1 * w + x0) * ld_in;
   const float* p11 = ib + ((long long)y1 * w + x1) * ld_in;
   const float hy = 1.f - ly, hx = 1.f - lx;
-  for (int c = threadIdx.x * 2; c < C; c += blockDim.x * 2) {
+  for (int c = lane * 2; c < C; c += 64) {
     const bool two = c + 1 < C;
     float v0 = hy * (hx * p00[c] + lx * p01[c]) + ly * (hx * p10[c] + lx * p11[c]);
     float v1 = two ? hy * (hx * p00[c + 1] + lx * p01[c + 1]) + ly * (hx * p10[c + 1] + lx * p11[c + 1]) : 0.f;
@@ -395,15 +409,15 @@ extern "C" int mtt_chan_logits(const float* cp, const void* xn_hi, const void* x
     return set_error(MTT_ERR_BAD_SHAPE, "mtt_chan_logits: bad arguments (T=%d grid %dx%d windows %dx%d)",
                      T, gh, gw, nh, nw);
   const int wp = (gh / nh) * (gw / nw);
-  const size_t smem = (size_t)T * wp * sizeof(float);
+  const size_t smem = ((size_t)T * wp + (size_t)T * 32 * 33) * sizeof(float);
   if (smem > 200 * 1024) return set_error(MTT_ERR_BAD_SHAPE, "mtt_chan_logits: window too large");
   static bool attr = false;
-  if (!attr && smem > 48 * 1024) {
+  if (!attr) {
     cudaFuncSetAttribute(chan_logits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr = true;
   }
-  dim3 grid((C + 127) / 128, nh * nw, B);
-  chan_logits_kernel<<<grid, 128, smem, STREAM>>>(cp, static_cast<const __nv_bfloat16*>(xn_hi),
+  dim3 grid((C + 31) / 32, nh * nw, B);
+  chan_logits_kernel<<<grid, dim3(32, 32), smem, STREAM>>>(cp, static_cast<const __nv_bfloat16*>(xn_hi),
                                                  static_cast<const __nv_bfloat16*>(xn_lo), ldx, N, T, C, gh,
                                                  gw, nh, nw, out);
   return check_launch("mtt_chan_logits");
@@ -467,8 +481,7 @@ extern "C" int mtt_bilinear(const float* in, int64_t ld_in, int32_t B, int32_t h
   if (out_f32 || out_hi) {
     if (out_hi && (ld_bf % 2))
       return set_error(MTT_ERR_MISALIGNED, "mtt_bilinear: ld_bf must be even");
-    const int threads = C >= 512 ? 256 : (C >= 128 ? 128 : 64);
-    bilinear_nhwc_kernel<<<(unsigned)opix, threads, 0, STREAM>>>(
+    bilinear_nhwc_kernel<<<(unsigned)((opix + 7) / 8), 256, 0, STREAM>>>(
         in, ld_in, in_batch_rows, in_row_offset, B, h, w, C, H2, W2, sy, sx, out_f32, ld_f32,
         static_cast<__nv_bfloat16*>(out_hi), static_cast<__nv_bfloat16*>(out_lo), ld_bf, out_batch_rows,
         out_row_offset, accumulate);

@@ -98,6 +98,57 @@ layernorm_kernel(const float* __restrict__ in, long long ld_in, const float* __r
   }
 }
 
+
+// Fast path: the whole row lives in registers (cols % 128 == 0, cols <= 1024): one global read,
+// 8-byte vector stores of the split planes.
+template <int NV>  // float4 per lane
+__global__ void __launch_bounds__(256)
+layernorm_reg_kernel(const float* __restrict__ in, long long ld_in, const float* __restrict__ gamma,
+                     const float* __restrict__ beta, float eps, float* __restrict__ out_f32, long long ld_f32,
+                     __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo, long long ld_bf,
+                     long long rows) {
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  constexpr int cols = NV * 128;
+  const float4* s4 = reinterpret_cast<const float4*>(in + row * ld_in);
+  float4 v[NV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    v[i] = s4[lane + i * 32];
+    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+  const float mean = warp_sum(s) / (float)cols;
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+    ss += (a * a + b * b) + (c * c + d * d);
+  }
+  const float rstd = 1.0f / sqrtf(warp_sum(ss) / (float)cols + eps);
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  const float4* b4 = reinterpret_cast<const float4*>(beta);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c4 = lane + i * 32;
+    const float4 g = __ldg(g4 + c4), bb = __ldg(b4 + c4);
+    float4 y;
+    y.x = (v[i].x - mean) * rstd * g.x + bb.x;
+    y.y = (v[i].y - mean) * rstd * g.y + bb.y;
+    y.z = (v[i].z - mean) * rstd * g.z + bb.z;
+    y.w = (v[i].w - mean) * rstd * g.w + bb.w;
+    if (out_f32) *reinterpret_cast<float4*>(out_f32 + row * ld_f32 + c4 * 4) = y;
+    if (out_hi) {
+      uint2 h, l;
+      split_pack2(y.x, y.y, h.x, l.x);
+      split_pack2(y.z, y.w, h.y, l.y);
+      *reinterpret_cast<uint2*>(out_hi + row * ld_bf + c4 * 4) = h;
+      if (out_lo) *reinterpret_cast<uint2*>(out_lo + row * ld_bf + c4 * 4) = l;
+    }
+  }
+}
+
 }  // namespace mtt
 
 extern "C" int mtt_split_f32(const float* in, int64_t ld_in, void* out_hi, void* out_lo,
@@ -124,6 +175,27 @@ extern "C" int mtt_layernorm(const float* in, int64_t ld_in, const float* gamma,
                      (long long)rows, cols);
   const int wpb = 8;
   const long long blocks = (rows + wpb - 1) / wpb;
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  const bool fast = cols % 128 == 0 && cols <= 1024 && ld_in % 4 == 0 && al16(in) && al16(gamma) && al16(beta) &&
+                    (!out_f32 || (ld_f32 % 4 == 0 && al16(out_f32))) &&
+                    (!out_hi || (ld_bf % 4 == 0 && (reinterpret_cast<uintptr_t>(out_hi) & 7) == 0 &&
+                                 (!out_lo || (reinterpret_cast<uintptr_t>(out_lo) & 7) == 0)));
+  if (fast) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    __nv_bfloat16* oh = static_cast<__nv_bfloat16*>(out_hi);
+    __nv_bfloat16* ol = static_cast<__nv_bfloat16*>(out_lo);
+#define MTT_LN_CASE(NV)                                                                                  \
+  case NV:                                                                                               \
+    layernorm_reg_kernel<NV><<<(unsigned)blocks, wpb * 32, 0, st>>>(in, ld_in, gamma, beta, eps, out_f32, \
+                                                                   ld_f32, oh, ol, ld_bf, rows);         \
+    break;
+    switch (cols / 128) {
+      MTT_LN_CASE(1) MTT_LN_CASE(2) MTT_LN_CASE(3) MTT_LN_CASE(4) MTT_LN_CASE(5) MTT_LN_CASE(6) MTT_LN_CASE(7)
+      MTT_LN_CASE(8)
+    }
+#undef MTT_LN_CASE
+    return check_launch("mtt_layernorm");
+  }
   layernorm_kernel<<<(unsigned)blocks, wpb * 32, 0, static_cast<cudaStream_t>(stream)>>>(
       in, ld_in, gamma, beta, eps, out_f32, ld_f32, static_cast<__nv_bfloat16*>(out_hi),
       static_cast<__nv_bfloat16*>(out_lo), ld_bf, rows, cols);

@@ -23,6 +23,7 @@ class GemmDesc(C.Structure):
         ("out_f32", C.c_void_p), ("ldo_f32", C.c_int64),
         ("out_hi", C.c_void_p), ("out_lo", C.c_void_p), ("ldo_bf", C.c_int64),
         ("in_group", C.c_int32), ("out_group", C.c_int32), ("out_offset", C.c_int32),
+        ("a_group_rows", C.c_int32), ("a_group_stride", C.c_int64),
     ]
 
 

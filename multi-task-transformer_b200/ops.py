@@ -84,12 +84,14 @@ def layernorm(x, gamma, beta, eps, out_f32=None, out_split=None):
 
 
 def gemm(a, w, *, M=None, N=None, K=None, bias=None, act=ACT_NONE, residual=None, res_row_mod=0,
-         out_f32=None, out_split=None, out_col_offset=0, regroup=None, conv=None, a_row_offset=0):
+         out_f32=None, out_split=None, out_col_offset=0, regroup=None, conv=None, a_row_offset=0,
+         a_gather=None):
     """D = act(A @ W^T + bias) + residual on the tcgen05 GEMM.
 
     a: Split [M, K] (or NHWC activation [B*H*W, C] when ``conv=(B, H, W, ksize, dil)``);
     w: Split [N, K] (conv: [N, ksize*ksize*cin_pad]); outputs: fp32 tensor and/or Split.
-    regroup=(in_group, out_group, out_offset) scatters output rows."""
+    regroup=(in_group, out_group, out_offset) scatters output rows; a_gather=(group_rows, group_stride)
+    gathers A rows in groups (M must be given)."""
     nsplit = min(a.nsplit, w.nsplit)
     d = _L.GemmDesc()
     aoff = 2 * a_row_offset * a.ld
@@ -121,6 +123,8 @@ def gemm(a, w, *, M=None, N=None, K=None, bias=None, act=ACT_NONE, residual=None
             raise ValueError("nsplit=2 GEMM needs a 2-plane split output")
     if regroup is not None:
         d.in_group, d.out_group, d.out_offset = regroup
+    if a_gather is not None:    # (group_rows, group_stride): logical row (g, i) at physical row g*stride + i
+        d.a_group_rows, d.a_group_stride = a_gather
     rc = _L.load().mtt_gemm(C.byref(d), _stream())
     _L.check(rc, "mtt_gemm")
 

@@ -261,8 +261,8 @@ class _Plan:
             w.eps = blk.norm1.eps
             w.qkv, w.qkv_b = pack_linear_weight(f32(blk.attn.qkv.weight), ns), f32(blk.attn.qkv.bias)
             w.proj, w.proj_b = pack_linear_weight(f32(blk.attn.proj.weight), ns), f32(blk.attn.proj.bias)
-            w.tt, w.tt_b = f32(blk.attn.token_trans.weight), f32(blk.attn.token_trans.bias)
-            w.tt1, w.tt1_b = f32(blk.attn.token_trans1.weight), f32(blk.attn.token_trans1.bias)
+            w.tt, w.tt_b = pack_linear_weight(f32(blk.attn.token_trans.weight), ns), f32(blk.attn.token_trans.bias)
+            w.tt1, w.tt1_b = pack_linear_weight(f32(blk.attn.token_trans1.weight), ns), f32(blk.attn.token_trans1.bias)
             w.fc1, w.fc1_b = pack_linear_weight(f32(blk.mlp.fc1.weight), ns), f32(blk.mlp.fc1.bias)
             w.fc2, w.fc2_b = pack_linear_weight(f32(blk.mlp.fc2.weight), ns), f32(blk.mlp.fc2.bias)
             W.blocks.append(w)
@@ -316,6 +316,7 @@ class _Plan:
         self.hid = S(B * N, W.blocks[0].fc1.rows)
         self.logits = z(B, self.H, T, N)
         self.cp = z(B * T, P)
+        self.cps = S(B * T, P)
         self.rc = z(B, T, C, self.nh, self.nw)
         self.xfin = z(B * N, C)
         self.ys, self.yc = S(B * P, C), S(B * P, C)
@@ -342,18 +343,18 @@ class _Plan:
         ops.attention(self.qkv, self.ao, B=B, N=N, H=self.H, scale=64 ** -0.5,
                       prompt_logits=self.logits if want_logits else None, T=T)               # :204-210
         ops.gemm(self.ao, w.proj, bias=w.proj_b, residual=self.xs, out_f32=self.xs)          # :212,:273,:276
-        bstep = max(1, 32 // T)
-        for b0 in range(0, B, bstep):                                                        # prompt rows
+        bstep = max(1, 128 // T)      # images per launch: their T prompt rows form one gathered 128-row A tile
+        for b0 in range(0, B, bstep):
             nb = min(bstep, B - b0)
-            ops.skinny_linear(w.tt, w.tt_b, self.cp, R=nb * T, a_split=self.xn, a_map=(T, N, 0),
-                              a_row_base=b0 * N, o_row_base=b0 * T)                          # :219
+            ops.gemm(self.xn, w.tt, M=nb * T, bias=w.tt_b, a_gather=(T, N), a_row_offset=b0 * N,
+                     out_f32=self.cp, out_split=self.cps, regroup=(nb * T, nb * T, b0 * T))  # :219 token_trans
         if want_logits:
             ops.chan_logits(self.cp, self.xn, self.rc, B=B, N=N, T=T, Cdim=C, gh=self.gh, gw=self.gw,
                             nh=self.nh, nw=self.nw)                                          # :236-246
         for b0 in range(0, B, bstep):
             nb = min(bstep, B - b0)
-            ops.skinny_linear(w.tt1, w.tt1_b, self.xs, R=nb * T, a_f32=self.cp, a_row_base=b0 * T,
-                              o_map=(T, N, 0), o_row_base=b0 * N, accumulate=True)           # :250
+            ops.gemm(self.cps, w.tt1, M=nb * T, bias=w.tt1_b, a_row_offset=b0 * T, residual=self.xs,
+                     out_f32=self.xs, regroup=(T, N, b0 * N))                                # :250 token_trans1
         ops.layernorm(self.xs, w.n2w, w.n2b, w.eps, out_split=self.xn)                       # :274,:277
         ops.gemm(self.xn, w.fc1, bias=w.fc1_b, act=ops.ACT_GELU, out_split=self.hid)
         ops.gemm(self.hid, w.fc2, bias=w.fc2_b, residual=self.xs, out_f32=self.xs)

@@ -56,11 +56,15 @@ def install(mp):
             _wsplit(out_split, y)
 
     def gemm(a, w, *, M=None, N=None, K=None, bias=None, act=0, residual=None, res_row_mod=0, out_f32=None,
-             out_split=None, out_col_offset=0, regroup=None, conv=None, a_row_offset=0):
+             out_split=None, out_col_offset=0, regroup=None, conv=None, a_row_offset=0, a_gather=None):
         M = a.rows if M is None else M
         N = w.rows if N is None else N
         K = a.cols if K is None else K
-        A = _rsplit(a, K)[a_row_offset:a_row_offset + M]
+        if a_gather is not None:
+            r_ = torch.arange(M)
+            A = _rsplit(a, K)[a_row_offset + (r_ // a_gather[0]) * a_gather[1] + r_ % a_gather[0]]
+        else:
+            A = _rsplit(a, K)[a_row_offset:a_row_offset + M]
         if conv is None:
             Wm = _rsplit(w, K)[:N]
             y = A @ Wm.t()

@@ -181,3 +181,49 @@ def test_attention(cuda_dev, nsplit, B, H, N, T):
     if T:
         e = relerr(logits, raw[:, :, :T, :])
         assert e < (3e-5 if nsplit == 2 else 2e-2), f"prompt logits rel err {e}"
+
+
+def test_gemm_gathered_rows(cuda_dev):
+    """token_trans-style: the T prompt rows of each image gathered out of a [B*N, C] stream (3-D TMA map),
+    then token_trans1-style scatter-accumulate back into those rows."""
+    from mtt_b200 import ops
+
+    torch.manual_seed(3)
+    B, N, T, C, P = 4, 69, 5, 256, 64
+    x = torch.randn(B * N, C, device=cuda_dev)
+    w = torch.randn(P, C, device=cuda_dev) * 0.05
+    bias = torch.randn(P, device=cuda_dev)
+    X, Wp = ops.split_f32(x), ops.split_f32(w)
+    cp = torch.full((B * T, P), float("nan"), device=cuda_dev)
+    cps = ops.Split(B * T, P, cuda_dev, 2)
+    ops.gemm(X, Wp, M=B * T, bias=bias, a_gather=(T, N), out_f32=cp, out_split=cps, regroup=(B * T, B * T, 0))
+    torch.cuda.synchronize()
+    rows = (torch.arange(B)[:, None] * N + torch.arange(T)[None]).reshape(-1)
+    ref = x.double().cpu()[rows] @ w.double().cpu().t() + bias.double().cpu()
+    assert relerr(cp, ref) < TOL[2]
+    assert relerr(cps.float(), ref) < TOL[2] + 1e-5
+    w1 = torch.randn(C, P, device=cuda_dev) * 0.05
+    xs = x.clone()
+    ops.gemm(cps, ops.split_f32(w1), M=B * T, residual=xs, out_f32=xs, regroup=(T, N, 0))
+    torch.cuda.synchronize()
+    ref2 = x.double().cpu().clone()
+    ref2[rows] += ref @ w1.double().cpu().t()
+    assert relerr(xs, ref2) < TOL[2]
+
+
+@pytest.mark.parametrize("nh", [1, 2])
+def test_chan_logits(cuda_dev, nh):
+    from mtt_b200 import ops
+
+    torch.manual_seed(4)
+    B, T, C, gh, gw = 2, 3, 96, 8, 12
+    P, N = gh * gw, T + gh * gw
+    xn = torch.randn(B * N, C, device=cuda_dev)
+    cp = torch.randn(B * T, P, device=cuda_dev)
+    out = torch.empty(B, T, C, nh, nh, device=cuda_dev)
+    ops.chan_logits(cp, ops.split_f32(xn), out, B=B, N=N, T=T, Cdim=C, gh=gh, gw=gw, nh=nh, nw=nh)
+    torch.cuda.synchronize()
+    x = xn.double().cpu().reshape(B, N, C)[:, T:].reshape(B, nh, gh // nh, nh, gw // nh, C)
+    c = cp.double().cpu().reshape(B, T, nh, gh // nh, nh, gw // nh)
+    ref = torch.einsum("btihjw,bihjwc->btcij", c, x)
+    assert relerr(out, ref) < 2e-5
