@@ -92,35 +92,6 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def dist_setup(n_gpus):
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world > 1:
-        import torch.distributed as dist
-
-        torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    return rank, world, local
-
-
-def barrier(world):
-    if world > 1:
-        import torch.distributed as dist
-
-        dist.barrier()
-
-
-def max_over_ranks(x, world, dev):
-    if world == 1:
-        return x
-    import torch.distributed as dist
-
-    t = torch.tensor([x], dtype=torch.float64, device=dev)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    return float(t.item())
-
-
 # ------------------------------------------------------------------------------------------------
 def cpu_oracle_rate(cfg_name, steps, warmup, threads):
     """images/s of the reference algorithm's CPU port (oracle/taskprompter_ref.py, fp32, eval) on a
@@ -209,11 +180,14 @@ def gemm_roofline(model, plan, x_dev, peaks, peak_src):
 
 
 def run_ours(args):
-    rank, world, local = dist_setup(args.gpus)
+    import mtt_b200  # noqa: F401
+    from mtt_b200 import dist as D
+    from mtt_b200 import ops
+
+    rank, world, local = D.setup("nccl")
+    barrier, max_over_ranks = D.barrier, D.max_over_ranks
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
-    import mtt_b200  # noqa: F401
-    from mtt_b200 import ops
     from mtt_b200 import taskprompter as TP
     from oracle import configs
 
@@ -300,10 +274,7 @@ def run_ours(args):
     e2e_value = world * B * args.steps / (e2e_ms * 1e-3)
 
     if rank != 0:
-        if world > 1:
-            import torch.distributed as dist
-
-            dist.destroy_process_group()
+        D.teardown(world)
         return
 
     peaks, peak_src = load_peaks()
@@ -338,10 +309,7 @@ def run_ours(args):
         line["cpu_baseline"] = {"value": rate, "unit": "images/s", "cores": threads, "kind": "port",
                                 "sample": f"3 forwards of batch 1 of {args.config} (oracle/taskprompter_ref.py, fp32 eager)"}
     print(json.dumps(line), flush=True)
-    if world > 1:
-        import torch.distributed as dist
-
-        dist.destroy_process_group()
+    D.teardown(world)
 
 
 def main():

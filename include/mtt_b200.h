@@ -106,6 +106,10 @@ typedef struct {
 } mtt_gemm_desc;
 
 int mtt_gemm(const mtt_gemm_desc* d, mtt_stream_t stream);
+/* Kernel variant used by mtt_gemm: 0 = automatic (default; also env MTT_GEMM_VARIANT), 1 = single-CTA
+ * 128x128 tiles, 2 = CTA pair (tcgen05 cta_group::2) 256x256 tiles, 3 = CTA pair 256x128 tiles.
+ * All variants compute the same function; this is a tuning / testing knob. */
+void mtt_set_gemm_variant(int variant);
 
 /* ---- fused multi-head attention over the joint [prompts; patches] sequence ----------------
  * Replaces TP taskprompter.py:204-210 (raw = q k^T, softmax(raw*scale), attn @ v) and IP

@@ -1,0 +1,241 @@
+// CTA-pair (tcgen05 cta_group::2) variant of the GEMM / implicit-GEMM convolution in gemm_tc.cu.
+//
+// Two CTAs of one cluster (same TPC) share every MMA: the pair computes a 256 x BN2 output tile,
+// CTA r holds rows [128 r, 128 r + 128) of A and rows [BN2/2 r, ...) of the weight tile in its own
+// shared memory and owns the 128 x BN2 fp32 accumulator slice in its own TMEM.  Per MMA each SM
+// reads only 128 x 16 of A and BN2/2 x 16 of B from shared memory (half the B traffic of the 1-CTA
+// kernel), which is what lifts the shared-memory-bandwidth cap of the 128x128 single-CTA tile
+// (profiles/r1a_gemm_tc_metrics.csv: tensor pipe 60-67 % active).
+//
+// Protocol (leader = cluster rank 0):
+//   * both CTAs' producer threads TMA their halves into their own smem; all complete_tx land on the
+//     LEADER's full barrier (cta_group::2 loads), which the leader's producer arms with 2x the bytes;
+//   * the leader's MMA thread issues tcgen05.mma.cta_group::2 and commits with a cluster multicast so
+//     the smem-empty and accumulator-full barriers fire in BOTH CTAs;
+//   * each CTA's 8 epilogue warps drain their own TMEM slice and arrive on the LEADER's
+//     accumulator-empty barrier (16 arrivals).
+#include "gemm_common.cuh"
+
+namespace mtt {
+
+template <int NSPLIT>
+struct Gemm2Cfg {
+  static constexpr int kStages = (NSPLIT == 2) ? 3 : 6;
+  static constexpr uint32_t kStageBytes = NSPLIT * 2 * kTileBytes;  // A 128x64 + B (<=128)x64 per plane
+  static constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 + 256;
+};
+
+template <int NSPLIT, int BN2>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+                const GemmParams p) {
+  using Cfg = Gemm2Cfg<NSPLIT>;
+  constexpr int ST = Cfg::kStages;
+  constexpr int BNH = BN2 / 2;                       // weight rows held by each CTA
+  constexpr uint32_t kBTile = BNH * BK * 2;          // bytes of one B plane per CTA
+  constexpr int kTmemCols = 2 * BN2;                 // two accumulator buffers
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + ST * Cfg::kStageBytes);
+  uint64_t* empty_bar = full_bar + ST;
+  uint64_t* tfull_bar = empty_bar + ST;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair = blockIdx.x >> 1;
+  const int num_pairs = gridDim.x >> 1;
+  const int pairs_m = (p.tiles_m + 1) >> 1;
+  const int num_tiles = pairs_m * p.tiles_n;
+  const int k_iters = p.taps * p.num_kb;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA_hi);
+    tma_prefetch_desc(&tmB_hi);
+    if (NSPLIT == 2) {
+      tma_prefetch_desc(&tmA_lo);
+      tma_prefetch_desc(&tmB_lo);
+    }
+    for (int s = 0; s < ST; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 2 * kEpiWarps);
+    }
+    fence_barrier_init();
+  }
+  cluster_sync_all();  // barriers of both CTAs are initialised before any remote arrive / TMA signal
+  if (warp == 1) tmem_alloc_cg2<kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (both CTAs)
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t stage_tx = 2 * NSPLIT * (p.a_box_bytes + kBTile);  // both CTAs' bytes
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        const int ms = (tile % pairs_m) * 2 + (int)rank;
+        const int nt = tile / pairs_m;
+        for (int tap = 0; tap < p.taps; ++tap) {
+          const int dy = (tap / p.ksize - p.ksize / 2) * p.dil;
+          const int dx = (tap % p.ksize - p.ksize / 2) * p.dil;
+          for (int kb = 0; kb < p.num_kb; ++kb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sa = smem + stage * Cfg::kStageBytes;
+            uint8_t* sb = sa + NSPLIT * kTileBytes;
+            if (leader) mbar_arrive_expect_tx(&full_bar[stage], stage_tx);
+            load_a_tile<NSPLIT, true>(p, &tmA_hi, &tmA_lo, sa, &full_bar[stage], ms, kb, dy, dx);
+            const int kcoord = tap * p.cin_pad + kb * BK;
+            const int nrow = nt * BN2 + (int)rank * BNH;
+            tma_load_2d_cg2(sb, &tmB_hi, &full_bar[stage], kcoord, nrow);
+            if (NSPLIT == 2) tma_load_2d_cg2(sb + kBTile, &tmB_lo, &full_bar[stage], kcoord, nrow);
+            if (++stage == ST) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (leader only)
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(256, BN2, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        mbar_wait(&tempty_bar[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + as * BN2;
+        uint32_t accum = 0;
+        for (int ki = 0; ki < k_iters; ++ki) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_hi = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint32_t b_hi = a_hi + NSPLIT * kTileBytes;
+#pragma unroll
+          for (int ks = 0; ks < BK / 16; ++ks) {
+            const uint64_t adh = umma_desc_sw128(a_hi + ks * 32);
+            const uint64_t bdh = umma_desc_sw128(b_hi + ks * 32);
+            umma_ss_cg2(tacc, adh, bdh, idesc, accum);
+            accum = 1;
+            if (NSPLIT == 2) {
+              const uint64_t adl = umma_desc_sw128(a_hi + kTileBytes + ks * 32);
+              const uint64_t bdl = umma_desc_sw128(b_hi + kBTile + ks * 32);
+              umma_ss_cg2(tacc, adh, bdl, idesc, 1);
+              umma_ss_cg2(tacc, adl, bdh, idesc, 1);
+            }
+          }
+          umma_commit_cg2(&empty_bar[stage]);  // frees the smem slot in both CTAs
+          if (++stage == ST) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit_cg2(&tfull_bar[as]);  // accumulator complete, both CTAs
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue warps (both CTAs)
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int row = q * 32 + lane;
+    constexpr int kColsPerWarp = BN2 / 2;  // 128 or 64 columns per epilogue warp
+    int it = 0;
+    for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      const int ms = (tile % pairs_m) * 2 + (int)rank;
+      const int nt = tile / pairs_m;
+      const RowInfo ri = row_info(p, ms, row);
+      mbar_wait(&tfull_bar[as], aphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN2 + half * kColsPerWarp;
+      const int nbase = nt * BN2 + half * kColsPerWarp;
+      if (kColsPerWarp == 64) {
+        uint32_t r0[32], r1[32];
+        tmem_ld32(taddr, r0);
+        tmem_ld32(taddr + 32, r1);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_leader(&tempty_bar[as]);
+        if (ri.ok) {
+          epilogue_store32(p, r0, nbase, ri);
+          epilogue_store32(p, r1, nbase + 32, ri);
+        }
+      } else {
+        uint32_t r0[32], r1[32], r2[32], r3[32];
+        tmem_ld32(taddr, r0);
+        tmem_ld32(taddr + 32, r1);
+        tmem_ld32(taddr + 64, r2);
+        tmem_ld32(taddr + 96, r3);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_leader(&tempty_bar[as]);
+        if (ri.ok) {
+          epilogue_store32(p, r0, nbase, ri);
+          epilogue_store32(p, r1, nbase + 32, ri);
+          epilogue_store32(p, r2, nbase + 64, ri);
+          epilogue_store32(p, r3, nbase + 96, ri);
+        }
+      }
+      __syncwarp();
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();  // nobody leaves (or frees TMEM) while the peer may still touch this CTA
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_cg2<kTmemCols>(tmem_base);
+  }
+}
+
+template <int NSPLIT, int BN2>
+static int launch_gemm2(const CUtensorMap* maps, const GemmParams& p, cudaStream_t stream) {
+  using Cfg = Gemm2Cfg<NSPLIT>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm2_tc_kernel<NSPLIT, BN2>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (e != cudaSuccess)
+      return set_error(MTT_ERR_LAUNCH, "gemm2: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const int pairs_m = (p.tiles_m + 1) / 2;
+  const int tiles = pairs_m * p.tiles_n;
+  const int max_pairs = sm_count() / 2;
+  const int pairs = tiles < max_pairs ? tiles : max_pairs;
+  gemm2_tc_kernel<NSPLIT, BN2><<<pairs * 2, kGemmThreads, Cfg::kSmemBytes, stream>>>(maps[0], maps[1], maps[2],
+                                                                                    maps[3], p);
+  return check_launch("mtt_gemm(cta pair)");
+}
+
+int launch_gemm_2cta(const mtt_gemm_desc* d, int bn2, cudaStream_t stream) {
+  GemmParams p;
+  CUtensorMap maps[4];
+  int rc = gemm_prepare(d, bn2 / 2, p, maps);
+  if (rc) return rc;
+  p.tiles_n = (d->N + bn2 - 1) / bn2;
+  if (bn2 == 256)
+    return d->nsplit == 2 ? launch_gemm2<2, 256>(maps, p, stream) : launch_gemm2<1, 256>(maps, p, stream);
+  return d->nsplit == 2 ? launch_gemm2<2, 128>(maps, p, stream) : launch_gemm2<1, 128>(maps, p, stream);
+}
+
+}  // namespace mtt

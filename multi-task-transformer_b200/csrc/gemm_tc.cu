@@ -16,38 +16,12 @@
 // Convolution (mode 1) is the same kernel: the A tile of 128 output pixels is a TH x TW patch of one
 // NHWC image and each filter tap is a shifted rank-4 TMA box; TMA's out-of-bounds zero fill is the
 // zero padding.  The K loop runs over taps x channel blocks.
-#include "host_common.h"
-#include "ptx.cuh"
+#include "gemm_common.cuh"
 
 namespace mtt {
 
-constexpr int BM = 128, BN = 128, BK = 64;
-constexpr int kEpiWarps = 8;
-constexpr int kGemmThreads = 64 + kEpiWarps * 32;
-constexpr uint32_t kTileBytes = BM * BK * 2;  // one bf16 operand tile: 16 KB
+constexpr int BN = 128;
 constexpr int kTmemCols = 2 * BN;
-
-struct GemmParams {
-  int M, N;
-  int num_kb, taps, ksize, dil, mode;
-  int H, W, TW, TH, tiles_x, tiles_y;
-  int tiles_m, tiles_n;
-  int cin_pad;
-  uint32_t a_box_bytes;
-  const float* bias;
-  int act;
-  const float* residual;
-  long long ldr;
-  int res_row_mod;
-  float* out_f32;
-  long long ldo_f32;
-  __nv_bfloat16* out_hi;
-  __nv_bfloat16* out_lo;
-  long long ldo_bf;
-  int in_group, out_group, out_offset;
-  int vec_ok;
-  int a_groups_per_tile;  // >0: A rows are gathered in groups through a rank-3 tensor map
-};
 
 template <int NSPLIT>
 struct GemmCfg {
@@ -109,14 +83,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int mt = tile % p.tiles_m;
         const int nt = tile / p.tiles_m;
-        int cb = 0, cy0 = 0, cx0 = 0;
-        if (p.mode == 1) {
-          const int per_img = p.tiles_x * p.tiles_y;
-          cb = mt / per_img;
-          const int r = mt - cb * per_img;
-          cy0 = (r / p.tiles_x) * p.TH;
-          cx0 = (r % p.tiles_x) * p.TW;
-        }
         for (int tap = 0; tap < p.taps; ++tap) {
           const int dy = (tap / p.ksize - p.ksize / 2) * p.dil;
           const int dx = (tap % p.ksize - p.ksize / 2) * p.dil;
@@ -125,18 +91,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             uint8_t* sa = smem + stage * Cfg::kStageBytes;
             uint8_t* sb = sa + NSPLIT * kTileBytes;
             mbar_arrive_expect_tx(&full_bar[stage], stage_tx);
-            if (p.mode == 0 && p.a_groups_per_tile > 0) {
-              tma_load_3d(sa, &tmA_hi, &full_bar[stage], kb * BK, 0, mt * p.a_groups_per_tile);
-              if (NSPLIT == 2)
-                tma_load_3d(sa + kTileBytes, &tmA_lo, &full_bar[stage], kb * BK, 0, mt * p.a_groups_per_tile);
-            } else if (p.mode == 0) {
-              tma_load_2d(sa, &tmA_hi, &full_bar[stage], kb * BK, mt * BM);
-              if (NSPLIT == 2) tma_load_2d(sa + kTileBytes, &tmA_lo, &full_bar[stage], kb * BK, mt * BM);
-            } else {
-              tma_load_4d(sa, &tmA_hi, &full_bar[stage], kb * BK, cx0 + dx, cy0 + dy, cb);
-              if (NSPLIT == 2)
-                tma_load_4d(sa + kTileBytes, &tmA_lo, &full_bar[stage], kb * BK, cx0 + dx, cy0 + dy, cb);
-            }
+            load_a_tile<NSPLIT, false>(p, &tmA_hi, &tmA_lo, sa, &full_bar[stage], mt, kb, dy, dx);
             const int kcoord = tap * p.cin_pad + kb * BK;
             tma_load_2d(sb, &tmB_hi, &full_bar[stage], kcoord, nt * BN);
             if (NSPLIT == 2) tma_load_2d(sb + kTileBytes, &tmB_lo, &full_bar[stage], kcoord, nt * BN);
@@ -200,24 +155,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       const uint32_t aphase = (it >> 1) & 1;
       const int mt = tile % p.tiles_m;
       const int nt = tile / p.tiles_m;
-      // ---- where does this thread's row go?
-      long long m;  // logical output row (before regrouping)
-      bool row_ok;
-      if (p.mode == 0) {
-        m = (long long)mt * BM + row;
-        row_ok = m < p.M;
-      } else {
-        const int per_img = p.tiles_x * p.tiles_y;
-        const int cb = mt / per_img;
-        const int r = mt - cb * per_img;
-        const int y = (r / p.tiles_x) * p.TH + row / p.TW;
-        const int x = (r % p.tiles_x) * p.TW + row % p.TW;
-        row_ok = (row < p.TW * p.TH) && (y < p.H) && (x < p.W);
-        m = ((long long)cb * p.H + y) * p.W + x;
-      }
-      long long mo = m;
-      if (p.in_group > 0) mo = (m / p.in_group) * p.out_group + p.out_offset + (m % p.in_group);
-      const long long mr = (p.res_row_mod > 0) ? (m % p.res_row_mod) : mo;
+      const RowInfo ri = row_info(p, mt, row);
 
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
@@ -230,73 +168,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[as]);  // accumulator buffer may be overwritten
 
-      if (row_ok) {
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          const uint32_t* rr = c ? r1 : r0;
-          const int n0 = nt * BN + half * 64 + c * 32;
-          if (n0 >= p.N) break;
-#pragma unroll
-          for (int j8 = 0; j8 < 32; j8 += 8) {
-            const int n = n0 + j8;
-            if (n >= p.N) break;
-            float v[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(rr[j8 + j]);
-            if (p.vec_ok && n + 8 <= p.N) {
-              if (p.bias) {
-                const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-                const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 4));
-                v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-                v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-              }
-              if (p.act == MTT_ACT_GELU) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = gelu_erf(v[j]);
-              } else if (p.act == MTT_ACT_RELU) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
-              }
-              if (p.residual) {
-                const float4* rp = reinterpret_cast<const float4*>(p.residual + mr * p.ldr + n);
-                const float4 a0 = rp[0], a1 = rp[1];
-                v[0] += a0.x; v[1] += a0.y; v[2] += a0.z; v[3] += a0.w;
-                v[4] += a1.x; v[5] += a1.y; v[6] += a1.z; v[7] += a1.w;
-              }
-              if (p.out_f32) {
-                float4* op = reinterpret_cast<float4*>(p.out_f32 + mo * p.ldo_f32 + n);
-                op[0] = make_float4(v[0], v[1], v[2], v[3]);
-                op[1] = make_float4(v[4], v[5], v[6], v[7]);
-              }
-              if (p.out_hi) {
-                uint4 h, l;
-                split_pack2(v[0], v[1], h.x, l.x);
-                split_pack2(v[2], v[3], h.y, l.y);
-                split_pack2(v[4], v[5], h.z, l.z);
-                split_pack2(v[6], v[7], h.w, l.w);
-                *reinterpret_cast<uint4*>(p.out_hi + mo * p.ldo_bf + n) = h;
-                if (p.out_lo) *reinterpret_cast<uint4*>(p.out_lo + mo * p.ldo_bf + n) = l;
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                if (n + j >= p.N) break;
-                float x = v[j];
-                if (p.bias) x += __ldg(p.bias + n + j);
-                if (p.act == MTT_ACT_GELU) x = gelu_erf(x);
-                else if (p.act == MTT_ACT_RELU) x = fmaxf(x, 0.f);
-                if (p.residual) x += p.residual[mr * p.ldr + n + j];
-                if (p.out_f32) p.out_f32[mo * p.ldo_f32 + n + j] = x;
-                if (p.out_hi) {
-                  __nv_bfloat16 h, l;
-                  split_bf16(x, h, l);
-                  p.out_hi[mo * p.ldo_bf + n + j] = h;
-                  if (p.out_lo) p.out_lo[mo * p.ldo_bf + n + j] = l;
-                }
-              }
-            }
-          }
-        }
+      if (ri.ok) {
+        const int n0 = nt * BN + half * 64;
+        epilogue_store32(p, r0, n0, ri);
+        epilogue_store32(p, r1, n0 + 32, ri);
       }
       __syncwarp();
     }
@@ -308,26 +183,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     tc_fence_after();
     tmem_dealloc<kTmemCols>(tmem_base);
   }
-}
-
-// Pick the TH x TW (<= 128 pixel) output patch that wastes the fewest MMA rows.
-static void pick_conv_tile(int H, int W, int* TW, int* TH) {
-  double best = -1;
-  int btw = 1, bth = 1;
-  for (int tw = 1; tw <= 128 && tw <= W; ++tw) {
-    int th = 128 / tw;
-    if (th > H) th = H;
-    if (th < 1) continue;
-    const long long tiles = (long long)((W + tw - 1) / tw) * ((H + th - 1) / th);
-    const double eff = (double)H * W / ((double)tiles * 128.0);
-    if (eff > best + 1e-9 || (eff > best - 1e-9 && tw > btw)) {
-      best = eff;
-      btw = tw;
-      bth = th;
-    }
-  }
-  *TW = btw;
-  *TH = bth;
 }
 
 template <int NSPLIT>
@@ -348,143 +203,14 @@ static int launch_gemm(const CUtensorMap* maps, const GemmParams& p, cudaStream_
   return check_launch("mtt_gemm");
 }
 
-}  // namespace mtt
 
-extern "C" int mtt_gemm(const mtt_gemm_desc* d, mtt_stream_t stream_) {
-  using namespace mtt;
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  if (!d) return set_error(MTT_ERR_BAD_SHAPE, "mtt_gemm: null descriptor");
-  if (d->M <= 0 || d->N <= 0 || d->K <= 0)
-    return set_error(MTT_ERR_BAD_SHAPE, "mtt_gemm: M=%d N=%d K=%d must be positive", d->M, d->N, d->K);
-  if (d->nsplit != 1 && d->nsplit != 2)
-    return set_error(MTT_ERR_BAD_SHAPE, "mtt_gemm: nsplit=%d (1 or 2)", d->nsplit);
-  if (!d->a_hi || !d->b_hi || (d->nsplit == 2 && (!d->a_lo || !d->b_lo)))
-    return set_error(MTT_ERR_BAD_SHAPE, "mtt_gemm: missing operand plane");
-  if (!d->out_f32 && !d->out_hi) return set_error(MTT_ERR_BAD_SHAPE, "mtt_gemm: no output");
-  if (d->lda % 8 || d->ldb % 8)
-    return set_error(MTT_ERR_MISALIGNED, "mtt_gemm: lda=%lld ldb=%lld must be multiples of 8",
-                     (long long)d->lda, (long long)d->ldb);
-
-  GemmParams p{};
-  p.M = d->M;
-  p.N = d->N;
-  p.mode = d->mode;
-  p.num_kb = (d->K + BK - 1) / BK;
-  p.tiles_n = (d->N + BN - 1) / BN;
-  p.bias = d->bias;
-  p.act = d->act;
-  p.residual = d->residual;
-  p.ldr = d->ldr;
-  p.res_row_mod = d->res_row_mod;
-  p.out_f32 = d->out_f32;
-  p.ldo_f32 = d->ldo_f32;
-  p.out_hi = static_cast<__nv_bfloat16*>(d->out_hi);
-  p.out_lo = d->nsplit == 2 ? static_cast<__nv_bfloat16*>(d->out_lo) : nullptr;
-  p.ldo_bf = d->ldo_bf;
-  p.in_group = d->in_group;
-  p.out_group = d->out_group;
-  p.out_offset = d->out_offset;
-  if (p.out_hi && d->nsplit == 2 && !p.out_lo)
-    return set_error(MTT_ERR_BAD_SHAPE, "mtt_gemm: out_lo missing for nsplit=2");
-
-  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
-  p.vec_ok = 1;
-  if (d->bias && !al16(d->bias)) p.vec_ok = 0;
-  if (d->residual && (!al16(d->residual) || d->ldr % 4)) p.vec_ok = 0;
-  if (d->out_f32 && (!al16(d->out_f32) || d->ldo_f32 % 4)) p.vec_ok = 0;
-  if (d->out_hi && (!al16(d->out_hi) || d->ldo_bf % 8 || (p.out_lo && !al16(p.out_lo)))) p.vec_ok = 0;
-
+int launch_gemm_1cta(const mtt_gemm_desc* d, cudaStream_t stream) {
+  GemmParams p;
   CUtensorMap maps[4];
-  int rc;
-  const int ksq = (d->mode == 1) ? d->ksize * d->ksize : 1;
-  if (d->mode == 0 && d->a_group_rows > 0) {
-    // gathered A: logical row r = (g, i) lives at physical row g * a_group_stride + i, i < a_group_rows
-    const int g = d->a_group_rows;
-    if (g > BM || d->M % g || d->a_group_stride < g)
-      return set_error(MTT_ERR_BAD_SHAPE, "mtt_gemm: a_group_rows=%d must divide M=%d and be <= %d", g, d->M, BM);
-    const int ngroups = d->M / g;
-    const int gpt = BM / g;  // groups per tile
-    if (ngroups > gpt && BM % g)
-      return set_error(MTT_ERR_BAD_SHAPE, "mtt_gemm: %d groups of %d rows need %d %% %d == 0", ngroups, g, BM, g);
-    p.taps = 1;
-    p.ksize = 1;
-    p.dil = 1;
-    p.cin_pad = 0;
-    p.a_groups_per_tile = ngroups < gpt ? ngroups : gpt;
-    p.tiles_m = (ngroups + p.a_groups_per_tile - 1) / p.a_groups_per_tile;
-    if (p.tiles_m > 1 && p.a_groups_per_tile * g != BM)
-      return set_error(MTT_ERR_BAD_SHAPE, "mtt_gemm: gathered A tiles must be full");
-    p.a_box_bytes = (uint32_t)(p.a_groups_per_tile * g) * BK * 2;
-    const uint64_t dims[3] = {(uint64_t)d->K, (uint64_t)g, (uint64_t)ngroups};
-    const uint64_t str[2] = {(uint64_t)d->lda * 2, (uint64_t)d->a_group_stride * d->lda * 2};
-    const uint32_t box[3] = {BK, (uint32_t)g, (uint32_t)p.a_groups_per_tile};
-    if ((rc = make_tmap_bf16(&maps[0], d->a_hi, 3, dims, str, box))) return rc;
-    if (d->nsplit == 2) {
-      if ((rc = make_tmap_bf16(&maps[1], d->a_lo, 3, dims, str, box))) return rc;
-    } else {
-      maps[1] = maps[0];
-    }
-  } else if (d->mode == 0) {
-    p.taps = 1;
-    p.ksize = 1;
-    p.dil = 1;
-    p.cin_pad = 0;
-    p.tiles_m = (d->M + BM - 1) / BM;
-    p.a_box_bytes = kTileBytes;
-    const uint64_t dims[2] = {(uint64_t)d->K, (uint64_t)d->M};
-    const uint64_t str[1] = {(uint64_t)d->lda * 2};
-    const uint32_t box[2] = {BK, BM};
-    if ((rc = make_tmap_bf16(&maps[0], d->a_hi, 2, dims, str, box))) return rc;
-    if (d->nsplit == 2) {
-      if ((rc = make_tmap_bf16(&maps[1], d->a_lo, 2, dims, str, box))) return rc;
-    } else {
-      maps[1] = maps[0];
-    }
-  } else if (d->mode == 1) {
-    if (d->B <= 0 || d->H <= 0 || d->W <= 0 || (long long)d->B * d->H * d->W != d->M)
-      return set_error(MTT_ERR_BAD_SHAPE, "mtt_gemm(conv): B*H*W = %d*%d*%d != M = %d", d->B, d->H,
-                       d->W, d->M);
-    if (d->ksize != 1 && d->ksize != 3)
-      return set_error(MTT_ERR_BAD_SHAPE, "mtt_gemm(conv): ksize=%d (1 or 3)", d->ksize);
-    if (d->dil < 1) return set_error(MTT_ERR_BAD_SHAPE, "mtt_gemm(conv): dil=%d", d->dil);
-    p.taps = ksq;
-    p.ksize = d->ksize;
-    p.dil = d->dil;
-    p.cin_pad = p.num_kb * BK;
-    p.H = d->H;
-    p.W = d->W;
-    pick_conv_tile(d->H, d->W, &p.TW, &p.TH);
-    p.tiles_x = (d->W + p.TW - 1) / p.TW;
-    p.tiles_y = (d->H + p.TH - 1) / p.TH;
-    p.tiles_m = d->B * p.tiles_x * p.tiles_y;
-    p.a_box_bytes = (uint32_t)(p.TW * p.TH) * BK * 2;
-    const uint64_t dims[4] = {(uint64_t)d->K, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->B};
-    const uint64_t str[3] = {(uint64_t)d->lda * 2, (uint64_t)d->W * d->lda * 2,
-                             (uint64_t)d->H * d->W * d->lda * 2};
-    const uint32_t box[4] = {BK, (uint32_t)p.TW, (uint32_t)p.TH, 1};
-    if ((rc = make_tmap_bf16(&maps[0], d->a_hi, 4, dims, str, box))) return rc;
-    if (d->nsplit == 2) {
-      if ((rc = make_tmap_bf16(&maps[1], d->a_lo, 4, dims, str, box))) return rc;
-    } else {
-      maps[1] = maps[0];
-    }
-  } else {
-    return set_error(MTT_ERR_BAD_SHAPE, "mtt_gemm: mode=%d", d->mode);
-  }
-  {
-    const uint64_t ktot = (d->mode == 1) ? (uint64_t)ksq * p.cin_pad : (uint64_t)d->K;
-    if ((uint64_t)d->ldb < ktot)
-      return set_error(MTT_ERR_BAD_SHAPE, "mtt_gemm: ldb=%lld < packed K=%llu", (long long)d->ldb,
-                       (unsigned long long)ktot);
-    const uint64_t dims[2] = {ktot, (uint64_t)d->N};
-    const uint64_t str[1] = {(uint64_t)d->ldb * 2};
-    const uint32_t box[2] = {BK, BN};
-    if ((rc = make_tmap_bf16(&maps[2], d->b_hi, 2, dims, str, box))) return rc;
-    if (d->nsplit == 2) {
-      if ((rc = make_tmap_bf16(&maps[3], d->b_lo, 2, dims, str, box))) return rc;
-    } else {
-      maps[3] = maps[2];
-    }
-  }
+  int rc = gemm_prepare(d, BN, p, maps);
+  if (rc) return rc;
+  p.tiles_n = (d->N + BN - 1) / BN;
   return d->nsplit == 2 ? launch_gemm<2>(maps, p, stream) : launch_gemm<1>(maps, p, stream);
 }
+
+}  // namespace mtt

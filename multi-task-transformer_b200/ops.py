@@ -146,6 +146,11 @@ def attention(qkv, out, *, B, N, H, scale, prompt_logits=None, T=0):
     _L.check(rc, "mtt_attention")
 
 
+def set_gemm_variant(v):
+    """0 auto, 1 single-CTA 128x128, 2 CTA-pair 256x256, 3 CTA-pair 256x128 (tuning / testing knob)."""
+    _L.load().mtt_set_gemm_variant(int(v))
+
+
 def launch_count(reset=False):
     lib = _L.load()
     n = lib.mtt_launch_count()

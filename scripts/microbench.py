@@ -51,6 +51,18 @@ def bench_attn(B, H, N, nsplit, T=5):
 
 if __name__ == "__main__":
     M = 4 * 1029
+    if len(sys.argv) > 1 and sys.argv[1] == "variants":
+        for v in (1, 2, 3):
+            ops.set_gemm_variant(v)
+            print("---- gemm variant", v)
+            for ns in (2, 1):
+                bench_gemm(M, 3072, 1024, ns)
+                bench_gemm(M, 1024, 1024, ns, res=True)
+                bench_gemm(M, 4096, 1024, ns, act=ops.ACT_GELU)
+                bench_gemm(M, 1024, 4096, ns, res=True)
+                bench_gemm(4096, 304, 1024, ns)
+                bench_gemm(4096, 352, 608, ns)
+        sys.exit(0)
     for ns in (2, 1):
         bench_gemm(M, 3072, 1024, ns)
         bench_gemm(M, 1024, 1024, ns, res=True)

@@ -19,6 +19,15 @@ def relerr(got, ref):
     return ((got.double().cpu() - ref.cpu()).abs().max() / ref.abs().max().clamp_min(1e-30)).item()
 
 
+@pytest.fixture(params=[0, 1, 2, 3], ids=["auto", "cta1_128x128", "pair_256x256", "pair_256x128"])
+def gemm_variant(request, cuda_dev):
+    from mtt_b200 import ops
+
+    ops.set_gemm_variant(request.param)
+    yield request.param
+    ops.set_gemm_variant(0)
+
+
 def test_split_exact(cuda_dev):
     from mtt_b200 import ops
 
@@ -103,7 +112,7 @@ def _gemm_case(dev, M, N, K, nsplit, bias, act, residual, regroup=None, res_row_
 
 
 @pytest.mark.parametrize("nsplit", [2, 1])
-def test_gemm_small_tails(cuda_dev, nsplit):
+def test_gemm_small_tails(cuda_dev, nsplit, gemm_variant):
     from mtt_b200 import ops
 
     _gemm_case(cuda_dev, 300, 200, 136, nsplit, True, ops.ACT_NONE, False)
@@ -113,7 +122,7 @@ def test_gemm_small_tails(cuda_dev, nsplit):
 
 
 @pytest.mark.parametrize("nsplit", [2, 1])
-def test_gemm_block_shapes(cuda_dev, nsplit):
+def test_gemm_block_shapes(cuda_dev, nsplit, gemm_variant):
     from mtt_b200 import ops
 
     # qkv-like (many tiles, persistent loop wraps the pipeline several times)
@@ -124,7 +133,7 @@ def test_gemm_block_shapes(cuda_dev, nsplit):
     _gemm_case(cuda_dev, 1029, 1024, 4096, nsplit, True, ops.ACT_NONE, True)
 
 
-def test_gemm_regroup_and_rowmod(cuda_dev):
+def test_gemm_regroup_and_rowmod(cuda_dev, gemm_variant):
     from mtt_b200 import ops
 
     # patch-embed style: rows of each image scattered behind T=5 prompt rows; pos-embed broadcast
@@ -134,7 +143,7 @@ def test_gemm_regroup_and_rowmod(cuda_dev):
 
 @pytest.mark.parametrize("ksize,dil", [(3, 1), (3, 2), (1, 1)])
 @pytest.mark.parametrize("nsplit", [2, 1])
-def test_conv(cuda_dev, ksize, dil, nsplit):
+def test_conv(cuda_dev, ksize, dil, nsplit, gemm_variant):
     from mtt_b200 import ops
     from mtt_b200.pack import pack_conv_weight
 
@@ -183,7 +192,7 @@ def test_attention(cuda_dev, nsplit, B, H, N, T):
         assert e < (3e-5 if nsplit == 2 else 2e-2), f"prompt logits rel err {e}"
 
 
-def test_gemm_gathered_rows(cuda_dev):
+def test_gemm_gathered_rows(cuda_dev, gemm_variant):
     """token_trans-style: the T prompt rows of each image gathered out of a [B*N, C] stream (3-D TMA map),
     then token_trans1-style scatter-accumulate back into those rows."""
     from mtt_b200 import ops
