@@ -10,7 +10,8 @@
 //   S = Q K^T          tcgen05.mma SS, fp32 accumulator in TMEM (128 columns)
 //   P = exp2(S*c - m)  registers; written back IN PLACE over S as packed bf16 hi/lo planes
 //   O_blk = P V        tcgen05.mma with A = P from TMEM, B = V from smem (MN-major), TMEM 64 columns
-//   O = O*alpha + O_blk  in registers (one query row per thread), online softmax
+//   O = O*alpha + O_blk  in registers, online softmax; 256 threads = two per query row, each owning
+//   half of the key columns of S/P and half of the output columns of O (row max / sum exchanged in smem)
 // Split-bf16 operands (NSPLIT = 2): every product is 3 MMAs, as in gemm_tc.cu.
 // The CTA is deliberately simple (no warp specialisation): 96 KB smem and 256 TMEM columns let two
 // CTAs share an SM, so one CTA's softmax overlaps the other's MMAs.
@@ -21,7 +22,7 @@
 
 namespace mtt {
 
-constexpr int kAttnThreads = 128;
+constexpr int kAttnThreads = 256;  // two threads per query row: each owns half of the key columns
 constexpr int kAttnTmemCols = 256;
 constexpr uint32_t kAttnTile = 128 * 64 * 2;  // 16 KB: 128 rows x 64 bf16
 
@@ -32,6 +33,35 @@ struct AttnParams {
   __nv_bfloat16* out_lo;
   float* prompt_logits;
 };
+
+// row maximum of one 32-column chunk (FULL: every column is a valid key)
+template <bool FULL>
+__device__ __forceinline__ float chunk_max(const uint32_t (&r)[32], int col0, int kn, float mx) {
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const float s = __uint_as_float(r[i]);
+    if (FULL || col0 + i < kn) mx = fmaxf(mx, s);
+  }
+  return mx;
+}
+// P = exp2(S*c - m*c) for one chunk, packed as bf16 hi / lo pairs; returns the chunk's row sum
+template <bool FULL>
+__device__ __forceinline__ float chunk_exp_pack(const uint32_t (&r)[32], int col0, int kn, float sl2, float mb,
+                                                uint32_t (&ph)[16], uint32_t (&pl)[16]) {
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 32; i += 2) {
+    float p0 = exp2f(fmaf(__uint_as_float(r[i]), sl2, -mb));
+    float p1 = exp2f(fmaf(__uint_as_float(r[i + 1]), sl2, -mb));
+    if (!FULL) {
+      if (col0 + i >= kn) p0 = 0.f;
+      if (col0 + i + 1 >= kn) p1 = 0.f;
+    }
+    sum += p0 + p1;
+    split_pack2(p0, p1, ph[i >> 1], pl[i >> 1]);
+  }
+  return sum;
+}
 
 template <int NSPLIT>
 __global__ void __launch_bounds__(kAttnThreads, 2)
@@ -50,9 +80,12 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
   uint64_t* bar_s = bars + 3;
   uint64_t* bar_o = bars + 4;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+  float* xch = reinterpret_cast<float*>(bars + 6);  // [2][128] row max / row sum exchange between halves
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
+  const int half = warp >> 2;              // which 64 key columns / 32 output columns this thread owns
+  const int row = (warp & 3) * 32 + (tid & 31);
   const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int C = p.H * 64;
   const int q0 = qt * 128;
@@ -76,7 +109,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tS = tmem_base;        // S / P: columns [0, 128)
   const uint32_t tO = tmem_base + 128;  // O_blk:  columns [128, 192)
-  const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+  const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
 
   if (tid == 0) {
     mbar_arrive_expect_tx(bar_q, NSPLIT * kAttnTile);
@@ -91,11 +124,11 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
   }
   __syncwarp();
 
-  float o_acc[64];
+  float o_acc[32];
 #pragma unroll
-  for (int i = 0; i < 64; ++i) o_acc[i] = 0.f;
+  for (int i = 0; i < 32; ++i) o_acc[i] = 0.f;
   float m_run = -INFINITY, l_run = 0.f;
-  const int q_row = q0 + tid;
+  const int q_row = q0 + row;
   const bool export_row = (p.prompt_logits != nullptr) && (q_row < p.T);
   float* export_ptr =
       export_row ? p.prompt_logits + (((long long)b * p.H + h) * p.T + q_row) * p.N : nullptr;
@@ -134,24 +167,28 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
     }
     __syncwarp();
 
-    // ---- pass 1: row maximum over the valid columns (and prompt-row logit export)
+    // ---- pass 1: row maximum over this thread's half of the valid columns (+ prompt-row export)
     const int nchunk = (kn16 + 31) >> 5;
+    const bool full = kn == 128;
     float mx = -INFINITY;
-    for (int c = 0; c < nchunk; ++c) {
-      uint32_t r[32];
-      tmem_ld32(tS + lane_addr + c * 32, r);
-      tmem_ld_wait();
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const float s = __uint_as_float(r[i]);
-        if (c * 32 + i < kn) mx = fmaxf(mx, s);
-      }
-      if (export_row) {
+    for (int cc = 0; cc < 2; ++cc) {
+      const int c = half * 2 + cc;
+      if (c < nchunk) {
+        uint32_t r[32];
+        tmem_ld32(tS + lane_addr + c * 32, r);
+        tmem_ld_wait();
+        mx = full ? chunk_max<true>(r, c * 32, kn, mx) : chunk_max<false>(r, c * 32, kn, mx);
+        if (export_row) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (c * 32 + i < kn) export_ptr[j * 128 + c * 32 + i] = __uint_as_float(r[i]);
+          for (int i = 0; i < 32; ++i)
+            if (c * 32 + i < kn) export_ptr[j * 128 + c * 32 + i] = __uint_as_float(r[i]);
+        }
       }
     }
+    xch[half * 128 + row] = mx;
+    __syncthreads();
+    mx = fmaxf(xch[row], xch[128 + row]);
     const float m_new = fmaxf(m_run, mx);
     const float alpha = exp2f((m_run - m_new) * p.scale_log2);
     const float mb = m_new * p.scale_log2;
@@ -159,22 +196,19 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
 
     // ---- pass 2: P = exp2(S*c - m*c), written in place as packed bf16 hi | lo (16 + 16 columns)
     float l_blk = 0.f;
-    for (int c = 0; c < nchunk; ++c) {
-      uint32_t r[32];
-      tmem_ld32(tS + lane_addr + c * 32, r);
-      tmem_ld_wait();
-      uint32_t ph_[16], pl_[16];
 #pragma unroll
-      for (int i = 0; i < 32; i += 2) {
-        float p0 = exp2f(__uint_as_float(r[i]) * p.scale_log2 - mb);
-        float p1 = exp2f(__uint_as_float(r[i + 1]) * p.scale_log2 - mb);
-        if (c * 32 + i >= kn) p0 = 0.f;
-        if (c * 32 + i + 1 >= kn) p1 = 0.f;
-        l_blk += p0 + p1;
-        split_pack2(p0, p1, ph_[i >> 1], pl_[i >> 1]);
+    for (int cc = 0; cc < 2; ++cc) {
+      const int c = half * 2 + cc;
+      if (c < nchunk) {
+        uint32_t r[32];
+        tmem_ld32(tS + lane_addr + c * 32, r);
+        tmem_ld_wait();
+        uint32_t ph_[16], pl_[16];
+        l_blk += full ? chunk_exp_pack<true>(r, c * 32, kn, p.scale_log2, mb, ph_, pl_)
+                      : chunk_exp_pack<false>(r, c * 32, kn, p.scale_log2, mb, ph_, pl_);
+        tmem_st16(tS + lane_addr + c * 32, ph_);
+        if (NSPLIT == 2) tmem_st16(tS + lane_addr + c * 32 + 16, pl_);
       }
-      tmem_st16(tS + lane_addr + c * 32, ph_);
-      if (NSPLIT == 2) tmem_st16(tS + lane_addr + c * 32 + 16, pl_);
     }
     tmem_st_wait();
     tc_fence_before();
@@ -209,22 +243,25 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
     }
     __syncwarp();
     l_run = l_run * alpha + l_blk;
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
+    {
       uint32_t r[32];
-      tmem_ld32(tO + lane_addr + c * 32, r);
+      tmem_ld32(tO + lane_addr + half * 32, r);
       tmem_ld_wait();
 #pragma unroll
-      for (int i = 0; i < 32; ++i) o_acc[c * 32 + i] = o_acc[c * 32 + i] * alpha + __uint_as_float(r[i]);
+      for (int i = 0; i < 32; ++i) o_acc[i] = o_acc[i] * alpha + __uint_as_float(r[i]);
     }
     tc_fence_before();
   }
 
+  // row sum = sum of the two halves' partial sums (same running max, so they add directly)
+  __syncthreads();
+  xch[half * 128 + row] = l_run;
+  __syncthreads();
   if (q_row < p.N) {
-    const float inv = 1.0f / l_run;
-    const long long off = ((long long)b * p.N + q_row) * C + h * 64;
+    const float inv = 1.0f / (xch[row] + xch[128 + row]);
+    const long long off = ((long long)b * p.N + q_row) * C + h * 64 + half * 32;
 #pragma unroll
-    for (int i = 0; i < 64; i += 8) {
+    for (int i = 0; i < 32; i += 8) {
       uint4 hv, lv;
       split_pack2(o_acc[i] * inv, o_acc[i + 1] * inv, hv.x, lv.x);
       split_pack2(o_acc[i + 2] * inv, o_acc[i + 3] * inv, hv.y, lv.y);
@@ -246,7 +283,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
 template <int NSPLIT>
 static int launch_attn(const CUtensorMap& mh, const CUtensorMap& ml, const AttnParams& p,
                        cudaStream_t stream) {
-  constexpr uint32_t smem = 3 * NSPLIT * kAttnTile + 1024 + 128;
+  constexpr uint32_t smem = 3 * NSPLIT * kAttnTile + 1024 + 64 + 2 * 128 * 4;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(attention_kernel<NSPLIT>,

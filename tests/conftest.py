@@ -9,6 +9,10 @@ if ROOT not in sys.path:
 
 
 def pytest_configure(config):
+    # the CPU oracle (eager PyTorch) collapses when over-subscribed on many-core hosts
+    import torch
+
+    torch.set_num_threads(min(16, os.cpu_count() or 1))
     config.addinivalue_line("markers", "gpu: needs a CUDA device (B200, sm_100a)")
 
 
