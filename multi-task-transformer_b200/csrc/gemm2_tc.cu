@@ -94,12 +94,16 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* sa = smem + stage * Cfg::kStageBytes;
             uint8_t* sb = sa + NSPLIT * kTileBytes;
-            if (leader) mbar_arrive_expect_tx(&full_bar[stage], stage_tx);
-            load_a_tile<NSPLIT, true>(p, &tmA_hi, &tmA_lo, sa, &full_bar[stage], ms, kb, dy, dx);
-            const int kcoord = tap * p.cin_pad + kb * BK;
-            const int nrow = nt * BN2 + (int)rank * BNH;
-            tma_load_2d_cg2(sb, &tmB_hi, &full_bar[stage], kcoord, nrow);
-            if (NSPLIT == 2) tma_load_2d_cg2(sb + kBTile, &tmB_lo, &full_bar[stage], kcoord, nrow);
+            if (p.debug & 1) {  // profiling aid: no loads, the MMAs run on whatever is in shared memory
+              if (leader) mbar_arrive(&full_bar[stage]);
+            } else {
+              if (leader) mbar_arrive_expect_tx(&full_bar[stage], stage_tx);
+              load_a_tile<NSPLIT, true>(p, &tmA_hi, &tmA_lo, sa, &full_bar[stage], ms, kb, dy, dx);
+              const int kcoord = tap * p.cin_pad + kb * BK;
+              const int nrow = nt * BN2 + (int)rank * BNH;
+              tma_load_2d_cg2(sb, &tmB_hi, &full_bar[stage], kcoord, nrow);
+              if (NSPLIT == 2) tma_load_2d_cg2(sb + kBTile, &tmB_lo, &full_bar[stage], kcoord, nrow);
+            }
             if (++stage == ST) {
               stage = 0;
               phase ^= 1;
@@ -174,25 +178,28 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_leader(&tempty_bar[as]);
-        if (ri.ok) {
+        if (ri.ok && !(p.debug & 2)) {
           epilogue_store32(p, r0, nbase, ri);
           epilogue_store32(p, r1, nbase + 32, ri);
         }
       } else {
-        uint32_t r0[32], r1[32], r2[32], r3[32];
-        tmem_ld32(taddr, r0);
-        tmem_ld32(taddr + 32, r1);
-        tmem_ld32(taddr + 64, r2);
-        tmem_ld32(taddr + 96, r3);
-        tmem_ld_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_leader(&tempty_bar[as]);
-        if (ri.ok) {
-          epilogue_store32(p, r0, nbase, ri);
-          epilogue_store32(p, r1, nbase + 32, ri);
-          epilogue_store32(p, r2, nbase + 64, ri);
-          epilogue_store32(p, r3, nbase + 96, ri);
+        // 128 columns per warp: two 64-column halves to keep the register footprint at 64 accumulators
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          uint32_t r0[32], r1[32];
+          tmem_ld32(taddr + hh * 64, r0);
+          tmem_ld32(taddr + hh * 64 + 32, r1);
+          tmem_ld_wait();
+          if (hh == 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_leader(&tempty_bar[as]);
+          }
+          if (ri.ok && !(p.debug & 2)) {
+            epilogue_store32(p, r0, nbase + hh * 64, ri);
+            epilogue_store32(p, r1, nbase + hh * 64 + 32, ri);
+          }
+          __syncwarp();
         }
       }
       __syncwarp();

@@ -32,7 +32,9 @@ struct GemmParams {
   long long ldo_bf;
   int in_group, out_group, out_offset;
   int vec_ok;
+  int vec32_ok;  // every epilogue pointer / stride allows 32-byte accesses
   int a_groups_per_tile;  // >0: A rows are gathered in groups through a rank-3 tensor map
+  int debug;              // profiling aid (env MTT_GEMM_DEBUG): bit0 = skip TMA loads, bit1 = skip global stores
 };
 
 // Host: validates the descriptor, fills GemmParams (tiles_n left to the caller) and encodes the four
@@ -102,6 +104,58 @@ __device__ __forceinline__ RowInfo row_info(const GemmParams& p, int ms, int row
 __device__ __forceinline__ void epilogue_store32(const GemmParams& p, const uint32_t (&rr)[32], int n0,
                                                  const RowInfo& ri) {
   if (n0 >= p.N) return;
+  if (p.vec32_ok && n0 + 32 <= p.N) {
+    // full chunk, 32-byte aligned everywhere: 256-bit loads / stores (one full sector per lane per access)
+    float v[32];
+    if (p.bias) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const U32x8 b = ld_global_nc_v8(p.bias + n0 + g * 8);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[g * 8 + j] = __uint_as_float(rr[g * 8 + j]) + __uint_as_float(b.v[j]);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rr[j]);
+    }
+    if (p.act == MTT_ACT_GELU) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+    } else if (p.act == MTT_ACT_RELU) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+    }
+    if (p.residual) {
+      const float* rp = p.residual + ri.mr * p.ldr + n0;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const U32x8 a = ld_global_v8(rp + g * 8);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[g * 8 + j] += __uint_as_float(a.v[j]);
+      }
+    }
+    if (p.out_f32) {
+      float* op = p.out_f32 + ri.mo * p.ldo_f32 + n0;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        U32x8 o;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o.v[j] = __float_as_uint(v[g * 8 + j]);
+        st_global_v8(op + g * 8, o);
+      }
+    }
+    if (p.out_hi) {
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        U32x8 h, l;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) split_pack2(v[g * 16 + 2 * j], v[g * 16 + 2 * j + 1], h.v[j], l.v[j]);
+        st_global_v8(p.out_hi + ri.mo * p.ldo_bf + n0 + g * 16, h);
+        if (p.out_lo) st_global_v8(p.out_lo + ri.mo * p.ldo_bf + n0 + g * 16, l);
+      }
+    }
+    return;
+  }
 #pragma unroll
   for (int j8 = 0; j8 < 32; j8 += 8) {
     const int n = n0 + j8;

@@ -40,6 +40,14 @@ int gemm_prepare(const mtt_gemm_desc* d, int b_box_rows, GemmParams& p, CUtensor
                      (long long)d->lda, (long long)d->ldb);
 
   p = GemmParams{};
+  {
+    static int dbg = -1;
+    if (dbg < 0) {
+      const char* e = getenv("MTT_GEMM_DEBUG");
+      dbg = e ? atoi(e) : 0;
+    }
+    p.debug = dbg;
+  }
   p.M = d->M;
   p.N = d->N;
   p.mode = d->mode;
@@ -67,6 +75,12 @@ int gemm_prepare(const mtt_gemm_desc* d, int b_box_rows, GemmParams& p, CUtensor
   if (d->residual && (!al16(d->residual) || d->ldr % 4)) p.vec_ok = 0;
   if (d->out_f32 && (!al16(d->out_f32) || d->ldo_f32 % 4)) p.vec_ok = 0;
   if (d->out_hi && (!al16(d->out_hi) || d->ldo_bf % 8 || (p.out_lo && !al16(p.out_lo)))) p.vec_ok = 0;
+  auto al32 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 31) == 0; };
+  p.vec32_ok = p.vec_ok;
+  if (d->bias && !al32(d->bias)) p.vec32_ok = 0;
+  if (d->residual && (!al32(d->residual) || d->ldr % 8)) p.vec32_ok = 0;
+  if (d->out_f32 && (!al32(d->out_f32) || d->ldo_f32 % 8)) p.vec32_ok = 0;
+  if (d->out_hi && (!al32(d->out_hi) || d->ldo_bf % 16 || (p.out_lo && !al32(p.out_lo)))) p.vec32_ok = 0;
 
   int rc;
   const int ksq = (d->mode == 1) ? d->ksize * d->ksize : 1;

@@ -215,9 +215,9 @@ __device__ __forceinline__ void cluster_sync_all() {
 }
 // arrive on the mbarrier at the same shared-memory offset in cluster rank 0
 __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) &
-                                                                                   kPeerBitMask)
-               : "memory");
+  // default semantics (release at CTA scope): the TMEM reads this orders are already fenced with
+  // tcgen05.fence::before_thread_sync; a cluster-scope release would cost a MEMBAR.ALL.GPU per arrive
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
 }
 __device__ __forceinline__ void tma_load_2d_cg2(void* smem, const CUtensorMap* m, uint64_t* bar, int c0,
                                                 int c1) {
@@ -276,6 +276,33 @@ __device__ __forceinline__ void umma_commit_cg2(uint64_t* bar) {
           "r"(smem_u32(bar) & kPeerBitMask),
       "h"((uint16_t)3)
       : "memory");
+}
+
+// ---------------------------------------------------------------- 256-bit global access (sm_100+)
+struct alignas(32) U32x8 {
+  uint32_t v[8];
+};
+__device__ __forceinline__ void st_global_v8(void* p, const U32x8& x) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(x.v[0]), "r"(x.v[1]),
+               "r"(x.v[2]), "r"(x.v[3]), "r"(x.v[4]), "r"(x.v[5]), "r"(x.v[6]), "r"(x.v[7])
+               : "memory");
+}
+__device__ __forceinline__ U32x8 ld_global_v8(const void* p) {
+  U32x8 x;
+  asm volatile("ld.global.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(x.v[0]), "=r"(x.v[1]), "=r"(x.v[2]), "=r"(x.v[3]), "=r"(x.v[4]), "=r"(x.v[5]), "=r"(x.v[6]),
+                 "=r"(x.v[7])
+               : "l"(p)
+               : "memory");
+  return x;
+}
+__device__ __forceinline__ U32x8 ld_global_nc_v8(const void* p) {
+  U32x8 x;
+  asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(x.v[0]), "=r"(x.v[1]), "=r"(x.v[2]), "=r"(x.v[3]), "=r"(x.v[4]), "=r"(x.v[5]), "=r"(x.v[6]),
+                 "=r"(x.v[7])
+               : "l"(p));
+  return x;
 }
 
 // ---------------------------------------------------------------- split-bf16 helpers

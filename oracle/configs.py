@@ -29,6 +29,14 @@ def taskprompter(name):
         "tp_cfg5": dict(tasks=["semseg", "depth", "3ddet"], num_output={"semseg": 19, "depth": 1, "3ddet": 18},
                         img_size=(1024, 2048), patch=16, C=1024, depth=24, heads=16, select=[6, 12, 18],
                         e=300, f=350, chan_nheads=1, use_ctr=False),
+        # long, non-square sequence (N = 2 + 16*128 = 2050 tokens) at ViT-L width: cheap stand-in for cfg5 in tests
+        "tp_long": dict(tasks=["semseg", "depth"], num_output={"semseg": 19, "depth": 1},
+                        img_size=(256, 2048), patch=16, C=1024, depth=4, heads=16, select=[1, 2, 3],
+                        e=300, f=350, chan_nheads=4, use_ctr=False),
+        # 4-block slice of the cfg5 geometry (N = 8195 tokens) for long-sequence parity at tractable oracle cost
+        "tp_cfg5_d4": dict(tasks=["semseg", "depth", "3ddet"], num_output={"semseg": 19, "depth": 1, "3ddet": 18},
+                           img_size=(1024, 2048), patch=16, C=1024, depth=4, heads=16, select=[1, 2, 3],
+                           e=300, f=350, chan_nheads=1, use_ctr=False),
     }[name]
     c = dict(c)
     c["name"] = name
