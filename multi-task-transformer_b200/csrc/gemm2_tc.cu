@@ -87,27 +87,34 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
       for (int tile = pair; tile < num_tiles; tile += num_pairs) {
         const int ms = (tile % pairs_m) * 2 + (int)rank;
         const int nt = tile / pairs_m;
-        for (int tap = 0; tap < p.taps; ++tap) {
+        const int nrow = nt * BN2 + (int)rank * BNH;
+        for (int ki = 0; ki < k_iters; ++ki) {
+          const int tap = ki / p.num_kb, kb = ki - tap * p.num_kb;
           const int dy = (tap / p.ksize - p.ksize / 2) * p.dil;
           const int dx = (tap % p.ksize - p.ksize / 2) * p.dil;
-          for (int kb = 0; kb < p.num_kb; ++kb) {
-            mbar_wait(&empty_bar[stage], phase ^ 1);
-            uint8_t* sa = smem + stage * Cfg::kStageBytes;
-            uint8_t* sb = sa + NSPLIT * kTileBytes;
-            if (p.debug & 1) {  // profiling aid: no loads, the MMAs run on whatever is in shared memory
-              if (leader) mbar_arrive(&full_bar[stage]);
-            } else {
-              if (leader) mbar_arrive_expect_tx(&full_bar[stage], stage_tx);
-              load_a_tile<NSPLIT, true>(p, &tmA_hi, &tmA_lo, sa, &full_bar[stage], ms, kb, dy, dx);
-              const int kcoord = tap * p.cin_pad + kb * BK;
-              const int nrow = nt * BN2 + (int)rank * BNH;
-              tma_load_2d_cg2(sb, &tmB_hi, &full_bar[stage], kcoord, nrow);
-              if (NSPLIT == 2) tma_load_2d_cg2(sb + kBTile, &tmB_lo, &full_bar[stage], kcoord, nrow);
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * Cfg::kStageBytes;
+          uint8_t* sb = sa + NSPLIT * kTileBytes;
+          if (p.debug & 1) {  // profiling aid: no loads, the MMAs run on whatever is in shared memory
+            if (leader) mbar_arrive(&full_bar[stage]);
+          } else {
+            if (leader) mbar_arrive_expect_tx(&full_bar[stage], stage_tx);
+            load_a_tile<NSPLIT, 1>(p, &tmA_hi, &tmA_lo, sa, &full_bar[stage], ms, kb, dy, dx);
+            const int kcoord = tap * p.cin_pad + kb * BK;
+            tma_load_2d_cg2(sb, &tmB_hi, &full_bar[stage], kcoord, nrow);
+            if (NSPLIT == 2) tma_load_2d_cg2(sb + kBTile, &tmB_lo, &full_bar[stage], kcoord, nrow);
+            const int kp = ki + ST + kPrefetchAhead - 1;  // warm L2 for a k-block the ring cannot hold yet
+            if (!(p.debug & 4) && kp < k_iters) {
+              const int tp = kp / p.num_kb, kbp = kp - tp * p.num_kb;
+              load_a_tile<NSPLIT, 2>(p, &tmA_hi, &tmA_lo, nullptr, nullptr, ms, kbp,
+                                     (tp / p.ksize - p.ksize / 2) * p.dil, (tp % p.ksize - p.ksize / 2) * p.dil);
+              tma_prefetch_2d(&tmB_hi, tp * p.cin_pad + kbp * BK, nrow);
+              if (NSPLIT == 2) tma_prefetch_2d(&tmB_lo, tp * p.cin_pad + kbp * BK, nrow);
             }
-            if (++stage == ST) {
-              stage = 0;
-              phase ^= 1;
-            }
+          }
+          if (++stage == ST) {
+            stage = 0;
+            phase ^= 1;
           }
         }
       }

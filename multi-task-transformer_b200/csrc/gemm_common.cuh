@@ -11,6 +11,7 @@ constexpr int BK = 64;   // K per pipeline stage: one 128-byte swizzle row of bf
 constexpr int kEpiWarps = 8;
 constexpr int kGemmThreads = 64 + kEpiWarps * 32;
 constexpr uint32_t kTileBytes = BM * BK * 2;  // 128 x 64 bf16 = 16 KB
+constexpr int kPrefetchAhead = 4;              // k-iterations of L2 prefetch beyond the smem ring
 
 struct GemmParams {
   int M, N;
@@ -42,18 +43,25 @@ struct GemmParams {
 int gemm_prepare(const mtt_gemm_desc* d, int b_box_rows, GemmParams& p, CUtensorMap maps[4]);
 
 // ---- A tile (128 rows x 64 K) of sub-tile `ms`, k-block kb, filter tap (dy, dx) -----------------
-template <int NSPLIT, bool kTwoCta>
+// kMode: 0 = load (1-CTA), 1 = load (CTA pair, signals the leader's barrier), 2 = L2 prefetch only
+template <int NSPLIT, int kMode>
 __device__ __forceinline__ void load_a_tile(const GemmParams& p, const CUtensorMap* tmA_hi,
                                             const CUtensorMap* tmA_lo, uint8_t* sa, uint64_t* bar, int ms,
                                             int kb, int dy, int dx) {
   auto ld2 = [&](void* dst, const CUtensorMap* m, int c0, int c1) {
-    if (kTwoCta) tma_load_2d_cg2(dst, m, bar, c0, c1); else tma_load_2d(dst, m, bar, c0, c1);
+    if (kMode == 2) tma_prefetch_2d(m, c0, c1);
+    else if (kMode == 1) tma_load_2d_cg2(dst, m, bar, c0, c1);
+    else tma_load_2d(dst, m, bar, c0, c1);
   };
   auto ld3 = [&](void* dst, const CUtensorMap* m, int c0, int c1, int c2) {
-    if (kTwoCta) tma_load_3d_cg2(dst, m, bar, c0, c1, c2); else tma_load_3d(dst, m, bar, c0, c1, c2);
+    if (kMode == 2) tma_prefetch_3d(m, c0, c1, c2);
+    else if (kMode == 1) tma_load_3d_cg2(dst, m, bar, c0, c1, c2);
+    else tma_load_3d(dst, m, bar, c0, c1, c2);
   };
   auto ld4 = [&](void* dst, const CUtensorMap* m, int c0, int c1, int c2, int c3) {
-    if (kTwoCta) tma_load_4d_cg2(dst, m, bar, c0, c1, c2, c3); else tma_load_4d(dst, m, bar, c0, c1, c2, c3);
+    if (kMode == 2) tma_prefetch_4d(m, c0, c1, c2, c3);
+    else if (kMode == 1) tma_load_4d_cg2(dst, m, bar, c0, c1, c2, c3);
+    else tma_load_4d(dst, m, bar, c0, c1, c2, c3);
   };
   if (p.mode == 0 && p.a_groups_per_tile > 0) {
     ld3(sa, tmA_hi, kb * BK, 0, ms * p.a_groups_per_tile);

@@ -196,8 +196,9 @@ extern "C" int mtt_gemm(const mtt_gemm_desc* d, mtt_stream_t stream_) {
     // it does not waste more than ~1/8 of the columns, otherwise pair up on a 128-wide tile.
     if (!d) return set_error(MTT_ERR_BAD_SHAPE, "mtt_gemm: null descriptor");
     const int n256 = (d->N + 255) / 256 * 256;
-    v = ((n256 - d->N) * 8 <= n256) ? 2 : 3;
-    if (d->N <= 64) v = 1;
+    // measured (profiles/r1c_gemm_variants.txt): the 256x256 pair wins for wide N, the single-CTA 128x128
+    // tile for narrow / ragged N (decoder widths 300, 350) where a 256-wide tile wastes columns
+    v = (d->N >= 512 && (n256 - d->N) * 8 <= n256) ? 2 : 1;
   }
   if (v == 1) return launch_gemm_1cta(d, stream);
   return launch_gemm_2cta(d, v == 2 ? 256 : 128, stream);
