@@ -51,14 +51,14 @@ __device__ __forceinline__ float chunk_exp_pack(const uint32_t (&r)[32], int col
   float sum = 0.f;
 #pragma unroll
   for (int i = 0; i < 32; i += 2) {
-    float p0 = exp2f(fmaf(__uint_as_float(r[i]), sl2, -mb));
-    float p1 = exp2f(fmaf(__uint_as_float(r[i + 1]), sl2, -mb));
+    float p0 = ex2_approx(fmaf(__uint_as_float(r[i]), sl2, -mb));
+    float p1 = ex2_approx(fmaf(__uint_as_float(r[i + 1]), sl2, -mb));
     if (!FULL) {
       if (col0 + i >= kn) p0 = 0.f;
       if (col0 + i + 1 >= kn) p1 = 0.f;
     }
     sum += p0 + p1;
-    split_pack2(p0, p1, ph[i >> 1], pl[i >> 1]);
+    split_pack2_alu(p0, p1, ph[i >> 1], pl[i >> 1]);
   }
   return sum;
 }
@@ -190,7 +190,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
     __syncthreads();
     mx = fmaxf(xch[row], xch[128 + row]);
     const float m_new = fmaxf(m_run, mx);
-    const float alpha = exp2f((m_run - m_new) * p.scale_log2);
+    const float alpha = ex2_approx((m_run - m_new) * p.scale_log2);
     const float mb = m_new * p.scale_log2;
     m_run = m_new;
 

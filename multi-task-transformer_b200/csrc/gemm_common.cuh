@@ -11,7 +11,6 @@ constexpr int BK = 64;   // K per pipeline stage: one 128-byte swizzle row of bf
 constexpr int kEpiWarps = 8;
 constexpr int kGemmThreads = 64 + kEpiWarps * 32;
 constexpr uint32_t kTileBytes = BM * BK * 2;  // 128 x 64 bf16 = 16 KB
-constexpr int kPrefetchAhead = 4;              // k-iterations of L2 prefetch beyond the smem ring
 
 struct GemmParams {
   int M, N;
@@ -44,6 +43,8 @@ int gemm_prepare(const mtt_gemm_desc* d, int b_box_rows, GemmParams& p, CUtensor
 
 // ---- A tile (128 rows x 64 K) of sub-tile `ms`, k-block kb, filter tap (dy, dx) -----------------
 // kMode: 0 = load (1-CTA), 1 = load (CTA pair, signals the leader's barrier), 2 = L2 prefetch only
+// (an L2 prefetch running kPrefetchAhead k-blocks ahead of the smem ring was measured and did not help:
+// 62.4 -> 63.5 us on the qkv GEMM, so the producers do not issue it)
 template <int NSPLIT, int kMode>
 __device__ __forceinline__ void load_a_tile(const GemmParams& p, const CUtensorMap* tmA_hi,
                                             const CUtensorMap* tmA_lo, uint8_t* sa, uint64_t* bar, int ms,

@@ -98,14 +98,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             const int kcoord = tap * p.cin_pad + kb * BK;
             tma_load_2d(sb, &tmB_hi, &full_bar[stage], kcoord, nt * BN);
             if (NSPLIT == 2) tma_load_2d(sb + kTileBytes, &tmB_lo, &full_bar[stage], kcoord, nt * BN);
-            const int kp = ki + ST + kPrefetchAhead - 1;  // warm L2 for a k-block the ring cannot hold yet
-            if (!(p.debug & 4) && kp < k_iters) {
-              const int tp = kp / p.num_kb, kbp = kp - tp * p.num_kb;
-              load_a_tile<NSPLIT, 2>(p, &tmA_hi, &tmA_lo, nullptr, nullptr, mt, kbp,
-                                     (tp / p.ksize - p.ksize / 2) * p.dil, (tp % p.ksize - p.ksize / 2) * p.dil);
-              tma_prefetch_2d(&tmB_hi, tp * p.cin_pad + kbp * BK, nt * BN);
-              if (NSPLIT == 2) tma_prefetch_2d(&tmB_lo, tp * p.cin_pad + kbp * BK, nt * BN);
-            }
           }
           if (++stage == ST) {
             stage = 0;

@@ -348,6 +348,24 @@ __device__ __forceinline__ void split_pack2(float a, float b, uint32_t& hi, uint
   lo = pack_bf16x2(a - bf16lo_to_f32(hi), b - bf16hi_to_f32(hi));
 }
 
+// Same split on the integer / FMA pipes only (no F2FP, which shares the 16-lane XU pipe with MUFU.EX2 and
+// is the bottleneck of the attention softmax): round-half-away by adding 0x8000 to the bit pattern, pack
+// the upper halves with PRMT.  Same 2^-9 / 2^-18 error bounds as the cvt.rn version; FINITE inputs only
+// (an Inf would round into a NaN pattern), which holds for softmax probabilities.
+__device__ __forceinline__ void split_pack2_alu(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const uint32_t ua = __float_as_uint(a) + 0x8000u, ub = __float_as_uint(b) + 0x8000u;
+  hi = __byte_perm(ua, ub, 0x7632);
+  const float ra = a - __uint_as_float(ua & 0xFFFF0000u), rb = b - __uint_as_float(ub & 0xFFFF0000u);
+  lo = __byte_perm(__float_as_uint(ra) + 0x8000u, __float_as_uint(rb) + 0x8000u, 0x7632);
+}
+
+// bare MUFU.EX2 (2 ulp, flushes denormal results to zero): no range fix-up code around it
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 __device__ __forceinline__ float gelu_erf(float x) {
   return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
 }

@@ -319,17 +319,21 @@ class _Plan:
         self.cps = S(B * T, P)
         self.rc = z(B, T, C, self.nh, self.nw)
         self.xfin = z(B * N, C)
-        self.ys, self.yc = S(B * P, C), S(B * P, C)
-        self.cat = S(B * P, 2 * e_pad, zero=True)
-        self.f1 = S(B * P, f, zero=True)
-        self.f2 = S(B * P, f, zero=True)
+        # one set of decoder scratch buffers per task: the T task chains of a level run concurrently on
+        # side streams (each chain's GEMMs are single-wave, 96 tiles on 148 SMs, and latency-bound)
+        self.ys = [S(B * P, C) for _ in range(T)]
+        self.yc = [S(B * P, C) for _ in range(T)]
+        self.cat = [S(B * P, 2 * e_pad, zero=True) for _ in range(T)]
+        self.f1 = [S(B * P, f, zero=True) for _ in range(T)]
+        self.f2 = [S(B * P, f, zero=True) for _ in range(T)]
         self.acc = z(T, B * P, self.f_ld)
         if self.use_ctr:
             self.F = z(T, B * P, self.f_ld)
             self.ctrw = z(B, T, T)
         gh4, gw4 = 4 * self.gh, 4 * self.gw
-        self.up = S(B * gh4 * gw4, f, zero=True)
-        self.hmid = S(B * gh4 * gw4, f, zero=True)
+        self.up = [S(B * gh4 * gw4, f, zero=True) for _ in range(T)]
+        self.hmid = [S(B * gh4 * gw4, f, zero=True) for _ in range(T)]
+        self.side = None   # side streams, created lazily on the plan's device
         self.pred = [z(B * gh4 * gw4, ops.round_up(hw.n_out, 4)) for hw in W.heads]
         oh, ow = self.target if self.target is not None else self.img
         self.out = {t: z(B, hw.n_out, oh, ow) for t, hw in zip(self.tasks, W.heads)}
@@ -359,29 +363,66 @@ class _Plan:
         ops.gemm(self.xn, w.fc1, bias=w.fc1_b, act=ops.ACT_GELU, out_split=self.hid)
         ops.gemm(self.hid, w.fc2, bias=w.fc2_b, residual=self.xs, out_f32=self.xs)
 
+    def _fork(self):
+        """T side streams forked off the current stream (captured into the same CUDA graph)."""
+        if self.dev.type != "cuda":
+            return None, [None] * self.T
+        if self.side is None:
+            self.side = [torch.cuda.Stream(device=self.dev) for _ in range(self.T)]
+        main = torch.cuda.current_stream()
+        for st in self.side:
+            st.wait_stream(main)
+        return main, self.side
+
+    def _join(self, main):
+        if main is not None:
+            for st in self.side:
+                main.wait_stream(st)
+
+    def _task_chain(self, il, ti, tw, x_src, first):
+        B, N, T, C, P = self.B, self.N, self.T, self.C, self.P
+        ys, yc, cat, f1, f2 = self.ys[ti], self.yc[ti], self.cat[ti], self.f1[ti], self.f2[ti]
+        ops.gate_split(x_src, N, T, self.logits, self.rc, ti, ys, yc, B=B, T=T, N=N, H=self.H,
+                       Cdim=C, gh=self.gh, gw=self.gw, nh=self.nh, nw=self.nw)               # :436-446,:452-467
+        ops.gemm(ys, tw.spa, bias=tw.spa_b, out_split=cat, N=self.e)                         # :447
+        ops.gemm(yc, tw.chan, bias=tw.chan_b, out_split=cat, N=self.e, out_col_offset=self.e_pad)  # :468,:471
+        ops.gemm(cat, tw.f0, bias=tw.f0_b, out_split=f1, N=self.f)                           # fea_fuse[0]
+        ops.gemm(f1, tw.f1, N=self.f, K=self.f, bias=tw.f1_b, act=ops.ACT_GELU, out_split=f2,
+                 conv=(B, self.gh, self.gw, 3, 1))                                           # fea_fuse[1..3]
+        if self.use_ctr:
+            ops.gemm(f2, tw.f4, bias=tw.f4_b, out_f32=self.F[ti][:, :self.f], N=self.f)
+        else:
+            a = self.acc[ti][:, :self.f]
+            ops.gemm(f2, tw.f4, bias=tw.f4_b, residual=None if first else a, out_f32=a, N=self.f)
+
     def _level(self, il, x_src):
         """cal_task_feature (:424-487) on X = x_src rows [b*N + T + pix]; accumulates into self.acc."""
         B, N, T, C, P = self.B, self.N, self.T, self.C, self.P
         lv = self.W.levels[il]
         first = il == 0
+        main, side = self._fork()
         for ti, tw in enumerate(lv.tasks):
-            ops.gate_split(x_src, N, T, self.logits, self.rc, ti, self.ys, self.yc, B=B, T=T, N=N, H=self.H,
-                           Cdim=C, gh=self.gh, gw=self.gw, nh=self.nh, nw=self.nw)           # :436-446,:452-467
-            ops.gemm(self.ys, tw.spa, bias=tw.spa_b, out_split=self.cat, N=self.e)           # :447
-            ops.gemm(self.yc, tw.chan, bias=tw.chan_b, out_split=self.cat, N=self.e,
-                     out_col_offset=self.e_pad)                                              # :468,:471
-            ops.gemm(self.cat, tw.f0, bias=tw.f0_b, out_split=self.f1, N=self.f)             # fea_fuse[0]
-            ops.gemm(self.f1, tw.f1, N=self.f, K=self.f, bias=tw.f1_b, act=ops.ACT_GELU, out_split=self.f2,
-                     conv=(B, self.gh, self.gw, 3, 1))                                       # fea_fuse[1..3]
-            if self.use_ctr:
-                ops.gemm(self.f2, tw.f4, bias=tw.f4_b, out_f32=self.F[ti][:, :self.f], N=self.f)
+            if side[ti] is None:
+                self._task_chain(il, ti, tw, x_src, first)
             else:
-                a = self.acc[ti][:, :self.f]
-                ops.gemm(self.f2, tw.f4, bias=tw.f4_b, residual=None if first else a, out_f32=a, N=self.f)
+                with torch.cuda.stream(side[ti]):
+                    self._task_chain(il, ti, tw, x_src, first)
+        self._join(main)
         if self.use_ctr:
             ops.ctr_weights(self.logits, lv.c0, lv.c0b, lv.c2, lv.c2b, self.ctrw, B=B, H=self.H, T=T, N=N)
             ops.ctr_mix(self.F, self.ctrw, self.acc, T=T, M=B * P, Cdim=self.f_ld, ld=self.f_ld,
                         rows_per_batch=P, accumulate=not first)                              # :481-485,:411
+
+    def _head_chain(self, ti, t, hw):
+        B = self.B
+        gh4, gw4 = 4 * self.gh, 4 * self.gw
+        oh, ow = self.out_hw
+        ops.bilinear(self.acc[ti], self.f_ld, B, self.gh, self.gw, self.f, gh4, gw4, out_split=self.up[ti])  # :420
+        ops.gemm(self.up[ti], hw.mt, N=self.f, K=self.f, bias=hw.mt_b, act=ops.ACT_GELU, out_split=self.hmid[ti],
+                 conv=(B, gh4, gw4, 3, 1))                                                   # ConvHead.mt_proj
+        ops.gemm(self.hmid[ti], hw.lp, bias=hw.lp_b, out_f32=self.pred[ti][:, :hw.n_out], N=hw.n_out)
+        ops.bilinear(self.pred[ti], self.pred[ti].stride(0), B, gh4, gw4, hw.n_out, oh, ow,
+                     out_nchw=self.out[t])                                                   # wrapper :35
 
     def _launch(self, img):
         B, N, T, C, P = self.B, self.N, self.T, self.C, self.P
@@ -398,15 +439,14 @@ class _Plan:
                 self._level(il, self.xs)
         ops.layernorm(self.xs, W.nw, W.nb, W.neps, out_f32=self.xfin)                        # :413
         self._level(3, self.xfin)                                                            # :416-417
-        gh4, gw4 = 4 * self.gh, 4 * self.gw
-        oh, ow = self.out_hw
+        main, side = self._fork()
         for ti, (t, hw) in enumerate(zip(self.tasks, W.heads)):
-            ops.bilinear(self.acc[ti], self.f_ld, B, self.gh, self.gw, self.f, gh4, gw4, out_split=self.up)  # :420
-            ops.gemm(self.up, hw.mt, N=self.f, K=self.f, bias=hw.mt_b, act=ops.ACT_GELU, out_split=self.hmid,
-                     conv=(B, gh4, gw4, 3, 1))                                               # ConvHead.mt_proj
-            ops.gemm(self.hmid, hw.lp, bias=hw.lp_b, out_f32=self.pred[ti][:, :hw.n_out], N=hw.n_out)
-            ops.bilinear(self.pred[ti], self.pred[ti].stride(0), B, gh4, gw4, hw.n_out, oh, ow,
-                         out_nchw=self.out[t])                                               # wrapper :35
+            if side[ti] is None:
+                self._head_chain(ti, t, hw)
+            else:
+                with torch.cuda.stream(side[ti]):
+                    self._head_chain(ti, t, hw)
+        self._join(main)
 
     def run(self, x, graph=True):
         if tuple(x.shape[1:]) != (3, *self.img) or x.dtype != torch.float32:
