@@ -346,7 +346,7 @@ class _Plan:
         self.back1 = z(B * P, dims[1])
         self.xfin = z(B * P, C)
         self.x0 = S(B * h0 * w0, C)
-        self.p1 = S(B * h0 * w0, C)
+        self.p1 = [S(B * h0 * w0, C) for _ in range(T)]   # per task: the task chains run on side streams
         self.cat = [S(B * h0 * w0, E + n, zero=True) for n in self.n_out]
         self.inter = [z(B * h0 * w0, ops.round_up(n, 4)) for n in self.n_out]
         self.st = []
@@ -372,14 +372,15 @@ class _Plan:
                 s.ln32 = z(T * B * h * w, Ci)
             else:
                 s.ln = S(T * B * h * w, Ci)
-                s.rc32 = z(B * h * w, dims[0])
-                s.ue0 = S(B * h * w, dims[i - 1])
-                s.ue1 = S(B * h * w, Ci)
+                s.rc32 = [z(B * h * w, dims[0]) for _ in range(T)]
+                s.ue0 = [S(B * h * w, dims[i - 1]) for _ in range(T)]
+                s.ue1 = [S(B * h * w, Ci) for _ in range(T)]
             self.st.append(s)
         tt = B * self.th * self.tw
         self.ms = z(T, tt, dims[0])
-        self.mss = S(tt, dims[0])
-        self.hm = S(tt, dims[0])
+        self.mss = [S(tt, dims[0]) for _ in range(T)]
+        self.hm = [S(tt, dims[0]) for _ in range(T)]
+        self.side = None
         self.pred = [z(tt, ops.round_up(n, 4)) for n in self.n_out]
         oh, ow = self.img
         self.out = {t: z(B, n, oh, ow) for t, n in zip(self.tasks, self.n_out)}
@@ -396,6 +397,24 @@ class _Plan:
         ops.gemm(self.xn, w.fc1, bias=w.fc1_b, act=ops.ACT_GELU, out_split=self.hid)
         ops.gemm(self.hid, w.fc2, bias=w.fc2_b, residual=self.xs, out_f32=self.xs)
 
+    def _par(self, fn):
+        """Run fn(k) for every task k, each on its own side stream forked from / joined to the current
+        stream (the per-task chains are independent and individually too small to fill 148 SMs)."""
+        T = self.T
+        if self.dev.type != "cuda":
+            for k in range(T):
+                fn(k)
+            return
+        if self.side is None:
+            self.side = [torch.cuda.Stream(device=self.dev) for _ in range(T)]
+        main = torch.cuda.current_stream()
+        for k in range(T):
+            self.side[k].wait_stream(main)
+            with torch.cuda.stream(self.side[k]):
+                fn(k)
+        for k in range(T):
+            main.wait_stream(self.side[k])
+
     def _stage(self, i):
         """InvPTStage + InvPTBlock + multi-scale aggregation for stage i (invpt.py:400-417,290-312,522-539)."""
         B, T, W = self.B, self.T, self.W
@@ -405,14 +424,15 @@ class _Plan:
         if i > 0:
             sp = self.st[i - 1]
             skip = self.back1 if i == 1 else self.back0
-            for k in range(T):
+            def up_embed(k):
                 wa, ba, wb, bb_ = sw.up[k]
-                ops.bilinear(sp.xj, sp.xj.stride(0), B, sp.h, sp.w, sp.C, h, w, out_split=s.ue0,
+                ops.bilinear(sp.xj, sp.xj.stride(0), B, sp.h, sp.w, sp.C, h, w, out_split=s.ue0[k],
                              in_batch_rows=T * sp.h * sp.w, in_row_offset=k * sp.h * sp.w)            # UpEmbed :32
-                ops.gemm(s.ue0, wa, N=Ci, K=sp.C, bias=ba, act=ops.ACT_RELU, out_split=s.ue1,
+                ops.gemm(s.ue0[k], wa, N=Ci, K=sp.C, bias=ba, act=ops.ACT_RELU, out_split=s.ue1[k],
                          conv=(B, h, w, 3, 2))                                                        # :33-35
-                ops.gemm(s.ue1, wb, N=Ci, K=Ci, bias=bb_, act=ops.ACT_RELU, residual=skip, res_row_mod=B * hw,
+                ops.gemm(s.ue1[k], wb, N=Ci, K=Ci, bias=bb_, act=ops.ACT_RELU, residual=skip, res_row_mod=B * hw,
                          out_f32=s.xj, regroup=(hw, T * hw, k * hw), conv=(B, h, w, 3, 2))            # :36-38,:406-411
+            self._par(up_embed)
         # ---- InvPTBlock
         ops.layernorm(s.xj, sw.n1w, sw.n1b, sw.eps, out_f32=s.xn32)                                    # :298
         ops.dwconv3x3_s2(s.xn32, sw.dw_w, sw.dw_b, s.qin, B=B, T=T, h=h, w=w, Cdim=Ci)                 # :171-173
@@ -426,9 +446,9 @@ class _Plan:
                             score_out=s.score)                                                          # :204-236
         ops.gemm(s.ao, sw.proj, bias=sw.proj_b, out_f32=s.a32)                                         # :238
         qhw = (h // 2) * (w // 2)
-        for k in range(T):                                                                             # :299-306
-            ops.bilinear(s.a32, s.a32.stride(0), B, h // 2, w // 2, Ci, h, w, out_f32=s.xj, accumulate=True,
-                         in_batch_rows=T * qhw, in_row_offset=k * qhw, out_batch_rows=T * hw, out_row_offset=k * hw)
+        self._par(lambda k: ops.bilinear(                                                              # :299-306
+            s.a32, s.a32.stride(0), B, h // 2, w // 2, Ci, h, w, out_f32=s.xj, accumulate=True,
+            in_batch_rows=T * qhw, in_row_offset=k * qhw, out_batch_rows=T * hw, out_row_offset=k * hw))
         ops.layernorm(s.xj, sw.n2w, sw.n2b, sw.eps, out_split=s.xn)                                    # :307
         ops.gemm(s.xn, sw.fc1, bias=sw.fc1_b, act=ops.ACT_GELU, out_split=s.hid)
         ops.gemm(s.hid, sw.fc2, bias=sw.fc2_b, residual=s.xj, out_f32=s.xj)
@@ -437,27 +457,29 @@ class _Plan:
                           seg_stride=hw, out_f32=s.ln32 if i == 0 else None,
                           out_split=None if i == 0 else s.ln, out_seg_stride=B * hw)                   # :524-526
         d0 = self.dims[0]
-        for k in range(T):
+
+        def aggregate(k):
             if i == 0:
                 ops.bilinear(s.ln32[k * B * hw:], s.ln32.stride(0), B, h, w, Ci, self.th, self.tw,
                              out_f32=self.ms[k])                                                       # :537-539
             else:
                 rw, rb = sw.redu[k]
-                ops.gemm(s.ln, rw, M=B * hw, bias=rb, out_f32=s.rc32, a_row_offset=k * B * hw)         # :535-536
+                ops.gemm(s.ln, rw, M=B * hw, bias=rb, out_f32=s.rc32[k], a_row_offset=k * B * hw)      # :535-536
                 last = i == 2
-                ops.bilinear(s.rc32, s.rc32.stride(0), B, h, w, d0, self.th, self.tw, out_f32=self.ms[k],
-                             accumulate=True, out_split=self.mss if last else None)
+                ops.bilinear(s.rc32[k], s.rc32[k].stride(0), B, h, w, d0, self.th, self.tw, out_f32=self.ms[k],
+                             accumulate=True, out_split=self.mss[k] if last else None)
                 if last:
                     self._head(k)
+        self._par(aggregate)
 
     def _head(self, k):
         B, W = self.B, self.W
         tw = W.tasks[k]
         d0 = self.dims[0]
-        ops.gemm(self.mss, tw.mt, N=d0, K=d0, bias=tw.mt_b, act=ops.ACT_RELU, out_split=self.hm,
+        ops.gemm(self.mss[k], tw.mt, N=d0, K=d0, bias=tw.mt_b, act=ops.ACT_RELU, out_split=self.hm[k],
                  conv=(B, self.th, self.tw, 3, 1))                                                     # invpt.py:541-543
         n = self.n_out[k]
-        ops.gemm(self.hm, tw.lp, bias=tw.lp_b, out_f32=self.pred[k][:, :n], N=n)                       # MLPHead
+        ops.gemm(self.hm[k], tw.lp, bias=tw.lp_b, out_f32=self.pred[k][:, :n], N=n)                    # MLPHead
         ops.bilinear(self.pred[k], self.pred[k].stride(0), B, self.th, self.tw, n, self.img[0], self.img[1],
                      out_nchw=self.out[self.tasks[k]])                                                 # transformer_net.py:35
 
@@ -486,17 +508,19 @@ class _Plan:
         ops.bilinear(self.xfin, C, B, self.gh, self.gw, C, h0, w0, out_split=self.x0)                  # transformer_decoder.py:85-86
         s0 = self.st[0]
         hw0 = h0 * w0
-        for k, tw in enumerate(W.tasks):
+        def prelim(k):
+            tw = W.tasks[k]
             n = self.n_out[k]
-            ops.gemm(self.x0, tw.pd0, N=C, K=C, bias=tw.pd0_b, act=ops.ACT_RELU, out_split=self.p1,
+            ops.gemm(self.x0, tw.pd0, N=C, K=C, bias=tw.pd0_b, act=ops.ACT_RELU, out_split=self.p1[k],
                      conv=(B, h0, w0, 3, 1))                                                           # ConvBlock 1
-            ops.gemm(self.p1, tw.pd1, N=E, K=C, bias=tw.pd1_b, act=ops.ACT_RELU, out_split=self.cat[k],
+            ops.gemm(self.p1[k], tw.pd1, N=E, K=C, bias=tw.pd1_b, act=ops.ACT_RELU, out_split=self.cat[k],
                      conv=(B, h0, w0, 3, 1))                                                           # ConvBlock 2
             ops.gemm(self.cat[k], tw.ih, K=E, bias=tw.ih_b, out_f32=self.inter[k][:, :n], N=n,
                      out_split=self.cat[k], out_col_offset=E)                                          # :94; invpt.py:511
             ops.gemm(self.cat[k], tw.mix, bias=tw.mix_b, out_f32=s0.xj, regroup=(hw0, T * hw0, k * hw0))  # invpt.py:512
             ops.bilinear(self.inter[k], self.inter[k].stride(0), B, h0, w0, n, self.img[0], self.img[1],
                          out_nchw=self.out_inter[self.tasks[k]])                                       # transformer_net.py:36
+        self._par(prelim)
         for i in range(3):
             self._stage(i)
 
