@@ -195,10 +195,12 @@ extern "C" int mtt_gemm(const mtt_gemm_desc* d, mtt_stream_t stream_) {
     // CTA pairs halve the shared-memory operand traffic per MMA; the 256-wide N tile is worth it when
     // it does not waste more than ~1/8 of the columns, otherwise pair up on a 128-wide tile.
     if (!d) return set_error(MTT_ERR_BAD_SHAPE, "mtt_gemm: null descriptor");
+    // measured on B200 (profiles/r1d_gemm_variants.md): the 256x256 CTA pair wins when there is enough
+    // work per tile column (qkv / fc1: N >= 2048, fc2: K >= 2048); the single-CTA 128x128 tile wins for
+    // narrow or ragged N (decoder widths 300 / 350), short K with N = 1024 (proj), and skinny M (token_trans)
     const int n256 = (d->N + 255) / 256 * 256;
-    // measured (profiles/r1c_gemm_variants.txt): the 256x256 pair wins for wide N, the single-CTA 128x128
-    // tile for narrow / ragged N (decoder widths 300, 350) where a 256-wide tile wastes columns
-    v = (d->N >= 512 && (n256 - d->N) * 8 <= n256) ? 2 : 1;
+    const bool wide = d->N >= 512 && (n256 - d->N) * 8 <= n256;
+    v = (wide && d->M > 128 && (d->N >= 2048 || d->K >= 2048)) ? 2 : 1;
   }
   if (v == 1) return launch_gemm_1cta(d, stream);
   return launch_gemm_2cta(d, v == 2 ? 256 : 128, stream);
