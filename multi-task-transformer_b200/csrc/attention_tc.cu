@@ -9,9 +9,10 @@
 // One CTA = one 128-row query tile of one (b, h); keys/values stream in blocks of 128 by TMA.
 //   S = Q K^T          tcgen05.mma SS, fp32 accumulator in TMEM (128 columns)
 //   P = exp2(S*c - m)  registers; written back IN PLACE over S as packed bf16 hi/lo planes
-//   O_blk = P V        tcgen05.mma with A = P from TMEM, B = V from smem (MN-major), TMEM 64 columns
-//   O = O*alpha + O_blk  in registers, online softmax; 256 threads = two per query row, each owning
-//   half of the key columns of S/P and half of the output columns of O (row max / sum exchanged in smem)
+//   O += P V           tcgen05.mma with A = P from TMEM, B = V from smem (MN-major), TMEM 64 columns
+//   O += P V accumulates in TMEM across key blocks; online softmax with lazy rescaling (O is only
+//   rescaled when the running max moves by more than 2^8); 256 threads = two per query row, each owning
+//   half of the key columns of S/P (read from TMEM once, kept in registers) and half of O's columns
 // Split-bf16 operands (NSPLIT = 2): every product is 3 MMAs, as in gemm_tc.cu.
 // The CTA is deliberately simple (no warp specialisation): 96 KB smem and 256 TMEM columns let two
 // CTAs share an SM, so one CTA's softmax overlaps the other's MMAs.
@@ -124,9 +125,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
   }
   __syncwarp();
 
-  float o_acc[32];
-#pragma unroll
-  for (int i = 0; i < 32; ++i) o_acc[i] = 0.f;
+  // Online softmax with the output accumulator kept in TMEM across key blocks and LAZY rescaling: the
+  // running maximum m_run only moves (and O / l are only rescaled) when a block's maximum exceeds it by
+  // more than 2^kLazyLog2 after scaling, so P stays below 2^kLazyLog2 and the TMEM round trip of O is rare.
+  constexpr float kLazyLog2 = 8.0f;
   float m_run = -INFINITY, l_run = 0.f;
   const int q_row = q0 + row;
   const bool export_row = (p.prompt_logits != nullptr) && (q_row < p.T);
@@ -167,48 +169,59 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
     }
     __syncwarp();
 
-    // ---- pass 1: row maximum over this thread's half of the valid columns (+ prompt-row export)
+    // ---- S (this thread's 64 columns) is read from TMEM ONCE and stays in registers
     const int nchunk = (kn16 + 31) >> 5;
     const bool full = kn == 128;
+    const int c0 = half * 2;
+    uint32_t s0[32], s1[32];
+    const bool have0 = c0 < nchunk, have1 = c0 + 1 < nchunk;
+    if (have0) tmem_ld32(tS + lane_addr + c0 * 32, s0);
+    if (have1) tmem_ld32(tS + lane_addr + (c0 + 1) * 32, s1);
+    tmem_ld_wait();
     float mx = -INFINITY;
+    if (have0) mx = full ? chunk_max<true>(s0, c0 * 32, kn, mx) : chunk_max<false>(s0, c0 * 32, kn, mx);
+    if (have1) mx = full ? chunk_max<true>(s1, c0 * 32 + 32, kn, mx) : chunk_max<false>(s1, c0 * 32 + 32, kn, mx);
+    if (export_row) {
 #pragma unroll
-    for (int cc = 0; cc < 2; ++cc) {
-      const int c = half * 2 + cc;
-      if (c < nchunk) {
-        uint32_t r[32];
-        tmem_ld32(tS + lane_addr + c * 32, r);
-        tmem_ld_wait();
-        mx = full ? chunk_max<true>(r, c * 32, kn, mx) : chunk_max<false>(r, c * 32, kn, mx);
-        if (export_row) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (c * 32 + i < kn) export_ptr[j * 128 + c * 32 + i] = __uint_as_float(r[i]);
-        }
+      for (int i = 0; i < 32; ++i) {
+        if (have0 && c0 * 32 + i < kn) export_ptr[j * 128 + c0 * 32 + i] = __uint_as_float(s0[i]);
+        if (have1 && c0 * 32 + 32 + i < kn) export_ptr[j * 128 + c0 * 32 + 32 + i] = __uint_as_float(s1[i]);
       }
     }
     xch[half * 128 + row] = mx;
     __syncthreads();
     mx = fmaxf(xch[row], xch[128 + row]);
-    const float m_new = fmaxf(m_run, mx);
-    const float alpha = ex2_approx((m_run - m_new) * p.scale_log2);
-    const float mb = m_new * p.scale_log2;
-    m_run = m_new;
-
-    // ---- pass 2: P = exp2(S*c - m*c), written in place as packed bf16 hi | lo (16 + 16 columns)
-    float l_blk = 0.f;
+    // ---- lazy rescale of the TMEM accumulator (both threads of a row take the same decision)
+    const bool need = (mx - m_run) * p.scale_log2 > kLazyLog2;  // true on the first block (m_run = -inf)
+    if (j == 0) {
+      m_run = mx;
+    } else if (__any_sync(0xffffffffu, need)) {
+      const float alpha = need ? ex2_approx((m_run - mx) * p.scale_log2) : 1.0f;
+      uint32_t o[32];
+      tmem_ld32(tO + lane_addr + half * 32, o);
+      tmem_ld_wait();
 #pragma unroll
-    for (int cc = 0; cc < 2; ++cc) {
-      const int c = half * 2 + cc;
-      if (c < nchunk) {
-        uint32_t r[32];
-        tmem_ld32(tS + lane_addr + c * 32, r);
-        tmem_ld_wait();
-        uint32_t ph_[16], pl_[16];
-        l_blk += full ? chunk_exp_pack<true>(r, c * 32, kn, p.scale_log2, mb, ph_, pl_)
-                      : chunk_exp_pack<false>(r, c * 32, kn, p.scale_log2, mb, ph_, pl_);
-        tmem_st16(tS + lane_addr + c * 32, ph_);
-        if (NSPLIT == 2) tmem_st16(tS + lane_addr + c * 32 + 16, pl_);
-      }
+      for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+      tmem_st32(tO + lane_addr + half * 32, o);
+      l_run *= alpha;
+      if (need) m_run = mx;
+    }
+    const float mb = m_run * p.scale_log2;
+
+    // ---- P = exp2(S*c - m*c), written in place as packed bf16 hi | lo (16 + 16 columns per chunk)
+    if (have0) {
+      uint32_t ph_[16], pl_[16];
+      l_run += full ? chunk_exp_pack<true>(s0, c0 * 32, kn, p.scale_log2, mb, ph_, pl_)
+                    : chunk_exp_pack<false>(s0, c0 * 32, kn, p.scale_log2, mb, ph_, pl_);
+      tmem_st16(tS + lane_addr + c0 * 32, ph_);
+      if (NSPLIT == 2) tmem_st16(tS + lane_addr + c0 * 32 + 16, pl_);
+    }
+    if (have1) {
+      uint32_t ph_[16], pl_[16];
+      l_run += full ? chunk_exp_pack<true>(s1, c0 * 32 + 32, kn, p.scale_log2, mb, ph_, pl_)
+                    : chunk_exp_pack<false>(s1, c0 * 32 + 32, kn, p.scale_log2, mb, ph_, pl_);
+      tmem_st16(tS + lane_addr + c0 * 32 + 32, ph_);
+      if (NSPLIT == 2) tmem_st16(tS + lane_addr + c0 * 32 + 48, pl_);
     }
     tmem_st_wait();
     tc_fence_before();
@@ -224,7 +237,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
       for (int ks = 0; ks < ksteps; ++ks) {
         const uint32_t a_hi = tS + (ks >> 1) * 32 + (ks & 1) * 8;
         const uint64_t vdh = umma_desc_sw128(vh + ks * 2048);
-        umma_ts(tO, a_hi, vdh, idesc_o, ks > 0);
+        umma_ts(tO, a_hi, vdh, idesc_o, (j > 0 || ks > 0) ? 1u : 0u);
         if (NSPLIT == 2) {
           const uint64_t vdl = umma_desc_sw128(vh + kAttnTile + ks * 2048);
           umma_ts(tO, a_hi, vdl, idesc_o, 1);
@@ -234,26 +247,20 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
       umma_commit(bar_o);
     }
     __syncwarp();
-    mbar_wait(bar_o, ph);
+    mbar_wait(bar_o, ph);  // P / O_tmem / the V buffer are free again once PV has retired
     tc_fence_after();
-    if (tid == 0 && j + 1 < nkv) {  // V buffer is free again
+    if (tid == 0 && j + 1 < nkv) {
       mbar_arrive_expect_tx(bar_v, NSPLIT * kAttnTile);
       tma_load_3d(sV, &tm_hi, bar_v, 2 * C + h * 64, (j + 1) * 128, b);
       if (NSPLIT == 2) tma_load_3d(sV + kAttnTile, &tm_lo, bar_v, 2 * C + h * 64, (j + 1) * 128, b);
     }
     __syncwarp();
-    l_run = l_run * alpha + l_blk;
-    {
-      uint32_t r[32];
-      tmem_ld32(tO + lane_addr + half * 32, r);
-      tmem_ld_wait();
-#pragma unroll
-      for (int i = 0; i < 32; ++i) o_acc[i] = o_acc[i] * alpha + __uint_as_float(r[i]);
-    }
-    tc_fence_before();
   }
 
-  // row sum = sum of the two halves' partial sums (same running max, so they add directly)
+  // ---- epilogue: O / l, where l is the sum of the two halves' partial row sums (same m_run)
+  uint32_t o[32];
+  tmem_ld32(tO + lane_addr + half * 32, o);
+  tmem_ld_wait();
   __syncthreads();
   xch[half * 128 + row] = l_run;
   __syncthreads();
@@ -263,10 +270,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
 #pragma unroll
     for (int i = 0; i < 32; i += 8) {
       uint4 hv, lv;
-      split_pack2(o_acc[i] * inv, o_acc[i + 1] * inv, hv.x, lv.x);
-      split_pack2(o_acc[i + 2] * inv, o_acc[i + 3] * inv, hv.y, lv.y);
-      split_pack2(o_acc[i + 4] * inv, o_acc[i + 5] * inv, hv.z, lv.z);
-      split_pack2(o_acc[i + 6] * inv, o_acc[i + 7] * inv, hv.w, lv.w);
+      split_pack2(__uint_as_float(o[i]) * inv, __uint_as_float(o[i + 1]) * inv, hv.x, lv.x);
+      split_pack2(__uint_as_float(o[i + 2]) * inv, __uint_as_float(o[i + 3]) * inv, hv.y, lv.y);
+      split_pack2(__uint_as_float(o[i + 4]) * inv, __uint_as_float(o[i + 5]) * inv, hv.z, lv.z);
+      split_pack2(__uint_as_float(o[i + 6]) * inv, __uint_as_float(o[i + 7]) * inv, hv.w, lv.w);
       *reinterpret_cast<uint4*>(p.out_hi + off + i) = hv;
       if (NSPLIT == 2) *reinterpret_cast<uint4*>(p.out_lo + off + i) = lv;
     }

@@ -343,10 +343,25 @@ class _Plan:
     def _block(self, w, want_logits):
         B, N, T, C, P = self.B, self.N, self.T, self.C, self.P
         ops.layernorm(self.xs, w.n1w, w.n1b, w.eps, out_split=self.xn)                       # :272
+        # channel-prompt path (token_trans -> raw channel logits -> token_trans1) only needs LN1's output and
+        # the prompt rows of xs: it runs on a side stream next to qkv + attention and joins before proj
+        main, side = self._fork(1)
+        if side[0] is None:
+            self._chan_path(w, want_logits)
+        else:
+            with torch.cuda.stream(side[0]):
+                self._chan_path(w, want_logits)
         ops.gemm(self.xn, w.qkv, bias=w.qkv_b, out_split=self.qkv)                           # :201
         ops.attention(self.qkv, self.ao, B=B, N=N, H=self.H, scale=64 ** -0.5,
                       prompt_logits=self.logits if want_logits else None, T=T)               # :204-210
+        self._join(main, 1)
         ops.gemm(self.ao, w.proj, bias=w.proj_b, residual=self.xs, out_f32=self.xs)          # :212,:273,:276
+        ops.layernorm(self.xs, w.n2w, w.n2b, w.eps, out_split=self.xn)                       # :274,:277
+        ops.gemm(self.xn, w.fc1, bias=w.fc1_b, act=ops.ACT_GELU, out_split=self.hid)
+        ops.gemm(self.hid, w.fc2, bias=w.fc2_b, residual=self.xs, out_f32=self.xs)
+
+    def _chan_path(self, w, want_logits):
+        B, N, T, C, P = self.B, self.N, self.T, self.C, self.P
         bstep = max(1, 128 // T)      # images per launch: their T prompt rows form one gathered 128-row A tile
         for b0 in range(0, B, bstep):
             nb = min(bstep, B - b0)
@@ -359,24 +374,22 @@ class _Plan:
             nb = min(bstep, B - b0)
             ops.gemm(self.cps, w.tt1, M=nb * T, bias=w.tt1_b, a_row_offset=b0 * T, residual=self.xs,
                      out_f32=self.xs, regroup=(T, N, b0 * N))                                # :250 token_trans1
-        ops.layernorm(self.xs, w.n2w, w.n2b, w.eps, out_split=self.xn)                       # :274,:277
-        ops.gemm(self.xn, w.fc1, bias=w.fc1_b, act=ops.ACT_GELU, out_split=self.hid)
-        ops.gemm(self.hid, w.fc2, bias=w.fc2_b, residual=self.xs, out_f32=self.xs)
 
-    def _fork(self):
-        """T side streams forked off the current stream (captured into the same CUDA graph)."""
+    def _fork(self, n=None):
+        """n (default T) side streams forked off the current stream (captured into the same CUDA graph)."""
+        n = self.T if n is None else n
         if self.dev.type != "cuda":
-            return None, [None] * self.T
+            return None, [None] * n
         if self.side is None:
-            self.side = [torch.cuda.Stream(device=self.dev) for _ in range(self.T)]
+            self.side = [torch.cuda.Stream(device=self.dev) for _ in range(max(self.T, 1))]
         main = torch.cuda.current_stream()
-        for st in self.side:
+        for st in self.side[:n]:
             st.wait_stream(main)
-        return main, self.side
+        return main, self.side[:n]
 
-    def _join(self, main):
+    def _join(self, main, n=None):
         if main is not None:
-            for st in self.side:
+            for st in self.side[:self.T if n is None else n]:
                 main.wait_stream(st)
 
     def _task_chain(self, il, ti, tw, x_src, first):

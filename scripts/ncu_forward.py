@@ -4,12 +4,16 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import mtt_b200
-from mtt_b200 import taskprompter as TP
 from oracle import configs
 
 cfg_name = sys.argv[1] if len(sys.argv) > 1 else "tp_cfg4"
 mode = sys.argv[2] if len(sys.argv) > 2 else "parity"
-cfg = configs.taskprompter(cfg_name)
+if cfg_name.startswith("tp_"):
+    from mtt_b200 import taskprompter as TP
+    cfg = configs.taskprompter(cfg_name)
+else:
+    from mtt_b200 import invpt as TP
+    cfg = configs.invpt(cfg_name)
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
 with torch.device(dev):
