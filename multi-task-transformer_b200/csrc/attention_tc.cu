@@ -135,29 +135,37 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
   float* export_ptr =
       export_row ? p.prompt_logits + (((long long)b * p.H + h) * p.T + q_row) * p.N : nullptr;
 
+  // S_j = Q K_j^T into TMEM (thread 0 only). Besides the first block it is issued right behind PV_{j-1}:
+  // the tensor pipe executes in issue order, so S_j cannot overwrite P_{j-1} before PV_{j-1} has read it,
+  // and no PV-complete -> wake-up -> issue round trip sits on the critical path.
+  auto issue_s = [&](int jj) {
+    mbar_wait(bar_k, jj & 1);
+    tc_fence_after();
+    const int knj = min(128, p.N - jj * 128);
+    const uint32_t idesc_s = umma_idesc_bf16(128, (knj + 15) & ~15, 0);
+    const uint32_t qh = smem_u32(sQ), kh = smem_u32(sK);
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      const uint64_t qdh = umma_desc_sw128(qh + ks * 32);
+      const uint64_t kdh = umma_desc_sw128(kh + ks * 32);
+      umma_ss(tS, qdh, kdh, idesc_s, ks > 0);
+      if (NSPLIT == 2) {
+        const uint64_t qdl = umma_desc_sw128(qh + kAttnTile + ks * 32);
+        const uint64_t kdl = umma_desc_sw128(kh + kAttnTile + ks * 32);
+        umma_ss(tS, qdh, kdl, idesc_s, 1);
+        umma_ss(tS, qdl, kdh, idesc_s, 1);
+      }
+    }
+    umma_commit(bar_s);
+  };
+
   for (int j = 0; j < nkv; ++j) {
     const uint32_t ph = j & 1;
     const int kn = min(128, p.N - j * 128);  // valid keys in this block
     const int kn16 = (kn + 15) & ~15;        // MMA N (S) / K extent (PV)
-    if (tid == 0) {
-      if (j == 0) mbar_wait(bar_q, 0);
-      mbar_wait(bar_k, ph);
-      tc_fence_after();
-      const uint32_t idesc_s = umma_idesc_bf16(128, kn16, 0);
-      const uint32_t qh = smem_u32(sQ), kh = smem_u32(sK);
-#pragma unroll
-      for (int ks = 0; ks < 4; ++ks) {
-        const uint64_t qdh = umma_desc_sw128(qh + ks * 32);
-        const uint64_t kdh = umma_desc_sw128(kh + ks * 32);
-        umma_ss(tS, qdh, kdh, idesc_s, ks > 0);
-        if (NSPLIT == 2) {
-          const uint64_t qdl = umma_desc_sw128(qh + kAttnTile + ks * 32);
-          const uint64_t kdl = umma_desc_sw128(kh + kAttnTile + ks * 32);
-          umma_ss(tS, qdh, kdl, idesc_s, 1);
-          umma_ss(tS, qdl, kdh, idesc_s, 1);
-        }
-      }
-      umma_commit(bar_s);
+    if (tid == 0 && j == 0) {
+      mbar_wait(bar_q, 0);
+      issue_s(0);
     }
     __syncwarp();
     mbar_wait(bar_s, ph);
@@ -245,17 +253,18 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
         }
       }
       umma_commit(bar_o);
-    }
-    __syncwarp();
-    mbar_wait(bar_o, ph);  // P / O_tmem / the V buffer are free again once PV has retired
-    tc_fence_after();
-    if (tid == 0 && j + 1 < nkv) {
-      mbar_arrive_expect_tx(bar_v, NSPLIT * kAttnTile);
-      tma_load_3d(sV, &tm_hi, bar_v, 2 * C + h * 64, (j + 1) * 128, b);
-      if (NSPLIT == 2) tma_load_3d(sV + kAttnTile, &tm_lo, bar_v, 2 * C + h * 64, (j + 1) * 128, b);
+      if (j + 1 < nkv) {
+        issue_s(j + 1);          // queued right behind PV_j
+        mbar_wait(bar_o, ph);    // PV_j retired: the V buffer is free, prefetch the next value block
+        mbar_arrive_expect_tx(bar_v, NSPLIT * kAttnTile);
+        tma_load_3d(sV, &tm_hi, bar_v, 2 * C + h * 64, (j + 1) * 128, b);
+        if (NSPLIT == 2) tma_load_3d(sV + kAttnTile, &tm_lo, bar_v, 2 * C + h * 64, (j + 1) * 128, b);
+      }
     }
     __syncwarp();
   }
+  mbar_wait(bar_o, (nkv - 1) & 1);  // last PV retired (every earlier one is ordered before the S that followed it)
+  tc_fence_after();
 
   // ---- epilogue: O / l, where l is the sum of the two halves' partial row sums (same m_run)
   uint32_t o[32];
