@@ -17,6 +17,7 @@
 // The CTA is deliberately simple (no warp specialisation): 96 KB smem and 256 TMEM columns let two
 // CTAs share an SM, so one CTA's softmax overlaps the other's MMAs.
 #include <math.h>
+#include <stdlib.h>
 
 #include "host_common.h"
 #include "ptx.cuh"
@@ -315,6 +316,13 @@ static int launch_attn(const CUtensorMap& mh, const CUtensorMap& ml, const AttnP
 
 }  // namespace mtt
 
+namespace mtt {
+int launch_attention2(const mtt_attn_desc* d, cudaStream_t stream);  // attention2_tc.cu
+static int g_attn_variant = -1;  // -1: read MTT_ATTN_VARIANT once; 0/2 = pipelined kernel (default), 1 = simple kernel
+}  // namespace mtt
+
+extern "C" void mtt_set_attention_variant(int v) { mtt::g_attn_variant = v; }
+
 extern "C" int mtt_attention(const mtt_attn_desc* d, mtt_stream_t stream_) {
   using namespace mtt;
   if (!d) return set_error(MTT_ERR_BAD_SHAPE, "mtt_attention: null descriptor");
@@ -327,6 +335,11 @@ extern "C" int mtt_attention(const mtt_attn_desc* d, mtt_stream_t stream_) {
   if (d->T > 128) return set_error(MTT_ERR_BAD_SHAPE, "mtt_attention: T=%d > 128 unsupported", d->T);
   if ((reinterpret_cast<uintptr_t>(d->out_hi) & 15) || (d->out_lo && (reinterpret_cast<uintptr_t>(d->out_lo) & 15)))
     return set_error(MTT_ERR_MISALIGNED, "mtt_attention: output not 16-byte aligned");
+  if (g_attn_variant < 0) {
+    const char* e = getenv("MTT_ATTN_VARIANT");
+    g_attn_variant = e ? atoi(e) : 0;
+  }
+  if (g_attn_variant != 1) return launch_attention2(d, static_cast<cudaStream_t>(stream_));
   const int C = d->H * 64;
   CUtensorMap mh, ml;
   const uint64_t dims[3] = {(uint64_t)3 * C, (uint64_t)d->N, (uint64_t)d->B};

@@ -151,6 +151,11 @@ def set_gemm_variant(v):
     _L.load().mtt_set_gemm_variant(int(v))
 
 
+def set_attention_variant(v):
+    """0 / 2 = software-pipelined attention kernel (default), 1 = simple kernel (tuning / testing knob)."""
+    _L.load().mtt_set_attention_variant(int(v))
+
+
 def launch_count(reset=False):
     lib = _L.load()
     n = lib.mtt_launch_count()

@@ -165,11 +165,14 @@ def test_conv(cuda_dev, ksize, dil, nsplit, gemm_variant):
         assert e < TOL[nsplit], f"conv {B,H,W,Cin,Cout} k{ksize} d{dil}: rel err {e}"
 
 
+@pytest.mark.parametrize("variant", [2, 1], ids=["pipelined", "simple"])
 @pytest.mark.parametrize("nsplit", [2, 1])
-@pytest.mark.parametrize("B,H,N,T", [(2, 3, 300, 4), (1, 2, 1029, 5), (1, 1, 128, 0), (2, 2, 65, 2)])
-def test_attention(cuda_dev, nsplit, B, H, N, T):
+@pytest.mark.parametrize("B,H,N,T", [(2, 3, 300, 4), (1, 2, 1029, 5), (1, 1, 128, 0), (2, 2, 65, 2), (1, 1, 64, 1),
+                                     (1, 2, 40, 3), (1, 1, 193, 0)])
+def test_attention(cuda_dev, nsplit, B, H, N, T, variant):
     from mtt_b200 import ops
 
+    ops.set_attention_variant(variant)
     torch.manual_seed(11)
     C = H * 64
     qkv = torch.randn(B * N, 3 * C, device=cuda_dev)
@@ -187,6 +190,7 @@ def test_attention(cuda_dev, nsplit, B, H, N, T):
     ref = ref.transpose(1, 2).reshape(B * N, C)
     e = relerr(out.float(), ref)
     assert e < (1e-4 if nsplit == 2 else 3e-2), f"attention out rel err {e}"
+    ops.set_attention_variant(0)
     if T:
         e = relerr(logits, raw[:, :, :T, :])
         assert e < (3e-5 if nsplit == 2 else 2e-2), f"prompt logits rel err {e}"
