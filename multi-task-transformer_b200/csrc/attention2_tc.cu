@@ -5,8 +5,9 @@
 // but restructured so that the tensor pipe never waits for the softmax of the SAME CTA:
 //   * keys/values stream in blocks of 64, S is double-buffered in TMEM (2 x 64 columns) and S_{j+1} = Q K_{j+1}^T
 //     is issued before softmax_j starts, so softmax phases run back to back while QK^T / PV execute;
-//   * a dedicated issuer warp owns TMA and tcgen05.mma; 8 softmax warps (two threads per query row) only
-//     wait on "S ready" and signal "P ready" through mbarriers;
+//   * a dedicated issuer warp owns TMA and tcgen05.mma; 16 softmax warps (FOUR threads per query row, 16 key
+//     columns each: the softmax is bound by per-warp instruction latency, ~9 cycles per issued instruction
+//     in ncu, so more, shorter warps win) only wait on "S ready" and signal "P ready" through mbarriers;
 //   * O accumulates in TMEM with lazy rescaling, P overwrites S in place as packed bf16 hi|lo.
 // TMEM: S0 [0,64) S1 [64,128) O [128,192) -> 256 columns; smem 96 KB -> two CTAs per SM.
 #include <math.h>
@@ -16,7 +17,9 @@
 
 namespace mtt {
 
-constexpr int kA2SoftmaxThreads = 256;
+constexpr int kA2Parts = 4;                            // threads per query row
+constexpr int kA2SoftmaxThreads = 128 * kA2Parts;       // 16 softmax warps
+constexpr int kA2Cols = 64 / kA2Parts;                  // S / O columns owned by one thread (16)
 constexpr int kA2Threads = kA2SoftmaxThreads + 32;
 constexpr int kA2TmemCols = 256;
 constexpr uint32_t kQTile = 128 * 64 * 2;  // 16 KB: 128 query rows x 64 bf16
@@ -54,7 +57,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmq_hi, const __grid_const
   uint64_t* bar_p = bars + 7;   // [2] P_j stored               (8 warp arrivals)
   uint64_t* bar_o = bars + 9;   // [2] PV_j complete            (tcgen05.commit)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
-  float* xch = reinterpret_cast<float*>(bars + 12);  // [2 buffers][2 halves][128 rows]
+  float* xch = reinterpret_cast<float*>(bars + 12);  // [2 buffers][kA2Parts][128 rows]
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -76,14 +79,14 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmq_hi, const __grid_const
     fence_barrier_init();
   }
   __syncwarp();
-  if (warp == 8) tmem_alloc<kA2TmemCols>(tmem_slot);
+  if (warp == kA2SoftmaxThreads / 32) tmem_alloc<kA2TmemCols>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tO = tmem_base + 128;
 
-  if (warp == 8) {
+  if (warp == kA2SoftmaxThreads / 32) {
     // ============================================================ issuer warp: TMA + tcgen05.mma
     if (lane == 0) {
       tma_prefetch_desc(&tmq_hi);
@@ -171,8 +174,8 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmq_hi, const __grid_const
     }
     __syncwarp();
   } else {
-    // ============================================================ softmax warps (two threads per query row)
-    const int half = warp >> 2;                 // which 32 of the block's 64 key columns / of O's 64 columns
+    // ============================================================ softmax warps (kA2Parts threads per query row)
+    const int part = warp >> 2;                 // which 16 of the block's 64 key columns / of O's 64 columns
     const int row = (warp & 3) * 32 + lane;
     const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
     constexpr float kLazyLog2 = 8.0f;           // rescale O only when the running max grows by > 2^8
@@ -186,29 +189,30 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmq_hi, const __grid_const
       const int bb = j & 1;
       const uint32_t ph = (j >> 1) & 1;
       const int kn = min(kKB, p.N - j * kKB);
-      const int kn16 = (kn + 15) & ~15;
-      const bool mine = half * 32 < kn16;       // this thread's 32 columns hold at least one computed key
+      const int c0 = part * kA2Cols;            // first key column of this thread
+      const bool mine = c0 < ((kn + 15) & ~15); // the MMA computed at least one of this thread's columns
+      const bool full = c0 + kA2Cols <= kn;
       const uint32_t tS = tmem_base + bb * 64;
       mbar_wait(&bar_s[bb], ph);
       tc_fence_after();
-      uint32_t s[32];
-      if (mine) tmem_ld32(tS + lane_addr + half * 32, s);
+      uint32_t s[kA2Cols];
+      if (mine) tmem_ld16(tS + lane_addr + c0, s);
       tmem_ld_wait();
       float mx = -INFINITY;
       if (mine) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (half * 32 + i < kn) mx = fmaxf(mx, __uint_as_float(s[i]));
+        for (int i = 0; i < kA2Cols; ++i)
+          if (full || c0 + i < kn) mx = fmaxf(mx, __uint_as_float(s[i]));
         if (export_row) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (half * 32 + i < kn) export_ptr[j * kKB + half * 32 + i] = __uint_as_float(s[i]);
+          for (int i = 0; i < kA2Cols; ++i)
+            if (c0 + i < kn) export_ptr[j * kKB + c0 + i] = __uint_as_float(s[i]);
         }
       }
-      float* x = xch + bb * 256;
-      x[half * 128 + row] = mx;
+      float* x = xch + bb * (kA2Parts * 128);
+      x[part * 128 + row] = mx;
       named_bar_sync(1, kA2SoftmaxThreads);     // also orders every thread's S read before any P write
-      mx = fmaxf(x[row], x[128 + row]);
+      mx = fmaxf(fmaxf(x[row], x[128 + row]), fmaxf(x[256 + row], x[384 + row]));
       const bool need = (mx - m_run) * p.scale_log2 > kLazyLog2;
       if (j == 0) {
         m_run = mx;
@@ -217,31 +221,33 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmq_hi, const __grid_const
         mbar_wait(&bar_o[(j - 1) & 1], ((j - 1) >> 1) & 1);
         tc_fence_after();
         const float alpha = need ? ex2_approx((m_run - mx) * p.scale_log2) : 1.0f;
-        uint32_t o[32];
-        tmem_ld32(tO + lane_addr + half * 32, o);
+        uint32_t o[kA2Cols];
+        tmem_ld16(tO + lane_addr + c0, o);
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-        tmem_st32(tO + lane_addr + half * 32, o);
+        for (int i = 0; i < kA2Cols; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+        tmem_st16(tO + lane_addr + c0, o);
         l_run *= alpha;
         if (need) m_run = mx;
       }
       if (mine) {
         const float mb = m_run * p.scale_log2;
-        uint32_t ph_[16], pl_[16];
+        uint32_t ph_[kA2Cols / 2], pl_[kA2Cols / 2];
         float sum = 0.f;
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
+        for (int i = 0; i < kA2Cols; i += 2) {
           float p0 = ex2_approx(fmaf(__uint_as_float(s[i]), p.scale_log2, -mb));
           float p1 = ex2_approx(fmaf(__uint_as_float(s[i + 1]), p.scale_log2, -mb));
-          if (half * 32 + i >= kn) p0 = 0.f;
-          if (half * 32 + i + 1 >= kn) p1 = 0.f;
+          if (!full) {
+            if (c0 + i >= kn) p0 = 0.f;
+            if (c0 + i + 1 >= kn) p1 = 0.f;
+          }
           sum += p0 + p1;
-          split_pack2_alu(p0, p1, ph_[i >> 1], pl_[i >> 1]);
+          split_pack2(p0, p1, ph_[i >> 1], pl_[i >> 1]);
         }
         l_run += sum;
-        tmem_st16(tS + lane_addr + half * 16, ph_);
-        if (NSPLIT == 2) tmem_st16(tS + lane_addr + 32 + half * 16, pl_);
+        tmem_st8(tS + lane_addr + part * (kA2Cols / 2), ph_);
+        if (NSPLIT == 2) tmem_st8(tS + lane_addr + 32 + part * (kA2Cols / 2), pl_);
       }
       tmem_st_wait();
       tc_fence_before();
@@ -249,20 +255,20 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmq_hi, const __grid_const
       if (lane == 0) mbar_arrive(&bar_p[bb]);
     }
 
-    // ---- epilogue: O / l (l = sum of the two halves' partial row sums, same running max)
+    // ---- epilogue: O / l (l = sum of the row's partial sums, all taken against the same running max)
     mbar_wait(&bar_o[(nkv - 1) & 1], ((nkv - 1) >> 1) & 1);
     tc_fence_after();
-    uint32_t o[32];
-    tmem_ld32(tO + lane_addr + half * 32, o);
+    uint32_t o[kA2Cols];
+    tmem_ld16(tO + lane_addr + part * kA2Cols, o);
     tmem_ld_wait();
-    float* x = xch + (nkv & 1) * 256;
-    x[half * 128 + row] = l_run;
+    float* x = xch + (nkv & 1) * (kA2Parts * 128);
+    x[part * 128 + row] = l_run;
     named_bar_sync(1, kA2SoftmaxThreads);
     if (q_row < p.N) {
-      const float inv = 1.0f / (x[row] + x[128 + row]);
-      const long long off = ((long long)b * p.N + q_row) * C + h * 64 + half * 32;
+      const float inv = 1.0f / ((x[row] + x[128 + row]) + (x[256 + row] + x[384 + row]));
+      const long long off = ((long long)b * p.N + q_row) * C + h * 64 + part * kA2Cols;
 #pragma unroll
-      for (int i = 0; i < 32; i += 8) {
+      for (int i = 0; i < kA2Cols; i += 8) {
         uint4 hv, lv;
         split_pack2(__uint_as_float(o[i]) * inv, __uint_as_float(o[i + 1]) * inv, hv.x, lv.x);
         split_pack2(__uint_as_float(o[i + 2]) * inv, __uint_as_float(o[i + 3]) * inv, hv.y, lv.y);
@@ -276,7 +282,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmq_hi, const __grid_const
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == kA2SoftmaxThreads / 32) {
     tc_fence_after();
     tmem_dealloc<kA2TmemCols>(tmem_base);
   }
@@ -284,7 +290,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmq_hi, const __grid_const
 
 template <int NSPLIT>
 static int launch_attn2(const CUtensorMap* maps, const Attn2Params& p, cudaStream_t stream) {
-  constexpr uint32_t smem = NSPLIT * kQTile + 4 * NSPLIT * kKVTile + 1024 + 128 + 2 * 256 * 4;
+  constexpr uint32_t smem = NSPLIT * kQTile + 4 * NSPLIT * kKVTile + 1024 + 128 + 2 * kA2Parts * 128 * 4;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(attention2_kernel<NSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -60,7 +60,7 @@ __device__ __forceinline__ float chunk_exp_pack(const uint32_t (&r)[32], int col
       if (col0 + i + 1 >= kn) p1 = 0.f;
     }
     sum += p0 + p1;
-    split_pack2_alu(p0, p1, ph[i >> 1], pl[i >> 1]);
+    split_pack2(p0, p1, ph[i >> 1], pl[i >> 1]);
   }
   return sum;
 }
