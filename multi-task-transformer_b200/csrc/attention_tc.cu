@@ -34,6 +34,7 @@ struct AttnParams {
   __nv_bfloat16* out_hi;
   __nv_bfloat16* out_lo;
   float* prompt_logits;
+  unsigned long long* trace;  // debug: clock64 timeline of CTA (1,0,0), threads 0 / 40 / 200 (NULL = off)
 };
 
 // row maximum of one 32-column chunk (FULL: every column is a valid key)
@@ -92,6 +93,11 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
   const int C = p.H * 64;
   const int q0 = qt * 128;
   const int nkv = (p.N + 127) / 128;
+  const bool traced = p.trace != nullptr && blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0 &&
+                      (tid == 0 || tid == 40 || tid == 200);
+  unsigned long long* tr = traced ? p.trace + (tid == 0 ? 0 : (tid == 40 ? 256 : 512)) : nullptr;
+  int trn = 0;
+#define MTT_TR() do { if (traced && trn < 256) tr[trn++] = clock64(); } while (0)
 
   if (tid == 0) {
     tma_prefetch_desc(&tm_hi);
@@ -169,8 +175,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
       issue_s(0);
     }
     __syncwarp();
+    MTT_TR();  // 0: iteration top
     mbar_wait(bar_s, ph);
     tc_fence_after();
+    MTT_TR();  // 1: S ready
     if (tid == 0 && j + 1 < nkv) {  // K buffer is free again: prefetch the next key block
       mbar_arrive_expect_tx(bar_k, NSPLIT * kAttnTile);
       tma_load_3d(sK, &tm_hi, bar_k, C + h * 64, (j + 1) * 128, b);
@@ -187,6 +195,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
     if (have0) tmem_ld32(tS + lane_addr + c0 * 32, s0);
     if (have1) tmem_ld32(tS + lane_addr + (c0 + 1) * 32, s1);
     tmem_ld_wait();
+    MTT_TR();  // 2: S in registers
     float mx = -INFINITY;
     if (have0) mx = full ? chunk_max<true>(s0, c0 * 32, kn, mx) : chunk_max<false>(s0, c0 * 32, kn, mx);
     if (have1) mx = full ? chunk_max<true>(s1, c0 * 32 + 32, kn, mx) : chunk_max<false>(s1, c0 * 32 + 32, kn, mx);
@@ -200,6 +209,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
     xch[half * 128 + row] = mx;
     __syncthreads();
     mx = fmaxf(xch[row], xch[128 + row]);
+    MTT_TR();  // 3: row max exchanged
     // ---- lazy rescale of the TMEM accumulator (both threads of a row take the same decision)
     const bool need = (mx - m_run) * p.scale_log2 > kLazyLog2;  // true on the first block (m_run = -inf)
     if (j == 0) {
@@ -232,9 +242,11 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
       tmem_st16(tS + lane_addr + c0 * 32 + 32, ph_);
       if (NSPLIT == 2) tmem_st16(tS + lane_addr + c0 * 32 + 48, pl_);
     }
+    MTT_TR();  // 4: exp / pack done, stores issued
     tmem_st_wait();
     tc_fence_before();
     __syncthreads();
+    MTT_TR();  // 5: P visible to the issuer
 
     if (tid == 0) {
       tc_fence_after();
@@ -254,12 +266,15 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
         }
       }
       umma_commit(bar_o);
+      MTT_TR();  // 6 (thread 0): PV issued
       if (j + 1 < nkv) {
         issue_s(j + 1);          // queued right behind PV_j
+        MTT_TR();  // 7 (thread 0): next S issued
         mbar_wait(bar_o, ph);    // PV_j retired: the V buffer is free, prefetch the next value block
         mbar_arrive_expect_tx(bar_v, NSPLIT * kAttnTile);
         tma_load_3d(sV, &tm_hi, bar_v, 2 * C + h * 64, (j + 1) * 128, b);
         if (NSPLIT == 2) tma_load_3d(sV + kAttnTile, &tm_lo, bar_v, 2 * C + h * 64, (j + 1) * 128, b);
+        MTT_TR();  // 8 (thread 0): PV retired, V prefetched
       }
     }
     __syncwarp();
@@ -318,10 +333,14 @@ static int launch_attn(const CUtensorMap& mh, const CUtensorMap& ml, const AttnP
 
 namespace mtt {
 int launch_attention2(const mtt_attn_desc* d, cudaStream_t stream);  // attention2_tc.cu
+static unsigned long long* g_attn_trace = nullptr;
 static int g_attn_variant = -1;  // -1: read MTT_ATTN_VARIANT once; 0/2 = pipelined kernel (default), 1 = simple kernel
 }  // namespace mtt
 
 extern "C" void mtt_set_attention_variant(int v) { mtt::g_attn_variant = v; }
+/* debug only (not in the public header): device buffer of 768 u64 receiving a clock64 timeline of the
+ * simple kernel (variant 1), CTA (1,0,0), threads 0 / 40 / 200; NULL switches it off. */
+extern "C" void mtt_debug_set_attn_trace(void* dev_buf) { mtt::g_attn_trace = static_cast<unsigned long long*>(dev_buf); }
 
 extern "C" int mtt_attention(const mtt_attn_desc* d, mtt_stream_t stream_) {
   using namespace mtt;
@@ -361,6 +380,7 @@ extern "C" int mtt_attention(const mtt_attn_desc* d, mtt_stream_t stream_) {
   p.out_hi = static_cast<__nv_bfloat16*>(d->out_hi);
   p.out_lo = static_cast<__nv_bfloat16*>(d->out_lo);
   p.prompt_logits = d->prompt_logits;
+  p.trace = g_attn_trace;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   return d->nsplit == 2 ? launch_attn<2>(mh, ml, p, stream) : launch_attn<1>(mh, ml, p, stream);
 }
