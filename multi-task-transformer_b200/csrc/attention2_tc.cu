@@ -88,7 +88,9 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmq_hi, const __grid_const
 
   if (warp == kA2SoftmaxThreads / 32) {
     // ============================================================ issuer warp: TMA + tcgen05.mma
-    if (lane == 0) {
+    // one ELECTED lane (not `lane == 0`): ptxas then keeps the MMA / TMA operands in uniform registers instead
+    // of wrapping every UTCHMMA in an ELECT / R2UR / BRA.U.ANY loop (~100 cycles per instruction)
+    if (elect_one()) {
       tma_prefetch_desc(&tmq_hi);
       tma_prefetch_desc(&tmkv_hi);
       auto load_k = [&](int j) {

@@ -99,7 +99,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
   int trn = 0;
 #define MTT_TR() do { if (traced && trn < 256) tr[trn++] = clock64(); } while (0)
 
-  if (tid == 0) {
+  if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&tm_hi);
     if (NSPLIT == 2) tma_prefetch_desc(&tm_lo);
     mbar_init(bar_q, 1);
@@ -119,7 +119,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
   const uint32_t tO = tmem_base + 128;  // O_blk:  columns [128, 192)
   const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
 
-  if (tid == 0) {
+  if (warp == 0 && elect_one()) {
     mbar_arrive_expect_tx(bar_q, NSPLIT * kAttnTile);
     tma_load_3d(sQ, &tm_hi, bar_q, h * 64, q0, b);
     if (NSPLIT == 2) tma_load_3d(sQ + kAttnTile, &tm_lo, bar_q, h * 64, q0, b);
@@ -170,16 +170,18 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
     const uint32_t ph = j & 1;
     const int kn = min(128, p.N - j * 128);  // valid keys in this block
     const int kn16 = (kn + 15) & ~15;        // MMA N (S) / K extent (PV)
-    if (tid == 0 && j == 0) {
-      mbar_wait(bar_q, 0);
-      issue_s(0);
+    if (warp == 0 && j == 0) {
+      if (elect_one()) {
+        mbar_wait(bar_q, 0);
+        issue_s(0);
+      }
     }
     __syncwarp();
     MTT_TR();  // 0: iteration top
     mbar_wait(bar_s, ph);
     tc_fence_after();
     MTT_TR();  // 1: S ready
-    if (tid == 0 && j + 1 < nkv) {  // K buffer is free again: prefetch the next key block
+    if (warp == 0 && j + 1 < nkv && elect_one()) {  // K buffer is free again: prefetch the next key block
       mbar_arrive_expect_tx(bar_k, NSPLIT * kAttnTile);
       tma_load_3d(sK, &tm_hi, bar_k, C + h * 64, (j + 1) * 128, b);
       if (NSPLIT == 2) tma_load_3d(sK + kAttnTile, &tm_lo, bar_k, C + h * 64, (j + 1) * 128, b);
@@ -248,7 +250,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
     __syncthreads();
     MTT_TR();  // 5: P visible to the issuer
 
-    if (tid == 0) {
+    if (warp == 0 && elect_one()) {
       tc_fence_after();
       mbar_wait(bar_v, ph);
       tc_fence_after();

@@ -80,7 +80,8 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (both CTAs)
-    if (lane == 0) {
+    // warp-uniform loop, one ELECTED lane issues (see gemm_tc.cu: `if (lane == 0)` costs ~100 cycles/instr)
+    {
       int stage = 0;
       uint32_t phase = 0;
       const uint32_t stage_tx = 2 * NSPLIT * (p.a_box_bytes + kBTile);  // both CTAs' bytes
@@ -95,15 +96,18 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
           uint8_t* sb = sa + NSPLIT * kTileBytes;
-          if (p.debug & 1) {  // profiling aid: no loads, the MMAs run on whatever is in shared memory
-            if (leader) mbar_arrive(&full_bar[stage]);
-          } else {
-            if (leader) mbar_arrive_expect_tx(&full_bar[stage], stage_tx);
-            load_a_tile<NSPLIT, 1>(p, &tmA_hi, &tmA_lo, sa, &full_bar[stage], ms, kb, dy, dx);
-            const int kcoord = tap * p.cin_pad + kb * BK;
-            tma_load_2d_cg2(sb, &tmB_hi, &full_bar[stage], kcoord, nrow);
-            if (NSPLIT == 2) tma_load_2d_cg2(sb + kBTile, &tmB_lo, &full_bar[stage], kcoord, nrow);
+          if (elect_one()) {
+            if (p.debug & 1) {  // profiling aid: no loads, the MMAs run on whatever is in shared memory
+              if (leader) mbar_arrive(&full_bar[stage]);
+            } else {
+              if (leader) mbar_arrive_expect_tx(&full_bar[stage], stage_tx);
+              load_a_tile<NSPLIT, 1>(p, &tmA_hi, &tmA_lo, sa, &full_bar[stage], ms, kb, dy, dx);
+              const int kcoord = tap * p.cin_pad + kb * BK;
+              tma_load_2d_cg2(sb, &tmB_hi, &full_bar[stage], kcoord, nrow);
+              if (NSPLIT == 2) tma_load_2d_cg2(sb + kBTile, &tmB_lo, &full_bar[stage], kcoord, nrow);
+            }
           }
+          __syncwarp();
           if (++stage == ST) {
             stage = 0;
             phase ^= 1;
@@ -112,8 +116,8 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer (leader only)
-    if (leader && lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA only; elected lane)
+    if (leader) {
       constexpr uint32_t idesc = umma_idesc_bf16(256, BN2, 0);
       int stage = 0;
       uint32_t phase = 0;
@@ -130,26 +134,30 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
           tc_fence_after();
           const uint32_t a_hi = smem_u32(smem + stage * Cfg::kStageBytes);
           const uint32_t b_hi = a_hi + NSPLIT * kTileBytes;
+          if (elect_one()) {
 #pragma unroll
-          for (int ks = 0; ks < BK / 16; ++ks) {
-            const uint64_t adh = umma_desc_sw128(a_hi + ks * 32);
-            const uint64_t bdh = umma_desc_sw128(b_hi + ks * 32);
-            umma_ss_cg2(tacc, adh, bdh, idesc, accum);
-            accum = 1;
-            if (NSPLIT == 2) {
-              const uint64_t adl = umma_desc_sw128(a_hi + kTileBytes + ks * 32);
-              const uint64_t bdl = umma_desc_sw128(b_hi + kBTile + ks * 32);
-              umma_ss_cg2(tacc, adh, bdl, idesc, 1);
-              umma_ss_cg2(tacc, adl, bdh, idesc, 1);
+            for (int ks = 0; ks < BK / 16; ++ks) {
+              const uint64_t adh = umma_desc_sw128(a_hi + ks * 32);
+              const uint64_t bdh = umma_desc_sw128(b_hi + ks * 32);
+              umma_ss_cg2(tacc, adh, bdh, idesc, (ks > 0) ? 1u : accum);
+              if (NSPLIT == 2) {
+                const uint64_t adl = umma_desc_sw128(a_hi + kTileBytes + ks * 32);
+                const uint64_t bdl = umma_desc_sw128(b_hi + kBTile + ks * 32);
+                umma_ss_cg2(tacc, adh, bdl, idesc, 1);
+                umma_ss_cg2(tacc, adl, bdh, idesc, 1);
+              }
             }
+            umma_commit_cg2(&empty_bar[stage]);  // frees the smem slot in both CTAs
           }
-          umma_commit_cg2(&empty_bar[stage]);  // frees the smem slot in both CTAs
+          __syncwarp();
+          accum = 1;
           if (++stage == ST) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit_cg2(&tfull_bar[as]);  // accumulator complete, both CTAs
+        if (elect_one()) umma_commit_cg2(&tfull_bar[as]);  // accumulator complete, both CTAs
+        __syncwarp();
       }
     }
   } else {

@@ -76,7 +76,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    // The whole warp runs the (warp-uniform) loop and ONE ELECTED lane issues: with `if (lane == 0)` ptxas
+    // cannot prove the operands uniform and wraps every UTMALDG / UTCHMMA in an ELECT / R2UR / BRA.U.ANY
+    // uniformisation loop (~100 cycles per instruction, measured with clock64 in the attention kernel).
+    {
       int stage = 0;
       uint32_t phase = 0;
       const uint32_t stage_tx = NSPLIT * (p.a_box_bytes + kTileBytes);
@@ -90,15 +93,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
           uint8_t* sb = sa + NSPLIT * kTileBytes;
-          if (p.debug & 1) {  // profiling aid: no loads
-            mbar_arrive(&full_bar[stage]);
-          } else {
-            mbar_arrive_expect_tx(&full_bar[stage], stage_tx);
-            load_a_tile<NSPLIT, 0>(p, &tmA_hi, &tmA_lo, sa, &full_bar[stage], mt, kb, dy, dx);
-            const int kcoord = tap * p.cin_pad + kb * BK;
-            tma_load_2d(sb, &tmB_hi, &full_bar[stage], kcoord, nt * BN);
-            if (NSPLIT == 2) tma_load_2d(sb + kTileBytes, &tmB_lo, &full_bar[stage], kcoord, nt * BN);
+          if (elect_one()) {
+            if (p.debug & 1) {  // profiling aid: no loads
+              mbar_arrive(&full_bar[stage]);
+            } else {
+              mbar_arrive_expect_tx(&full_bar[stage], stage_tx);
+              load_a_tile<NSPLIT, 0>(p, &tmA_hi, &tmA_lo, sa, &full_bar[stage], mt, kb, dy, dx);
+              const int kcoord = tap * p.cin_pad + kb * BK;
+              tma_load_2d(sb, &tmB_hi, &full_bar[stage], kcoord, nt * BN);
+              if (NSPLIT == 2) tma_load_2d(sb + kTileBytes, &tmB_lo, &full_bar[stage], kcoord, nt * BN);
+            }
           }
+          __syncwarp();
           if (++stage == ST) {
             stage = 0;
             phase ^= 1;
@@ -107,8 +113,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer (warp-uniform loop, elected lane issues)
+    {
       constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, 0);
       int stage = 0;
       uint32_t phase = 0;
@@ -125,26 +131,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           tc_fence_after();
           const uint32_t a_hi = smem_u32(smem + stage * Cfg::kStageBytes);
           const uint32_t b_hi = a_hi + NSPLIT * kTileBytes;
+          if (elect_one()) {
 #pragma unroll
-          for (int ks = 0; ks < BK / 16; ++ks) {
-            const uint64_t adh = umma_desc_sw128(a_hi + ks * 32);
-            const uint64_t bdh = umma_desc_sw128(b_hi + ks * 32);
-            umma_ss(tacc, adh, bdh, idesc, accum);
-            accum = 1;
-            if (NSPLIT == 2) {
-              const uint64_t adl = umma_desc_sw128(a_hi + kTileBytes + ks * 32);
-              const uint64_t bdl = umma_desc_sw128(b_hi + kTileBytes + ks * 32);
-              umma_ss(tacc, adh, bdl, idesc, 1);
-              umma_ss(tacc, adl, bdh, idesc, 1);
+            for (int ks = 0; ks < BK / 16; ++ks) {
+              const uint64_t adh = umma_desc_sw128(a_hi + ks * 32);
+              const uint64_t bdh = umma_desc_sw128(b_hi + ks * 32);
+              umma_ss(tacc, adh, bdh, idesc, (ks > 0) ? 1u : accum);
+              if (NSPLIT == 2) {
+                const uint64_t adl = umma_desc_sw128(a_hi + kTileBytes + ks * 32);
+                const uint64_t bdl = umma_desc_sw128(b_hi + kTileBytes + ks * 32);
+                umma_ss(tacc, adh, bdl, idesc, 1);
+                umma_ss(tacc, adl, bdh, idesc, 1);
+              }
             }
+            umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+          __syncwarp();
+          accum = 1;
           if (++stage == ST) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tfull_bar[as]);  // accumulator complete
+        if (elect_one()) umma_commit(&tfull_bar[as]);  // accumulator complete
+        __syncwarp();
       }
     }
   } else {
