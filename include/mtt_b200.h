@@ -130,8 +130,8 @@ typedef struct {
 } mtt_attn_desc;
 
 int mtt_attention(const mtt_attn_desc* d, mtt_stream_t stream);
-/* 0 / 2 = software-pipelined kernel (default; also env MTT_ATTN_VARIANT), 1 = the simpler predecessor.
- * Same function; tuning / testing knob. */
+/* 0 / 1 = persistent kernel (default; also env MTT_ATTN_VARIANT), 2 = double-buffered-S variant with a
+ * dedicated issuer warp. Same function; tuning / testing knob. */
 void mtt_set_attention_variant(int variant);
 
 /* ---- patch embedding im2col ---------------------------------------------------------------

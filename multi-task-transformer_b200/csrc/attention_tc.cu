@@ -34,7 +34,6 @@ struct AttnParams {
   __nv_bfloat16* out_hi;
   __nv_bfloat16* out_lo;
   float* prompt_logits;
-  unsigned long long* trace;  // debug: clock64 timeline of CTA (1,0,0), threads 0 / 40 / 200 (NULL = off)
 };
 
 // row maximum of one 32-column chunk (FULL: every column is a valid key)
@@ -89,15 +88,12 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
   const int warp = tid >> 5;
   const int half = warp >> 2;              // which 64 key columns / 32 output columns this thread owns
   const int row = (warp & 3) * 32 + (tid & 31);
-  const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int C = p.H * 64;
-  const int q0 = qt * 128;
-  const int nkv = (p.N + 127) / 128;
-  const bool traced = p.trace != nullptr && blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0 &&
-                      (tid == 0 || tid == 40 || tid == 200);
-  unsigned long long* tr = traced ? p.trace + (tid == 0 ? 0 : (tid == 40 ? 256 : 512)) : nullptr;
-  int trn = 0;
-#define MTT_TR() do { if (traced && trn < 256) tr[trn++] = clock64(); } while (0)
+  const int nq = (p.N + 127) / 128;        // query tiles per (b, h)
+  const int nkv = nq;                      // key blocks per (b, h)
+  const int total = nq * p.H * p.B;        // work items; PERSISTENT: item = blockIdx.x, + gridDim.x, ...
+  // (measured with %globaltimer: ~7 us of every 28 us non-persistent CTA was prologue / epilogue -- barrier
+  //  init, TMEM allocation, first-load latency -- so CTAs now stay resident and walk the item list)
 
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&tm_hi);
@@ -116,39 +112,41 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tS = tmem_base;        // S / P: columns [0, 128)
-  const uint32_t tO = tmem_base + 128;  // O_blk:  columns [128, 192)
+  const uint32_t tO = tmem_base + 128;  // O:      columns [128, 192)
   const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
 
-  if (warp == 0 && elect_one()) {
+  // ---- issuer-side helpers (executed by ONE elected lane of warp 0; see gemm_tc.cu on why elected) ----
+  auto item_coords = [&](int item, int& qt, int& h, int& b) {
+    qt = item % nq;
+    h = (item / nq) % p.H;
+    b = item / (nq * p.H);
+  };
+  auto load_q = [&](int item) {
+    int qt, h, b;
+    item_coords(item, qt, h, b);
     mbar_arrive_expect_tx(bar_q, NSPLIT * kAttnTile);
-    tma_load_3d(sQ, &tm_hi, bar_q, h * 64, q0, b);
-    if (NSPLIT == 2) tma_load_3d(sQ + kAttnTile, &tm_lo, bar_q, h * 64, q0, b);
+    tma_load_3d(sQ, &tm_hi, bar_q, h * 64, qt * 128, b);
+    if (NSPLIT == 2) tma_load_3d(sQ + kAttnTile, &tm_lo, bar_q, h * 64, qt * 128, b);
+  };
+  auto load_k = [&](int item, int j) {
+    int qt, h, b;
+    item_coords(item, qt, h, b);
     mbar_arrive_expect_tx(bar_k, NSPLIT * kAttnTile);
-    tma_load_3d(sK, &tm_hi, bar_k, C + h * 64, 0, b);
-    if (NSPLIT == 2) tma_load_3d(sK + kAttnTile, &tm_lo, bar_k, C + h * 64, 0, b);
+    tma_load_3d(sK, &tm_hi, bar_k, C + h * 64, j * 128, b);
+    if (NSPLIT == 2) tma_load_3d(sK + kAttnTile, &tm_lo, bar_k, C + h * 64, j * 128, b);
+  };
+  auto load_v = [&](int item, int j) {
+    int qt, h, b;
+    item_coords(item, qt, h, b);
     mbar_arrive_expect_tx(bar_v, NSPLIT * kAttnTile);
-    tma_load_3d(sV, &tm_hi, bar_v, 2 * C + h * 64, 0, b);
-    if (NSPLIT == 2) tma_load_3d(sV + kAttnTile, &tm_lo, bar_v, 2 * C + h * 64, 0, b);
-  }
-  __syncwarp();
-
-  // Online softmax with the output accumulator kept in TMEM across key blocks and LAZY rescaling: the
-  // running maximum m_run only moves (and O / l are only rescaled) when a block's maximum exceeds it by
-  // more than 2^kLazyLog2 after scaling, so P stays below 2^kLazyLog2 and the TMEM round trip of O is rare.
-  constexpr float kLazyLog2 = 8.0f;
-  float m_run = -INFINITY, l_run = 0.f;
-  const int q_row = q0 + row;
-  const bool export_row = (p.prompt_logits != nullptr) && (q_row < p.T);
-  float* export_ptr =
-      export_row ? p.prompt_logits + (((long long)b * p.H + h) * p.T + q_row) * p.N : nullptr;
-
-  // S_j = Q K_j^T into TMEM (thread 0 only). Besides the first block it is issued right behind PV_{j-1}:
-  // the tensor pipe executes in issue order, so S_j cannot overwrite P_{j-1} before PV_{j-1} has read it,
-  // and no PV-complete -> wake-up -> issue round trip sits on the critical path.
-  auto issue_s = [&](int jj) {
-    mbar_wait(bar_k, jj & 1);
+    tma_load_3d(sV, &tm_hi, bar_v, 2 * C + h * 64, j * 128, b);
+    if (NSPLIT == 2) tma_load_3d(sV + kAttnTile, &tm_lo, bar_v, 2 * C + h * 64, j * 128, b);
+  };
+  // S = Q K_j^T into TMEM; g = running key-block count of this CTA (barrier phase)
+  auto issue_s = [&](int j, uint32_t g) {
+    mbar_wait(bar_k, g & 1);
     tc_fence_after();
-    const int knj = min(128, p.N - jj * 128);
+    const int knj = min(128, p.N - j * 128);
     const uint32_t idesc_s = umma_idesc_bf16(128, (knj + 15) & ~15, 0);
     const uint32_t qh = smem_u32(sQ), kh = smem_u32(sK);
 #pragma unroll
@@ -166,143 +164,163 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
     umma_commit(bar_s);
   };
 
-  for (int j = 0; j < nkv; ++j) {
-    const uint32_t ph = j & 1;
-    const int kn = min(128, p.N - j * 128);  // valid keys in this block
-    const int kn16 = (kn + 15) & ~15;        // MMA N (S) / K extent (PV)
-    if (warp == 0 && j == 0) {
-      if (elect_one()) {
-        mbar_wait(bar_q, 0);
-        issue_s(0);
-      }
-    }
-    __syncwarp();
-    MTT_TR();  // 0: iteration top
-    mbar_wait(bar_s, ph);
-    tc_fence_after();
-    MTT_TR();  // 1: S ready
-    if (warp == 0 && j + 1 < nkv && elect_one()) {  // K buffer is free again: prefetch the next key block
-      mbar_arrive_expect_tx(bar_k, NSPLIT * kAttnTile);
-      tma_load_3d(sK, &tm_hi, bar_k, C + h * 64, (j + 1) * 128, b);
-      if (NSPLIT == 2) tma_load_3d(sK + kAttnTile, &tm_lo, bar_k, C + h * 64, (j + 1) * 128, b);
-    }
-    __syncwarp();
+  const int first = blockIdx.x;
+  if (first < total && warp == 0 && elect_one()) {
+    load_q(first);
+    load_k(first, 0);
+    load_v(first, 0);
+    mbar_wait(bar_q, 0);
+    issue_s(0, 0);
+  }
+  __syncwarp();
 
-    // ---- S (this thread's 64 columns) is read from TMEM ONCE and stays in registers
-    const int nchunk = (kn16 + 31) >> 5;
-    const bool full = kn == 128;
-    const int c0 = half * 2;
-    uint32_t s0[32], s1[32];
-    const bool have0 = c0 < nchunk, have1 = c0 + 1 < nchunk;
-    if (have0) tmem_ld32(tS + lane_addr + c0 * 32, s0);
-    if (have1) tmem_ld32(tS + lane_addr + (c0 + 1) * 32, s1);
-    tmem_ld_wait();
-    MTT_TR();  // 2: S in registers
-    float mx = -INFINITY;
-    if (have0) mx = full ? chunk_max<true>(s0, c0 * 32, kn, mx) : chunk_max<false>(s0, c0 * 32, kn, mx);
-    if (have1) mx = full ? chunk_max<true>(s1, c0 * 32 + 32, kn, mx) : chunk_max<false>(s1, c0 * 32 + 32, kn, mx);
-    if (export_row) {
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        if (have0 && c0 * 32 + i < kn) export_ptr[j * 128 + c0 * 32 + i] = __uint_as_float(s0[i]);
-        if (have1 && c0 * 32 + 32 + i < kn) export_ptr[j * 128 + c0 * 32 + 32 + i] = __uint_as_float(s1[i]);
-      }
-    }
-    xch[half * 128 + row] = mx;
-    __syncthreads();
-    mx = fmaxf(xch[row], xch[128 + row]);
-    MTT_TR();  // 3: row max exchanged
-    // ---- lazy rescale of the TMEM accumulator (both threads of a row take the same decision)
-    const bool need = (mx - m_run) * p.scale_log2 > kLazyLog2;  // true on the first block (m_run = -inf)
-    if (j == 0) {
-      m_run = mx;
-    } else if (__any_sync(0xffffffffu, need)) {
-      const float alpha = need ? ex2_approx((m_run - mx) * p.scale_log2) : 1.0f;
-      uint32_t o[32];
-      tmem_ld32(tO + lane_addr + half * 32, o);
-      tmem_ld_wait();
-#pragma unroll
-      for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-      tmem_st32(tO + lane_addr + half * 32, o);
-      l_run *= alpha;
-      if (need) m_run = mx;
-    }
-    const float mb = m_run * p.scale_log2;
+  constexpr float kLazyLog2 = 8.0f;  // lazy rescaling threshold (see below)
+  uint32_t g = 0;                    // key blocks processed by this CTA: phase of bar_k / bar_v / bar_s / bar_o
+  uint32_t qn = 0;                   // items processed by this CTA: phase of bar_q
+  for (int item = first; item < total; item += gridDim.x, ++qn) {
+    int qt, h, b;
+    item_coords(item, qt, h, b);
+    const int next = item + gridDim.x;
+    const int q_row = qt * 128 + row;
+    const bool export_row = (p.prompt_logits != nullptr) && (q_row < p.T);
+    float* export_ptr =
+        export_row ? p.prompt_logits + (((long long)b * p.H + h) * p.T + q_row) * p.N : nullptr;
+    // Online softmax with O accumulated in TMEM across key blocks and LAZY rescaling: m_run only moves (and
+    // O / l are only rescaled) when a block's maximum exceeds it by more than 2^kLazyLog2 after scaling.
+    float m_run = -INFINITY, l_run = 0.f;
 
-    // ---- P = exp2(S*c - m*c), written in place as packed bf16 hi | lo (16 + 16 columns per chunk)
-    if (have0) {
-      uint32_t ph_[16], pl_[16];
-      l_run += full ? chunk_exp_pack<true>(s0, c0 * 32, kn, p.scale_log2, mb, ph_, pl_)
-                    : chunk_exp_pack<false>(s0, c0 * 32, kn, p.scale_log2, mb, ph_, pl_);
-      tmem_st16(tS + lane_addr + c0 * 32, ph_);
-      if (NSPLIT == 2) tmem_st16(tS + lane_addr + c0 * 32 + 16, pl_);
-    }
-    if (have1) {
-      uint32_t ph_[16], pl_[16];
-      l_run += full ? chunk_exp_pack<true>(s1, c0 * 32 + 32, kn, p.scale_log2, mb, ph_, pl_)
-                    : chunk_exp_pack<false>(s1, c0 * 32 + 32, kn, p.scale_log2, mb, ph_, pl_);
-      tmem_st16(tS + lane_addr + c0 * 32 + 32, ph_);
-      if (NSPLIT == 2) tmem_st16(tS + lane_addr + c0 * 32 + 48, pl_);
-    }
-    MTT_TR();  // 4: exp / pack done, stores issued
-    tmem_st_wait();
-    tc_fence_before();
-    __syncthreads();
-    MTT_TR();  // 5: P visible to the issuer
-
-    if (warp == 0 && elect_one()) {
+    for (int j = 0; j < nkv; ++j, ++g) {
+      const uint32_t ph = g & 1;
+      const int kn = min(128, p.N - j * 128);  // valid keys in this block
+      const int kn16 = (kn + 15) & ~15;        // MMA N (S) / K extent (PV)
+      const bool last = j + 1 == nkv;
+      mbar_wait(bar_s, ph);                    // S_j was queued behind the previous PV by the issuer
       tc_fence_after();
-      mbar_wait(bar_v, ph);
-      tc_fence_after();
-      constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, 1);
-      const uint32_t vh = smem_u32(sV);
-      const int ksteps = kn16 >> 4;
-      for (int ks = 0; ks < ksteps; ++ks) {
-        const uint32_t a_hi = tS + (ks >> 1) * 32 + (ks & 1) * 8;
-        const uint64_t vdh = umma_desc_sw128(vh + ks * 2048);
-        umma_ts(tO, a_hi, vdh, idesc_o, (j > 0 || ks > 0) ? 1u : 0u);
-        if (NSPLIT == 2) {
-          const uint64_t vdl = umma_desc_sw128(vh + kAttnTile + ks * 2048);
-          umma_ts(tO, a_hi, vdl, idesc_o, 1);
-          umma_ts(tO, a_hi + 16, vdh, idesc_o, 1);
+      if (warp == 0 && elect_one()) {          // S_j retired: its K block (and, after the last block, Q) is free
+        if (!last) {
+          load_k(item, j + 1);
+        } else if (next < total) {
+          load_q(next);
+          load_k(next, 0);
         }
       }
-      umma_commit(bar_o);
-      MTT_TR();  // 6 (thread 0): PV issued
-      if (j + 1 < nkv) {
-        issue_s(j + 1);          // queued right behind PV_j
-        MTT_TR();  // 7 (thread 0): next S issued
-        mbar_wait(bar_o, ph);    // PV_j retired: the V buffer is free, prefetch the next value block
-        mbar_arrive_expect_tx(bar_v, NSPLIT * kAttnTile);
-        tma_load_3d(sV, &tm_hi, bar_v, 2 * C + h * 64, (j + 1) * 128, b);
-        if (NSPLIT == 2) tma_load_3d(sV + kAttnTile, &tm_lo, bar_v, 2 * C + h * 64, (j + 1) * 128, b);
-        MTT_TR();  // 8 (thread 0): PV retired, V prefetched
-      }
-    }
-    __syncwarp();
-  }
-  mbar_wait(bar_o, (nkv - 1) & 1);  // last PV retired (every earlier one is ordered before the S that followed it)
-  tc_fence_after();
+      __syncwarp();
 
-  // ---- epilogue: O / l, where l is the sum of the two halves' partial row sums (same m_run)
-  uint32_t o[32];
-  tmem_ld32(tO + lane_addr + half * 32, o);
-  tmem_ld_wait();
-  __syncthreads();
-  xch[half * 128 + row] = l_run;
-  __syncthreads();
-  if (q_row < p.N) {
-    const float inv = 1.0f / (xch[row] + xch[128 + row]);
-    const long long off = ((long long)b * p.N + q_row) * C + h * 64 + half * 32;
+      // ---- S (this thread's 64 columns) is read from TMEM ONCE and stays in registers
+      const int nchunk = (kn16 + 31) >> 5;
+      const bool full = kn == 128;
+      const int c0 = half * 2;
+      uint32_t s0[32], s1[32];
+      const bool have0 = c0 < nchunk, have1 = c0 + 1 < nchunk;
+      if (have0) tmem_ld32(tS + lane_addr + c0 * 32, s0);
+      if (have1) tmem_ld32(tS + lane_addr + (c0 + 1) * 32, s1);
+      tmem_ld_wait();
+      float mx = -INFINITY;
+      if (have0) mx = full ? chunk_max<true>(s0, c0 * 32, kn, mx) : chunk_max<false>(s0, c0 * 32, kn, mx);
+      if (have1) mx = full ? chunk_max<true>(s1, c0 * 32 + 32, kn, mx) : chunk_max<false>(s1, c0 * 32 + 32, kn, mx);
+      if (export_row) {
 #pragma unroll
-    for (int i = 0; i < 32; i += 8) {
-      uint4 hv, lv;
-      split_pack2(__uint_as_float(o[i]) * inv, __uint_as_float(o[i + 1]) * inv, hv.x, lv.x);
-      split_pack2(__uint_as_float(o[i + 2]) * inv, __uint_as_float(o[i + 3]) * inv, hv.y, lv.y);
-      split_pack2(__uint_as_float(o[i + 4]) * inv, __uint_as_float(o[i + 5]) * inv, hv.z, lv.z);
-      split_pack2(__uint_as_float(o[i + 6]) * inv, __uint_as_float(o[i + 7]) * inv, hv.w, lv.w);
-      *reinterpret_cast<uint4*>(p.out_hi + off + i) = hv;
-      if (NSPLIT == 2) *reinterpret_cast<uint4*>(p.out_lo + off + i) = lv;
+        for (int i = 0; i < 32; ++i) {
+          if (have0 && c0 * 32 + i < kn) export_ptr[j * 128 + c0 * 32 + i] = __uint_as_float(s0[i]);
+          if (have1 && c0 * 32 + 32 + i < kn) export_ptr[j * 128 + c0 * 32 + 32 + i] = __uint_as_float(s1[i]);
+        }
+      }
+      xch[half * 128 + row] = mx;
+      __syncthreads();
+      mx = fmaxf(xch[row], xch[128 + row]);
+      // ---- lazy rescale of the TMEM accumulator (both threads of a row take the same decision)
+      const bool need = (mx - m_run) * p.scale_log2 > kLazyLog2;
+      if (j == 0) {
+        m_run = mx;
+      } else if (__any_sync(0xffffffffu, need)) {
+        const float alpha = need ? ex2_approx((m_run - mx) * p.scale_log2) : 1.0f;
+        uint32_t o[32];
+        tmem_ld32(tO + lane_addr + half * 32, o);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+        tmem_st32(tO + lane_addr + half * 32, o);
+        l_run *= alpha;
+        if (need) m_run = mx;
+      }
+      const float mb = m_run * p.scale_log2;
+
+      // ---- P = exp2(S*c - m*c), written in place as packed bf16 hi | lo (16 + 16 columns per chunk)
+      if (have0) {
+        uint32_t ph_[16], pl_[16];
+        l_run += full ? chunk_exp_pack<true>(s0, c0 * 32, kn, p.scale_log2, mb, ph_, pl_)
+                      : chunk_exp_pack<false>(s0, c0 * 32, kn, p.scale_log2, mb, ph_, pl_);
+        tmem_st16(tS + lane_addr + c0 * 32, ph_);
+        if (NSPLIT == 2) tmem_st16(tS + lane_addr + c0 * 32 + 16, pl_);
+      }
+      if (have1) {
+        uint32_t ph_[16], pl_[16];
+        l_run += full ? chunk_exp_pack<true>(s1, c0 * 32 + 32, kn, p.scale_log2, mb, ph_, pl_)
+                      : chunk_exp_pack<false>(s1, c0 * 32 + 32, kn, p.scale_log2, mb, ph_, pl_);
+        tmem_st16(tS + lane_addr + c0 * 32 + 32, ph_);
+        if (NSPLIT == 2) tmem_st16(tS + lane_addr + c0 * 32 + 48, pl_);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncthreads();
+
+      if (warp == 0 && elect_one()) {
+        tc_fence_after();
+        mbar_wait(bar_v, ph);
+        tc_fence_after();
+        constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, 1);
+        const uint32_t vh = smem_u32(sV);
+        const int ksteps = kn16 >> 4;
+        for (int ks = 0; ks < ksteps; ++ks) {
+          const uint32_t a_hi = tS + (ks >> 1) * 32 + (ks & 1) * 8;
+          const uint64_t vdh = umma_desc_sw128(vh + ks * 2048);
+          umma_ts(tO, a_hi, vdh, idesc_o, (j > 0 || ks > 0) ? 1u : 0u);
+          if (NSPLIT == 2) {
+            const uint64_t vdl = umma_desc_sw128(vh + kAttnTile + ks * 2048);
+            umma_ts(tO, a_hi, vdl, idesc_o, 1);
+            umma_ts(tO, a_hi + 16, vdh, idesc_o, 1);
+          }
+        }
+        umma_commit(bar_o);
+        // The next S (of this item or of the CTA's next item) is queued right behind PV_j: the tensor pipe
+        // executes in issue order, so it cannot overwrite P_j before PV_j has read it.
+        if (!last) {
+          issue_s(j + 1, g + 1);
+          mbar_wait(bar_o, ph);  // PV_j retired: the V buffer is free
+          load_v(item, j + 1);
+        } else if (next < total) {
+          mbar_wait(bar_q, (qn + 1) & 1);  // next item's Q (requested when S_last retired)
+          issue_s(0, g + 1);
+          mbar_wait(bar_o, ph);
+          load_v(next, 0);
+        }
+      }
+      __syncwarp();
+    }
+
+    // ---- item epilogue: O / l, where l is the sum of the two halves' partial row sums (same m_run).
+    // The next item's PV_0 (which overwrites O) is only issued after every thread has passed this point.
+    mbar_wait(bar_o, (g - 1) & 1);
+    tc_fence_after();
+    uint32_t o[32];
+    tmem_ld32(tO + lane_addr + half * 32, o);
+    tmem_ld_wait();
+    __syncthreads();
+    xch[half * 128 + row] = l_run;
+    __syncthreads();
+    if (q_row < p.N) {
+      const float inv = 1.0f / (xch[row] + xch[128 + row]);
+      const long long off = ((long long)b * p.N + q_row) * C + h * 64 + half * 32;
+#pragma unroll
+      for (int i = 0; i < 32; i += 8) {
+        uint4 hv, lv;
+        split_pack2(__uint_as_float(o[i]) * inv, __uint_as_float(o[i + 1]) * inv, hv.x, lv.x);
+        split_pack2(__uint_as_float(o[i + 2]) * inv, __uint_as_float(o[i + 3]) * inv, hv.y, lv.y);
+        split_pack2(__uint_as_float(o[i + 4]) * inv, __uint_as_float(o[i + 5]) * inv, hv.z, lv.z);
+        split_pack2(__uint_as_float(o[i + 6]) * inv, __uint_as_float(o[i + 7]) * inv, hv.w, lv.w);
+        *reinterpret_cast<uint4*>(p.out_hi + off + i) = hv;
+        if (NSPLIT == 2) *reinterpret_cast<uint4*>(p.out_lo + off + i) = lv;
+      }
     }
   }
 
@@ -326,8 +344,9 @@ static int launch_attn(const CUtensorMap& mh, const CUtensorMap& ml, const AttnP
       return set_error(MTT_ERR_LAUNCH, "attention: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  dim3 grid((p.N + 127) / 128, p.H, p.B);
-  attention_kernel<NSPLIT><<<grid, kAttnThreads, smem, stream>>>(mh, ml, p);
+  const int total = ((p.N + 127) / 128) * p.H * p.B;
+  const int slots = 2 * sm_count();  // two CTAs per SM (96 KB smem, 256 TMEM columns each)
+  attention_kernel<NSPLIT><<<total < slots ? total : slots, kAttnThreads, smem, stream>>>(mh, ml, p);
   return check_launch("mtt_attention");
 }
 
@@ -335,14 +354,11 @@ static int launch_attn(const CUtensorMap& mh, const CUtensorMap& ml, const AttnP
 
 namespace mtt {
 int launch_attention2(const mtt_attn_desc* d, cudaStream_t stream);  // attention2_tc.cu
-static unsigned long long* g_attn_trace = nullptr;
-static int g_attn_variant = -1;  // -1: read MTT_ATTN_VARIANT once; 0/2 = pipelined kernel (default), 1 = simple kernel
+static int g_attn_variant = -1;  // -1: read MTT_ATTN_VARIANT once; 0/1 = persistent kernel below (default, fastest
+                                 // measured), 2 = attention2_tc.cu (double-buffered S, dedicated issuer warp)
 }  // namespace mtt
 
 extern "C" void mtt_set_attention_variant(int v) { mtt::g_attn_variant = v; }
-/* debug only (not in the public header): device buffer of 768 u64 receiving a clock64 timeline of the
- * simple kernel (variant 1), CTA (1,0,0), threads 0 / 40 / 200; NULL switches it off. */
-extern "C" void mtt_debug_set_attn_trace(void* dev_buf) { mtt::g_attn_trace = static_cast<unsigned long long*>(dev_buf); }
 
 extern "C" int mtt_attention(const mtt_attn_desc* d, mtt_stream_t stream_) {
   using namespace mtt;
@@ -360,7 +376,7 @@ extern "C" int mtt_attention(const mtt_attn_desc* d, mtt_stream_t stream_) {
     const char* e = getenv("MTT_ATTN_VARIANT");
     g_attn_variant = e ? atoi(e) : 0;
   }
-  if (g_attn_variant != 1) return launch_attention2(d, static_cast<cudaStream_t>(stream_));
+  if (g_attn_variant == 2) return launch_attention2(d, static_cast<cudaStream_t>(stream_));
   const int C = d->H * 64;
   CUtensorMap mh, ml;
   const uint64_t dims[3] = {(uint64_t)3 * C, (uint64_t)d->N, (uint64_t)d->B};
@@ -382,7 +398,6 @@ extern "C" int mtt_attention(const mtt_attn_desc* d, mtt_stream_t stream_) {
   p.out_hi = static_cast<__nv_bfloat16*>(d->out_hi);
   p.out_lo = static_cast<__nv_bfloat16*>(d->out_lo);
   p.prompt_logits = d->prompt_logits;
-  p.trace = g_attn_trace;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   return d->nsplit == 2 ? launch_attn<2>(mh, ml, p, stream) : launch_attn<1>(mh, ml, p, stream);
 }

@@ -70,7 +70,7 @@ if __name__ == "__main__":
         bench_gemm(M, 1024, 4096, ns, res=True)
         bench_attn(4, 16, 1029, ns)
     bench_attn(1, 16, 8195, 2, T=3)
-    ops.set_attention_variant(1)
-    print("---- attention variant 1 (simple)")
+    ops.set_attention_variant(2)
+    print("---- attention variant 2 (double-buffered S)")
     bench_attn(4, 16, 1029, 2)
     bench_attn(4, 16, 1029, 1)

@@ -165,10 +165,10 @@ def test_conv(cuda_dev, ksize, dil, nsplit, gemm_variant):
         assert e < TOL[nsplit], f"conv {B,H,W,Cin,Cout} k{ksize} d{dil}: rel err {e}"
 
 
-@pytest.mark.parametrize("variant", [2, 1], ids=["pipelined", "simple"])
+@pytest.mark.parametrize("variant", [1, 2], ids=["persistent", "double_buffered_s"])
 @pytest.mark.parametrize("nsplit", [2, 1])
 @pytest.mark.parametrize("B,H,N,T", [(2, 3, 300, 4), (1, 2, 1029, 5), (1, 1, 128, 0), (2, 2, 65, 2), (1, 1, 64, 1),
-                                     (1, 2, 40, 3), (1, 1, 193, 0)])
+                                     (1, 2, 40, 3), (1, 1, 193, 0), (3, 16, 1029, 5)])
 def test_attention(cuda_dev, nsplit, B, H, N, T, variant):
     from mtt_b200 import ops
 
