@@ -146,28 +146,6 @@ int mtt_im2col_patch(const float* img, int32_t B, int32_t Cin, int32_t H, int32_
 int mtt_broadcast_rows(const float* src, float* dst, int32_t B, int32_t T, int32_t C,
                        int64_t group_rows, int64_t ld, mtt_stream_t stream);
 
-/* ---- skinny linear (<= 32 rows, fp32 weights) ----------------------------------------------
- * out[r, n] (+)= sum_k A[r, k] W[n, k] + bias[n]; A is either split planes (a_hi[, a_lo]) or fp32.
- * Row r of A lives at (r / a_in_group) * a_out_group + a_offset + r % a_in_group (a_in_group = 0:
- * identity); same for the output rows. Replaces token_trans / token_trans1 on the B*T prompt rows
- * (TP taskprompter.py:219, :250). */
-typedef struct {
-  const void* a_hi;
-  const void* a_lo;
-  const float* a_f32;
-  int64_t lda;
-  int32_t a_in_group, a_out_group, a_offset;
-  const float* w;
-  int64_t ldw;
-  const float* bias;
-  int32_t R, N, K;
-  float* out;
-  int64_t ldo;
-  int32_t o_in_group, o_out_group, o_offset;
-  int32_t accumulate;
-} mtt_skinny_desc;
-int mtt_skinny_linear(const mtt_skinny_desc* d, mtt_stream_t stream);
-
 /* Raw channel logits Rc[b,t,c,i,j] = sum_{pixel in window (i,j)} cp[b,t,pixel] * xn[b,pixel,c]
  * (TP taskprompter.py:236-240,246). cp fp32 [B,T,P]; xn = split LN1 output of the joint stream
  * [B*N, ldx] (patch rows start at T); out fp32 [B,T,C,nh,nw]. */

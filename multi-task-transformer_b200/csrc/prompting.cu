@@ -1,5 +1,5 @@
-// HBM-bound kernels around the GEMMs: patch im2col, prompt broadcast, the channel-prompt path
-// (skinny linears + windowed channel logits), spatial/channel gating, cross-task reweighting and
+// HBM-bound kernels around the GEMMs: patch im2col, prompt broadcast, the windowed channel-prompt
+// logits (token_trans / token_trans1 themselves run on the tcgen05 GEMM with gathered A rows), spatial/channel gating, cross-task reweighting and
 // bilinear resampling.  All are coalesced along the channel (innermost NHWC / token-major) axis,
 // float4 / bf16x2 vectorised where the layout allows, with grids sized by the data (>= several
 // waves of 148 SMs at the benchmark shapes).
@@ -40,75 +40,6 @@ __global__ void broadcast_rows_kernel(const float* __restrict__ src, float* __re
   const int t = (int)((i / C) % T);
   const int b = (int)(i / ((long long)C * T));
   dst[((long long)b * group + t) * ld + c] = src[(long long)t * C + c];
-}
-
-// ------------------------------------------------------------------------------------------------
-// Skinny linear: out[r, n] (+)= sum_k A[r, k] * W[n, k] + bias[n], R <= 32 rows, fp32 weights read
-// once.  reference: token_trans / token_trans1 at taskprompter.py:219,250 (M = B*T prompt rows).
-struct SkinnyParams {
-  const __nv_bfloat16* a_hi;
-  const __nv_bfloat16* a_lo;
-  const float* a_f32;
-  long long lda;
-  int a_in, a_out, a_off;
-  const float* w;
-  long long ldw;
-  const float* bias;
-  int R, N, K, kc;
-  float* out;
-  long long ldo;
-  int o_in, o_out, o_off, accumulate;
-};
-
-template <int RMAX>
-__global__ void __launch_bounds__(256) skinny_linear_kernel(const SkinnyParams p) {
-  extern __shared__ float sA[];  // [R][kc]
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nwarps = blockDim.x >> 5;
-  const int n = blockIdx.x * nwarps + warp;
-  float acc[RMAX];
-#pragma unroll
-  for (int r = 0; r < RMAX; ++r) acc[r] = 0.f;
-  for (int k0 = 0; k0 < p.K; k0 += p.kc) {
-    const int kc = min(p.kc, p.K - k0);
-    __syncthreads();
-    for (int i = threadIdx.x; i < p.R * kc; i += blockDim.x) {
-      const int r = i / kc, k = i % kc;
-      const long long ar = (p.a_in > 0) ? ((long long)(r / p.a_in) * p.a_out + p.a_off + r % p.a_in) : r;
-      float v;
-      if (p.a_f32) {
-        v = p.a_f32[ar * p.lda + k0 + k];
-      } else {
-        v = __bfloat162float(p.a_hi[ar * p.lda + k0 + k]);
-        if (p.a_lo) v += __bfloat162float(p.a_lo[ar * p.lda + k0 + k]);
-      }
-      sA[r * p.kc + k] = v;
-    }
-    __syncthreads();
-    if (n < p.N) {
-      const float* wr = p.w + (long long)n * p.ldw + k0;
-      for (int k = lane; k < kc; k += 32) {
-        const float wv = __ldg(wr + k);
-#pragma unroll
-        for (int r = 0; r < RMAX; ++r)
-          if (r < p.R) acc[r] = fmaf(wv, sA[r * p.kc + k], acc[r]);
-      }
-    }
-  }
-  if (n >= p.N) return;
-#pragma unroll
-  for (int r = 0; r < RMAX; ++r) {
-    if (r >= p.R) break;
-    float v = acc[r];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (lane == 0) {
-      if (p.bias) v += p.bias[n];
-      const long long orow = (p.o_in > 0) ? ((long long)(r / p.o_in) * p.o_out + p.o_off + r % p.o_in) : r;
-      float* dst = p.out + orow * p.ldo + n;
-      *dst = p.accumulate ? (*dst + v) : v;
-    }
-  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -358,47 +289,6 @@ extern "C" int mtt_broadcast_rows(const float* src, float* dst, int32_t B, int32
   broadcast_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, STREAM>>>(src, dst, B, T, C, group_rows,
                                                                             ld);
   return check_launch("mtt_broadcast_rows");
-}
-
-extern "C" int mtt_skinny_linear(const mtt_skinny_desc* d, mtt_stream_t stream) {
-  if (!d || d->R <= 0 || d->R > 32 || d->N <= 0 || d->K <= 0 || !d->w || !d->out ||
-      (!d->a_hi && !d->a_f32))
-    return set_error(MTT_ERR_BAD_SHAPE, "mtt_skinny_linear: bad arguments (R=%d N=%d K=%d)",
-                     d ? d->R : -1, d ? d->N : -1, d ? d->K : -1);
-  SkinnyParams p;
-  p.a_hi = static_cast<const __nv_bfloat16*>(d->a_hi);
-  p.a_lo = static_cast<const __nv_bfloat16*>(d->a_lo);
-  p.a_f32 = d->a_f32;
-  p.lda = d->lda;
-  p.a_in = d->a_in_group;
-  p.a_out = d->a_out_group;
-  p.a_off = d->a_offset;
-  p.w = d->w;
-  p.ldw = d->ldw;
-  p.bias = d->bias;
-  p.R = d->R;
-  p.N = d->N;
-  p.K = d->K;
-  int kc = (48 * 1024 / 4) / d->R;  // A chunk of <= 48 KB in shared memory
-  kc &= ~31;
-  if (kc > d->K) kc = (d->K + 31) & ~31;
-  p.kc = kc;
-  p.out = d->out;
-  p.ldo = d->ldo;
-  p.o_in = d->o_in_group;
-  p.o_out = d->o_out_group;
-  p.o_off = d->o_offset;
-  p.accumulate = d->accumulate;
-  const int nwarps = 8;
-  const size_t smem = (size_t)d->R * kc * sizeof(float);
-  const unsigned grid = (d->N + nwarps - 1) / nwarps;
-  if (d->R <= 8)
-    skinny_linear_kernel<8><<<grid, nwarps * 32, smem, STREAM>>>(p);
-  else if (d->R <= 16)
-    skinny_linear_kernel<16><<<grid, nwarps * 32, smem, STREAM>>>(p);
-  else
-    skinny_linear_kernel<32><<<grid, nwarps * 32, smem, STREAM>>>(p);
-  return check_launch("mtt_skinny_linear");
 }
 
 extern "C" int mtt_chan_logits(const float* cp, const void* xn_hi, const void* xn_lo, int64_t ldx,

@@ -37,18 +37,6 @@ class AttnDesc(C.Structure):
     ]
 
 
-class SkinnyDesc(C.Structure):
-    _fields_ = [
-        ("a_hi", C.c_void_p), ("a_lo", C.c_void_p), ("a_f32", C.c_void_p), ("lda", C.c_int64),
-        ("a_in_group", C.c_int32), ("a_out_group", C.c_int32), ("a_offset", C.c_int32),
-        ("w", C.c_void_p), ("ldw", C.c_int64), ("bias", C.c_void_p),
-        ("R", C.c_int32), ("N", C.c_int32), ("K", C.c_int32),
-        ("out", C.c_void_p), ("ldo", C.c_int64),
-        ("o_in_group", C.c_int32), ("o_out_group", C.c_int32), ("o_offset", C.c_int32),
-        ("accumulate", C.c_int32),
-    ]
-
-
 class InvptAttnDesc(C.Structure):
     _fields_ = [
         ("q", C.c_void_p), ("k", C.c_void_p), ("v", C.c_void_p), ("ldq", C.c_int64), ("ldk", C.c_int64),
@@ -75,7 +63,6 @@ SYMBOLS = {
     "mtt_set_attention_variant": (None, [C.c_int]),
     "mtt_im2col_patch": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _i64, _vp]),
     "mtt_broadcast_rows": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i64, _i64, _vp]),
-    "mtt_skinny_linear": (C.c_int, [C.POINTER(SkinnyDesc), _vp]),
     "mtt_chan_logits": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
     "mtt_gate_split": (C.c_int, [_vp, _i64, _i64, _i64, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32,
                                  _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i64, _vp]),

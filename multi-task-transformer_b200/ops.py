@@ -181,32 +181,6 @@ def broadcast_rows(src, dst, B, group_rows):
     _L.check(rc, "mtt_broadcast_rows")
 
 
-def skinny_linear(w, bias, out, *, R, a_split=None, a_f32=None, a_map=None, o_map=None, accumulate=False,
-                  K=None, a_row_base=0, o_row_base=0):
-    """out[r, :] (+)= A[r, :] @ w^T + bias for R <= 32 rows; w fp32 [N, K]."""
-    d = _L.SkinnyDesc()
-    if a_split is not None:
-        d.a_hi = a_split.hi.data_ptr() + 2 * a_row_base * a_split.ld
-        d.a_lo = (a_split.lo.data_ptr() + 2 * a_row_base * a_split.ld) if a_split.nsplit == 2 else 0
-        d.lda = a_split.ld
-    else:
-        assert a_f32.dtype == torch.float32 and a_f32.stride(-1) == 1
-        d.a_f32, d.lda = a_f32.data_ptr() + 4 * a_row_base * a_f32.stride(-2), a_f32.stride(-2)
-    if a_map is not None:
-        d.a_in_group, d.a_out_group, d.a_offset = a_map
-    assert w.dtype == torch.float32 and w.stride(1) == 1
-    d.w, d.ldw = w.data_ptr(), w.stride(0)
-    d.bias = bias.data_ptr() if bias is not None else 0
-    d.R, d.N, d.K = R, w.shape[0], (w.shape[1] if K is None else K)
-    assert out.dtype == torch.float32 and out.stride(-1) == 1
-    d.out, d.ldo = out.data_ptr() + 4 * o_row_base * out.stride(-2), out.stride(-2)
-    if o_map is not None:
-        d.o_in_group, d.o_out_group, d.o_offset = o_map
-    d.accumulate = 1 if accumulate else 0
-    rc = _L.load().mtt_skinny_linear(C.byref(d), _stream())
-    _L.check(rc, "mtt_skinny_linear")
-
-
 def chan_logits(cp, xn, out, *, B, N, T, Cdim, gh, gw, nh, nw):
     rc = _L.load().mtt_chan_logits(_ptr(cp), _ptr(xn.hi), _ptr(xn.lo), xn.ld, B, N, T, Cdim, gh, gw, nh, nw,
                                    _ptr(out), _stream())

@@ -113,21 +113,6 @@ def install(mp):
         for b in range(B):
             dst[b * group_rows:b * group_rows + T, :src.shape[1]] = src
 
-    def skinny_linear(w, bias, out, *, R, a_split=None, a_f32=None, a_map=None, o_map=None, accumulate=False,
-                      K=None, a_row_base=0, o_row_base=0):
-        K = w.shape[1] if K is None else K
-        r = torch.arange(R)
-        ar = _map(r, a_map, a_row_base)
-        A = _rsplit(a_split, K)[ar] if a_split is not None else a_f32[ar, :K]
-        y = A @ w[:, :K].t()
-        if bias is not None:
-            y = y + bias
-        orow = _map(r, o_map, o_row_base)
-        if accumulate:
-            out[orow, :w.shape[0]] += y
-        else:
-            out[orow, :w.shape[0]] = y
-
     def chan_logits(cp, xn, out, *, B, N, T, Cdim, gh, gw, nh, nw):
         x = _rsplit(xn, Cdim).reshape(B, N, Cdim)[:, T:]
         wh, ww = gh // nh, gw // nw
