@@ -184,6 +184,16 @@ int mtt_bilinear(const float* in, int64_t ld_in, int32_t B, int32_t h, int32_t w
                  float* out_nchw, int32_t accumulate, int64_t in_batch_rows, int64_t in_row_offset,
                  int64_t out_batch_rows, int64_t out_row_offset, mtt_stream_t stream);
 
+/* Bilinear resize to the output size FUSED with the reference's prediction post-processing
+ * (`get_output`, TP/utils/utils.py:27-63 -- the step right after the hot path), so the
+ * full-resolution fp32 logits are never materialised. in: NHWC fp32 [B,h,w,C] (ld_in).
+ * kind 0 argmax -> int64 [B,H2,W2] (semseg, human_parts); 1 255*sigmoid -> fp32 [B,H2,W2] (edge);
+ * 2 255*softmax[...,1] -> fp32 [B,H2,W2] (sal); 3 (normalize+1)*255/2 -> fp32 [B,H2,W2,3] (normals);
+ * 4 clamp(min=0) -> fp32 [B,H2,W2,1] (depth). */
+int mtt_bilinear_postproc(const float* in, int64_t ld_in, int32_t B, int32_t h, int32_t w, int32_t C,
+                          int32_t H2, int32_t W2, int32_t kind, int64_t* out_i64, float* out_f32,
+                          mtt_stream_t stream);
+
 /* ---- InvPT decoder (IP/models/transformers/invpt.py, transformer_decoder.py) ---------------- */
 /* fp32 rows gathered at (r / in_group) * src_group + src_offset + r % in_group -> dense split rows.
  * Replaces x[:, 1:] token selection + layout copies (IP vit.py:345-346, transformer_decoder.py:77). */

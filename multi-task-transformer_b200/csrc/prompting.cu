@@ -263,6 +263,59 @@ bilinear_to_nchw_kernel(const float* __restrict__ in, long long ld_in, long long
   }
 }
 
+// Bilinear resize to the output size fused with the reference's prediction post-processing
+// (get_output, TP/utils/utils.py:27-63): the full-resolution fp32 logits are never written.
+//   kind 0: argmax over channels -> int64 [B,H2,W2]        (semseg, human_parts; first maximum wins, like torch.max)
+//   kind 1: 255 * sigmoid(x)     -> fp32  [B,H2,W2]        (edge)
+//   kind 2: 255 * softmax(x)[1]  -> fp32  [B,H2,W2]        (sal, 2 channels)
+//   kind 3: (x/||x|| + 1)*255/2  -> fp32  [B,H2,W2,3]      (normals; F.normalize eps 1e-12)
+//   kind 4: max(x, 0)            -> fp32  [B,H2,W2,1]      (depth)
+__global__ void __launch_bounds__(256)
+bilinear_postproc_kernel(const float* __restrict__ in, long long ld_in, int B, int h, int w, int C, int H2, int W2,
+                         float sy, float sx, int kind, long long* __restrict__ out_i64, float* __restrict__ out_f32) {
+  const long long opix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (opix >= (long long)B * H2 * W2) return;
+  const int x = (int)(opix % W2), y = (int)((opix / W2) % H2), b = (int)(opix / ((long long)W2 * H2));
+  int y0, y1, x0, x1;
+  float ly, lx;
+  bilin_coord(y, sy, h, y0, y1, ly);
+  bilin_coord(x, sx, w, x0, x1, lx);
+  const float* ib = in + (long long)b * h * w * ld_in;
+  const float* p00 = ib + ((long long)y0 * w + x0) * ld_in;
+  const float* p01 = ib + ((long long)y0 * w + x1) * ld_in;
+  const float* p10 = ib + ((long long)y1 * w + x0) * ld_in;
+  const float* p11 = ib + ((long long)y1 * w + x1) * ld_in;
+  const float hy = 1.f - ly, hx = 1.f - lx;
+  auto val = [&](int c) { return hy * (hx * p00[c] + lx * p01[c]) + ly * (hx * p10[c] + lx * p11[c]); };
+  if (kind == 0) {
+    float best = val(0);
+    int bi = 0;
+    for (int c = 1; c < C; ++c) {
+      const float v = val(c);
+      if (v > best) {
+        best = v;
+        bi = c;
+      }
+    }
+    out_i64[opix] = bi;
+  } else if (kind == 1) {
+    out_f32[opix] = 255.f * (1.f / (1.f + expf(-val(0))));
+  } else if (kind == 2) {
+    const float a = val(0), c1 = val(1);
+    const float m = fmaxf(a, c1);
+    const float e0 = expf(a - m), e1 = expf(c1 - m);
+    out_f32[opix] = e1 / (e0 + e1) * 255.f;
+  } else if (kind == 3) {
+    const float a = val(0), c1 = val(1), c2 = val(2);
+    const float n = fmaxf(sqrtf(a * a + c1 * c1 + c2 * c2), 1e-12f);
+    out_f32[opix * 3 + 0] = (a / n + 1.f) * 255.f / 2.f;
+    out_f32[opix * 3 + 1] = (c1 / n + 1.f) * 255.f / 2.f;
+    out_f32[opix * 3 + 2] = (c2 / n + 1.f) * 255.f / 2.f;
+  } else {
+    out_f32[opix] = fmaxf(val(0), 0.f);
+  }
+}
+
 }  // namespace mtt
 
 using namespace mtt;
@@ -378,4 +431,18 @@ extern "C" int mtt_bilinear(const float* in, int64_t ld_in, int32_t B, int32_t h
     return check_launch("mtt_bilinear(nhwc)");
   }
   return MTT_OK;
+}
+
+extern "C" int mtt_bilinear_postproc(const float* in, int64_t ld_in, int32_t B, int32_t h, int32_t w, int32_t C,
+                                     int32_t H2, int32_t W2, int32_t kind, int64_t* out_i64, float* out_f32,
+                                     mtt_stream_t stream) {
+  const int need_c[5] = {1, 1, 2, 3, 1};
+  if (!in || B <= 0 || h <= 0 || w <= 0 || H2 <= 0 || W2 <= 0 || kind < 0 || kind > 4 || C < need_c[kind] ||
+      (kind == 0 ? !out_i64 : !out_f32))
+    return set_error(MTT_ERR_BAD_SHAPE, "mtt_bilinear_postproc: bad arguments (kind=%d C=%d)", kind, C);
+  const float sy = (float)h / (float)H2, sx = (float)w / (float)W2;
+  const long long opix = (long long)B * H2 * W2;
+  bilinear_postproc_kernel<<<(unsigned)((opix + 255) / 256), 256, 0, STREAM>>>(
+      in, ld_in, B, h, w, C, H2, W2, sy, sx, kind, reinterpret_cast<long long*>(out_i64), out_f32);
+  return check_launch("mtt_bilinear_postproc");
 }

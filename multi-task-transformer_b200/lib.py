@@ -70,6 +70,7 @@ SYMBOLS = {
     "mtt_ctr_mix": (C.c_int, [_vp, _vp, _vp, _i32, _i64, _i32, _i64, _i32, _i32, _vp]),
     "mtt_bilinear": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _i64, _vp, _vp, _i64, _vp,
                                _i32, _i64, _i64, _i64, _i64, _vp]),
+    "mtt_bilinear_postproc": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
     "mtt_split_rows": (C.c_int, [_vp, _i64, _i64, _i64, _i64, _vp, _vp, _i64, _i64, _i32, _vp]),
     "mtt_layernorm_seg": (C.c_int, [_vp, _i64, _i64, _i64, _i64, _i64, _i32, _vp, _vp, _f32, _vp, _i64, _vp,
                                     _vp, _i64, _i64, _i64, _i32, _vp]),

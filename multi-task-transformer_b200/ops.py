@@ -221,6 +221,20 @@ def bilinear(x, ld_in, B, h, w, Cdim, H2, W2, *, out_f32=None, out_split=None, o
     _L.check(rc, "mtt_bilinear")
 
 
+POSTPROC_KIND = {"semseg": 0, "human_parts": 0, "edge": 1, "sal": 2, "normals": 3, "depth": 4}
+
+
+def bilinear_postproc(x, ld_in, B, h, w, Cdim, H2, W2, kind, out):
+    """Bilinear resize fused with get_output's post-processing (TP/utils/utils.py:27-63); `out` is int64
+    [B,H2,W2] for kind 0, fp32 otherwise."""
+    i64 = out if kind == 0 else None
+    f32 = None if kind == 0 else out
+    assert out.is_contiguous() and out.dtype == (torch.int64 if kind == 0 else torch.float32)
+    rc = _L.load().mtt_bilinear_postproc(_ptr(x), ld_in, B, h, w, Cdim, H2, W2, kind, _ptr(i64), _ptr(f32),
+                                         _stream())
+    _L.check(rc, "mtt_bilinear_postproc")
+
+
 def split_rows(x, out, *, rows, cols, in_group=0, src_group=0, src_offset=0):
     """Gather fp32 rows of x (row r at (r // in_group) * src_group + src_offset + r % in_group) -> Split."""
     assert x.dtype == torch.float32 and x.stride(-1) == 1

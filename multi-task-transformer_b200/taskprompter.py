@@ -192,23 +192,35 @@ class TaskPrompterWrapper(nn.Module):
     def _param_version(self):
         return sum(int(q._version) for q in self.parameters()) + sum(int(b._version) for b in self.buffers())
 
-    def plan(self, batch, device):
-        key = (int(batch), str(device), int(self.nsplit))
+    def plan(self, batch, device, postproc=False):
+        key = (int(batch), str(device), int(self.nsplit), bool(postproc))
         ver = self._param_version()
         pl = self._plans.get(key)
         if pl is None or pl.version != ver:
-            pl = _Plan(self, batch, device, self.nsplit)
+            pl = _Plan(self, batch, device, self.nsplit, postproc=postproc)
             pl.version = ver
             self._plans[key] = pl
         return pl
 
-    def forward(self, x):
+    def _check(self, x):
         if self.training:
             raise NotImplementedError("mtt_b200 TaskPrompter: fused forward is eval-only; backward kernels "
                                       "are not built yet (SURVEY.md section 8f N1)")
         if not x.is_cuda:
             raise RuntimeError("mtt_b200 has no CPU path: input must be a CUDA tensor on an sm_100a device")
+
+    def forward(self, x):
+        self._check(x)
         pl = self.plan(x.shape[0], x.device)
+        return pl.run(x, graph=self.use_graph)
+
+    def predict(self, x):
+        """forward + the reference's `get_output` post-processing (TaskPrompter/utils/utils.py:27-63) fused
+        into the final resize: {task: int64 [B,H,W] class map | fp32 map} without materialising the
+        full-resolution logits (semseg / human_parts argmax, edge 255*sigmoid, sal 255*softmax[1], normals
+        (normalize+1)*255/2, depth clamp)."""
+        self._check(x)
+        pl = self.plan(x.shape[0], x.device, postproc=True)
         return pl.run(x, graph=self.use_graph)
 
 
@@ -218,8 +230,9 @@ class TaskPrompterWrapper(nn.Module):
 class _Plan:
     """Packed weights + workspace + launch sequence for one (batch size, device, nsplit)."""
 
-    def __init__(self, wrapper, B, device, nsplit):
+    def __init__(self, wrapper, B, device, nsplit, postproc=False):
         ops._L.check(ops._L.load().mtt_device_check(), "mtt_device_check")
+        self.postproc = postproc
         bb = wrapper.backbone
         p = bb.p
         self.B, self.dev, self.ns = B, device, nsplit
@@ -336,7 +349,16 @@ class _Plan:
         self.side = None   # side streams, created lazily on the plan's device
         self.pred = [z(B * gh4 * gw4, ops.round_up(hw.n_out, 4)) for hw in W.heads]
         oh, ow = self.target if self.target is not None else self.img
-        self.out = {t: z(B, hw.n_out, oh, ow) for t, hw in zip(self.tasks, W.heads)}
+        if not postproc:
+            self.out = {t: z(B, hw.n_out, oh, ow) for t, hw in zip(self.tasks, W.heads)}
+        else:
+            self.out = {}
+            for t in self.tasks:
+                if t not in ops.POSTPROC_KIND:
+                    raise ValueError(f"no get_output post-processing defined for task {t!r}")
+                kind = ops.POSTPROC_KIND[t]
+                shape = {0: (B, oh, ow), 1: (B, oh, ow), 2: (B, oh, ow), 3: (B, oh, ow, 3), 4: (B, oh, ow, 1)}[kind]
+                self.out[t] = torch.zeros(shape, device=device, dtype=torch.int64 if kind == 0 else torch.float32)
         self.out_hw = (oh, ow)
 
     # -- launch sequence ------------------------------------------------------------------------
@@ -434,8 +456,12 @@ class _Plan:
         ops.gemm(self.up[ti], hw.mt, N=self.f, K=self.f, bias=hw.mt_b, act=ops.ACT_GELU, out_split=self.hmid[ti],
                  conv=(B, gh4, gw4, 3, 1))                                                   # ConvHead.mt_proj
         ops.gemm(self.hmid[ti], hw.lp, bias=hw.lp_b, out_f32=self.pred[ti][:, :hw.n_out], N=hw.n_out)
-        ops.bilinear(self.pred[ti], self.pred[ti].stride(0), B, gh4, gw4, hw.n_out, oh, ow,
-                     out_nchw=self.out[t])                                                   # wrapper :35
+        if self.postproc:
+            ops.bilinear_postproc(self.pred[ti], self.pred[ti].stride(0), B, gh4, gw4, hw.n_out, oh, ow,
+                                  ops.POSTPROC_KIND[t], self.out[t])                         # wrapper :35 + utils.py:27-63
+        else:
+            ops.bilinear(self.pred[ti], self.pred[ti].stride(0), B, gh4, gw4, hw.n_out, oh, ow,
+                         out_nchw=self.out[t])                                               # wrapper :35
 
     def _launch(self, img):
         B, N, T, C, P = self.B, self.N, self.T, self.C, self.P

@@ -166,6 +166,20 @@ def install(mp):
             if out_split.nsplit == 2:
                 out_split.buf[1, rows_out, :Cdim] = (yn - hi.float()).bfloat16()
 
+    def bilinear_postproc(x, ld_in, B, h, w, Cdim, H2, W2, kind, out):
+        img = x.reshape(B, h, w, ld_in)[..., :Cdim].permute(0, 3, 1, 2)
+        y = F.interpolate(img, size=(H2, W2), mode="bilinear", align_corners=False).permute(0, 2, 3, 1)
+        if kind == 0:
+            out.copy_(y.max(dim=3)[1])
+        elif kind == 1:
+            out.copy_(255 * 1 / (1 + torch.exp(-y[..., 0])))
+        elif kind == 2:
+            out.copy_(F.softmax(y[..., :2], dim=3)[..., 1] * 255)
+        elif kind == 3:
+            out.copy_((F.normalize(y[..., :3], p=2, dim=3) + 1.0) * 255 / 2.0)
+        else:
+            out.copy_(y[..., :1].clamp(min=0.))
+
     def _rows(rows, in_group, src_group, src_offset):
         r = torch.arange(rows)
         return (r // in_group) * src_group + src_offset + r % in_group if in_group > 0 else r + src_offset

@@ -76,3 +76,29 @@ def test_invpt_plan_matches_oracle(monkeypatch, name, nsplit, tol):
         assert err < tol, f"{name} {t}: rel-L2 {err:.3e}"
         err = (got["inter_preds"][t] - ref["inter_preds"][t]).norm() / ref["inter_preds"][t].norm()
         assert err < tol, f"{name} inter {t}: rel-L2 {err:.3e}"
+
+
+def test_taskprompter_predict_matches_get_output(monkeypatch):
+    """predict() = forward + get_output (TP/utils/utils.py:27-63) fused into the final resize."""
+    import mtt_b200  # noqa: F401
+    from mtt_b200 import taskprompter as TP
+    from oracle import postproc_ref
+    import emul_ops
+
+    emul_ops.install(monkeypatch)
+    cfg = configs.taskprompter("tp_tiny")
+    sd = TPR.init_state_dict(cfg, seed=3)
+    model = TP.build_from_config(cfg, nsplit=2, use_graph=False).eval()
+    model.load_state_dict(sd, strict=True)
+    torch.manual_seed(1)
+    x = torch.randn(2, 3, *cfg["img_size"])
+    with torch.no_grad():
+        ref = TPR.forward(sd, cfg, x)
+        got = model.plan(2, torch.device("cpu"), postproc=True).run(x, graph=False)
+    for t in cfg["tasks"]:
+        want = postproc_ref.get_output(ref[t], t)
+        assert got[t].shape == want.shape and got[t].dtype == want.dtype, t
+        if want.dtype == torch.int64:
+            assert (got[t] == want).float().mean() > 0.995, t
+        else:
+            assert (got[t] - want).abs().max() <= 2e-3 * want.abs().max().clamp_min(1.0), t

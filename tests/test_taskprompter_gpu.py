@@ -106,3 +106,34 @@ def test_full_width_parity(cuda_dev, name, batch):
         got = m(x.cuda())
     torch.cuda.synchronize()
     _check(got, ref, cfg["tasks"], 2e-4, 1e-3)
+
+
+def test_predict_fused_postprocessing(cuda_dev):
+    """predict(): bilinear-to-image fused with get_output (TP/utils/utils.py:27-63). Index maps must be
+    bit-exact against the argmax of this build's own logits (same arithmetic), float maps within 1e-4, and
+    agree with get_output(oracle logits) away from near ties."""
+    from oracle import postproc_ref
+
+    for name in ("tp_tiny", "tp_tiny1"):
+        cfg = configs.taskprompter(name)
+        sd = TPR.init_state_dict(cfg, seed=13)
+        torch.manual_seed(14)
+        x = torch.randn(2, 3, *cfg["img_size"])
+        m = _build(cfg, sd, 2, False)
+        with torch.no_grad():
+            logits = {k: v.clone() for k, v in m(x.cuda()).items()}
+            pred = m.predict(x.cuda())
+            ref = TPR.forward(sd, cfg, x)
+        torch.cuda.synchronize()
+        for t in cfg["tasks"]:
+            own = postproc_ref.get_output(logits[t], t)
+            want = postproc_ref.get_output(ref[t], t)
+            assert pred[t].shape == want.shape and pred[t].dtype == want.dtype
+            if want.dtype == torch.int64:
+                assert torch.equal(pred[t], own), t
+                top2 = ref[t].topk(2, dim=1).values
+                safe = (top2[:, 0] - top2[:, 1]) > 1e-4 * ref[t].abs().max()
+                assert (pred[t].cpu() == want)[safe].all(), t
+            else:
+                assert (pred[t] - own).abs().max() <= 1e-4 * own.abs().max().clamp_min(1.0), t
+                assert (pred[t].cpu() - want).abs().max() <= 2e-3 * want.abs().max().clamp_min(1.0), t
