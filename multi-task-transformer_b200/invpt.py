@@ -206,31 +206,41 @@ class TransformerNet(nn.Module):
     def _param_version(self):
         return sum(int(q._version) for q in self.parameters()) + sum(int(b._version) for b in self.buffers())
 
-    def plan(self, batch, device):
-        key = (int(batch), str(device), int(self.nsplit))
+    def plan(self, batch, device, postproc=False):
+        key = (int(batch), str(device), int(self.nsplit), bool(postproc))
         ver = self._param_version()
         pl = self._plans.get(key)
         if pl is None or pl.version != ver:
-            pl = _Plan(self, batch, device, self.nsplit)
+            pl = _Plan(self, batch, device, self.nsplit, postproc=postproc)
             pl.version = ver
             self._plans[key] = pl
         return pl
 
-    def forward(self, x):
+    def _check(self, x):
         if self.training:
             raise NotImplementedError("mtt_b200 InvPT: fused forward is eval-only; backward kernels are not built "
                                       "yet (SURVEY.md section 8f N1)")
         if not x.is_cuda:
             raise RuntimeError("mtt_b200 has no CPU path: input must be a CUDA tensor on an sm_100a device")
+
+    def forward(self, x):
+        self._check(x)
         return self.plan(x.shape[0], x.device).run(x, graph=self.use_graph)
+
+    def predict(self, x):
+        """forward + the reference's `get_output` post-processing (InvPT/utils/utils.py:18-48) fused into the
+        final resize of every task head (no full-resolution logits, no inter_preds)."""
+        self._check(x)
+        return self.plan(x.shape[0], x.device, postproc=True).run(x, graph=self.use_graph)
 
 
 # --------------------------------------------------------------------------------------------
 # the fused forward
 # --------------------------------------------------------------------------------------------
 class _Plan:
-    def __init__(self, net, B, device, nsplit):
+    def __init__(self, net, B, device, nsplit, postproc=False):
         ops._L.check(ops._L.load().mtt_device_check(), "mtt_device_check")
+        self.postproc = postproc
         bb, dec, p = net.backbone, net.multi_task_decoder, net.p
         inv = dec.invpt
         self.B, self.dev, self.ns = B, device, nsplit
@@ -383,8 +393,15 @@ class _Plan:
         self.side = None
         self.pred = [z(tt, ops.round_up(n, 4)) for n in self.n_out]
         oh, ow = self.img
-        self.out = {t: z(B, n, oh, ow) for t, n in zip(self.tasks, self.n_out)}
-        self.out_inter = {t: z(B, n, oh, ow) for t, n in zip(self.tasks, self.n_out)}
+        if not postproc:
+            self.out = {t: z(B, n, oh, ow) for t, n in zip(self.tasks, self.n_out)}
+            self.out_inter = {t: z(B, n, oh, ow) for t, n in zip(self.tasks, self.n_out)}
+        else:
+            self.out, self.out_inter = {}, None
+            for t in self.tasks:
+                kind = ops.POSTPROC_KIND[t]
+                shape = {0: (B, oh, ow), 1: (B, oh, ow), 2: (B, oh, ow), 3: (B, oh, ow, 3), 4: (B, oh, ow, 1)}[kind]
+                self.out[t] = torch.zeros(shape, device=device, dtype=torch.int64 if kind == 0 else torch.float32)
 
     # ------------------------------------------------------------------------------------------
     def _vit_block(self, w):
@@ -480,8 +497,12 @@ class _Plan:
                  conv=(B, self.th, self.tw, 3, 1))                                                     # invpt.py:541-543
         n = self.n_out[k]
         ops.gemm(self.hm[k], tw.lp, bias=tw.lp_b, out_f32=self.pred[k][:, :n], N=n)                    # MLPHead
-        ops.bilinear(self.pred[k], self.pred[k].stride(0), B, self.th, self.tw, n, self.img[0], self.img[1],
-                     out_nchw=self.out[self.tasks[k]])                                                 # transformer_net.py:35
+        if self.postproc:
+            ops.bilinear_postproc(self.pred[k], self.pred[k].stride(0), B, self.th, self.tw, n, self.img[0],
+                                  self.img[1], ops.POSTPROC_KIND[self.tasks[k]], self.out[self.tasks[k]])
+        else:
+            ops.bilinear(self.pred[k], self.pred[k].stride(0), B, self.th, self.tw, n, self.img[0], self.img[1],
+                         out_nchw=self.out[self.tasks[k]])                                             # transformer_net.py:35
 
     def _launch(self, img):
         B, N, P, C, T, W = self.B, self.N, self.P, self.C, self.T, self.W
@@ -518,8 +539,9 @@ class _Plan:
             ops.gemm(self.cat[k], tw.ih, K=E, bias=tw.ih_b, out_f32=self.inter[k][:, :n], N=n,
                      out_split=self.cat[k], out_col_offset=E)                                          # :94; invpt.py:511
             ops.gemm(self.cat[k], tw.mix, bias=tw.mix_b, out_f32=s0.xj, regroup=(hw0, T * hw0, k * hw0))  # invpt.py:512
-            ops.bilinear(self.inter[k], self.inter[k].stride(0), B, h0, w0, n, self.img[0], self.img[1],
-                         out_nchw=self.out_inter[self.tasks[k]])                                       # transformer_net.py:36
+            if not self.postproc:
+                ops.bilinear(self.inter[k], self.inter[k].stride(0), B, h0, w0, n, self.img[0], self.img[1],
+                             out_nchw=self.out_inter[self.tasks[k]])                                   # transformer_net.py:36
         self._par(prelim)
         for i in range(3):
             self._stage(i)
@@ -542,7 +564,8 @@ class _Plan:
                 self.graph = g
             self.graph.replay()
         out = dict(self.out)
-        out["inter_preds"] = dict(self.out_inter)
+        if self.out_inter is not None:
+            out["inter_preds"] = dict(self.out_inter)
         return out
 
 
@@ -559,3 +582,18 @@ def build_from_config(cfg, nsplit=PARITY, use_graph=True):
                            depth=cfg["depth"], num_heads=cfg["heads"])
     heads = nn.ModuleDict({t: MLPHead(p.final_embed_dim, cfg["num_output"][t]) for t in cfg["tasks"]})
     return TransformerNet(p, bb, p.backbone_channels, heads, nsplit=nsplit, use_graph=use_graph)
+
+
+def accelerate(ref_model, nsplit=PARITY, use_graph=True):
+    """Drop-in: build the fused InvPT from a REFERENCE TransformerNet instance (InvPT/models/transformer_net.py),
+    sharing its parameters through an exact `load_state_dict(strict=True)`."""
+    p = ref_model.multi_task_decoder.p
+    bb = ref_model.backbone
+    mine_bb = VisionTransformer(list(bb.select_list), img_size=tuple(bb.patch_embed.img_size),
+                                patch_size=bb.patch_embed.patch_size[0], embed_dim=bb.embed_dim,
+                                depth=len(bb.blocks), num_heads=bb.blocks[0].attn.num_heads)
+    heads = nn.ModuleDict({t: MLPHead(ref_model.heads[t].linear_pred.weight.shape[1],
+                                      ref_model.heads[t].linear_pred.weight.shape[0]) for t in ref_model.tasks})
+    m = TransformerNet(p, mine_bb, p.backbone_channels, heads, nsplit=nsplit, use_graph=use_graph)
+    m.load_state_dict(ref_model.state_dict(), strict=True)
+    return m.eval()

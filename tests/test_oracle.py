@@ -90,3 +90,16 @@ def test_invpt_oracle_vs_reference(name):
     for t in cfg["tasks"]:
         assert (out[t] - ref[t]).abs().max() <= 5e-6, t
         assert (out["inter_preds"][t] - ref["inter_preds"][t]).abs().max() <= 5e-6, t
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="reference tree not present")
+def test_invpt_accelerate_shares_reference_state_dict():
+    import mtt_b200  # noqa: F401
+    from mtt_b200 import invpt as IP
+
+    cfg = configs.invpt("ip_tiny")
+    ref = ref_loader.build_invpt(cfg).eval()
+    mine = IP.accelerate(ref)
+    a, b = ref.state_dict(), mine.state_dict()
+    assert set(a.keys()) == set(b.keys())
+    assert all(torch.equal(a[k], b[k]) for k in a)
