@@ -194,6 +194,19 @@ int mtt_bilinear_postproc(const float* in, int64_t ld_in, int32_t B, int32_t h, 
                           int32_t H2, int32_t W2, int32_t kind, int64_t* out_i64, float* out_f32,
                           mtt_stream_t stream);
 
+/* Sum of up to three bilinearly resized NHWC fp32 sources written once as a split tensor [B*H2*W2, ld_bf]:
+ * InvPT's multi-scale aggregation of the three stages' per-task maps (IP invpt.py:528-539), in the
+ * reference's accumulation order, without read-modify-write passes over the full-resolution map. */
+typedef struct {
+  const float* in;
+  int64_t ld_in;
+  int32_t h, w;
+  int64_t batch_rows; /* rows between images of `in` (0: h*w) */
+  int64_t row_offset; /* first row of image 0 */
+} mtt_bilinear_src;
+int mtt_bilinear_sum3(const mtt_bilinear_src* srcs, int32_t nsrc, int32_t B, int32_t C, int32_t H2, int32_t W2,
+                      void* out_hi, void* out_lo, int64_t ld_bf, mtt_stream_t stream);
+
 /* ---- InvPT decoder (IP/models/transformers/invpt.py, transformer_decoder.py) ---------------- */
 /* fp32 rows gathered at (r / in_group) * src_group + src_offset + r % in_group -> dense split rows.
  * Replaces x[:, 1:] token selection + layout copies (IP vit.py:345-346, transformer_decoder.py:77). */

@@ -263,6 +263,58 @@ bilinear_to_nchw_kernel(const float* __restrict__ in, long long ld_in, long long
   }
 }
 
+// Sum of up to three bilinearly resized NHWC sources, written once as a split tensor: InvPT's multi-scale
+// aggregation (invpt.py:528-539 accumulates the three stages' per-task maps at 8h x 8w) without the three
+// read-modify-write passes over the full-resolution fp32 map.  One warp per output pixel.
+struct BilinSrc {
+  const float* p;
+  long long ld, batch_rows, row_off;
+  int h, w;
+};
+__global__ void __launch_bounds__(256)
+bilinear_sum3_kernel(BilinSrc s0, BilinSrc s1, BilinSrc s2, int nsrc, int B, int C, int H2, int W2,
+                     __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo, long long ld_bf) {
+  const long long gpix = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (gpix >= (long long)B * H2 * W2) return;
+  const int lane = threadIdx.x & 31;
+  const int x = (int)(gpix % W2), y = (int)((gpix / W2) % H2), b = (int)(gpix / ((long long)W2 * H2));
+  const float* q[3][4];
+  float wgt[3][4];
+  const BilinSrc* ss[3] = {&s0, &s1, &s2};
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    if (i >= nsrc) break;
+    const BilinSrc& s = *ss[i];
+    int y0, y1, x0, x1;
+    float ly, lx;
+    bilin_coord(y, (float)s.h / (float)H2, s.h, y0, y1, ly);
+    bilin_coord(x, (float)s.w / (float)W2, s.w, x0, x1, lx);
+    const float* ib = s.p + ((long long)b * s.batch_rows + s.row_off) * s.ld;
+    q[i][0] = ib + ((long long)y0 * s.w + x0) * s.ld;
+    q[i][1] = ib + ((long long)y0 * s.w + x1) * s.ld;
+    q[i][2] = ib + ((long long)y1 * s.w + x0) * s.ld;
+    q[i][3] = ib + ((long long)y1 * s.w + x1) * s.ld;
+    wgt[i][0] = 1.f - ly;
+    wgt[i][1] = ly;
+    wgt[i][2] = 1.f - lx;
+    wgt[i][3] = lx;
+  }
+  for (int c = lane * 2; c < C; c += 64) {
+    float v0 = 0.f, v1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      if (i >= nsrc) break;
+      const float hy = wgt[i][0], ly = wgt[i][1], hx = wgt[i][2], lx = wgt[i][3];
+      v0 += hy * (hx * q[i][0][c] + lx * q[i][1][c]) + ly * (hx * q[i][2][c] + lx * q[i][3][c]);
+      v1 += hy * (hx * q[i][0][c + 1] + lx * q[i][1][c + 1]) + ly * (hx * q[i][2][c + 1] + lx * q[i][3][c + 1]);
+    }
+    uint32_t hh, ll;
+    split_pack2(v0, v1, hh, ll);
+    *reinterpret_cast<uint32_t*>(out_hi + gpix * ld_bf + c) = hh;
+    if (out_lo) *reinterpret_cast<uint32_t*>(out_lo + gpix * ld_bf + c) = ll;
+  }
+}
+
 // Bilinear resize to the output size fused with the reference's prediction post-processing
 // (get_output, TP/utils/utils.py:27-63): the full-resolution fp32 logits are never written.
 //   kind 0: argmax over channels -> int64 [B,H2,W2]        (semseg, human_parts; first maximum wins, like torch.max)
@@ -445,4 +497,26 @@ extern "C" int mtt_bilinear_postproc(const float* in, int64_t ld_in, int32_t B, 
   bilinear_postproc_kernel<<<(unsigned)((opix + 255) / 256), 256, 0, STREAM>>>(
       in, ld_in, B, h, w, C, H2, W2, sy, sx, kind, reinterpret_cast<long long*>(out_i64), out_f32);
   return check_launch("mtt_bilinear_postproc");
+}
+
+extern "C" int mtt_bilinear_sum3(const mtt_bilinear_src* srcs, int32_t nsrc, int32_t B, int32_t C, int32_t H2,
+                                 int32_t W2, void* out_hi, void* out_lo, int64_t ld_bf, mtt_stream_t stream) {
+  if (!srcs || nsrc < 1 || nsrc > 3 || B <= 0 || C <= 0 || (C & 1) || (ld_bf & 1) || !out_hi)
+    return set_error(MTT_ERR_BAD_SHAPE, "mtt_bilinear_sum3: bad arguments (nsrc=%d C=%d)", nsrc, C);
+  BilinSrc s[3] = {};
+  for (int i = 0; i < nsrc; ++i) {
+    if (!srcs[i].in || srcs[i].h <= 0 || srcs[i].w <= 0)
+      return set_error(MTT_ERR_BAD_SHAPE, "mtt_bilinear_sum3: bad source %d", i);
+    s[i].p = srcs[i].in;
+    s[i].ld = srcs[i].ld_in;
+    s[i].h = srcs[i].h;
+    s[i].w = srcs[i].w;
+    s[i].batch_rows = srcs[i].batch_rows > 0 ? srcs[i].batch_rows : (long long)srcs[i].h * srcs[i].w;
+    s[i].row_off = srcs[i].row_offset;
+  }
+  const long long opix = (long long)B * H2 * W2;
+  bilinear_sum3_kernel<<<(unsigned)((opix + 7) / 8), 256, 0, STREAM>>>(
+      s[0], s[1], s[2], nsrc, B, C, H2, W2, static_cast<__nv_bfloat16*>(out_hi),
+      static_cast<__nv_bfloat16*>(out_lo), ld_bf);
+  return check_launch("mtt_bilinear_sum3");
 }

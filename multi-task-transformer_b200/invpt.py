@@ -387,7 +387,6 @@ class _Plan:
                 s.ue1 = [S(B * h * w, Ci) for _ in range(T)]
             self.st.append(s)
         tt = B * self.th * self.tw
-        self.ms = z(T, tt, dims[0])
         self.mss = [S(tt, dims[0]) for _ in range(T)]
         self.hm = [S(tt, dims[0]) for _ in range(T)]
         self.side = None
@@ -476,17 +475,18 @@ class _Plan:
         d0 = self.dims[0]
 
         def aggregate(k):
-            if i == 0:
-                ops.bilinear(s.ln32[k * B * hw:], s.ln32.stride(0), B, h, w, Ci, self.th, self.tw,
-                             out_f32=self.ms[k])                                                       # :537-539
-            else:
+            # per-task slice -> (i > 0: 1x1 redu_chan) kept at its own resolution; after the last stage the three
+            # maps are resized to 8h0 x 8w0, summed and written ONCE as the split operand of mt_proj (:528-543)
+            if i > 0:
                 rw, rb = sw.redu[k]
                 ops.gemm(s.ln, rw, M=B * hw, bias=rb, out_f32=s.rc32[k], a_row_offset=k * B * hw)      # :535-536
-                last = i == 2
-                ops.bilinear(s.rc32[k], s.rc32[k].stride(0), B, h, w, d0, self.th, self.tw, out_f32=self.ms[k],
-                             accumulate=True, out_split=self.mss[k] if last else None)
-                if last:
-                    self._head(k)
+            if i == 2:
+                s0_, s1_ = self.st[0], self.st[1]
+                ops.bilinear_sum3([(s0_.ln32, s0_.h, s0_.w, 0, k * B * s0_.h * s0_.w),
+                                   (s1_.rc32[k], s1_.h, s1_.w, 0, 0),
+                                   (s.rc32[k], h, w, 0, 0)],
+                                  self.mss[k], B=B, Cdim=d0, H2=self.th, W2=self.tw)                   # :537-539
+                self._head(k)
         self._par(aggregate)
 
     def _head(self, k):

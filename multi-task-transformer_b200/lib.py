@@ -37,6 +37,11 @@ class AttnDesc(C.Structure):
     ]
 
 
+class BilinearSrc(C.Structure):
+    _fields_ = [("in_", C.c_void_p), ("ld_in", C.c_int64), ("h", C.c_int32), ("w", C.c_int32),
+                ("batch_rows", C.c_int64), ("row_offset", C.c_int64)]
+
+
 class InvptAttnDesc(C.Structure):
     _fields_ = [
         ("q", C.c_void_p), ("k", C.c_void_p), ("v", C.c_void_p), ("ldq", C.c_int64), ("ldk", C.c_int64),
@@ -71,6 +76,7 @@ SYMBOLS = {
     "mtt_bilinear": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _i64, _vp, _vp, _i64, _vp,
                                _i32, _i64, _i64, _i64, _i64, _vp]),
     "mtt_bilinear_postproc": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
+    "mtt_bilinear_sum3": (C.c_int, [C.POINTER(BilinearSrc), _i32, _i32, _i32, _i32, _i32, _vp, _vp, _i64, _vp]),
     "mtt_split_rows": (C.c_int, [_vp, _i64, _i64, _i64, _i64, _vp, _vp, _i64, _i64, _i32, _vp]),
     "mtt_layernorm_seg": (C.c_int, [_vp, _i64, _i64, _i64, _i64, _i64, _i32, _vp, _vp, _f32, _vp, _i64, _vp,
                                     _vp, _i64, _i64, _i64, _i32, _vp]),

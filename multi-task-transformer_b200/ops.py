@@ -235,6 +235,19 @@ def bilinear_postproc(x, ld_in, B, h, w, Cdim, H2, W2, kind, out):
     _L.check(rc, "mtt_bilinear_postproc")
 
 
+def bilinear_sum3(srcs, out, *, B, Cdim, H2, W2):
+    """out (Split [B*H2*W2, C]) = sum_i bilinear(src_i -> H2 x W2); srcs: list of up to three
+    (tensor fp32 [rows, ld], h, w, batch_rows, row_offset)."""
+    arr = (_L.BilinearSrc * len(srcs))()
+    for i, (t, h, w, brows, roff) in enumerate(srcs):
+        assert t.dtype == torch.float32 and t.stride(-1) == 1
+        arr[i].in_, arr[i].ld_in, arr[i].h, arr[i].w = t.data_ptr(), t.stride(-2), h, w
+        arr[i].batch_rows, arr[i].row_offset = brows, roff
+    rc = _L.load().mtt_bilinear_sum3(arr, len(srcs), B, Cdim, H2, W2, _ptr(out.hi), _ptr(out.lo), out.ld,
+                                     _stream())
+    _L.check(rc, "mtt_bilinear_sum3")
+
+
 def split_rows(x, out, *, rows, cols, in_group=0, src_group=0, src_offset=0):
     """Gather fp32 rows of x (row r at (r // in_group) * src_group + src_offset + r % in_group) -> Split."""
     assert x.dtype == torch.float32 and x.stride(-1) == 1

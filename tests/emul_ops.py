@@ -180,6 +180,15 @@ def install(mp):
         else:
             out.copy_(y[..., :1].clamp(min=0.))
 
+    def bilinear_sum3(srcs, out, *, B, Cdim, H2, W2):
+        acc = 0
+        for t, h, w, brows, roff in srcs:
+            brows = brows or h * w
+            rows = (torch.arange(B)[:, None] * brows + roff + torch.arange(h * w)[None]).reshape(-1)
+            img = t[rows, :Cdim].reshape(B, h, w, Cdim).permute(0, 3, 1, 2)
+            acc = acc + F.interpolate(img, size=(H2, W2), mode="bilinear", align_corners=False)
+        _wsplit(out, acc.permute(0, 2, 3, 1).reshape(B * H2 * W2, Cdim))
+
     def _rows(rows, in_group, src_group, src_offset):
         r = torch.arange(rows)
         return (r // in_group) * src_group + src_offset + r % in_group if in_group > 0 else r + src_offset

@@ -240,3 +240,26 @@ def test_chan_logits(cuda_dev, nh):
     c = cp.double().cpu().reshape(B, T, nh, gh // nh, nh, gw // nh)
     ref = torch.einsum("btihjw,bihjwc->btcij", c, x)
     assert relerr(out, ref) < 2e-5
+
+
+def test_bilinear_sum3(cuda_dev):
+    """InvPT multi-scale aggregation: three sources at different resolutions / row layouts -> one split map."""
+    from mtt_b200 import ops
+
+    torch.manual_seed(6)
+    B, C, T, H2, W2 = 2, 48, 3, 16, 24
+    k = 1
+    s0 = torch.randn(T * B * 2 * 3, C, device=cuda_dev)           # task-major rows, 2x3 maps
+    s1 = torch.randn(B * 4 * 6, C + 8, device=cuda_dev)[:, :C]    # strided rows, 4x6 maps
+    s2 = torch.randn(B * 8 * 12, C, device=cuda_dev)              # 8x12 maps
+    out = ops.Split(B * H2 * W2, C, cuda_dev)
+    ops.bilinear_sum3([(s0, 2, 3, 0, k * B * 6), (s1, 4, 6, 0, 0), (s2, 8, 12, 0, 0)], out, B=B, Cdim=C, H2=H2, W2=W2)
+    torch.cuda.synchronize()
+
+    def up(t, h, w):
+        img = t.double().cpu().reshape(B, h, w, C).permute(0, 3, 1, 2)
+        return F.interpolate(img, size=(H2, W2), mode="bilinear", align_corners=False)
+
+    ref = up(s0[k * B * 6:(k + 1) * B * 6], 2, 3) + up(s1.contiguous(), 4, 6) + up(s2, 8, 12)
+    got = out.float()[:, :C].reshape(B, H2, W2, C).permute(0, 3, 1, 2)
+    assert relerr(got, ref) < 3e-5
