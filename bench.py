@@ -97,7 +97,7 @@ def pick_cpu_threads():
     """Eager PyTorch on a many-core host collapses when over-subscribed (measured on the 128-thread GPU
     box: 16 threads 0.61 s, 64 threads 1.4 s, 128 threads 56 s for the same 4-block slice), so the CPU arm
     uses the thread count that is actually fastest for this workload, found on a short slice."""
-    from oracle import configs
+    from mtt_b200 import configs
     from oracle import taskprompter_ref as TPR
 
     ncpu = os.cpu_count() or 1
@@ -126,7 +126,7 @@ def pick_cpu_threads():
 def cpu_oracle_rate(cfg_name, steps, warmup, threads):
     """images/s of the reference algorithm's CPU port (oracle/taskprompter_ref.py, fp32, eval) on a
     bounded sample: batch 1 of the same workload per step."""
-    from oracle import configs
+    from mtt_b200 import configs
     from oracle import taskprompter_ref as TPR
 
     torch.set_num_threads(threads)
@@ -166,8 +166,12 @@ def run_reference(args):
 
 # ------------------------------------------------------------------------------------------------
 def gemm_roofline(model, plan, x_dev, peaks, peak_src):
-    """Average duration and algorithmic FLOPs of the dominant kernel (gemm_tc_kernel: every GEMM / conv
-    launch of one forward), measured live with CUDA events on the launching stream."""
+    """Average duration and algorithmic FLOPs of the dominant kernel family (the tcgen05 GEMM / implicit-GEMM
+    conv kernels: every mtt_gemm launch of one forward), measured live with CUDA events on the launching stream.
+
+    The forward is enqueued eagerly on ONE stream behind a device-side blocker, so the whole launch queue is
+    resident before the first kernel runs and the events bracket device time only (without the blocker an
+    eager pass measures the host's per-launch latency instead: 102 us / launch against 44 us real)."""
     from mtt_b200 import ops
 
     recs = []
@@ -184,29 +188,47 @@ def gemm_roofline(model, plan, x_dev, peaks, peak_src):
         s.record()
         real(a, w, **kw)
         e.record()
-        recs.append((s, e, 2.0 * M * N * K * taps))
+        recs.append((s, e, 2.0 * M * N * K * taps, min(N, K) >= 1024))
 
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ops.gemm = timed
+    plan.serial = True
     try:
         plan._launch(x_dev)   # warm
+        torch.cuda.synchronize()
         recs.clear()
+        torch.cuda._sleep(int(60e6))   # ~30 ms of device time: the host enqueues the whole forward meanwhile
+        f0.record()
         plan._launch(x_dev)
+        f1.record()
         torch.cuda.synchronize()
     finally:
         ops.gemm = real
-    tot_ms = sum(s.elapsed_time(e) for s, e, _ in recs)
-    tot_fl = sum(f for _, _, f in recs)
+        plan.serial = False
+    fwd_ms = f0.elapsed_time(f1)
+    tot_ms = sum(s.elapsed_time(e) for s, e, _, _ in recs)
+    tot_fl = sum(f for _, _, f, _ in recs)
+    bb_ms = sum(s.elapsed_time(e) for s, e, _, bb in recs if bb)
+    bb_fl = sum(f for _, _, f, bb in recs if bb)
     achieved = tot_fl / (tot_ms * 1e-3) / 1e12
     peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
     mma_factor = 3 if model.nsplit == 2 else 1
+    bb = bb_fl / (bb_ms * 1e-3) / 1e12 if bb_ms > 0 else None
     return {
-        "bound": "tensor", "kernel": "gemm_tc_kernel (all GEMM + implicit-GEMM conv launches of one forward)",
+        "bound": "tensor",
+        "kernel": "gemm_tc_kernel + gemm2_tc_kernel (every GEMM / implicit-GEMM conv launch of one forward)",
         "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
         "peak_source": f"bf16 dense sustained, {peak_src}", "traffic": None,
-        "launches": len(recs), "avg_launch_us": tot_ms * 1e3 / len(recs), "share_of_forward_ms": tot_ms,
-        "note": ("achieved counts the reference's ALGORITHMIC fp32 FLOPs (2*M*N*K); the parity mode issues "
-                 f"{mma_factor} bf16 tcgen05.mma per product, so the tensor pipe runs at "
-                 f"{achieved * mma_factor:.0f} TFLOP/s = {achieved * mma_factor / peak:.2f} of peak"),
+        "launches": len(recs), "avg_launch_us": tot_ms * 1e3 / len(recs),
+        "share_of_forward": tot_ms / fwd_ms, "serial_forward_ms": fwd_ms,
+        "issued_mma_tflops": achieved * mma_factor, "issued_mma_frac": achieved * mma_factor / peak,
+        "backbone_gemms": None if bb is None else {
+            "launches": sum(1 for r in recs if r[3]), "achieved": bb, "issued_mma_tflops": bb * mma_factor,
+            "issued_mma_frac": bb * mma_factor / peak, "avg_launch_us": bb_ms * 1e3 / sum(1 for r in recs if r[3])},
+        "note": ("achieved counts the reference's ALGORITHMIC fp32 FLOPs (2*M*N*K*taps per launch, DESIGN.md); the "
+                 f"parity mode issues {mma_factor} bf16 tcgen05.mma per product (issued_mma_*); one eager forward on a "
+                 "single stream behind a device-side blocker, CUDA events around every launch; backbone_gemms = the "
+                 "qkv / proj / fc1 / fc2 launches alone"),
     }
 
 
@@ -220,7 +242,7 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
     from mtt_b200 import taskprompter as TP
-    from oracle import configs
+    from mtt_b200 import configs
 
     cfg = configs.taskprompter(args.config)
     nsplit = 2 if args.mode == "parity" else 1

@@ -129,7 +129,10 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
         tc_fence_after();
         const uint32_t tacc = tmem_base + as * BN2;
         uint32_t accum = 0;
+        int kb = 0;
         for (int ki = 0; ki < k_iters; ++ki) {
+          const int nks = (++kb == p.num_kb) ? p.k_last_steps : BK / 16;  // zero-padded tail of K: no MMAs
+          if (kb == p.num_kb) kb = 0;
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t a_hi = smem_u32(smem + stage * Cfg::kStageBytes);
@@ -137,6 +140,7 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
           if (elect_one()) {
 #pragma unroll
             for (int ks = 0; ks < BK / 16; ++ks) {
+              if (ks >= nks) break;
               const uint64_t adh = umma_desc_sw128(a_hi + ks * 32);
               const uint64_t bdh = umma_desc_sw128(b_hi + ks * 32);
               umma_ss_cg2(tacc, adh, bdh, idesc, (ks > 0) ? 1u : accum);

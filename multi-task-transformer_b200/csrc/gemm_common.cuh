@@ -19,6 +19,7 @@ struct GemmParams {
   int tiles_m;  // number of 128-row sub-tiles
   int tiles_n;  // number of N tiles (of the kernel's BN)
   int cin_pad;
+  int k_last_steps;  // 16-wide MMA k-steps holding data in the last k-block of a tap (1..4); the rest is zero padding
   uint32_t a_box_bytes;
   const float* bias;
   int act;

@@ -52,6 +52,7 @@ int gemm_prepare(const mtt_gemm_desc* d, int b_box_rows, GemmParams& p, CUtensor
   p.N = d->N;
   p.mode = d->mode;
   p.num_kb = (d->K + BK - 1) / BK;
+  p.k_last_steps = (d->K - (p.num_kb - 1) * BK + 15) / 16;  // columns past K are TMA zero fill: skip their MMAs
   p.tiles_n = 0;
   p.bias = d->bias;
   p.act = d->act;

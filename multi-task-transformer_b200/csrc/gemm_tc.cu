@@ -115,7 +115,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (warp-uniform loop, elected lane issues)
     {
-      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, 0);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -125,8 +124,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         mbar_wait(&tempty_bar[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t tacc = tmem_base + as * BN;
+        // ragged last N tile: a narrower MMA (N rounded up to 16) instead of multiplying zero-filled weight rows
+        const int n_left = p.N - (tile / p.tiles_m) * BN;
+        const uint32_t idesc = umma_idesc_bf16(BM, n_left >= BN ? BN : ((n_left + 15) & ~15), 0);
         uint32_t accum = 0;
+        int kb = 0;
         for (int ki = 0; ki < k_iters; ++ki) {
+          const int nks = (++kb == p.num_kb) ? p.k_last_steps : BK / 16;  // zero-padded tail of K: no MMAs
+          if (kb == p.num_kb) kb = 0;
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t a_hi = smem_u32(smem + stage * Cfg::kStageBytes);
@@ -134,6 +139,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           if (elect_one()) {
 #pragma unroll
             for (int ks = 0; ks < BK / 16; ++ks) {
+              if (ks >= nks) break;
               const uint64_t adh = umma_desc_sw128(a_hi + ks * 32);
               const uint64_t bdh = umma_desc_sw128(b_hi + ks * 32);
               umma_ss(tacc, adh, bdh, idesc, (ks > 0) ? 1u : accum);

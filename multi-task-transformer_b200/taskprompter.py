@@ -400,7 +400,7 @@ class _Plan:
     def _fork(self, n=None):
         """n (default T) side streams forked off the current stream (captured into the same CUDA graph)."""
         n = self.T if n is None else n
-        if self.dev.type != "cuda":
+        if self.dev.type != "cuda" or getattr(self, "serial", False):   # serial: one stream (per-kernel timing)
             return None, [None] * n
         if self.side is None:
             self.side = [torch.cuda.Stream(device=self.dev) for _ in range(max(self.T, 1))]

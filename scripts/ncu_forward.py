@@ -4,7 +4,7 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import mtt_b200
-from oracle import configs
+from mtt_b200 import configs
 
 cfg_name = sys.argv[1] if len(sys.argv) > 1 else "tp_cfg4"
 mode = sys.argv[2] if len(sys.argv) > 2 else "parity"

@@ -3,7 +3,7 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import mtt_b200
-from oracle import configs
+from mtt_b200 import configs
 
 name = sys.argv[1]
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 4
