@@ -378,6 +378,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    # stdout carries exactly one JSON line: NCCL's version banner (NCCL_DEBUG=VERSION, printed to stdout) goes away
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"
     if args.impl == "reference":
         run_reference(args)
     else:

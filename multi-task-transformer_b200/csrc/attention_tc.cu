@@ -354,6 +354,7 @@ static int launch_attn(const CUtensorMap& mh, const CUtensorMap& ml, const AttnP
 
 namespace mtt {
 int launch_attention2(const mtt_attn_desc* d, cudaStream_t stream);  // attention2_tc.cu
+int launch_attention3(const mtt_attn_desc* d, cudaStream_t stream);  // attention3_tc.cu
 static int g_attn_variant = -1;  // -1: read MTT_ATTN_VARIANT once; 0/1 = persistent kernel below (default, fastest
                                  // measured), 2 = attention2_tc.cu (double-buffered S, dedicated issuer warp)
 }  // namespace mtt
@@ -377,6 +378,7 @@ extern "C" int mtt_attention(const mtt_attn_desc* d, mtt_stream_t stream_) {
     g_attn_variant = e ? atoi(e) : 0;
   }
   if (g_attn_variant == 2) return launch_attention2(d, static_cast<cudaStream_t>(stream_));
+  if (g_attn_variant == 3) return launch_attention3(d, static_cast<cudaStream_t>(stream_));
   const int C = d->H * 64;
   CUtensorMap mh, ml;
   const uint64_t dims[3] = {(uint64_t)3 * C, (uint64_t)d->N, (uint64_t)d->B};

@@ -51,6 +51,15 @@ def bench_attn(B, H, N, nsplit, T=5):
 
 if __name__ == "__main__":
     M = 4 * 1029
+    if len(sys.argv) > 1 and sys.argv[1] == "attn":
+        for v in (1, 3):
+            ops.set_attention_variant(v)
+            print("---- attention variant", v)
+            for ns in (2, 1):
+                bench_attn(4, 16, 1029, ns)
+            bench_attn(4, 12, 1012, 2, T=4)
+            bench_attn(1, 16, 8195, 2, T=3)
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "variants":
         for v in (1, 2, 3):
             ops.set_gemm_variant(v)

@@ -165,18 +165,22 @@ def test_conv(cuda_dev, ksize, dil, nsplit, gemm_variant):
         assert e < TOL[nsplit], f"conv {B,H,W,Cin,Cout} k{ksize} d{dil}: rel err {e}"
 
 
-@pytest.mark.parametrize("variant", [1, 2], ids=["persistent", "double_buffered_s"])
+@pytest.mark.parametrize("variant", [1, 2, 3], ids=["persistent", "double_buffered_s", "warp_specialised"])
 @pytest.mark.parametrize("nsplit", [2, 1])
-@pytest.mark.parametrize("B,H,N,T", [(2, 3, 300, 4), (1, 2, 1029, 5), (1, 1, 128, 0), (2, 2, 65, 2), (1, 1, 64, 1),
-                                     (1, 2, 40, 3), (1, 1, 193, 0), (3, 16, 1029, 5)])
-def test_attention(cuda_dev, nsplit, B, H, N, T, variant):
+@pytest.mark.parametrize("B,H,N,T,qscale", [(2, 3, 300, 4, 1.5), (1, 2, 1029, 5, 1.5), (1, 1, 128, 0, 1.5),
+                                            (2, 2, 65, 2, 1.5), (1, 1, 64, 1, 1.5), (1, 2, 40, 3, 1.5),
+                                            (1, 1, 193, 0, 1.5), (3, 16, 1029, 5, 1.5), (5, 16, 1029, 5, 1.5),
+                                            (1, 2, 517, 2, 12.0)])
+def test_attention(cuda_dev, nsplit, B, H, N, T, qscale, variant):
+    """qscale 12: logits spread over ~+-50 nats, so the running maximum moves by more than the lazy-rescaling
+    threshold between key blocks (the rescale / redo paths run); B=5,H=16: more items than persistent CTAs."""
     from mtt_b200 import ops
 
     ops.set_attention_variant(variant)
     torch.manual_seed(11)
     C = H * 64
     qkv = torch.randn(B * N, 3 * C, device=cuda_dev)
-    qkv[:, :C] *= 1.5
+    qkv[:, :C] *= qscale
     Q = ops.split_f32(qkv, nsplit)
     out = ops.Split(B * N, C, cuda_dev, nsplit)
     logits = torch.full((B, H, T, N), float("nan"), device=cuda_dev) if T else None
