@@ -190,13 +190,25 @@ def gemm_roofline(model, plan, x_dev, peaks, peak_src):
         e.record()
         recs.append((s, e, 2.0 * M * N * K * taps, min(N, K) >= 1024))
 
+    arecs = []
+    real_attn = ops.attention
+
+    def timed_attn(q, o, **kw):
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        real_attn(q, o, **kw)
+        e.record()
+        arecs.append((s, e, 4.0 * kw["B"] * kw["H"] * kw["N"] * kw["N"] * 64))
+
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ops.gemm = timed
+    ops.attention = timed_attn
     plan.serial = True
     try:
         plan._launch(x_dev)   # warm
         torch.cuda.synchronize()
         recs.clear()
+        arecs.clear()
         torch.cuda._sleep(int(60e6))   # ~30 ms of device time: the host enqueues the whole forward meanwhile
         f0.record()
         plan._launch(x_dev)
@@ -204,6 +216,7 @@ def gemm_roofline(model, plan, x_dev, peaks, peak_src):
         torch.cuda.synchronize()
     finally:
         ops.gemm = real
+        ops.attention = real_attn
         plan.serial = False
     fwd_ms = f0.elapsed_time(f1)
     tot_ms = sum(s.elapsed_time(e) for s, e, _, _ in recs)
@@ -214,6 +227,8 @@ def gemm_roofline(model, plan, x_dev, peaks, peak_src):
     peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
     mma_factor = 3 if model.nsplit == 2 else 1
     bb = bb_fl / (bb_ms * 1e-3) / 1e12 if bb_ms > 0 else None
+    at_ms = sum(s.elapsed_time(e) for s, e, _ in arecs)
+    at = sum(f for _, _, f in arecs) / (at_ms * 1e-3) / 1e12 if at_ms > 0 else None
     return {
         "bound": "tensor",
         "kernel": "gemm_tc_kernel + gemm2_tc_kernel (every GEMM / implicit-GEMM conv launch of one forward)",
@@ -225,6 +240,11 @@ def gemm_roofline(model, plan, x_dev, peaks, peak_src):
         "backbone_gemms": None if bb is None else {
             "launches": sum(1 for r in recs if r[3]), "achieved": bb, "issued_mma_tflops": bb * mma_factor,
             "issued_mma_frac": bb * mma_factor / peak, "avg_launch_us": bb_ms * 1e3 / sum(1 for r in recs if r[3])},
+        "attention": None if at is None else {
+            "kernel": "attention3_kernel (fused QK^T / softmax / PV, one launch per block)", "launches": len(arecs),
+            "avg_launch_us": at_ms * 1e3 / len(arecs), "achieved": at, "issued_mma_tflops": at * mma_factor,
+            "issued_mma_frac": at * mma_factor / peak, "share_of_forward": at_ms / fwd_ms,
+            "flops": "4*B*H*N*N*64 per launch (QK^T + PV)"},
         "note": ("achieved counts the reference's ALGORITHMIC fp32 FLOPs (2*M*N*K*taps per launch, DESIGN.md); the "
                  f"parity mode issues {mma_factor} bf16 tcgen05.mma per product (issued_mma_*); one eager forward on a "
                  "single stream behind a device-side blocker, CUDA events around every launch; backbone_gemms = the "

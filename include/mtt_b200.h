@@ -130,8 +130,9 @@ typedef struct {
 } mtt_attn_desc;
 
 int mtt_attention(const mtt_attn_desc* d, mtt_stream_t stream);
-/* 0 / 1 = persistent kernel (default; also env MTT_ATTN_VARIANT), 2 = double-buffered-S variant with a
- * dedicated issuer warp. Same function; tuning / testing knob. */
+/* 0 / 3 = warp-specialised kernel (default: TMA warp, MMA warp, 4 softmax warps, 64-key blocks with two S
+ * buffers, Q in TMEM); 1 = the earlier single-role persistent kernel. Same function and results contract;
+ * tuning / testing knob (also env MTT_ATTN_VARIANT). */
 void mtt_set_attention_variant(int variant);
 
 /* ---- patch embedding im2col ---------------------------------------------------------------

@@ -322,6 +322,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
         if (NSPLIT == 2) *reinterpret_cast<uint4*>(p.out_lo + off + i) = lv;
       }
     }
+    __syncthreads();  // xch is rewritten by the next item's first block: every thread must have read its row sums
   }
 
   tc_fence_before();
@@ -353,10 +354,9 @@ static int launch_attn(const CUtensorMap& mh, const CUtensorMap& ml, const AttnP
 }  // namespace mtt
 
 namespace mtt {
-int launch_attention2(const mtt_attn_desc* d, cudaStream_t stream);  // attention2_tc.cu
 int launch_attention3(const mtt_attn_desc* d, cudaStream_t stream);  // attention3_tc.cu
-static int g_attn_variant = -1;  // -1: read MTT_ATTN_VARIANT once; 0/1 = persistent kernel below (default, fastest
-                                 // measured), 2 = attention2_tc.cu (double-buffered S, dedicated issuer warp)
+static int g_attn_variant = -1;  // -1: read MTT_ATTN_VARIANT once; 0 = default = 3 (warp-specialised kernel,
+                                 // attention3_tc.cu), 1 = the single-role persistent kernel in this file
 }  // namespace mtt
 
 extern "C" void mtt_set_attention_variant(int v) { mtt::g_attn_variant = v; }
@@ -377,8 +377,7 @@ extern "C" int mtt_attention(const mtt_attn_desc* d, mtt_stream_t stream_) {
     const char* e = getenv("MTT_ATTN_VARIANT");
     g_attn_variant = e ? atoi(e) : 0;
   }
-  if (g_attn_variant == 2) return launch_attention2(d, static_cast<cudaStream_t>(stream_));
-  if (g_attn_variant == 3) return launch_attention3(d, static_cast<cudaStream_t>(stream_));
+  if (g_attn_variant != 1) return launch_attention3(d, static_cast<cudaStream_t>(stream_));
   const int C = d->H * 64;
   CUtensorMap mh, ml;
   const uint64_t dims[3] = {(uint64_t)3 * C, (uint64_t)d->N, (uint64_t)d->B};

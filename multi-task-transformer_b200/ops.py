@@ -152,7 +152,7 @@ def set_gemm_variant(v):
 
 
 def set_attention_variant(v):
-    """0 / 1 = persistent attention kernel (default), 2 = double-buffered-S variant (tuning / testing knob)."""
+    """0 / 3 = warp-specialised attention kernel (default), 1 = single-role persistent kernel (tuning / testing knob)."""
     _L.load().mtt_set_attention_variant(int(v))
 
 

@@ -52,7 +52,7 @@ def bench_attn(B, H, N, nsplit, T=5):
 if __name__ == "__main__":
     M = 4 * 1029
     if len(sys.argv) > 1 and sys.argv[1] == "attn":
-        for v in (1, 3):
+        for v in [int(x) for x in os.environ.get("ATTN_VARIANTS", "1,3").split(",")]:
             ops.set_attention_variant(v)
             print("---- attention variant", v)
             for ns in (2, 1):
@@ -79,7 +79,3 @@ if __name__ == "__main__":
         bench_gemm(M, 1024, 4096, ns, res=True)
         bench_attn(4, 16, 1029, ns)
     bench_attn(1, 16, 8195, 2, T=3)
-    ops.set_attention_variant(2)
-    print("---- attention variant 2 (double-buffered S)")
-    bench_attn(4, 16, 1029, 2)
-    bench_attn(4, 16, 1029, 1)
