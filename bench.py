@@ -226,6 +226,16 @@ def gemm_roofline(model, plan, x_dev, peaks, peak_src):
     achieved = tot_fl / (tot_ms * 1e-3) / 1e12
     peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
     mma_factor = 3 if model.nsplit == 2 else 1
+    # DRAM bytes per launch of the same kernel family, from the committed ncu capture of one forward of this workload
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "dram_traffic.json")
+    if os.path.exists(tpath) and model.nsplit == 2 and tuple(x_dev.shape) == (4, 3, 512, 512):
+        with open(tpath) as f:
+            tj = json.load(f)
+        traffic = tj["gemm_family"]["bytes_per_launch"]
+        traffic_src = ("dram__bytes_read.sum + dram__bytes_write.sum averaged over the %d GEMM / conv launches of one "
+                       "tp_cfg4 bs 4 forward (profiles/dram_traffic.json <- %s)" % (tj["gemm_family"]["launches"],
+                                                                                    "profiles/r1j_dram_launches.csv"))
     bb = bb_fl / (bb_ms * 1e-3) / 1e12 if bb_ms > 0 else None
     at_ms = sum(s.elapsed_time(e) for s, e, _ in arecs)
     at = sum(f for _, _, f in arecs) / (at_ms * 1e-3) / 1e12 if at_ms > 0 else None
@@ -233,7 +243,8 @@ def gemm_roofline(model, plan, x_dev, peaks, peak_src):
         "bound": "tensor",
         "kernel": "gemm_tc_kernel + gemm2_tc_kernel (every GEMM / implicit-GEMM conv launch of one forward)",
         "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-        "peak_source": f"bf16 dense sustained, {peak_src}", "traffic": None,
+        "peak_source": f"bf16 dense sustained, {peak_src}", "traffic": traffic, "traffic_unit": "bytes per launch",
+        "traffic_source": traffic_src,
         "launches": len(recs), "avg_launch_us": tot_ms * 1e3 / len(recs),
         "share_of_forward": tot_ms / fwd_ms, "serial_forward_ms": fwd_ms,
         "issued_mma_tflops": achieved * mma_factor, "issued_mma_frac": achieved * mma_factor / peak,
@@ -241,7 +252,7 @@ def gemm_roofline(model, plan, x_dev, peaks, peak_src):
             "launches": sum(1 for r in recs if r[3]), "achieved": bb, "issued_mma_tflops": bb * mma_factor,
             "issued_mma_frac": bb * mma_factor / peak, "avg_launch_us": bb_ms * 1e3 / sum(1 for r in recs if r[3])},
         "attention": None if at is None else {
-            "kernel": "attention3_kernel (fused QK^T / softmax / PV, one launch per block)", "launches": len(arecs),
+            "kernel": "attention5_kernel (fused QK^T / softmax / PV, one launch per transformer block)", "launches": len(arecs),
             "avg_launch_us": at_ms * 1e3 / len(arecs), "achieved": at, "issued_mma_tflops": at * mma_factor,
             "issued_mma_frac": at * mma_factor / peak, "share_of_forward": at_ms / fwd_ms,
             "flops": "4*B*H*N*N*64 per launch (QK^T + PV)"},

@@ -130,10 +130,14 @@ typedef struct {
 } mtt_attn_desc;
 
 int mtt_attention(const mtt_attn_desc* d, mtt_stream_t stream);
-/* 0 / 3 = warp-specialised kernel (default: TMA warp, MMA warp, 4 softmax warps, 64-key blocks with two S
- * buffers, Q in TMEM); 1 = the earlier single-role persistent kernel. Same function and results contract;
- * tuning / testing knob (also env MTT_ATTN_VARIANT). */
+/* 0 / 5 = the default warp-specialised kernel (TMA warp, MMA warp, 4 softmax warps, 64-key blocks with two S
+ * buffers, Q in TMEM); 3 = its predecessor (attention3_tc.cu), kept as an independent implementation. Same function
+ * and results contract; tuning / testing knob (also env MTT_ATTN_VARIANT). */
 void mtt_set_attention_variant(int variant);
+/* Debug aid: a device buffer of 4096 uint32 that receives %clock stamps of the MMA warp and of softmax warp 0 of
+ * two co-resident CTAs for every following parity-mode launch of the warp-specialised kernel (NULL = off, the
+ * default; the traced kernel is a separate instantiation). See scripts/attn_trace.py. */
+void mtt_set_attention_trace(void* device_buf);
 
 /* ---- patch embedding im2col ---------------------------------------------------------------
  * timm PatchEmbed (Conv2d k = s = patch) as a GEMM: img NCHW fp32 -> split [B*P, Cin*patch*patch],

@@ -1,3 +1,13 @@
+// Fused multi-head attention, variant 5 of mtt_attention = attention3_tc.cu after the clock-stamp timeline of
+// profiles/r1k_attention_trace.md (a block costs a CTA ~2150 cycles for 768 cycles of tensor work; the softmax warps
+// are XU-bound when both resident CTAs are in phase, the MMA warp spends ~850 cycles per block on non-MMA issue
+// overhead, and an item boundary costs ~7500 cycles):
+//   * the hi plane of P is rounded on the integer pipe (add 0x8000, PRMT), only the lo plane goes through F2FP:
+//     one XU instruction per pair instead of two (XU: 130 -> 98 warp instructions per block);
+//   * two tcgen05.commit per block instead of four: the TMA warp waits on s_ready / pv_done (the K slot of block g
+//     is free when S_{g-2} is complete, the V slot when PV_{g-2} has retired; two stages = two S buffers);
+//   * the item epilogue writes whole 32-byte sectors (st.global.v8) instead of 16-byte halves.
+// Everything else as in variant 3:
 // Fused multi-head attention, warp-specialised variant (variant 3 of mtt_attention; same contract as
 // attention_tc.cu: TP/models/transformers/taskprompter.py:204-210, prompt-row raw logits :436-437,:482).
 //
@@ -25,26 +35,28 @@
 
 namespace mtt {
 
-constexpr int kA3Threads = 192;            // warps 0-3: softmax (thread = query row), 4: MMA issue, 5: TMA
-constexpr uint32_t kA3QTile = 128 * 64 * 2;  // one plane of the query tile (16 KB)
-constexpr uint32_t kA3KVTile = 64 * 64 * 2;  // one plane of a 64-key K or V block (8 KB)
-constexpr int kA3KStages = 2;
-constexpr int kA3VStages = 2;
-constexpr float kA3LazyLog2 = 8.0f;
+constexpr int kA5Threads = 192;            // warps 0-3: softmax (thread = query row), 4: MMA issue, 5: TMA
+constexpr uint32_t kA5QTile = 128 * 64 * 2;  // one plane of the query tile (16 KB)
+constexpr uint32_t kA5KVTile = 64 * 64 * 2;  // one plane of a 64-key K or V block (8 KB)
+constexpr int kA5KStages = 2;
+constexpr int kA5VStages = 2;
+constexpr float kA5LazyLog2 = 8.0f;
+static_assert(kA5KStages == 2 && kA5VStages == 2, "the TMA warp reuses s_ready / pv_done (two S buffers) as slot-free signals");
 
-struct Attn3Params {
+struct Attn5Params {
   int B, N, H, T;
   float scale_log2;  // scale * log2(e)
   __nv_bfloat16* out_hi;
   __nv_bfloat16* out_lo;
   float* prompt_logits;
+  int wide_store;       // out planes 32-byte aligned: st.global.v8
   unsigned int* trace;  // TRACE instantiation only: [2 CTAs][2 roles][1024] clock stamps (scripts/attn_trace.py)
 };
 
 // One pass over this thread's row of S_j (64 columns in TMEM): tracks the raw block maximum, and -- against the
 // scaled running maximum mb -- produces P = exp2(S c - mb) as packed bf16 hi / lo and its row sum.
 template <bool FULL, int NSPLIT>
-__device__ __forceinline__ float softmax_block(uint32_t taddr, int kn, float sl2, float mb, float& bmax,
+__device__ __forceinline__ float softmax_block5(uint32_t taddr, int kn, float sl2, float mb, float& bmax,
                                                uint32_t (&ph)[32], uint32_t (&pl)[32], float* export_ptr) {
   float sum = 0.f, mx = -INFINITY;
 #pragma unroll
@@ -74,10 +86,11 @@ __device__ __forceinline__ float softmax_block(uint32_t taddr, int kn, float sl2
         if (c * 32 + i + 1 < kn) mx = fmaxf(mx, s1); else p1 = 0.f;
       }
       sum += p0 + p1;
-      uint32_t h, l;
-      split_pack2(p0, p1, h, l);
-      ph[c * 16 + (i >> 1)] = h;
-      if (NSPLIT == 2) pl[c * 16 + (i >> 1)] = l;
+      // hi = bf16(p) by round-half-up on the integer pipe (p is finite and >= 0), lo = bf16(p - hi) by F2FP
+      const uint32_t u0 = __float_as_uint(p0) + 0x8000u, u1 = __float_as_uint(p1) + 0x8000u;
+      ph[c * 16 + (i >> 1)] = __byte_perm(u0, u1, 0x7632);
+      if (NSPLIT == 2)
+        pl[c * 16 + (i >> 1)] = pack_bf16x2(p0 - __uint_as_float(u0 & 0xFFFF0000u), p1 - __uint_as_float(u1 & 0xFFFF0000u));
     }
   }
   bmax = mx;
@@ -86,7 +99,7 @@ __device__ __forceinline__ float softmax_block(uint32_t taddr, int kn, float sl2
 
 // raw maximum of this thread's row of S_j (first block of an item: the running maximum does not exist yet)
 template <bool FULL>
-__device__ __forceinline__ float block_max(uint32_t taddr, int kn) {
+__device__ __forceinline__ float block_max5(uint32_t taddr, int kn) {
   float mx = -INFINITY;
 #pragma unroll
   for (int c = 0; c < 2; ++c) {
@@ -102,24 +115,24 @@ __device__ __forceinline__ float block_max(uint32_t taddr, int kn) {
 }
 
 template <int NSPLIT, bool TRACE>
-__global__ void __launch_bounds__(kA3Threads, 2)
-attention3_kernel(const __grid_constant__ CUtensorMap tmq_hi, const __grid_constant__ CUtensorMap tmq_lo,
+__global__ void __launch_bounds__(kA5Threads, 2)
+attention5_kernel(const __grid_constant__ CUtensorMap tmq_hi, const __grid_constant__ CUtensorMap tmq_lo,
                   const __grid_constant__ CUtensorMap tmk_hi, const __grid_constant__ CUtensorMap tmk_lo,
-                  const Attn3Params p) {
+                  const Attn5Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
   uint8_t* sQ = smem;                                  // [NSPLIT][16 KB]
-  uint8_t* sK = sQ + NSPLIT * kA3QTile;                // [kA3KStages][NSPLIT][8 KB]
-  uint8_t* sV = sK + kA3KStages * NSPLIT * kA3KVTile;  // [kA3VStages][NSPLIT][8 KB]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + kA3VStages * NSPLIT * kA3KVTile);
+  uint8_t* sK = sQ + NSPLIT * kA5QTile;                // [kA5KStages][NSPLIT][8 KB]
+  uint8_t* sV = sK + kA5KStages * NSPLIT * kA5KVTile;  // [kA5VStages][NSPLIT][8 KB]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + kA5VStages * NSPLIT * kA5KVTile);
   uint64_t* q_full = bars + 0;    // TMA: next query tile landed in sQ
   uint64_t* q_ready = bars + 1;   // softmax warps: query tile copied to TMEM (sQ free again), count 4
-  uint64_t* k_full = bars + 2;    // [kA3KStages]
-  uint64_t* k_empty = k_full + kA3KStages;
-  uint64_t* v_full = k_empty + kA3KStages;  // [kA3VStages]
-  uint64_t* v_empty = v_full + kA3VStages;
-  uint64_t* s_ready = v_empty + kA3VStages;  // [2] S_j complete in TMEM
+  uint64_t* k_full = bars + 2;    // [kA5KStages]
+  uint64_t* k_empty = k_full + kA5KStages;
+  uint64_t* v_full = k_empty + kA5KStages;  // [kA5VStages]
+  uint64_t* v_empty = v_full + kA5VStages;
+  uint64_t* s_ready = v_empty + kA5VStages;  // [2] S_j complete in TMEM
   uint64_t* p_ready = s_ready + 2;           // [2] P_j published by the 4 softmax warps
   uint64_t* pv_done = p_ready + 2;           // [2] O += P_j V_j retired (two barriers: a softmax warp may be two
                                              //     PVs behind, which one parity bit cannot tell apart)
@@ -141,11 +154,11 @@ attention3_kernel(const __grid_constant__ CUtensorMap tmq_hi, const __grid_const
     }
     mbar_init(q_full, 1);
     mbar_init(q_ready, 4);
-    for (int s = 0; s < kA3KStages; ++s) {
+    for (int s = 0; s < kA5KStages; ++s) {
       mbar_init(&k_full[s], 1);
       mbar_init(&k_empty[s], 1);
     }
-    for (int s = 0; s < kA3VStages; ++s) {
+    for (int s = 0; s < kA5VStages; ++s) {
       mbar_init(&v_full[s], 1);
       mbar_init(&v_empty[s], 1);
     }
@@ -185,27 +198,27 @@ attention3_kernel(const __grid_constant__ CUtensorMap tmq_hi, const __grid_const
       int qt, h, b;
       item_coords(item, qt, h, b);
       if (qi == 0 && elect_one()) {
-        mbar_arrive_expect_tx(q_full, NSPLIT * kA3QTile);
+        mbar_arrive_expect_tx(q_full, NSPLIT * kA5QTile);
         tma_load_3d(sQ, &tmq_hi, q_full, h * 64, qt * 128, b);
-        if (NSPLIT == 2) tma_load_3d(sQ + kA3QTile, &tmq_lo, q_full, h * 64, qt * 128, b);
+        if (NSPLIT == 2) tma_load_3d(sQ + kA5QTile, &tmq_lo, q_full, h * 64, qt * 128, b);
       }
       __syncwarp();
       for (int j = 0; j < nkv; ++j, ++g) {
-        const int ks = g % kA3KStages, vs = g % kA3VStages;
-        mbar_wait(&k_empty[ks], ((g / kA3KStages) & 1) ^ 1);
+        const int ks = g % kA5KStages, vs = g % kA5VStages;
+        if (g >= 2) mbar_wait(&s_ready[g & 1], ((g - 2) >> 1) & 1);  // S_{g-2} complete: its K slot is free
         if (elect_one()) {
-          uint8_t* dk = sK + ks * NSPLIT * kA3KVTile;
-          mbar_arrive_expect_tx(&k_full[ks], NSPLIT * kA3KVTile);
+          uint8_t* dk = sK + ks * NSPLIT * kA5KVTile;
+          mbar_arrive_expect_tx(&k_full[ks], NSPLIT * kA5KVTile);
           tma_load_3d(dk, &tmk_hi, &k_full[ks], C + h * 64, j * 64, b);
-          if (NSPLIT == 2) tma_load_3d(dk + kA3KVTile, &tmk_lo, &k_full[ks], C + h * 64, j * 64, b);
+          if (NSPLIT == 2) tma_load_3d(dk + kA5KVTile, &tmk_lo, &k_full[ks], C + h * 64, j * 64, b);
         }
         __syncwarp();
-        mbar_wait(&v_empty[vs], ((g / kA3VStages) & 1) ^ 1);
+        if (g >= 2) mbar_wait(&pv_done[g & 1], ((g - 2) >> 1) & 1);  // PV_{g-2} retired: its V slot is free
         if (elect_one()) {
-          uint8_t* dv = sV + vs * NSPLIT * kA3KVTile;
-          mbar_arrive_expect_tx(&v_full[vs], NSPLIT * kA3KVTile);
+          uint8_t* dv = sV + vs * NSPLIT * kA5KVTile;
+          mbar_arrive_expect_tx(&v_full[vs], NSPLIT * kA5KVTile);
           tma_load_3d(dv, &tmk_hi, &v_full[vs], 2 * C + h * 64, j * 64, b);
-          if (NSPLIT == 2) tma_load_3d(dv + kA3KVTile, &tmk_lo, &v_full[vs], 2 * C + h * 64, j * 64, b);
+          if (NSPLIT == 2) tma_load_3d(dv + kA5KVTile, &tmk_lo, &v_full[vs], 2 * C + h * 64, j * 64, b);
         }
         __syncwarp();
         if (j == 0 && item + (int)gridDim.x < total) {
@@ -214,9 +227,9 @@ attention3_kernel(const __grid_constant__ CUtensorMap tmq_hi, const __grid_const
           if (elect_one()) {
             int qt2, h2, b2;
             item_coords(item + gridDim.x, qt2, h2, b2);
-            mbar_arrive_expect_tx(q_full, NSPLIT * kA3QTile);
+            mbar_arrive_expect_tx(q_full, NSPLIT * kA5QTile);
             tma_load_3d(sQ, &tmq_hi, q_full, h2 * 64, qt2 * 128, b2);
-            if (NSPLIT == 2) tma_load_3d(sQ + kA3QTile, &tmq_lo, q_full, h2 * 64, qt2 * 128, b2);
+            if (NSPLIT == 2) tma_load_3d(sQ + kA5QTile, &tmq_lo, q_full, h2 * 64, qt2 * 128, b2);
           }
           __syncwarp();
         }
@@ -236,26 +249,25 @@ attention3_kernel(const __grid_constant__ CUtensorMap tmq_hi, const __grid_const
         mbar_wait(q_ready, qis & 1);  // Q of this item is in TMEM
         tc_fence_after();
       }
-      const int ks_ = gs % kA3KStages;
-      mbar_wait(&k_full[ks_], (gs / kA3KStages) & 1);
+      const int ks_ = gs % kA5KStages;
+      mbar_wait(&k_full[ks_], (gs / kA5KStages) & 1);
       tc_fence_after();
       const int kn = min(64, p.N - (int)js * 64);
       const uint32_t idesc_s = umma_idesc_bf16(128, (kn + 15) & ~15, 0);
       const uint32_t tS = tmem_base + (gs & 1) * 64;
-      const uint32_t kh = smem_u32(sK + ks_ * NSPLIT * kA3KVTile);
+      const uint32_t kh = smem_u32(sK + ks_ * NSPLIT * kA5KVTile);
       if (elect_one()) {
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
           const uint64_t kdh = umma_desc_sw128(kh + ks * 32);
           umma_ts(tS, tQ + ks * 8, kdh, idesc_s, ks > 0);
           if (NSPLIT == 2) {
-            const uint64_t kdl = umma_desc_sw128(kh + kA3KVTile + ks * 32);
+            const uint64_t kdl = umma_desc_sw128(kh + kA5KVTile + ks * 32);
             umma_ts(tS, tQ + ks * 8, kdl, idesc_s, 1);
             umma_ts(tS, tQ + 32 + ks * 8, kdh, idesc_s, 1);
           }
         }
         umma_commit(&s_ready[gs & 1]);
-        umma_commit(&k_empty[ks_]);
       }
       __syncwarp();
       ++gs;
@@ -268,26 +280,25 @@ attention3_kernel(const __grid_constant__ CUtensorMap tmq_hi, const __grid_const
     if (nblocks > 1) issue_s();
     uint32_t jp = 0;
     for (uint32_t gp = 0; gp < nblocks; ++gp) {
-      const int vs = gp % kA3VStages;
+      const int vs = gp % kA5VStages;
       mbar_wait(&p_ready[gp & 1], (gp >> 1) & 1);
       stamp(1);
-      mbar_wait(&v_full[vs], (gp / kA3VStages) & 1);
+      mbar_wait(&v_full[vs], (gp / kA5VStages) & 1);
       tc_fence_after();
       const int kn = min(64, p.N - (int)jp * 64);
       const int ksteps = (kn + 15) >> 4;
       const uint32_t tP = tmem_base + (gp & 1) * 64;
-      const uint32_t vh = smem_u32(sV + vs * NSPLIT * kA3KVTile);
+      const uint32_t vh = smem_u32(sV + vs * NSPLIT * kA5KVTile);
       if (elect_one()) {
         for (int ks = 0; ks < ksteps; ++ks) {
           const uint64_t vdh = umma_desc_sw128(vh + ks * 2048);
           umma_ts(tO, tP + ks * 8, vdh, idesc_o, (jp > 0 || ks > 0) ? 1u : 0u);
           if (NSPLIT == 2) {
-            const uint64_t vdl = umma_desc_sw128(vh + kA3KVTile + ks * 2048);
+            const uint64_t vdl = umma_desc_sw128(vh + kA5KVTile + ks * 2048);
             umma_ts(tO, tP + ks * 8, vdl, idesc_o, 1);
             umma_ts(tO, tP + 32 + ks * 8, vdh, idesc_o, 1);
           }
         }
-        umma_commit(&v_empty[vs]);
         umma_commit(&pv_done[gp & 1]);
       }
       __syncwarp();
@@ -305,7 +316,7 @@ attention3_kernel(const __grid_constant__ CUtensorMap tmq_hi, const __grid_const
 #pragma unroll
       for (int pl_ = 0; pl_ < NSPLIT; ++pl_) {
         uint32_t r[32];
-        const uint8_t* base = sQ + pl_ * kA3QTile + row * 128;
+        const uint8_t* base = sQ + pl_ * kA5QTile + row * 128;
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           const uint4 v = *reinterpret_cast<const uint4*>(base + ((c ^ (row & 7)) << 4));
@@ -350,10 +361,10 @@ attention3_kernel(const __grid_constant__ CUtensorMap tmq_hi, const __grid_const
         float* ex = export_row ? export_base + j * 64 : nullptr;
         uint32_t ph[32], pl[32];
         float bmax, sum;
-        if (j == 0) m_run = full ? block_max<true>(tS, kn) : block_max<false>(tS, kn);
-        sum = full ? softmax_block<true, NSPLIT>(tS, kn, p.scale_log2, m_run * p.scale_log2, bmax, ph, pl, ex)
-                   : softmax_block<false, NSPLIT>(tS, kn, p.scale_log2, m_run * p.scale_log2, bmax, ph, pl, ex);
-        const bool need = (bmax - m_run) * p.scale_log2 > kA3LazyLog2;
+        if (j == 0) m_run = full ? block_max5<true>(tS, kn) : block_max5<false>(tS, kn);
+        sum = full ? softmax_block5<true, NSPLIT>(tS, kn, p.scale_log2, m_run * p.scale_log2, bmax, ph, pl, ex)
+                   : softmax_block5<false, NSPLIT>(tS, kn, p.scale_log2, m_run * p.scale_log2, bmax, ph, pl, ex);
+        const bool need = (bmax - m_run) * p.scale_log2 > kA5LazyLog2;
         if (__any_sync(0xffffffffu, need)) {
           // rare: the block maximum ran away from the running maximum.  O / l are rescaled (O is quiescent: PV_{g-1}
           // has retired and PV_g needs this warp's P_g) and the block is redone against the new maximum.
@@ -371,8 +382,8 @@ attention3_kernel(const __grid_constant__ CUtensorMap tmq_hi, const __grid_const
           }
           l_run *= alpha;
           if (need) m_run = bmax;
-          sum = full ? softmax_block<true, NSPLIT>(tS, kn, p.scale_log2, m_run * p.scale_log2, bmax, ph, pl, nullptr)
-                     : softmax_block<false, NSPLIT>(tS, kn, p.scale_log2, m_run * p.scale_log2, bmax, ph, pl,
+          sum = full ? softmax_block5<true, NSPLIT>(tS, kn, p.scale_log2, m_run * p.scale_log2, bmax, ph, pl, nullptr)
+                     : softmax_block5<false, NSPLIT>(tS, kn, p.scale_log2, m_run * p.scale_log2, bmax, ph, pl,
                                                     nullptr);
         }
         l_run += sum;
@@ -399,14 +410,22 @@ attention3_kernel(const __grid_constant__ CUtensorMap tmq_hi, const __grid_const
         tmem_ld_wait();
         if (q_row < p.N) {
 #pragma unroll
-          for (int i = 0; i < 32; i += 8) {
-            uint4 hv, lv;
-            split_pack2(__uint_as_float(o[i]) * inv, __uint_as_float(o[i + 1]) * inv, hv.x, lv.x);
-            split_pack2(__uint_as_float(o[i + 2]) * inv, __uint_as_float(o[i + 3]) * inv, hv.y, lv.y);
-            split_pack2(__uint_as_float(o[i + 4]) * inv, __uint_as_float(o[i + 5]) * inv, hv.z, lv.z);
-            split_pack2(__uint_as_float(o[i + 6]) * inv, __uint_as_float(o[i + 7]) * inv, hv.w, lv.w);
-            *reinterpret_cast<uint4*>(p.out_hi + off + c * 32 + i) = hv;
-            if (NSPLIT == 2) *reinterpret_cast<uint4*>(p.out_lo + off + c * 32 + i) = lv;
+          for (int i = 0; i < 32; i += 16) {
+            U32x8 hv, lv;
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              split_pack2(__uint_as_float(o[i + 2 * k]) * inv, __uint_as_float(o[i + 2 * k + 1]) * inv, hv.v[k], lv.v[k]);
+            if (p.wide_store) {  // whole 32-byte sectors per lane
+              st_global_v8(p.out_hi + off + c * 32 + i, hv);
+              if (NSPLIT == 2) st_global_v8(p.out_lo + off + c * 32 + i, lv);
+            } else {
+              *reinterpret_cast<uint4*>(p.out_hi + off + c * 32 + i) = make_uint4(hv.v[0], hv.v[1], hv.v[2], hv.v[3]);
+              *reinterpret_cast<uint4*>(p.out_hi + off + c * 32 + i + 8) = make_uint4(hv.v[4], hv.v[5], hv.v[6], hv.v[7]);
+              if (NSPLIT == 2) {
+                *reinterpret_cast<uint4*>(p.out_lo + off + c * 32 + i) = make_uint4(lv.v[0], lv.v[1], lv.v[2], lv.v[3]);
+                *reinterpret_cast<uint4*>(p.out_lo + off + c * 32 + i + 8) = make_uint4(lv.v[4], lv.v[5], lv.v[6], lv.v[7]);
+              }
+            }
           }
         }
       }
@@ -423,12 +442,12 @@ attention3_kernel(const __grid_constant__ CUtensorMap tmq_hi, const __grid_const
 }
 
 template <int NSPLIT, bool TRACE>
-static int launch_attn3(const CUtensorMap* maps, const Attn3Params& p, cudaStream_t stream) {
+static int launch_attn5(const CUtensorMap* maps, const Attn5Params& p, cudaStream_t stream) {
   constexpr uint32_t smem =
-      NSPLIT * kA3QTile + (kA3KStages + kA3VStages) * NSPLIT * kA3KVTile + 1024 + 256;
+      NSPLIT * kA5QTile + (kA5KStages + kA5VStages) * NSPLIT * kA5KVTile + 1024 + 256;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attention3_kernel<NSPLIT, TRACE>,
+    cudaError_t e = cudaFuncSetAttribute(attention5_kernel<NSPLIT, TRACE>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess)
       return set_error(MTT_ERR_LAUNCH, "attention3: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
@@ -436,18 +455,14 @@ static int launch_attn3(const CUtensorMap* maps, const Attn3Params& p, cudaStrea
   }
   const int total = ((p.N + 127) / 128) * p.H * p.B;
   const int slots = 2 * sm_count();
-  attention3_kernel<NSPLIT, TRACE><<<total < slots ? total : slots, kA3Threads, smem, stream>>>(maps[0], maps[1], maps[2],
+  attention5_kernel<NSPLIT, TRACE><<<total < slots ? total : slots, kA5Threads, smem, stream>>>(maps[0], maps[1], maps[2],
                                                                                        maps[3], p);
-  return check_launch("mtt_attention(variant 3)");
+  return check_launch("mtt_attention(variant 5)");
 }
 
-unsigned int* g_attn_trace = nullptr;  // shared with attention5_tc.cu
-}  // namespace mtt
-// debug: a device buffer of 4096 uint32 receives clock stamps of the next parity-mode launches (NULL = off)
-extern "C" void mtt_set_attention_trace(void* buf) { mtt::g_attn_trace = static_cast<unsigned int*>(buf); }
-namespace mtt {
+extern unsigned int* g_attn_trace;  // attention3_tc.cu (mtt_set_attention_trace)
 
-int launch_attention3(const mtt_attn_desc* d, cudaStream_t stream) {
+int launch_attention5(const mtt_attn_desc* d, cudaStream_t stream) {
   const int C = d->H * 64;
   CUtensorMap maps[4];
   const uint64_t dims[3] = {(uint64_t)3 * C, (uint64_t)d->N, (uint64_t)d->B};
@@ -464,7 +479,7 @@ int launch_attention3(const mtt_attn_desc* d, cudaStream_t stream) {
     maps[1] = maps[0];
     maps[3] = maps[2];
   }
-  Attn3Params p;
+  Attn5Params p;
   p.B = d->B;
   p.N = d->N;
   p.H = d->H;
@@ -473,9 +488,10 @@ int launch_attention3(const mtt_attn_desc* d, cudaStream_t stream) {
   p.out_hi = static_cast<__nv_bfloat16*>(d->out_hi);
   p.out_lo = static_cast<__nv_bfloat16*>(d->out_lo);
   p.prompt_logits = d->prompt_logits;
+  p.wide_store = ((reinterpret_cast<uintptr_t>(d->out_hi) | reinterpret_cast<uintptr_t>(d->out_lo)) & 31) == 0;
   p.trace = g_attn_trace;
-  if (g_attn_trace && d->nsplit == 2) return launch_attn3<2, true>(maps, p, stream);
-  return d->nsplit == 2 ? launch_attn3<2, false>(maps, p, stream) : launch_attn3<1, false>(maps, p, stream);
+  if (g_attn_trace && d->nsplit == 2) return launch_attn5<2, true>(maps, p, stream);
+  return d->nsplit == 2 ? launch_attn5<2, false>(maps, p, stream) : launch_attn5<1, false>(maps, p, stream);
 }
 
 }  // namespace mtt

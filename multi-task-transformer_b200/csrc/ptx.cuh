@@ -36,6 +36,18 @@ __device__ __forceinline__ void setmaxnreg_inc() {
   asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegs));
 }
 
+// ---------------------------------------------------------------- debug: SM clock / SM id
+__device__ __forceinline__ unsigned int clock32() {
+  unsigned int c;
+  asm volatile("mov.u32 %0, %%clock;" : "=r"(c));
+  return c;
+}
+__device__ __forceinline__ unsigned int smid() {
+  unsigned int c;
+  asm volatile("mov.u32 %0, %%smid;" : "=r"(c));
+  return c;
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));

@@ -66,6 +66,7 @@ SYMBOLS = {
     "mtt_set_gemm_variant": (None, [C.c_int]),
     "mtt_attention": (C.c_int, [C.POINTER(AttnDesc), _vp]),
     "mtt_set_attention_variant": (None, [C.c_int]),
+    "mtt_set_attention_trace": (None, [C.c_void_p]),
     "mtt_im2col_patch": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _i64, _vp]),
     "mtt_broadcast_rows": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i64, _i64, _vp]),
     "mtt_chan_logits": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),

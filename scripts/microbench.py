@@ -52,7 +52,7 @@ def bench_attn(B, H, N, nsplit, T=5):
 if __name__ == "__main__":
     M = 4 * 1029
     if len(sys.argv) > 1 and sys.argv[1] == "attn":
-        for v in [int(x) for x in os.environ.get("ATTN_VARIANTS", "1,3").split(",")]:
+        for v in [int(x) for x in os.environ.get("ATTN_VARIANTS", "3,5").split(",")]:
             ops.set_attention_variant(v)
             print("---- attention variant", v)
             for ns in (2, 1):
