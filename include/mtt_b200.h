@@ -199,6 +199,15 @@ int mtt_bilinear_postproc(const float* in, int64_t ld_in, int32_t B, int32_t h, 
                           int32_t H2, int32_t W2, int32_t kind, int64_t* out_i64, float* out_f32,
                           mtt_stream_t stream);
 
+/* Inference-time image pre-processing of the reference in one kernel -- the step in FRONT of the hot path
+ * (SURVEY.md section 8f N3): TP/inference.py:127-133 (cv2.imread, float32, BGR2RGB), :93-115 get_infer_transforms =
+ * Normalize (data/transforms.py:236-251: x/255, -mean, /std) -> DirectResize (inference.py:66-81: cv2.resize
+ * INTER_LINEAR) -> ToTensor (transforms.py:265-273). img: uint8 [B,h,w,3] on the device, channel order BGR if
+ * bgr != 0 (cv2.imread) else RGB; mean3 / std3: HOST pointers to three floats (RGB order); out: fp32 NCHW
+ * [B,3,H,W], ready for mtt_im2col_patch. */
+int mtt_preprocess_image(const uint8_t* img, int32_t B, int32_t h, int32_t w, int32_t bgr, const float* mean3,
+                         const float* std3, float* out, int32_t H, int32_t W, mtt_stream_t stream);
+
 /* Sum of up to three bilinearly resized NHWC fp32 sources written once as a split tensor [B*H2*W2, ld_bf]:
  * InvPT's multi-scale aggregation of the three stages' per-task maps (IP invpt.py:528-539), in the
  * reference's accumulation order, without read-modify-write passes over the full-resolution map. */

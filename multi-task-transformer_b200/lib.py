@@ -76,6 +76,8 @@ SYMBOLS = {
     "mtt_ctr_mix": (C.c_int, [_vp, _vp, _vp, _i32, _i64, _i32, _i64, _i32, _i32, _vp]),
     "mtt_bilinear": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _i64, _vp, _vp, _i64, _vp,
                                _i32, _i64, _i64, _i64, _i64, _vp]),
+    "mtt_preprocess_image": (C.c_int, [_vp, _i32, _i32, _i32, _i32, C.POINTER(C.c_float), C.POINTER(C.c_float), _vp,
+                                       _i32, _i32, _vp]),
     "mtt_bilinear_postproc": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
     "mtt_bilinear_sum3": (C.c_int, [C.POINTER(BilinearSrc), _i32, _i32, _i32, _i32, _i32, _vp, _vp, _i64, _vp]),
     "mtt_split_rows": (C.c_int, [_vp, _i64, _i64, _i64, _i64, _vp, _vp, _i64, _i64, _i32, _vp]),

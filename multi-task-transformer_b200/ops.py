@@ -235,6 +235,30 @@ def bilinear_postproc(x, ld_in, B, h, w, Cdim, H2, W2, kind, out):
     _L.check(rc, "mtt_bilinear_postproc")
 
 
+IMAGENET_MEAN = (0.485, 0.456, 0.406)   # TP/inference.py:99,107
+IMAGENET_STD = (0.229, 0.224, 0.225)
+
+
+def preprocess_image(img_u8, out_hw, *, bgr=True, mean=IMAGENET_MEAN, std=IMAGENET_STD, out=None):
+    """The reference's inference pre-processing (TP/inference.py:93-115,127-133) on the device: img_u8 is a CUDA
+    uint8 tensor [h,w,3] or [B,h,w,3] as cv2.imread returns it (BGR); returns fp32 [B,3,H,W] normalised and
+    bilinearly resized (cv2 INTER_LINEAR), the tensor `model(x)` takes."""
+    import ctypes
+    if img_u8.dim() == 3:
+        img_u8 = img_u8.unsqueeze(0)
+    assert img_u8.is_cuda and img_u8.dtype == torch.uint8 and img_u8.is_contiguous() and img_u8.shape[-1] == 3
+    B, h, w, _ = img_u8.shape
+    H, W = out_hw
+    if out is None:
+        out = torch.empty(B, 3, H, W, device=img_u8.device, dtype=torch.float32)
+    assert out.is_contiguous() and tuple(out.shape) == (B, 3, H, W) and out.dtype == torch.float32
+    m3 = (ctypes.c_float * 3)(*mean)
+    s3 = (ctypes.c_float * 3)(*std)
+    rc = _L.load().mtt_preprocess_image(_ptr(img_u8), B, h, w, int(bool(bgr)), m3, s3, _ptr(out), H, W, _stream())
+    _L.check(rc, "mtt_preprocess_image")
+    return out
+
+
 def bilinear_sum3(srcs, out, *, B, Cdim, H2, W2):
     """out (Split [B*H2*W2, C]) = sum_i bilinear(src_i -> H2 x W2); srcs: list of up to three
     (tensor fp32 [rows, ld], h, w, batch_rows, row_offset)."""
