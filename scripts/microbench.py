@@ -49,8 +49,30 @@ def bench_attn(B, H, N, nsplit, T=5):
           f"{fl*(3 if nsplit==2 else 1)/ms/1e9:.1f} TFLOP/s bf16-MMA")
 
 
+def bench_conv(B, H, W, Cin, Cout, nsplit, act=ops.ACT_GELU):
+    from mtt_b200 import pack
+    x = ops.split_f32(torch.randn(B * H * W, Cin, device=dev), nsplit)
+    w = pack.pack_conv_weight(torch.randn(Cout, Cin, 3, 3, device=dev) * 0.02, nsplit)
+    bias = torch.randn(Cout, device=dev)
+    osp = ops.Split(B * H * W, Cout, dev, nsplit)
+    fn = lambda: ops.gemm(x, w, N=Cout, K=Cin, bias=bias, act=act, out_split=osp, conv=(B, H, W, 3, 1))
+    ms = timeit(fn)
+    fl = 2.0 * B * H * W * Cout * 9 * Cin
+    print(f"conv3x3 B={B} {H}x{W} {Cin}->{Cout} nsplit={nsplit}: {ms*1e3:.1f} us  {fl/ms/1e9:.1f} TFLOP/s algorithmic, "
+          f"{fl*(3 if nsplit==2 else 1)/ms/1e9:.1f} TFLOP/s bf16-MMA")
+
+
 if __name__ == "__main__":
     M = 4 * 1029
+    if len(sys.argv) > 1 and sys.argv[1] == "conv":
+        for v in (1, 2, 3):
+            ops.set_gemm_variant(v)
+            print("---- gemm variant", v)
+            bench_conv(4, 128, 128, 350, 350, 2)      # TaskPrompter ConvHead.mt_proj (taskprompter.py:691), cfg4
+            bench_conv(4, 32, 32, 350, 350, 2)        # fea_fuse 3x3 (:362), cfg4
+            bench_conv(4, 128, 128, 576, 576, 2)      # InvPT mt_proj (invpt.py:493), cfg3
+            bench_conv(4, 112, 144, 768, 768, 2)      # ConvHead, cfg2
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "attn":
         for v in [int(x) for x in os.environ.get("ATTN_VARIANTS", "3,5").split(",")]:
             ops.set_attention_variant(v)
