@@ -72,6 +72,9 @@ if __name__ == "__main__":
             bench_conv(4, 32, 32, 350, 350, 2)        # fea_fuse 3x3 (:362), cfg4
             bench_conv(4, 128, 128, 576, 576, 2)      # InvPT mt_proj (invpt.py:493), cfg3
             bench_conv(4, 112, 144, 768, 768, 2)      # ConvHead, cfg2
+            bench_conv(4, 28, 36, 768, 768, 2)        # fea_fuse 3x3, cfg2 (48 pair tiles)
+            bench_conv(4, 16, 16, 1024, 1024, 2, act=ops.ACT_RELU)   # InvPT ConvBlock (16 pair tiles)
+            bench_conv(4, 16, 16, 1024, 512, 2, act=ops.ACT_RELU)
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "attn":
         for v in [int(x) for x in os.environ.get("ATTN_VARIANTS", "3,5").split(",")]:
