@@ -199,15 +199,19 @@ extern "C" int mtt_gemm(const mtt_gemm_desc* d, mtt_stream_t stream_) {
     // measured on B200 (profiles/r1d_gemm_variants.md): the 256x256 CTA pair wins when there is enough
     // work per tile column (qkv / fc1: N >= 2048, fc2: K >= 2048); the single-CTA 128x128 tile wins for
     // narrow or ragged N (decoder widths 300 / 350), short K with N = 1024 (proj), and skinny M (token_trans)
-    // A 3x3 convolution reduces over taps x Cin: ConvHead 768 -> 768 at 112x144 (cfg2) is K = 6912 and runs 16 %
-    // faster on the CTA pair (1246 vs 1481 us, profiles/r1p_conv_variants.txt).
     const int n256 = (d->N + 255) / 256 * 256;
-    const bool wide = d->N >= 512 && (n256 - d->N) * 8 <= n256;
-    // Only with enough pair tiles to fill the 74 CTA pairs (InvPT's 1024 -> 1024 ConvBlock at 16x16 has 16).
-    const long long k_eff = (long long)d->K * (d->mode == 1 ? d->ksize * d->ksize : 1);
-    const long long pair_tiles = (long long)((d->M + 255) / 256) * (n256 / 256);
-    const bool long_k = d->mode == 1 ? (k_eff >= 2048 && pair_tiles >= 64) : d->K >= 2048;
-    v = (wide && d->M > 128 && (d->N >= 2048 || long_k)) ? 2 : 1;
+    if (d->mode == 1) {
+      // 3x3 convolutions reduce over taps x Cin (K = 3150 ... 9216): with enough 256-row tiles to fill the 74 CTA
+      // pairs the pair kernel wins even for ragged N, because it narrows the last N tile (profiles/r1r_conv_variants.txt:
+      // 768 -> 768 at 112x144 1525 -> 1293 us, at 28x36 140 -> 134 us, 350 -> 350 at 128x128 380 -> 366 us); with few
+      // tiles it loses (1024 -> 1024 at 16x16: 95 vs 179 us; 350 -> 350 at 32x32: 44 vs 74 us).
+      const long long k_eff = (long long)d->K * d->ksize * d->ksize;
+      const long long pair_tiles = (long long)((d->M + 255) / 256) * (n256 / 256);
+      v = (k_eff >= 2048 && pair_tiles >= 48 && d->N > 256) ? 2 : 1;
+    } else {
+      const bool wide = d->N >= 512 && (n256 - d->N) * 8 <= n256;
+      v = (wide && d->M > 128 && (d->N >= 2048 || d->K >= 2048)) ? 2 : 1;
+    }
   }
   if (v == 1) return launch_gemm_1cta(d, stream);
   return launch_gemm_2cta(d, v == 2 ? 256 : 128, stream);
