@@ -28,6 +28,7 @@ sys.path.insert(0, ROOT)
 
 import torch  # noqa: E402
 
+_OUT = sys.stdout  # main() replaces it with a duplicate of the original stdout
 GFLOP_PER_IMAGE = {"tp_cfg4": 993.2, "tp_cfg2": 1163.5, "tp_cfg5": 12842.7}
 
 
@@ -161,7 +162,7 @@ def run_reference(args):
         "e2e": {"value": rate, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_OUT, flush=True)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -393,7 +394,7 @@ def run_ours(args):
         line["cpu_baseline"] = {"value": rate, "unit": "images/s", "cores": threads, "kind": "port",
                                 "sample": f"3 forwards of batch 1 of {args.config} (oracle/taskprompter_ref.py, fp32 "
                                           f"eager, {threads} of {os.cpu_count()} host threads = fastest setting)"}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_OUT, flush=True)
     D.teardown(world)
 
 
@@ -409,9 +410,12 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
-    # stdout carries exactly one JSON line: NCCL's version banner (NCCL_DEBUG=VERSION, printed to stdout) goes away
-    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"
+    # stdout carries exactly ONE JSON line: whatever a library prints to file descriptor 1 (NCCL's "NCCL version ..."
+    # banner at init, for one) is sent to stderr; the JSON line goes to the saved descriptor.
+    global _OUT
+    sys.stdout.flush()
+    _OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:
