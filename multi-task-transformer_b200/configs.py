@@ -18,6 +18,10 @@ def taskprompter(name):
         "tp_tiny1": dict(tasks=["semseg", "edge"], num_output={"semseg": 4, "edge": 1},
                          img_size=(64, 64), patch=16, C=128, depth=4, heads=2, select=[1, 2, 3],
                          e=20, f=28, chan_nheads=1, use_ctr=False),
+        # DEConvHead heads (taskprompter.py:700-715; `head: deconv`, the Cityscapes-3D yml) on a tiny ViT backbone
+        "tp_tiny_de": dict(tasks=["semseg", "depth"], num_output={"semseg": 6, "depth": 1},
+                           img_size=(64, 96), patch=16, C=128, depth=4, heads=2, select=[1, 2, 3],
+                           e=24, f=32, chan_nheads=1, use_ctr=False, head="deconv"),
         # BASELINE.json configs[1]: ViT-B geometry + NYUD decoder dims
         "tp_cfg2": dict(tasks=NYUD_TASKS, num_output=NYUD_OUT, img_size=(448, 576), patch=16, C=768, depth=12,
                         heads=12, select=[3, 6, 9], e=768, f=768, chan_nheads=16, use_ctr=False),
@@ -43,6 +47,7 @@ def taskprompter(name):
     c = dict(c)
     c["name"] = name
     c["prompt_len"] = 1
+    c.setdefault("head", "conv")     # utils/common_config.py:64-70: 'conv' -> ConvHead, 'deconv' -> DEConvHead
     return c
 
 

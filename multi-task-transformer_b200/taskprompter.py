@@ -173,6 +173,25 @@ class ConvHead(nn.Module):
         raise RuntimeError("ConvHead runs fused inside TaskPrompterWrapper.forward")
 
 
+class DEConvHead(nn.Module):
+    """taskprompter.py:700-715 (`head: deconv`, utils/common_config.py:68-70): ConvTranspose2d(k2,s2) + BN + GELU,
+    3x3 conv + BN + GELU, 1x1 conv -- predicts at twice the resolution of its input."""
+
+    def __init__(self, in_channels, num_classes):
+        super().__init__()
+        h2 = in_channels // 2
+        self.mt_proj = nn.Sequential(nn.ConvTranspose2d(in_channels, h2, 2, stride=2, padding=0),
+                                     nn.BatchNorm2d(h2), nn.GELU(),
+                                     nn.Conv2d(h2, h2, 3, padding=1), nn.BatchNorm2d(h2), nn.GELU())
+        self.linear_pred = nn.Conv2d(h2, num_classes, kernel_size=1)
+        _trunc_normal_(self.mt_proj[0].weight, std=0.02)
+        _trunc_normal_(self.mt_proj[3].weight, std=0.02)
+        _trunc_normal_(self.linear_pred.weight, std=0.02)
+
+    def forward(self, x):
+        raise RuntimeError("DEConvHead runs fused inside TaskPrompterWrapper.forward")
+
+
 class TaskPrompterWrapper(nn.Module):
     """models/taskprompter_wrapper.py:9-40: backbone -> per-task head -> bilinear resize to the input
     size (or p.dd_label_map_size). forward(x[B,3,H,W]) -> {task: [B,n_out,H,W]} fp32."""
@@ -311,7 +330,24 @@ class _Plan:
         for t in self.tasks:
             hd = wrapper.heads[t]
             hw = SimpleNamespace()
-            w1, b1 = fold_bn(f32(hd.mt_proj[0].weight), f32(hd.mt_proj[0].bias), hd.mt_proj[1])
+            hw.deconv = isinstance(hd.mt_proj[0], nn.ConvTranspose2d)
+            if hw.deconv:
+                # ConvTranspose2d(k2, s2, p0): out[2y+dy, 2x+dx] = in[y, x] . W[:, :, dy, dx].  On the zero-inserted map
+                # (in[y, x] at (2y, 2x)) that is a 3x3 convolution (pad 1) whose tap (1-dy, 1-dx) holds W[:, :, dy, dx]^T
+                # and whose other five taps are zero -- the same mtt_zero_insert + mtt_gemm(conv) pair InvPT's
+                # scale_embed uses; eval BatchNorm folds into it like into any conv.
+                wt = f32(hd.mt_proj[0].weight)                                   # [Cin, Cout, 2, 2]
+                w3 = torch.zeros(wt.shape[1], wt.shape[0], 3, 3, device=device)
+                for dy in range(2):
+                    for dx in range(2):
+                        w3[:, :, 1 - dy, 1 - dx] = wt[:, :, dy, dx].t()
+                w0, b0 = fold_bn(w3, f32(hd.mt_proj[0].bias), hd.mt_proj[1])
+                hw.dc, hw.dc_b = pack_conv_weight(w0, ns), b0.contiguous()
+                w1, b1 = fold_bn(f32(hd.mt_proj[3].weight), f32(hd.mt_proj[3].bias), hd.mt_proj[4])
+                hw.mid = wt.shape[1]
+            else:
+                w1, b1 = fold_bn(f32(hd.mt_proj[0].weight), f32(hd.mt_proj[0].bias), hd.mt_proj[1])
+                hw.mid = self.f
             hw.mt, hw.mt_b = pack_conv_weight(w1, ns), b1.contiguous()
             hw.lp, hw.lp_b = pack_linear_weight(f32(hd.linear_pred.weight), ns), f32(hd.linear_pred.bias)
             hw.n_out = hd.linear_pred.weight.shape[0]
@@ -344,10 +380,18 @@ class _Plan:
             self.F = z(T, B * P, self.f_ld)
             self.ctrw = z(B, T, T)
         gh4, gw4 = 4 * self.gh, 4 * self.gw
-        self.up = [S(B * gh4 * gw4, f, zero=True) for _ in range(T)]
-        self.hmid = [S(B * gh4 * gw4, f, zero=True) for _ in range(T)]
+        # head input / hidden / prediction maps; a DEConvHead works at (2*gh4) x (2*gw4)
+        self.up, self.hmid, self.pred, self.upf, self.zi, self.hdc = [], [], [], [], [], []
+        for hw in W.heads:
+            k = 2 if hw.deconv else 1
+            rows = B * (k * gh4) * (k * gw4)
+            self.up.append(None if hw.deconv else S(B * gh4 * gw4, f, zero=True))
+            self.upf.append(z(B * gh4 * gw4, self.f_ld) if hw.deconv else None)
+            self.zi.append(S(rows, f, zero=True) if hw.deconv else None)
+            self.hdc.append(S(rows, hw.mid, zero=True) if hw.deconv else None)
+            self.hmid.append(S(rows, hw.mid, zero=True))
+            self.pred.append(z(rows, ops.round_up(hw.n_out, 4)))
         self.side = None   # side streams, created lazily on the plan's device
-        self.pred = [z(B * gh4 * gw4, ops.round_up(hw.n_out, 4)) for hw in W.heads]
         oh, ow = self.target if self.target is not None else self.img
         if not postproc:
             self.out = {t: z(B, hw.n_out, oh, ow) for t, hw in zip(self.tasks, W.heads)}
@@ -452,15 +496,27 @@ class _Plan:
         B = self.B
         gh4, gw4 = 4 * self.gh, 4 * self.gw
         oh, ow = self.out_hw
-        ops.bilinear(self.acc[ti], self.f_ld, B, self.gh, self.gw, self.f, gh4, gw4, out_split=self.up[ti])  # :420
-        ops.gemm(self.up[ti], hw.mt, N=self.f, K=self.f, bias=hw.mt_b, act=ops.ACT_GELU, out_split=self.hmid[ti],
-                 conv=(B, gh4, gw4, 3, 1))                                                   # ConvHead.mt_proj
+        if hw.deconv:                                                                       # DEConvHead :700-715
+            ops.bilinear(self.acc[ti], self.f_ld, B, self.gh, self.gw, self.f, gh4, gw4,
+                         out_f32=self.upf[ti][:, :self.f])                                   # :420
+            ops.zero_insert(self.upf[ti], self.zi[ti], B=B, h=gh4, w=gw4, Cdim=self.f, src_group=gh4 * gw4,
+                            src_offset=0)
+            ph, pw = 2 * gh4, 2 * gw4
+            ops.gemm(self.zi[ti], hw.dc, N=hw.mid, K=self.f, bias=hw.dc_b, act=ops.ACT_GELU, out_split=self.hdc[ti],
+                     conv=(B, ph, pw, 3, 1))                                                 # mt_proj[0..2]
+            ops.gemm(self.hdc[ti], hw.mt, N=hw.mid, K=hw.mid, bias=hw.mt_b, act=ops.ACT_GELU,
+                     out_split=self.hmid[ti], conv=(B, ph, pw, 3, 1))                        # mt_proj[3..5]
+        else:
+            ph, pw = gh4, gw4
+            ops.bilinear(self.acc[ti], self.f_ld, B, self.gh, self.gw, self.f, gh4, gw4, out_split=self.up[ti])  # :420
+            ops.gemm(self.up[ti], hw.mt, N=self.f, K=self.f, bias=hw.mt_b, act=ops.ACT_GELU, out_split=self.hmid[ti],
+                     conv=(B, gh4, gw4, 3, 1))                                               # ConvHead.mt_proj
         ops.gemm(self.hmid[ti], hw.lp, bias=hw.lp_b, out_f32=self.pred[ti][:, :hw.n_out], N=hw.n_out)
         if self.postproc:
-            ops.bilinear_postproc(self.pred[ti], self.pred[ti].stride(0), B, gh4, gw4, hw.n_out, oh, ow,
+            ops.bilinear_postproc(self.pred[ti], self.pred[ti].stride(0), B, ph, pw, hw.n_out, oh, ow,
                                   ops.POSTPROC_KIND[t], self.out[t])                         # wrapper :35 + utils.py:27-63
         else:
-            ops.bilinear(self.pred[ti], self.pred[ti].stride(0), B, gh4, gw4, hw.n_out, oh, ow,
+            ops.bilinear(self.pred[ti], self.pred[ti].stride(0), B, ph, pw, hw.n_out, oh, ow,
                          out_nchw=self.out[t])                                               # wrapper :35
 
     def _launch(self, img):
@@ -539,7 +595,8 @@ def build_from_config(cfg, nsplit=PARITY, use_graph=True):
     bb = TaskPrompter(p, cfg["select"], img_size=tuple(cfg["img_size"]), patch_size=cfg["patch"],
                       embed_dim=cfg["C"], depth=cfg["depth"], num_heads=cfg["heads"],
                       chan_nheads=cfg["chan_nheads"])
-    heads = nn.ModuleDict({t: ConvHead(cfg["f"], cfg["num_output"][t]) for t in cfg["tasks"]})
+    head_cls = DEConvHead if cfg.get("head", "conv") == "deconv" else ConvHead       # utils/common_config.py:64-70
+    heads = nn.ModuleDict({t: head_cls(cfg["f"], cfg["num_output"][t]) for t in cfg["tasks"]})
     return TaskPrompterWrapper(p, bb, heads, nsplit=nsplit, use_graph=use_graph)
 
 
@@ -552,8 +609,12 @@ def accelerate(ref_model, nsplit=PARITY, use_graph=True):
                            patch_size=bb.patch_embed.patch_size[0], embed_dim=bb.embed_dim,
                            depth=len(bb.blocks), num_heads=bb.blocks[0].attn.num_heads,
                            chan_nheads=bb.blocks[0].attn.chan_nheads)
-    heads = nn.ModuleDict({t: ConvHead(ref_model.heads[t].linear_pred.weight.shape[1],
-                                       ref_model.heads[t].linear_pred.weight.shape[0]) for t in ref_model.tasks})
+    def mirror(hd):      # ConvHead (:688-698) or DEConvHead (:700-715), told apart by the first layer
+        if isinstance(hd.mt_proj[0], nn.ConvTranspose2d):
+            return DEConvHead(hd.mt_proj[0].weight.shape[0], hd.linear_pred.weight.shape[0])
+        return ConvHead(hd.linear_pred.weight.shape[1], hd.linear_pred.weight.shape[0])
+
+    heads = nn.ModuleDict({t: mirror(ref_model.heads[t]) for t in ref_model.tasks})
     m = TaskPrompterWrapper(p, mine_bb, heads, nsplit=nsplit, use_graph=use_graph)
     m.load_state_dict(ref_model.state_dict(), strict=True)
     return m.eval()

@@ -92,8 +92,10 @@ def main():
     if not ref_loader.available():
         raise SystemExit("reference not found (set MTT_REFERENCE or mount /root/reference)")
     os.makedirs(GOLD, exist_ok=True)
-    jobs = [("taskprompter", "tp_tiny", 3, 2), ("taskprompter", "tp_tiny1", 4, 2)]
-    if os.path.exists(os.path.join(ROOT, "oracle", "invpt_ref.py")):
+    jobs = [("taskprompter", "tp_tiny", 3, 2), ("taskprompter", "tp_tiny1", 4, 2), ("taskprompter", "tp_tiny_de", 8, 2)]
+    if os.environ.get("MTT_GOLDEN_ONLY") in ("tp_tiny_de",):
+        jobs = [j for j in jobs if j[1] == os.environ["MTT_GOLDEN_ONLY"]]
+    elif os.path.exists(os.path.join(ROOT, "oracle", "invpt_ref.py")):
         jobs += [("invpt", "ip_tiny", 5, 2), ("invpt", "ip_cfg1", 6, 2)]
     path = os.path.join(GOLD, "preproc.pt")
     torch.save(make_preproc(), path)

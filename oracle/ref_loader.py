@@ -43,7 +43,7 @@ def build_taskprompter(cfg):
 
     _activate("TaskPrompter")
     from easydict import EasyDict
-    from models.transformers.taskprompter import TaskPrompter, ConvHead
+    from models.transformers.taskprompter import TaskPrompter, ConvHead, DEConvHead
     from models.taskprompter_wrapper import TaskPrompterWrapper
 
     p = EasyDict(TASKS=EasyDict(NAMES=list(cfg["tasks"]), NUM_OUTPUT=dict(cfg["num_output"])),
@@ -52,7 +52,8 @@ def build_taskprompter(cfg):
     backbone = TaskPrompter(p=p, select_list=list(cfg["select"]), img_size=tuple(cfg["img_size"]),
                             patch_size=cfg["patch"], embed_dim=cfg["C"], depth=cfg["depth"],
                             num_heads=cfg["heads"], chan_nheads=cfg["chan_nheads"], drop_path_rate=0.15)
-    heads = nn.ModuleDict({t: ConvHead(cfg["f"], cfg["num_output"][t]) for t in cfg["tasks"]})
+    head_cls = DEConvHead if cfg.get("head", "conv") == "deconv" else ConvHead       # utils/common_config.py:64-70
+    heads = nn.ModuleDict({t: head_cls(cfg["f"], cfg["num_output"][t]) for t in cfg["tasks"]})
     return TaskPrompterWrapper(p, backbone, heads)
 
 

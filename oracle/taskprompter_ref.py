@@ -16,6 +16,7 @@ Reference lines (relative to TaskPrompter/):
   TaskPrompter.forward   models/transformers/taskprompter.py:392-422
   cal_task_feature       models/transformers/taskprompter.py:424-487
   ConvHead.forward       models/transformers/taskprompter.py:688-698
+  DEConvHead.forward     models/transformers/taskprompter.py:700-715
   wrapper forward        models/taskprompter_wrapper.py:22-40
   PatchEmbed / Mlp       timm==0.5.4 (pinned TaskPrompter/README.md:75), restated in oracle/shim
 """
@@ -183,6 +184,17 @@ def conv_head(sd, task, x):
     return _conv(y, sd, pre + "linear_pred")
 
 
+def deconv_head(sd, task, x):
+    """DEConvHead.forward (taskprompter.py:700-715): ConvTranspose2d(k2,s2) -> BN -> GELU -> 3x3 conv -> BN -> GELU
+    -> 1x1 conv, at twice the input resolution."""
+    pre = f"heads.{task}."
+    y = F.conv_transpose2d(x, sd[pre + "mt_proj.0.weight"].to(x.dtype), sd[pre + "mt_proj.0.bias"].to(x.dtype),
+                           stride=2)
+    y = F.gelu(_bn(y, sd, pre + "mt_proj.1"))
+    y = F.gelu(_bn(_conv(y, sd, pre + "mt_proj.3", padding=1), sd, pre + "mt_proj.4"))
+    return _conv(y, sd, pre + "linear_pred")
+
+
 def forward(sd, cfg, img, taps=None):
     """TaskPrompterWrapper.forward (models/taskprompter_wrapper.py:22-40): {task: [B,n_out,H,W]}."""
     feats = backbone_forward(sd, cfg, img, taps)
@@ -190,7 +202,8 @@ def forward(sd, cfg, img, taps=None):
     for t in cfg["tasks"]:
         if taps is not None:
             taps[f"task_fea.{t}"] = feats[t]
-        out[t] = F.interpolate(conv_head(sd, t, feats[t]), img.shape[-2:], mode="bilinear")
+        head = deconv_head if cfg.get("head", "conv") == "deconv" else conv_head      # utils/common_config.py:64-70
+        out[t] = F.interpolate(head(sd, t, feats[t]), img.shape[-2:], mode="bilinear")
     return out
 
 
@@ -256,7 +269,16 @@ def init_state_dict(cfg, seed=0, dtype=torch.float32):
             conv(f"backbone.fea_decode_spa.{il}.{t}.0", e, C, 1)
             conv(f"backbone.fea_decode_chan.{il}.{t}.0", e, C, 1)
     for t in cfg["tasks"]:
-        conv(f"heads.{t}.mt_proj.0", f, f, 3)
-        bn(f"heads.{t}.mt_proj.1", f)
-        conv(f"heads.{t}.linear_pred", cfg["num_output"][t], f, 1)
+        if cfg.get("head", "conv") == "deconv":                       # DEConvHead (:700-715)
+            h2 = f // 2
+            conv(f"heads.{t}.mt_proj.0", f, h2, 2, bias=False)        # ConvTranspose2d weight is [in, out, kh, kw]
+            sd[f"heads.{t}.mt_proj.0.bias"] = ((torch.rand(h2, generator=g) * 2 - 1) * 0.1).to(dtype)
+            bn(f"heads.{t}.mt_proj.1", h2)
+            conv(f"heads.{t}.mt_proj.3", h2, h2, 3)
+            bn(f"heads.{t}.mt_proj.4", h2)
+            conv(f"heads.{t}.linear_pred", cfg["num_output"][t], h2, 1)
+        else:
+            conv(f"heads.{t}.mt_proj.0", f, f, 3)
+            bn(f"heads.{t}.mt_proj.1", f)
+            conv(f"heads.{t}.linear_pred", cfg["num_output"][t], f, 1)
     return sd

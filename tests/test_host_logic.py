@@ -7,7 +7,8 @@ from oracle import configs
 from oracle import taskprompter_ref as TPR
 
 
-@pytest.mark.parametrize("name,nsplit,tol", [("tp_tiny", 2, 2e-4), ("tp_tiny1", 2, 2e-4), ("tp_tiny", 1, 8e-2)])
+@pytest.mark.parametrize("name,nsplit,tol", [("tp_tiny", 2, 2e-4), ("tp_tiny1", 2, 2e-4), ("tp_tiny", 1, 8e-2),
+                                             ("tp_tiny_de", 2, 2e-4)])
 def test_taskprompter_plan_matches_oracle(monkeypatch, name, nsplit, tol):
     import mtt_b200  # noqa: F401
     from mtt_b200 import taskprompter as TP
@@ -45,7 +46,7 @@ def test_state_dict_keys_match_oracle_names():
     import mtt_b200  # noqa: F401
     from mtt_b200 import taskprompter as TP
 
-    for name in ("tp_tiny", "tp_tiny1"):
+    for name in ("tp_tiny", "tp_tiny1", "tp_tiny_de"):
         cfg = configs.taskprompter(name)
         model = TP.build_from_config(cfg)
         sd = TPR.init_state_dict(cfg)

@@ -13,7 +13,7 @@ from oracle.make_golden import sd_checksum
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
-@pytest.mark.parametrize("name", ["tp_tiny", "tp_tiny1"])
+@pytest.mark.parametrize("name", ["tp_tiny", "tp_tiny1", "tp_tiny_de"])
 def test_taskprompter_oracle_vs_golden(name):
     fx = torch.load(os.path.join(GOLD, f"{name}.pt"), weights_only=False)
     cfg = configs.taskprompter(fx["cfg"])
@@ -29,7 +29,7 @@ def test_taskprompter_oracle_vs_golden(name):
 
 
 @pytest.mark.skipif(not ref_loader.available(), reason="reference tree not present")
-@pytest.mark.parametrize("name", ["tp_tiny", "tp_tiny1"])
+@pytest.mark.parametrize("name", ["tp_tiny", "tp_tiny1", "tp_tiny_de"])
 def test_taskprompter_oracle_vs_reference(name):
     cfg = configs.taskprompter(name)
     torch.manual_seed(0)
@@ -47,11 +47,12 @@ def test_taskprompter_oracle_vs_reference(name):
 
 
 @pytest.mark.skipif(not ref_loader.available(), reason="reference tree not present")
-def test_accelerate_shares_reference_state_dict():
+@pytest.mark.parametrize("name", ["tp_tiny", "tp_tiny_de"])
+def test_accelerate_shares_reference_state_dict(name):
     import mtt_b200  # noqa: F401
     from mtt_b200 import taskprompter as TP
 
-    cfg = configs.taskprompter("tp_tiny")
+    cfg = configs.taskprompter(name)
     ref = ref_loader.build_taskprompter(cfg).eval()
     mine = TP.accelerate(ref)
     a, b = ref.state_dict(), mine.state_dict()

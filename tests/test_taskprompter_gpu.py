@@ -46,7 +46,7 @@ def _check(got, ref, tasks, rel_l2, max_rel, check_argmax=True):
             assert agree.float().mean().item() > 0.999, f"{t}: argmax agreement {agree.float().mean().item():.5f}"
 
 
-@pytest.mark.parametrize("name", ["tp_tiny", "tp_tiny1"])
+@pytest.mark.parametrize("name", ["tp_tiny", "tp_tiny1", "tp_tiny_de"])
 def test_golden_parity(cuda_dev, name):
     fx = torch.load(os.path.join(GOLD, f"{name}.pt"), weights_only=False)
     cfg = configs.taskprompter(fx["cfg"])
