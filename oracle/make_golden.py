@@ -88,6 +88,81 @@ def make_preproc():
             "made_by": "oracle/make_golden.py: reference Normalize/ToTensor + cv2.resize (TP/inference.py pipeline)"}
 
 
+LOSS_WEIGHTS = {"semseg": 1.0, "human_parts": 2.0, "sal": 5.0, "edge": 50.0, "normals": 10.0, "depth": 1.0}  # the ymls
+
+
+def synthetic_labels(tasks, num_output, B, H, W, g):
+    """Labels of the shapes the reference's datasets produce, with ignore regions (255; depth: -1)."""
+    lab = {}
+    hole = lambda frac: torch.rand(B, 1, H, W, generator=g) < frac
+    for t in tasks:
+        if t in ("semseg", "human_parts"):
+            y = torch.randint(0, num_output[t], (B, 1, H, W), generator=g).float()
+            y[hole(0.1)] = 255.0
+        elif t == "sal":
+            y = (torch.rand(B, 1, H, W, generator=g) < 0.3).float()
+            y[hole(0.05)] = 255.0
+        elif t == "edge":
+            y = (torch.rand(B, 1, H, W, generator=g) < 0.1).float()
+            y[hole(0.05)] = 255.0
+        elif t == "normals":
+            y = torch.nn.functional.normalize(torch.randn(B, 3, H, W, generator=g), dim=1)
+            y = torch.where(hole(0.1).expand(-1, 3, -1, -1), torch.full_like(y, 255.0), y)
+        elif t == "depth":
+            y = torch.rand(B, 1, H, W, generator=g) * 9 + 0.5
+            y[hole(0.15)] = -1.0
+        lab[t] = y
+    return lab
+
+
+def make_losses():
+    """Golden vectors for the training losses and for the backward pass they drive: (a) every task loss and the
+    weighted total of the reference's criterion (utils/common_config.py:211-244 -> losses/) on random predictions,
+    with d total / d prediction; (b) the tp_tiny reference model in eval mode -> criterion -> autograd: total loss
+    and, per parameter, the gradient's L2 norm and sum (full gradients for a few small parameters)."""
+    ref_loader._activate("TaskPrompter")
+    from easydict import EasyDict
+    from utils.common_config import get_criterion
+
+    def criterion(tasks):
+        p = EasyDict(TASKS=EasyDict(NAMES=list(tasks)), edge_w=0.95, ignore_index=255, ignore_invalid_area_depth=True,
+                     loss_kwargs=EasyDict(loss_weights={t: LOSS_WEIGHTS[t] for t in tasks}))
+        return get_criterion(p)
+
+    g = torch.Generator().manual_seed(77)
+    tasks = ["semseg", "human_parts", "sal", "edge", "normals", "depth"]
+    nout = {"semseg": 7, "human_parts": 5, "sal": 2, "edge": 1, "normals": 3, "depth": 1}
+    B, H, W = 2, 24, 32
+    preds = {t: (torch.randn(B, nout[t], H, W, generator=g) * 2).requires_grad_() for t in tasks}
+    labels = synthetic_labels(tasks, nout, B, H, W, g)
+    out = criterion(tasks)(preds, labels, tasks=tasks)
+    out["total"].backward()
+    part_a = {"tasks": tasks, "preds": {t: preds[t].detach().clone() for t in tasks}, "labels": labels,
+              "losses": {k: float(v.detach()) for k, v in out.items()},
+              "dpreds": {t: preds[t].grad.clone() for t in tasks}}
+
+    from oracle import taskprompter_ref as R
+    cfg = configs.taskprompter("tp_tiny")
+    sd = R.init_state_dict(cfg, seed=3)
+    model = ref_loader.build_taskprompter(cfg).eval()
+    model.load_state_dict(sd, strict=True)
+    crit = criterion(cfg["tasks"])          # build_taskprompter re-activated the same reference root
+    x = torch.randn(2, 3, *cfg["img_size"], generator=g)
+    lab = synthetic_labels(cfg["tasks"], cfg["num_output"], 2, *cfg["img_size"], g)
+    loss = crit(model(x), lab, tasks=cfg["tasks"])
+    model.zero_grad()
+    loss["total"].backward()
+    grads = {k: v.grad for k, v in model.named_parameters()}
+    full = ["backbone.task_prompts", "backbone.blocks.0.attn.qkv.bias", "backbone.blocks.3.attn.token_trans1.bias",
+            "backbone.norm.weight", "heads.semseg.linear_pred.weight", "backbone.ctr_attn_conv.0.depth.0.weight"]
+    part_b = {"cfg": "tp_tiny", "seed": 3, "x": x, "labels": lab, "losses": {k: float(v.detach()) for k, v in loss.items()},
+              "grad_norm": {k: float(v.norm()) for k, v in grads.items()},
+              "grad_sum": {k: float(v.double().sum()) for k, v in grads.items()},
+              "grad_full": {k: grads[k].clone() for k in full}}
+    return {"family": "losses", "criterion": part_a, "model": part_b, "weights": LOSS_WEIGHTS, "torch": torch.__version__,
+            "made_by": "oracle/make_golden.py: reference get_criterion + autograd through the unmodified reference model"}
+
+
 def main():
     if not ref_loader.available():
         raise SystemExit("reference not found (set MTT_REFERENCE or mount /root/reference)")
@@ -102,6 +177,12 @@ def main():
     print(f"wrote {path} ({os.path.getsize(path) / 1024:.0f} KiB)")
     if os.environ.get("MTT_GOLDEN_ONLY") == "preproc":
         return
+    if os.environ.get("MTT_GOLDEN_ONLY") in (None, "", "losses"):
+        path = os.path.join(GOLD, "losses.pt")
+        torch.save(make_losses(), path)
+        print(f"wrote {path} ({os.path.getsize(path) / 1024:.0f} KiB)")
+        if os.environ.get("MTT_GOLDEN_ONLY") == "losses":
+            return
     for fam, name, seed, batch in jobs:
         fx = make_taskprompter(name, seed, batch) if fam == "taskprompter" else make_invpt(name, seed, batch)
         path = os.path.join(GOLD, f"{name}.pt")
