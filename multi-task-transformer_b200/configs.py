@@ -51,6 +51,31 @@ def taskprompter(name):
     return c
 
 
+def taskprompter_swin(name):
+    """Config dicts for the Swin TaskPrompter (TP/models/transformers/taskprompter_swin.py:542-666, built by
+    TP/utils/common_config.py:34-41): SURVEY.md section 8f N2. Only the CPU oracle uses them so far."""
+    c = {
+        # tiny: 64x96 image, patch 4 -> 16x24 tokens, four stages (levels 8x12 / 4x6 / 2x3 / 2x3 after merging); window 4
+        # with shifted windows in the first stages, then windows clipped to the map and PADDED (2x3 -> 2x4)
+        "tps_tiny": dict(tasks=["semseg", "depth"], num_output={"semseg": 5, "depth": 1}, img_size=(64, 96), patch=4,
+                         embed_dim=16, depths=(2, 2, 2, 2), heads=(1, 2, 4, 8), window=4, img_ds_ratio=1.0,
+                         level_embed_dim=12, f=24, chan_embed_dim=16, chan_nheads=1, head="deconv"),
+        # 64x128 image (levels 8x16 / 4x8 / 2x4 / 2x4), 2x2 channel-attention windows, ConvHead, three tasks
+        "tps_tiny4": dict(tasks=["semseg", "depth", "normals"], num_output={"semseg": 4, "depth": 1, "normals": 3},
+                          img_size=(64, 128), patch=4, embed_dim=16, depths=(2, 2, 2, 2), heads=(2, 2, 4, 4), window=4,
+                          img_ds_ratio=1.0, level_embed_dim=10, f=20, chan_embed_dim=16, chan_nheads=4, head="conv"),
+        # the reference's Cityscapes-3D model (cs_swinB_taskprompter.yml) without the 3ddet task
+        "tps_swinB": dict(tasks=["semseg", "depth"], num_output={"semseg": 19, "depth": 1}, img_size=(1024, 2048),
+                          patch=4, embed_dim=128, depths=(2, 2, 18, 2), heads=(4, 8, 16, 32), window=12,
+                          img_ds_ratio=0.75, level_embed_dim=256, f=450, chan_embed_dim=256, chan_nheads=1,
+                          head="deconv", dd_label_map_size=(512, 1024)),
+    }[name]
+    c = dict(c)
+    c["name"] = name
+    c["prompt_len"] = 1
+    return c
+
+
 def invpt(name):
     """Config dicts for InvPT (IP/models/transformer_net.py, IP/utils/common_config.py:15-51)."""
     c = {

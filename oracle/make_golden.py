@@ -45,6 +45,23 @@ def make_taskprompter(name, seed, batch):
             "made_by": "oracle/make_golden.py from the unmodified reference forward (eval, fp32, CPU)"}
 
 
+def make_taskprompter_swin(name, seed, batch):
+    from oracle import taskprompter_swin_ref as R
+
+    cfg = configs.taskprompter_swin(name)
+    sd = R.init_state_dict(cfg, seed=seed)
+    model = ref_loader.build_taskprompter_swin(cfg).eval()
+    missing, unexpected = model.load_state_dict(sd, strict=False)   # index / mask buffers are derived, not stored
+    assert not unexpected and all("relative_position_index" in k or "attn_mask" in k for k in missing), (missing, unexpected)
+    g = torch.Generator().manual_seed(seed + 1000)
+    x = torch.randn(batch, 3, *cfg["img_size"], generator=g)
+    with torch.no_grad():
+        y = model(x)
+    return {"family": "taskprompter_swin", "cfg": name, "seed": seed, "x": x, "out": {k: v.clone() for k, v in y.items()},
+            "sd_sha256": sd_checksum(sd), "torch": torch.__version__,
+            "made_by": "oracle/make_golden.py from the unmodified reference Swin TaskPrompter forward (eval, fp32, CPU)"}
+
+
 def make_invpt(name, seed, batch):
     from oracle import invpt_ref as R
 
@@ -167,8 +184,9 @@ def main():
     if not ref_loader.available():
         raise SystemExit("reference not found (set MTT_REFERENCE or mount /root/reference)")
     os.makedirs(GOLD, exist_ok=True)
-    jobs = [("taskprompter", "tp_tiny", 3, 2), ("taskprompter", "tp_tiny1", 4, 2), ("taskprompter", "tp_tiny_de", 8, 2)]
-    if os.environ.get("MTT_GOLDEN_ONLY") in ("tp_tiny_de",):
+    jobs = [("taskprompter", "tp_tiny", 3, 2), ("taskprompter", "tp_tiny1", 4, 2), ("taskprompter", "tp_tiny_de", 8, 2),
+            ("taskprompter_swin", "tps_tiny", 11, 2), ("taskprompter_swin", "tps_tiny4", 12, 2)]
+    if os.environ.get("MTT_GOLDEN_ONLY") in ("tp_tiny_de", "tps_tiny", "tps_tiny4"):
         jobs = [j for j in jobs if j[1] == os.environ["MTT_GOLDEN_ONLY"]]
     elif os.path.exists(os.path.join(ROOT, "oracle", "invpt_ref.py")):
         jobs += [("invpt", "ip_tiny", 5, 2), ("invpt", "ip_cfg1", 6, 2)]
@@ -184,7 +202,8 @@ def main():
         if os.environ.get("MTT_GOLDEN_ONLY") == "losses":
             return
     for fam, name, seed, batch in jobs:
-        fx = make_taskprompter(name, seed, batch) if fam == "taskprompter" else make_invpt(name, seed, batch)
+        fx = {"taskprompter": make_taskprompter, "taskprompter_swin": make_taskprompter_swin,
+              "invpt": make_invpt}[fam](name, seed, batch)
         path = os.path.join(GOLD, f"{name}.pt")
         torch.save(fx, path)
         print(f"wrote {path} ({os.path.getsize(path) / 1024:.0f} KiB)")

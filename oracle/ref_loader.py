@@ -57,6 +57,34 @@ def build_taskprompter(cfg):
     return TaskPrompterWrapper(p, backbone, heads)
 
 
+def build_taskprompter_swin(cfg):
+    """Reference TaskPrompterWrapper around TaskPrompterSwin for a dict from oracle.configs.taskprompter_swin()
+    (mirrors TP/utils/common_config.py:34-41,64-90)."""
+    import torch.nn as nn
+
+    _activate("TaskPrompter")
+    from easydict import EasyDict
+    from models.transformers.taskprompter_swin import TaskPrompterSwin
+    from models.transformers.taskprompter import ConvHead, DEConvHead
+    from models.taskprompter_wrapper import TaskPrompterWrapper
+
+    h, w = cfg["img_size"]
+    E = cfg["embed_dim"]
+    p = EasyDict(TASKS=EasyDict(NAMES=list(cfg["tasks"]), NUM_OUTPUT=dict(cfg["num_output"])),
+                 prompt_len=cfg["prompt_len"], chan_embed_dim=cfg["chan_embed_dim"], chan_nheads=cfg["chan_nheads"],
+                 img_ds_ratio=cfg["img_ds_ratio"], level_embed_dim=cfg["level_embed_dim"], final_embed_dim=cfg["f"],
+                 backbone_channels=[2 * E, 4 * E, 8 * E, 8 * E],                      # common_config.py:36
+                 ori_spatial_dim=[[h // st, w // st] for st in (8, 16, 32, 32)])       # :37-39
+    if "dd_label_map_size" in cfg:
+        p.dd_label_map_size = list(cfg["dd_label_map_size"])
+    backbone = TaskPrompterSwin(p=p, img_size=tuple(cfg["img_size"]), patch_size=cfg["patch"], embed_dim=E,
+                                depths=tuple(cfg["depths"]), num_heads=tuple(cfg["heads"]),
+                                window_size=cfg["window"], drop_path_rate=0.15)
+    head_cls = DEConvHead if cfg.get("head", "conv") == "deconv" else ConvHead
+    heads = nn.ModuleDict({t: head_cls(cfg["f"], cfg["num_output"][t]) for t in cfg["tasks"]})
+    return TaskPrompterWrapper(p, backbone, heads)
+
+
 def build_invpt(cfg):
     """Reference TransformerNet (InvPT) for a config dict from oracle.configs.invpt()
     (mirrors IP/utils/common_config.py:15-21,39-51)."""

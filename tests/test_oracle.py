@@ -104,3 +104,67 @@ def test_invpt_accelerate_shares_reference_state_dict():
     a, b = ref.state_dict(), mine.state_dict()
     assert set(a.keys()) == set(b.keys())
     assert all(torch.equal(a[k], b[k]) for k in a)
+
+
+# ---- Swin-backbone TaskPrompter: oracle only, no CUDA path yet -------------------------
+@pytest.mark.parametrize("name", ["tps_tiny", "tps_tiny4"])
+def test_swin_oracle_vs_golden(name):
+    from oracle import taskprompter_swin_ref as SR
+
+    fx = torch.load(os.path.join(GOLD, f"{name}.pt"), weights_only=False)
+    cfg = configs.taskprompter_swin(fx["cfg"])
+    sd = SR.init_state_dict(cfg, seed=fx["seed"])
+    assert sd_checksum(sd) == fx["sd_sha256"], "deterministic initialiser drifted from the fixture"
+    with torch.no_grad():
+        out = SR.forward(sd, cfg, fx["x"])
+    for t, ref in fx["out"].items():
+        assert out[t].shape == ref.shape
+        assert (out[t] - ref).abs().max() <= 5e-6 * ref.abs().max().clamp_min(1.0) + 2e-6, t
+        if t == "semseg":
+            assert torch.equal(out[t].argmax(1), ref.argmax(1))
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="reference tree not present")
+@pytest.mark.parametrize("name", ["tps_tiny", "tps_tiny4"])
+def test_swin_oracle_vs_reference(name):
+    """Against the unmodified reference with ITS OWN initialisation (plus non-trivial biases, bias tables and
+    BatchNorm statistics): shifted and padded windows, 2x2 channel windows, patch merging of the logit maps."""
+    from oracle import taskprompter_swin_ref as SR
+
+    cfg = configs.taskprompter_swin(name)
+    torch.manual_seed(0)
+    model = ref_loader.build_taskprompter_swin(cfg).eval()
+    with torch.no_grad():
+        for m in model.modules():
+            if isinstance(m, (torch.nn.BatchNorm2d, torch.nn.SyncBatchNorm)):
+                m.running_mean.normal_(0, 0.1)
+                m.running_var.uniform_(0.8, 1.2)
+        for k, v in model.named_parameters():
+            if "relative_position_bias_table" in k:
+                v.normal_(0, 0.5)
+            elif k.endswith(".bias"):
+                v.normal_(0, 0.05)
+    ref_sd = model.state_dict()
+    derived = {k for k in ref_sd if "relative_position_index" in k or "attn_mask" in k}
+    shapes = SR.param_shapes(cfg)
+    assert set(shapes) == set(ref_sd) - derived
+    assert all(tuple(ref_sd[k].shape) == tuple(shapes[k]) for k in shapes)
+    x = torch.randn(2, 3, *cfg["img_size"])
+    with torch.no_grad():
+        ref = model(x)
+        out = SR.forward(ref_sd, cfg, x)
+    for t in cfg["tasks"]:
+        assert (out[t] - ref[t]).abs().max() <= 5e-6, t
+
+
+def test_swin_window_tables_match_definitions():
+    """The derived tables the oracle recomputes (instead of reading the reference's buffers)."""
+    from oracle import taskprompter_swin_ref as SR
+
+    idx = SR.relative_position_index(3)
+    assert idx.shape == (9, 9) and idx.min() == 0 and idx.max() == 24 and idx[0, 0] == 12      # centre of a 5x5 table
+    assert idx[0, 8] == 0 and idx[8, 0] == 24
+    m = SR.shifted_window_mask(8, 8, 4, 2)
+    assert m.shape == (4, 16, 16) and set(m.unique().tolist()) == {-100.0, 0.0}
+    assert (m[0] == 0).all()                      # the top-left window holds one region only
+    assert (m[3] != 0).any() and torch.equal(m[3], m[3].t())
