@@ -152,7 +152,7 @@ def set_gemm_variant(v):
 
 
 def set_attention_variant(v):
-    """0 / 3 = warp-specialised attention kernel (default), 1 = single-role persistent kernel (tuning / testing knob)."""
+    """0 / 5 = default warp-specialised attention kernel (attention5_tc.cu), 3 = its predecessor (tuning / testing knob)."""
     _L.load().mtt_set_attention_variant(int(v))
 
 
