@@ -9,7 +9,7 @@
 //     softmax warps work on S_j, and issues O += P_j V_j the moment P_j is published;
 //   * Q lives in TMEM (copied once per item), so S = Q K^T is a TS-form MMA that reads only the 64-key K block
 //     from shared memory (64 B/clk instead of 192 B/clk for an SS-form N = 64 MMA: the SS form is shared-memory
-//     bound, which is what made attention2_tc.cu slower);
+//     bound: 49 cycles per MMA against 33, scripts/mma_probe.cu -- which is what made an earlier SS-form variant slower);
 //   * one thread per query row (4 softmax warps): no cross-thread max / sum exchange, no __syncthreads;
 //   * the row maximum is OPTIMISTIC: P is computed against the running maximum while the block maximum is
 //     tracked alongside, and only when that maximum moved by more than 2^8 (rare after the first block) is the

@@ -1,31 +1,26 @@
-// Fused multi-head attention, variant 5 of mtt_attention = attention3_tc.cu after the clock-stamp timeline of
-// profiles/r1k_attention_trace.md (a block costs a CTA ~2150 cycles for 768 cycles of tensor work; the softmax warps
-// are XU-bound when both resident CTAs are in phase, the MMA warp spends ~850 cycles per block on non-MMA issue
-// overhead, and an item boundary costs ~7500 cycles):
-//   * the hi plane of P is rounded on the integer pipe (add 0x8000, PRMT), only the lo plane goes through F2FP:
-//     one XU instruction per pair instead of two (XU: 130 -> 98 warp instructions per block);
-//   * two tcgen05.commit per block instead of four: the TMA warp waits on s_ready / pv_done (the K slot of block g
-//     is free when S_{g-2} is complete, the V slot when PV_{g-2} has retired; two stages = two S buffers);
-//   * the item epilogue writes whole 32-byte sectors (st.global.v8) instead of 16-byte halves.
-// Everything else as in variant 3:
-// Fused multi-head attention, warp-specialised variant (variant 3 of mtt_attention; same contract as
-// attention_tc.cu: TP/models/transformers/taskprompter.py:204-210, prompt-row raw logits :436-437,:482).
+// Fused multi-head attention, the default kernel of mtt_attention (variant 5; contract in attention_tc.cu:
+// TP/models/transformers/taskprompter.py:204-210, prompt-row raw logits :436-437,:482; IP vit.py:189-193).
 //
-// What the profile of attention_tc.cu said (profiles/README.md): tensor pipe 36 % active, issue slots 40 %, XU 24 %,
-// stalls dominated by long-scoreboard waits -- every CTA walks ONE serial chain per key block
-//   S = Q K^T  ->  TMEM read  ->  row max  ->  (sync)  ->  exp / split  ->  TMEM write  ->  (sync)  ->  O += P V
-// and two co-resident CTAs only hide part of it.  This variant breaks the chain instead:
-//   * key blocks of 64 with TWO S buffers in TMEM: the MMA warp keeps S_{j+1} (and S_{j+2}) in flight while the
-//     softmax warps work on S_j, and issues O += P_j V_j the moment P_j is published;
-//   * Q lives in TMEM (copied once per item), so S = Q K^T is a TS-form MMA that reads only the 64-key K block
-//     from shared memory (64 B/clk instead of 192 B/clk for an SS-form N = 64 MMA: the SS form is shared-memory
-//     bound, which is what made attention2_tc.cu slower);
-//   * one thread per query row (4 softmax warps): no cross-thread max / sum exchange, no __syncthreads;
-//   * the row maximum is OPTIMISTIC: P is computed against the running maximum while the block maximum is
-//     tracked alongside, and only when that maximum moved by more than 2^8 (rare after the first block) is the
-//     block redone with the new maximum and O / l rescaled -- same lazy-rescaling arithmetic as variant 1;
-//   * dedicated TMA warp (K ring, V ring, next item's Q) and MMA warp; 192 threads, 96 KB smem, 256 TMEM
-//     columns: two CTAs per SM.
+// Warp-specialised, persistent: each CTA (192 threads, 99 KB smem, 256 TMEM columns -> two CTAs per SM) walks
+// (batch, head, 128-query tile) items:
+//   * warp 5 = TMA (K ring, V ring, the next item's Q), warp 4 = MMA issue (one elected lane), warps 0-3 = softmax,
+//     ONE thread per query row: no cross-thread max / sum exchange, no __syncthreads in the loop;
+//   * key blocks of 64 with TWO S buffers in TMEM: S_{j+1} is in flight while the softmax warps work on S_j, and
+//     O += P_j V_j is issued the moment P_j is published (issue order S_0 S_1 | PV_0 S_2 | PV_1 S_3 ...; the tensor pipe
+//     executes in issue order, so S_{j+2} cannot overwrite P_j early);
+//   * Q is copied to TMEM once per item, so S = Q K^T is a TS-form MMA that reads only the 64-key K block from shared
+//     memory: 33 cycles per 128x64x16 MMA against 49 for the SS form, which is shared-memory bound (scripts/mma_probe.cu);
+//   * P = exp2(S c - m) is written back IN PLACE over S as packed bf16 hi / lo; the hi plane is rounded on the integer
+//     pipe (add 0x8000, PRMT), only the lo plane goes through F2FP;
+//   * the row maximum is OPTIMISTIC: P is computed against the running maximum while the block maximum is tracked
+//     alongside, and only when it moved by more than 2^8 (rare after the first block) is the block redone and O / l
+//     rescaled (lazy rescaling);
+//   * two tcgen05.commit per block: the TMA warp reuses s_ready / pv_done as "slot free" signals (the K slot of block g
+//     is free when S_{g-2} is complete, the V slot when PV_{g-2} has retired; two stages = two S buffers);
+//   * the item epilogue (O / l, split, store) writes whole 32-byte sectors per lane (st.global.v8).
+// Measured and what bounds it: profiles/r1k_attention_analysis.md (a block costs a CTA ~2150 cycles for 768 cycles of
+// tensor work; the per-block softmax hand-off, not the tensor pipe, sets the pace). attention3_tc.cu is the predecessor
+// (four commits per block, cvt-based hi plane, 16-byte epilogue stores), kept as variant 3.
 // TMEM columns: S0 [0,64) | S1 [64,128) | O [128,192) | Q hi [192,224) | Q lo [224,256); P_j overwrites S_j in
 // place as packed bf16 (hi in the first 32 columns, lo in the next 32).
 #include <math.h>
