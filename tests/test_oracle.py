@@ -168,3 +168,20 @@ def test_swin_window_tables_match_definitions():
     assert m.shape == (4, 16, 16) and set(m.unique().tolist()) == {-100.0, 0.0}
     assert (m[0] == 0).all()                      # the top-left window holds one region only
     assert (m[3] != 0).any() and torch.equal(m[3], m[3].t())
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="reference tree not present")
+def test_swin_param_shapes_at_the_reference_config():
+    """The reference's Cityscapes-3D Swin-B model (cs_swinB_taskprompter.yml: 1024x2048, img_ds_ratio 0.75, window 12,
+    depths 2-2-18-2): every parameter name and shape the oracle expects equals the reference module's (274.6 M
+    parameters; construction only, no forward)."""
+    from oracle import taskprompter_swin_ref as SR
+
+    cfg = configs.taskprompter_swin("tps_swinB")
+    ref_sd = ref_loader.build_taskprompter_swin(cfg).state_dict()
+    derived = {k for k in ref_sd if "relative_position_index" in k or "attn_mask" in k}
+    shapes = SR.param_shapes(cfg)
+    assert set(shapes) == set(ref_sd) - derived and len(shapes) == 732
+    assert all(tuple(ref_sd[k].shape) == tuple(shapes[k]) for k in shapes)
+    assert [SR.stage_geometry(cfg, i)[1] for i in range(4)] == [(192, 384), (96, 192), (48, 96), (24, 48)]
+    assert [SR.level_resolution(cfg, i) for i in range(4)] == [(96, 192), (48, 96), (24, 48), (24, 48)]
