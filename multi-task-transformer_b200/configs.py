@@ -64,6 +64,12 @@ def taskprompter_swin(name):
         "tps_tiny4": dict(tasks=["semseg", "depth", "normals"], num_output={"semseg": 4, "depth": 1, "normals": 3},
                           img_size=(64, 128), patch=4, embed_dim=16, depths=(2, 2, 2, 2), heads=(2, 2, 4, 4), window=4,
                           img_ds_ratio=1.0, level_embed_dim=10, f=20, chan_embed_dim=16, chan_nheads=4, head="conv"),
+        # the reference config's window (12, shift 6), input down-scaling (0.75) and dd_label_map_size at toy width:
+        # 256x512 -> 192x384 -> tokens 48x96 / 24x48 / 12x24 (window clipped to 12) / 6x12 (window 6)
+        "tps_mid": dict(tasks=["semseg", "depth"], num_output={"semseg": 19, "depth": 1}, img_size=(256, 512), patch=4,
+                        embed_dim=16, depths=(2, 2, 2, 2), heads=(1, 2, 4, 8), window=12, img_ds_ratio=0.75,
+                        level_embed_dim=16, f=24, chan_embed_dim=16, chan_nheads=1, head="deconv",
+                        dd_label_map_size=(128, 256)),
         # the reference's Cityscapes-3D model (cs_swinB_taskprompter.yml) without the 3ddet task
         "tps_swinB": dict(tasks=["semseg", "depth"], num_output={"semseg": 19, "depth": 1}, img_size=(1024, 2048),
                           patch=4, embed_dim=128, depths=(2, 2, 18, 2), heads=(4, 8, 16, 32), window=12,
