@@ -29,7 +29,24 @@ sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
 _OUT = sys.stdout  # main() replaces it with a duplicate of the original stdout
-GFLOP_PER_IMAGE = {"tp_cfg4": 993.2, "tp_cfg2": 1163.5, "tp_cfg5": 12842.7}
+GFLOP_PER_IMAGE = {"tp_cfg4": 993.2, "tp_cfg2": 1163.5, "tp_cfg5": 12842.7, "ip_cfg3": 1344.8}
+WORKLOAD = {
+    "tp_cfg4": "TaskPrompter ViT-L PASCAL-Context (5 tasks) 512x512 forward",
+    "tp_cfg2": "TaskPrompter ViT-B NYUD-v2 (4 tasks) 448x576 forward",
+    "tp_cfg5": "TaskPrompter ViT-L Cityscapes-3D shape (seg + depth + 18-channel 3ddet ConvHead stand-in) 1024x2048 forward",
+    "ip_cfg3": "InvPT ViT-L PASCAL-Context (5 tasks) 512x512 forward",
+}
+DEFAULT_BATCH = {"tp_cfg4": 4, "tp_cfg2": 4, "tp_cfg5": 1, "ip_cfg3": 4}
+
+
+def family(cfg_name):
+    """(config dict, product module, oracle module) for a named configuration."""
+    from mtt_b200 import configs
+    if cfg_name.startswith("ip_"):
+        from mtt_b200 import invpt as M
+        return configs.invpt(cfg_name), M, "oracle.invpt_ref"
+    from mtt_b200 import taskprompter as M
+    return configs.taskprompter(cfg_name), M, "oracle.taskprompter_ref"
 
 
 def load_peaks():
@@ -124,24 +141,79 @@ def pick_cpu_threads():
     return best
 
 
-def cpu_oracle_rate(cfg_name, steps, warmup, threads):
-    """images/s of the reference algorithm's CPU port (oracle/taskprompter_ref.py, fp32, eval) on a
-    bounded sample: batch 1 of the same workload per step."""
-    from mtt_b200 import configs
-    from oracle import taskprompter_ref as TPR
+def reference_forward(cfg_name, device="cpu"):
+    """A callable x -> outputs running the reference algorithm in eager PyTorch on `device`, and its kind:
+    "reference" = the UNMODIFIED reference model imported through oracle/shim (only where /root/reference or
+    $MTT_REFERENCE or baseline/_ref exists -- not on the GPU box), "port" = the oracle restatement."""
+    import importlib
 
+    from oracle import ref_loader
+    cfg, _, oracle_name = family(cfg_name)
+    R = importlib.import_module(oracle_name)
+    sd = R.init_state_dict(cfg, seed=0)
+    if ref_loader.available():
+        build = ref_loader.build_invpt if cfg_name.startswith("ip_") else ref_loader.build_taskprompter
+        model = build(cfg).eval()
+        model.load_state_dict(sd, strict=True)
+        model = model.to(device)
+        return (lambda x: model(x)), "reference", cfg
+    sd = {k: v.to(device) for k, v in sd.items()}
+    return (lambda x: R.forward(sd, cfg, x)), "port", cfg
+
+
+def cpu_oracle_rate(cfg_name, steps, warmup, threads, batch=1):
+    """images/s of the reference's eager fp32 CPU forward (the unmodified reference where importable, else its
+    port oracle/*_ref.py) on a bounded sample: `batch` images of the same workload per step."""
     torch.set_num_threads(threads)
-    cfg = configs.taskprompter(cfg_name)
-    sd = TPR.init_state_dict(cfg, seed=0)
-    x = torch.randn(1, 3, *cfg["img_size"], generator=torch.Generator().manual_seed(1))
+    fwd, kind, cfg = reference_forward(cfg_name, "cpu")
+    x = torch.randn(batch, 3, *cfg["img_size"], generator=torch.Generator().manual_seed(1))
     with torch.no_grad():
         for _ in range(warmup):
-            TPR.forward(sd, cfg, x)
+            fwd(x)
         t0 = time.perf_counter()
         for _ in range(steps):
-            TPR.forward(sd, cfg, x)
+            fwd(x)
         dt = time.perf_counter() - t0
-    return steps / dt, dt / steps
+    return batch * steps / dt, dt / steps, kind
+
+
+def gpu_eager_baseline(cfg_name, batch, dev, steps=5, warmup=2):
+    """The library-call baseline SURVEY.md 2.2 / 8(d) sets: the reference algorithm in eager PyTorch (cuBLAS / cuDNN)
+    on the SAME B200, same batch, CUDA-event timed: fp32 with TF32 off (the reference's arithmetic), TF32 on, and
+    bf16 autocast. A baseline leg like cpu_baseline -- nothing here is on the product path."""
+    fwd, kind, cfg = reference_forward(cfg_name, dev)
+    x = torch.randn(batch, 3, *cfg["img_size"], device=dev)
+    res = {"kind": kind, "batch": batch, "steps": steps, "warmup": warmup, "unit": "images/s",
+           "what": "eager PyTorch forward of the reference algorithm on this GPU (cuBLAS / cuDNN kernels)"}
+    old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+
+    def timed(ctx):
+        with torch.no_grad(), ctx:
+            for _ in range(warmup):
+                fwd(x)
+            torch.cuda.synchronize()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            for _ in range(steps):
+                fwd(x)
+            e.record()
+            torch.cuda.synchronize()
+        return batch * steps / (s.elapsed_time(e) * 1e-3)
+
+    import contextlib
+    try:
+        torch.backends.cuda.matmul.allow_tf32 = False
+        torch.backends.cudnn.allow_tf32 = False
+        res["fp32"] = timed(contextlib.nullcontext())
+        torch.backends.cuda.matmul.allow_tf32 = True
+        torch.backends.cudnn.allow_tf32 = True
+        res["tf32"] = timed(contextlib.nullcontext())
+        res["bf16_autocast"] = timed(torch.autocast("cuda", dtype=torch.bfloat16))
+    except Exception as ex:  # e.g. out of memory at cfg5: report what ran
+        res["error"] = f"{type(ex).__name__}: {ex}"[:200]
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+    return res
 
 
 def run_reference(args):
@@ -149,16 +221,19 @@ def run_reference(args):
     if rank != 0:
         return
     threads = pick_cpu_threads()
-    rate, sec = cpu_oracle_rate(args.config, args.steps, min(args.warmup, 1), threads)
-    sample = (f"batch 1 of {args.config} per step (fp32 eager CPU, eval), {args.steps} steps, {threads} of "
-              f"{os.cpu_count()} host threads (fastest setting, see pick_cpu_threads)")
+    B = args.batch
+    rate, sec, kind = cpu_oracle_rate(args.config, args.steps, args.warmup, threads, batch=B)
+    what = "the unmodified reference model" if kind == "reference" else "CPU port of the reference forward (oracle/)"
+    sample = (f"batch {B} of {args.config} per step (fp32 eager CPU, eval, {what}), {args.warmup} warm-up + "
+              f"{args.steps} timed steps, {threads} of {os.cpu_count()} host threads (fastest setting, see pick_cpu_threads)")
     line = {
         "impl": "reference", "metric": "images/sec", "value": rate, "unit": "images/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"TaskPrompter ViT-L PASCAL-Context 512x512 5 tasks ({args.config}), "
-                               "CPU port of the reference forward, batch 1 per step"},
-        "cpu_baseline": {"value": rate, "unit": "images/s", "cores": threads, "kind": "port", "sample": sample},
+        "config": {"workload": f"{WORKLOAD[args.config]}, {args.config}, bs {B}/GPU, random-init weights, eval",
+                   "global_batch": B, "parallelism": "one CPU process (rank 0), host threads as stated",
+                   "precision_mode": "fp32 eager CPU"},
+        "cpu_baseline": {"value": rate, "unit": "images/s", "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": rate, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -230,7 +305,8 @@ def gemm_roofline(model, plan, x_dev, peaks, peak_src):
     # DRAM bytes per launch of the same kernel family, from the committed ncu capture of one forward of this workload
     traffic, traffic_src = None, None
     tpath = os.path.join(ROOT, "profiles", "dram_traffic.json")
-    if os.path.exists(tpath) and model.nsplit == 2 and tuple(x_dev.shape) == (4, 3, 512, 512):
+    if (os.path.exists(tpath) and model.nsplit == 2 and tuple(x_dev.shape) == (4, 3, 512, 512)
+            and type(model).__name__ == "TaskPrompterWrapper"):
         with open(tpath) as f:
             tj = json.load(f)
         traffic = tj["gemm_family"]["bytes_per_launch"]
@@ -273,14 +349,11 @@ def run_ours(args):
     barrier, max_over_ranks = D.barrier, D.max_over_ranks
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
-    from mtt_b200 import taskprompter as TP
-    from mtt_b200 import configs
-
-    cfg = configs.taskprompter(args.config)
+    cfg, M, _ = family(args.config)
     nsplit = 2 if args.mode == "parity" else 1
     torch.manual_seed(0)
     with torch.device(dev):
-        model = TP.build_from_config(cfg, nsplit=nsplit, use_graph=True).eval()
+        model = M.build_from_config(cfg, nsplit=nsplit, use_graph=True).eval()
     B = args.batch
     H, W = cfg["img_size"]
     n_rot = 4
@@ -302,18 +375,23 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    barrier(world)
-    torch.cuda.synchronize()
-    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    s.record()
-    with torch.no_grad():
-        for i in range(args.steps):
-            model(dev_in[i % n_rot])
-    e.record()
-    torch.cuda.synchronize()
-    barrier(world)
-    ms_total = max_over_ranks(s.elapsed_time(e), world, dev)
+    # `repeats` timed regions of EXACTLY `steps` steps each (barrier + synchronize on both sides, max over ranks);
+    # the reported region is the median one, so a single power-cap excursion does not move the headline
+    regions = []
+    for _ in range(max(1, args.repeats)):
+        barrier(world)
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        with torch.no_grad():
+            for i in range(args.steps):
+                model(dev_in[i % n_rot])
+        e.record()
+        torch.cuda.synchronize()
+        barrier(world)
+        regions.append(max_over_ranks(s.elapsed_time(e), world, dev))
     clocks = sampler.stop() if rank == 0 else None
+    ms_total = sorted(regions)[len(regions) // 2]
     value = world * B * args.steps / (ms_total * 1e-3)
 
     # ---------------- end to end through the public call, host buffers, H2D + D2H inside the timed region
@@ -365,20 +443,22 @@ def run_ours(args):
     peaks, peak_src = load_peaks()
     roof = gemm_roofline(model, plan, dev_in[0], peaks, peak_src)
     gflop_img = GFLOP_PER_IMAGE.get(args.config)
+    tot_gflop = gflop_img * B if gflop_img else None
     line = {
         "metric": "images/sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16x3 (split-bf16 operands, fp32 accumulate)" if nsplit == 2 else "bf16",
         "data": "synthetic",
         "config": {
-            "workload": f"TaskPrompter ViT-L PASCAL-Context (5 tasks) 512x512 forward, {args.config}, "
-                        f"bs {B}/GPU, random-init weights, eval",
+            "workload": f"{WORKLOAD[args.config]}, {args.config}, bs {B}/GPU, random-init weights, eval",
             "global_batch": world * B, "parallelism": f"dp{world} (batch-sharded forward, no collective)",
             "precision_mode": args.mode,
             "l2": "no explicit flush: each step streams 1.6 GB of packed weights plus ~1 GB of activations "
                   "(>> 126 MB L2) and the input rotates over 4 buffers",
         },
         "clocks": clocks,
+        "repeats": {"n": len(regions), "steps_each": args.steps, "reported": "median region",
+                    "images_per_s": [world * B * args.steps / (r * 1e-3) for r in regions]},
         "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": in_bytes,
                 "d2h_bytes_per_step": out_bytes, "ms_per_step": e2e_ms / args.steps, "wall_ms_per_step": wall_ms / args.steps,
                 "note": "pinned-host input -> H2D -> model(x) -> all task logits D2H (overlapped with the next step)"},
@@ -388,12 +468,25 @@ def run_ours(args):
     }
     if gflop_img:
         line["model_tflops_algorithmic"] = value * gflop_img / 1e3 / world
+        peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
+        line["whole_step"] = {"gflop_per_step_algorithmic": tot_gflop, "tflops_algorithmic": value * gflop_img / 1e3 / world,
+                              "frac_of_sustained_bf16_peak": value * gflop_img / 1e3 / world / peak,
+                              "note": "every FLOP of the reference forward (SURVEY.md 8d) over the whole step time"}
+    if world == 1 and not args.no_gpu_eager:
+        del model, plan
+        torch.cuda.empty_cache()
+        ge = gpu_eager_baseline(args.config, B, dev)
+        for k in ("fp32", "tf32", "bf16_autocast"):
+            if k in ge:
+                ge[f"ours_over_{k}"] = value / ge[k]
+        line["gpu_eager_baseline"] = ge
     if world == 1 and not args.no_cpu_baseline:
         threads = pick_cpu_threads()
-        rate, sec = cpu_oracle_rate(args.config, 3, 1, threads)
-        line["cpu_baseline"] = {"value": rate, "unit": "images/s", "cores": threads, "kind": "port",
-                                "sample": f"3 forwards of batch 1 of {args.config} (oracle/taskprompter_ref.py, fp32 "
-                                          f"eager, {threads} of {os.cpu_count()} host threads = fastest setting)"}
+        n_fwd = 1 if args.config == "tp_cfg5" else 3
+        rate, sec, kind = cpu_oracle_rate(args.config, n_fwd, 1, threads)
+        line["cpu_baseline"] = {"value": rate, "unit": "images/s", "cores": threads, "kind": kind,
+                                "sample": f"{n_fwd} forward(s) of batch 1 of {args.config} (fp32 eager, eval, "
+                                          f"{threads} of {os.cpu_count()} host threads = fastest setting)"}
     print(json.dumps(line), file=_OUT, flush=True)
     D.teardown(world)
 
@@ -406,9 +499,19 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default="parity", choices=["parity", "speed"])
     ap.add_argument("--config", default="tp_cfg4")
-    ap.add_argument("--batch", type=int, default=4)
+    ap.add_argument("--batch", type=int, default=0, help="images per GPU per step (default: the config's)")
+    ap.add_argument("--repeats", type=int, default=5, help="timed regions of --steps steps; the median is reported")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-eager", action="store_true")
     args = ap.parse_args()
+    if args.config not in WORKLOAD:       # any named configuration of mtt_b200/configs.py (tiny ones: contract tests)
+        try:
+            family(args.config)
+        except KeyError:
+            ap.error(f"--config: unknown configuration {args.config!r}")
+        WORKLOAD[args.config] = f"{args.config} (test configuration)"
+    if args.batch <= 0:
+        args.batch = DEFAULT_BATCH.get(args.config, 2)
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     # stdout carries exactly ONE JSON line: whatever a library prints to file descriptor 1 (NCCL's "NCCL version ..."
     # banner at init, for one) is sent to stderr; the JSON line goes to the saved descriptor.

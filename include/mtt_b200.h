@@ -103,6 +103,11 @@ typedef struct {
    * of every image out of the joint [B*N, C] stream for token_trans (TP taskprompter.py:219). */
   int32_t a_group_rows;
   int64_t a_group_stride;
+  /* >1: the in-group row index is multiplied by this stride, r_out = (r / in_group) * out_group + out_offset +
+   * (r % in_group) * out_row_stride -- with in_group = W, out_group = 4W, stride 2, offset 2W*dy + dx the rows of an
+   * [B,H,W] map land on the (dy,dx) phase of the [B,2H,2W] map: ConvTranspose2d(k2,s2) as four GEMMs
+   * (TP taskprompter.py:704, DEConvHead). 0 / 1 = dense. */
+  int32_t out_row_stride;
 } mtt_gemm_desc;
 
 int mtt_gemm(const mtt_gemm_desc* d, mtt_stream_t stream);
@@ -130,9 +135,9 @@ typedef struct {
 } mtt_attn_desc;
 
 int mtt_attention(const mtt_attn_desc* d, mtt_stream_t stream);
-/* 0 / 5 = the default warp-specialised kernel (TMA warp, MMA warp, 4 softmax warps, 64-key blocks with two S
- * buffers, Q in TMEM); 3 = its predecessor (attention3_tc.cu), kept as an independent implementation. Same function
- * and results contract; tuning / testing knob (also env MTT_ATTN_VARIANT). */
+/* 0 = the default warp-specialised kernel (TMA warp, MMA warp, softmax warps, S / P / O in TMEM); other values select
+ * development variants of the same function when the library was built with them. Tuning / testing knob (also env
+ * MTT_ATTN_VARIANT). */
 void mtt_set_attention_variant(int variant);
 /* Debug aid: a device buffer of 4096 uint32 that receives %clock stamps of the MMA warp and of softmax warp 0 of
  * two co-resident CTAs for every following parity-mode launch of the warp-specialised kernel (NULL = off, the
@@ -277,6 +282,87 @@ typedef struct {
   int64_t ldo;
 } mtt_invpt_attn_desc;
 int mtt_invpt_attention(const mtt_invpt_attn_desc* d, mtt_stream_t stream);
+
+/* ---- the named operators of SURVEY.md section 8(b) -----------------------------------------------------------
+ * Each replaces one eager-op group of the reference block / decoder with a fixed launch sequence; intermediates
+ * live in the caller's workspace (size from mtt_workspace_bytes, 256-byte aligned), so nothing is allocated and
+ * the whole forward stays capturable in one CUDA graph.
+ *
+ * DEVIATIONS from the entry-point list SURVEY.md 8(b) sketched (all deliberate, same ownership / error / stream
+ * rules): (1) attn_fwd, chan_prompt_logits, bilinear_up, invpt_attn, layernorm are the single-kernel entries above
+ * (mtt_attention, mtt_chan_logits, mtt_bilinear, mtt_invpt_attention, mtt_layernorm) under their round-1 names;
+ * (2) shapes travel in mtt_shape and weights in mtt_weight (pre-packed planes) instead of a flat argument list;
+ * (3) LayerNorm is a kernel of the sequence, not a prologue inside the GEMM: the normalised rows are written once as
+ * split planes (8.4 us per 16.8 MB at cfg4) and read back from L2 by the TMA producer. */
+enum mtt_op {
+  MTT_OP_LN_QKV = 1, MTT_OP_ATTN_FWD = 2, MTT_OP_PROJ_RESIDUAL = 3, MTT_OP_LN_MLP_RESIDUAL = 4,
+  MTT_OP_CHAN_PROMPT_LOGITS = 5, MTT_OP_GATED_CONV1X1 = 6, MTT_OP_CONV3X3_BN_ACT = 7, MTT_OP_BILINEAR_UP = 8,
+  MTT_OP_INVPT_ATTN = 9, MTT_OP_LAYERNORM = 10
+};
+typedef struct {
+  int32_t rows;   /* token rows of the joint stream (B*N), or output pixels (B*H*W) for the conv operators */
+  int32_t C;      /* model width */
+  int32_t hidden; /* Mlp hidden width / conv output channels */
+  int32_t nsplit; /* 2 = parity mode (both planes), 1 = speed mode */
+  int32_t B, N, H, T; /* batch, tokens per image, heads, prompt rows */
+} mtt_shape;
+typedef struct {
+  const void* hi; /* packed planes produced by mtt_pack_weight / mtt_pack_conv_weight (caller-owned) */
+  const void* lo;
+  int64_t ld;
+} mtt_weight;
+
+size_t mtt_workspace_bytes(int32_t op, const mtt_shape* shape);
+
+/* qkv = LN(x) . Wqkv^T + b: TP taskprompter.py:272 (norm1 on prompts and patches), :199, :201. x fp32 [rows, C];
+ * workspace receives LN(x) as split planes [nsplit][rows][pad8(C)] (the channel-prompt path reads it from there). */
+int mtt_ln_qkv(const float* x, int64_t ldx, const float* gamma, const float* beta, float eps, const mtt_weight* wqkv,
+               const float* bias, void* qkv_hi, void* qkv_lo, int64_t ldq, const mtt_shape* shape, void* workspace,
+               size_t ws_bytes, mtt_stream_t stream);
+/* x += attn_out . Wproj^T + b: TP taskprompter.py:212 + the residual adds of :273 / :276 (in place on x). */
+int mtt_proj_residual(const void* a_hi, const void* a_lo, int64_t lda, const mtt_weight* wproj, const float* bias,
+                      float* x, int64_t ldx, const mtt_shape* shape, mtt_stream_t stream);
+/* x += fc2(gelu(fc1(LN(x)))): TP taskprompter.py:274 / :277 (timm Mlp, exact-erf GELU), in place on x. */
+int mtt_ln_mlp_residual(float* x, int64_t ldx, const float* gamma, const float* beta, float eps, const mtt_weight* w1,
+                        const float* b1, const mtt_weight* w2, const float* b2, const mtt_shape* shape,
+                        void* workspace, size_t ws_bytes, mtt_stream_t stream);
+/* Spatial and channel gating of the patch map for one task + the two 1x1 decode convs, written side by side into
+ * the `cat` operand of fea_fuse (TP taskprompter.py:436-447, :452-468, :471): columns [0, e) = spatial branch,
+ * [chan_col, chan_col + e) = channel branch. x / prompt_logits / chan_logits as in mtt_gate_split. */
+int mtt_gated_conv1x1(const float* x, int64_t ldx, int64_t x_group_rows, int64_t x_row_offset,
+                      const float* prompt_logits, const float* chan_logits, int32_t task, int32_t gh, int32_t gw,
+                      int32_t nh, int32_t nw, const mtt_weight* w_spa, const float* b_spa, const mtt_weight* w_chan,
+                      const float* b_chan, int32_t e, void* cat_hi, void* cat_lo, int64_t ld_cat, int32_t chan_col,
+                      const mtt_shape* shape, void* workspace, size_t ws_bytes, mtt_stream_t stream);
+/* 3x3 conv (stride 1, dilation dil, zero padding) with folded eval BatchNorm + activation on an NHWC split map, and
+ * optionally the 1x1 prediction head right behind it (TP taskprompter.py:362 fea_fuse[1..3]; :691-695 ConvHead;
+ * IP transformer_decoder.py:113, invpt.py:33-38, :493). mid_* = the activation map (NULL with a fused head: it then
+ * lives in the workspace); w_head NULL = no head. */
+int mtt_conv3x3_bn_act(const void* a_hi, const void* a_lo, int64_t lda, int32_t B, int32_t H, int32_t W, int32_t Cin,
+                       int32_t dil, const mtt_weight* w3, const float* b3, int32_t Cout, int32_t act, void* mid_hi,
+                       void* mid_lo, int64_t ld_mid, const mtt_weight* w_head, const float* b_head, int32_t n_out,
+                       float* out_f32, int64_t ldo, int32_t nsplit, void* workspace, size_t ws_bytes,
+                       mtt_stream_t stream);
+
+/* ---- parameter pre-packing (once per parameter version; outputs are caller-owned tensors) ---------------------
+ * mtt_pack_weight: nn.Linear / 1x1 conv weight fp32 [N, K] -> split planes [N, ld_out], K zero-padded to 8.
+ * mtt_pack_conv_weight: Conv2d weight [N, Cin, k, k] (transposed = 0) or ConvTranspose2d weight [Cin, N, k, k]
+ *   (transposed = 1: stored as the spatially flipped kernel of the equivalent convolution over the zero-inserted
+ *   map) -> tap-major planes [N, k*k*cin_pad], cin_pad = Cin rounded up to 64, with an eval-mode BatchNorm folded in
+ *   (bn_gamma NULL = none): w' = w * gamma / sqrt(var + eps), bias_out = (bias - mean) * gamma / sqrt(var + eps) +
+ *   beta. scale_ws: N floats of scratch. */
+int mtt_pack_weight(const float* w, int64_t ld_w, int32_t N, int32_t K, int32_t nsplit, void* out_hi, void* out_lo,
+                    int64_t ld_out, mtt_stream_t stream);
+int mtt_pack_conv_weight(const float* w, const float* bias, const float* bn_gamma, const float* bn_beta,
+                         const float* bn_mean, const float* bn_var, float bn_eps, int32_t N, int32_t Cin,
+                         int32_t ksize, int32_t transposed, int32_t nsplit, void* out_hi, void* out_lo, int64_t ld_out,
+                         float* bias_out, float* scale_ws, mtt_stream_t stream);
+
+/* ---- layout changes at the nn.Module boundaries (ConvHead.forward takes / returns NCHW like the reference) ---- */
+int mtt_nchw_to_nhwc_split(const float* in, int32_t B, int32_t C, int32_t H, int32_t W, void* out_hi, void* out_lo,
+                           int64_t ld_out, mtt_stream_t stream);
+int mtt_nhwc_to_nchw(const float* in, int64_t ld_in, int32_t B, int32_t C, int32_t H, int32_t W, float* out,
+                     mtt_stream_t stream);
 
 #ifdef __cplusplus
 }

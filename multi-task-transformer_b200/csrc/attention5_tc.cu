@@ -440,13 +440,14 @@ template <int NSPLIT, bool TRACE>
 static int launch_attn5(const CUtensorMap* maps, const Attn5Params& p, cudaStream_t stream) {
   constexpr uint32_t smem =
       NSPLIT * kA5QTile + (kA5KStages + kA5VStages) * NSPLIT * kA5KVTile + 1024 + 256;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[kMaxDevices] = {};  // the opt-in is per device (and per kernel instantiation)
+  const int dev_ = current_device();
+  if (!attr_set[dev_]) {
     cudaError_t e = cudaFuncSetAttribute(attention5_kernel<NSPLIT, TRACE>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess)
-      return set_error(MTT_ERR_LAUNCH, "attention3: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    attr_set = true;
+      return set_error(MTT_ERR_LAUNCH, "attention5: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr_set[dev_] = true;
   }
   const int total = ((p.N + 127) / 128) * p.H * p.B;
   const int slots = 2 * sm_count();
@@ -455,7 +456,7 @@ static int launch_attn5(const CUtensorMap* maps, const Attn5Params& p, cudaStrea
   return check_launch("mtt_attention(variant 5)");
 }
 
-extern unsigned int* g_attn_trace;  // attention3_tc.cu (mtt_set_attention_trace)
+extern unsigned int* g_attn_trace;  // attention_tc.cu (mtt_set_attention_trace)
 
 int launch_attention5(const mtt_attn_desc* d, cudaStream_t stream) {
   const int C = d->H * 64;

@@ -10,7 +10,6 @@
 //   attention5_tc.cu  (default)  warp-specialised: TMA warp, MMA warp, four softmax warps, 64-key blocks with two
 //                                S buffers in TMEM, Q in TMEM (TS-form S = Q K^T), P written back in place over S,
 //                                O accumulated in TMEM with lazy rescaling; two CTAs per SM
-//   attention3_tc.cu  (variant 3) its predecessor, kept as an independent implementation for A/B runs and tests
 // Measured and dropped (profiles/README.md): a single-role kernel with 128-key blocks (tensor pipe 40 %), an
 // SS-form variant (shared-memory bound at N = 64: 49 cycles per MMA against 33 for TS, scripts/mma_probe.cu) and a
 // variant with eight softmax warps / two threads per row (20 % slower: pair barriers, 96-register cap).
@@ -19,12 +18,13 @@
 #include "host_common.h"
 
 namespace mtt {
-int launch_attention3(const mtt_attn_desc* d, cudaStream_t stream);  // attention3_tc.cu
 int launch_attention5(const mtt_attn_desc* d, cudaStream_t stream);  // attention5_tc.cu
-static int g_attn_variant = -1;  // -1: read MTT_ATTN_VARIANT once; 0 / 5 = default, 3 = attention3_tc.cu
+static int g_attn_variant = -1;  // -1: read MTT_ATTN_VARIANT once; 0 = default
+unsigned int* g_attn_trace = nullptr;  // mtt_set_attention_trace: clock-stamp buffer of the TRACE instantiation
 }  // namespace mtt
 
 extern "C" void mtt_set_attention_variant(int v) { mtt::g_attn_variant = v; }
+extern "C" void mtt_set_attention_trace(void* buf) { mtt::g_attn_trace = static_cast<unsigned int*>(buf); }
 
 extern "C" int mtt_attention(const mtt_attn_desc* d, mtt_stream_t stream_) {
   using namespace mtt;
@@ -42,6 +42,5 @@ extern "C" int mtt_attention(const mtt_attn_desc* d, mtt_stream_t stream_) {
     const char* e = getenv("MTT_ATTN_VARIANT");
     g_attn_variant = e ? atoi(e) : 0;
   }
-  if (g_attn_variant == 3) return launch_attention3(d, static_cast<cudaStream_t>(stream_));
   return launch_attention5(d, static_cast<cudaStream_t>(stream_));
 }

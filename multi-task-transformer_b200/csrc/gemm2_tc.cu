@@ -228,13 +228,14 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
 template <int NSPLIT, int BN2>
 static int launch_gemm2(const CUtensorMap* maps, const GemmParams& p, cudaStream_t stream) {
   using Cfg = Gemm2Cfg<NSPLIT>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[kMaxDevices] = {};  // the opt-in is per device (and per kernel instantiation)
+  const int dev_ = current_device();
+  if (!attr_set[dev_]) {
     cudaError_t e = cudaFuncSetAttribute(gemm2_tc_kernel<NSPLIT, BN2>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess)
       return set_error(MTT_ERR_LAUNCH, "gemm2: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    attr_set = true;
+    attr_set[dev_] = true;
   }
   const int pairs_m = (p.tiles_m + 1) / 2;
   const int tiles = pairs_m * p.tiles_n;

@@ -32,6 +32,7 @@ struct GemmParams {
   __nv_bfloat16* out_lo;
   long long ldo_bf;
   int in_group, out_group, out_offset;
+  int out_row_stride;  // >= 1: stride of the in-group row index (see mtt_gemm_desc)
   int vec_ok;
   int vec32_ok;  // every epilogue pointer / stride allows 32-byte accesses
   int a_groups_per_tile;  // >0: A rows are gathered in groups through a rank-3 tensor map
@@ -105,7 +106,7 @@ __device__ __forceinline__ RowInfo row_info(const GemmParams& p, int ms, int row
     m = ((long long)cb * p.H + y) * p.W + x;
   }
   r.mo = m;
-  if (p.in_group > 0) r.mo = (m / p.in_group) * p.out_group + p.out_offset + (m % p.in_group);
+  if (p.in_group > 0) r.mo = (m / p.in_group) * p.out_group + p.out_offset + (m % p.in_group) * p.out_row_stride;
   r.mr = (p.res_row_mod > 0) ? (m % p.res_row_mod) : r.mo;
   return r;
 }

@@ -67,6 +67,7 @@ int gemm_prepare(const mtt_gemm_desc* d, int b_box_rows, GemmParams& p, CUtensor
   p.in_group = d->in_group;
   p.out_group = d->out_group;
   p.out_offset = d->out_offset;
+  p.out_row_stride = d->out_row_stride > 1 ? d->out_row_stride : 1;
   if (p.out_hi && d->nsplit == 2 && !p.out_lo)
     return set_error(MTT_ERR_BAD_SHAPE, "mtt_gemm: out_lo missing for nsplit=2");
 

@@ -207,13 +207,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 template <int NSPLIT>
 static int launch_gemm(const CUtensorMap* maps, const GemmParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg<NSPLIT>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[kMaxDevices] = {};  // the opt-in is per device (and per kernel instantiation)
+  const int dev_ = current_device();
+  if (!attr_set[dev_]) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<NSPLIT>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess)
       return set_error(MTT_ERR_LAUNCH, "gemm: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    attr_set = true;
+    attr_set[dev_] = true;
   }
   const int tiles = p.tiles_m * p.tiles_n;
   const int grid = tiles < sm_count() ? tiles : sm_count();

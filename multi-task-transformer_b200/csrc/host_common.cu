@@ -76,14 +76,17 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
   return MTT_OK;
 }
 
+int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return (dev >= 0 && dev < kMaxDevices) ? dev : 0;
+}
+
 int sm_count() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-  }
-  return n;
+  static int n[kMaxDevices] = {};
+  const int dev = current_device();
+  if (!n[dev]) cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, dev);
+  return n[dev];
 }
 
 }  // namespace mtt

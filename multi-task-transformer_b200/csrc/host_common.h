@@ -19,6 +19,9 @@ int check_launch(const char* what);
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                    const uint64_t* strides_bytes, const uint32_t* box);
 
+// ordinal of the calling thread's current device (< kMaxDevices), and its SM count (cached per device)
+constexpr int kMaxDevices = 64;
+int current_device();
 int sm_count();
 
 }  // namespace mtt

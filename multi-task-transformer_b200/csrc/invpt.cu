@@ -402,10 +402,11 @@ extern "C" int mtt_invpt_attention(const mtt_invpt_attn_desc* d, mtt_stream_t st
     return set_error(MTT_ERR_BAD_SHAPE, "mtt_invpt_attention: bad fusion geometry");
   const size_t smem = ((size_t)kQT * d->C + (size_t)d->Tk * 33 + (size_t)2 * kQT * d->Tk) * sizeof(float);
   if (smem > 220 * 1024) return set_error(MTT_ERR_BAD_SHAPE, "mtt_invpt_attention: shared memory %zu", smem);
-  static bool attr = false;
-  if (!attr) {
+  static bool attr[kMaxDevices] = {};  // per device
+  const int dev_ = current_device();
+  if (!attr[dev_]) {
     cudaFuncSetAttribute(invpt_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-    attr = true;
+    attr[dev_] = true;
   }
   dim3 grid((d->Lq + kQT - 1) / kQT, d->B);
   invpt_attn_kernel<<<grid, kIAThreads, smem, STREAM>>>(

@@ -406,10 +406,11 @@ extern "C" int mtt_chan_logits(const float* cp, const void* xn_hi, const void* x
   const int wp = (gh / nh) * (gw / nw);
   const size_t smem = ((size_t)T * wp + (size_t)T * 32 * 33) * sizeof(float);
   if (smem > 200 * 1024) return set_error(MTT_ERR_BAD_SHAPE, "mtt_chan_logits: window too large");
-  static bool attr = false;
-  if (!attr) {
+  static bool attr[kMaxDevices] = {};  // per device
+  const int dev_ = current_device();
+  if (!attr[dev_]) {
     cudaFuncSetAttribute(chan_logits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attr = true;
+    attr[dev_] = true;
   }
   dim3 grid((C + 31) / 32, nh * nw, B);
   chan_logits_kernel<<<grid, dim3(32, 32), smem, STREAM>>>(cp, static_cast<const __nv_bfloat16*>(xn_hi),

@@ -417,7 +417,7 @@ class _Plan:
         """Run fn(k) for every task k, each on its own side stream forked from / joined to the current
         stream (the per-task chains are independent and individually too small to fill 148 SMs)."""
         T = self.T
-        if self.dev.type != "cuda":
+        if self.dev.type != "cuda" or getattr(self, "serial", False):   # serial: one stream (per-kernel timing)
             for k in range(T):
                 fn(k)
             return

@@ -24,6 +24,7 @@ class GemmDesc(C.Structure):
         ("out_hi", C.c_void_p), ("out_lo", C.c_void_p), ("ldo_bf", C.c_int64),
         ("in_group", C.c_int32), ("out_group", C.c_int32), ("out_offset", C.c_int32),
         ("a_group_rows", C.c_int32), ("a_group_stride", C.c_int64),
+        ("out_row_stride", C.c_int32),
     ]
 
 
@@ -35,6 +36,19 @@ class AttnDesc(C.Structure):
         ("B", C.c_int32), ("N", C.c_int32), ("H", C.c_int32), ("T", C.c_int32),
         ("nsplit", C.c_int32), ("scale", C.c_float),
     ]
+
+
+class Shape(C.Structure):
+    _fields_ = [("rows", C.c_int32), ("C", C.c_int32), ("hidden", C.c_int32), ("nsplit", C.c_int32),
+                ("B", C.c_int32), ("N", C.c_int32), ("H", C.c_int32), ("T", C.c_int32)]
+
+
+class Weight(C.Structure):
+    _fields_ = [("hi", C.c_void_p), ("lo", C.c_void_p), ("ld", C.c_int64)]
+
+
+OP_LN_QKV, OP_ATTN_FWD, OP_PROJ_RESIDUAL, OP_LN_MLP_RESIDUAL, OP_CHAN_PROMPT_LOGITS = 1, 2, 3, 4, 5
+OP_GATED_CONV1X1, OP_CONV3X3_BN_ACT, OP_BILINEAR_UP, OP_INVPT_ATTN, OP_LAYERNORM = 6, 7, 8, 9, 10
 
 
 class BilinearSrc(C.Structure):
@@ -87,6 +101,23 @@ SYMBOLS = {
     "mtt_dwconv3x3_s2": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i64, _vp]),
     "mtt_avgpool": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _i64, _vp]),
     "mtt_invpt_attention": (C.c_int, [C.POINTER(InvptAttnDesc), _vp]),
+    "mtt_workspace_bytes": (C.c_size_t, [_i32, C.POINTER(Shape)]),
+    "mtt_ln_qkv": (C.c_int, [_vp, _i64, _vp, _vp, _f32, C.POINTER(Weight), _vp, _vp, _vp, _i64, C.POINTER(Shape), _vp,
+                             C.c_size_t, _vp]),
+    "mtt_proj_residual": (C.c_int, [_vp, _vp, _i64, C.POINTER(Weight), _vp, _vp, _i64, C.POINTER(Shape), _vp]),
+    "mtt_ln_mlp_residual": (C.c_int, [_vp, _i64, _vp, _vp, _f32, C.POINTER(Weight), _vp, C.POINTER(Weight), _vp,
+                                      C.POINTER(Shape), _vp, C.c_size_t, _vp]),
+    "mtt_gated_conv1x1": (C.c_int, [_vp, _i64, _i64, _i64, _vp, _vp, _i32, _i32, _i32, _i32, _i32, C.POINTER(Weight), _vp,
+                                    C.POINTER(Weight), _vp, _i32, _vp, _vp, _i64, _i32, C.POINTER(Shape), _vp,
+                                    C.c_size_t, _vp]),
+    "mtt_conv3x3_bn_act": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, C.POINTER(Weight), _vp, _i32, _i32,
+                                     _vp, _vp, _i64, C.POINTER(Weight), _vp, _i32, _vp, _i64, _i32, _vp, C.c_size_t,
+                                     _vp]),
+    "mtt_pack_weight": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _vp, _vp, _i64, _vp]),
+    "mtt_pack_conv_weight": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _f32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _i64,
+                                       _vp, _vp, _vp]),
+    "mtt_nchw_to_nhwc_split": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _i64, _vp]),
+    "mtt_nhwc_to_nchw": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp]),
 }
 
 _lib = None

@@ -85,18 +85,19 @@ def layernorm(x, gamma, beta, eps, out_f32=None, out_split=None):
 
 def gemm(a, w, *, M=None, N=None, K=None, bias=None, act=ACT_NONE, residual=None, res_row_mod=0,
          out_f32=None, out_split=None, out_col_offset=0, regroup=None, conv=None, a_row_offset=0,
-         a_gather=None):
+         a_gather=None, w_col_offset=0):
     """D = act(A @ W^T + bias) + residual on the tcgen05 GEMM.
 
     a: Split [M, K] (or NHWC activation [B*H*W, C] when ``conv=(B, H, W, ksize, dil)``);
     w: Split [N, K] (conv: [N, ksize*ksize*cin_pad]); outputs: fp32 tensor and/or Split.
-    regroup=(in_group, out_group, out_offset) scatters output rows; a_gather=(group_rows, group_stride)
-    gathers A rows in groups (M must be given)."""
+    regroup=(in_group, out_group, out_offset[, row_stride]) scatters output rows; a_gather=(group_rows,
+    group_stride) gathers A rows in groups (M must be given); w_col_offset selects a K-slice of a wider packed W."""
     nsplit = min(a.nsplit, w.nsplit)
     d = _L.GemmDesc()
     aoff = 2 * a_row_offset * a.ld
     d.a_hi, d.a_lo, d.lda = a.hi.data_ptr() + aoff, (a.lo.data_ptr() + aoff if nsplit == 2 else 0), a.ld
-    d.b_hi, d.b_lo, d.ldb = w.hi.data_ptr(), (w.lo.data_ptr() if nsplit == 2 else 0), w.ld
+    woff = 2 * w_col_offset
+    d.b_hi, d.b_lo, d.ldb = w.hi.data_ptr() + woff, (w.lo.data_ptr() + woff if nsplit == 2 else 0), w.ld
     d.M = a.rows if M is None else M
     d.N = w.rows if N is None else N
     d.K = a.cols if K is None else K
@@ -122,7 +123,8 @@ def gemm(a, w, *, M=None, N=None, K=None, bias=None, act=ACT_NONE, residual=None
         if nsplit == 2 and out_split.nsplit != 2:
             raise ValueError("nsplit=2 GEMM needs a 2-plane split output")
     if regroup is not None:
-        d.in_group, d.out_group, d.out_offset = regroup
+        d.in_group, d.out_group, d.out_offset = regroup[:3]
+        d.out_row_stride = regroup[3] if len(regroup) > 3 else 1
     if a_gather is not None:    # (group_rows, group_stride): logical row (g, i) at physical row g*stride + i
         d.a_group_rows, d.a_group_stride = a_gather
     rc = _L.load().mtt_gemm(C.byref(d), _stream())
@@ -152,7 +154,7 @@ def set_gemm_variant(v):
 
 
 def set_attention_variant(v):
-    """0 / 5 = default warp-specialised attention kernel (attention5_tc.cu), 3 = its predecessor (tuning / testing knob)."""
+    """0 = default attention kernel; other values select development variants when built (tuning / testing knob)."""
     _L.load().mtt_set_attention_variant(int(v))
 
 
@@ -331,3 +333,141 @@ def invpt_attention(q, k, v, out, *, B, Lq, Tk, Cdim, scale, prev_score=None, T=
     d.out_hi, d.out_lo, d.ldo = out.hi.data_ptr(), (out.lo.data_ptr() if out.nsplit == 2 else 0), out.ld
     rc = _L.load().mtt_invpt_attention(C.byref(d), _stream())
     _L.check(rc, "mtt_invpt_attention")
+
+
+# ------------------------------------------------------------------------------------------------
+# named operators of SURVEY.md section 8(b) (block_ops.cu) and the packing / layout entry points
+# ------------------------------------------------------------------------------------------------
+def _shape(rows=0, Cdim=0, hidden=0, nsplit=2, B=0, N=0, H=0, T=0):
+    s = _L.Shape()
+    s.rows, s.C, s.hidden, s.nsplit, s.B, s.N, s.H, s.T = rows, Cdim, hidden, nsplit, B, N, H, T
+    return s
+
+
+def _weight(w, nsplit):
+    x = _L.Weight()
+    x.hi, x.lo, x.ld = w.hi.data_ptr(), (w.lo.data_ptr() if nsplit == 2 else 0), w.ld
+    return x
+
+
+def workspace_bytes(op, **shape):
+    return int(_L.load().mtt_workspace_bytes(op, C.byref(_shape(**shape))))
+
+
+def workspace(nbytes, device):
+    """A 256-byte aligned byte buffer (torch's caching allocator aligns to 512)."""
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+def ws_split_view(ws, byte_offset, rows, cols, nsplit):
+    """The Split living at `byte_offset` of a workspace, laid out as block_ops.cu does: [nsplit][rows][pad8(cols)]."""
+    ld = round_up(cols, 8)
+    n = nsplit * rows * ld
+    sp = Split.__new__(Split)
+    sp.rows, sp.cols, sp.ld, sp.nsplit = rows, cols, ld, nsplit
+    sp.buf = ws[byte_offset: byte_offset + 2 * n].view(torch.bfloat16).view(nsplit, rows, ld)
+    return sp
+
+
+def ln_qkv(x, gamma, beta, eps, wqkv, bias, qkv, ws):
+    """qkv = LN(x) @ Wqkv^T + b (taskprompter.py:272,:199,:201); LN(x) stays in `ws` as split planes."""
+    rows, Cd = x.shape
+    ns = min(wqkv.nsplit, qkv.nsplit)
+    rc = _L.load().mtt_ln_qkv(_ptr(x), x.stride(0), _ptr(gamma), _ptr(beta), float(eps), C.byref(_weight(wqkv, ns)),
+                              _ptr(bias), _ptr(qkv.hi), _ptr(qkv.lo), qkv.ld, C.byref(_shape(rows, Cd, nsplit=ns)),
+                              _ptr(ws), ws.numel(), _stream())
+    _L.check(rc, "mtt_ln_qkv")
+
+
+def proj_residual(ao, wproj, bias, x):
+    """x += ao @ Wproj^T + b in place (taskprompter.py:212,:273,:276)."""
+    rows, Cd = x.shape
+    ns = min(ao.nsplit, wproj.nsplit)
+    rc = _L.load().mtt_proj_residual(_ptr(ao.hi), _ptr(ao.lo), ao.ld, C.byref(_weight(wproj, ns)), _ptr(bias), _ptr(x),
+                                     x.stride(0), C.byref(_shape(rows, Cd, nsplit=ns)), _stream())
+    _L.check(rc, "mtt_proj_residual")
+
+
+def ln_mlp_residual(x, gamma, beta, eps, w1, b1, w2, b2, ws):
+    """x += fc2(gelu(fc1(LN(x)))) in place (taskprompter.py:274,:277)."""
+    rows, Cd = x.shape
+    ns = min(w1.nsplit, w2.nsplit)
+    rc = _L.load().mtt_ln_mlp_residual(_ptr(x), x.stride(0), _ptr(gamma), _ptr(beta), float(eps),
+                                       C.byref(_weight(w1, ns)), _ptr(b1), C.byref(_weight(w2, ns)), _ptr(b2),
+                                       C.byref(_shape(rows, Cd, hidden=w1.rows, nsplit=ns)), _ptr(ws), ws.numel(),
+                                       _stream())
+    _L.check(rc, "mtt_ln_mlp_residual")
+
+
+def gated_conv1x1(x, x_group_rows, x_row_offset, prompt_logits, chan_lg, task, w_spa, b_spa, w_chan, b_chan, e, cat,
+                  chan_col, ws, *, B, T, N, H, Cdim, gh, gw, nh, nw):
+    """Spatial + channel gating of task `task` and the two 1x1 decode convs into `cat` (taskprompter.py:436-471)."""
+    ns = min(w_spa.nsplit, cat.nsplit)
+    rc = _L.load().mtt_gated_conv1x1(_ptr(x), x.stride(-2), x_group_rows, x_row_offset, _ptr(prompt_logits),
+                                     _ptr(chan_lg), task, gh, gw, nh, nw, C.byref(_weight(w_spa, ns)), _ptr(b_spa),
+                                     C.byref(_weight(w_chan, ns)), _ptr(b_chan), e, _ptr(cat.hi), _ptr(cat.lo), cat.ld,
+                                     chan_col, C.byref(_shape(0, Cdim, nsplit=ns, B=B, N=N, H=H, T=T)), _ptr(ws),
+                                     ws.numel(), _stream())
+    _L.check(rc, "mtt_gated_conv1x1")
+
+
+def conv3x3_bn_act(a, w3, b3, Cin, Cout, act, *, B, H, W, dil=1, mid=None, w_head=None, b_head=None, n_out=0,
+                   out_f32=None, ws=None):
+    """3x3 conv + folded BN + act on an NHWC Split (optionally followed by the fused 1x1 head -> out_f32)."""
+    ns = min(a.nsplit, w3.nsplit)
+    rc = _L.load().mtt_conv3x3_bn_act(
+        _ptr(a.hi), _ptr(a.lo), a.ld, B, H, W, Cin, dil, C.byref(_weight(w3, ns)), _ptr(b3), Cout, act,
+        _ptr(mid.hi) if mid is not None else None, _ptr(mid.lo) if mid is not None else None,
+        mid.ld if mid is not None else 0, C.byref(_weight(w_head, ns)) if w_head is not None else None, _ptr(b_head),
+        n_out, _ptr(out_f32), out_f32.stride(-2) if out_f32 is not None else 0, ns, _ptr(ws),
+        ws.numel() if ws is not None else 0, _stream())
+    _L.check(rc, "mtt_conv3x3_bn_act")
+
+
+def pack_weight(w, nsplit):
+    """fp32 [N, K] -> Split [N, K] through mtt_pack_weight."""
+    assert w.dtype == torch.float32 and w.dim() == 2 and w.stride(1) == 1
+    N, K = w.shape
+    out = Split(N, round_up(K, 8), w.device, nsplit)
+    out.cols = K
+    rc = _L.load().mtt_pack_weight(_ptr(w), w.stride(0), N, K, nsplit, _ptr(out.hi), _ptr(out.lo), out.ld, _stream())
+    _L.check(rc, "mtt_pack_weight")
+    return out
+
+
+def pack_conv_weight(w, bias, bn, nsplit, transposed=False):
+    """Conv2d [N,Cin,k,k] (or ConvTranspose2d [Cin,N,k,k], transposed=True) + optional eval BatchNorm -> (Split
+    [N, k*k*cin_pad] tap-major, folded bias fp32 [N]) through mtt_pack_conv_weight."""
+    assert w.dtype == torch.float32 and w.is_contiguous() and w.dim() == 4 and w.shape[2] == w.shape[3]
+    N, Cin = (w.shape[1], w.shape[0]) if transposed else (w.shape[0], w.shape[1])
+    k = w.shape[2]
+    cin_pad = round_up(Cin, 64)
+    out = Split(N, k * k * cin_pad, w.device, nsplit)
+    bias_out = torch.empty(N, dtype=torch.float32, device=w.device)
+    scale = torch.empty(N, dtype=torch.float32, device=w.device)
+    f = lambda t: t.detach().to(device=w.device, dtype=torch.float32).contiguous()
+    if bn is not None:
+        g, b, m, v, eps = f(bn.weight), f(bn.bias), f(bn.running_mean), f(bn.running_var), float(bn.eps)
+    else:
+        g = b = m = v = None
+        eps = 0.0
+    bias = f(bias) if bias is not None else None
+    rc = _L.load().mtt_pack_conv_weight(_ptr(w), _ptr(bias), _ptr(g), _ptr(b), _ptr(m), _ptr(v), eps, N, Cin, k,
+                                        1 if transposed else 0, nsplit, _ptr(out.hi), _ptr(out.lo), out.ld,
+                                        _ptr(bias_out), _ptr(scale), _stream())
+    _L.check(rc, "mtt_pack_conv_weight")
+    return out, bias_out
+
+
+def nchw_to_nhwc_split(x, out):
+    """x fp32 NCHW [B,C,H,W] -> out Split [B*H*W, C] (module-boundary forwards take NCHW like the reference)."""
+    assert x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 4
+    B, Cd, H, W = x.shape
+    rc = _L.load().mtt_nchw_to_nhwc_split(_ptr(x), B, Cd, H, W, _ptr(out.hi), _ptr(out.lo), out.ld, _stream())
+    _L.check(rc, "mtt_nchw_to_nhwc_split")
+
+
+def nhwc_to_nchw(x, ld_in, B, Cd, H, W, out):
+    assert x.dtype == torch.float32 and out.is_contiguous() and tuple(out.shape) == (B, Cd, H, W)
+    rc = _L.load().mtt_nhwc_to_nchw(_ptr(x), ld_in, B, Cd, H, W, _ptr(out), _stream())
+    _L.check(rc, "mtt_nhwc_to_nchw")

@@ -7,12 +7,25 @@ checkpoints (`backbone.blocks.{i}.attn.qkv.weight`, `backbone.fea_fuse.{il}.{tas
   Attention / Block / TaskPrompter / ConvHead   TaskPrompter/models/transformers/taskprompter.py:168-487,688-698
   TaskPrompterWrapper                           TaskPrompter/models/taskprompter_wrapper.py:9-40
 
-The modules only OWN parameters; all arithmetic runs in libmtt_sm100.so through `ops`. The fused
-forward lives in `_Plan`: packed (split-bf16, BatchNorm-folded) weights plus a fixed workspace for one
-batch size, optionally captured in a CUDA graph. Changes to the reference's internal contract:
-`Block` no longer returns the full [B,H,N,N] attention maps (only their prompt rows are ever
-consumed), and dead code (`chan_x`, taskprompter.py:241-245) is not executed.
-Forward is eval-mode only (DropPath identity, BatchNorm running statistics); training raises.
+The modules OWN parameters and expose the reference's forward signatures; all arithmetic runs in
+libmtt_sm100.so through `ops`:
+
+  TaskPrompterWrapper.forward(x)      -> {task: [B,n_out,H,W]}      the fused path: one `_Plan` (packed weights +
+                                                                    fixed workspace) replayed as ONE CUDA graph
+  TaskPrompter.forward(x)             -> (task_fea {task: [B,f,4h,4w]}, {})      taskprompter.py:392-422
+  Block.forward(x, task_prompts)      -> (x, (prompt_logits, raw_chan), task_prompts)   :270-279
+  ConvHead / DEConvHead.forward(x)    -> [B,n_out,h,w] / [B,n_out,2h,2w]          :697, :712-715
+
+The sub-module forwards run the SAME kernels eagerly on small private workspaces (NCHW tensors in and out like the
+reference); they exist so that code written against the reference's module boundaries keeps working, the wrapper
+forward is the one to time. Packed weights (split-bf16, BatchNorm folded, tap-major convs) are cached per module,
+device, precision mode and parameter version and shared by every plan / sub-module forward.
+
+Changes to the reference's internal contract: `Block` returns `(prompt_logits [B,H,T,N], raw_chan [B,T,C,nh,nw])`
+in place of the full [B,H,N,N] attention maps (only those parts are ever consumed; the logits are
+None unless `Block.emit_logits` is set, which TaskPrompter does for the blocks that need them), and dead code
+(`chan_x`, taskprompter.py:241-245) is not executed. Forward is eval-mode only (DropPath identity, BatchNorm running
+statistics); training raises.
 """
 import math
 from types import SimpleNamespace
@@ -21,13 +34,86 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from .pack import fold_bn, pack_conv_weight, pack_linear_weight
 
 PARITY, SPEED = 2, 1  # nsplit: 3-MMA split-bf16 (fp32-grade) vs plain bf16
+MAX_PLANS = 4         # cached plans (workspace + CUDA graph) per module, least recently used is dropped
 
 
 # --------------------------------------------------------------------------------------------
-# parameter containers (names = reference state_dict keys)
+# per-module caches: packed weights and eager workspaces
+# --------------------------------------------------------------------------------------------
+def _version(mod):
+    return sum(int(q._version) for q in mod.parameters()) + sum(int(b._version) for b in mod.buffers())
+
+
+def _cached(mod, key, build, versioned=True):
+    """build() once per (module, key, parameter version); lives in the module's __dict__ (not a parameter / buffer)."""
+    store = mod.__dict__.setdefault("_mtt_cache", {})
+    ver = _version(mod) if versioned else 0
+    hit = store.get(key)
+    if hit is None or hit[0] != ver:
+        with _dev_ctx(key[1]):
+            hit = (ver, build())
+        store[key] = hit
+    return hit[1]
+
+
+def _dev_ctx(device):
+    """torch.cuda.device(device) for CUDA devices (the C side works on the CURRENT device: streams, kernel attributes,
+    SM count), a no-op otherwise (CPU emulation in the tests)."""
+    import contextlib
+    device = torch.device(device)
+    return torch.cuda.device(device) if device.type == "cuda" else contextlib.nullcontext()
+
+
+def _f32(t, device):
+    return t.detach().to(device=device, dtype=torch.float32).contiguous()
+
+
+def _check_input(mod, x):
+    if mod.training:
+        raise NotImplementedError("mtt_b200: the fused forward is eval-only; call .eval() (backward kernels: "
+                                  "SURVEY.md section 8f N1)")
+    if not x.is_cuda:
+        raise RuntimeError("mtt_b200 has no CPU path: input must be a CUDA tensor on an sm_100a device")
+    ops._L.check(ops._L.load().mtt_device_check(), "mtt_device_check")
+
+
+class _Streams:
+    """Fork / join of side streams off the current stream (captured into the same CUDA graph)."""
+
+    def __init__(self, dev, n):
+        self.dev, self.n, self.side, self.serial = dev, max(n, 1), None, False
+
+    def fork(self, n):
+        if self.dev.type != "cuda" or self.serial:   # serial: one stream (per-kernel timing)
+            return None, [None] * n
+        if self.side is None:
+            self.side = [torch.cuda.Stream(device=self.dev) for _ in range(self.n)]
+        main = torch.cuda.current_stream()
+        for st in self.side[:n]:
+            st.wait_stream(main)
+        return main, self.side[:n]
+
+    def join(self, main, n):
+        if main is not None:
+            for st in self.side[:n]:
+                main.wait_stream(st)
+
+    def par(self, fns):
+        """Run the callables concurrently, one per side stream."""
+        main, side = self.fork(len(fns))
+        for st, fn in zip(side, fns):
+            if st is None:
+                fn()
+            else:
+                with torch.cuda.stream(st):
+                    fn()
+        self.join(main, len(fns))
+
+
+# --------------------------------------------------------------------------------------------
+# parameter containers (names = reference state_dict keys) with the reference's forward signatures
 # --------------------------------------------------------------------------------------------
 class Mlp(nn.Module):
     """timm.models.layers.Mlp parameters (fc1, fc2)."""
@@ -55,8 +141,89 @@ class Attention(nn.Module):
         self.token_trans1 = nn.Linear(self.pixel_no, dim)
 
 
+def _pack_block(blk, device, ns):
+    """Packed operands of one Block (taskprompter.py:257-268), cached on the module."""
+    def build():
+        f = lambda t: _f32(t, device)
+        w = SimpleNamespace()
+        w.n1w, w.n1b, w.n2w, w.n2b = f(blk.norm1.weight), f(blk.norm1.bias), f(blk.norm2.weight), f(blk.norm2.bias)
+        w.eps = blk.norm1.eps
+        zeros = lambda n: torch.zeros(n, device=device)
+        a = blk.attn
+        w.qkv, w.qkv_b = ops.pack_weight(f(a.qkv.weight), ns), (f(a.qkv.bias) if a.qkv.bias is not None else zeros(3 * a.dim))
+        w.proj, w.proj_b = ops.pack_weight(f(a.proj.weight), ns), f(a.proj.bias)
+        w.tt, w.tt_b = ops.pack_weight(f(a.token_trans.weight), ns), f(a.token_trans.bias)
+        w.tt1, w.tt1_b = ops.pack_weight(f(a.token_trans1.weight), ns), f(a.token_trans1.bias)
+        w.fc1, w.fc1_b = ops.pack_weight(f(blk.mlp.fc1.weight), ns), f(blk.mlp.fc1.bias)
+        w.fc2, w.fc2_b = ops.pack_weight(f(blk.mlp.fc2.weight), ns), f(blk.mlp.fc2.bias)
+        return w
+    return _cached(blk, ("pack", device, ns), build)
+
+
+class _BlockSpace:
+    """Activations of the joint [prompts; patches] stream for one batch size (shared by all blocks of a plan)."""
+
+    def __init__(self, B, T, gh, gw, C, H, hidden, chan_nheads, device, ns, streams=None):
+        self.B, self.T, self.gh, self.gw, self.C, self.H, self.ns, self.dev = B, T, gh, gw, C, H, ns, device
+        self.P = P = gh * gw
+        self.N = N = T + P
+        self.nh = self.nw = int(round(math.sqrt(chan_nheads)))
+        S = lambda r, c, **kw: ops.Split(r, c, device, ns, **kw)
+        z = lambda *s: torch.zeros(*s, device=device, dtype=torch.float32)
+        self.xs = z(B * N, C)
+        self.qkv = S(B * N, 3 * C)
+        self.ao = S(B * N, C)
+        self.logits = z(B, H, T, N)
+        self.cp = z(B * T, P)
+        self.cps = S(B * T, P)
+        self.rc = z(B, T, C, self.nh, self.nw)
+        # workspaces of the two LayerNorm-fronted operators; LN1's output is read back by the channel-prompt path
+        self.ws_qkv = ops.workspace(ops.workspace_bytes(ops._L.OP_LN_QKV, rows=B * N, Cdim=C, nsplit=ns), device)
+        self.ws_mlp = ops.workspace(ops.workspace_bytes(ops._L.OP_LN_MLP_RESIDUAL, rows=B * N, Cdim=C, hidden=hidden,
+                                                        nsplit=ns), device)
+        self.xn = ops.ws_split_view(self.ws_qkv, 0, B * N, C, ns)
+        self.streams = streams if streams is not None else _Streams(device, max(T, 1))
+
+
+def _launch_block(sp, w, want_logits):
+    """One Block on the joint stream sp.xs (taskprompter.py:270-279, Attention :195-254)."""
+    B, N, T = sp.B, sp.N, sp.T
+    ops.ln_qkv(sp.xs, w.n1w, w.n1b, w.eps, w.qkv, w.qkv_b, sp.qkv, sp.ws_qkv)                 # :272, :199, :201
+    # the channel-prompt path (token_trans -> raw channel logits -> token_trans1) needs only LN1's output and the
+    # prompt rows of xs: it runs on a side stream next to the attention kernel and joins before proj
+    main, side = sp.streams.fork(1)
+    if side[0] is None:
+        _launch_chan_path(sp, w, want_logits)
+    else:
+        with torch.cuda.stream(side[0]):
+            _launch_chan_path(sp, w, want_logits)
+    ops.attention(sp.qkv, sp.ao, B=B, N=N, H=sp.H, scale=64 ** -0.5,
+                  prompt_logits=sp.logits if want_logits else None, T=T)                      # :204-210
+    sp.streams.join(main, 1)
+    ops.proj_residual(sp.ao, w.proj, w.proj_b, sp.xs)                                          # :212, :273, :276
+    ops.ln_mlp_residual(sp.xs, w.n2w, w.n2b, w.eps, w.fc1, w.fc1_b, w.fc2, w.fc2_b, sp.ws_mlp)  # :274, :277
+
+
+def _launch_chan_path(sp, w, want_logits):
+    B, N, T, C = sp.B, sp.N, sp.T, sp.C
+    bstep = max(1, 128 // T)      # images per launch: their T prompt rows form one gathered 128-row A tile
+    for b0 in range(0, B, bstep):
+        nb = min(bstep, B - b0)
+        ops.gemm(sp.xn, w.tt, M=nb * T, bias=w.tt_b, a_gather=(T, N), a_row_offset=b0 * N,
+                 out_f32=sp.cp, out_split=sp.cps, regroup=(nb * T, nb * T, b0 * T))           # :219 token_trans
+    if want_logits:
+        ops.chan_logits(sp.cp, sp.xn, sp.rc, B=B, N=N, T=T, Cdim=C, gh=sp.gh, gw=sp.gw,
+                        nh=sp.nh, nw=sp.nw)                                                   # :236-246
+    for b0 in range(0, B, bstep):
+        nb = min(bstep, B - b0)
+        ops.gemm(sp.cps, w.tt1, M=nb * T, bias=w.tt1_b, a_row_offset=b0 * T, residual=sp.xs,
+                 out_f32=sp.xs, regroup=(T, N, b0 * N))                                       # :250 token_trans1
+
+
 class Block(nn.Module):
-    """taskprompter.py:257-268."""
+    """taskprompter.py:257-279. forward(x [B,P,C], task_prompts [B,T,C]) -> (x, attn_weight, task_prompts) with
+    attn_weight = (prompt_logits [B,H,T,N] | None, raw_chan [B,T,C,nh,nw] | None): the parts of the reference's
+    attention maps that cal_task_feature consumes, produced when `emit_logits` is set."""
 
     def __init__(self, chan_nheads, resolution, dim, num_heads, mlp_ratio=4., qkv_bias=False):
         super().__init__()
@@ -64,6 +231,28 @@ class Block(nn.Module):
         self.attn = Attention(chan_nheads, resolution, dim, num_heads=num_heads, qkv_bias=qkv_bias)
         self.norm2 = nn.LayerNorm(dim, eps=1e-6)
         self.mlp = Mlp(dim, int(dim * mlp_ratio))
+        self.nsplit = PARITY
+        self.emit_logits = True
+
+    def forward(self, x, task_prompts):
+        _check_input(self, x)
+        B, P, C = x.shape
+        T = task_prompts.shape[1]
+        a = self.attn
+        if P != a.pixel_no or C != a.dim or C // a.num_heads != 64:
+            raise ValueError(f"Block: expected x [B,{a.pixel_no},{a.dim}] with head dim 64, got {tuple(x.shape)}")
+        dev, ns = x.device, self.nsplit
+        with _dev_ctx(dev):
+            w = _pack_block(self, dev, ns)
+            sp = _cached(self, ("space", dev, ns, B, T), lambda: _BlockSpace(
+                B, T, a.resolution[0], a.resolution[1], C, a.num_heads, self.mlp.fc1.out_features, a.chan_nheads, dev,
+                ns), versioned=False)
+            xs = sp.xs.view(B, sp.N, C)
+            xs[:, :T].copy_(task_prompts)                                                     # :199 prompts first
+            xs[:, T:].copy_(x)
+            _launch_block(sp, w, self.emit_logits)
+            attn_weight = (sp.logits.clone(), sp.rc.clone()) if self.emit_logits else (None, None)
+            return xs[:, T:].clone(), attn_weight, xs[:, :T].clone()
 
 
 class PatchEmbed(nn.Module):
@@ -84,8 +273,8 @@ def _trunc_normal_(t, mean=0., std=1., a=-2., b=2.):
 
 
 class TaskPrompter(nn.Module):
-    """taskprompter.py:281-368 (same constructor arguments; `p` needs TASKS.NAMES, prompt_len,
-    chan_nheads, use_ctr, embed_dim, final_embed_dim)."""
+    """taskprompter.py:281-422 (same constructor arguments; `p` needs TASKS.NAMES, prompt_len, chan_nheads, use_ctr,
+    embed_dim, final_embed_dim). forward(x [B,3,H,W]) -> (task_fea {task: [B,f,4h,4w]}, info {})."""
 
     def __init__(self, p, select_list, img_size=(224, 224), patch_size=16, in_chans=3, embed_dim=768, depth=12,
                  num_heads=12, chan_nheads=1, mlp_ratio=4., qkv_bias=True, drop_rate=0., attn_drop_rate=0.,
@@ -139,6 +328,8 @@ class TaskPrompter(nn.Module):
                                                               nn.Conv2d(prompt_dim, 1, 1))
                 self.fea_decode_spa[-1][t] = nn.Sequential(nn.Conv2d(embed_dim, e, 1))
                 self.fea_decode_chan[-1][t] = nn.Sequential(nn.Conv2d(embed_dim, e, 1))
+        self.nsplit = PARITY
+        self.use_graph = False
         self._init_weights()
 
     def _init_weights(self):
@@ -155,11 +346,107 @@ class TaskPrompter(nn.Module):
                 nn.init.ones_(m.weight)
 
     def forward(self, x):
-        raise RuntimeError("TaskPrompter runs fused inside TaskPrompterWrapper.forward "
-                           "(the head convolutions consume its workspace); call the wrapper")
+        """taskprompter.py:392-422: {task: [B, final_embed_dim, 4h, 4w]} (summed over the 4 levels, bilinear x4) and the
+        (empty) info dict. Outputs are fresh tensors."""
+        _check_input(self, x)
+        pl = _plan_for(self, (x.shape[0], x.device, self.nsplit, "backbone"), lambda: _Plan(
+            self, None, list(self.p.TASKS.NAMES), None, x.shape[0], x.device, self.nsplit, mode="backbone"))
+        out = pl.run(x, graph=self.use_graph)
+        return {t: v.clone() for t, v in out.items()}, {}
 
 
-class ConvHead(nn.Module):
+def _plan_for(mod, key, build):
+    """LRU cache of plans on `mod` (a plan = workspace + CUDA graph for one batch size; weights are shared)."""
+    plans = mod.__dict__.setdefault("_mtt_plans", {})
+    pl = plans.pop(key, None)
+    if pl is None:
+        pl = build()
+    plans[key] = pl                      # most recently used last
+    while len(plans) > MAX_PLANS:
+        plans.pop(next(iter(plans)))
+    return pl
+
+
+def _pack_head(hd, device, ns):
+    """ConvHead (taskprompter.py:688-698) / DEConvHead (:700-715) operands, BatchNorm folded."""
+    def build():
+        f = lambda t: _f32(t, device)
+        hw = SimpleNamespace()
+        hw.deconv = isinstance(hd.mt_proj[0], nn.ConvTranspose2d)
+        if hw.deconv:
+            # ConvTranspose2d(k2, s2, p0): out[2y+dy, 2x+dx] = W[:, :, dy, dx]^T . in[y, x] -- four dense GEMMs, one per
+            # output phase (dy, dx), each scattering its rows into the 2x map (mtt_gemm out_row_stride); eval
+            # BatchNorm folds into every phase alike
+            wt = f(hd.mt_proj[0].weight)                                              # [Cin, Cout, 2, 2]
+            hw.mid = wt.shape[1]
+            hw.dc = []
+            for dy in range(2):
+                for dx in range(2):
+                    wp, bp = ops.pack_conv_weight(wt[:, :, dy, dx].contiguous().reshape(wt.shape[0], hw.mid, 1, 1),
+                                                  hd.mt_proj[0].bias, hd.mt_proj[1], ns, transposed=True)
+                    hw.dc.append((dy, dx, wp, bp))
+            hw.mt, hw.mt_b = ops.pack_conv_weight(f(hd.mt_proj[3].weight), hd.mt_proj[3].bias, hd.mt_proj[4], ns)
+        else:
+            hw.mid = hd.mt_proj[0].weight.shape[0]
+            hw.mt, hw.mt_b = ops.pack_conv_weight(f(hd.mt_proj[0].weight), hd.mt_proj[0].bias, hd.mt_proj[1], ns)
+        hw.cin = hd.mt_proj[0].weight.shape[0] if hw.deconv else hd.mt_proj[0].weight.shape[1]
+        hw.lp, hw.lp_b = ops.pack_weight(f(hd.linear_pred.weight).reshape(hd.linear_pred.weight.shape[0], -1), ns), \
+            f(hd.linear_pred.bias)
+        hw.n_out = hd.linear_pred.weight.shape[0]
+        return hw
+    return _cached(hd, ("pack", device, ns), build)
+
+
+class _HeadSpace:
+    """Input / hidden / prediction maps of one head for B images of h x w (NHWC)."""
+
+    def __init__(self, hw, B, h, w, device, ns):
+        S = lambda r, c, **kw: ops.Split(r, c, device, ns, **kw)
+        k = 2 if hw.deconv else 1
+        self.B, self.h, self.w, self.ph, self.pw = B, h, w, k * h, k * w
+        rows = B * self.ph * self.pw
+        self.up = S(B * h * w, hw.cin, zero=True)
+        self.hdc = S(rows, hw.mid, zero=True) if hw.deconv else None
+        self.hmid = S(rows, hw.mid, zero=True)
+        self.pred = torch.zeros(rows, ops.round_up(hw.n_out, 4), device=device, dtype=torch.float32)
+
+
+def _launch_head(hs, hw):
+    """hs.up (NHWC split head input) -> hs.pred (NHWC fp32 logits at the head's resolution)."""
+    B = hs.B
+    if hw.deconv:                                                                             # DEConvHead :700-715
+        for dy, dx, wp, bp in hw.dc:                                                          # mt_proj[0..2]
+            ops.gemm(hs.up, wp, N=hw.mid, K=hw.cin, bias=bp, act=ops.ACT_GELU, out_split=hs.hdc,
+                     regroup=(hs.w, 4 * hs.w, 2 * hs.w * dy + dx, 2))
+        ops.conv3x3_bn_act(hs.hdc, hw.mt, hw.mt_b, hw.mid, hw.mid, ops.ACT_GELU, B=B, H=hs.ph, W=hs.pw, mid=hs.hmid,
+                           w_head=hw.lp, b_head=hw.lp_b, n_out=hw.n_out, out_f32=hs.pred)     # mt_proj[3..5], linear_pred
+    else:                                                                                     # ConvHead :688-698
+        ops.conv3x3_bn_act(hs.up, hw.mt, hw.mt_b, hw.cin, hw.mid, ops.ACT_GELU, B=B, H=hs.ph, W=hs.pw, mid=hs.hmid,
+                           w_head=hw.lp, b_head=hw.lp_b, n_out=hw.n_out, out_f32=hs.pred)
+
+
+class _HeadForward:
+    """forward(x [B,Cin,h,w] NCHW fp32) -> [B,n_out,h',w'] NCHW, like the reference heads."""
+
+    nsplit = PARITY
+
+    def forward(self, x):
+        _check_input(self, x)
+        B, Cin, h, w = x.shape
+        dev, ns = x.device, self.nsplit
+        with _dev_ctx(dev):
+            hw = _pack_head(self, dev, ns)
+            if Cin != hw.cin:
+                raise ValueError(f"{type(self).__name__}: expected {hw.cin} input channels, got {Cin}")
+            hs = _cached(self, ("space", dev, ns, B, h, w), lambda: _HeadSpace(hw, B, h, w, dev, ns), versioned=False)
+            ops.nchw_to_nhwc_split(x.contiguous(), hs.up)
+            _launch_head(hs, hw)
+            out = torch.empty(B, hw.n_out, hs.ph, hs.pw, device=dev, dtype=torch.float32)
+            ops.nhwc_to_nchw(hs.pred, hs.pred.stride(0), B, hw.n_out, hs.ph, hs.pw, out)
+            return out
+
+
+class ConvHead(_HeadForward, nn.Module):
     """taskprompter.py:688-698."""
 
     def __init__(self, in_channels, num_classes):
@@ -169,11 +456,8 @@ class ConvHead(nn.Module):
         _trunc_normal_(self.mt_proj[0].weight, std=0.02)
         self.linear_pred = nn.Conv2d(in_channels, num_classes, kernel_size=1)
 
-    def forward(self, x):
-        raise RuntimeError("ConvHead runs fused inside TaskPrompterWrapper.forward")
 
-
-class DEConvHead(nn.Module):
+class DEConvHead(_HeadForward, nn.Module):
     """taskprompter.py:700-715 (`head: deconv`, utils/common_config.py:68-70): ConvTranspose2d(k2,s2) + BN + GELU,
     3x3 conv + BN + GELU, 1x1 conv -- predicts at twice the resolution of its input."""
 
@@ -188,13 +472,11 @@ class DEConvHead(nn.Module):
         _trunc_normal_(self.mt_proj[3].weight, std=0.02)
         _trunc_normal_(self.linear_pred.weight, std=0.02)
 
-    def forward(self, x):
-        raise RuntimeError("DEConvHead runs fused inside TaskPrompterWrapper.forward")
-
 
 class TaskPrompterWrapper(nn.Module):
-    """models/taskprompter_wrapper.py:9-40: backbone -> per-task head -> bilinear resize to the input
-    size (or p.dd_label_map_size). forward(x[B,3,H,W]) -> {task: [B,n_out,H,W]} fp32."""
+    """models/taskprompter_wrapper.py:9-40: backbone -> per-task head -> bilinear resize to the input size (or
+    p.dd_label_map_size; the '3ddet' task is NOT resized, :34-38). forward(x [B,3,H,W]) -> {task: [B,n_out,H,W]}
+    fp32, written into the plan's static buffers (clone to keep results across calls)."""
 
     def __init__(self, p, backbone, heads, nsplit=PARITY, use_graph=True):
         super().__init__()
@@ -205,57 +487,95 @@ class TaskPrompterWrapper(nn.Module):
         self.target_size = tuple(p.dd_label_map_size) if "dd_label_map_size" in keys else None
         self.nsplit = nsplit
         self.use_graph = use_graph
-        self._plans = {}
-
-    # -- plan cache ---------------------------------------------------------------------------
-    def _param_version(self):
-        return sum(int(q._version) for q in self.parameters()) + sum(int(b._version) for b in self.buffers())
+        for t in self.tasks:
+            if not isinstance(heads[t], (ConvHead, DEConvHead)):
+                raise NotImplementedError(f"mtt_b200: unsupported head {type(heads[t]).__name__} for task {t!r} (the "
+                                          "FCOS3D detection head of the reference needs mmdet3d: SURVEY.md 8f N4)")
 
     def plan(self, batch, device, postproc=False):
-        key = (int(batch), str(device), int(self.nsplit), bool(postproc))
-        ver = self._param_version()
-        pl = self._plans.get(key)
-        if pl is None or pl.version != ver:
-            pl = _Plan(self, batch, device, self.nsplit, postproc=postproc)
-            pl.version = ver
-            self._plans[key] = pl
-        return pl
-
-    def _check(self, x):
-        if self.training:
-            raise NotImplementedError("mtt_b200 TaskPrompter: fused forward is eval-only; backward kernels "
-                                      "are not built yet (SURVEY.md section 8f N1)")
-        if not x.is_cuda:
-            raise RuntimeError("mtt_b200 has no CPU path: input must be a CUDA tensor on an sm_100a device")
+        mode = "postproc" if postproc else "full"
+        return _plan_for(self, (int(batch), torch.device(device), int(self.nsplit), mode), lambda: _Plan(
+            self.backbone, self.heads, self.tasks, self.target_size, batch, torch.device(device), self.nsplit, mode=mode))
 
     def forward(self, x):
-        self._check(x)
-        pl = self.plan(x.shape[0], x.device)
-        return pl.run(x, graph=self.use_graph)
+        _check_input(self, x)
+        return self.plan(x.shape[0], x.device).run(x, graph=self.use_graph)
 
     def predict(self, x):
         """forward + the reference's `get_output` post-processing (TaskPrompter/utils/utils.py:27-63) fused
         into the final resize: {task: int64 [B,H,W] class map | fp32 map} without materialising the
         full-resolution logits (semseg / human_parts argmax, edge 255*sigmoid, sal 255*softmax[1], normals
         (normalize+1)*255/2, depth clamp)."""
-        self._check(x)
-        pl = self.plan(x.shape[0], x.device, postproc=True)
-        return pl.run(x, graph=self.use_graph)
+        _check_input(self, x)
+        return self.plan(x.shape[0], x.device, postproc=True).run(x, graph=self.use_graph)
 
 
 # --------------------------------------------------------------------------------------------
 # the fused forward
 # --------------------------------------------------------------------------------------------
-class _Plan:
-    """Packed weights + workspace + launch sequence for one (batch size, device, nsplit)."""
+def _pack_stem(bb, device, ns):
+    def build():
+        f = lambda t: _f32(t, device)
+        W = SimpleNamespace()
+        W.pe_w = ops.pack_weight(f(bb.patch_embed.proj.weight).reshape(bb.embed_dim, -1), ns)
+        W.pe_b = f(bb.patch_embed.proj.bias)
+        W.pos = f(bb.pos_embed)[0, 1:].contiguous()           # [P, C] (cls slot skipped, :394)
+        W.prompts = f(bb.task_prompts)
+        W.nw, W.nb, W.neps = f(bb.norm.weight), f(bb.norm.bias), bb.norm.eps
+        return W
+    return _cached(bb, ("stem", device, ns), build)
 
-    def __init__(self, wrapper, B, device, nsplit, postproc=False):
-        ops._L.check(ops._L.load().mtt_device_check(), "mtt_device_check")
-        self.postproc = postproc
-        bb = wrapper.backbone
+
+def _pack_levels(bb, tasks, device, ns):
+    """fea_decode_spa / fea_decode_chan / fea_fuse / ctr_attn_conv operands of all 4 levels (:352-366)."""
+    def build():
+        f = lambda t: _f32(t, device)
         p = bb.p
+        e, ff, H = p.embed_dim, p.final_embed_dim, bb.num_heads
+        e_pad = ops.round_up(e, 8)
+        levels = []
+        for il in range(4):
+            lv = SimpleNamespace(tasks=[])
+            for t in tasks:
+                tw = SimpleNamespace()
+                tw.spa = ops.pack_weight(f(bb.fea_decode_spa[il][t][0].weight).reshape(e, -1), ns)
+                tw.spa_b = f(bb.fea_decode_spa[il][t][0].bias)
+                tw.chan = ops.pack_weight(f(bb.fea_decode_chan[il][t][0].weight).reshape(e, -1), ns)
+                tw.chan_b = f(bb.fea_decode_chan[il][t][0].bias)
+                fu = bb.fea_fuse[il][t]
+                w0 = f(fu[0].weight).reshape(ff, 2 * e)
+                w0p = torch.zeros(ff, 2 * e_pad, device=device)   # K laid out like the `cat` buffer
+                w0p[:, :e] = w0[:, :e]
+                w0p[:, e_pad:e_pad + e] = w0[:, e:]
+                tw.f0, tw.f0_b = ops.pack_weight(w0p, ns), f(fu[0].bias)
+                tw.f1, tw.f1_b = ops.pack_conv_weight(f(fu[1].weight), fu[1].bias, fu[2], ns)   # conv3x3 + eval BN
+                tw.f4, tw.f4_b = ops.pack_weight(f(fu[4].weight).reshape(ff, -1), ns), f(fu[4].bias)
+                lv.tasks.append(tw)
+            if p.use_ctr:
+                cc = [bb.ctr_attn_conv[il][t] for t in tasks]
+                lv.c0 = torch.stack([f(c[0].weight).reshape(H, H) for c in cc]).contiguous()
+                lv.c0b = torch.stack([f(c[0].bias) for c in cc]).contiguous()
+                lv.c2 = torch.stack([f(c[2].weight).reshape(H) for c in cc]).contiguous()
+                lv.c2b = torch.stack([f(c[2].bias).reshape(()) for c in cc]).contiguous()
+            levels.append(lv)
+        return levels
+    return _cached(bb, ("levels", device, ns, tuple(tasks)), build)
+
+
+class _Plan:
+    """Workspace + launch sequence (+ CUDA graph) for one (batch size, device, nsplit, mode); the packed weights are
+    the per-module caches above. mode: "full" = wrapper forward (logits at the output size), "postproc" = predict(),
+    "backbone" = TaskPrompter.forward alone (task features, NCHW)."""
+
+    def __init__(self, bb, heads, tasks, target, B, device, nsplit, mode="full"):
+        ops._L.check(ops._L.load().mtt_device_check(), "mtt_device_check")
+        device = torch.device(device)
+        self.mode = mode
+        self.postproc = mode == "postproc"
+        p = bb.p
+        self.bb, self.heads = bb, heads
         self.B, self.dev, self.ns = B, device, nsplit
-        self.tasks = list(wrapper.tasks)
+        self.tasks = list(tasks)
         self.T = T = len(self.tasks)
         self.C = C = bb.embed_dim
         self.H = bb.num_heads
@@ -270,204 +590,76 @@ class _Plan:
         self.e, self.f = p.embed_dim, p.final_embed_dim
         self.e_pad = ops.round_up(self.e, 8)
         self.f_ld = ops.round_up(self.f, 8)
-        self.nh = self.nw = int(round(math.sqrt(bb.chan_nheads)))
         self.use_ctr = bool(p.use_ctr)
-        self.target = wrapper.target_size
+        self.target = target
         self.graph = None
         self.static_in = None
         ns = nsplit
-
-        def f32(t):
-            return t.detach().to(device=device, dtype=torch.float32).contiguous()
-
-        # ---- weights ------------------------------------------------------------------------
-        W = SimpleNamespace()
-        W.pe_w = pack_linear_weight(f32(bb.patch_embed.proj.weight), ns)
-        W.pe_b = f32(bb.patch_embed.proj.bias)
-        W.pos = f32(bb.pos_embed)[0, 1:]                     # [P, C] (cls slot skipped, :394)
-        W.prompts = f32(bb.task_prompts)
-        W.blocks = []
-        for blk in bb.blocks:
-            w = SimpleNamespace()
-            w.n1w, w.n1b, w.n2w, w.n2b = f32(blk.norm1.weight), f32(blk.norm1.bias), f32(blk.norm2.weight), f32(blk.norm2.bias)
-            w.eps = blk.norm1.eps
-            w.qkv, w.qkv_b = pack_linear_weight(f32(blk.attn.qkv.weight), ns), f32(blk.attn.qkv.bias)
-            w.proj, w.proj_b = pack_linear_weight(f32(blk.attn.proj.weight), ns), f32(blk.attn.proj.bias)
-            w.tt, w.tt_b = pack_linear_weight(f32(blk.attn.token_trans.weight), ns), f32(blk.attn.token_trans.bias)
-            w.tt1, w.tt1_b = pack_linear_weight(f32(blk.attn.token_trans1.weight), ns), f32(blk.attn.token_trans1.bias)
-            w.fc1, w.fc1_b = pack_linear_weight(f32(blk.mlp.fc1.weight), ns), f32(blk.mlp.fc1.bias)
-            w.fc2, w.fc2_b = pack_linear_weight(f32(blk.mlp.fc2.weight), ns), f32(blk.mlp.fc2.bias)
-            W.blocks.append(w)
-        W.nw, W.nb, W.neps = f32(bb.norm.weight), f32(bb.norm.bias), bb.norm.eps
-        W.levels = []
-        e, f, e_pad = self.e, self.f, self.e_pad
-        for il in range(4):
-            lv = SimpleNamespace(tasks=[])
-            for t in self.tasks:
-                tw = SimpleNamespace()
-                tw.spa = pack_linear_weight(f32(bb.fea_decode_spa[il][t][0].weight), ns)
-                tw.spa_b = f32(bb.fea_decode_spa[il][t][0].bias)
-                tw.chan = pack_linear_weight(f32(bb.fea_decode_chan[il][t][0].weight), ns)
-                tw.chan_b = f32(bb.fea_decode_chan[il][t][0].bias)
-                ff = bb.fea_fuse[il][t]
-                w0 = f32(ff[0].weight).reshape(f, 2 * e)
-                w0p = torch.zeros(f, 2 * e_pad, device=device)   # K laid out like the `cat` buffer
-                w0p[:, :e] = w0[:, :e]
-                w0p[:, e_pad:e_pad + e] = w0[:, e:]
-                tw.f0, tw.f0_b = pack_linear_weight(w0p, ns), f32(ff[0].bias)
-                w1, b1 = fold_bn(f32(ff[1].weight), f32(ff[1].bias), ff[2])   # conv3x3 + eval BN
-                tw.f1, tw.f1_b = pack_conv_weight(w1, ns), b1.contiguous()
-                tw.f4, tw.f4_b = pack_linear_weight(f32(ff[4].weight), ns), f32(ff[4].bias)
-                lv.tasks.append(tw)
+        e_pad, f = self.e_pad, self.f
+        with _dev_ctx(device):
+            self.streams = _Streams(device, max(T, 1))
+            self._pack()
+            # ---- workspace ------------------------------------------------------------------------------
+            S = lambda r, c, **kw: ops.Split(r, c, device, ns, **kw)
+            z = lambda *s: torch.zeros(*s, device=device, dtype=torch.float32)
+            self.cols = S(B * P, self.patch * self.patch * bb.in_chans)
+            self.sp = _BlockSpace(B, T, self.gh, self.gw, C, self.H, bb.blocks[0].mlp.fc1.out_features, bb.chan_nheads,
+                                  device, ns, streams=self.streams)
+            self.nh, self.nw = self.sp.nh, self.sp.nw
+            self.xs, self.logits, self.rc = self.sp.xs, self.sp.logits, self.sp.rc
+            self.xfin = z(B * N, C)
+            # one set of decoder scratch buffers per task: the T task chains of a level run concurrently on side
+            # streams (each chain's GEMMs are single-wave, 96 tiles on 148 SMs, and latency-bound)
+            gate_ws = ops.workspace_bytes(ops._L.OP_GATED_CONV1X1, rows=B * P, Cdim=C, nsplit=ns)
+            self.ws_gate = [ops.workspace(gate_ws, device) for _ in range(T)]
+            self.cat = [S(B * P, 2 * e_pad, zero=True) for _ in range(T)]
+            self.f1 = [S(B * P, f, zero=True) for _ in range(T)]
+            self.f2 = [S(B * P, f, zero=True) for _ in range(T)]
+            self.acc = z(T, B * P, self.f_ld)
             if self.use_ctr:
-                cc = [bb.ctr_attn_conv[il][t] for t in self.tasks]
-                lv.c0 = torch.stack([f32(c[0].weight).reshape(self.H, self.H) for c in cc]).contiguous()
-                lv.c0b = torch.stack([f32(c[0].bias) for c in cc]).contiguous()
-                lv.c2 = torch.stack([f32(c[2].weight).reshape(self.H) for c in cc]).contiguous()
-                lv.c2b = torch.stack([f32(c[2].bias).reshape(()) for c in cc]).contiguous()
-            W.levels.append(lv)
-        W.heads = []
-        for t in self.tasks:
-            hd = wrapper.heads[t]
-            hw = SimpleNamespace()
-            hw.deconv = isinstance(hd.mt_proj[0], nn.ConvTranspose2d)
-            if hw.deconv:
-                # ConvTranspose2d(k2, s2, p0): out[2y+dy, 2x+dx] = in[y, x] . W[:, :, dy, dx].  On the zero-inserted map
-                # (in[y, x] at (2y, 2x)) that is a 3x3 convolution (pad 1) whose tap (1-dy, 1-dx) holds W[:, :, dy, dx]^T
-                # and whose other five taps are zero -- the same mtt_zero_insert + mtt_gemm(conv) pair InvPT's
-                # scale_embed uses; eval BatchNorm folds into it like into any conv.
-                wt = f32(hd.mt_proj[0].weight)                                   # [Cin, Cout, 2, 2]
-                w3 = torch.zeros(wt.shape[1], wt.shape[0], 3, 3, device=device)
-                for dy in range(2):
-                    for dx in range(2):
-                        w3[:, :, 1 - dy, 1 - dx] = wt[:, :, dy, dx].t()
-                w0, b0 = fold_bn(w3, f32(hd.mt_proj[0].bias), hd.mt_proj[1])
-                hw.dc, hw.dc_b = pack_conv_weight(w0, ns), b0.contiguous()
-                w1, b1 = fold_bn(f32(hd.mt_proj[3].weight), f32(hd.mt_proj[3].bias), hd.mt_proj[4])
-                hw.mid = wt.shape[1]
-            else:
-                w1, b1 = fold_bn(f32(hd.mt_proj[0].weight), f32(hd.mt_proj[0].bias), hd.mt_proj[1])
-                hw.mid = self.f
-            hw.mt, hw.mt_b = pack_conv_weight(w1, ns), b1.contiguous()
-            hw.lp, hw.lp_b = pack_linear_weight(f32(hd.linear_pred.weight), ns), f32(hd.linear_pred.bias)
-            hw.n_out = hd.linear_pred.weight.shape[0]
-            W.heads.append(hw)
-        self.W = W
-
-        # ---- workspace ----------------------------------------------------------------------
-        S = lambda r, c, **kw: ops.Split(r, c, device, ns, **kw)
-        z = lambda *s: torch.zeros(*s, device=device, dtype=torch.float32)
-        self.cols = S(B * P, self.patch * self.patch * bb.in_chans)
-        self.xs = z(B * N, C)
-        self.xn = S(B * N, C)
-        self.qkv = S(B * N, 3 * C)
-        self.ao = S(B * N, C)
-        self.hid = S(B * N, W.blocks[0].fc1.rows)
-        self.logits = z(B, self.H, T, N)
-        self.cp = z(B * T, P)
-        self.cps = S(B * T, P)
-        self.rc = z(B, T, C, self.nh, self.nw)
-        self.xfin = z(B * N, C)
-        # one set of decoder scratch buffers per task: the T task chains of a level run concurrently on
-        # side streams (each chain's GEMMs are single-wave, 96 tiles on 148 SMs, and latency-bound)
-        self.ys = [S(B * P, C) for _ in range(T)]
-        self.yc = [S(B * P, C) for _ in range(T)]
-        self.cat = [S(B * P, 2 * e_pad, zero=True) for _ in range(T)]
-        self.f1 = [S(B * P, f, zero=True) for _ in range(T)]
-        self.f2 = [S(B * P, f, zero=True) for _ in range(T)]
-        self.acc = z(T, B * P, self.f_ld)
-        if self.use_ctr:
-            self.F = z(T, B * P, self.f_ld)
-            self.ctrw = z(B, T, T)
-        gh4, gw4 = 4 * self.gh, 4 * self.gw
-        # head input / hidden / prediction maps; a DEConvHead works at (2*gh4) x (2*gw4)
-        self.up, self.hmid, self.pred, self.upf, self.zi, self.hdc = [], [], [], [], [], []
-        for hw in W.heads:
-            k = 2 if hw.deconv else 1
-            rows = B * (k * gh4) * (k * gw4)
-            self.up.append(None if hw.deconv else S(B * gh4 * gw4, f, zero=True))
-            self.upf.append(z(B * gh4 * gw4, self.f_ld) if hw.deconv else None)
-            self.zi.append(S(rows, f, zero=True) if hw.deconv else None)
-            self.hdc.append(S(rows, hw.mid, zero=True) if hw.deconv else None)
-            self.hmid.append(S(rows, hw.mid, zero=True))
-            self.pred.append(z(rows, ops.round_up(hw.n_out, 4)))
-        self.side = None   # side streams, created lazily on the plan's device
-        oh, ow = self.target if self.target is not None else self.img
-        if not postproc:
-            self.out = {t: z(B, hw.n_out, oh, ow) for t, hw in zip(self.tasks, W.heads)}
-        else:
+                self.F = z(T, B * P, self.f_ld)
+                self.ctrw = z(B, T, T)
+            gh4, gw4 = 4 * self.gh, 4 * self.gw
+            oh, ow = self.target if self.target is not None else self.img
+            self.out_hw = (oh, ow)
             self.out = {}
-            for t in self.tasks:
-                if t not in ops.POSTPROC_KIND:
-                    raise ValueError(f"no get_output post-processing defined for task {t!r}")
-                kind = ops.POSTPROC_KIND[t]
-                shape = {0: (B, oh, ow), 1: (B, oh, ow), 2: (B, oh, ow), 3: (B, oh, ow, 3), 4: (B, oh, ow, 1)}[kind]
-                self.out[t] = torch.zeros(shape, device=device, dtype=torch.int64 if kind == 0 else torch.float32)
-        self.out_hw = (oh, ow)
+            if mode == "backbone":
+                self.hs = None
+                self.out = {t: z(B, f, gh4, gw4) for t in self.tasks}
+                return
+            self.hs = [_HeadSpace(hw, B, gh4, gw4, device, ns) for hw in self.Wh]
+            for t, hw, hs in zip(self.tasks, self.Wh, self.hs):
+                if t == "3ddet":                                   # wrapper :34-38: this task is not resized
+                    if self.postproc:
+                        raise ValueError("no get_output post-processing defined for task '3ddet'")
+                    self.out[t] = z(B, hw.n_out, hs.ph, hs.pw)
+                elif not self.postproc:
+                    self.out[t] = z(B, hw.n_out, oh, ow)
+                else:
+                    if t not in ops.POSTPROC_KIND:
+                        raise ValueError(f"no get_output post-processing defined for task {t!r}")
+                    kind = ops.POSTPROC_KIND[t]
+                    shape = {0: (B, oh, ow), 1: (B, oh, ow), 2: (B, oh, ow), 3: (B, oh, ow, 3), 4: (B, oh, ow, 1)}[kind]
+                    self.out[t] = torch.zeros(shape, device=device, dtype=torch.int64 if kind == 0 else torch.float32)
+
+    def _pack(self):
+        """(Re)resolve the packed weights from the per-module caches (cheap when nothing changed)."""
+        bb, dev, ns = self.bb, self.dev, self.ns
+        self.Ws = _pack_stem(bb, dev, ns)
+        self.Wb = [_pack_block(blk, dev, ns) for blk in bb.blocks]
+        self.Wl = _pack_levels(bb, self.tasks, dev, ns)
+        self.Wh = [_pack_head(self.heads[t], dev, ns) for t in self.tasks] if self.heads is not None else None
+        self.version = _version(bb) + (_version(self.heads) if self.heads is not None else 0)
 
     # -- launch sequence ------------------------------------------------------------------------
-    def _block(self, w, want_logits):
-        B, N, T, C, P = self.B, self.N, self.T, self.C, self.P
-        ops.layernorm(self.xs, w.n1w, w.n1b, w.eps, out_split=self.xn)                       # :272
-        # channel-prompt path (token_trans -> raw channel logits -> token_trans1) only needs LN1's output and
-        # the prompt rows of xs: it runs on a side stream next to qkv + attention and joins before proj
-        main, side = self._fork(1)
-        if side[0] is None:
-            self._chan_path(w, want_logits)
-        else:
-            with torch.cuda.stream(side[0]):
-                self._chan_path(w, want_logits)
-        ops.gemm(self.xn, w.qkv, bias=w.qkv_b, out_split=self.qkv)                           # :201
-        ops.attention(self.qkv, self.ao, B=B, N=N, H=self.H, scale=64 ** -0.5,
-                      prompt_logits=self.logits if want_logits else None, T=T)               # :204-210
-        self._join(main, 1)
-        ops.gemm(self.ao, w.proj, bias=w.proj_b, residual=self.xs, out_f32=self.xs)          # :212,:273,:276
-        ops.layernorm(self.xs, w.n2w, w.n2b, w.eps, out_split=self.xn)                       # :274,:277
-        ops.gemm(self.xn, w.fc1, bias=w.fc1_b, act=ops.ACT_GELU, out_split=self.hid)
-        ops.gemm(self.hid, w.fc2, bias=w.fc2_b, residual=self.xs, out_f32=self.xs)
-
-    def _chan_path(self, w, want_logits):
-        B, N, T, C, P = self.B, self.N, self.T, self.C, self.P
-        bstep = max(1, 128 // T)      # images per launch: their T prompt rows form one gathered 128-row A tile
-        for b0 in range(0, B, bstep):
-            nb = min(bstep, B - b0)
-            ops.gemm(self.xn, w.tt, M=nb * T, bias=w.tt_b, a_gather=(T, N), a_row_offset=b0 * N,
-                     out_f32=self.cp, out_split=self.cps, regroup=(nb * T, nb * T, b0 * T))  # :219 token_trans
-        if want_logits:
-            ops.chan_logits(self.cp, self.xn, self.rc, B=B, N=N, T=T, Cdim=C, gh=self.gh, gw=self.gw,
-                            nh=self.nh, nw=self.nw)                                          # :236-246
-        for b0 in range(0, B, bstep):
-            nb = min(bstep, B - b0)
-            ops.gemm(self.cps, w.tt1, M=nb * T, bias=w.tt1_b, a_row_offset=b0 * T, residual=self.xs,
-                     out_f32=self.xs, regroup=(T, N, b0 * N))                                # :250 token_trans1
-
-    def _fork(self, n=None):
-        """n (default T) side streams forked off the current stream (captured into the same CUDA graph)."""
-        n = self.T if n is None else n
-        if self.dev.type != "cuda" or getattr(self, "serial", False):   # serial: one stream (per-kernel timing)
-            return None, [None] * n
-        if self.side is None:
-            self.side = [torch.cuda.Stream(device=self.dev) for _ in range(max(self.T, 1))]
-        main = torch.cuda.current_stream()
-        for st in self.side[:n]:
-            st.wait_stream(main)
-        return main, self.side[:n]
-
-    def _join(self, main, n=None):
-        if main is not None:
-            for st in self.side[:self.T if n is None else n]:
-                main.wait_stream(st)
-
     def _task_chain(self, il, ti, tw, x_src, first):
         B, N, T, C, P = self.B, self.N, self.T, self.C, self.P
-        ys, yc, cat, f1, f2 = self.ys[ti], self.yc[ti], self.cat[ti], self.f1[ti], self.f2[ti]
-        ops.gate_split(x_src, N, T, self.logits, self.rc, ti, ys, yc, B=B, T=T, N=N, H=self.H,
-                       Cdim=C, gh=self.gh, gw=self.gw, nh=self.nh, nw=self.nw)               # :436-446,:452-467
-        ops.gemm(ys, tw.spa, bias=tw.spa_b, out_split=cat, N=self.e)                         # :447
-        ops.gemm(yc, tw.chan, bias=tw.chan_b, out_split=cat, N=self.e, out_col_offset=self.e_pad)  # :468,:471
+        cat, f1, f2 = self.cat[ti], self.f1[ti], self.f2[ti]
+        ops.gated_conv1x1(x_src, N, T, self.logits, self.rc, ti, tw.spa, tw.spa_b, tw.chan, tw.chan_b, self.e, cat,
+                          self.e_pad, self.ws_gate[ti], B=B, T=T, N=N, H=self.H, Cdim=C, gh=self.gh, gw=self.gw,
+                          nh=self.nh, nw=self.nw)                                            # :436-447, :452-468, :471
         ops.gemm(cat, tw.f0, bias=tw.f0_b, out_split=f1, N=self.f)                           # fea_fuse[0]
-        ops.gemm(f1, tw.f1, N=self.f, K=self.f, bias=tw.f1_b, act=ops.ACT_GELU, out_split=f2,
-                 conv=(B, self.gh, self.gw, 3, 1))                                           # fea_fuse[1..3]
+        ops.conv3x3_bn_act(f1, tw.f1, tw.f1_b, self.f, self.f, ops.ACT_GELU, B=B, H=self.gh, W=self.gw, mid=f2)  # [1..3]
         if self.use_ctr:
             ops.gemm(f2, tw.f4, bias=tw.f4_b, out_f32=self.F[ti][:, :self.f], N=self.f)
         else:
@@ -476,97 +668,91 @@ class _Plan:
 
     def _level(self, il, x_src):
         """cal_task_feature (:424-487) on X = x_src rows [b*N + T + pix]; accumulates into self.acc."""
-        B, N, T, C, P = self.B, self.N, self.T, self.C, self.P
-        lv = self.W.levels[il]
+        B, N, T, P = self.B, self.N, self.T, self.P
+        lv = self.Wl[il]
         first = il == 0
-        main, side = self._fork()
-        for ti, tw in enumerate(lv.tasks):
-            if side[ti] is None:
-                self._task_chain(il, ti, tw, x_src, first)
-            else:
-                with torch.cuda.stream(side[ti]):
-                    self._task_chain(il, ti, tw, x_src, first)
-        self._join(main)
+        self.streams.par([lambda ti=ti, tw=tw: self._task_chain(il, ti, tw, x_src, first)
+                          for ti, tw in enumerate(lv.tasks)])
         if self.use_ctr:
             ops.ctr_weights(self.logits, lv.c0, lv.c0b, lv.c2, lv.c2b, self.ctrw, B=B, H=self.H, T=T, N=N)
             ops.ctr_mix(self.F, self.ctrw, self.acc, T=T, M=B * P, Cdim=self.f_ld, ld=self.f_ld,
                         rows_per_batch=P, accumulate=not first)                              # :481-485,:411
 
-    def _head_chain(self, ti, t, hw):
+    def _head_chain(self, ti, t, hw, hs):
         B = self.B
-        gh4, gw4 = 4 * self.gh, 4 * self.gw
         oh, ow = self.out_hw
-        if hw.deconv:                                                                       # DEConvHead :700-715
-            ops.bilinear(self.acc[ti], self.f_ld, B, self.gh, self.gw, self.f, gh4, gw4,
-                         out_f32=self.upf[ti][:, :self.f])                                   # :420
-            ops.zero_insert(self.upf[ti], self.zi[ti], B=B, h=gh4, w=gw4, Cdim=self.f, src_group=gh4 * gw4,
-                            src_offset=0)
-            ph, pw = 2 * gh4, 2 * gw4
-            ops.gemm(self.zi[ti], hw.dc, N=hw.mid, K=self.f, bias=hw.dc_b, act=ops.ACT_GELU, out_split=self.hdc[ti],
-                     conv=(B, ph, pw, 3, 1))                                                 # mt_proj[0..2]
-            ops.gemm(self.hdc[ti], hw.mt, N=hw.mid, K=hw.mid, bias=hw.mt_b, act=ops.ACT_GELU,
-                     out_split=self.hmid[ti], conv=(B, ph, pw, 3, 1))                        # mt_proj[3..5]
-        else:
-            ph, pw = gh4, gw4
-            ops.bilinear(self.acc[ti], self.f_ld, B, self.gh, self.gw, self.f, gh4, gw4, out_split=self.up[ti])  # :420
-            ops.gemm(self.up[ti], hw.mt, N=self.f, K=self.f, bias=hw.mt_b, act=ops.ACT_GELU, out_split=self.hmid[ti],
-                     conv=(B, gh4, gw4, 3, 1))                                               # ConvHead.mt_proj
-        ops.gemm(self.hmid[ti], hw.lp, bias=hw.lp_b, out_f32=self.pred[ti][:, :hw.n_out], N=hw.n_out)
-        if self.postproc:
-            ops.bilinear_postproc(self.pred[ti], self.pred[ti].stride(0), B, ph, pw, hw.n_out, oh, ow,
+        ops.bilinear(self.acc[ti], self.f_ld, B, self.gh, self.gw, self.f, hs.h, hs.w, out_split=hs.up)      # :420
+        _launch_head(hs, hw)
+        if t == "3ddet":
+            ops.nhwc_to_nchw(hs.pred, hs.pred.stride(0), B, hw.n_out, hs.ph, hs.pw, self.out[t])            # wrapper :38
+        elif self.postproc:
+            ops.bilinear_postproc(hs.pred, hs.pred.stride(0), B, hs.ph, hs.pw, hw.n_out, oh, ow,
                                   ops.POSTPROC_KIND[t], self.out[t])                         # wrapper :35 + utils.py:27-63
         else:
-            ops.bilinear(self.pred[ti], self.pred[ti].stride(0), B, ph, pw, hw.n_out, oh, ow,
-                         out_nchw=self.out[t])                                               # wrapper :35
+            ops.bilinear(hs.pred, hs.pred.stride(0), B, hs.ph, hs.pw, hw.n_out, oh, ow, out_nchw=self.out[t])  # :35
 
     def _launch(self, img):
-        B, N, T, C, P = self.B, self.N, self.T, self.C, self.P
-        W = self.W
+        B, N, T, P = self.B, self.N, self.T, self.P
+        W = self.Ws
         ops.im2col_patch(img, self.patch, self.cols)
         ops.gemm(self.cols, W.pe_w, bias=W.pe_b, residual=W.pos, res_row_mod=P, out_f32=self.xs,
                  regroup=(P, N, T))                                                          # :393-394
         ops.broadcast_rows(W.prompts, self.xs, B, N)                                         # :397
-        for idx, w in enumerate(W.blocks):
+        for idx, w in enumerate(self.Wb):
             sel = (idx + 1) in self.select
-            self._block(w, sel or idx == self.depth - 1)
+            _launch_block(self.sp, w, sel or idx == self.depth - 1)
             if sel:
                 il = sum(1 for s in self.select if idx >= s - 1) - 1                         # :408
                 self._level(il, self.xs)
         ops.layernorm(self.xs, W.nw, W.nb, W.neps, out_f32=self.xfin)                        # :413
         self._level(3, self.xfin)                                                            # :416-417
-        main, side = self._fork()
-        for ti, (t, hw) in enumerate(zip(self.tasks, W.heads)):
-            if side[ti] is None:
-                self._head_chain(ti, t, hw)
-            else:
-                with torch.cuda.stream(side[ti]):
-                    self._head_chain(ti, t, hw)
-        self._join(main)
+        if self.mode == "backbone":
+            gh4, gw4 = 4 * self.gh, 4 * self.gw
+            self.streams.par([lambda ti=ti, t=t: ops.bilinear(self.acc[ti], self.f_ld, B, self.gh, self.gw, self.f, gh4,
+                                                              gw4, out_nchw=self.out[t])
+                              for ti, t in enumerate(self.tasks)])                           # :419-420
+            return
+        self.streams.par([lambda ti=ti, t=t, hw=hw, hs=hs: self._head_chain(ti, t, hw, hs)
+                          for ti, (t, hw, hs) in enumerate(zip(self.tasks, self.Wh, self.hs))])
+
+    @property
+    def serial(self):
+        return self.streams.serial
+
+    @serial.setter
+    def serial(self, v):
+        self.streams.serial = bool(v)
 
     def run(self, x, graph=True):
         if tuple(x.shape[1:]) != (3, *self.img) or x.dtype != torch.float32:
             raise ValueError(f"expected fp32 input [B,3,{self.img[0]},{self.img[1]}], got {tuple(x.shape)} {x.dtype}")
-        if not graph:
-            self._launch(x.contiguous())
+        with _dev_ctx(self.dev):
+            ver = _version(self.bb) + (_version(self.heads) if self.heads is not None else 0)
+            if ver != self.version:          # parameters changed in place: re-pack (same shapes), re-capture
+                self._pack()
+                self.graph = None
+            if not graph:
+                self._launch(x.contiguous())
+                return dict(self.out)
+            if self.static_in is None:
+                self.static_in = torch.empty_like(x, memory_format=torch.contiguous_format)
+            self.static_in.copy_(x, non_blocking=True)
+            if self.graph is None:
+                self._launch(self.static_in)  # warm-up outside capture (sets kernel attributes, loads modules)
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._launch(self.static_in)
+                self.graph = g
+            self.graph.replay()
             return dict(self.out)
-        if self.static_in is None:
-            self.static_in = torch.empty_like(x, memory_format=torch.contiguous_format)
-        self.static_in.copy_(x, non_blocking=True)
-        if self.graph is None:
-            self._launch(self.static_in)  # warm-up outside capture (sets kernel attributes, loads modules)
-            torch.cuda.synchronize()
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                self._launch(self.static_in)
-            self.graph = g
-        self.graph.replay()
-        return dict(self.out)
 
     def launches_per_forward(self):
-        n0 = ops.launch_count()
-        self._launch(self.static_in if self.static_in is not None else
-                     torch.zeros(self.B, 3, *self.img, device=self.dev))
-        return ops.launch_count() - n0
+        with _dev_ctx(self.dev):
+            n0 = ops.launch_count()
+            self._launch(self.static_in if self.static_in is not None else
+                         torch.zeros(self.B, 3, *self.img, device=self.dev))
+            return ops.launch_count() - n0
 
 
 # --------------------------------------------------------------------------------------------
@@ -592,6 +778,8 @@ def build_from_config(cfg, nsplit=PARITY, use_graph=True):
     p = SimpleNamespace(TASKS=SimpleNamespace(NAMES=list(cfg["tasks"]), NUM_OUTPUT=dict(cfg["num_output"])),
                         prompt_len=1, chan_nheads=cfg["chan_nheads"], use_ctr=cfg["use_ctr"],
                         embed_dim=cfg["e"], final_embed_dim=cfg["f"])
+    if "dd_label_map_size" in cfg:
+        p.dd_label_map_size = tuple(cfg["dd_label_map_size"])
     bb = TaskPrompter(p, cfg["select"], img_size=tuple(cfg["img_size"]), patch_size=cfg["patch"],
                       embed_dim=cfg["C"], depth=cfg["depth"], num_heads=cfg["heads"],
                       chan_nheads=cfg["chan_nheads"])
@@ -601,20 +789,27 @@ def build_from_config(cfg, nsplit=PARITY, use_graph=True):
 
 
 def accelerate(ref_model, nsplit=PARITY, use_graph=True):
-    """Drop-in: build the fused wrapper from a REFERENCE TaskPrompterWrapper instance, sharing its
-    parameters (same names, so `load_state_dict(ref.state_dict())` is exact)."""
+    """Drop-in: build the fused wrapper from a REFERENCE TaskPrompterWrapper instance. Parameters and BatchNorm
+    statistics are COPIED (`load_state_dict(ref.state_dict(), strict=True)`: same names, so the copy is exact);
+    later in-place updates of `ref_model` are not seen -- call `load_state_dict` again (plans re-pack by themselves
+    when parameter versions change). Raises for heads this library has no kernels for (FCOS3DHead, task '3ddet' of
+    the reference's Cityscapes-3D config)."""
     bb = ref_model.backbone
     p = bb.p
     mine_bb = TaskPrompter(p, list(bb.select_list), img_size=tuple(bb.patch_embed.img_size),
                            patch_size=bb.patch_embed.patch_size[0], embed_dim=bb.embed_dim,
                            depth=len(bb.blocks), num_heads=bb.blocks[0].attn.num_heads,
                            chan_nheads=bb.blocks[0].attn.chan_nheads)
-    def mirror(hd):      # ConvHead (:688-698) or DEConvHead (:700-715), told apart by the first layer
+
+    def mirror(t, hd):   # ConvHead (:688-698) or DEConvHead (:700-715), told apart by the first layer
+        if not hasattr(hd, "mt_proj") or not hasattr(hd, "linear_pred"):
+            raise NotImplementedError(f"mtt_b200.accelerate: unsupported head {type(hd).__name__} for task {t!r} "
+                                      "(FCOS3DHead / '3ddet' needs mmdet3d: SURVEY.md 8f N4)")
         if isinstance(hd.mt_proj[0], nn.ConvTranspose2d):
             return DEConvHead(hd.mt_proj[0].weight.shape[0], hd.linear_pred.weight.shape[0])
         return ConvHead(hd.linear_pred.weight.shape[1], hd.linear_pred.weight.shape[0])
 
-    heads = nn.ModuleDict({t: mirror(ref_model.heads[t]) for t in ref_model.tasks})
+    heads = nn.ModuleDict({t: mirror(t, ref_model.heads[t]) for t in ref_model.tasks})
     m = TaskPrompterWrapper(p, mine_bb, heads, nsplit=nsplit, use_graph=use_graph)
     m.load_state_dict(ref_model.state_dict(), strict=True)
     return m.eval()

@@ -180,6 +180,88 @@ def make_losses():
             "made_by": "oracle/make_golden.py: reference get_criterion + autograd through the unmodified reference model"}
 
 
+# ---------------------------------------------------------------------------------------------------------
+# Full-size configurations (BASELINE.json configs[1..4]): the reference's outputs are hundreds of MB, so the
+# fixture keeps (i) every output value on a stride-8 pixel lattice whose offset changes per (image, task) --
+# the outputs are bilinear up-samplings of 4x / 8x coarser maps, so the lattice sees every coarse cell --
+# (ii) the exact norms of the full tensors, and (iii) for multi-class tasks the full-resolution arg-max map
+# (uint8) with the mask of pixels whose top-2 margin exceeds 1e-4 * max|logit| (where arg-max must be exact).
+# The input is regenerated from the seed; its SHA-256 is stored.
+BIG_STRIDE = 8
+BIG_JOBS = [  # (family, config, seed, batch)
+    ("taskprompter", "tp_cfg5_d4", 41, 1),   # N = 8195 tokens: 65 query tiles, ragged last key block
+    ("taskprompter", "tp_cfg4", 42, 4),      # the bench configuration: 24 blocks, bs 4
+    ("taskprompter", "tp_cfg2", 43, 4),      # BASELINE.json configs[1]
+    ("invpt", "ip_cfg3", 44, 4),             # BASELINE.json configs[2]
+    ("taskprompter", "tp_cfg5", 45, 1),      # BASELINE.json configs[4]: full 24-block, N = 8195
+]
+
+
+def big_input(cfg, seed, batch):
+    g = torch.Generator().manual_seed(seed + 1000)
+    return torch.randn(batch, 3, *cfg["img_size"], generator=g)
+
+
+def lattice(b, ti, H, W, stride=BIG_STRIDE):
+    """Row / column indices of the sampled pixels of image b, task index ti."""
+    oy, ox = (3 * b + 5 * ti + 1) % stride, (5 * b + 3 * ti + 2) % stride
+    return torch.arange(oy, H, stride), torch.arange(ox, W, stride)
+
+
+def compress_output(y, ti, with_argmax=True):
+    """y [B, n_out, H, W] fp32 -> the fixture record described above (`safe` is bit-packed, numpy.packbits order)."""
+    B, n, H, W = y.shape
+    samp = []
+    for b in range(B):
+        iy, ix = lattice(b, ti, H, W)
+        samp.append(y[b][:, iy][:, :, ix].clone())
+    rec = {"shape": tuple(y.shape), "samples": torch.stack(samp), "norm": float(y.double().norm()),
+           "absmax": float(y.abs().max())}
+    if n > 1 and with_argmax:
+        import numpy as np
+        top2 = y.topk(2, dim=1).values
+        rec["argmax"] = y.argmax(1).to(torch.uint8)
+        safe = (top2[:, 0] - top2[:, 1]) > 1e-4 * y.abs().max()
+        rec["safe_bits"] = torch.from_numpy(np.packbits(safe.numpy().reshape(-1)))
+    return rec
+
+
+def make_big(family, name, seed, batch):
+    if family == "taskprompter":
+        from oracle import taskprompter_ref as R
+        cfg = configs.taskprompter(name)
+        model = ref_loader.build_taskprompter(cfg).eval()
+    else:
+        from oracle import invpt_ref as R
+        cfg = configs.invpt(name)
+        model = ref_loader.build_invpt(cfg).eval()
+    sd = R.init_state_dict(cfg, seed=seed)
+    model.load_state_dict(sd, strict=True)
+    x = big_input(cfg, seed, batch)
+    with torch.no_grad():
+        y = model(x)
+    out = {t: compress_output(y[t], ti) for ti, t in enumerate(cfg["tasks"])}
+    inter = None
+    if family == "invpt":
+        inter = {t: compress_output(y["inter_preds"][t], ti, with_argmax=False) for ti, t in enumerate(cfg["tasks"])}
+    return {"family": family, "cfg": name, "seed": seed, "batch": batch, "stride": BIG_STRIDE, "out": out,
+            "inter_preds": inter, "x_sha256": hashlib.sha256(x.numpy().tobytes()).hexdigest(),
+            "sd_sha256": sd_checksum(sd), "torch": torch.__version__,
+            "made_by": "oracle/make_golden.py make_big: unmodified reference forward (eval, fp32, CPU), lattice-sampled"}
+
+
+def main_big(only=None):
+    import time
+    for fam, name, seed, batch in BIG_JOBS:
+        if only and name not in only:
+            continue
+        t0 = time.time()
+        fx = make_big(fam, name, seed, batch)
+        path = os.path.join(GOLD, f"big_{name}_b{batch}.pt")
+        torch.save(fx, path)
+        print(f"wrote {path} ({os.path.getsize(path) / 1024:.0f} KiB, {time.time() - t0:.0f} s)", flush=True)
+
+
 def main():
     if not ref_loader.available():
         raise SystemExit("reference not found (set MTT_REFERENCE or mount /root/reference)")
@@ -210,4 +292,9 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "big":      # python -m oracle.make_golden big [config ...]
+        if not ref_loader.available():
+            raise SystemExit("reference not found (set MTT_REFERENCE or mount /root/reference)")
+        main_big(set(sys.argv[2:]) or None)
+    else:
+        main()

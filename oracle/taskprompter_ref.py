@@ -203,7 +203,9 @@ def forward(sd, cfg, img, taps=None):
         if taps is not None:
             taps[f"task_fea.{t}"] = feats[t]
         head = deconv_head if cfg.get("head", "conv") == "deconv" else conv_head      # utils/common_config.py:64-70
-        out[t] = F.interpolate(head(sd, t, feats[t]), img.shape[-2:], mode="bilinear")
+        y = head(sd, t, feats[t])
+        # wrapper :34-38: every task is resized to the input size (or dd_label_map_size) EXCEPT '3ddet'
+        out[t] = y if t == "3ddet" else F.interpolate(y, tuple(cfg.get("dd_label_map_size", img.shape[-2:])), mode="bilinear")
     return out
 
 

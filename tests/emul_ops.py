@@ -31,7 +31,8 @@ def _rsplit(sp, cols=None):
 def _map(r, m, base=0):
     if m is None or m[0] == 0:
         return r + base
-    return (r // m[0]) * m[1] + m[2] + r % m[0] + base
+    stride = m[3] if len(m) > 3 else 1
+    return (r // m[0]) * m[1] + m[2] + (r % m[0]) * stride + base
 
 
 def install(mp):
@@ -56,7 +57,8 @@ def install(mp):
             _wsplit(out_split, y)
 
     def gemm(a, w, *, M=None, N=None, K=None, bias=None, act=0, residual=None, res_row_mod=0, out_f32=None,
-             out_split=None, out_col_offset=0, regroup=None, conv=None, a_row_offset=0, a_gather=None):
+             out_split=None, out_col_offset=0, regroup=None, conv=None, a_row_offset=0, a_gather=None,
+             w_col_offset=0):
         M = a.rows if M is None else M
         N = w.rows if N is None else N
         K = a.cols if K is None else K
@@ -66,7 +68,7 @@ def install(mp):
         else:
             A = _rsplit(a, K)[a_row_offset:a_row_offset + M]
         if conv is None:
-            Wm = _rsplit(w, K)[:N]
+            Wm = _rsplit(w, w_col_offset + K)[:N, w_col_offset:]
             y = A @ Wm.t()
         else:
             B, H, Wd, ks, dil = conv
@@ -250,6 +252,82 @@ def install(mp):
             score_out.copy_(score)
         o = (score.softmax(-1) @ V).transpose(1, 2).reshape(B * Lq, Cdim)
         _wsplit(out, o)
+
+    # ---- the named operators of block_ops.cu, written like their C bodies: the same primitive sequence over the
+    # ---- same workspace layout (so a wrong workspace offset or size fails here)
+    def _al256(n):
+        return (n + 255) // 256 * 256
+
+    def workspace_bytes(op, rows=0, Cdim=0, hidden=0, nsplit=2, B=0, N=0, H=0, T=0):
+        pl = lambda r, c: _al256(nsplit * r * ops.round_up(c, 8) * 2)
+        return {ops._L.OP_LN_QKV: pl(rows, Cdim), ops._L.OP_LN_MLP_RESIDUAL: pl(rows, Cdim) + pl(rows, hidden),
+                ops._L.OP_GATED_CONV1X1: 2 * pl(rows, Cdim), ops._L.OP_CONV3X3_BN_ACT: pl(rows, hidden)}.get(op, 0)
+
+    def ln_qkv(x, gamma, beta, eps, wqkv, bias, qkv, ws):
+        rows, Cd = x.shape
+        xn = ops.ws_split_view(ws, 0, rows, Cd, qkv.nsplit)
+        ops.layernorm(x, gamma, beta, eps, out_split=xn)
+        ops.gemm(xn, wqkv, N=3 * Cd, K=Cd, bias=bias, out_split=qkv)
+
+    def proj_residual(ao, wproj, bias, x):
+        ops.gemm(ao, wproj, N=x.shape[1], K=x.shape[1], bias=bias, residual=x, out_f32=x)
+
+    def ln_mlp_residual(x, gamma, beta, eps, w1, b1, w2, b2, ws):
+        rows, Cd = x.shape
+        ns = w1.nsplit
+        xn = ops.ws_split_view(ws, 0, rows, Cd, ns)
+        hid = ops.ws_split_view(ws, _al256(ns * rows * ops.round_up(Cd, 8) * 2), rows, w1.rows, ns)
+        ops.layernorm(x, gamma, beta, eps, out_split=xn)
+        ops.gemm(xn, w1, K=Cd, bias=b1, act=1, out_split=hid)
+        ops.gemm(hid, w2, N=Cd, K=w1.rows, bias=b2, residual=x, out_f32=x)
+
+    def gated_conv1x1(x, x_group_rows, x_row_offset, prompt_logits, chan_lg, task, w_spa, b_spa, w_chan, b_chan, e, cat,
+                      chan_col, ws, *, B, T, N, H, Cdim, gh, gw, nh, nw):
+        rows, ns = B * gh * gw, cat.nsplit
+        ys = ops.ws_split_view(ws, 0, rows, Cdim, ns)
+        yc = ops.ws_split_view(ws, _al256(ns * rows * ops.round_up(Cdim, 8) * 2), rows, Cdim, ns)
+        ops.gate_split(x, x_group_rows, x_row_offset, prompt_logits, chan_lg, task, ys, yc, B=B, T=T, N=N, H=H, Cdim=Cdim,
+                       gh=gh, gw=gw, nh=nh, nw=nw)
+        ops.gemm(ys, w_spa, N=e, K=Cdim, bias=b_spa, out_split=cat)
+        ops.gemm(yc, w_chan, N=e, K=Cdim, bias=b_chan, out_split=cat, out_col_offset=chan_col)
+
+    def conv3x3_bn_act(a, w3, b3, Cin, Cout, act, *, B, H, W, dil=1, mid=None, w_head=None, b_head=None, n_out=0,
+                       out_f32=None, ws=None):
+        if mid is None:
+            mid = ops.ws_split_view(ws, 0, B * H * W, Cout, a.nsplit)
+        ops.gemm(a, w3, N=Cout, K=Cin, bias=b3, act=act, out_split=mid, conv=(B, H, W, 3, dil))
+        if w_head is not None:
+            ops.gemm(mid, w_head, N=n_out, K=Cout, bias=b_head, out_f32=out_f32)
+
+    def pack_weight(w, nsplit):
+        out = ops.split_f32(w.contiguous(), nsplit, cols_pad=ops.round_up(w.shape[1], 8))
+        out.cols = w.shape[1]
+        return out
+
+    def pack_conv_weight(w, bias, bn, nsplit, transposed=False):
+        w = w.detach().float()
+        if transposed:                                   # ConvTranspose2d [Cin, N, k, k] -> flipped forward kernel
+            w = w.flip(2, 3).permute(1, 0, 2, 3)
+        N, Cin, k, _ = w.shape
+        b0 = bias.detach().float() if bias is not None else torch.zeros(N)
+        if bn is not None:
+            sc = bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + bn.eps)
+            w = w * sc.reshape(-1, 1, 1, 1)
+            b0 = (b0 - bn.running_mean.detach().float()) * sc + bn.bias.detach().float()
+        cin_pad = ops.round_up(Cin, 64)
+        wt = torch.zeros(N, k * k, cin_pad)
+        wt[:, :, :Cin] = w.permute(0, 2, 3, 1).reshape(N, k * k, Cin)
+        return ops.split_f32(wt.reshape(N, k * k * cin_pad), nsplit), b0.contiguous()
+
+    def nchw_to_nhwc_split(x, out):
+        B, Cd, H, W = x.shape
+        _wsplit(out, x.permute(0, 2, 3, 1).reshape(B * H * W, Cd))
+
+    def nhwc_to_nchw(x, ld_in, B, Cd, H, W, out):
+        out.copy_(x[:B * H * W, :Cd].reshape(B, H, W, Cd).permute(0, 3, 1, 2))
+
+    def workspace(nbytes, device):
+        return torch.zeros(max(int(nbytes), 256), dtype=torch.uint8, device=device)
 
     for name, fn in list(locals().items()):
         if callable(fn) and hasattr(ops, name) and name not in ("mp",):

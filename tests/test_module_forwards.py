@@ -1,0 +1,97 @@
+"""The reference's sub-module forward signatures on the fused kernels, against the oracle's taps:
+
+  Block.forward(x, task_prompts) -> (x, (prompt_logits, raw_chan), task_prompts)     TP taskprompter.py:270-279
+  TaskPrompter.forward(x)        -> (task_fea, {})                                   :392-422
+  ConvHead / DEConvHead.forward  -> logits at the head's resolution                  :697, :712-715
+
+Each case runs twice: on CPU with the kernels replaced by tests/emul_ops.py (host logic: packing, joint-stream
+layout, workspaces) and, marked gpu, through the C ABI on the device.
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import configs
+from oracle import taskprompter_ref as TPR
+
+
+def _model(name, seed=3):
+    import mtt_b200  # noqa: F401
+    from mtt_b200 import taskprompter as TP
+
+    cfg = configs.taskprompter(name)
+    sd = TPR.init_state_dict(cfg, seed=seed)
+    m = TP.build_from_config(cfg, nsplit=2, use_graph=False).eval()
+    m.load_state_dict(sd, strict=True)
+    return TP, cfg, sd, m
+
+
+def _rel(a, b):
+    return ((a.double().cpu() - b.double().cpu()).norm() / b.double().cpu().norm()).item()
+
+
+def _run_cases(dev, tol):
+    out = {}
+    for name in ("tp_tiny", "tp_tiny_de"):
+        TP, cfg, sd, m = _model(name)
+        m = m.to(dev)
+        g = torch.Generator().manual_seed(17)
+        x = torch.randn(2, 3, *cfg["img_size"], generator=g)
+        taps = {}
+        with torch.no_grad():
+            ref = TPR.forward(sd, cfg, x, taps=taps)
+            # ---- TaskPrompter.forward
+            fea, info = m.backbone(x.to(dev))
+            assert info == {}
+            for t in cfg["tasks"]:
+                assert fea[t].shape == taps[f"task_fea.{t}"].shape
+                assert _rel(fea[t], taps[f"task_fea.{t}"]) < tol, (name, "task_fea", t)
+            # ---- heads on the oracle's task features
+            for t in cfg["tasks"]:
+                hd = TPR.deconv_head if cfg["head"] == "deconv" else TPR.conv_head
+                want = hd(sd, t, taps[f"task_fea.{t}"])
+                got = m.heads[t](taps[f"task_fea.{t}"].to(dev))
+                assert got.shape == want.shape
+                assert _rel(got, want) < tol, (name, "head", t)
+            # ---- Block.forward: block 1 on the oracle's block-0 outputs
+            xb, pb = taps["block0.x"].to(dev), taps["block0.prompts"].to(dev)
+            x1, (lg, rc), p1 = m.backbone.blocks[1](xb, pb)
+            rx, rp, rl, rrc = TPR.block_forward(sd, "backbone.blocks.1.", cfg, taps["block0.x"], taps["block0.prompts"], True)
+            assert _rel(x1, rx) < tol and _rel(p1, rp) < tol, (name, "block")
+            assert _rel(lg, rl) < tol and _rel(rc, rrc) < tol, (name, "block logits")
+            m.backbone.blocks[1].emit_logits = False
+            _, (lg2, rc2), _ = m.backbone.blocks[1](xb, pb)
+            assert lg2 is None and rc2 is None
+        out[name] = True
+    return out
+
+
+def test_module_forwards_emulated(monkeypatch):
+    import mtt_b200  # noqa: F401
+    from mtt_b200 import taskprompter as TP
+    import emul_ops
+
+    emul_ops.install(monkeypatch)
+    monkeypatch.setattr(TP, "_check_input", lambda mod, x: None)
+    _run_cases(torch.device("cpu"), 2e-4)
+
+
+@pytest.mark.gpu
+def test_module_forwards_gpu(cuda_dev):
+    _run_cases(cuda_dev, 2e-4)
+
+
+@pytest.mark.gpu
+def test_weights_are_shared_between_plans_and_repacked_on_update(cuda_dev):
+    """One packed copy per (module, device, mode) serves every plan; an in-place parameter update re-packs it."""
+    TP, cfg, sd, m = _model("tp_tiny1", seed=4)
+    m = m.to(cuda_dev)
+    x = torch.randn(2, 3, *cfg["img_size"], device=cuda_dev)
+    with torch.no_grad():
+        a = {k: v.clone() for k, v in m(x).items()}
+        pl2, pl1 = m.plan(2, cuda_dev), m.plan(1, cuda_dev)
+        assert pl2.Wb[0] is pl1.Wb[0] and pl2.Wh[0] is pl1.Wh[0]
+        m.heads[cfg["tasks"][0]].linear_pred.bias.add_(1.0)
+        b = m(x)
+    t0 = cfg["tasks"][0]
+    assert torch.allclose(b[t0], a[t0] + 1.0, atol=1e-4)
