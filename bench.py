@@ -243,57 +243,38 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 def gemm_roofline(model, plan, x_dev, peaks, peak_src):
     """Average duration and algorithmic FLOPs of the dominant kernel family (the tcgen05 GEMM / implicit-GEMM
-    conv kernels: every mtt_gemm launch of one forward), measured live with CUDA events on the launching stream.
+    conv kernels: every mtt_gemm launch of one forward, including those inside the composite block operators),
+    measured live with CUDA events recorded by the library around each launch on the launching stream
+    (mtt_profile_begin / mtt_profile_end).
 
     The forward is enqueued eagerly on ONE stream behind a device-side blocker, so the whole launch queue is
     resident before the first kernel runs and the events bracket device time only (without the blocker an
     eager pass measures the host's per-launch latency instead: 102 us / launch against 44 us real)."""
     from mtt_b200 import ops
 
-    recs = []
-    real = ops.gemm
-
-    def timed(a, w, **kw):
-        M = kw.get("M") or a.rows
-        N = kw.get("N") or w.rows
-        K = kw.get("K") or a.cols
-        taps = 1
-        if kw.get("conv") is not None:
-            taps = kw["conv"][3] ** 2
-        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s.record()
-        real(a, w, **kw)
-        e.record()
-        recs.append((s, e, 2.0 * M * N * K * taps, min(N, K) >= 1024))
-
-    arecs = []
-    real_attn = ops.attention
-
-    def timed_attn(q, o, **kw):
-        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s.record()
-        real_attn(q, o, **kw)
-        e.record()
-        arecs.append((s, e, 4.0 * kw["B"] * kw["H"] * kw["N"] * kw["N"] * 64))
-
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ops.gemm = timed
-    ops.attention = timed_attn
     plan.serial = True
     try:
         plan._launch(x_dev)   # warm
         torch.cuda.synchronize()
-        recs.clear()
-        arecs.clear()
         torch.cuda._sleep(int(60e6))   # ~30 ms of device time: the host enqueues the whole forward meanwhile
+        ops.profile_begin()
         f0.record()
         plan._launch(x_dev)
         f1.record()
-        torch.cuda.synchronize()
+        prof = ops.profile_end()
     finally:
-        ops.gemm = real
-        ops.attention = real_attn
         plan.serial = False
+
+    class _R:      # (ms, flops, backbone?) records in the shape the summary below expects
+        def __init__(self, ms):
+            self.ms = ms
+
+        def elapsed_time(self, other):
+            return self.ms
+
+    recs = [(_R(ms), None, fl, min(N, K) >= 1024) for kind, M, N, K, ms, fl in prof if kind == 0]
+    arecs = [(_R(ms), None, fl) for kind, M, N, K, ms, fl in prof if kind == 1]
     fwd_ms = f0.elapsed_time(f1)
     tot_ms = sum(s.elapsed_time(e) for s, e, _, _ in recs)
     tot_fl = sum(f for _, _, f, _ in recs)

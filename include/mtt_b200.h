@@ -50,6 +50,19 @@ int mtt_device_check(void);
 int64_t mtt_launch_count(void);
 void mtt_launch_count_reset(void);
 
+/* Per-launch timing of the tensor-core kernels (bench.py's roofline block): between begin and end every mtt_gemm
+ * (kind 0) and mtt_attention (kind 1) launch -- including those issued inside the composite operators -- is bracketed
+ * by CUDA events on its stream and recorded with its algorithmic FLOPs (2*M*N*K*taps; attention 4*B*H*N*N*64).
+ * mtt_profile_end synchronises the device, fills up to max_recs records and returns the total count in *n_recs.
+ * Not usable during stream capture. */
+typedef struct {
+  int32_t kind, M, N, K;
+  float ms;
+  double flops;
+} mtt_profile_rec;
+int mtt_profile_begin(void);
+int mtt_profile_end(mtt_profile_rec* out, int32_t max_recs, int32_t* n_recs);
+
 /* ---- fp32 -> split bf16 planes ------------------------------------------------------------
  * Used for weight pre-packing and for inputs produced outside the library.
  * rows x cols fp32 (ld_in) -> hi/lo bf16 (ld_out); columns [cols, cols_pad) are written as zero. */

@@ -92,6 +92,54 @@ __device__ __forceinline__ float softmax_block5(uint32_t taddr, int kn, float sl
   return sum;
 }
 
+// The same pass with the instruction stream cut to ~4.5 issue slots per element (the pass above: ~8 plus an F2FP on
+// the exp unit's pipe): packed FFMA2 / FADD2, truncation split through PRMT, both 32-column TMEM loads in flight
+// before the first use, and NO per-element maximum -- an exponent that ran away from the running maximum shows up
+// in the row sum (any p > 2^kA5LazyLog2 makes sum exceed it), which is all the caller needs to trigger its redo path.
+template <bool FULL, int NSPLIT>
+__device__ __forceinline__ float softmax_block6(uint32_t taddr, int kn, float sl2, float mb, uint32_t (&ph)[32],
+                                               uint32_t (&pl)[32], float* export_ptr) {
+  const int ncols = FULL ? 64 : ((kn + 15) & ~15);
+  uint32_t s0[32], s1[32];
+  tmem_ld32(taddr, s0);
+  if (FULL || ncols > 32) tmem_ld32(taddr + 32, s1);
+  tmem_ld_wait();
+  if (export_ptr) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      if (FULL || i < kn) export_ptr[i] = __uint_as_float(s0[i]);
+      if (FULL || 32 + i < kn) export_ptr[32 + i] = __uint_as_float(s1[i]);
+    }
+  }
+  const float2 c2 = make_float2(sl2, sl2), m2 = make_float2(-mb, -mb);
+  float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    const uint32_t(&s)[32] = c ? s1 : s0;
+    if (!FULL && c * 32 >= ncols) {  // columns the (narrowed) MMA never wrote
+#pragma unroll
+      for (int i = 0; i < 16; ++i) ph[c * 16 + i] = pl[c * 16 + i] = 0u;
+      continue;
+    }
+#pragma unroll
+    for (int i = 0; i < 32; i += 2) {
+      const float2 t = ffma2(make_float2(__uint_as_float(s[i]), __uint_as_float(s[i + 1])), c2, m2);
+      float2 p = make_float2(ex2_approx(t.x), ex2_approx(t.y));
+      if (!FULL) {
+        if (c * 32 + i >= kn) p.x = 0.f;
+        if (c * 32 + i + 1 >= kn) p.y = 0.f;
+      }
+      acc = fadd2(acc, p);
+      if (NSPLIT == 2) {
+        split_trunc2(p, ph[c * 16 + (i >> 1)], pl[c * 16 + (i >> 1)]);
+      } else {
+        ph[c * 16 + (i >> 1)] = pack_bf16x2(p.x, p.y);
+      }
+    }
+  }
+  return acc.x + acc.y;
+}
+
 // raw maximum of this thread's row of S_j (first block of an item: the running maximum does not exist yet)
 template <bool FULL>
 __device__ __forceinline__ float block_max5(uint32_t taddr, int kn) {
@@ -109,7 +157,7 @@ __device__ __forceinline__ float block_max5(uint32_t taddr, int kn) {
   return mx;
 }
 
-template <int NSPLIT, bool TRACE>
+template <int NSPLIT, bool TRACE, bool FAST>
 __global__ void __launch_bounds__(kA5Threads, 2)
 attention5_kernel(const __grid_constant__ CUtensorMap tmq_hi, const __grid_constant__ CUtensorMap tmq_lo,
                   const __grid_constant__ CUtensorMap tmk_hi, const __grid_constant__ CUtensorMap tmk_lo,
@@ -357,14 +405,27 @@ attention5_kernel(const __grid_constant__ CUtensorMap tmq_hi, const __grid_const
         uint32_t ph[32], pl[32];
         float bmax, sum;
         if (j == 0) m_run = full ? block_max5<true>(tS, kn) : block_max5<false>(tS, kn);
-        sum = full ? softmax_block5<true, NSPLIT>(tS, kn, p.scale_log2, m_run * p.scale_log2, bmax, ph, pl, ex)
-                   : softmax_block5<false, NSPLIT>(tS, kn, p.scale_log2, m_run * p.scale_log2, bmax, ph, pl, ex);
-        const bool need = (bmax - m_run) * p.scale_log2 > kA5LazyLog2;
+        bool need;
+        if (FAST) {
+          sum = full ? softmax_block6<true, NSPLIT>(tS, kn, p.scale_log2, m_run * p.scale_log2, ph, pl, ex)
+                     : softmax_block6<false, NSPLIT>(tS, kn, p.scale_log2, m_run * p.scale_log2, ph, pl, ex);
+          // some p above 2^kA5LazyLog2 => the sum is above it too (the converse may fire early: a harmless redo);
+          // an overflowed (inf) or NaN sum takes the redo path as well
+          need = !(sum <= exp2f(kA5LazyLog2));
+        } else {
+          sum = full ? softmax_block5<true, NSPLIT>(tS, kn, p.scale_log2, m_run * p.scale_log2, bmax, ph, pl, ex)
+                     : softmax_block5<false, NSPLIT>(tS, kn, p.scale_log2, m_run * p.scale_log2, bmax, ph, pl, ex);
+          need = (bmax - m_run) * p.scale_log2 > kA5LazyLog2;
+        }
         if (__any_sync(0xffffffffu, need)) {
           // rare: the block maximum ran away from the running maximum.  O / l are rescaled (O is quiescent: PV_{g-1}
           // has retired and PV_g needs this warp's P_g) and the block is redone against the new maximum.
           mbar_wait(&pv_done[(g - 1) & 1], ((g - 1) >> 1) & 1);  // S_g retired => PV_{g-2} retired: no aliasing
           tc_fence_after();
+          if (FAST) {
+            bmax = full ? block_max5<true>(tS, kn) : block_max5<false>(tS, kn);
+            need = bmax > m_run;  // any upward move is taken now that the block is redone anyway
+          }
           const float alpha = need ? ex2_approx((m_run - bmax) * p.scale_log2) : 1.0f;
 #pragma unroll
           for (int c = 0; c < 2; ++c) {
@@ -436,14 +497,14 @@ attention5_kernel(const __grid_constant__ CUtensorMap tmq_hi, const __grid_const
   }
 }
 
-template <int NSPLIT, bool TRACE>
+template <int NSPLIT, bool TRACE, bool FAST>
 static int launch_attn5(const CUtensorMap* maps, const Attn5Params& p, cudaStream_t stream) {
   constexpr uint32_t smem =
       NSPLIT * kA5QTile + (kA5KStages + kA5VStages) * NSPLIT * kA5KVTile + 1024 + 256;
   static bool attr_set[kMaxDevices] = {};  // the opt-in is per device (and per kernel instantiation)
   const int dev_ = current_device();
   if (!attr_set[dev_]) {
-    cudaError_t e = cudaFuncSetAttribute(attention5_kernel<NSPLIT, TRACE>,
+    cudaError_t e = cudaFuncSetAttribute(attention5_kernel<NSPLIT, TRACE, FAST>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess)
       return set_error(MTT_ERR_LAUNCH, "attention5: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
@@ -451,14 +512,14 @@ static int launch_attn5(const CUtensorMap* maps, const Attn5Params& p, cudaStrea
   }
   const int total = ((p.N + 127) / 128) * p.H * p.B;
   const int slots = 2 * sm_count();
-  attention5_kernel<NSPLIT, TRACE><<<total < slots ? total : slots, kA5Threads, smem, stream>>>(maps[0], maps[1], maps[2],
+  attention5_kernel<NSPLIT, TRACE, FAST><<<total < slots ? total : slots, kA5Threads, smem, stream>>>(maps[0], maps[1], maps[2],
                                                                                        maps[3], p);
   return check_launch("mtt_attention(variant 5)");
 }
 
 extern unsigned int* g_attn_trace;  // attention_tc.cu (mtt_set_attention_trace)
 
-int launch_attention5(const mtt_attn_desc* d, cudaStream_t stream) {
+int launch_attention5(const mtt_attn_desc* d, bool fast, cudaStream_t stream) {
   const int C = d->H * 64;
   CUtensorMap maps[4];
   const uint64_t dims[3] = {(uint64_t)3 * C, (uint64_t)d->N, (uint64_t)d->B};
@@ -486,8 +547,10 @@ int launch_attention5(const mtt_attn_desc* d, cudaStream_t stream) {
   p.prompt_logits = d->prompt_logits;
   p.wide_store = ((reinterpret_cast<uintptr_t>(d->out_hi) | reinterpret_cast<uintptr_t>(d->out_lo)) & 31) == 0;
   p.trace = g_attn_trace;
-  if (g_attn_trace && d->nsplit == 2) return launch_attn5<2, true>(maps, p, stream);
-  return d->nsplit == 2 ? launch_attn5<2, false>(maps, p, stream) : launch_attn5<1, false>(maps, p, stream);
+  if (g_attn_trace && d->nsplit == 2)
+    return fast ? launch_attn5<2, true, true>(maps, p, stream) : launch_attn5<2, true, false>(maps, p, stream);
+  if (fast) return d->nsplit == 2 ? launch_attn5<2, false, true>(maps, p, stream) : launch_attn5<1, false, true>(maps, p, stream);
+  return d->nsplit == 2 ? launch_attn5<2, false, false>(maps, p, stream) : launch_attn5<1, false, false>(maps, p, stream);
 }
 
 }  // namespace mtt

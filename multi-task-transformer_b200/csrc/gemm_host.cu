@@ -214,6 +214,8 @@ extern "C" int mtt_gemm(const mtt_gemm_desc* d, mtt_stream_t stream_) {
       v = (wide && d->M > 128 && (d->N >= 2048 || d->K >= 2048)) ? 2 : 1;
     }
   }
+  const int taps = (d && d->mode == 1) ? d->ksize * d->ksize : 1;
+  ProfileScope prof(stream, 0, d ? 2.0 * d->M * d->N * d->K * taps : 0.0, d ? d->M : 0, d ? d->N : 0, d ? d->K * taps : 0);
   if (v == 1) return launch_gemm_1cta(d, stream);
   return launch_gemm_2cta(d, v == 2 ? 256 : 128, stream);
 }

@@ -4,6 +4,8 @@
 #include <stdarg.h>
 #include <stdio.h>
 
+#include <vector>
+
 namespace mtt {
 
 static thread_local char g_err[512] = "";
@@ -89,11 +91,71 @@ int sm_count() {
   return n[dev];
 }
 
+// ---------------------------------------------------------------- per-launch timing (bench.py's roofline block)
+struct ProfileEntry {
+  cudaEvent_t start, stop;
+  int kind, M, N, K;
+  double flops;
+};
+static bool g_prof_on = false;
+static std::vector<ProfileEntry> g_prof;
+
+ProfileScope::ProfileScope(cudaStream_t stream, int kind, double flops, int M, int N, int K) : stream_(stream), slot_(-1) {
+  if (!g_prof_on) return;
+  ProfileEntry e;
+  e.kind = kind;
+  e.M = M;
+  e.N = N;
+  e.K = K;
+  e.flops = flops;
+  if (cudaEventCreate(&e.start) != cudaSuccess || cudaEventCreate(&e.stop) != cudaSuccess) return;
+  cudaEventRecord(e.start, stream);
+  g_prof.push_back(e);
+  slot_ = (int)g_prof.size() - 1;
+}
+ProfileScope::~ProfileScope() {
+  if (slot_ >= 0) cudaEventRecord(g_prof[slot_].stop, stream_);
+}
+
 }  // namespace mtt
 
 extern "C" {
 
-int mtt_version(void) { return 100; }
+int mtt_profile_begin(void) {
+  for (auto& e : mtt::g_prof) {
+    cudaEventDestroy(e.start);
+    cudaEventDestroy(e.stop);
+  }
+  mtt::g_prof.clear();
+  mtt::g_prof_on = true;
+  return MTT_OK;
+}
+
+int mtt_profile_end(mtt_profile_rec* out, int32_t max_recs, int32_t* n_recs) {
+  mtt::g_prof_on = false;
+  if (cudaDeviceSynchronize() != cudaSuccess) return mtt::set_error(MTT_ERR_LAUNCH, "mtt_profile_end: device sync failed");
+  int n = 0;
+  for (auto& e : mtt::g_prof) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e.start, e.stop);
+    if (out && n < max_recs) {
+      out[n].kind = e.kind;
+      out[n].M = e.M;
+      out[n].N = e.N;
+      out[n].K = e.K;
+      out[n].ms = ms;
+      out[n].flops = e.flops;
+    }
+    ++n;
+    cudaEventDestroy(e.start);
+    cudaEventDestroy(e.stop);
+  }
+  mtt::g_prof.clear();
+  if (n_recs) *n_recs = n;
+  return MTT_OK;
+}
+
+int mtt_version(void) { return 200; }
 
 const char* mtt_last_error(void) { return mtt::g_err; }
 

@@ -24,4 +24,13 @@ constexpr int kMaxDevices = 64;
 int current_device();
 int sm_count();
 
+// Profiling aid (mtt_profile_begin / mtt_profile_end): while active, every tensor-core launch of the library is
+// bracketed by CUDA events on its own stream and recorded with its algorithmic FLOPs. Not usable during graph capture.
+struct ProfileScope {
+  ProfileScope(cudaStream_t stream, int kind, double flops, int M, int N, int K);
+  ~ProfileScope();
+  cudaStream_t stream_;
+  int slot_;
+};
+
 }  // namespace mtt

@@ -410,6 +410,44 @@ __device__ __forceinline__ void split_pack2_alu(float a, float b, uint32_t& hi, 
   lo = __byte_perm(__float_as_uint(ra) + 0x8000u, __float_as_uint(rb) + 0x8000u, 0x7632);
 }
 
+// ---------------------------------------------------------------- packed fp32 pairs (FFMA2 / FADD2, sm_100+)
+// Two independent fp32 operations per instruction on a 64-bit register pair: halves the FMA-pipe issue slots of
+// the softmax inner loop.
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  unsigned long long r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;"
+      : "=l"(r)
+      : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)),
+        "l"(*reinterpret_cast<unsigned long long*>(&c)));
+  return *reinterpret_cast<float2*>(&r);
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+  unsigned long long r;
+  asm("add.rn.f32x2 %0, %1, %2;"
+      : "=l"(r)
+      : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
+  return *reinterpret_cast<float2*>(&r);
+}
+__device__ __forceinline__ float2 fsub2(float2 a, float2 b) {
+  unsigned long long r;
+  asm("sub.rn.f32x2 %0, %1, %2;"
+      : "=l"(r)
+      : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
+  return *reinterpret_cast<float2*>(&r);
+}
+
+// Split of a NON-NEGATIVE finite pair (softmax probabilities) into bf16 planes by TRUNCATION, integer / FMA pipes
+// only (no F2FP, which shares the 16-lane XU pipe with MUFU.EX2): hi = upper 16 bits of p (PRMT), lo = upper 16
+// bits of the exact residual p - hi (FADD2 + PRMT).  p - (hi + lo) in [0, 2^-15 p): 15-16 significant bits like the
+// rounded split, with a one-sided error of mean ~2^-17 p.
+__device__ __forceinline__ void split_trunc2(float2 p, uint32_t& hi, uint32_t& lo) {
+  const uint32_t u0 = __float_as_uint(p.x), u1 = __float_as_uint(p.y);
+  hi = __byte_perm(u0, u1, 0x7632);
+  const float2 h = make_float2(__uint_as_float(hi << 16), __uint_as_float(hi & 0xFFFF0000u));
+  const float2 r = fsub2(p, h);
+  lo = __byte_perm(__float_as_uint(r.x), __float_as_uint(r.y), 0x7632);
+}
+
 // bare MUFU.EX2 (2 ulp, flushes denormal results to zero): no range fix-up code around it
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;

@@ -50,15 +50,29 @@ def shard_batch(global_batch, rank, world):
 
 
 def gather_outputs(out, world, dst=0):
-    """Concatenate per-rank output dicts {task: [b, ...]} along the batch on rank `dst` (evaluation)."""
+    """Concatenate per-rank output dicts {task: [b_rank, ...]} along the batch on rank `dst` (evaluation).
+    Ranks may hold DIFFERENT batch sizes (shard_batch gives the remainder to the low ranks): the sizes are
+    all-gathered first, every rank pads its shard to the largest one for the collective, and `dst` trims."""
     if world == 1:
         return out
+    rank = dist.get_rank()
+    first = out[sorted(out)[0]]
+    n = torch.tensor([first.shape[0]], dtype=torch.int64, device=first.device)
+    sizes = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(sizes, n)
+    sizes = [int(s.item()) for s in sizes]
+    mx = max(sizes)
     res = {}
     for k in sorted(out):
-        parts = [torch.empty_like(out[k]) for _ in range(world)] if dist.get_rank() == dst else None
-        dist.gather(out[k].contiguous(), parts, dst=dst)
+        t = out[k].contiguous()
+        if t.shape[0] != sizes[rank]:
+            raise ValueError(f"gather_outputs: {k!r} has batch {t.shape[0]}, expected {sizes[rank]}")
+        if t.shape[0] < mx:
+            t = torch.cat([t, t.new_zeros((mx - t.shape[0],) + tuple(t.shape[1:]))], dim=0)
+        parts = [torch.empty_like(t) for _ in range(world)] if rank == dst else None
+        dist.gather(t, parts, dst=dst)
         if parts is not None:
-            res[k] = torch.cat(parts, dim=0)
+            res[k] = torch.cat([p[:s] for p, s in zip(parts, sizes)], dim=0)
     return res
 
 

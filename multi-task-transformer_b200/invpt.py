@@ -8,10 +8,18 @@ Module classes and parameter names mirror the reference so that its checkpoints 
   InvPT / InvPTStage / InvPTBlock / SelfAttention / UpEmbed   InvPT/models/transformers/invpt.py:19-544
   TransformerNet                               InvPT/models/transformer_net.py:12-38
 
-The modules only own parameters; all arithmetic runs in libmtt_sm100.so through `ops` (see
-taskprompter.py for the conventions). Eval-mode only (SyncBatchNorm = running statistics, DropPath =
-identity). Not reproduced because the reference never consumes them: scale_embed[2]'s output and
-`norm_mt`.
+The modules own parameters and expose the reference's forward signatures; all arithmetic runs in libmtt_sm100.so
+through `ops` (conventions: taskprompter.py):
+
+  TransformerNet.forward(x)              -> {task: [B,n,H,W], 'inter_preds': {...}}   the fused path, ONE CUDA graph
+  VisionTransformer.forward(x)           -> (x [B,P,C], [4 x [B,P,C]])                 vit.py:332-361
+  TransformerDecoder.forward(x_list)     -> (x_dict {task: [B,C0,8h,8w]}, inter_pred)  transformer_decoder.py:69-98
+  InvPT.forward(x_dict, inter_pred, back_fea) -> x_dict                                invpt.py:502-544
+  MLPHead.forward(x)                     -> linear_pred(x)                             transformer_decoder.py:130
+
+The sub-module forwards run segments of the same launch plan eagerly, with NCHW / token tensors in and out like the
+reference. Eval-mode only (SyncBatchNorm = running statistics, DropPath = identity). Not reproduced because the
+reference never consumes them: scale_embed[2]'s output and `norm_mt`.
 """
 from types import SimpleNamespace
 
@@ -19,8 +27,8 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from .pack import fold_bn, pack_conv_weight, pack_linear_weight
-from .taskprompter import PARITY, Mlp, PatchEmbed, _trunc_normal_
+from .taskprompter import (PARITY, Mlp, PatchEmbed, _cached, _check_input, _dev_ctx, _f32, _plan_for, _Streams,
+                           _trunc_normal_, _version)
 
 
 # --------------------------------------------------------------------------------------------
@@ -61,12 +69,25 @@ class VisionTransformer(nn.Module):
         self.blocks = nn.Sequential(*[VitBlock(embed_dim, num_heads, mlp_ratio, qkv_bias) for _ in range(depth)])
         self.norm = nn.LayerNorm(embed_dim, eps=1e-6)
         self.select_list = list(select_list)
+        self.nsplit = PARITY
+        self.use_graph = False
         _trunc_normal_(self.pos_embed, std=.02)
         _trunc_normal_(self.cls_token, std=.02)
         for m in self.modules():
             if isinstance(m, nn.Linear):
                 _trunc_normal_(m.weight, std=.02)
                 nn.init.zeros_(m.bias)
+
+    def forward(self, x):
+        """vit.py:332-361: (final-norm patch tokens [B,P,C], [x[:,1:] after each selected block ..., the same final
+        tokens]). Fresh tensors."""
+        _check_input(self, x)
+        B, dev = x.shape[0], x.device
+        pl = _plan_for(self, (B, dev, self.nsplit, "backbone"), lambda: _Plan(
+            self, None, None, None, [], B, dev, self.nsplit, mode="backbone"))
+        feats = pl.run(x, graph=self.use_graph)["selected_fea"]
+        feats = [f.clone() for f in feats]
+        return feats[-1], feats
 
 
 class ConvBlock(nn.Module):
@@ -82,9 +103,29 @@ class ConvBlock(nn.Module):
 class MLPHead(nn.Module):
     """transformer_decoder.py:124-131."""
 
+    nsplit = PARITY
+
     def __init__(self, in_channels, num_classes):
         super().__init__()
         self.linear_pred = nn.Conv2d(in_channels, num_classes, kernel_size=1)
+
+    def forward(self, x):
+        """x [B,Cin,h,w] NCHW -> [B,n_out,h,w] (1x1 conv on the tcgen05 GEMM)."""
+        _check_input(self, x)
+        B, Cin, h, w = x.shape
+        dev, ns = x.device, self.nsplit
+        with _dev_ctx(dev):
+            lp = _cached(self, ("pack", dev, ns), lambda: (
+                ops.pack_weight(_f32(self.linear_pred.weight, dev).reshape(self.linear_pred.weight.shape[0], -1), ns),
+                _f32(self.linear_pred.bias, dev)))
+            n = self.linear_pred.weight.shape[0]
+            a = ops.Split(B * h * w, Cin, dev, ns)
+            ops.nchw_to_nhwc_split(x.contiguous(), a)
+            y = torch.empty(B * h * w, ops.round_up(n, 4), device=dev, dtype=torch.float32)
+            ops.gemm(a, lp[0], bias=lp[1], out_f32=y[:, :n], N=n)
+            out = torch.empty(B, n, h, w, device=dev, dtype=torch.float32)
+            ops.nhwc_to_nchw(y, y.stride(0), B, n, h, w, out)
+            return out
 
 
 class UpEmbed(nn.Module):
@@ -153,6 +194,10 @@ class InvPT(nn.Module):
         T = len(tasks)
         dims = [in_chans, in_chans // 2, in_chans // 4]
         self.dims = dims
+        self.p = p
+        self.tasks = tasks
+        self.ori_embed_dim = ori_embed_dim
+        self.nsplit = PARITY
         self.norm_mts = nn.ModuleList()
         self.redu_chan = nn.ModuleList()
         self.invpt_stages = nn.ModuleList()
@@ -168,12 +213,27 @@ class InvPT(nn.Module):
         self.mix_proj = nn.ModuleDict({t: nn.Sequential(nn.Conv2d(ori_embed_dim + p.TASKS.NUM_OUTPUT[t], in_chans, 1))
                                        for t in tasks})
 
+    def forward(self, x_dict, inter_pred, back_fea):
+        """invpt.py:502-544. x_dict {task: [B,E,h,w]}, inter_pred {task: [B,n,h,w]}, back_fea [[B,C0/4,4h',4w'],
+        [B,C0/2,2h',2w'], ...] (the first two are the skips of stages 2 and 1) -> {task: [B,C0,8h,8w]}."""
+        x0 = x_dict[self.tasks[0]]
+        _check_input(self, x0)
+        B, _, h0, w0 = x0.shape
+        dev = x0.device
+        pl = _plan_for(self, (B, dev, self.nsplit, "invpt", h0, w0), lambda: _Plan(
+            None, None, None, self.p, self.tasks, B, dev, self.nsplit, mode="invpt", inv=self, hw0=(h0, w0)))
+        with _dev_ctx(dev):
+            pl.load_invpt_inputs(x_dict, inter_pred, back_fea)
+            return {t: v.clone() for t, v in pl.run(None, graph=False)["x_dict"].items()}
+
 
 class TransformerDecoder(nn.Module):
     """transformer_decoder.py:18-67."""
 
     def __init__(self, p):
         super().__init__()
+        self.p = p
+        self.nsplit = PARITY
         self.embed_dim = p.embed_dim
         d0 = p.embed_dim + p.PRED_OUT_NUM_CONSTANT
         tasks = list(p.TASKS.NAMES)
@@ -188,6 +248,20 @@ class TransformerDecoder(nn.Module):
             nn.Conv2d(p.backbone_channels[2], d0, 3, padding=1),
             None])
 
+    def forward(self, x_list):
+        """transformer_decoder.py:69-98. x_list: the backbone's 4 selected features [B,P,C] ->
+        (x_dict {task: [B,C0,8h,8w]}, inter_pred {task: [B,n_out,h,w]}) with (h,w) = the mtt resolution."""
+        _check_input(self, x_list[0])
+        B, dev = x_list[0].shape[0], x_list[0].device
+        tasks = list(self.p.TASKS.NAMES)
+        pl = _plan_for(self, (B, dev, self.nsplit, "decoder"), lambda: _Plan(
+            None, self, None, self.p, tasks, B, dev, self.nsplit, mode="decoder"))
+        with _dev_ctx(dev):
+            pl.load_features(x_list)
+            out = pl.run(None, graph=False)
+            return ({t: v.clone() for t, v in out["x_dict"].items()},
+                    {t: v.clone() for t, v in out["inter_pred"].items()})
+
 
 class TransformerNet(nn.Module):
     """transformer_net.py:12-38. forward(x[B,3,H,W]) -> {task: [B,n_out,H,W], 'inter_preds': {task: ...}}."""
@@ -201,239 +275,324 @@ class TransformerNet(nn.Module):
         self.heads = heads
         self.nsplit = nsplit
         self.use_graph = use_graph
-        self._plans = {}
-
-    def _param_version(self):
-        return sum(int(q._version) for q in self.parameters()) + sum(int(b._version) for b in self.buffers())
 
     def plan(self, batch, device, postproc=False):
-        key = (int(batch), str(device), int(self.nsplit), bool(postproc))
-        ver = self._param_version()
-        pl = self._plans.get(key)
-        if pl is None or pl.version != ver:
-            pl = _Plan(self, batch, device, self.nsplit, postproc=postproc)
-            pl.version = ver
-            self._plans[key] = pl
-        return pl
-
-    def _check(self, x):
-        if self.training:
-            raise NotImplementedError("mtt_b200 InvPT: fused forward is eval-only; backward kernels are not built "
-                                      "yet (SURVEY.md section 8f N1)")
-        if not x.is_cuda:
-            raise RuntimeError("mtt_b200 has no CPU path: input must be a CUDA tensor on an sm_100a device")
+        mode = "postproc" if postproc else "full"
+        return _plan_for(self, (int(batch), torch.device(device), int(self.nsplit), mode), lambda: _Plan(
+            self.backbone, self.multi_task_decoder, self.heads, self.p, self.tasks, batch, torch.device(device),
+            self.nsplit, mode=mode))
 
     def forward(self, x):
-        self._check(x)
+        _check_input(self, x)
         return self.plan(x.shape[0], x.device).run(x, graph=self.use_graph)
 
     def predict(self, x):
         """forward + the reference's `get_output` post-processing (InvPT/utils/utils.py:18-48) fused into the
         final resize of every task head (no full-resolution logits, no inter_preds)."""
-        self._check(x)
+        _check_input(self, x)
         return self.plan(x.shape[0], x.device, postproc=True).run(x, graph=self.use_graph)
 
 
 # --------------------------------------------------------------------------------------------
 # the fused forward
 # --------------------------------------------------------------------------------------------
-class _Plan:
-    def __init__(self, net, B, device, nsplit, postproc=False):
-        ops._L.check(ops._L.load().mtt_device_check(), "mtt_device_check")
-        self.postproc = postproc
-        bb, dec, p = net.backbone, net.multi_task_decoder, net.p
-        inv = dec.invpt
-        self.B, self.dev, self.ns = B, device, nsplit
-        self.tasks = list(net.tasks)
-        self.T = T = len(self.tasks)
-        self.C = C = bb.embed_dim
-        self.H = bb.num_heads
-        assert C // self.H == 64, "attention kernel is built for head_dim 64"
-        self.gh, self.gw = bb.patch_embed.grid_size
-        self.P = P = self.gh * self.gw
-        self.N = N = 1 + P
-        self.patch = bb.patch_size
-        self.img = (self.gh * self.patch, self.gw * self.patch)
-        self.select = list(bb.select_list)
-        self.depth = len(bb.blocks)
-        self.E = E = p.embed_dim
-        self.dims = dims = list(inv.dims)
-        down = p.mtt_resolution_downsample_rate
-        self.h0, self.w0 = self.gh // down, self.gw // down
-        self.th, self.tw = self.h0 * 8, self.w0 * 8
-        self.n_out = [p.TASKS.NUM_OUTPUT[t] for t in self.tasks]
-        self.graph = None
-        self.static_in = None
-        ns = nsplit
-        h0, w0 = self.h0, self.w0
-
-        def f32(t):
-            return t.detach().to(device=device, dtype=torch.float32).contiguous()
-
+def _pack_vit(bb, device, ns):
+    """Patch embedding, cls / position rows, the ViT blocks and the final norm (vit.py:172-351)."""
+    def build():
+        f = lambda t: _f32(t, device)
         W = SimpleNamespace()
-        W.pe_w = pack_linear_weight(f32(bb.patch_embed.proj.weight), ns)
-        W.pe_b = f32(bb.patch_embed.proj.bias)
-        W.pos = f32(bb.pos_embed)[0, 1:]
-        W.cls = (f32(bb.cls_token)[0] + f32(bb.pos_embed)[0, :1]).contiguous()      # vit.py:334-339, row 0
+        W.pe_w = ops.pack_weight(f(bb.patch_embed.proj.weight).reshape(bb.embed_dim, -1), ns)
+        W.pe_b = f(bb.patch_embed.proj.bias)
+        W.pos = f(bb.pos_embed)[0, 1:].contiguous()
+        W.cls = (f(bb.cls_token)[0] + f(bb.pos_embed)[0, :1]).contiguous()      # vit.py:334-339, row 0
         W.blocks = []
         for blk in bb.blocks:
             w = SimpleNamespace()
-            w.n1w, w.n1b, w.n2w, w.n2b = f32(blk.norm1.weight), f32(blk.norm1.bias), f32(blk.norm2.weight), f32(blk.norm2.bias)
+            w.n1w, w.n1b, w.n2w, w.n2b = f(blk.norm1.weight), f(blk.norm1.bias), f(blk.norm2.weight), f(blk.norm2.bias)
             w.eps = blk.norm1.eps
-            w.qkv, w.qkv_b = pack_linear_weight(f32(blk.attn.qkv.weight), ns), f32(blk.attn.qkv.bias)
-            w.proj, w.proj_b = pack_linear_weight(f32(blk.attn.proj.weight), ns), f32(blk.attn.proj.bias)
-            w.fc1, w.fc1_b = pack_linear_weight(f32(blk.mlp.fc1.weight), ns), f32(blk.mlp.fc1.bias)
-            w.fc2, w.fc2_b = pack_linear_weight(f32(blk.mlp.fc2.weight), ns), f32(blk.mlp.fc2.bias)
+            w.qkv, w.qkv_b = ops.pack_weight(f(blk.attn.qkv.weight), ns), f(blk.attn.qkv.bias)
+            w.proj, w.proj_b = ops.pack_weight(f(blk.attn.proj.weight), ns), f(blk.attn.proj.bias)
+            w.fc1, w.fc1_b = ops.pack_weight(f(blk.mlp.fc1.weight), ns), f(blk.mlp.fc1.bias)
+            w.fc2, w.fc2_b = ops.pack_weight(f(blk.mlp.fc2.weight), ns), f(blk.mlp.fc2.bias)
             W.blocks.append(w)
-        W.nw, W.nb, W.neps = f32(bb.norm.weight), f32(bb.norm.bias), bb.norm.eps
+        W.nw, W.nb, W.neps = f(bb.norm.weight), f(bb.norm.bias), bb.norm.eps
+        return W
+    return _cached(bb, ("pack", device, ns), build)
+
+
+def _pack_decoder(dec, tasks, device, ns):
+    """scale_embed, preliminary decoders and intermediate heads (transformer_decoder.py:18-98), BatchNorm folded."""
+    def build():
+        f = lambda t: _f32(t, device)
+        W = SimpleNamespace()
         # ConvTranspose2d(k3,s2,p1,op1) == zero-insert + conv3x3(pad 1) with the spatially flipped,
-        # in/out-transposed kernel
-        wt = f32(dec.scale_embed[0].weight)                                           # [Cin, Cout, 3, 3]
-        W.se0 = pack_conv_weight(wt.flip(2, 3).permute(1, 0, 2, 3).contiguous(), ns)
-        W.se0_b = f32(dec.scale_embed[0].bias)
-        W.se1, W.se1_b = pack_conv_weight(f32(dec.scale_embed[1].weight), ns), f32(dec.scale_embed[1].bias)
+        # in/out-transposed kernel (mtt_pack_conv_weight transposed = 1)
+        W.se0, W.se0_b = ops.pack_conv_weight(f(dec.scale_embed[0].weight), dec.scale_embed[0].bias, None, ns,
+                                              transposed=True)
+        W.se1, W.se1_b = ops.pack_conv_weight(f(dec.scale_embed[1].weight), dec.scale_embed[1].bias, None, ns)
         W.tasks = []
-        for t in self.tasks:
+        for t in tasks:
             tw = SimpleNamespace()
             pd = dec.preliminary_decoder[t]
-            w0_, b0_ = fold_bn(f32(pd[0].conv.weight), None, pd[0].bn1)
-            w1_, b1_ = fold_bn(f32(pd[1].conv.weight), None, pd[1].bn1)
-            tw.pd0, tw.pd0_b = pack_conv_weight(w0_, ns), b0_.contiguous()
-            tw.pd1, tw.pd1_b = pack_conv_weight(w1_, ns), b1_.contiguous()
-            tw.ih, tw.ih_b = pack_linear_weight(f32(dec.intermediate_head[t].weight), ns), f32(dec.intermediate_head[t].bias)
-            tw.mix, tw.mix_b = pack_linear_weight(f32(inv.mix_proj[t][0].weight), ns), f32(inv.mix_proj[t][0].bias)
-            wm, bm = fold_bn(f32(inv.mt_proj[t][0].weight), f32(inv.mt_proj[t][0].bias), inv.mt_proj[t][1])
-            tw.mt, tw.mt_b = pack_conv_weight(wm, ns), bm.contiguous()
-            hd = net.heads[t]
-            tw.lp, tw.lp_b = pack_linear_weight(f32(hd.linear_pred.weight), ns), f32(hd.linear_pred.bias)
+            tw.pd0, tw.pd0_b = ops.pack_conv_weight(f(pd[0].conv.weight), None, pd[0].bn1, ns)
+            tw.pd1, tw.pd1_b = ops.pack_conv_weight(f(pd[1].conv.weight), None, pd[1].bn1, ns)
+            ih = dec.intermediate_head[t]
+            tw.ih, tw.ih_b = ops.pack_weight(f(ih.weight).reshape(ih.weight.shape[0], -1), ns), f(ih.bias)
             W.tasks.append(tw)
-        W.stages = []
+        return W
+    return _cached(dec, ("pack_dec", device, ns, tuple(tasks)), build)
+
+
+def _pack_invpt(inv, tasks, device, ns):
+    """mix_proj, the three stages, norm_mts / redu_chan and mt_proj (invpt.py:400-544)."""
+    def build():
+        f = lambda t: _f32(t, device)
+        T, dims = len(tasks), list(inv.dims)
+        W = SimpleNamespace(tasks=[], stages=[])
+        for t in tasks:
+            tw = SimpleNamespace()
+            mx = inv.mix_proj[t][0]
+            tw.mix, tw.mix_b = ops.pack_weight(f(mx.weight).reshape(mx.weight.shape[0], -1), ns), f(mx.bias)
+            tw.mt, tw.mt_b = ops.pack_conv_weight(f(inv.mt_proj[t][0].weight), inv.mt_proj[t][0].bias, inv.mt_proj[t][1], ns)
+            W.tasks.append(tw)
         for i, st in enumerate(inv.invpt_stages):
             sw = SimpleNamespace()
             if i > 0:
                 sw.up = []
                 for k in range(T):
                     pr = st.patch_embed[k].proj
-                    wa, ba = fold_bn(f32(pr[1].weight), None, pr[2])
-                    wb, bb_ = fold_bn(f32(pr[4].weight), None, pr[5])
-                    sw.up.append((pack_conv_weight(wa, ns), ba.contiguous(), pack_conv_weight(wb, ns), bb_.contiguous()))
+                    wa, ba = ops.pack_conv_weight(f(pr[1].weight), None, pr[2], ns)
+                    wb, bb_ = ops.pack_conv_weight(f(pr[4].weight), None, pr[5], ns)
+                    sw.up.append((wa, ba, wb, bb_))
             blk = st.blocks[0]
-            sw.n1w, sw.n1b, sw.n2w, sw.n2b = f32(blk.norm1.weight), f32(blk.norm1.bias), f32(blk.norm2.weight), f32(blk.norm2.bias)
+            sw.n1w, sw.n1b, sw.n2w, sw.n2b = f(blk.norm1.weight), f(blk.norm1.bias), f(blk.norm2.weight), f(blk.norm2.bias)
             sw.eps = blk.norm1.eps
             qw, qb = [], []
-            for k in range(T):
-                cw, cb = fold_bn(f32(blk.attn.conv_proj_q[k].conv.weight), None, blk.attn.conv_proj_q[k].bn)
-                qw.append(cw.reshape(dims[i], 9))
-                qb.append(cb)
+            for k in range(T):                       # depthwise 3x3 + eval BN: a per-channel fold, kept in fp32
+                cq = blk.attn.conv_proj_q[k]
+                sc = f(cq.bn.weight) / torch.sqrt(f(cq.bn.running_var) + cq.bn.eps)
+                qw.append((f(cq.conv.weight) * sc.reshape(-1, 1, 1, 1)).reshape(dims[i], 9))
+                qb.append(f(cq.bn.bias) - f(cq.bn.running_mean) * sc)
             sw.dw_w, sw.dw_b = torch.stack(qw).contiguous(), torch.stack(qb).contiguous()
             for nm in ("proj_q", "proj_k", "proj_v", "proj"):
                 lin = getattr(blk.attn, nm)
-                setattr(sw, nm, pack_linear_weight(f32(lin.weight), ns))
-                setattr(sw, nm + "_b", f32(lin.bias))
-            sw.fuse_w = f32(blk.attn.fuse_attn.weight).reshape(2, 4).contiguous()
-            sw.fuse_b = f32(blk.attn.fuse_attn.bias)
-            sw.fc1, sw.fc1_b = pack_linear_weight(f32(blk.mlp.fc1.weight), ns), f32(blk.mlp.fc1.bias)
-            sw.fc2, sw.fc2_b = pack_linear_weight(f32(blk.mlp.fc2.weight), ns), f32(blk.mlp.fc2.bias)
-            sw.nmw, sw.nmb, sw.nmeps = f32(inv.norm_mts[i].weight), f32(inv.norm_mts[i].bias), inv.norm_mts[i].eps
+                setattr(sw, nm, ops.pack_weight(f(lin.weight), ns))
+                setattr(sw, nm + "_b", f(lin.bias))
+            sw.fuse_w = f(blk.attn.fuse_attn.weight).reshape(2, 4).contiguous()
+            sw.fuse_b = f(blk.attn.fuse_attn.bias)
+            sw.fc1, sw.fc1_b = ops.pack_weight(f(blk.mlp.fc1.weight), ns), f(blk.mlp.fc1.bias)
+            sw.fc2, sw.fc2_b = ops.pack_weight(f(blk.mlp.fc2.weight), ns), f(blk.mlp.fc2.bias)
+            sw.nmw, sw.nmb, sw.nmeps = f(inv.norm_mts[i].weight), f(inv.norm_mts[i].bias), inv.norm_mts[i].eps
             if i > 0:
-                sw.redu = [(pack_linear_weight(f32(inv.redu_chan[i][k].weight), ns), f32(inv.redu_chan[i][k].bias))
-                           for k in range(T)]
+                sw.redu = [(ops.pack_weight(f(inv.redu_chan[i][k].weight).reshape(dims[0], -1), ns),
+                            f(inv.redu_chan[i][k].bias)) for k in range(T)]
             W.stages.append(sw)
-        self.W = W
+        return W
+    return _cached(inv, ("pack_inv", device, ns, tuple(tasks)), build)
 
-        # ---- workspace
+
+class _Plan:
+    """Workspace + launch sequence (+ CUDA graph) for one batch size. mode: "full" / "postproc" = TransformerNet
+    forward / predict; "backbone" = VisionTransformer.forward; "decoder" = TransformerDecoder.forward on given
+    backbone features; "invpt" = InvPT.forward on given task features, preliminary predictions and skips."""
+
+    def __init__(self, bb, dec, heads, p, tasks, B, device, nsplit, mode="full", inv=None, hw0=None):
+        ops._L.check(ops._L.load().mtt_device_check(), "mtt_device_check")
+        device = torch.device(device)
+        self.mode = mode
+        self.postproc = mode == "postproc"
+        self.bb, self.dec, self.heads, self.p = bb, dec, heads, p
+        self.inv = inv if inv is not None else (dec.invpt if dec is not None else None)
+        self.B, self.dev, self.ns = B, device, nsplit
+        self.tasks = list(tasks)
+        self.T = T = len(self.tasks)
+        self.graph = None
+        self.static_in = None
+        self.streams = _Streams(device, max(T, 1))
+        ns = nsplit
         S = lambda r, c, **kw: ops.Split(r, c, device, ns, **kw)
         z = lambda *s: torch.zeros(*s, device=device, dtype=torch.float32)
-        self.cols = S(B * P, self.patch * self.patch * bb.in_chans)
-        self.xs = z(B * N, C)
-        self.xn = S(B * N, C)
-        self.qkv = S(B * N, 3 * C)
-        self.ao = S(B * N, C)
-        self.hid = S(B * N, 4 * C)
-        self.zi = S(B * 4 * P, C)
-        self.f1 = S(B * P, C)
-        self.back0 = z(B * 4 * P, dims[2])
-        self.back1 = z(B * P, dims[1])
-        self.xfin = z(B * P, C)
-        self.x0 = S(B * h0 * w0, C)
-        self.p1 = [S(B * h0 * w0, C) for _ in range(T)]   # per task: the task chains run on side streams
-        self.cat = [S(B * h0 * w0, E + n, zero=True) for n in self.n_out]
-        self.inter = [z(B * h0 * w0, ops.round_up(n, 4)) for n in self.n_out]
-        self.st = []
-        for i in range(3):
-            h, w = h0 * 2 ** i, w0 * 2 ** i
-            Ci = dims[i]
-            s = SimpleNamespace(h=h, w=w, C=Ci)
-            s.kvs = 2 ** (i + 1)
-            s.kh, s.kw = -(-h // s.kvs), -(-w // s.kvs)
-            s.Lq = T * (h // 2) * (w // 2)
-            s.Tk = T * s.kh * s.kw
-            s.xj = z(B * T * h * w, Ci)
-            s.xn32 = z(B * T * h * w, Ci)
-            s.qin = S(B * s.Lq, Ci)
-            s.kvin = S(B * s.Tk, Ci)
-            s.q32, s.k32, s.v32 = z(B * s.Lq, Ci), z(B * s.Tk, Ci), z(B * s.Tk, Ci)
-            s.score = z(B, 2, s.Lq, s.Tk) if i < 2 else None
-            s.ao = S(B * s.Lq, Ci)
-            s.a32 = z(B * s.Lq, Ci)
-            s.xn = S(B * T * h * w, Ci)
-            s.hid = S(B * T * h * w, 4 * Ci)
-            if i == 0:
-                s.ln32 = z(T * B * h * w, Ci)
+        with _dev_ctx(device):
+            self._pack()
+            if bb is not None:
+                self.C = C = bb.embed_dim
+                self.H = bb.num_heads
+                assert C // self.H == 64, "attention kernel is built for head_dim 64"
+                self.gh, self.gw = bb.patch_embed.grid_size
+                self.patch = bb.patch_size
+                self.img = (self.gh * self.patch, self.gw * self.patch)
+                self.select = list(bb.select_list)
+                self.depth = len(bb.blocks)
+            elif mode == "decoder":
+                self.C = C = p.backbone_channels[-1]
+                self.gh, self.gw = p.spatial_dim[-1]
+            self.P = P = self.gh * self.gw if mode != "invpt" else 0
+            self.N = N = 1 + P
+            # ---- backbone workspace
+            if bb is not None:
+                self.cols = S(B * P, self.patch * self.patch * bb.in_chans)
+                self.qkv = S(B * N, 3 * C)
+                self.ao = S(B * N, C)
+                self.ws_qkv = ops.workspace(ops.workspace_bytes(ops._L.OP_LN_QKV, rows=B * N, Cdim=C, nsplit=ns), device)
+                self.ws_mlp = ops.workspace(ops.workspace_bytes(ops._L.OP_LN_MLP_RESIDUAL, rows=B * N, Cdim=C,
+                                                                hidden=bb.blocks[0].mlp.fc1.out_features, nsplit=ns),
+                                            device)
+            if mode != "invpt":
+                self.xs = z(B * N, C)
+                self.xfin = z(B * P, C)
+            if mode == "backbone":
+                self.sel = [z(B, P, C) for _ in range(len(self.select))]
+                self.out = {"selected_fea": self.sel + [self.xfin.view(B, P, C)]}
+                return
+            # ---- decoder workspace
+            inv_ = self.inv
+            self.E = E = inv_.ori_embed_dim
+            self.dims = dims = list(inv_.dims)
+            if mode == "invpt":
+                self.h0, self.w0 = hw0
             else:
-                s.ln = S(T * B * h * w, Ci)
-                s.rc32 = [z(B * h * w, dims[0]) for _ in range(T)]
-                s.ue0 = [S(B * h * w, dims[i - 1]) for _ in range(T)]
-                s.ue1 = [S(B * h * w, Ci) for _ in range(T)]
-            self.st.append(s)
-        tt = B * self.th * self.tw
-        self.mss = [S(tt, dims[0]) for _ in range(T)]
-        self.hm = [S(tt, dims[0]) for _ in range(T)]
-        self.side = None
-        self.pred = [z(tt, ops.round_up(n, 4)) for n in self.n_out]
-        oh, ow = self.img
-        if not postproc:
-            self.out = {t: z(B, n, oh, ow) for t, n in zip(self.tasks, self.n_out)}
-            self.out_inter = {t: z(B, n, oh, ow) for t, n in zip(self.tasks, self.n_out)}
-        else:
-            self.out, self.out_inter = {}, None
-            for t in self.tasks:
-                kind = ops.POSTPROC_KIND[t]
-                shape = {0: (B, oh, ow), 1: (B, oh, ow), 2: (B, oh, ow), 3: (B, oh, ow, 3), 4: (B, oh, ow, 1)}[kind]
-                self.out[t] = torch.zeros(shape, device=device, dtype=torch.int64 if kind == 0 else torch.float32)
+                down = p.mtt_resolution_downsample_rate
+                self.h0, self.w0 = self.gh // down, self.gw // down
+            h0, w0 = self.h0, self.w0
+            self.th, self.tw = h0 * 8, w0 * 8
+            self.n_out = [p.TASKS.NUM_OUTPUT[t] for t in self.tasks]
+            if mode != "invpt":
+                self.zi = S(B * 4 * P, C)
+                self.f1 = S(B * P, C)
+                self.x0 = S(B * h0 * w0, C)
+                self.p1 = [S(B * h0 * w0, C) for _ in range(T)]   # per task: the task chains run on side streams
+                self.back0 = z(B * 4 * P, dims[2])
+                self.back1 = z(B * P, dims[1])
+            else:
+                self.back0 = z(B * 16 * h0 * w0, dims[2])
+                self.back1 = z(B * 4 * h0 * w0, dims[1])
+            self.cat = [S(B * h0 * w0, E + n, zero=True) for n in self.n_out]
+            self.inter = [z(B * h0 * w0, ops.round_up(n, 4)) for n in self.n_out]
+            self.st = []
+            for i in range(3):
+                h, w = h0 * 2 ** i, w0 * 2 ** i
+                Ci = dims[i]
+                s = SimpleNamespace(h=h, w=w, C=Ci)
+                s.kvs = 2 ** (i + 1)
+                s.kh, s.kw = -(-h // s.kvs), -(-w // s.kvs)
+                s.Lq = T * (h // 2) * (w // 2)
+                s.Tk = T * s.kh * s.kw
+                s.xj = z(B * T * h * w, Ci)
+                s.xn32 = z(B * T * h * w, Ci)
+                s.qin = S(B * s.Lq, Ci)
+                s.kvin = S(B * s.Tk, Ci)
+                s.q32, s.k32, s.v32 = z(B * s.Lq, Ci), z(B * s.Tk, Ci), z(B * s.Tk, Ci)
+                s.score = z(B, 2, s.Lq, s.Tk) if i < 2 else None
+                s.ao = S(B * s.Lq, Ci)
+                s.a32 = z(B * s.Lq, Ci)
+                s.ws_mlp = ops.workspace(ops.workspace_bytes(ops._L.OP_LN_MLP_RESIDUAL, rows=B * T * h * w, Cdim=Ci,
+                                                             hidden=4 * Ci, nsplit=ns), device)
+                if i == 0:
+                    s.ln32 = z(T * B * h * w, Ci)
+                else:
+                    s.ln = S(T * B * h * w, Ci)
+                    s.rc32 = [z(B * h * w, dims[0]) for _ in range(T)]
+                    s.ue0 = [S(B * h * w, dims[i - 1]) for _ in range(T)]
+                    s.ue1 = [S(B * h * w, Ci) for _ in range(T)]
+                self.st.append(s)
+            tt = B * self.th * self.tw
+            self.mss = [S(tt, dims[0]) for _ in range(T)]
+            self.hm = [S(tt, dims[0]) for _ in range(T)]
+            if mode in ("decoder", "invpt"):
+                self.hm32 = z(tt, dims[0])                       # one NHWC fp32 staging map, reused per task
+                self.x_dict = {t: z(B, dims[0], self.th, self.tw) for t in self.tasks}
+                self.out = {"x_dict": self.x_dict}
+                if mode == "decoder":
+                    self.inter_nchw = {t: z(B, n, h0, w0) for t, n in zip(self.tasks, self.n_out)}
+                    self.out["inter_pred"] = self.inter_nchw
+                self.out_inter = None
+                return
+            self.pred = [z(tt, ops.round_up(n, 4)) for n in self.n_out]
+            oh, ow = self.img
+            if not self.postproc:
+                self.out = {t: z(B, n, oh, ow) for t, n in zip(self.tasks, self.n_out)}
+                self.out_inter = {t: z(B, n, oh, ow) for t, n in zip(self.tasks, self.n_out)}
+            else:
+                self.out, self.out_inter = {}, None
+                for t in self.tasks:
+                    kind = ops.POSTPROC_KIND[t]
+                    shape = {0: (B, oh, ow), 1: (B, oh, ow), 2: (B, oh, ow), 3: (B, oh, ow, 3), 4: (B, oh, ow, 1)}[kind]
+                    self.out[t] = torch.zeros(shape, device=device, dtype=torch.int64 if kind == 0 else torch.float32)
 
-    # ------------------------------------------------------------------------------------------
-    def _vit_block(self, w):
-        B, N = self.B, self.N
-        ops.layernorm(self.xs, w.n1w, w.n1b, w.eps, out_split=self.xn)                     # vit.py:213
-        ops.gemm(self.xn, w.qkv, bias=w.qkv_b, out_split=self.qkv)                         # :186
-        ops.attention(self.qkv, self.ao, B=B, N=N, H=self.H, scale=64 ** -0.5)             # :189-193
-        ops.gemm(self.ao, w.proj, bias=w.proj_b, residual=self.xs, out_f32=self.xs)        # :194,:213
-        ops.layernorm(self.xs, w.n2w, w.n2b, w.eps, out_split=self.xn)                     # :214
-        ops.gemm(self.xn, w.fc1, bias=w.fc1_b, act=ops.ACT_GELU, out_split=self.hid)
-        ops.gemm(self.hid, w.fc2, bias=w.fc2_b, residual=self.xs, out_f32=self.xs)
+    def _pack(self):
+        dev, ns = self.dev, self.ns
+        self.Wv = _pack_vit(self.bb, dev, ns) if self.bb is not None else None
+        self.Wd = _pack_decoder(self.dec, self.tasks, dev, ns) if self.dec is not None else None
+        self.Wi = _pack_invpt(self.inv, self.tasks, dev, ns) if self.inv is not None else None
+        self.Wh = None
+        if self.heads is not None:
+            self.Wh = [_cached(self.heads[t], ("pack", dev, ns), lambda t=t: (
+                ops.pack_weight(_f32(self.heads[t].linear_pred.weight, dev).reshape(
+                    self.heads[t].linear_pred.weight.shape[0], -1), ns), _f32(self.heads[t].linear_pred.bias, dev)))
+                for t in self.tasks]
+        self.version = self._ver()
+
+    def _ver(self):
+        return sum(_version(m) for m in (self.bb, self.dec if self.dec is not None else self.inv, self.heads)
+                   if m is not None)
+
+    @property
+    def serial(self):
+        return self.streams.serial
+
+    @serial.setter
+    def serial(self, v):
+        self.streams.serial = bool(v)
 
     def _par(self, fn):
         """Run fn(k) for every task k, each on its own side stream forked from / joined to the current
         stream (the per-task chains are independent and individually too small to fill 148 SMs)."""
-        T = self.T
-        if self.dev.type != "cuda" or getattr(self, "serial", False):   # serial: one stream (per-kernel timing)
-            for k in range(T):
-                fn(k)
-            return
-        if self.side is None:
-            self.side = [torch.cuda.Stream(device=self.dev) for _ in range(T)]
-        main = torch.cuda.current_stream()
-        for k in range(T):
-            self.side[k].wait_stream(main)
-            with torch.cuda.stream(self.side[k]):
-                fn(k)
-        for k in range(T):
-            main.wait_stream(self.side[k])
+        self.streams.par([lambda k=k: fn(k) for k in range(self.T)])
+
+    # ------------------------------------------------------------------------------------------ inputs of the
+    # module-boundary modes (copies into the plan's buffers; the fused modes never run these)
+    def load_features(self, x_list):
+        """TransformerDecoder.forward input: 4 x [B,P,C] token maps (transformer_decoder.py:74-83)."""
+        B, P, C = self.B, self.P, self.C
+        for which in (0, 1):
+            self.xs.view(B, self.N, C)[:, 1:].copy_(x_list[which])
+            self._scale_embed(which)
+        self.xfin.view(B, P, C).copy_(x_list[3])
+
+    def load_invpt_inputs(self, x_dict, inter_pred, back_fea):
+        """InvPT.forward inputs (invpt.py:502-513): NCHW task features + preliminary predictions -> the `cat`
+        operands of mix_proj; back_fea[0], [1] -> the NHWC skip maps of stages 2 and 1."""
+        B, E = self.B, self.E
+        for k, t in enumerate(self.tasks):
+            ops.nchw_to_nhwc_split(x_dict[t].contiguous(), self.cat[k])
+            ops.nchw_to_nhwc_split(inter_pred[t].contiguous(), self.cat[k], col_offset=E)
+        for buf, src in ((self.back0, back_fea[0]), (self.back1, back_fea[1])):
+            b_, c_, h_, w_ = src.shape
+            buf.view(b_, h_, w_, c_).copy_(src.permute(0, 2, 3, 1))
+
+    # ------------------------------------------------------------------------------------------
+    def _vit_block(self, w):
+        B, N = self.B, self.N
+        ops.ln_qkv(self.xs, w.n1w, w.n1b, w.eps, w.qkv, w.qkv_b, self.qkv, self.ws_qkv)     # vit.py:213, :186
+        ops.attention(self.qkv, self.ao, B=B, N=N, H=self.H, scale=64 ** -0.5)             # :189-193
+        ops.proj_residual(self.ao, w.proj, w.proj_b, self.xs)                              # :194,:213
+        ops.ln_mlp_residual(self.xs, w.n2w, w.n2b, w.eps, w.fc1, w.fc1_b, w.fc2, w.fc2_b, self.ws_mlp)  # :214
+
+    def _scale_embed(self, which):
+        B, N, P, C, W = self.B, self.N, self.P, self.C, self.Wd
+        if which == 0:      # scale_embed[0]: ConvTranspose2d as zero-insert + flipped 3x3 conv
+            ops.zero_insert(self.xs, self.zi, B=B, h=self.gh, w=self.gw, Cdim=C, src_group=N, src_offset=1)
+            ops.gemm(self.zi, W.se0, N=self.dims[2], K=C, bias=W.se0_b, out_f32=self.back0,
+                     conv=(B, 2 * self.gh, 2 * self.gw, 3, 1))                             # transformer_decoder.py:63,80
+        elif which == 1:    # scale_embed[1]
+            ops.split_rows(self.xs, self.f1, rows=B * P, cols=C, in_group=P, src_group=N, src_offset=1)
+            ops.gemm(self.f1, W.se1, N=self.dims[1], K=C, bias=W.se1_b, out_f32=self.back1,
+                     conv=(B, self.gh, self.gw, 3, 1))                                     # :64,:80
+        # which == 2: scale_embed[2]'s output is never consumed by the reference
 
     def _stage(self, i):
         """InvPTStage + InvPTBlock + multi-scale aggregation for stage i (invpt.py:400-417,290-312,522-539)."""
-        B, T, W = self.B, self.T, self.W
+        B, T, W = self.B, self.T, self.Wi
         s, sw = self.st[i], W.stages[i]
         h, w, Ci = s.h, s.w, s.C
         hw = h * w
@@ -444,8 +603,7 @@ class _Plan:
                 wa, ba, wb, bb_ = sw.up[k]
                 ops.bilinear(sp.xj, sp.xj.stride(0), B, sp.h, sp.w, sp.C, h, w, out_split=s.ue0[k],
                              in_batch_rows=T * sp.h * sp.w, in_row_offset=k * sp.h * sp.w)            # UpEmbed :32
-                ops.gemm(s.ue0[k], wa, N=Ci, K=sp.C, bias=ba, act=ops.ACT_RELU, out_split=s.ue1[k],
-                         conv=(B, h, w, 3, 2))                                                        # :33-35
+                ops.conv3x3_bn_act(s.ue0[k], wa, ba, sp.C, Ci, ops.ACT_RELU, B=B, H=h, W=w, dil=2, mid=s.ue1[k])  # :33-35
                 ops.gemm(s.ue1[k], wb, N=Ci, K=Ci, bias=bb_, act=ops.ACT_RELU, residual=skip, res_row_mod=B * hw,
                          out_f32=s.xj, regroup=(hw, T * hw, k * hw), conv=(B, h, w, 3, 2))            # :36-38,:406-411
             self._par(up_embed)
@@ -465,9 +623,7 @@ class _Plan:
         self._par(lambda k: ops.bilinear(                                                              # :299-306
             s.a32, s.a32.stride(0), B, h // 2, w // 2, Ci, h, w, out_f32=s.xj, accumulate=True,
             in_batch_rows=T * qhw, in_row_offset=k * qhw, out_batch_rows=T * hw, out_row_offset=k * hw))
-        ops.layernorm(s.xj, sw.n2w, sw.n2b, sw.eps, out_split=s.xn)                                    # :307
-        ops.gemm(s.xn, sw.fc1, bias=sw.fc1_b, act=ops.ACT_GELU, out_split=s.hid)
-        ops.gemm(s.hid, sw.fc2, bias=sw.fc2_b, residual=s.xj, out_f32=s.xj)
+        ops.ln_mlp_residual(s.xj, sw.n2w, sw.n2b, sw.eps, sw.fc1, sw.fc1_b, sw.fc2, sw.fc2_b, s.ws_mlp)  # :307-308
         # ---- joint-channel LayerNorm over all tasks, per-task slices to the common resolution
         ops.layernorm_seg(s.xj, sw.nmw, sw.nmb, sw.nmeps, rows=B * hw, cols=Ci, S=T, in_group=hw, src_group=T * hw,
                           seg_stride=hw, out_f32=s.ln32 if i == 0 else None,
@@ -486,17 +642,24 @@ class _Plan:
                                    (s1_.rc32[k], s1_.h, s1_.w, 0, 0),
                                    (s.rc32[k], h, w, 0, 0)],
                                   self.mss[k], B=B, Cdim=d0, H2=self.th, W2=self.tw)                   # :537-539
-                self._head(k)
+                if self.mode in ("full", "postproc"):
+                    self._head(k)
         self._par(aggregate)
+        if i == 2 and self.mode in ("decoder", "invpt"):
+            for k, t in enumerate(self.tasks):     # mt_proj -> NCHW x_dict (one fp32 staging map: sequential)
+                tw = W.tasks[k]
+                ops.gemm(self.mss[k], tw.mt, N=d0, K=d0, bias=tw.mt_b, act=ops.ACT_RELU, out_f32=self.hm32,
+                         conv=(B, self.th, self.tw, 3, 1))                                             # :541-543
+                ops.nhwc_to_nchw(self.hm32, d0, B, d0, self.th, self.tw, self.x_dict[t])
 
     def _head(self, k):
-        B, W = self.B, self.W
-        tw = W.tasks[k]
+        B = self.B
+        tw = self.Wi.tasks[k]
+        lp, lp_b = self.Wh[k]
         d0 = self.dims[0]
-        ops.gemm(self.mss[k], tw.mt, N=d0, K=d0, bias=tw.mt_b, act=ops.ACT_RELU, out_split=self.hm[k],
-                 conv=(B, self.th, self.tw, 3, 1))                                                     # invpt.py:541-543
         n = self.n_out[k]
-        ops.gemm(self.hm[k], tw.lp, bias=tw.lp_b, out_f32=self.pred[k][:, :n], N=n)                    # MLPHead
+        ops.conv3x3_bn_act(self.mss[k], tw.mt, tw.mt_b, d0, d0, ops.ACT_RELU, B=B, H=self.th, W=self.tw, mid=self.hm[k],
+                           w_head=lp, b_head=lp_b, n_out=n, out_f32=self.pred[k][:, :n])               # invpt.py:541-543, MLPHead
         if self.postproc:
             ops.bilinear_postproc(self.pred[k], self.pred[k].stride(0), B, self.th, self.tw, n, self.img[0],
                                   self.img[1], ops.POSTPROC_KIND[self.tasks[k]], self.out[self.tasks[k]])
@@ -504,9 +667,8 @@ class _Plan:
             ops.bilinear(self.pred[k], self.pred[k].stride(0), B, self.th, self.tw, n, self.img[0], self.img[1],
                          out_nchw=self.out[self.tasks[k]])                                             # transformer_net.py:35
 
-    def _launch(self, img):
-        B, N, P, C, T, W = self.B, self.N, self.P, self.C, self.T, self.W
-        h0, w0, E = self.h0, self.w0, self.E
+    def _launch_backbone(self, img):
+        B, N, P, C, W = self.B, self.N, self.P, self.C, self.Wv
         ops.im2col_patch(img, self.patch, self.cols)
         ops.gemm(self.cols, W.pe_w, bias=W.pe_b, residual=W.pos, res_row_mod=P, out_f32=self.xs,
                  regroup=(P, N, 1))                                                                    # vit.py:333,339
@@ -515,58 +677,85 @@ class _Plan:
             self._vit_block(w)
             if idx + 1 in self.select:
                 which = self.select.index(idx + 1)
-                if which == 0:      # scale_embed[0]: ConvTranspose2d as zero-insert + flipped 3x3 conv
-                    ops.zero_insert(self.xs, self.zi, B=B, h=self.gh, w=self.gw, Cdim=C, src_group=N, src_offset=1)
-                    ops.gemm(self.zi, W.se0, N=self.dims[2], K=C, bias=W.se0_b, out_f32=self.back0,
-                             conv=(B, 2 * self.gh, 2 * self.gw, 3, 1))                                 # transformer_decoder.py:63,80
-                elif which == 1:    # scale_embed[1]
-                    ops.split_rows(self.xs, self.f1, rows=B * P, cols=C, in_group=P, src_group=N, src_offset=1)
-                    ops.gemm(self.f1, W.se1, N=self.dims[1], K=C, bias=W.se1_b, out_f32=self.back1,
-                             conv=(B, self.gh, self.gw, 3, 1))                                         # :64,:80
-                # which == 2: scale_embed[2]'s output is never consumed by the reference
+                if self.mode == "backbone":
+                    self.sel[which].copy_(self.xs.view(B, N, C)[:, 1:])                                # :345-346
+                else:
+                    self._scale_embed(which)
         ops.layernorm_seg(self.xs, W.nw, W.nb, W.neps, rows=B * P, cols=C, S=1, in_group=P, src_group=N,
                           src_offset=1, out_f32=self.xfin)                                             # vit.py:348-349
+
+    def _launch_decoder_front(self):
+        B, C, T, W = self.B, self.C, self.T, self.Wd
+        h0, w0, E = self.h0, self.w0, self.E
         ops.bilinear(self.xfin, C, B, self.gh, self.gw, C, h0, w0, out_split=self.x0)                  # transformer_decoder.py:85-86
-        s0 = self.st[0]
-        hw0 = h0 * w0
+
         def prelim(k):
             tw = W.tasks[k]
             n = self.n_out[k]
-            ops.gemm(self.x0, tw.pd0, N=C, K=C, bias=tw.pd0_b, act=ops.ACT_RELU, out_split=self.p1[k],
-                     conv=(B, h0, w0, 3, 1))                                                           # ConvBlock 1
+            ops.conv3x3_bn_act(self.x0, tw.pd0, tw.pd0_b, C, C, ops.ACT_RELU, B=B, H=h0, W=w0, mid=self.p1[k])  # ConvBlock 1
             ops.gemm(self.p1[k], tw.pd1, N=E, K=C, bias=tw.pd1_b, act=ops.ACT_RELU, out_split=self.cat[k],
                      conv=(B, h0, w0, 3, 1))                                                           # ConvBlock 2
             ops.gemm(self.cat[k], tw.ih, K=E, bias=tw.ih_b, out_f32=self.inter[k][:, :n], N=n,
                      out_split=self.cat[k], out_col_offset=E)                                          # :94; invpt.py:511
-            ops.gemm(self.cat[k], tw.mix, bias=tw.mix_b, out_f32=s0.xj, regroup=(hw0, T * hw0, k * hw0))  # invpt.py:512
-            if not self.postproc:
+            if self.mode == "full":
                 ops.bilinear(self.inter[k], self.inter[k].stride(0), B, h0, w0, n, self.img[0], self.img[1],
                              out_nchw=self.out_inter[self.tasks[k]])                                   # transformer_net.py:36
+            elif self.mode == "decoder":
+                ops.nhwc_to_nchw(self.inter[k], self.inter[k].stride(0), B, n, h0, w0, self.inter_nchw[self.tasks[k]])
         self._par(prelim)
+
+    def _launch_invpt(self):
+        B, T = self.B, self.T
+        s0 = self.st[0]
+        hw0 = self.h0 * self.w0
+        self._par(lambda k: ops.gemm(self.cat[k], self.Wi.tasks[k].mix, bias=self.Wi.tasks[k].mix_b, out_f32=s0.xj,
+                                     regroup=(hw0, T * hw0, k * hw0)))                                 # invpt.py:512
         for i in range(3):
             self._stage(i)
 
+    def _launch(self, img):
+        if self.mode in ("full", "postproc", "backbone"):
+            self._launch_backbone(img)
+        if self.mode in ("full", "postproc", "decoder"):
+            self._launch_decoder_front()
+        if self.mode != "backbone":
+            self._launch_invpt()
+
     def run(self, x, graph=True):
-        if tuple(x.shape[1:]) != (3, *self.img) or x.dtype != torch.float32:
-            raise ValueError(f"expected fp32 input [B,3,{self.img[0]},{self.img[1]}], got {tuple(x.shape)} {x.dtype}")
-        if not graph:
-            self._launch(x.contiguous())
-        else:
-            if self.static_in is None:
-                self.static_in = torch.empty_like(x, memory_format=torch.contiguous_format)
-            self.static_in.copy_(x, non_blocking=True)
-            if self.graph is None:
-                self._launch(self.static_in)
-                torch.cuda.synchronize()
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
+        with _dev_ctx(self.dev):
+            if self._ver() != self.version:      # parameters changed in place: re-pack, re-capture
+                self._pack()
+                self.graph = None
+            if self.mode in ("decoder", "invpt"):
+                self._launch(None)
+                return self.out
+            if tuple(x.shape[1:]) != (3, *self.img) or x.dtype != torch.float32:
+                raise ValueError(f"expected fp32 input [B,3,{self.img[0]},{self.img[1]}], got {tuple(x.shape)} {x.dtype}")
+            if not graph:
+                self._launch(x.contiguous())
+            else:
+                if self.static_in is None:
+                    self.static_in = torch.empty_like(x, memory_format=torch.contiguous_format)
+                self.static_in.copy_(x, non_blocking=True)
+                if self.graph is None:
                     self._launch(self.static_in)
-                self.graph = g
-            self.graph.replay()
-        out = dict(self.out)
-        if self.out_inter is not None:
-            out["inter_preds"] = dict(self.out_inter)
-        return out
+                    torch.cuda.synchronize()
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        self._launch(self.static_in)
+                    self.graph = g
+                self.graph.replay()
+            out = dict(self.out)
+            if self.mode == "full":
+                out["inter_preds"] = dict(self.out_inter)
+            return out
+
+    def launches_per_forward(self):
+        with _dev_ctx(self.dev):
+            n0 = ops.launch_count()
+            self._launch(self.static_in if self.static_in is not None else
+                         torch.zeros(self.B, 3, *self.img, device=self.dev))
+            return ops.launch_count() - n0
 
 
 def build_from_config(cfg, nsplit=PARITY, use_graph=True):
@@ -585,8 +774,9 @@ def build_from_config(cfg, nsplit=PARITY, use_graph=True):
 
 
 def accelerate(ref_model, nsplit=PARITY, use_graph=True):
-    """Drop-in: build the fused InvPT from a REFERENCE TransformerNet instance (InvPT/models/transformer_net.py),
-    sharing its parameters through an exact `load_state_dict(strict=True)`."""
+    """Drop-in: build the fused InvPT from a REFERENCE TransformerNet instance (InvPT/models/transformer_net.py).
+    Parameters and BatchNorm statistics are COPIED by an exact `load_state_dict(strict=True)`; later in-place updates
+    of `ref_model` are not seen (load again; plans re-pack by themselves when parameter versions change)."""
     p = ref_model.multi_task_decoder.p
     bb = ref_model.backbone
     mine_bb = VisionTransformer(list(bb.select_list), img_size=tuple(bb.patch_embed.img_size),

@@ -51,6 +51,11 @@ OP_LN_QKV, OP_ATTN_FWD, OP_PROJ_RESIDUAL, OP_LN_MLP_RESIDUAL, OP_CHAN_PROMPT_LOG
 OP_GATED_CONV1X1, OP_CONV3X3_BN_ACT, OP_BILINEAR_UP, OP_INVPT_ATTN, OP_LAYERNORM = 6, 7, 8, 9, 10
 
 
+class ProfileRec(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32), ("ms", C.c_float),
+                ("flops", C.c_double)]
+
+
 class BilinearSrc(C.Structure):
     _fields_ = [("in_", C.c_void_p), ("ld_in", C.c_int64), ("h", C.c_int32), ("w", C.c_int32),
                 ("batch_rows", C.c_int64), ("row_offset", C.c_int64)]
@@ -74,6 +79,8 @@ SYMBOLS = {
     "mtt_device_check": (C.c_int, []),
     "mtt_launch_count": (C.c_int64, []),
     "mtt_launch_count_reset": (None, []),
+    "mtt_profile_begin": (C.c_int, []),
+    "mtt_profile_end": (C.c_int, [C.POINTER(ProfileRec), _i32, C.POINTER(C.c_int32)]),
     "mtt_split_f32": (C.c_int, [_vp, _i64, _vp, _vp, _i64, _i64, _i32, _i32, _vp]),
     "mtt_layernorm": (C.c_int, [_vp, _i64, _vp, _vp, _f32, _vp, _i64, _vp, _vp, _i64, _i64, _i32, _vp]),
     "mtt_gemm": (C.c_int, [C.POINTER(GemmDesc), _vp]),

@@ -158,6 +158,20 @@ def set_attention_variant(v):
     _L.load().mtt_set_attention_variant(int(v))
 
 
+def profile_begin():
+    """Start per-launch timing of the tensor-core kernels (see mtt_profile_begin)."""
+    _L.check(_L.load().mtt_profile_begin(), "mtt_profile_begin")
+
+
+def profile_end(max_recs=4096):
+    """Synchronise and return [(kind, M, N, K, ms, flops)] for every mtt_gemm (kind 0) / mtt_attention (kind 1) launch
+    since profile_begin()."""
+    arr = (_L.ProfileRec * max_recs)()
+    n = C.c_int32(0)
+    _L.check(_L.load().mtt_profile_end(arr, max_recs, C.byref(n)), "mtt_profile_end")
+    return [(r.kind, r.M, r.N, r.K, r.ms, r.flops) for r in arr[:min(n.value, max_recs)]]
+
+
 def launch_count(reset=False):
     lib = _L.load()
     n = lib.mtt_launch_count()
@@ -459,11 +473,14 @@ def pack_conv_weight(w, bias, bn, nsplit, transposed=False):
     return out, bias_out
 
 
-def nchw_to_nhwc_split(x, out):
-    """x fp32 NCHW [B,C,H,W] -> out Split [B*H*W, C] (module-boundary forwards take NCHW like the reference)."""
+def nchw_to_nhwc_split(x, out, col_offset=0):
+    """x fp32 NCHW [B,C,H,W] -> columns [col_offset, col_offset + C) of out Split [B*H*W, >= C] (module-boundary
+    forwards take NCHW like the reference)."""
     assert x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 4
     B, Cd, H, W = x.shape
-    rc = _L.load().mtt_nchw_to_nhwc_split(_ptr(x), B, Cd, H, W, _ptr(out.hi), _ptr(out.lo), out.ld, _stream())
+    hi = C.c_void_p(out.hi.data_ptr() + 2 * col_offset)
+    lo = C.c_void_p(out.lo.data_ptr() + 2 * col_offset) if out.nsplit == 2 else C.c_void_p(0)
+    rc = _L.load().mtt_nchw_to_nhwc_split(_ptr(x), B, Cd, H, W, hi, lo, out.ld, _stream())
     _L.check(rc, "mtt_nchw_to_nhwc_split")
 
 

@@ -1,9 +1,6 @@
-"""Weight pre-packing: fp32 parameters -> split-bf16 operand planes in the layouts the kernels read.
-
-Packing is parameter preprocessing (done once per parameter version, outside the timed hot path);
-it uses torch only for permutes / BatchNorm folding of the parameters themselves and the library's
-mtt_split_f32 for the cast.
-"""
+"""Weight pre-packing helpers kept for the kernel tests and micro-benchmarks: thin wrappers over the C entry points
+mtt_pack_weight / mtt_pack_conv_weight (include/mtt_b200.h), plus the eval-BatchNorm folding identity in plain torch
+(tests/test_pack_identities.py checks the C packing against it). The models pack through ops.pack_* directly."""
 import torch
 
 from . import ops
@@ -11,17 +8,12 @@ from . import ops
 
 def pack_linear_weight(w, nsplit):
     """nn.Linear / 1x1 conv weight [N, K] (or [N, K, 1, 1]) -> Split [N, K] (K-major, ld multiple of 8)."""
-    w2 = w.detach().reshape(w.shape[0], -1).float().contiguous()
-    return ops.split_f32(w2, nsplit)
+    return ops.pack_weight(w.detach().reshape(w.shape[0], -1).float().contiguous(), nsplit)
 
 
 def pack_conv_weight(w, nsplit):
     """Conv2d weight [N, Cin, kh, kw] -> Split [N, kh*kw*cin_pad], tap-major, Cin zero-padded to 64."""
-    N, Cin, kh, kw = w.shape
-    cin_pad = ops.round_up(Cin, 64)
-    wt = torch.zeros(N, kh * kw, cin_pad, dtype=torch.float32, device=w.device)
-    wt[:, :, :Cin] = w.detach().float().permute(0, 2, 3, 1).reshape(N, kh * kw, Cin)
-    return ops.split_f32(wt.reshape(N, kh * kw * cin_pad), nsplit)
+    return ops.pack_conv_weight(w.detach().float().contiguous(), None, None, nsplit)[0]
 
 
 def fold_bn(w, b, bn):

@@ -171,7 +171,11 @@ def forward(sd, cfg, img, taps=None):
             pre = f"{D}preliminary_decoder.{t}.{j}."
             y = F.relu(_bn(_conv(y, sd, pre + "conv", padding=1), sd, pre + "bn1"))
         inter[t] = _conv(y, sd, f"{D}intermediate_head.{t}")                                             # :94
+        if taps is not None:
+            taps[f"ms_feat.{t}"], taps[f"inter.{t}"] = y, inter[t]
         x_list.append(_conv(torch.cat([y, inter[t]], 1), sd, f"{D}invpt.mix_proj.{t}.0"))                # invpt.py:509-513
+    if taps is not None:
+        taps["back0"], taps["back1"] = back
     # ---- InvPT.forward (invpt.py:516-543)
     th, tw = h0 * 8, w0 * 8
     ms = {t: 0 for t in tasks}
@@ -198,6 +202,8 @@ def forward(sd, cfg, img, taps=None):
     for t in tasks:
         pre = f"{D}invpt.mt_proj.{t}."
         y = F.relu(_bn(_conv(ms[t], sd, pre + "0", padding=1), sd, pre + "1"))                           # :541-543
+        if taps is not None:
+            taps[f"x_dict.{t}"] = y
         y = _conv(y, sd, f"heads.{t}.linear_pred")                                                       # MLPHead
         out[t] = F.interpolate(y, img.shape[-2:], mode="bilinear")                                       # transformer_net.py:35
     out["inter_preds"] = {t: F.interpolate(v, img.shape[-2:], mode="bilinear") for t, v in inter.items()}

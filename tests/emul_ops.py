@@ -319,9 +319,9 @@ def install(mp):
         wt[:, :, :Cin] = w.permute(0, 2, 3, 1).reshape(N, k * k, Cin)
         return ops.split_f32(wt.reshape(N, k * k * cin_pad), nsplit), b0.contiguous()
 
-    def nchw_to_nhwc_split(x, out):
+    def nchw_to_nhwc_split(x, out, col_offset=0):
         B, Cd, H, W = x.shape
-        _wsplit(out, x.permute(0, 2, 3, 1).reshape(B * H * W, Cd))
+        _wsplit(out, x.permute(0, 2, 3, 1).reshape(B * H * W, Cd), col_offset)
 
     def nhwc_to_nchw(x, ld_in, B, Cd, H, W, out):
         out.copy_(x[:B * H * W, :Cd].reshape(B, H, W, Cd).permute(0, 3, 1, 2))

@@ -19,10 +19,13 @@ WORKER = textwrap.dedent("""
     assert t == 11.0, t
     a, b = D.shard_batch(7, rank, world)
     assert (a, b) == ((0, 4) if rank == 0 else (4, 7))
-    out = {"semseg": torch.full((2, 3), float(rank)), "depth": torch.full((2, 1), 10.0 + rank)}
+    # the shards shard_batch actually produces: 7 images -> 4 + 3 (uneven)
+    n = b - a
+    out = {"semseg": torch.arange(a, b, dtype=torch.float32)[:, None].repeat(1, 3), "depth": torch.full((n, 1), 10.0 + rank)}
     g = D.gather_outputs(out, world)
     if rank == 0:
-        assert g["semseg"].shape == (4, 3) and g["semseg"][2:].eq(1).all() and g["depth"][:2].eq(10).all()
+        assert g["semseg"].shape == (7, 3) and torch.equal(g["semseg"][:, 0], torch.arange(7.0))
+        assert g["depth"].shape == (7, 1) and g["depth"][:4].eq(10).all() and g["depth"][4:].eq(11).all()
         print("OK")
     D.teardown(world)
 """) % ROOT

@@ -165,7 +165,7 @@ def test_conv(cuda_dev, ksize, dil, nsplit, gemm_variant):
         assert e < TOL[nsplit], f"conv {B,H,W,Cin,Cout} k{ksize} d{dil}: rel err {e}"
 
 
-@pytest.mark.parametrize("variant", [0], ids=["default"])
+@pytest.mark.parametrize("variant", [0, 5], ids=["default", "round1_softmax"])
 @pytest.mark.parametrize("nsplit", [2, 1])
 @pytest.mark.parametrize("B,H,N,T,qscale", [(2, 3, 300, 4, 1.5), (1, 2, 1029, 5, 1.5), (1, 1, 128, 0, 1.5),
                                             (2, 2, 65, 2, 1.5), (1, 1, 64, 1, 1.5), (1, 2, 40, 3, 1.5),

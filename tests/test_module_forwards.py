@@ -66,6 +66,58 @@ def _run_cases(dev, tol):
     return out
 
 
+def _run_invpt_cases(dev, tol):
+    import mtt_b200  # noqa: F401
+    from mtt_b200 import invpt as IP
+    from oracle import invpt_ref as IPR
+
+    cfg = configs.invpt("ip_tiny")
+    sd = IPR.init_state_dict(cfg, seed=5)
+    m = IP.build_from_config(cfg, nsplit=2, use_graph=False).eval()
+    m.load_state_dict(sd, strict=True)
+    m = m.to(dev)
+    x = torch.randn(2, 3, *cfg["img_size"], generator=torch.Generator().manual_seed(23))
+    taps = {}
+    with torch.no_grad():
+        ref = IPR.forward(sd, cfg, x, taps=taps)
+        feats_ref = IPR.vit_forward(sd, cfg, x)
+        # ---- VisionTransformer.forward (vit.py:332-361)
+        last, feats = m.backbone(x.to(dev))
+        assert len(feats) == 4 and feats[-1].shape == last.shape
+        for a, b in zip(feats, feats_ref):
+            assert a.shape == b.shape and _rel(a, b) < tol, "vit features"
+        # ---- TransformerDecoder.forward on the oracle's features (transformer_decoder.py:69-98)
+        x_dict, inter = m.multi_task_decoder([f.to(dev) for f in feats_ref])
+        for t in cfg["tasks"]:
+            assert _rel(x_dict[t], taps[f"x_dict.{t}"]) < tol, ("x_dict", t)
+            assert _rel(inter[t], taps[f"inter.{t}"]) < tol, ("inter_pred", t)
+            # ---- MLPHead.forward + the wrapper's resize reproduce the model output
+            y = F.interpolate(m.heads[t](x_dict[t]).cpu(), x.shape[-2:], mode="bilinear")
+            assert _rel(y, ref[t]) < tol, ("head", t)
+        # ---- InvPT.forward on the oracle's intermediate tensors (invpt.py:502-544)
+        xd = m.multi_task_decoder.invpt({t: taps[f"ms_feat.{t}"].to(dev) for t in cfg["tasks"]},
+                                       {t: taps[f"inter.{t}"].to(dev) for t in cfg["tasks"]},
+                                       [taps["back0"].to(dev), taps["back1"].to(dev), None, None])
+        for t in cfg["tasks"]:
+            assert _rel(xd[t], taps[f"x_dict.{t}"]) < tol, ("invpt", t)
+
+
+def test_invpt_module_forwards_emulated(monkeypatch):
+    import mtt_b200  # noqa: F401
+    from mtt_b200 import taskprompter as TP, invpt as IP
+    import emul_ops
+
+    emul_ops.install(monkeypatch)
+    monkeypatch.setattr(TP, "_check_input", lambda mod, x: None)
+    monkeypatch.setattr(IP, "_check_input", lambda mod, x: None)
+    _run_invpt_cases(torch.device("cpu"), 3e-4)
+
+
+@pytest.mark.gpu
+def test_invpt_module_forwards_gpu(cuda_dev):
+    _run_invpt_cases(cuda_dev, 3e-4)
+
+
 def test_module_forwards_emulated(monkeypatch):
     import mtt_b200  # noqa: F401
     from mtt_b200 import taskprompter as TP
