@@ -124,6 +124,10 @@ typedef struct {
 } mtt_gemm_desc;
 
 int mtt_gemm(const mtt_gemm_desc* d, mtt_stream_t stream);
+/* `count` (<= 12) problems that differ ONLY in their pointers (operands, bias, residual, outputs) as one persistent
+ * launch: the T per-task 1x1 / 3x3 convs of a decoder level (TP taskprompter.py:447,:468,:362 for every task) are 96
+ * tiles each -- less than one wave of 148 SMs -- and run as T x 96 tiles here. Same function as `count` mtt_gemm calls. */
+int mtt_gemm_grouped(const mtt_gemm_desc* d, int32_t count, mtt_stream_t stream);
 /* Kernel variant used by mtt_gemm: 0 = automatic (default; also env MTT_GEMM_VARIANT), 1 = single-CTA
  * 128x128 tiles, 2 = CTA pair (tcgen05 cta_group::2) 256x256 tiles, 3 = CTA pair 256x128 tiles.
  * All variants compute the same function; this is a tuning / testing knob. */
@@ -176,14 +180,15 @@ int mtt_chan_logits(const float* cp, const void* xn_hi, const void* xn_lo, int64
                     int32_t N, int32_t T, int32_t C, int32_t gh, int32_t gw, int32_t nh, int32_t nw,
                     float* out, mtt_stream_t stream);
 
-/* Spatial + channel gating of the patch feature map for one task (TP taskprompter.py:436-446,
- * :452-467): Ys = X*(1 + R[b, c/dh, t, T+pix]), Yc = X*(1 + Rc[b,t,c,window(pix)]), both written as
- * split [B*P, ldy] operands of the 1x1 decode convs. X row (b, pix) is at
- * x + (b*x_group_rows + x_row_offset + pix)*ldx. */
+/* Spatial + channel gating of the patch feature map for `ntasks` consecutive tasks starting at `task`, X read once
+ * (TP taskprompter.py:436-446, :452-467): Ys_t = X*(1 + R[b, c/dh, t, T+pix]), Yc_t = X*(1 + Rc[b,t,c,window(pix)]),
+ * written as split [B*P, ldy] operands of the 1x1 decode convs; task t's planes start (t - task) * task_stride
+ * ELEMENTS after the given pointers. X row (b, pix) is at x + (b*x_group_rows + x_row_offset + pix)*ldx.
+ * C and the head dim must be multiples of 8. */
 int mtt_gate_split(const float* x, int64_t ldx, int64_t x_group_rows, int64_t x_row_offset,
-                   const float* prompt_logits, const float* chan_logits, int32_t task, int32_t B,
+                   const float* prompt_logits, const float* chan_logits, int32_t task, int32_t ntasks, int32_t B,
                    int32_t T, int32_t N, int32_t H, int32_t C, int32_t gh, int32_t gw, int32_t nh,
-                   int32_t nw, void* ys_hi, void* ys_lo, void* yc_hi, void* yc_lo, int64_t ldy,
+                   int32_t nw, void* ys_hi, void* ys_lo, void* yc_hi, void* yc_lo, int64_t ldy, int64_t task_stride,
                    mtt_stream_t stream);
 
 /* Cross-task reweighting (TP taskprompter.py:478-485).
@@ -339,13 +344,22 @@ int mtt_proj_residual(const void* a_hi, const void* a_lo, int64_t lda, const mtt
 int mtt_ln_mlp_residual(float* x, int64_t ldx, const float* gamma, const float* beta, float eps, const mtt_weight* w1,
                         const float* b1, const mtt_weight* w2, const float* b2, const mtt_shape* shape,
                         void* workspace, size_t ws_bytes, mtt_stream_t stream);
-/* Spatial and channel gating of the patch map for one task + the two 1x1 decode convs, written side by side into
- * the `cat` operand of fea_fuse (TP taskprompter.py:436-447, :452-468, :471): columns [0, e) = spatial branch,
- * [chan_col, chan_col + e) = channel branch. x / prompt_logits / chan_logits as in mtt_gate_split. */
+/* Spatial and channel gating of the patch map for ALL `ntasks` tasks of a level + their 2*ntasks 1x1 decode convs,
+ * each task's pair written side by side into its `cat` operand of fea_fuse (TP taskprompter.py:436-447, :452-468,
+ * :471): columns [0, e) = spatial branch, [chan_col, chan_col + e) = channel branch. One gating launch (X read once)
+ * and one grouped GEMM launch of 2*ntasks problems (chunks of 6 tasks). x / prompt_logits / chan_logits as in
+ * mtt_gate_split; workspace: mtt_workspace_bytes(MTT_OP_GATED_CONV1X1) with shape.rows = B*gh*gw, shape.T = ntasks. */
+typedef struct {
+  mtt_weight w_spa;
+  const float* b_spa;
+  mtt_weight w_chan;
+  const float* b_chan;
+  void* cat_hi;
+  void* cat_lo;
+} mtt_gated_task;
 int mtt_gated_conv1x1(const float* x, int64_t ldx, int64_t x_group_rows, int64_t x_row_offset,
-                      const float* prompt_logits, const float* chan_logits, int32_t task, int32_t gh, int32_t gw,
-                      int32_t nh, int32_t nw, const mtt_weight* w_spa, const float* b_spa, const mtt_weight* w_chan,
-                      const float* b_chan, int32_t e, void* cat_hi, void* cat_lo, int64_t ld_cat, int32_t chan_col,
+                      const float* prompt_logits, const float* chan_logits, int32_t ntasks, const mtt_gated_task* tasks,
+                      int32_t gh, int32_t gw, int32_t nh, int32_t nw, int32_t e, int64_t ld_cat, int32_t chan_col,
                       const mtt_shape* shape, void* workspace, size_t ws_bytes, mtt_stream_t stream);
 /* 3x3 conv (stride 1, dilation dil, zero padding) with folded eval BatchNorm + activation on an NHWC split map, and
  * optionally the 1x1 prediction head right behind it (TP taskprompter.py:362 fea_fuse[1..3]; :691-695 ConvHead;
@@ -370,6 +384,46 @@ int mtt_pack_conv_weight(const float* w, const float* bias, const float* bn_gamm
                          const float* bn_mean, const float* bn_var, float bn_eps, int32_t N, int32_t Cin,
                          int32_t ksize, int32_t transposed, int32_t nsplit, void* out_hi, void* out_lo, int64_t ld_out,
                          float* bias_out, float* scale_ws, mtt_stream_t stream);
+
+/* ---- training losses and their gradients w.r.t. the predictions -------------------------------
+ * TP/losses/loss_functions.py: CrossEntropyLoss :15-55 (ignore regions; balanced = binary class balancing :32-41),
+ * BalancedBinaryCrossEntropyLoss :57-87 (fixed pos_weight, or hed != 0: HED-style weight from the labels), L1Loss
+ * :144-176 (normalize = L2-normalise the prediction first; a pixel is valid when EVERY label channel differs from
+ * ignore_index). pred NCHW fp32 [B,C,H,W] (the model's outputs), label fp32 ([B,1,H,W] for cross entropy / BCE,
+ * [B,C,H,W] for L1). loss_out: one float ON THE DEVICE (reduction 'mean' exactly as the reference divides). No host
+ * synchronisation; reductions run in a fixed order (bitwise reproducible). workspace: mtt_loss_workspace_bytes()
+ * bytes, 8-byte aligned; the *_grad calls read the statistics the forward call left there and write
+ * dpred = (*grad_scale) * d loss / d pred (grad_scale: one float on the device, the upstream gradient). */
+size_t mtt_loss_workspace_bytes(void);
+int mtt_loss_cross_entropy(const float* pred, const float* label, int32_t B, int32_t C, int32_t H, int32_t W,
+                           float ignore_index, int32_t balanced, float* loss_out, void* workspace, mtt_stream_t stream);
+int mtt_loss_cross_entropy_grad(const float* pred, const float* label, int32_t B, int32_t C, int32_t H, int32_t W,
+                                float ignore_index, int32_t balanced, const float* grad_scale, float* dpred,
+                                const void* workspace, mtt_stream_t stream);
+int mtt_loss_balanced_bce(const float* pred, const float* label, int64_t n, float ignore_index, float pos_weight,
+                          int32_t hed, float* loss_out, void* workspace, mtt_stream_t stream);
+int mtt_loss_balanced_bce_grad(const float* pred, const float* label, int64_t n, float ignore_index, float pos_weight,
+                               int32_t hed, const float* grad_scale, float* dpred, const void* workspace,
+                               mtt_stream_t stream);
+int mtt_loss_l1(const float* pred, const float* label, int32_t B, int32_t C, int32_t H, int32_t W, float ignore_index,
+                int32_t use_ignore, int32_t normalize, float* loss_out, void* workspace, mtt_stream_t stream);
+int mtt_loss_l1_grad(const float* pred, const float* label, int32_t B, int32_t C, int32_t H, int32_t W,
+                     float ignore_index, int32_t use_ignore, int32_t normalize, const float* grad_scale, float* dpred,
+                     const void* workspace, mtt_stream_t stream);
+
+/* ---- BEV IoU of rotated boxes and NMS ---------------------------------------------------------
+ * Replaces the reference's native extension TP/detection_toolbox/iou3d (iou3d_kernel.cu:253-439, iou3d.cpp:51-202).
+ * Boxes are [x1, y1, x2, y2, ry] fp32 rows on the device. mtt_boxes_bev_pairwise: out[a, b] = overlap area (mode 0,
+ * boxes_overlap_bev_gpu) or rotated IoU (mode 1, boxes_iou_bev_gpu). mtt_nms_bev: boxes must already be sorted by
+ * descending score (iou3d_utils.py:38-42 does that before the call); keep[0 .. *num_keep) = indices of the survivors in
+ * order, greedy suppression of every later box with IoU > thresh (rotated != 0: nms_gpu, else nms_normal_gpu). The
+ * sweep runs on the device: keep (int64) and num_keep (int32) are DEVICE pointers, nothing is copied to the host or
+ * allocated; workspace = mtt_nms_workspace_bytes(n) bytes, 8-byte aligned. */
+int mtt_boxes_bev_pairwise(const float* boxes_a, int32_t num_a, const float* boxes_b, int32_t num_b, int32_t mode,
+                           float* out, mtt_stream_t stream);
+size_t mtt_nms_workspace_bytes(int32_t n);
+int mtt_nms_bev(const float* boxes, int32_t n, float thresh, int32_t rotated, int64_t* keep, int32_t* num_keep,
+                void* workspace, size_t ws_bytes, mtt_stream_t stream);
 
 /* ---- layout changes at the nn.Module boundaries (ConvHead.forward takes / returns NCHW like the reference) ---- */
 int mtt_nchw_to_nhwc_split(const float* in, int32_t B, int32_t C, int32_t H, int32_t W, void* out_hi, void* out_lo,

@@ -96,7 +96,9 @@ __device__ __forceinline__ float softmax_block5(uint32_t taddr, int kn, float sl
 // the exp unit's pipe): packed FFMA2 / FADD2, truncation split through PRMT, both 32-column TMEM loads in flight
 // before the first use, and NO per-element maximum -- an exponent that ran away from the running maximum shows up
 // in the row sum (any p > 2^kA5LazyLog2 makes sum exceed it), which is all the caller needs to trigger its redo path.
-template <bool FULL, int NSPLIT>
+// POLY: every fourth pair takes its exponentials from ex2_poly2 (FMA pipe) instead of MUFU.EX2: the exp unit
+// (16 results per clock per SM) is the busiest pipe of the softmax phase when both resident CTAs are in it.
+template <bool FULL, int NSPLIT, bool POLY>
 __device__ __forceinline__ float softmax_block6(uint32_t taddr, int kn, float sl2, float mb, uint32_t (&ph)[32],
                                                uint32_t (&pl)[32], float* export_ptr) {
   const int ncols = FULL ? 64 : ((kn + 15) & ~15);
@@ -124,7 +126,7 @@ __device__ __forceinline__ float softmax_block6(uint32_t taddr, int kn, float sl
 #pragma unroll
     for (int i = 0; i < 32; i += 2) {
       const float2 t = ffma2(make_float2(__uint_as_float(s[i]), __uint_as_float(s[i + 1])), c2, m2);
-      float2 p = make_float2(ex2_approx(t.x), ex2_approx(t.y));
+      float2 p = (POLY && ((i >> 1) & 3) == 3) ? ex2_poly2(t) : make_float2(ex2_approx(t.x), ex2_approx(t.y));
       if (!FULL) {
         if (c * 32 + i >= kn) p.x = 0.f;
         if (c * 32 + i + 1 >= kn) p.y = 0.f;
@@ -157,11 +159,15 @@ __device__ __forceinline__ float block_max5(uint32_t taddr, int kn) {
   return mx;
 }
 
-template <int NSPLIT, bool TRACE, bool FAST>
+// MODE 0: the round-1 softmax pass; 1: packed-math pass; 2: packed-math pass with a quarter of the exponentials
+// on the FMA pipe
+template <int NSPLIT, bool TRACE, int MODE>
 __global__ void __launch_bounds__(kA5Threads, 2)
 attention5_kernel(const __grid_constant__ CUtensorMap tmq_hi, const __grid_constant__ CUtensorMap tmq_lo,
                   const __grid_constant__ CUtensorMap tmk_hi, const __grid_constant__ CUtensorMap tmk_lo,
                   const Attn5Params p) {
+  constexpr bool FAST = MODE > 0;
+  constexpr bool POLY = MODE == 2;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -407,8 +413,8 @@ attention5_kernel(const __grid_constant__ CUtensorMap tmq_hi, const __grid_const
         if (j == 0) m_run = full ? block_max5<true>(tS, kn) : block_max5<false>(tS, kn);
         bool need;
         if (FAST) {
-          sum = full ? softmax_block6<true, NSPLIT>(tS, kn, p.scale_log2, m_run * p.scale_log2, ph, pl, ex)
-                     : softmax_block6<false, NSPLIT>(tS, kn, p.scale_log2, m_run * p.scale_log2, ph, pl, ex);
+          sum = full ? softmax_block6<true, NSPLIT, POLY>(tS, kn, p.scale_log2, m_run * p.scale_log2, ph, pl, ex)
+                     : softmax_block6<false, NSPLIT, false>(tS, kn, p.scale_log2, m_run * p.scale_log2, ph, pl, ex);
           // some p above 2^kA5LazyLog2 => the sum is above it too (the converse may fire early: a harmless redo);
           // an overflowed (inf) or NaN sum takes the redo path as well
           need = !(sum <= exp2f(kA5LazyLog2));
@@ -497,14 +503,14 @@ attention5_kernel(const __grid_constant__ CUtensorMap tmq_hi, const __grid_const
   }
 }
 
-template <int NSPLIT, bool TRACE, bool FAST>
+template <int NSPLIT, bool TRACE, int MODE>
 static int launch_attn5(const CUtensorMap* maps, const Attn5Params& p, cudaStream_t stream) {
   constexpr uint32_t smem =
       NSPLIT * kA5QTile + (kA5KStages + kA5VStages) * NSPLIT * kA5KVTile + 1024 + 256;
   static bool attr_set[kMaxDevices] = {};  // the opt-in is per device (and per kernel instantiation)
   const int dev_ = current_device();
   if (!attr_set[dev_]) {
-    cudaError_t e = cudaFuncSetAttribute(attention5_kernel<NSPLIT, TRACE, FAST>,
+    cudaError_t e = cudaFuncSetAttribute(attention5_kernel<NSPLIT, TRACE, MODE>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess)
       return set_error(MTT_ERR_LAUNCH, "attention5: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
@@ -512,14 +518,14 @@ static int launch_attn5(const CUtensorMap* maps, const Attn5Params& p, cudaStrea
   }
   const int total = ((p.N + 127) / 128) * p.H * p.B;
   const int slots = 2 * sm_count();
-  attention5_kernel<NSPLIT, TRACE, FAST><<<total < slots ? total : slots, kA5Threads, smem, stream>>>(maps[0], maps[1], maps[2],
+  attention5_kernel<NSPLIT, TRACE, MODE><<<total < slots ? total : slots, kA5Threads, smem, stream>>>(maps[0], maps[1], maps[2],
                                                                                        maps[3], p);
   return check_launch("mtt_attention(variant 5)");
 }
 
 extern unsigned int* g_attn_trace;  // attention_tc.cu (mtt_set_attention_trace)
 
-int launch_attention5(const mtt_attn_desc* d, bool fast, cudaStream_t stream) {
+int launch_attention5(const mtt_attn_desc* d, int mode, cudaStream_t stream) {
   const int C = d->H * 64;
   CUtensorMap maps[4];
   const uint64_t dims[3] = {(uint64_t)3 * C, (uint64_t)d->N, (uint64_t)d->B};
@@ -548,9 +554,12 @@ int launch_attention5(const mtt_attn_desc* d, bool fast, cudaStream_t stream) {
   p.wide_store = ((reinterpret_cast<uintptr_t>(d->out_hi) | reinterpret_cast<uintptr_t>(d->out_lo)) & 31) == 0;
   p.trace = g_attn_trace;
   if (g_attn_trace && d->nsplit == 2)
-    return fast ? launch_attn5<2, true, true>(maps, p, stream) : launch_attn5<2, true, false>(maps, p, stream);
-  if (fast) return d->nsplit == 2 ? launch_attn5<2, false, true>(maps, p, stream) : launch_attn5<1, false, true>(maps, p, stream);
-  return d->nsplit == 2 ? launch_attn5<2, false, false>(maps, p, stream) : launch_attn5<1, false, false>(maps, p, stream);
+    return mode == 2 ? launch_attn5<2, true, 2>(maps, p, stream)
+                     : (mode == 1 ? launch_attn5<2, true, 1>(maps, p, stream) : launch_attn5<2, true, 0>(maps, p, stream));
+  if (d->nsplit == 2)
+    return mode == 2 ? launch_attn5<2, false, 2>(maps, p, stream)
+                     : (mode == 1 ? launch_attn5<2, false, 1>(maps, p, stream) : launch_attn5<2, false, 0>(maps, p, stream));
+  return mode == 0 ? launch_attn5<1, false, 0>(maps, p, stream) : launch_attn5<1, false, 1>(maps, p, stream);
 }
 
 }  // namespace mtt

@@ -18,7 +18,7 @@
 #include "host_common.h"
 
 namespace mtt {
-int launch_attention5(const mtt_attn_desc* d, bool fast, cudaStream_t stream);  // attention5_tc.cu
+int launch_attention5(const mtt_attn_desc* d, int mode, cudaStream_t stream);  // attention5_tc.cu
 static int g_attn_variant = -1;  // -1: read MTT_ATTN_VARIANT once; 0 = default
 unsigned int* g_attn_trace = nullptr;  // mtt_set_attention_trace: clock-stamp buffer of the TRACE instantiation
 }  // namespace mtt
@@ -44,6 +44,8 @@ extern "C" int mtt_attention(const mtt_attn_desc* d, mtt_stream_t stream_) {
   }
   ProfileScope prof(static_cast<cudaStream_t>(stream_), 1, 4.0 * d->B * d->H * (double)d->N * d->N * 64, d->B * d->N, d->N,
                     d->H * 64);
-  // variant 5 = the round-1 softmax pass (rounded split, per-element maximum); 0 / 6 = the packed-math pass
-  return launch_attention5(d, g_attn_variant != 5, static_cast<cudaStream_t>(stream_));
+  // variant 5 = the round-1 softmax pass (rounded split, per-element maximum); 6 = the packed-math pass; 7 = packed
+  // math with a quarter of the exponentials as FMA-pipe polynomials; 0 = default
+  const int mode = g_attn_variant == 5 ? 0 : (g_attn_variant == 7 ? 2 : 1);
+  return launch_attention5(d, mode, static_cast<cudaStream_t>(stream_));
 }

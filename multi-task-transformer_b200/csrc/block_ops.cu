@@ -164,8 +164,8 @@ size_t mtt_workspace_bytes(int32_t op, const mtt_shape* s) {
       return align256(planes_bytes(ns, s->rows, pad8(s->C)));
     case MTT_OP_LN_MLP_RESIDUAL:  // LN2 output + hidden activations
       return align256(planes_bytes(ns, s->rows, pad8(s->C))) + align256(planes_bytes(ns, s->rows, pad8(s->hidden)));
-    case MTT_OP_GATED_CONV1X1:  // the two gated copies of the patch map
-      return 2 * align256(planes_bytes(ns, s->rows, pad8(s->C)));
+    case MTT_OP_GATED_CONV1X1:  // two gated copies of the patch map per task: [task][spatial | channel][plane][rows][ld]
+      return (size_t)(s->T > 0 ? s->T : 1) * 2 * align256(planes_bytes(ns, s->rows, pad8(s->C)));
     case MTT_OP_CONV3X3_BN_ACT:  // hidden map between the 3x3 and a fused 1x1 head
       return align256(planes_bytes(ns, s->rows, pad8(s->hidden)));
     case MTT_OP_ATTN_FWD:
@@ -291,42 +291,53 @@ int mtt_ln_mlp_residual(float* x, int64_t ldx, const float* gamma, const float* 
 }
 
 int mtt_gated_conv1x1(const float* x, int64_t ldx, int64_t x_group_rows, int64_t x_row_offset,
-                      const float* prompt_logits, const float* chan_logits, int32_t task, int32_t gh, int32_t gw,
-                      int32_t nh, int32_t nw, const mtt_weight* w_spa, const float* b_spa, const mtt_weight* w_chan,
-                      const float* b_chan, int32_t e, void* cat_hi, void* cat_lo, int64_t ld_cat, int32_t chan_col,
+                      const float* prompt_logits, const float* chan_logits, int32_t ntasks, const mtt_gated_task* tasks,
+                      int32_t gh, int32_t gw, int32_t nh, int32_t nw, int32_t e, int64_t ld_cat, int32_t chan_col,
                       const mtt_shape* s, void* ws, size_t ws_bytes, mtt_stream_t stream) {
-  if (!x || !w_spa || !w_chan || !cat_hi || !s || s->B <= 0 || gh <= 0 || gw <= 0 || e <= 0)
+  if (!x || !tasks || !s || ntasks <= 0 || ntasks > s->T || s->B <= 0 || gh <= 0 || gw <= 0 || e <= 0)
     return set_error(MTT_ERR_BAD_SHAPE, "mtt_gated_conv1x1: bad arguments");
   mtt_shape sh = *s;
   sh.rows = s->B * gh * gw;
+  sh.T = ntasks;
   int rc = need_ws("mtt_gated_conv1x1", ws, ws_bytes, mtt_workspace_bytes(MTT_OP_GATED_CONV1X1, &sh));
   if (rc) return rc;
   const int ns = s->nsplit == 1 ? 1 : 2;
   const long long ldy = pad8(s->C), rows = sh.rows;
+  const size_t pb = align256(planes_bytes(ns, rows, ldy));
+  const long long task_stride = (long long)(2 * pb / 2);  // elements between consecutive tasks' planes
   uint8_t* base = static_cast<uint8_t*>(ws);
-  __nv_bfloat16* ys_hi = reinterpret_cast<__nv_bfloat16*>(base);
-  __nv_bfloat16* ys_lo = ns == 2 ? ys_hi + rows * ldy : nullptr;
-  __nv_bfloat16* yc_hi = reinterpret_cast<__nv_bfloat16*>(base + align256(planes_bytes(ns, rows, ldy)));
-  __nv_bfloat16* yc_lo = ns == 2 ? yc_hi + rows * ldy : nullptr;
-  if ((rc = mtt_gate_split(x, ldx, x_group_rows, x_row_offset, prompt_logits, chan_logits, task, s->B, s->T, s->N,
-                           s->H, s->C, gh, gw, nh, nw, ys_hi, ys_lo, yc_hi, yc_lo, ldy, stream)))
+  auto ys_hi = [&](int k) { return reinterpret_cast<__nv_bfloat16*>(base + (size_t)k * 2 * pb); };
+  auto yc_hi = [&](int k) { return reinterpret_cast<__nv_bfloat16*>(base + (size_t)k * 2 * pb + pb); };
+  if ((rc = mtt_gate_split(x, ldx, x_group_rows, x_row_offset, prompt_logits, chan_logits, 0, ntasks, s->B, s->T, s->N,
+                           s->H, s->C, gh, gw, nh, nw, ys_hi(0), ns == 2 ? ys_hi(0) + rows * ldy : nullptr, yc_hi(0),
+                           ns == 2 ? yc_hi(0) + rows * ldy : nullptr, ldy, task_stride, stream)))
     return rc;
-  for (int which = 0; which < 2; ++which) {
-    mtt_gemm_desc g = {};
-    g.a_hi = which ? yc_hi : ys_hi;
-    g.a_lo = which ? yc_lo : ys_lo;
-    g.lda = ldy;
-    fill_b(g, which ? w_chan : w_spa);
-    g.M = (int32_t)rows;
-    g.N = e;
-    g.K = s->C;
-    g.nsplit = ns;
-    g.bias = which ? b_chan : b_spa;
-    const long long col = which ? chan_col : 0;
-    g.out_hi = static_cast<__nv_bfloat16*>(cat_hi) + col;
-    g.out_lo = cat_lo ? static_cast<__nv_bfloat16*>(cat_lo) + col : nullptr;
-    g.ldo_bf = ld_cat;
-    if ((rc = mtt_gemm(&g, stream))) return rc;
+  constexpr int kChunk = 6;  // 12 problems per grouped launch
+  for (int k0 = 0; k0 < ntasks; k0 += kChunk) {
+    const int nk = ntasks - k0 < kChunk ? ntasks - k0 : kChunk;
+    mtt_gemm_desc g[2 * kChunk];
+    for (int k = 0; k < nk; ++k) {
+      const mtt_gated_task& t = tasks[k0 + k];
+      for (int which = 0; which < 2; ++which) {
+        mtt_gemm_desc& d = g[2 * k + which];
+        d = mtt_gemm_desc{};
+        __nv_bfloat16* a = which ? yc_hi(k0 + k) : ys_hi(k0 + k);
+        d.a_hi = a;
+        d.a_lo = ns == 2 ? a + rows * ldy : nullptr;
+        d.lda = ldy;
+        fill_b(d, which ? &t.w_chan : &t.w_spa);
+        d.M = (int32_t)rows;
+        d.N = e;
+        d.K = s->C;
+        d.nsplit = ns;
+        d.bias = which ? t.b_chan : t.b_spa;
+        const long long col = which ? chan_col : 0;
+        d.out_hi = static_cast<__nv_bfloat16*>(t.cat_hi) + col;
+        d.out_lo = t.cat_lo ? static_cast<__nv_bfloat16*>(t.cat_lo) + col : nullptr;
+        d.ldo_bf = ld_cat;
+      }
+    }
+    if ((rc = mtt_gemm_grouped(g, 2 * nk, stream))) return rc;
   }
   return MTT_OK;
 }

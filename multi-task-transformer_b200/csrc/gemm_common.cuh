@@ -39,6 +39,27 @@ struct GemmParams {
   int debug;              // profiling aid (env MTT_GEMM_DEBUG): bit0 = skip TMA loads, bit1 = skip global stores
 };
 
+// Grouped launch (mtt_gemm_grouped): up to kMaxGroup problems of IDENTICAL geometry (M, N, K, mode, conv shape, nsplit,
+// activation, row regrouping) that differ only in their operand / bias / residual / output pointers run as ONE
+// persistent launch; tile index = problem * tiles_per_problem + tile. The per-task decoder chains of TaskPrompter
+// (5 tasks x {spatial, channel} 1x1 convs, fea_fuse) are single-wave launches (96 tiles on 148 SMs) on their own.
+constexpr int kMaxGroup = 12;
+struct GroupProblem {
+  const float* bias;
+  const float* residual;
+  float* out_f32;
+  __nv_bfloat16* out_hi;
+  __nv_bfloat16* out_lo;
+};
+struct GemmGroup {
+  int count;              // 0: not grouped (the kernel uses its four direct tensor-map parameters)
+  int tiles_per_problem;
+  GroupProblem prob[kMaxGroup];
+};
+struct GemmGroupMaps {
+  CUtensorMap m[kMaxGroup][4];  // A hi, A lo, B hi, B lo per problem
+};
+
 // Host: validates the descriptor, fills GemmParams (tiles_n left to the caller) and encodes the four
 // tensor maps; the B map's box has `b_box_rows` rows of N.
 int gemm_prepare(const mtt_gemm_desc* d, int b_box_rows, GemmParams& p, CUtensorMap maps[4]);
@@ -231,6 +252,7 @@ __device__ __forceinline__ void epilogue_store32(const GemmParams& p, const uint
 
 // Entry points of the two kernels (defined in gemm_tc.cu / gemm2_tc.cu)
 int launch_gemm_1cta(const mtt_gemm_desc* d, cudaStream_t stream);
+int launch_gemm_1cta_grouped(const mtt_gemm_desc* d, int count, cudaStream_t stream);
 int launch_gemm_2cta(const mtt_gemm_desc* d, int bn2, cudaStream_t stream);
 
 }  // namespace mtt

@@ -219,3 +219,29 @@ extern "C" int mtt_gemm(const mtt_gemm_desc* d, mtt_stream_t stream_) {
   if (v == 1) return launch_gemm_1cta(d, stream);
   return launch_gemm_2cta(d, v == 2 ? 256 : 128, stream);
 }
+
+extern "C" int mtt_gemm_grouped(const mtt_gemm_desc* d, int32_t count, mtt_stream_t stream_) {
+  using namespace mtt;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!d || count <= 0) return set_error(MTT_ERR_BAD_SHAPE, "mtt_gemm_grouped: no problems");
+  if (count == 1) return mtt_gemm(d, stream_);
+  if (count > kMaxGroup) return set_error(MTT_ERR_BAD_SHAPE, "mtt_gemm_grouped: %d problems > %d", count, kMaxGroup);
+  const mtt_gemm_desc& a = d[0];
+  for (int g = 1; g < count; ++g) {
+    const mtt_gemm_desc& b = d[g];
+    const bool same = a.M == b.M && a.N == b.N && a.K == b.K && a.nsplit == b.nsplit && a.mode == b.mode && a.B == b.B &&
+                      a.H == b.H && a.W == b.W && a.ksize == b.ksize && a.dil == b.dil && a.act == b.act &&
+                      a.lda == b.lda && a.ldb == b.ldb && a.ldr == b.ldr && a.res_row_mod == b.res_row_mod &&
+                      a.ldo_f32 == b.ldo_f32 && a.ldo_bf == b.ldo_bf && a.in_group == b.in_group &&
+                      a.out_group == b.out_group && a.out_offset == b.out_offset && a.out_row_stride == b.out_row_stride &&
+                      a.a_group_rows == b.a_group_rows && a.a_group_stride == b.a_group_stride &&
+                      (a.bias == nullptr) == (b.bias == nullptr) && (a.residual == nullptr) == (b.residual == nullptr) &&
+                      (a.out_f32 == nullptr) == (b.out_f32 == nullptr) && (a.out_hi == nullptr) == (b.out_hi == nullptr);
+    if (!same)
+      return set_error(MTT_ERR_BAD_SHAPE, "mtt_gemm_grouped: problem %d differs from problem 0 in more than its pointers", g);
+  }
+  double fl = 0;
+  for (int g = 0; g < count; ++g) fl += 2.0 * d[g].M * d[g].N * d[g].K * (d[g].mode == 1 ? d[g].ksize * d[g].ksize : 1);
+  ProfileScope prof(stream, 0, fl, a.M * count, a.N, a.K * (a.mode == 1 ? a.ksize * a.ksize : 1));
+  return launch_gemm_1cta_grouped(d, count, stream);
+}

@@ -30,11 +30,10 @@ struct GemmCfg {
   static constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 + 256;
 };
 
-template <int NSPLIT>
-__global__ void __launch_bounds__(kGemmThreads, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
-               const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
-               const GemmParams p) {
+// The kernel body, shared by the single-problem kernel (GROUPED = false: `maps` holds one set of four tensor maps)
+// and the grouped one (GROUPED = true: one set per problem, tile -> (problem, tile) through grp).
+template <int NSPLIT, bool GROUPED>
+__device__ __forceinline__ void gemm_tc_body(const CUtensorMap (*maps)[4], const GemmParams& p, const GemmGroup* grp) {
   using Cfg = GemmCfg<NSPLIT>;
   constexpr int ST = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
@@ -48,15 +47,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_tiles = p.tiles_m * p.tiles_n;
+  const int tpp = p.tiles_m * p.tiles_n;                       // tiles per problem
+  const int num_tiles = GROUPED ? tpp * grp->count : tpp;
   const int k_iters = p.taps * p.num_kb;
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmA_hi);
-    tma_prefetch_desc(&tmB_hi);
+    tma_prefetch_desc(&maps[0][0]);
+    tma_prefetch_desc(&maps[0][2]);
     if (NSPLIT == 2) {
-      tma_prefetch_desc(&tmA_lo);
-      tma_prefetch_desc(&tmB_lo);
+      tma_prefetch_desc(&maps[0][1]);
+      tma_prefetch_desc(&maps[0][3]);
     }
     for (int s = 0; s < ST; ++s) {
       mbar_init(&full_bar[s], 1);
@@ -84,8 +84,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       uint32_t phase = 0;
       const uint32_t stage_tx = NSPLIT * (p.a_box_bytes + kTileBytes);
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int mt = tile % p.tiles_m;
-        const int nt = tile / p.tiles_m;
+        const int g = GROUPED ? tile / tpp : 0;
+        const int tl = GROUPED ? tile - g * tpp : tile;
+        const int mt = tl % p.tiles_m;
+        const int nt = tl / p.tiles_m;
+        const CUtensorMap* tmA_hi = &maps[g][0];
+        const CUtensorMap* tmA_lo = &maps[g][1];
+        const CUtensorMap* tmB_hi = &maps[g][2];
+        const CUtensorMap* tmB_lo = &maps[g][3];
         for (int ki = 0; ki < k_iters; ++ki) {
           const int tap = ki / p.num_kb, kb = ki - tap * p.num_kb;
           const int dy = (tap / p.ksize - p.ksize / 2) * p.dil;
@@ -98,10 +104,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
               mbar_arrive(&full_bar[stage]);
             } else {
               mbar_arrive_expect_tx(&full_bar[stage], stage_tx);
-              load_a_tile<NSPLIT, 0>(p, &tmA_hi, &tmA_lo, sa, &full_bar[stage], mt, kb, dy, dx);
+              load_a_tile<NSPLIT, 0>(p, tmA_hi, tmA_lo, sa, &full_bar[stage], mt, kb, dy, dx);
               const int kcoord = tap * p.cin_pad + kb * BK;
-              tma_load_2d(sb, &tmB_hi, &full_bar[stage], kcoord, nt * BN);
-              if (NSPLIT == 2) tma_load_2d(sb + kTileBytes, &tmB_lo, &full_bar[stage], kcoord, nt * BN);
+              tma_load_2d(sb, tmB_hi, &full_bar[stage], kcoord, nt * BN);
+              if (NSPLIT == 2) tma_load_2d(sb + kTileBytes, tmB_lo, &full_bar[stage], kcoord, nt * BN);
             }
           }
           __syncwarp();
@@ -125,7 +131,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         tc_fence_after();
         const uint32_t tacc = tmem_base + as * BN;
         // ragged last N tile: a narrower MMA (N rounded up to 16) instead of multiplying zero-filled weight rows
-        const int n_left = p.N - (tile / p.tiles_m) * BN;
+        const int n_left = p.N - (((GROUPED ? tile % tpp : tile)) / p.tiles_m) * BN;
         const uint32_t idesc = umma_idesc_bf16(BM, n_left >= BN ? BN : ((n_left + 15) & ~15), 0);
         uint32_t accum = 0;
         int kb = 0;
@@ -172,8 +178,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
-      const int mt = tile % p.tiles_m;
-      const int nt = tile / p.tiles_m;
+      const int g = GROUPED ? tile / tpp : 0;
+      const int tl = GROUPED ? tile - g * tpp : tile;
+      const int mt = tl % p.tiles_m;
+      const int nt = tl / p.tiles_m;
       const RowInfo ri = row_info(p, mt, row);
 
       mbar_wait(&tfull_bar[as], aphase);
@@ -189,8 +197,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 
       if (ri.ok && !(p.debug & 2)) {
         const int n0 = nt * BN + half * 64;
-        epilogue_store32(p, r0, n0, ri);
-        epilogue_store32(p, r1, n0 + 32, ri);
+        if (GROUPED) {
+          GemmParams q = p;                       // this problem's pointers over the shared geometry
+          const GroupProblem& gp = grp->prob[g];
+          q.bias = gp.bias;
+          q.residual = gp.residual;
+          q.out_f32 = gp.out_f32;
+          q.out_hi = gp.out_hi;
+          q.out_lo = gp.out_lo;
+          epilogue_store32(q, r0, n0, ri);
+          epilogue_store32(q, r1, n0 + 32, ri);
+        } else {
+          epilogue_store32(p, r0, n0, ri);
+          epilogue_store32(p, r1, n0 + 32, ri);
+        }
       }
       __syncwarp();
     }
@@ -202,6 +222,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     tc_fence_after();
     tmem_dealloc<kTmemCols>(tmem_base);
   }
+}
+
+struct GemmMaps1 {
+  CUtensorMap m[1][4];
+};
+
+template <int NSPLIT>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tc_kernel(const __grid_constant__ GemmMaps1 maps, const GemmParams p) {
+  gemm_tc_body<NSPLIT, false>(maps.m, p, nullptr);
+}
+
+template <int NSPLIT>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tc_grouped_kernel(const __grid_constant__ GemmGroupMaps maps, const __grid_constant__ GemmGroup grp,
+                       const GemmParams p) {
+  gemm_tc_body<NSPLIT, true>(maps.m, p, &grp);
 }
 
 template <int NSPLIT>
@@ -218,9 +255,51 @@ static int launch_gemm(const CUtensorMap* maps, const GemmParams& p, cudaStream_
   }
   const int tiles = p.tiles_m * p.tiles_n;
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  gemm_tc_kernel<NSPLIT><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(maps[0], maps[1], maps[2],
-                                                                         maps[3], p);
+  GemmMaps1 gm;
+  for (int i = 0; i < 4; ++i) gm.m[0][i] = maps[i];
+  gemm_tc_kernel<NSPLIT><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(gm, p);
   return check_launch("mtt_gemm");
+}
+
+template <int NSPLIT>
+static int launch_gemm_grouped(const GemmGroupMaps& gm, const GemmGroup& grp, const GemmParams& p,
+                               cudaStream_t stream) {
+  using Cfg = GemmCfg<NSPLIT>;
+  static bool attr_set[kMaxDevices] = {};
+  const int dev_ = current_device();
+  if (!attr_set[dev_]) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_grouped_kernel<NSPLIT>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (e != cudaSuccess)
+      return set_error(MTT_ERR_LAUNCH, "gemm(grouped): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr_set[dev_] = true;
+  }
+  const int tiles = grp.tiles_per_problem * grp.count;
+  const int grid = tiles < sm_count() ? tiles : sm_count();
+  gemm_tc_grouped_kernel<NSPLIT><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(gm, grp, p);
+  return check_launch("mtt_gemm_grouped");
+}
+
+int launch_gemm_1cta_grouped(const mtt_gemm_desc* d, int count, cudaStream_t stream) {
+  GemmParams p;
+  GemmGroupMaps gm;
+  GemmGroup grp;
+  grp.count = count;
+  for (int g = 0; g < count; ++g) {
+    GemmParams pg;
+    int rc = gemm_prepare(&d[g], BN, pg, gm.m[g]);
+    if (rc) return rc;
+    pg.tiles_n = (d[g].N + BN - 1) / BN;
+    if (g == 0) {
+      p = pg;
+    } else if (pg.vec_ok != p.vec_ok || pg.vec32_ok != p.vec32_ok) {  // the epilogue's vector width is shared
+      p.vec_ok = p.vec_ok && pg.vec_ok;
+      p.vec32_ok = p.vec32_ok && pg.vec32_ok;
+    }
+    grp.prob[g] = GroupProblem{pg.bias, pg.residual, pg.out_f32, pg.out_hi, pg.out_lo};
+  }
+  grp.tiles_per_problem = p.tiles_m * p.tiles_n;
+  return d[0].nsplit == 2 ? launch_gemm_grouped<2>(gm, grp, p, stream) : launch_gemm_grouped<1>(gm, grp, p, stream);
 }
 
 

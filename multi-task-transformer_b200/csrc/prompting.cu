@@ -97,31 +97,53 @@ chan_logits_kernel(const float* __restrict__ cp, const __nv_bfloat16* __restrict
 //   Ys[b,pix,c] = X[b,pix,c] * (1 + R[b, c / dh, t, T + pix])
 //   Yc[b,pix,c] = X[b,pix,c] * (1 + Rc[b, t, c, window(pix)])
 // written as split-bf16 A operands of the two 1x1 decode convolutions.
-__global__ void __launch_bounds__(256)
+// One block per patch row (b, pix), one thread per 8 consecutive channels: X is read ONCE (two float4) and gated for
+// `nt` consecutive tasks; every plane is written with 16-byte stores. Task k's planes start k * task_stride elements
+// after task t0's (the workspace layout of mtt_gated_conv1x1).
+__global__ void __launch_bounds__(128)
 gate_split_kernel(const float* __restrict__ x, long long ldx, long long x_group, long long x_off,
-                  const float* __restrict__ logits, const float* __restrict__ rc, int t, int T, int N, int H,
+                  const float* __restrict__ logits, const float* __restrict__ rc, int t0, int nt, int T, int N, int H,
                   int dh, int C, int gh, int gw, int nh, int nw, __nv_bfloat16* __restrict__ ys_hi,
                   __nv_bfloat16* __restrict__ ys_lo, __nv_bfloat16* __restrict__ yc_hi,
-                  __nv_bfloat16* __restrict__ yc_lo, long long ldy) {
+                  __nv_bfloat16* __restrict__ yc_lo, long long ldy, long long task_stride) {
   const int P = gh * gw;
   const long long row = blockIdx.x;  // b * P + pix
   const int b = (int)(row / P), pix = (int)(row % P);
   const int py = pix / gw, px = pix % gw;
+  const int nwin = nh * nw;
   const int win = (py / (gh / nh)) * nw + px / (gw / nw);
   const float* xr = x + ((long long)b * x_group + x_off + pix) * ldx;
-  const float* lg = logits + (((long long)b * H) * T + t) * N + T + pix;  // + head * T * N
-  const float* rcr = rc + (((long long)b * T + t) * C) * (nh * nw) + win;  // + c * nh*nw
-  for (int c = threadIdx.x * 2; c < C; c += blockDim.x * 2) {
-    const float x0 = xr[c], x1 = xr[c + 1];
-    const float g0 = lg[(long long)(c / dh) * T * N], g1 = lg[(long long)((c + 1) / dh) * T * N];
-    const float r0 = rcr[(long long)c * (nh * nw)], r1 = rcr[(long long)(c + 1) * (nh * nw)];
-    uint32_t h, l;
-    split_pack2(x0 * (1.f + g0), x1 * (1.f + g1), h, l);
-    *reinterpret_cast<uint32_t*>(ys_hi + row * ldy + c) = h;
-    if (ys_lo) *reinterpret_cast<uint32_t*>(ys_lo + row * ldy + c) = l;
-    split_pack2(x0 * (1.f + r0), x1 * (1.f + r1), h, l);
-    *reinterpret_cast<uint32_t*>(yc_hi + row * ldy + c) = h;
-    if (yc_lo) *reinterpret_cast<uint32_t*>(yc_lo + row * ldy + c) = l;
+  for (int c = threadIdx.x * 8; c < C; c += blockDim.x * 8) {
+    const float4 xa = *reinterpret_cast<const float4*>(xr + c), xb = *reinterpret_cast<const float4*>(xr + c + 4);
+    const float xv[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+    for (int k = 0; k < nt; ++k) {
+      const int t = t0 + k;
+      // spatial gate: one scalar per (head, pixel); the 8 channels of this thread lie in one head (dh % 8 == 0)
+      const float g = logits[(((long long)b * H + c / dh) * T + t) * N + T + pix];
+      const float* rcr = rc + (((long long)b * T + t) * C + c) * nwin + win;  // + i * nwin
+      float gc[8];
+      if (nwin == 1) {
+        const float4 ra = *reinterpret_cast<const float4*>(rcr), rb = *reinterpret_cast<const float4*>(rcr + 4);
+        gc[0] = ra.x; gc[1] = ra.y; gc[2] = ra.z; gc[3] = ra.w; gc[4] = rb.x; gc[5] = rb.y; gc[6] = rb.z; gc[7] = rb.w;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) gc[i] = rcr[(long long)i * nwin];
+      }
+      uint4 sh, sl, ch, cl;
+      split_pack2(xv[0] * (1.f + g), xv[1] * (1.f + g), sh.x, sl.x);
+      split_pack2(xv[2] * (1.f + g), xv[3] * (1.f + g), sh.y, sl.y);
+      split_pack2(xv[4] * (1.f + g), xv[5] * (1.f + g), sh.z, sl.z);
+      split_pack2(xv[6] * (1.f + g), xv[7] * (1.f + g), sh.w, sl.w);
+      split_pack2(xv[0] * (1.f + gc[0]), xv[1] * (1.f + gc[1]), ch.x, cl.x);
+      split_pack2(xv[2] * (1.f + gc[2]), xv[3] * (1.f + gc[3]), ch.y, cl.y);
+      split_pack2(xv[4] * (1.f + gc[4]), xv[5] * (1.f + gc[5]), ch.z, cl.z);
+      split_pack2(xv[6] * (1.f + gc[6]), xv[7] * (1.f + gc[7]), ch.w, cl.w);
+      const long long o = (long long)k * task_stride + row * ldy + c;
+      *reinterpret_cast<uint4*>(ys_hi + o) = sh;
+      if (ys_lo) *reinterpret_cast<uint4*>(ys_lo + o) = sl;
+      *reinterpret_cast<uint4*>(yc_hi + o) = ch;
+      if (yc_lo) *reinterpret_cast<uint4*>(yc_lo + o) = cl;
+    }
   }
 }
 
@@ -420,17 +442,22 @@ extern "C" int mtt_chan_logits(const float* cp, const void* xn_hi, const void* x
 }
 
 extern "C" int mtt_gate_split(const float* x, int64_t ldx, int64_t x_group_rows, int64_t x_row_offset,
-                              const float* prompt_logits, const float* chan_logits, int32_t task,
-                              int32_t B, int32_t T, int32_t N, int32_t H, int32_t C, int32_t gh,
-                              int32_t gw, int32_t nh, int32_t nw, void* ys_hi, void* ys_lo, void* yc_hi,
-                              void* yc_lo, int64_t ldy, mtt_stream_t stream) {
-  if (!x || !prompt_logits || !chan_logits || !ys_hi || !yc_hi || C % 2 || ldy % 2 || C % H ||
-      task < 0 || task >= T || gh % nh || gw % nw)
-    return set_error(MTT_ERR_BAD_SHAPE, "mtt_gate_split: bad arguments");
-  gate_split_kernel<<<B * gh * gw, 256, 0, STREAM>>>(
-      x, ldx, x_group_rows, x_row_offset, prompt_logits, chan_logits, task, T, N, H, C / H, C, gh, gw, nh,
+                              const float* prompt_logits, const float* chan_logits, int32_t task, int32_t ntasks,
+                              int32_t B, int32_t T, int32_t N, int32_t H, int32_t C, int32_t gh, int32_t gw,
+                              int32_t nh, int32_t nw, void* ys_hi, void* ys_lo, void* yc_hi, void* yc_lo, int64_t ldy,
+                              int64_t task_stride, mtt_stream_t stream) {
+  if (!x || !prompt_logits || !chan_logits || !ys_hi || !yc_hi || C % 8 || ldy % 8 || ldx % 4 || C % H || (C / H) % 8 ||
+      task < 0 || ntasks < 1 || task + ntasks > T || gh % nh || gw % nw || task_stride % 8)
+    return set_error(MTT_ERR_BAD_SHAPE, "mtt_gate_split: bad arguments (C=%d H=%d tasks [%d,%d) of %d)", C, H, task,
+                     task + ntasks, T);
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  if (!al16(x) || !al16(ys_hi) || !al16(yc_hi) || (ys_lo && !al16(ys_lo)) || (yc_lo && !al16(yc_lo)) ||
+      (nh * nw == 1 && !al16(chan_logits)))
+    return set_error(MTT_ERR_MISALIGNED, "mtt_gate_split: pointers must be 16-byte aligned");
+  gate_split_kernel<<<B * gh * gw, 128, 0, STREAM>>>(
+      x, ldx, x_group_rows, x_row_offset, prompt_logits, chan_logits, task, ntasks, T, N, H, C / H, C, gh, gw, nh,
       nw, static_cast<__nv_bfloat16*>(ys_hi), static_cast<__nv_bfloat16*>(ys_lo),
-      static_cast<__nv_bfloat16*>(yc_hi), static_cast<__nv_bfloat16*>(yc_lo), ldy);
+      static_cast<__nv_bfloat16*>(yc_hi), static_cast<__nv_bfloat16*>(yc_lo), ldy, task_stride);
   return check_launch("mtt_gate_split");
 }
 

@@ -47,6 +47,11 @@ class Weight(C.Structure):
     _fields_ = [("hi", C.c_void_p), ("lo", C.c_void_p), ("ld", C.c_int64)]
 
 
+class GatedTask(C.Structure):
+    _fields_ = [("w_spa", Weight), ("b_spa", C.c_void_p), ("w_chan", Weight), ("b_chan", C.c_void_p),
+                ("cat_hi", C.c_void_p), ("cat_lo", C.c_void_p)]
+
+
 OP_LN_QKV, OP_ATTN_FWD, OP_PROJ_RESIDUAL, OP_LN_MLP_RESIDUAL, OP_CHAN_PROMPT_LOGITS = 1, 2, 3, 4, 5
 OP_GATED_CONV1X1, OP_CONV3X3_BN_ACT, OP_BILINEAR_UP, OP_INVPT_ATTN, OP_LAYERNORM = 6, 7, 8, 9, 10
 
@@ -84,6 +89,7 @@ SYMBOLS = {
     "mtt_split_f32": (C.c_int, [_vp, _i64, _vp, _vp, _i64, _i64, _i32, _i32, _vp]),
     "mtt_layernorm": (C.c_int, [_vp, _i64, _vp, _vp, _f32, _vp, _i64, _vp, _vp, _i64, _i64, _i32, _vp]),
     "mtt_gemm": (C.c_int, [C.POINTER(GemmDesc), _vp]),
+    "mtt_gemm_grouped": (C.c_int, [C.POINTER(GemmDesc), _i32, _vp]),
     "mtt_set_gemm_variant": (None, [C.c_int]),
     "mtt_attention": (C.c_int, [C.POINTER(AttnDesc), _vp]),
     "mtt_set_attention_variant": (None, [C.c_int]),
@@ -91,8 +97,8 @@ SYMBOLS = {
     "mtt_im2col_patch": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _i64, _vp]),
     "mtt_broadcast_rows": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i64, _i64, _vp]),
     "mtt_chan_logits": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
-    "mtt_gate_split": (C.c_int, [_vp, _i64, _i64, _i64, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32,
-                                 _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i64, _vp]),
+    "mtt_gate_split": (C.c_int, [_vp, _i64, _i64, _i64, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32,
+                                 _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i64, _i64, _vp]),
     "mtt_ctr_weights": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "mtt_ctr_mix": (C.c_int, [_vp, _vp, _vp, _i32, _i64, _i32, _i64, _i32, _i32, _vp]),
     "mtt_bilinear": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _i64, _vp, _vp, _i64, _vp,
@@ -114,15 +120,24 @@ SYMBOLS = {
     "mtt_proj_residual": (C.c_int, [_vp, _vp, _i64, C.POINTER(Weight), _vp, _vp, _i64, C.POINTER(Shape), _vp]),
     "mtt_ln_mlp_residual": (C.c_int, [_vp, _i64, _vp, _vp, _f32, C.POINTER(Weight), _vp, C.POINTER(Weight), _vp,
                                       C.POINTER(Shape), _vp, C.c_size_t, _vp]),
-    "mtt_gated_conv1x1": (C.c_int, [_vp, _i64, _i64, _i64, _vp, _vp, _i32, _i32, _i32, _i32, _i32, C.POINTER(Weight), _vp,
-                                    C.POINTER(Weight), _vp, _i32, _vp, _vp, _i64, _i32, C.POINTER(Shape), _vp,
-                                    C.c_size_t, _vp]),
+    "mtt_gated_conv1x1": (C.c_int, [_vp, _i64, _i64, _i64, _vp, _vp, _i32, C.POINTER(GatedTask), _i32, _i32, _i32, _i32,
+                                    _i32, _i64, _i32, C.POINTER(Shape), _vp, C.c_size_t, _vp]),
     "mtt_conv3x3_bn_act": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, C.POINTER(Weight), _vp, _i32, _i32,
                                      _vp, _vp, _i64, C.POINTER(Weight), _vp, _i32, _vp, _i64, _i32, _vp, C.c_size_t,
                                      _vp]),
     "mtt_pack_weight": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _vp, _vp, _i64, _vp]),
     "mtt_pack_conv_weight": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _f32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _i64,
                                        _vp, _vp, _vp]),
+    "mtt_loss_workspace_bytes": (C.c_size_t, []),
+    "mtt_loss_cross_entropy": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _f32, _i32, _vp, _vp, _vp]),
+    "mtt_loss_cross_entropy_grad": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _f32, _i32, _vp, _vp, _vp, _vp]),
+    "mtt_loss_balanced_bce": (C.c_int, [_vp, _vp, _i64, _f32, _f32, _i32, _vp, _vp, _vp]),
+    "mtt_loss_balanced_bce_grad": (C.c_int, [_vp, _vp, _i64, _f32, _f32, _i32, _vp, _vp, _vp, _vp]),
+    "mtt_loss_l1": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _f32, _i32, _i32, _vp, _vp, _vp]),
+    "mtt_loss_l1_grad": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _f32, _i32, _i32, _vp, _vp, _vp, _vp]),
+    "mtt_boxes_bev_pairwise": (C.c_int, [_vp, _i32, _vp, _i32, _i32, _vp, _vp]),
+    "mtt_nms_workspace_bytes": (C.c_size_t, [_i32]),
+    "mtt_nms_bev": (C.c_int, [_vp, _i32, _f32, _i32, _vp, _vp, _vp, C.c_size_t, _vp]),
     "mtt_nchw_to_nhwc_split": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _i64, _vp]),
     "mtt_nhwc_to_nchw": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp]),
 }

@@ -92,8 +92,29 @@ def gemm(a, w, *, M=None, N=None, K=None, bias=None, act=ACT_NONE, residual=None
     w: Split [N, K] (conv: [N, ksize*ksize*cin_pad]); outputs: fp32 tensor and/or Split.
     regroup=(in_group, out_group, out_offset[, row_stride]) scatters output rows; a_gather=(group_rows,
     group_stride) gathers A rows in groups (M must be given); w_col_offset selects a K-slice of a wider packed W."""
-    nsplit = min(a.nsplit, w.nsplit)
     d = _L.GemmDesc()
+    _fill_gemm_desc(d, a, w, M, N, K, bias, act, residual, res_row_mod, out_f32, out_split, out_col_offset, regroup, conv,
+                    a_row_offset, a_gather, w_col_offset)
+    rc = _L.load().mtt_gemm(C.byref(d), _stream())
+    _L.check(rc, "mtt_gemm")
+
+
+def gemm_grouped(calls):
+    """calls: [(a, w, kwargs)] with gemm()'s arguments -- problems of identical geometry that differ only in their
+    tensors -- as ONE persistent launch (mtt_gemm_grouped)."""
+    arr = (_L.GemmDesc * len(calls))()
+    for d, (a, w, kw) in zip(arr, calls):
+        k = dict(M=None, N=None, K=None, bias=None, act=ACT_NONE, residual=None, res_row_mod=0, out_f32=None,
+                 out_split=None, out_col_offset=0, regroup=None, conv=None, a_row_offset=0, a_gather=None, w_col_offset=0)
+        k.update(kw)
+        _fill_gemm_desc(d, a, w, **k)
+    rc = _L.load().mtt_gemm_grouped(arr, len(calls), _stream())
+    _L.check(rc, "mtt_gemm_grouped")
+
+
+def _fill_gemm_desc(d, a, w, M, N, K, bias, act, residual, res_row_mod, out_f32, out_split, out_col_offset, regroup, conv,
+                    a_row_offset, a_gather, w_col_offset):
+    nsplit = min(a.nsplit, w.nsplit)
     aoff = 2 * a_row_offset * a.ld
     d.a_hi, d.a_lo, d.lda = a.hi.data_ptr() + aoff, (a.lo.data_ptr() + aoff if nsplit == 2 else 0), a.ld
     woff = 2 * w_col_offset
@@ -127,8 +148,6 @@ def gemm(a, w, *, M=None, N=None, K=None, bias=None, act=ACT_NONE, residual=None
         d.out_row_stride = regroup[3] if len(regroup) > 3 else 1
     if a_gather is not None:    # (group_rows, group_stride): logical row (g, i) at physical row g*stride + i
         d.a_group_rows, d.a_group_stride = a_gather
-    rc = _L.load().mtt_gemm(C.byref(d), _stream())
-    _L.check(rc, "mtt_gemm")
 
 
 def attention(qkv, out, *, B, N, H, scale, prompt_logits=None, T=0):
@@ -204,11 +223,13 @@ def chan_logits(cp, xn, out, *, B, N, T, Cdim, gh, gw, nh, nw):
 
 
 def gate_split(x, x_group_rows, x_row_offset, prompt_logits, chan_lg, task, ys, yc, *, B, T, N, H, Cdim, gh,
-               gw, nh, nw):
+               gw, nh, nw, ntasks=1, task_stride=0):
+    """Gate the patch map for tasks [task, task + ntasks) in one pass; ys / yc are the Splits of the FIRST task, task k's
+    planes live k * task_stride elements further on (one task: plain Splits)."""
     assert x.dtype == torch.float32 and x.stride(-1) == 1 and ys.ld == yc.ld
     rc = _L.load().mtt_gate_split(_ptr(x), x.stride(-2), x_group_rows, x_row_offset, _ptr(prompt_logits),
-                                  _ptr(chan_lg), task, B, T, N, H, Cdim, gh, gw, nh, nw, _ptr(ys.hi),
-                                  _ptr(ys.lo), _ptr(yc.hi), _ptr(yc.lo), ys.ld, _stream())
+                                  _ptr(chan_lg), task, ntasks, B, T, N, H, Cdim, gh, gw, nh, nw, _ptr(ys.hi),
+                                  _ptr(ys.lo), _ptr(yc.hi), _ptr(yc.lo), ys.ld, task_stride, _stream())
     _L.check(rc, "mtt_gate_split")
 
 
@@ -413,15 +434,21 @@ def ln_mlp_residual(x, gamma, beta, eps, w1, b1, w2, b2, ws):
     _L.check(rc, "mtt_ln_mlp_residual")
 
 
-def gated_conv1x1(x, x_group_rows, x_row_offset, prompt_logits, chan_lg, task, w_spa, b_spa, w_chan, b_chan, e, cat,
-                  chan_col, ws, *, B, T, N, H, Cdim, gh, gw, nh, nw):
-    """Spatial + channel gating of task `task` and the two 1x1 decode convs into `cat` (taskprompter.py:436-471)."""
-    ns = min(w_spa.nsplit, cat.nsplit)
+def gated_conv1x1(x, x_group_rows, x_row_offset, prompt_logits, chan_lg, tasks, e, chan_col, ws, *, B, T, N, H, Cdim,
+                  gh, gw, nh, nw):
+    """Spatial + channel gating of ALL tasks of a level and their 2 * len(tasks) 1x1 decode convs (taskprompter.py:
+    436-471) -- one gating launch, one grouped GEMM launch. tasks: [(w_spa, b_spa, w_chan, b_chan, cat Split)]."""
+    cat0 = tasks[0][4]
+    ns = min(tasks[0][0].nsplit, cat0.nsplit)
+    arr = (_L.GatedTask * len(tasks))()
+    for g, (w_spa, b_spa, w_chan, b_chan, cat) in zip(arr, tasks):
+        assert cat.ld == cat0.ld
+        g.w_spa, g.b_spa, g.w_chan, g.b_chan = _weight(w_spa, ns), b_spa.data_ptr(), _weight(w_chan, ns), b_chan.data_ptr()
+        g.cat_hi, g.cat_lo = cat.hi.data_ptr(), (cat.lo.data_ptr() if ns == 2 else 0)
     rc = _L.load().mtt_gated_conv1x1(_ptr(x), x.stride(-2), x_group_rows, x_row_offset, _ptr(prompt_logits),
-                                     _ptr(chan_lg), task, gh, gw, nh, nw, C.byref(_weight(w_spa, ns)), _ptr(b_spa),
-                                     C.byref(_weight(w_chan, ns)), _ptr(b_chan), e, _ptr(cat.hi), _ptr(cat.lo), cat.ld,
-                                     chan_col, C.byref(_shape(0, Cdim, nsplit=ns, B=B, N=N, H=H, T=T)), _ptr(ws),
-                                     ws.numel(), _stream())
+                                     _ptr(chan_lg), len(tasks), arr, gh, gw, nh, nw, e, cat0.ld, chan_col,
+                                     C.byref(_shape(0, Cdim, nsplit=ns, B=B, N=N, H=H, T=T)), _ptr(ws), ws.numel(),
+                                     _stream())
     _L.check(rc, "mtt_gated_conv1x1")
 
 

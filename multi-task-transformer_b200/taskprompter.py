@@ -608,10 +608,10 @@ class _Plan:
             self.nh, self.nw = self.sp.nh, self.sp.nw
             self.xs, self.logits, self.rc = self.sp.xs, self.sp.logits, self.sp.rc
             self.xfin = z(B * N, C)
-            # one set of decoder scratch buffers per task: the T task chains of a level run concurrently on side
-            # streams (each chain's GEMMs are single-wave, 96 tiles on 148 SMs, and latency-bound)
-            gate_ws = ops.workspace_bytes(ops._L.OP_GATED_CONV1X1, rows=B * P, Cdim=C, nsplit=ns)
-            self.ws_gate = [ops.workspace(gate_ws, device) for _ in range(T)]
+            # one set of decoder scratch buffers per task: the T tasks' identically shaped convolutions of a level run
+            # as grouped launches
+            self.ws_gate = ops.workspace(ops.workspace_bytes(ops._L.OP_GATED_CONV1X1, rows=B * P, Cdim=C, nsplit=ns, T=T),
+                                         device)
             self.cat = [S(B * P, 2 * e_pad, zero=True) for _ in range(T)]
             self.f1 = [S(B * P, f, zero=True) for _ in range(T)]
             self.f2 = [S(B * P, f, zero=True) for _ in range(T)]
@@ -652,31 +652,31 @@ class _Plan:
         self.version = _version(bb) + (_version(self.heads) if self.heads is not None else 0)
 
     # -- launch sequence ------------------------------------------------------------------------
-    def _task_chain(self, il, ti, tw, x_src, first):
-        B, N, T, C, P = self.B, self.N, self.T, self.C, self.P
-        cat, f1, f2 = self.cat[ti], self.f1[ti], self.f2[ti]
-        ops.gated_conv1x1(x_src, N, T, self.logits, self.rc, ti, tw.spa, tw.spa_b, tw.chan, tw.chan_b, self.e, cat,
-                          self.e_pad, self.ws_gate[ti], B=B, T=T, N=N, H=self.H, Cdim=C, gh=self.gh, gw=self.gw,
-                          nh=self.nh, nw=self.nw)                                            # :436-447, :452-468, :471
-        ops.gemm(cat, tw.f0, bias=tw.f0_b, out_split=f1, N=self.f)                           # fea_fuse[0]
-        ops.conv3x3_bn_act(f1, tw.f1, tw.f1_b, self.f, self.f, ops.ACT_GELU, B=B, H=self.gh, W=self.gw, mid=f2)  # [1..3]
-        if self.use_ctr:
-            ops.gemm(f2, tw.f4, bias=tw.f4_b, out_f32=self.F[ti][:, :self.f], N=self.f)
-        else:
-            a = self.acc[ti][:, :self.f]
-            ops.gemm(f2, tw.f4, bias=tw.f4_b, residual=None if first else a, out_f32=a, N=self.f)
-
     def _level(self, il, x_src):
-        """cal_task_feature (:424-487) on X = x_src rows [b*N + T + pix]; accumulates into self.acc."""
-        B, N, T, P = self.B, self.N, self.T, self.P
+        """cal_task_feature (:424-487) on X = x_src rows [b*N + T + pix]; accumulates into self.acc. The T tasks'
+        identically shaped convolutions run as grouped launches (T x 96 tiles instead of T single-wave launches)."""
+        B, N, T, C, P = self.B, self.N, self.T, self.C, self.P
         lv = self.Wl[il]
         first = il == 0
-        self.streams.par([lambda ti=ti, tw=tw: self._task_chain(il, ti, tw, x_src, first)
-                          for ti, tw in enumerate(lv.tasks)])
+        ops.gated_conv1x1(x_src, N, T, self.logits, self.rc,
+                          [(tw.spa, tw.spa_b, tw.chan, tw.chan_b, self.cat[ti]) for ti, tw in enumerate(lv.tasks)],
+                          self.e, self.e_pad, self.ws_gate, B=B, T=T, N=N, H=self.H, Cdim=C, gh=self.gh, gw=self.gw,
+                          nh=self.nh, nw=self.nw)                                            # :436-447, :452-468, :471
+        ops.gemm_grouped([(self.cat[ti], tw.f0, dict(bias=tw.f0_b, out_split=self.f1[ti], N=self.f))
+                          for ti, tw in enumerate(lv.tasks)])                                # fea_fuse[0]
+        ops.gemm_grouped([(self.f1[ti], tw.f1, dict(N=self.f, K=self.f, bias=tw.f1_b, act=ops.ACT_GELU,
+                                                    out_split=self.f2[ti], conv=(B, self.gh, self.gw, 3, 1)))
+                          for ti, tw in enumerate(lv.tasks)])                                # fea_fuse[1..3]
         if self.use_ctr:
+            ops.gemm_grouped([(self.f2[ti], tw.f4, dict(bias=tw.f4_b, out_f32=self.F[ti][:, :self.f], N=self.f))
+                              for ti, tw in enumerate(lv.tasks)])                            # fea_fuse[4]
             ops.ctr_weights(self.logits, lv.c0, lv.c0b, lv.c2, lv.c2b, self.ctrw, B=B, H=self.H, T=T, N=N)
             ops.ctr_mix(self.F, self.ctrw, self.acc, T=T, M=B * P, Cdim=self.f_ld, ld=self.f_ld,
                         rows_per_batch=P, accumulate=not first)                              # :481-485,:411
+        else:
+            ops.gemm_grouped([(self.f2[ti], tw.f4, dict(bias=tw.f4_b, out_f32=self.acc[ti][:, :self.f], N=self.f,
+                                                        residual=None if first else self.acc[ti][:, :self.f]))
+                              for ti, tw in enumerate(lv.tasks)])                            # fea_fuse[4] + level sum :411
 
     def _head_chain(self, ti, t, hw, hs):
         B = self.B

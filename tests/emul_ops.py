@@ -95,6 +95,10 @@ def install(mp):
             if out_split.nsplit == 2:
                 out_split.buf[1, ro, out_col_offset:out_col_offset + N] = (y - hi.float()).bfloat16()
 
+    def gemm_grouped(calls):
+        for a, w, kw in calls:
+            ops.gemm(a, w, **kw)
+
     def attention(qkv, out, *, B, N, H, scale, prompt_logits=None, T=0):
         C = H * 64
         x = _rsplit(qkv, 3 * C).reshape(B, N, 3, H, 64).permute(2, 0, 3, 1, 4)
@@ -123,7 +127,8 @@ def install(mp):
         out.copy_(torch.einsum("btihjw,bihjwc->btcij", cpw, xw))
 
     def gate_split(x, x_group_rows, x_row_offset, prompt_logits, chan_lg, task, ys, yc, *, B, T, N, H, Cdim, gh,
-                   gw, nh, nw):
+                   gw, nh, nw, ntasks=1, task_stride=0):
+        assert ntasks == 1, "the emulation gates one task per call (gated_conv1x1 loops)"
         P = gh * gw
         X = x.reshape(B, x_group_rows, -1)[:, x_row_offset:x_row_offset + P, :Cdim]
         g = prompt_logits[:, :, task, T:]                                    # [B,H,P]
@@ -261,7 +266,7 @@ def install(mp):
     def workspace_bytes(op, rows=0, Cdim=0, hidden=0, nsplit=2, B=0, N=0, H=0, T=0):
         pl = lambda r, c: _al256(nsplit * r * ops.round_up(c, 8) * 2)
         return {ops._L.OP_LN_QKV: pl(rows, Cdim), ops._L.OP_LN_MLP_RESIDUAL: pl(rows, Cdim) + pl(rows, hidden),
-                ops._L.OP_GATED_CONV1X1: 2 * pl(rows, Cdim), ops._L.OP_CONV3X3_BN_ACT: pl(rows, hidden)}.get(op, 0)
+                ops._L.OP_GATED_CONV1X1: max(T, 1) * 2 * pl(rows, Cdim), ops._L.OP_CONV3X3_BN_ACT: pl(rows, hidden)}.get(op, 0)
 
     def ln_qkv(x, gamma, beta, eps, wqkv, bias, qkv, ws):
         rows, Cd = x.shape
@@ -281,15 +286,19 @@ def install(mp):
         ops.gemm(xn, w1, K=Cd, bias=b1, act=1, out_split=hid)
         ops.gemm(hid, w2, N=Cd, K=w1.rows, bias=b2, residual=x, out_f32=x)
 
-    def gated_conv1x1(x, x_group_rows, x_row_offset, prompt_logits, chan_lg, task, w_spa, b_spa, w_chan, b_chan, e, cat,
-                      chan_col, ws, *, B, T, N, H, Cdim, gh, gw, nh, nw):
-        rows, ns = B * gh * gw, cat.nsplit
-        ys = ops.ws_split_view(ws, 0, rows, Cdim, ns)
-        yc = ops.ws_split_view(ws, _al256(ns * rows * ops.round_up(Cdim, 8) * 2), rows, Cdim, ns)
-        ops.gate_split(x, x_group_rows, x_row_offset, prompt_logits, chan_lg, task, ys, yc, B=B, T=T, N=N, H=H, Cdim=Cdim,
-                       gh=gh, gw=gw, nh=nh, nw=nw)
-        ops.gemm(ys, w_spa, N=e, K=Cdim, bias=b_spa, out_split=cat)
-        ops.gemm(yc, w_chan, N=e, K=Cdim, bias=b_chan, out_split=cat, out_col_offset=chan_col)
+    def gated_conv1x1(x, x_group_rows, x_row_offset, prompt_logits, chan_lg, tasks, e, chan_col, ws, *, B, T, N, H,
+                      Cdim, gh, gw, nh, nw):
+        rows, ns = B * gh * gw, tasks[0][4].nsplit
+        pb = _al256(ns * rows * ops.round_up(Cdim, 8) * 2)
+        calls = []
+        for k, (w_spa, b_spa, w_chan, b_chan, cat) in enumerate(tasks):      # workspace: [task][spatial | channel]
+            ys = ops.ws_split_view(ws, 2 * k * pb, rows, Cdim, ns)
+            yc = ops.ws_split_view(ws, 2 * k * pb + pb, rows, Cdim, ns)
+            ops.gate_split(x, x_group_rows, x_row_offset, prompt_logits, chan_lg, k, ys, yc, B=B, T=T, N=N, H=H,
+                           Cdim=Cdim, gh=gh, gw=gw, nh=nh, nw=nw)
+            calls.append((ys, w_spa, dict(N=e, K=Cdim, bias=b_spa, out_split=cat)))
+            calls.append((yc, w_chan, dict(N=e, K=Cdim, bias=b_chan, out_split=cat, out_col_offset=chan_col)))
+        ops.gemm_grouped(calls)
 
     def conv3x3_bn_act(a, w3, b3, Cin, Cout, act, *, B, H, W, dil=1, mid=None, w_head=None, b_head=None, n_out=0,
                        out_f32=None, ws=None):

@@ -59,6 +59,7 @@ def rnd(*shape, dev, scale=1.0):
 
 
 def test_gate_split(both, cuda_dev):
+    """All tasks in one launch (X read once) against the per-task restatement; 1x1 and 2x2 channel windows."""
     ops, emu = both
     torch.manual_seed(1)
     for (B, T, H, dh, gh, gw, nh) in [(2, 3, 2, 64, 4, 6, 2), (1, 5, 4, 32, 8, 8, 1)]:
@@ -67,14 +68,58 @@ def test_gate_split(both, cuda_dev):
         x = rnd(B * N, C, dev=cuda_dev)
         lg = rnd(B, H, T, N, dev=cuda_dev)
         rc = rnd(B, T, C, nh, nh, dev=cuda_dev)
+        ys = [ops.Split(B * P, C, cuda_dev) for _ in range(T)]
+        yc = [ops.Split(B * P, C, cuda_dev) for _ in range(T)]
+        big = torch.zeros(T, 2, 2, B * P, C, dtype=torch.bfloat16, device=cuda_dev)      # [task][ys|yc][plane]
+        y0, c0 = ops.Split.__new__(ops.Split), ops.Split.__new__(ops.Split)
+        for sp, j in ((y0, 0), (c0, 1)):
+            sp.rows, sp.cols, sp.ld, sp.nsplit, sp.buf = B * P, C, C, 2, big[0, j]
+        ops.gate_split(x, N, T, lg, rc, 0, y0, c0, B=B, T=T, N=N, H=H, Cdim=C, gh=gh, gw=gw, nh=nh, nw=nh, ntasks=T,
+                       task_stride=big.stride(0))
+        torch.cuda.synchronize()
         for task in range(T):
-            ys, yc = ops.Split(B * P, C, cuda_dev), ops.Split(B * P, C, cuda_dev)
-            ops.gate_split(x, N, T, lg, rc, task, ys, yc, B=B, T=T, N=N, H=H, Cdim=C, gh=gh, gw=gw, nh=nh, nw=nh)
-            eys, eyc = cpu_split(ops, ys), cpu_split(ops, yc)
+            eys, eyc = cpu_split(ops, ys[task]), cpu_split(ops, yc[task])
             emu["gate_split"](x.cpu(), N, T, lg.cpu(), rc.cpu(), task, eys, eyc, B=B, T=T, N=N, H=H, Cdim=C, gh=gh, gw=gw,
                               nh=nh, nw=nh)
-            torch.cuda.synchronize()
-            assert relerr(ys.float(), eys.float()) < 2e-5 and relerr(yc.float(), eyc.float()) < 2e-5
+            got_s = big[task, 0, 0].float() + big[task, 0, 1].float()
+            got_c = big[task, 1, 0].float() + big[task, 1, 1].float()
+            assert relerr(got_s, eys.float()) < 2e-5 and relerr(got_c, eyc.float()) < 2e-5
+
+
+def test_gemm_grouped_equals_separate_launches(both, cuda_dev):
+    """mtt_gemm_grouped == the same problems launched one by one, bit for bit (linear and 3x3 conv, ragged N)."""
+    ops, emu = both
+    torch.manual_seed(12)
+    G, M, N, K = 5, 4 * 96, 300, 200
+    A = [ops.split_f32(rnd(M, K, dev=cuda_dev)) for _ in range(G)]
+    W = [ops.pack_weight(rnd(N, K, dev=cuda_dev, scale=0.05), 2) for _ in range(G)]
+    bias = [rnd(N, dev=cuda_dev) for _ in range(G)]
+    res = [rnd(M, 304, dev=cuda_dev) for _ in range(G)]
+    o1 = [torch.zeros(M, 304, device=cuda_dev) for _ in range(G)]
+    o2 = [torch.zeros(M, 304, device=cuda_dev) for _ in range(G)]
+    s1 = [ops.Split(M, 304, cuda_dev, zero=True) for _ in range(G)]
+    s2 = [ops.Split(M, 304, cuda_dev, zero=True) for _ in range(G)]
+    kw = lambda g, o, sp: dict(N=N, bias=bias[g], act=ops.ACT_GELU, residual=res[g], out_f32=o[g], out_split=sp[g])
+    for g in range(G):
+        ops.gemm(A[g], W[g], **kw(g, o1, s1))
+    ops.gemm_grouped([(A[g], W[g], kw(g, o2, s2)) for g in range(G)])
+    torch.cuda.synchronize()
+    for g in range(G):
+        assert torch.equal(o1[g], o2[g]) and torch.equal(s1[g].buf, s2[g].buf)
+    B, H, Wd, Cin, Cout = 2, 8, 12, 70, 44
+    X = [ops.split_f32(rnd(B * H * Wd, Cin, dev=cuda_dev)) for _ in range(G)]
+    Wc = [ops.pack_conv_weight(rnd(Cout, Cin, 3, 3, dev=cuda_dev, scale=0.05), rnd(Cout, dev=cuda_dev), None, 2) for _ in range(G)]
+    c1 = [ops.Split(B * H * Wd, Cout, cuda_dev, zero=True) for _ in range(G)]
+    c2 = [ops.Split(B * H * Wd, Cout, cuda_dev, zero=True) for _ in range(G)]
+    ckw = lambda g, sp: dict(N=Cout, K=Cin, bias=Wc[g][1], act=ops.ACT_RELU, out_split=sp[g], conv=(B, H, Wd, 3, 1))
+    for g in range(G):
+        ops.gemm(X[g], Wc[g][0], **ckw(g, c1))
+    ops.gemm_grouped([(X[g], Wc[g][0], ckw(g, c2)) for g in range(G)])
+    torch.cuda.synchronize()
+    for g in range(G):
+        assert torch.equal(c1[g].buf, c2[g].buf)
+    with pytest.raises(RuntimeError):       # geometry must match
+        ops.gemm_grouped([(A[0], W[0], dict(N=N, out_f32=o1[0])), (A[1], W[1], dict(N=N - 8, out_f32=o1[1]))])
 
 
 def test_ctr_weights_and_mix(both, cuda_dev):
@@ -321,18 +366,22 @@ def test_named_block_operators(both, cuda_dev):
     assert relerr(x2, rx2) < 5e-5
 
     lg, rc = rnd(B, H, T, N, dev=dev), rnd(B, T, C, 2, 2, dev=dev)
-    wsp, bsp = ops.pack_weight(rnd(e, C, dev=dev, scale=0.05), 2), rnd(e, dev=dev)
-    wch, bch = ops.pack_weight(rnd(e, C, dev=dev, scale=0.05), 2), rnd(e, dev=dev)
     e_pad = ops.round_up(e, 8)
-    cat = ops.Split(B * P, 2 * e_pad, dev, zero=True)
-    ws3 = ops.workspace(ops.workspace_bytes(L.OP_GATED_CONV1X1, rows=B * P, Cdim=C, nsplit=2), dev)
+    tasks, rtasks = [], []
+    for _ in range(T):
+        wsp, bsp = ops.pack_weight(rnd(e, C, dev=dev, scale=0.05), 2), rnd(e, dev=dev)
+        wch, bch = ops.pack_weight(rnd(e, C, dev=dev, scale=0.05), 2), rnd(e, dev=dev)
+        cat = ops.Split(B * P, 2 * e_pad, dev, zero=True)
+        tasks.append((wsp, bsp, wch, bch, cat))
+        rtasks.append((twin(wsp), bsp.cpu(), twin(wch), bch.cpu(), cpu_split(ops, cat)))
+    ws3 = ops.workspace(ops.workspace_bytes(L.OP_GATED_CONV1X1, rows=B * P, Cdim=C, nsplit=2, T=T), dev)
     kw = dict(B=B, T=T, N=N, H=H, Cdim=C, gh=gh, gw=gw, nh=2, nw=2)
-    ops.gated_conv1x1(x, N, T, lg, rc, 1, wsp, bsp, wch, bch, e, cat, e_pad, ws3, **kw)
-    rcat = cpu_split(ops, cat)
-    emu["gated_conv1x1"](x.cpu(), N, T, lg.cpu(), rc.cpu(), 1, twin(wsp), bsp.cpu(), twin(wch), bch.cpu(), e, rcat, e_pad,
-                         torch.zeros(ws3.numel(), dtype=torch.uint8), **kw)
+    ops.gated_conv1x1(x, N, T, lg, rc, tasks, e, e_pad, ws3, **kw)
+    emu["gated_conv1x1"](x.cpu(), N, T, lg.cpu(), rc.cpu(), rtasks, e, e_pad, torch.zeros(ws3.numel(), dtype=torch.uint8),
+                         **kw)
     torch.cuda.synchronize()
-    assert relerr(cat.float(), rcat.float()) < 3e-5
+    for tk, rt in zip(tasks, rtasks):
+        assert relerr(tk[4].float(), rt[4].float()) < 3e-5
 
     Cin, Cout, n_out, Hh, Ww = 40, 24, 5, 7, 9
     a = ops.split_f32(rnd(B * Hh * Ww, Cin, dev=dev))

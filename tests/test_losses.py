@@ -63,3 +63,38 @@ def test_backward_through_the_forward_restatement_matches_reference_autograd(fx)
     for k, want in m["grad_sum"].items():
         got = float(grad[k].double().sum())
         assert abs(got - want) <= 1e-5 + 2e-3 * m["grad_norm"][k], (k, got, want)
+
+
+@pytest.mark.gpu
+def test_device_losses_match_the_reference_criterion(cuda_dev, fx):
+    """mtt_b200.losses (device reductions + gradient kernels) against the values and prediction gradients the
+    REFERENCE criterion produced (golden part a), and on the all-ignored / no-positive edge cases."""
+    import mtt_b200  # noqa: F401
+    from mtt_b200 import losses as ML
+
+    c = fx["criterion"]
+    p = {"TASKS": {"NAMES": c["tasks"]}, "edge_w": 0.95, "ignore_index": 255, "ignore_invalid_area_depth": True,
+         "loss_kwargs": {"loss_weights": fx["weights"]}}
+    crit = ML.get_criterion(p)
+    preds = {t: c["preds"][t].to(cuda_dev).requires_grad_() for t in c["tasks"]}
+    labels = {t: c["labels"][t].to(cuda_dev) for t in c["tasks"]}
+    out = crit(preds, labels, tasks=c["tasks"])
+    for k, want in c["losses"].items():
+        assert abs(float(out[k].detach()) - want) <= 3e-6 * max(1.0, abs(want)), (k, float(out[k].detach()), want)
+    out["total"].backward()
+    for t in c["tasks"]:
+        d = (preds[t].grad.cpu() - c["dpreds"][t]).abs().max().item()
+        assert d <= 1e-7 + 2e-5 * c["dpreds"][t].abs().max().item(), (t, d)
+    # edge cases (the reference divides by max(n_valid, 1) / returns 0)
+    z = lambda *s: torch.randn(*s, device=cuda_dev)
+    assert float(ML.CrossEntropyLoss()(z(1, 4, 5, 6), torch.full((1, 1, 5, 6), 255.0))) == 0.0
+    assert float(ML.L1Loss(ignore_index=-1)(z(1, 1, 5, 6), torch.full((1, 1, 5, 6), -1.0))) == 0.0
+    assert float(ML.BalancedBinaryCrossEntropyLoss()(z(1, 1, 4, 4), torch.zeros(1, 1, 4, 4))) == 0.0
+    # HED weighting and a large map (more elements than one pass of the grid) against the oracle restatement
+    x, y = z(2, 1, 300, 400), (torch.rand(2, 1, 300, 400) < 0.2).float()
+    y[torch.rand(2, 1, 300, 400) < 0.05] = 255.0
+    want = loss_ref.balanced_bce(x.cpu(), y)
+    assert abs(float(ML.BalancedBinaryCrossEntropyLoss()(x, y)) - float(want)) <= 3e-6 * float(want)
+    xs, ys = z(2, 21, 300, 400), torch.randint(0, 21, (2, 1, 300, 400)).float()
+    want = loss_ref.cross_entropy(xs.cpu(), ys)
+    assert abs(float(ML.CrossEntropyLoss()(xs, ys)) - float(want)) <= 3e-6 * float(want)
