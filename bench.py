@@ -35,8 +35,9 @@ WORKLOAD = {
     "tp_cfg2": "TaskPrompter ViT-B NYUD-v2 (4 tasks) 448x576 forward",
     "tp_cfg5": "TaskPrompter ViT-L Cityscapes-3D shape (seg + depth + 18-channel 3ddet ConvHead stand-in) 1024x2048 forward",
     "ip_cfg3": "InvPT ViT-L PASCAL-Context (5 tasks) 512x512 forward",
+    "tps_swinB": "TaskPrompter Swin-B Cityscapes-3D shape (seg + depth, DEConvHead) 1024x2048 forward",
 }
-DEFAULT_BATCH = {"tp_cfg4": 4, "tp_cfg2": 4, "tp_cfg5": 1, "ip_cfg3": 4}
+DEFAULT_BATCH = {"tp_cfg4": 4, "tp_cfg2": 4, "tp_cfg5": 1, "ip_cfg3": 4, "tps_swinB": 1}
 
 
 def family(cfg_name):
@@ -45,6 +46,9 @@ def family(cfg_name):
     if cfg_name.startswith("ip_"):
         from mtt_b200 import invpt as M
         return configs.invpt(cfg_name), M, "oracle.invpt_ref"
+    if cfg_name.startswith("tps_"):
+        from mtt_b200 import taskprompter_swin as M
+        return configs.taskprompter_swin(cfg_name), M, "oracle.taskprompter_swin_ref"
     from mtt_b200 import taskprompter as M
     return configs.taskprompter(cfg_name), M, "oracle.taskprompter_ref"
 
@@ -152,9 +156,10 @@ def reference_forward(cfg_name, device="cpu"):
     R = importlib.import_module(oracle_name)
     sd = R.init_state_dict(cfg, seed=0)
     if ref_loader.available():
-        build = ref_loader.build_invpt if cfg_name.startswith("ip_") else ref_loader.build_taskprompter
+        build = (ref_loader.build_invpt if cfg_name.startswith("ip_") else
+                 ref_loader.build_taskprompter_swin if cfg_name.startswith("tps_") else ref_loader.build_taskprompter)
         model = build(cfg).eval()
-        model.load_state_dict(sd, strict=True)
+        model.load_state_dict(sd, strict=not cfg_name.startswith("tps_"))   # Swin: index / mask buffers are derived
         model = model.to(device)
         return (lambda x: model(x)), "reference", cfg
     sd = {k: v.to(device) for k, v in sd.items()}
@@ -463,7 +468,7 @@ def run_ours(args):
         line["gpu_eager_baseline"] = ge
     if world == 1 and not args.no_cpu_baseline:
         threads = pick_cpu_threads()
-        n_fwd = 1 if args.config == "tp_cfg5" else 3
+        n_fwd = 1 if args.config in ("tp_cfg5", "tps_swinB") else 3
         rate, sec, kind = cpu_oracle_rate(args.config, n_fwd, 1, threads)
         line["cpu_baseline"] = {"value": rate, "unit": "images/s", "cores": threads, "kind": kind,
                                 "sample": f"{n_fwd} forward(s) of batch 1 of {args.config} (fp32 eager, eval, "

@@ -425,6 +425,53 @@ size_t mtt_nms_workspace_bytes(int32_t n);
 int mtt_nms_bev(const float* boxes, int32_t n, float thresh, int32_t rotated, int64_t* keep, int32_t* num_keep,
                 void* workspace, size_t ws_bytes, mtt_stream_t stream);
 
+/* ---- Swin-backbone TaskPrompter (TP = TaskPrompter/models/transformers/taskprompter_swin.py) --------
+ * The joint window stream has, for image b and window w (row-major over the zero-padded, cyclically shifted map),
+ * T prompt rows followed by ws*ws token rows: rows [(b*nW + w)*(T + ws*ws), ...). Geometry is always given as the
+ * un-padded map (H, W), the window size ws and the cyclic shift (0 <= shift < ws); padding to multiples of ws is implied.
+ *
+ * mtt_swin_window_gather: LN1 outputs xn [B*H*W, C] and pn [B*T, C] (fp32) -> split joint window stream (TP:326-340,
+ *   :177-181; padding rows are zero).
+ * mtt_swin_window_attention: per (window, head) softmax((q k^T) * scale + B) v over the T + L tokens of a window, B =
+ *   relative-position bias (+ shift mask of window w % nW) on the patch x patch entries only (TP:183-206). qkv = split
+ *   output of the qkv GEMM on the joint stream, columns (q|k|v, head, head_dim). biasT [heads, L, L] and maskT
+ *   [nW, L, L] (NULL = no shift) are stored TRANSPOSED ([.., key, query]). raw [BW, heads, T, L] receives the un-scaled
+ *   q.k of the prompt rows against the window's tokens (TP:189). head_dim in {8, 16, 32, 64}.
+ * mtt_swin_window_scatter: o = proj output on the joint stream (fp32) -> xa [B*H*W, C] (window reverse, un-shift,
+ *   crop; TP:343-360), x += xa (TP:399), prompts += mean over windows of the prompt rows (TP:210; skipped when
+ *   update_prompts = 0), and raw -> logits [B, heads, T, T + H*W] at column T + pixel: the layout mtt_gate_split reads.
+ * mtt_transpose_split: [B, L, C] fp32 -> split [B*C, ld_out >= L]: the A operand of chan_kv (TP:379).
+ * mtt_swin_chan_attention: q [B*T, ce], kv [B*C, 2*ce] (k | v) fp32 -> raw_chan [B,T,C,nh,nw] = un-scaled logits between
+ *   each prompt and each CHANNEL inside every window of the sqrt(ce) x sqrt(ce) embedding grid, and chan_out [B*T, ce]
+ *   (fp32 + split) = softmax(raw * ce^-1/2) v (TP:383-396).
+ * mtt_swin_merge_gather: [B,H,W,C] -> [B*(H/2)*(W/2), 4C], quadrant order (0,0), (1,0), (0,1), (1,1) (TP:441-447).
+ * mtt_conv3x3_s2_maps: stride-2 3x3 conv (pad 1) over maps stored as in[b, ci, in_offset + y*W + x] with channel stride
+ *   in_stride (PatchMerging.spa_attn_ds on the logit maps, TP:458-460). w [Cout, Cin, 3, 3].
+ * mtt_swin_chan_up: out[bt, o, win] = sum_c w[o, c] raw_chan[bt, c, win] (process_chan_attn, TP:463-466). */
+int mtt_swin_window_gather(const float* xn, int64_t ldx, const float* pn, int64_t ldp, int32_t B, int32_t H, int32_t W,
+                           int32_t C, int32_t T, int32_t ws, int32_t shift, void* out_hi, void* out_lo, int64_t ld_out,
+                           mtt_stream_t stream);
+int mtt_swin_window_attention(const void* qkv_hi, const void* qkv_lo, int64_t ldq, int32_t BW, int32_t nW, int32_t T,
+                              int32_t L, int32_t heads, int32_t head_dim, float scale, const float* biasT,
+                              const float* maskT, void* out_hi, void* out_lo, int64_t ldo, float* raw,
+                              mtt_stream_t stream);
+int mtt_swin_window_scatter(const float* o, int64_t ldo, const float* raw, int32_t B, int32_t H, int32_t W, int32_t C,
+                            int32_t T, int32_t ws, int32_t shift, int32_t heads, int32_t update_prompts, float* xa,
+                            int64_t ldxa, float* x, int64_t ldx, float* prompts, int64_t ldp, float* logits,
+                            mtt_stream_t stream);
+int mtt_transpose_split(const float* in, int64_t ld_in, int32_t B, int32_t L, int32_t C, void* out_hi, void* out_lo,
+                        int64_t ld_out, mtt_stream_t stream);
+int mtt_swin_chan_attention(const float* q, int64_t ldq, const float* kv, int64_t ldkv, int32_t B, int32_t T, int32_t C,
+                            int32_t ce, int32_t nh, int32_t nw, float* chan_out, int64_t ldco, void* cs_hi, void* cs_lo,
+                            int64_t ldcs, float* raw_chan, mtt_stream_t stream);
+int mtt_swin_merge_gather(const float* x, int64_t ldx, int32_t B, int32_t H, int32_t W, int32_t C, float* out, int64_t ldo,
+                          mtt_stream_t stream);
+int mtt_conv3x3_s2_maps(const float* in, const float* w, const float* bias, int32_t B, int32_t Cin, int32_t Cout, int32_t H,
+                        int32_t W, int64_t in_stride, int32_t in_offset, int64_t out_stride, int32_t out_offset, float* out,
+                        mtt_stream_t stream);
+int mtt_swin_chan_up(const float* raw_chan, const float* w, int32_t BT, int32_t C, int32_t Cout, int32_t nwin, float* out,
+                     mtt_stream_t stream);
+
 /* ---- layout changes at the nn.Module boundaries (ConvHead.forward takes / returns NCHW like the reference) ---- */
 int mtt_nchw_to_nhwc_split(const float* in, int32_t B, int32_t C, int32_t H, int32_t W, void* out_hi, void* out_lo,
                            int64_t ld_out, mtt_stream_t stream);

@@ -96,9 +96,11 @@ __device__ __forceinline__ float softmax_block5(uint32_t taddr, int kn, float sl
 // the exp unit's pipe): packed FFMA2 / FADD2, truncation split through PRMT, both 32-column TMEM loads in flight
 // before the first use, and NO per-element maximum -- an exponent that ran away from the running maximum shows up
 // in the row sum (any p > 2^kA5LazyLog2 makes sum exceed it), which is all the caller needs to trigger its redo path.
-// POLY: every fourth pair takes its exponentials from ex2_poly2 (FMA pipe) instead of MUFU.EX2: the exp unit
-// (16 results per clock per SM) is the busiest pipe of the softmax phase when both resident CTAs are in it.
-template <bool FULL, int NSPLIT, bool POLY>
+// RN_LO: round the lo plane of P to nearest instead of truncating it (two more ALU instructions per pair; the default
+// truncates and removes the mean truncation loss in the item epilogue). Measured and dropped: taking a quarter of the
+// exponentials from a degree-5 FMA-pipe polynomial instead of MUFU.EX2 (57-59 us against 55: the softmax warps are
+// bound by issue slots and dependent-issue latency, not by the exp unit; profiles/r2_attention.md).
+template <bool FULL, int NSPLIT, bool RN_LO>
 __device__ __forceinline__ float softmax_block6(uint32_t taddr, int kn, float sl2, float mb, uint32_t (&ph)[32],
                                                uint32_t (&pl)[32], float* export_ptr) {
   const int ncols = FULL ? 64 : ((kn + 15) & ~15);
@@ -126,14 +128,15 @@ __device__ __forceinline__ float softmax_block6(uint32_t taddr, int kn, float sl
 #pragma unroll
     for (int i = 0; i < 32; i += 2) {
       const float2 t = ffma2(make_float2(__uint_as_float(s[i]), __uint_as_float(s[i + 1])), c2, m2);
-      float2 p = (POLY && ((i >> 1) & 3) == 3) ? ex2_poly2(t) : make_float2(ex2_approx(t.x), ex2_approx(t.y));
+      float2 p = make_float2(ex2_approx(t.x), ex2_approx(t.y));
       if (!FULL) {
         if (c * 32 + i >= kn) p.x = 0.f;
         if (c * 32 + i + 1 >= kn) p.y = 0.f;
       }
       acc = fadd2(acc, p);
       if (NSPLIT == 2) {
-        split_trunc2(p, ph[c * 16 + (i >> 1)], pl[c * 16 + (i >> 1)]);
+        if (RN_LO) split_trunc_rn2(p, ph[c * 16 + (i >> 1)], pl[c * 16 + (i >> 1)]);
+        else split_trunc2(p, ph[c * 16 + (i >> 1)], pl[c * 16 + (i >> 1)]);
       } else {
         ph[c * 16 + (i >> 1)] = pack_bf16x2(p.x, p.y);
       }
@@ -159,15 +162,15 @@ __device__ __forceinline__ float block_max5(uint32_t taddr, int kn) {
   return mx;
 }
 
-// MODE 0: the round-1 softmax pass; 1: packed-math pass; 2: packed-math pass with a quarter of the exponentials
-// on the FMA pipe
+// MODE 0: the round-1 softmax pass; 1: packed-math pass, truncated P planes with the mean loss folded into the
+// normalisation (default); 2: packed-math pass with the lo plane of P rounded to nearest
 template <int NSPLIT, bool TRACE, int MODE>
 __global__ void __launch_bounds__(kA5Threads, 2)
 attention5_kernel(const __grid_constant__ CUtensorMap tmq_hi, const __grid_constant__ CUtensorMap tmq_lo,
                   const __grid_constant__ CUtensorMap tmk_hi, const __grid_constant__ CUtensorMap tmk_lo,
                   const Attn5Params p) {
   constexpr bool FAST = MODE > 0;
-  constexpr bool POLY = MODE == 2;
+  constexpr bool RN_LO = MODE == 2;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -413,8 +416,8 @@ attention5_kernel(const __grid_constant__ CUtensorMap tmq_hi, const __grid_const
         if (j == 0) m_run = full ? block_max5<true>(tS, kn) : block_max5<false>(tS, kn);
         bool need;
         if (FAST) {
-          sum = full ? softmax_block6<true, NSPLIT, POLY>(tS, kn, p.scale_log2, m_run * p.scale_log2, ph, pl, ex)
-                     : softmax_block6<false, NSPLIT, false>(tS, kn, p.scale_log2, m_run * p.scale_log2, ph, pl, ex);
+          sum = full ? softmax_block6<true, NSPLIT, RN_LO>(tS, kn, p.scale_log2, m_run * p.scale_log2, ph, pl, ex)
+                     : softmax_block6<false, NSPLIT, RN_LO>(tS, kn, p.scale_log2, m_run * p.scale_log2, ph, pl, ex);
           // some p above 2^kA5LazyLog2 => the sum is above it too (the converse may fire early: a harmless redo);
           // an overflowed (inf) or NaN sum takes the redo path as well
           need = !(sum <= exp2f(kA5LazyLog2));
@@ -463,7 +466,9 @@ attention5_kernel(const __grid_constant__ CUtensorMap tmq_hi, const __grid_const
       // ---- item epilogue: O / l.  PV_0 of the next item (which overwrites O) needs this warp's next P.
       mbar_wait(&pv_done[(g - 1) & 1], ((g - 1) >> 1) & 1);
       tc_fence_after();
-      const float inv = 1.0f / l_run;
+      // MODE 1 truncates both planes of P: their mean loss (kSplitTruncBias per element) is removed here, where the
+      // probabilities are normalised by the sum l of the un-truncated p
+      const float inv = (MODE == 1 && NSPLIT == 2) ? 1.0f / (l_run * (1.0f - kSplitTruncBias)) : 1.0f / l_run;
       const long long off = ((long long)b * p.N + q_row) * C + h * 64;
 #pragma unroll
       for (int c = 0; c < 2; ++c) {

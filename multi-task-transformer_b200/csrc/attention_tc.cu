@@ -44,8 +44,8 @@ extern "C" int mtt_attention(const mtt_attn_desc* d, mtt_stream_t stream_) {
   }
   ProfileScope prof(static_cast<cudaStream_t>(stream_), 1, 4.0 * d->B * d->H * (double)d->N * d->N * 64, d->B * d->N, d->N,
                     d->H * 64);
-  // variant 5 = the round-1 softmax pass (rounded split, per-element maximum); 6 = the packed-math pass; 7 = packed
-  // math with a quarter of the exponentials as FMA-pipe polynomials; 0 = default
+  // variant 5 = the round-1 softmax pass (rounded split, per-element maximum); 0 / 6 = the packed-math pass with
+  // truncated P planes (default); 7 = packed-math pass with the lo plane of P rounded to nearest
   const int mode = g_attn_variant == 5 ? 0 : (g_attn_variant == 7 ? 2 : 1);
   return launch_attention5(d, mode, static_cast<cudaStream_t>(stream_));
 }

@@ -437,37 +437,27 @@ __device__ __forceinline__ float2 fsub2(float2 a, float2 b) {
 }
 
 // Split of a NON-NEGATIVE finite pair (softmax probabilities) into bf16 planes on the integer / FMA pipes only (no
-// F2FP, which shares the 16-lane XU pipe with MUFU.EX2): hi = the upper 16 bits of p (TRUNCATED, one PRMT), lo = the
-// exact residual p - hi in [0, ulp_bf16(p)) ROUNDED to bf16 by adding 0x8000 to its bit pattern (the residual is
-// finite and non-negative, so the carry can only move it to the next bf16).  |p - (hi + lo)| <= 2^-17 ulp-scaled
-// (2^-16 p worst case), zero-mean: a truncated lo plane is 4x coarser and biases every probability downwards, which
-// showed up as a 20 % larger end-to-end error on the InvPT outputs.
+// F2FP, which shares the 16-lane XU pipe with MUFU.EX2, no integer adds): hi = the upper 16 bits of p (PRMT), lo = the
+// upper 16 bits of the exact residual p - hi (FADD2 + PRMT) -- both TRUNCATED.  p - (hi + lo) lies in [0, 2^-15 p)
+// with mean kSplitTruncBias * p and standard deviation 6.5e-6 p (measured over p = 2^t, t uniform; rounding the lo
+// plane instead gives mean 0, std 4.9e-6 but costs two more ALU instructions per pair = 4 us of the 55 us cfg4
+// attention launch).  The one-sided mean is removed where the probabilities are normalised: the attention kernel
+// divides O by l * (1 - kSplitTruncBias), l being the sum of the un-truncated p.
+constexpr float kSplitTruncBias = 7.0e-6f;
 __device__ __forceinline__ void split_trunc2(float2 p, uint32_t& hi, uint32_t& lo) {
   const uint32_t u0 = __float_as_uint(p.x), u1 = __float_as_uint(p.y);
   hi = __byte_perm(u0, u1, 0x7632);
   const float2 h = make_float2(__uint_as_float(hi << 16), __uint_as_float(hi & 0xFFFF0000u));
   const float2 r = fsub2(p, h);
-  lo = __byte_perm(__float_as_uint(r.x) + 0x8000u, __float_as_uint(r.y) + 0x8000u, 0x7632);
+  lo = __byte_perm(__float_as_uint(r.x), __float_as_uint(r.y), 0x7632);
 }
-
-// 2^t for a pair on the FMA / integer pipes (no MUFU): t = n + f with n = round(t), f in [-0.5, 0.5]; 2^f by a
-// degree-5 polynomial (least-squares fit on Chebyshev nodes, relative error 2.5e-7 in fp32 Horner), 2^n by adding n to
-// the exponent field. n comes out of the "magic number" addition 1.5 * 2^23 + t, whose low mantissa bits hold n in
-// two's complement. Arguments below -125 are clamped (result ~2^-125 instead of a denormal: zero for the softmax).
-__device__ __forceinline__ float2 ex2_poly2(float2 t) {
-  t.x = fmaxf(t.x, -125.f);
-  t.y = fmaxf(t.y, -125.f);
-  const float2 magic = make_float2(12582912.f, 12582912.f);
-  const float2 r = fadd2(t, magic);
-  const float2 f = fsub2(t, fsub2(r, magic));
-  float2 p = make_float2(0.0013400432653725147f, 0.0013400432653725147f);
-  p = ffma2(p, f, make_float2(0.009676037356257439f, 0.009676037356257439f));
-  p = ffma2(p, f, make_float2(0.05550327152013779f, 0.05550327152013779f));
-  p = ffma2(p, f, make_float2(0.2402210682630539f, 0.2402210682630539f));
-  p = ffma2(p, f, make_float2(0.6931471824645996f, 0.6931471824645996f));
-  p = ffma2(p, f, make_float2(1.0000001192092896f, 1.0000001192092896f));
-  return make_float2(__uint_as_float(__float_as_uint(p.x) + (__float_as_uint(r.x) << 23)),
-                     __uint_as_float(__float_as_uint(p.y) + (__float_as_uint(r.y) << 23)));
+// the same with the lo plane rounded to nearest (add 0x8000 to the bit pattern of the non-negative residual)
+__device__ __forceinline__ void split_trunc_rn2(float2 p, uint32_t& hi, uint32_t& lo) {
+  const uint32_t u0 = __float_as_uint(p.x), u1 = __float_as_uint(p.y);
+  hi = __byte_perm(u0, u1, 0x7632);
+  const float2 h = make_float2(__uint_as_float(hi << 16), __uint_as_float(hi & 0xFFFF0000u));
+  const float2 r = fsub2(p, h);
+  lo = __byte_perm(__float_as_uint(r.x) + 0x8000u, __float_as_uint(r.y) + 0x8000u, 0x7632);
 }
 
 // bare MUFU.EX2 (2 ulp, flushes denormal results to zero): no range fix-up code around it

@@ -30,6 +30,8 @@ def boxes_iou_bev(boxes_a, boxes_b):
 def _pairwise(boxes_a, boxes_b, mode):
     a, b = _boxes(boxes_a), _boxes(boxes_b)
     out = a.new_zeros((a.shape[0], b.shape[0]))
+    if out.numel() == 0:
+        return out
     rc = _L.load().mtt_boxes_bev_pairwise(_ptr(a), a.shape[0], _ptr(b), b.shape[0], mode, _ptr(out), _stream())
     _L.check(rc, "mtt_boxes_bev_pairwise")
     return out

@@ -138,6 +138,17 @@ SYMBOLS = {
     "mtt_boxes_bev_pairwise": (C.c_int, [_vp, _i32, _vp, _i32, _i32, _vp, _vp]),
     "mtt_nms_workspace_bytes": (C.c_size_t, [_i32]),
     "mtt_nms_bev": (C.c_int, [_vp, _i32, _f32, _i32, _vp, _vp, _vp, C.c_size_t, _vp]),
+    "mtt_swin_window_gather": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _i64, _vp]),
+    "mtt_swin_window_attention": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _vp, _vp, _vp, _vp,
+                                            _i64, _vp, _vp]),
+    "mtt_swin_window_scatter": (C.c_int, [_vp, _i64, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _i64,
+                                          _vp, _i64, _vp, _i64, _vp, _vp]),
+    "mtt_transpose_split": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _vp, _vp, _i64, _vp]),
+    "mtt_swin_chan_attention": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _i64, _vp, _vp,
+                                          _i64, _vp, _vp]),
+    "mtt_swin_merge_gather": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _i32, _vp, _i64, _vp]),
+    "mtt_conv3x3_s2_maps": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i64, _i32, _i64, _i32, _vp, _vp]),
+    "mtt_swin_chan_up": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp]),
     "mtt_nchw_to_nhwc_split": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _i64, _vp]),
     "mtt_nhwc_to_nchw": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp]),
 }

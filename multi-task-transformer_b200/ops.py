@@ -515,3 +515,62 @@ def nhwc_to_nchw(x, ld_in, B, Cd, H, W, out):
     assert x.dtype == torch.float32 and out.is_contiguous() and tuple(out.shape) == (B, Cd, H, W)
     rc = _L.load().mtt_nhwc_to_nchw(_ptr(x), ld_in, B, Cd, H, W, _ptr(out), _stream())
     _L.check(rc, "mtt_nhwc_to_nchw")
+
+
+# ------------------------------------------------------------------------------------------------
+# Swin-backbone TaskPrompter kernels (swin.cu)
+# ------------------------------------------------------------------------------------------------
+def swin_window_gather(xn, pn, out, *, B, H, W, Cdim, T, ws, shift):
+    """LN1 outputs xn [B*H*W, C], pn [B*T, C] (fp32) -> out: split joint window stream [B*nW*(T + ws*ws), C]."""
+    rc = _L.load().mtt_swin_window_gather(_ptr(xn), xn.stride(0), _ptr(pn), pn.stride(0), B, H, W, Cdim, T, ws, shift,
+                                          _ptr(out.hi), _ptr(out.lo), out.ld, _stream())
+    _L.check(rc, "mtt_swin_window_gather")
+
+
+def swin_window_attention(qkv, out, raw, biasT, maskT, *, BW, nW, T, L, heads, scale):
+    """Window attention with prompts; biasT [heads, L, L] / maskT [nW, L, L] are stored transposed ([.., key, query])."""
+    Cd = out.cols
+    assert biasT.is_contiguous() and (maskT is None or maskT.is_contiguous()) and raw.is_contiguous()
+    rc = _L.load().mtt_swin_window_attention(_ptr(qkv.hi), _ptr(qkv.lo), qkv.ld, BW, nW, T, L, heads, Cd // heads,
+                                             float(scale), _ptr(biasT), _ptr(maskT), _ptr(out.hi), _ptr(out.lo), out.ld,
+                                             _ptr(raw), _stream())
+    _L.check(rc, "mtt_swin_window_attention")
+
+
+def swin_window_scatter(o32, raw, xa, x, p, logits, *, B, H, W, Cdim, T, ws, shift, heads, last):
+    """proj output on the joint stream -> xa, x += xa, p += mean prompt rows (unless last), raw -> logits map."""
+    rc = _L.load().mtt_swin_window_scatter(_ptr(o32), o32.stride(0), _ptr(raw), B, H, W, Cdim, T, ws, shift, heads,
+                                           0 if last else 1, _ptr(xa), xa.stride(0), _ptr(x), x.stride(0), _ptr(p),
+                                           p.stride(0), _ptr(logits), _stream())
+    _L.check(rc, "mtt_swin_window_scatter")
+
+
+def transpose_split(x, out, *, B, L, Cdim):
+    """x fp32 [B*L, C] -> out Split [B*C, L] (per-image transpose)."""
+    rc = _L.load().mtt_transpose_split(_ptr(x), x.stride(0), B, L, Cdim, _ptr(out.hi), _ptr(out.lo), out.ld, _stream())
+    _L.check(rc, "mtt_transpose_split")
+
+
+def swin_chan_attention(q, kv, co32, cos, rc_out, *, B, T, Cdim, ce, nh, nw):
+    rc = _L.load().mtt_swin_chan_attention(_ptr(q), q.stride(0), _ptr(kv), kv.stride(0), B, T, Cdim, ce, nh, nw,
+                                           _ptr(co32), co32.stride(0), _ptr(cos.hi), _ptr(cos.lo), cos.ld, _ptr(rc_out),
+                                           _stream())
+    _L.check(rc, "mtt_swin_chan_attention")
+
+
+def swin_merge_gather(x, out, *, B, H, W, Cdim):
+    rc = _L.load().mtt_swin_merge_gather(_ptr(x), x.stride(0), B, H, W, Cdim, _ptr(out), out.stride(0), _stream())
+    _L.check(rc, "mtt_swin_merge_gather")
+
+
+def conv3x3_s2_maps(x, w, b, out, *, B, Cin, H, W, in_stride, in_offset, out_stride, out_offset):
+    assert w.is_contiguous() and x.is_contiguous() and out.is_contiguous()
+    rc = _L.load().mtt_conv3x3_s2_maps(_ptr(x), _ptr(w), _ptr(b), B, Cin, w.shape[0], H, W, in_stride, in_offset,
+                                       out_stride, out_offset, _ptr(out), _stream())
+    _L.check(rc, "mtt_conv3x3_s2_maps")
+
+
+def swin_chan_up(rc_in, w, out, *, BT, Cdim, nwin):
+    assert rc_in.is_contiguous() and w.is_contiguous() and out.is_contiguous()
+    rc = _L.load().mtt_swin_chan_up(_ptr(rc_in), _ptr(w), BT, Cdim, w.shape[0], nwin, _ptr(out), _stream())
+    _L.check(rc, "mtt_swin_chan_up")

@@ -494,7 +494,10 @@ class TaskPrompterWrapper(nn.Module):
 
     def plan(self, batch, device, postproc=False):
         mode = "postproc" if postproc else "full"
-        return _plan_for(self, (int(batch), torch.device(device), int(self.nsplit), mode), lambda: _Plan(
+        P = _Plan
+        if type(self.backbone).__name__ == "TaskPrompterSwin":       # the Swin family has its own launch plan
+            from .taskprompter_swin import _SwinPlan as P
+        return _plan_for(self, (int(batch), torch.device(device), int(self.nsplit), mode), lambda: P(
             self.backbone, self.heads, self.tasks, self.target_size, batch, torch.device(device), self.nsplit, mode=mode))
 
     def forward(self, x):

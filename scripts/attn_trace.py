@@ -13,6 +13,8 @@ import mtt_b200
 from mtt_b200 import ops, lib
 
 B, H, N = [int(x) for x in sys.argv[1:4]] if len(sys.argv) > 3 else (4, 16, 1029)
+if os.environ.get("MTT_ATTN_VARIANT"):
+    ops.set_attention_variant(int(os.environ["MTT_ATTN_VARIANT"]))
 dev = torch.device("cuda:0")
 C = H * 64
 qkv = ops.split_f32(torch.randn(B * N, 3 * C, device=dev), 2)

@@ -338,9 +338,99 @@ def install(mp):
     def workspace(nbytes, device):
         return torch.zeros(max(int(nbytes), 256), dtype=torch.uint8, device=device)
 
+    # ---- Swin TaskPrompter kernels (swin.cu): restated from the algorithm (TP taskprompter_swin.py line numbers in
+    # ---- multi-task-transformer_b200/taskprompter_swin.py), on the same buffers and layouts
+    def _win_index(B, H, W, ws, shift):
+        """For every (b, window, token): source pixel index into [B*H*W] or -1 (zero padding), in joint-stream order."""
+        Hp, Wp = H + (ws - H % ws) % ws, W + (ws - W % ws) % ws
+        ys, xs = torch.meshgrid(torch.arange(Hp), torch.arange(Wp), indexing="ij")
+        sy, sx = (ys + shift) % Hp, (xs + shift) % Wp           # rolled frame (y', x') reads padded frame (y' + s, x' + s)
+        src = torch.where((sy < H) & (sx < W), sy * W + sx, torch.full_like(sy, -1))       # [Hp, Wp]
+        win = src.reshape(Hp // ws, ws, Wp // ws, ws).permute(0, 2, 1, 3).reshape(-1, ws * ws)   # [nW, ws*ws]
+        return win, Hp, Wp
+
+    def swin_window_gather(xn, pn, out, *, B, H, W, Cdim, T, ws, shift):
+        win, Hp, Wp = _win_index(B, H, W, ws, shift)
+        nW, wl = win.shape
+        rows = torch.zeros(B, nW, T + wl, Cdim)
+        xb = xn[:, :Cdim].reshape(B, H * W, Cdim)
+        rows[:, :, :T] = pn[:, :Cdim].reshape(B, 1, T, Cdim)
+        g = xb[:, win.clamp(min=0).reshape(-1)].reshape(B, nW, wl, Cdim)
+        rows[:, :, T:] = g * (win >= 0).reshape(1, nW, wl, 1)
+        _wsplit(out, rows.reshape(-1, Cdim))
+
+    def swin_window_attention(qkv, out, raw, biasT, maskT, *, BW, nW, T, L, heads, scale):
+        bias = biasT.transpose(1, 2)                                          # stored [.., key, query]
+        mask = maskT.transpose(1, 2) if maskT is not None else None
+        Cdim = out.cols
+        dh = Cdim // heads
+        N = T + L
+        x = _rsplit(qkv, 3 * Cdim).reshape(BW, N, 3, heads, dh).permute(2, 0, 3, 1, 4)
+        q, k, v = x[0], x[1], x[2]
+        r = q @ k.transpose(-2, -1)                                           # [BW, heads, N, N], un-scaled
+        lg = r * scale
+        extra = bias[None]                                                    # [1, heads, L, L]
+        if mask is not None:
+            extra = extra + mask.repeat(BW // nW, 1, 1)[:, None]
+        lg[:, :, T:, T:] = lg[:, :, T:, T:] + extra
+        o = (lg.softmax(-1) @ v).transpose(1, 2).reshape(BW * N, Cdim)
+        _wsplit(out, o)
+        raw.copy_(r[:, :, :T, T:])
+
+    def swin_window_scatter(o32, raw, xa, x, p, logits, *, B, H, W, Cdim, T, ws, shift, heads, last):
+        win, Hp, Wp = _win_index(B, H, W, ws, shift)
+        nW, wl = win.shape
+        o = o32[:, :Cdim].reshape(B, nW, T + wl, Cdim)
+        valid = (win >= 0).reshape(-1)
+        idx = win.reshape(-1)[valid]
+        xa_b = xa[:, :Cdim].reshape(B, H * W, Cdim)
+        xa_b[:, idx] = o[:, :, T:].reshape(B, nW * wl, Cdim)[:, valid]
+        x[:, :Cdim] += xa[:, :Cdim]
+        if not last:
+            p[:, :Cdim] += o[:, :, :T].mean(dim=1).reshape(B * T, Cdim)
+        r = raw.reshape(B, nW, heads, T, wl).permute(0, 2, 3, 1, 4).reshape(B, heads, T, nW * wl)
+        lg = logits.reshape(B, heads, T, -1)
+        lg[..., T + idx] = r[..., valid]
+
+    def transpose_split(x, out, *, B, L, Cdim):
+        _wsplit(out, x[:, :Cdim].reshape(B, L, Cdim).transpose(1, 2).reshape(B * Cdim, L))
+
+    def swin_chan_attention(q, kv, co32, cos, rc, *, B, T, Cdim, ce, nh, nw):
+        r = int(round(math.sqrt(ce)))
+        wh, ww = r // nh, r // nw
+        qq = q[:, :ce].reshape(B, T, ce)
+        k = kv[:, :ce].reshape(B, Cdim, ce)
+        v = kv[:, ce:2 * ce].reshape(B, Cdim, ce)
+
+        def grid(t):
+            n = t.shape[1]
+            return t.reshape(B, n, nh, wh, nw, ww).permute(0, 2, 4, 1, 3, 5).reshape(B, nh * nw, n, wh * ww)
+        qg, kg, vg = grid(qq), grid(k), grid(v)
+        raw_c = qg @ kg.transpose(-2, -1)                                     # [B, nh*nw, T, C]
+        out = (raw_c * ce ** -0.5).softmax(-1) @ vg                           # [B, nh*nw, T, wh*ww]
+        out = out.reshape(B, nh, nw, T, wh, ww).permute(0, 3, 1, 4, 2, 5).reshape(B * T, ce)
+        co32[:, :ce] = out
+        _wsplit(cos, out)
+        rc.copy_(raw_c.reshape(B, nh, nw, T, Cdim).permute(0, 3, 4, 1, 2))
+
+    def swin_merge_gather(x, out, *, B, H, W, Cdim):
+        g = x[:, :Cdim].reshape(B, H, W, Cdim)
+        m = torch.cat([g[:, 0::2, 0::2], g[:, 1::2, 0::2], g[:, 0::2, 1::2], g[:, 1::2, 1::2]], dim=-1)
+        out[:, :4 * Cdim] = m.reshape(-1, 4 * Cdim)
+
+    def conv3x3_s2_maps(x, w, b, out, *, B, Cin, H, W, in_stride, in_offset, out_stride, out_offset):
+        Cout = w.shape[0]
+        xi = x.reshape(B, Cin, in_stride)[:, :, in_offset:in_offset + H * W].reshape(B, Cin, H, W)
+        y = F.conv2d(xi, w, b, stride=2, padding=1)
+        out.reshape(B, Cout, out_stride)[:, :, out_offset:out_offset + (H // 2) * (W // 2)] = y.reshape(B, Cout, -1)
+
+    def swin_chan_up(rc, w, out, *, BT, Cdim, nwin):
+        r = rc.reshape(BT, Cdim, nwin)
+        out.copy_(torch.einsum("oc,bcw->bow", w, r).reshape(out.shape))
+
     for name, fn in list(locals().items()):
-        if callable(fn) and hasattr(ops, name) and name not in ("mp",):
-            mp.setattr(ops, name, fn)
+        if callable(fn) and not name.startswith("_") and name not in ("mp",):
+            mp.setattr(ops, name, fn, raising=False)
     mp.setattr(ops._L, "check", lambda rc, what: None)
 
     class _FakeLib:
