@@ -29,7 +29,8 @@ sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
 _OUT = sys.stdout  # main() replaces it with a duplicate of the original stdout
-GFLOP_PER_IMAGE = {"tp_cfg4": 993.2, "tp_cfg2": 1163.5, "tp_cfg5": 12842.7, "ip_cfg3": 1344.8}
+GFLOP_PER_IMAGE = {"tp_cfg4": 993.2, "tp_cfg2": 1163.5, "tp_cfg5": 12842.7, "ip_cfg3": 1344.8,
+                   "tps_swinB": 3678.8}  # SURVEY.md 8(d); tps_swinB: FlopCounterMode over the oracle forward (bs 1)
 WORKLOAD = {
     "tp_cfg4": "TaskPrompter ViT-L PASCAL-Context (5 tasks) 512x512 forward",
     "tp_cfg2": "TaskPrompter ViT-B NYUD-v2 (4 tasks) 448x576 forward",
