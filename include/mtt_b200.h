@@ -124,10 +124,15 @@ typedef struct {
 } mtt_gemm_desc;
 
 int mtt_gemm(const mtt_gemm_desc* d, mtt_stream_t stream);
-/* `count` (<= 12) problems that differ ONLY in their pointers (operands, bias, residual, outputs) as one persistent
+/* `count` (<= 32) problems that differ ONLY in their pointers (operands, bias, residual, outputs) as one persistent
  * launch: the T per-task 1x1 / 3x3 convs of a decoder level (TP taskprompter.py:447,:468,:362 for every task) are 96
  * tiles each -- less than one wave of 148 SMs -- and run as T x 96 tiles here. Same function as `count` mtt_gemm calls. */
 int mtt_gemm_grouped(const mtt_gemm_desc* d, int32_t count, mtt_stream_t stream);
+/* out[m, n] = bias[n] + sum_s partial[s][m, n] (fixed order: bitwise reproducible): the reduction step of a split-K GEMM
+ * whose K chunks ran as the problems of one mtt_gemm_grouped launch (skinny M with a very long K: the Swin TaskPrompter's
+ * chan_kv, Linear(H*W -> 2*ce) over 128 .. 1024 channel rows, TP taskprompter_swin.py:379). partial fp32 [S, M, ld]. */
+int mtt_sum_partials(const float* partial, int32_t S, int64_t M, int32_t N, int64_t ld, const float* bias, float* out,
+                     int64_t ldo, mtt_stream_t stream);
 /* Kernel variant used by mtt_gemm: 0 = automatic (default; also env MTT_GEMM_VARIANT), 1 = single-CTA
  * 128x128 tiles, 2 = CTA pair (tcgen05 cta_group::2) 256x256 tiles, 3 = CTA pair 256x128 tiles.
  * All variants compute the same function; this is a tuning / testing knob. */

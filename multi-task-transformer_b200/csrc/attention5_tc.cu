@@ -233,7 +233,7 @@ attention5_kernel(const __grid_constant__ CUtensorMap tmq_hi, const __grid_const
   const int tr_cta = (blockIdx.x == 0) ? 0 : ((blockIdx.x == gridDim.x / 2) ? 1 : -1);
   unsigned int tr_n = 1;
   auto stamp = [&](int role) {
-    if (TRACE && tr_cta >= 0 && tid == role * 128 && tr_n < 1024) p.trace[(tr_cta * 2 + role) * 1024 + tr_n++] = clock32();
+    if (TRACE && tr_cta >= 0 && tid == role * 128 && tr_n < 960) p.trace[(tr_cta * 2 + role) * 1024 + tr_n++] = clock32();
   };
   if (TRACE && tr_cta >= 0 && (tid == 0 || tid == 128)) p.trace[(tr_cta * 2 + (tid == 128)) * 1024] = smid();
 
@@ -464,8 +464,13 @@ attention5_kernel(const __grid_constant__ CUtensorMap tmq_hi, const __grid_const
       }
 
       // ---- item epilogue: O / l.  PV_0 of the next item (which overwrites O) needs this warp's next P.
+      auto stamp_e = [&](int k) {   // TRACE: epilogue timeline of the first 20 items at trace[.. + 960 + 3 * item + k]
+        if (TRACE && tr_cta >= 0 && tid == 0 && qi < 20) p.trace[(tr_cta * 2) * 1024 + 960 + 3 * qi + k] = clock32();
+      };
+      stamp_e(0);
       mbar_wait(&pv_done[(g - 1) & 1], ((g - 1) >> 1) & 1);
       tc_fence_after();
+      stamp_e(1);
       // MODE 1 truncates both planes of P: their mean loss (kSplitTruncBias per element) is removed here, where the
       // probabilities are normalised by the sum l of the un-truncated p
       const float inv = (MODE == 1 && NSPLIT == 2) ? 1.0f / (l_run * (1.0f - kSplitTruncBias)) : 1.0f / l_run;
@@ -497,6 +502,7 @@ attention5_kernel(const __grid_constant__ CUtensorMap tmq_hi, const __grid_const
         }
       }
       tc_fence_before();
+      stamp_e(2);
     }
   }
 

@@ -43,7 +43,7 @@ struct GemmParams {
 // activation, row regrouping) that differ only in their operand / bias / residual / output pointers run as ONE
 // persistent launch; tile index = problem * tiles_per_problem + tile. The per-task decoder chains of TaskPrompter
 // (5 tasks x {spatial, channel} 1x1 convs, fea_fuse) are single-wave launches (96 tiles on 148 SMs) on their own.
-constexpr int kMaxGroup = 12;
+constexpr int kMaxGroup = 32;
 struct GroupProblem {
   const float* bias;
   const float* residual;

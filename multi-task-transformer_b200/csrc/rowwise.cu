@@ -149,7 +149,31 @@ layernorm_reg_kernel(const float* __restrict__ in, long long ld_in, const float*
   }
 }
 
+__global__ void __launch_bounds__(256)
+sum_partials_kernel(const float* __restrict__ part, int S, long long M, int N, long long ld, const float* __restrict__ bias,
+                    float* __restrict__ out, long long ldo) {
+  const long long n = M * N;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    const long long m = e / N;
+    const int c = (int)(e % N);
+    float acc = bias ? bias[c] : 0.f;
+    for (int s = 0; s < S; ++s) acc += part[((long long)s * M + m) * ld + c];
+    out[m * ldo + c] = acc;
+  }
+}
+
 }  // namespace mtt
+
+extern "C" int mtt_sum_partials(const float* partial, int32_t S, int64_t M, int32_t N, int64_t ld, const float* bias,
+                                float* out, int64_t ldo, mtt_stream_t stream) {
+  using namespace mtt;
+  if (!partial || !out || S <= 0 || M <= 0 || N <= 0 || ld < N || ldo < N)
+    return set_error(MTT_ERR_BAD_SHAPE, "mtt_sum_partials: bad arguments");
+  const long long n = M * N;
+  const int blocks = (int)((n + 255) / 256 < 4096 ? (n + 255) / 256 : 4096);
+  sum_partials_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(partial, S, M, N, ld, bias, out, ldo);
+  return check_launch("mtt_sum_partials");
+}
 
 extern "C" int mtt_split_f32(const float* in, int64_t ld_in, void* out_hi, void* out_lo,
                              int64_t ld_out, int64_t rows, int32_t cols, int32_t cols_pad,

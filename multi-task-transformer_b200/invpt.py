@@ -599,14 +599,16 @@ class _Plan:
         if i > 0:
             sp = self.st[i - 1]
             skip = self.back1 if i == 1 else self.back0
-            def up_embed(k):
-                wa, ba, wb, bb_ = sw.up[k]
-                ops.bilinear(sp.xj, sp.xj.stride(0), B, sp.h, sp.w, sp.C, h, w, out_split=s.ue0[k],
-                             in_batch_rows=T * sp.h * sp.w, in_row_offset=k * sp.h * sp.w)            # UpEmbed :32
-                ops.conv3x3_bn_act(s.ue0[k], wa, ba, sp.C, Ci, ops.ACT_RELU, B=B, H=h, W=w, dil=2, mid=s.ue1[k])  # :33-35
-                ops.gemm(s.ue1[k], wb, N=Ci, K=Ci, bias=bb_, act=ops.ACT_RELU, residual=skip, res_row_mod=B * hw,
-                         out_f32=s.xj, regroup=(hw, T * hw, k * hw), conv=(B, h, w, 3, 2))            # :36-38,:406-411
-            self._par(up_embed)
+            # UpEmbed of the T tasks (invpt.py:32-38): per-task bilinear x2, then the two dilated 3x3 convs of all tasks
+            # as grouped launches (T x 96 tiles instead of T single-wave launches); the second adds the backbone skip
+            # (:406-411) and writes each task's slice of the joint token buffer
+            self._par(lambda k: ops.bilinear(sp.xj, sp.xj.stride(0), B, sp.h, sp.w, sp.C, h, w, out_split=s.ue0[k],
+                                             in_batch_rows=T * sp.h * sp.w, in_row_offset=k * sp.h * sp.w))   # :32
+            ops.gemm_grouped([(s.ue0[k], sw.up[k][0], dict(N=Ci, K=sp.C, bias=sw.up[k][1], act=ops.ACT_RELU,
+                                                          out_split=s.ue1[k], conv=(B, h, w, 3, 2))) for k in range(T)])
+            ops.gemm_grouped([(s.ue1[k], sw.up[k][2], dict(N=Ci, K=Ci, bias=sw.up[k][3], act=ops.ACT_RELU, residual=skip,
+                                                          res_row_mod=B * hw, out_f32=s.xj[k * hw:], regroup=(hw, T * hw, 0),
+                                                          conv=(B, h, w, 3, 2))) for k in range(T)])
         # ---- InvPTBlock
         ops.layernorm(s.xj, sw.n1w, sw.n1b, sw.eps, out_f32=s.xn32)                                    # :298
         ops.dwconv3x3_s2(s.xn32, sw.dw_w, sw.dw_b, s.qin, B=B, T=T, h=h, w=w, Cdim=Ci)                 # :171-173
@@ -630,21 +632,22 @@ class _Plan:
                           out_split=None if i == 0 else s.ln, out_seg_stride=B * hw)                   # :524-526
         d0 = self.dims[0]
 
+        if i > 0:       # per-task slice -> 1x1 redu_chan (:535-536), all tasks in one grouped launch
+            ops.gemm_grouped([(s.ln, sw.redu[k][0], dict(M=B * hw, bias=sw.redu[k][1], out_f32=s.rc32[k],
+                                                         a_row_offset=k * B * hw)) for k in range(T)])
+
         def aggregate(k):
-            # per-task slice -> (i > 0: 1x1 redu_chan) kept at its own resolution; after the last stage the three
-            # maps are resized to 8h0 x 8w0, summed and written ONCE as the split operand of mt_proj (:528-543)
-            if i > 0:
-                rw, rb = sw.redu[k]
-                ops.gemm(s.ln, rw, M=B * hw, bias=rb, out_f32=s.rc32[k], a_row_offset=k * B * hw)      # :535-536
-            if i == 2:
-                s0_, s1_ = self.st[0], self.st[1]
-                ops.bilinear_sum3([(s0_.ln32, s0_.h, s0_.w, 0, k * B * s0_.h * s0_.w),
-                                   (s1_.rc32[k], s1_.h, s1_.w, 0, 0),
-                                   (s.rc32[k], h, w, 0, 0)],
-                                  self.mss[k], B=B, Cdim=d0, H2=self.th, W2=self.tw)                   # :537-539
-                if self.mode in ("full", "postproc"):
-                    self._head(k)
-        self._par(aggregate)
+            # after the last stage the three per-stage maps of a task are resized to 8h0 x 8w0, summed and written ONCE
+            # as the split operand of mt_proj (:528-543)
+            s0_, s1_ = self.st[0], self.st[1]
+            ops.bilinear_sum3([(s0_.ln32, s0_.h, s0_.w, 0, k * B * s0_.h * s0_.w),
+                               (s1_.rc32[k], s1_.h, s1_.w, 0, 0),
+                               (s.rc32[k], h, w, 0, 0)],
+                              self.mss[k], B=B, Cdim=d0, H2=self.th, W2=self.tw)                       # :537-539
+            if self.mode in ("full", "postproc"):
+                self._head(k)
+        if i == 2:
+            self._par(aggregate)
         if i == 2 and self.mode in ("decoder", "invpt"):
             for k, t in enumerate(self.tasks):     # mt_proj -> NCHW x_dict (one fp32 staging map: sequential)
                 tw = W.tasks[k]
@@ -689,12 +692,16 @@ class _Plan:
         h0, w0, E = self.h0, self.w0, self.E
         ops.bilinear(self.xfin, C, B, self.gh, self.gw, C, h0, w0, out_split=self.x0)                  # transformer_decoder.py:85-86
 
+        # preliminary decoders (transformer_decoder.py:88-94): the two ConvBlocks of all tasks as grouped launches
+        ops.gemm_grouped([(self.x0, W.tasks[k].pd0, dict(N=C, K=C, bias=W.tasks[k].pd0_b, act=ops.ACT_RELU,
+                                                         out_split=self.p1[k], conv=(B, h0, w0, 3, 1))) for k in range(T)])
+        ops.gemm_grouped([(self.p1[k], W.tasks[k].pd1, dict(N=E, K=C, bias=W.tasks[k].pd1_b, act=ops.ACT_RELU,
+                                                            out_split=self.cat[k], conv=(B, h0, w0, 3, 1)))
+                          for k in range(T)])
+
         def prelim(k):
             tw = W.tasks[k]
             n = self.n_out[k]
-            ops.conv3x3_bn_act(self.x0, tw.pd0, tw.pd0_b, C, C, ops.ACT_RELU, B=B, H=h0, W=w0, mid=self.p1[k])  # ConvBlock 1
-            ops.gemm(self.p1[k], tw.pd1, N=E, K=C, bias=tw.pd1_b, act=ops.ACT_RELU, out_split=self.cat[k],
-                     conv=(B, h0, w0, 3, 1))                                                           # ConvBlock 2
             ops.gemm(self.cat[k], tw.ih, K=E, bias=tw.ih_b, out_f32=self.inter[k][:, :n], N=n,
                      out_split=self.cat[k], out_col_offset=E)                                          # :94; invpt.py:511
             if self.mode == "full":

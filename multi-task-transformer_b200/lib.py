@@ -90,6 +90,7 @@ SYMBOLS = {
     "mtt_layernorm": (C.c_int, [_vp, _i64, _vp, _vp, _f32, _vp, _i64, _vp, _vp, _i64, _i64, _i32, _vp]),
     "mtt_gemm": (C.c_int, [C.POINTER(GemmDesc), _vp]),
     "mtt_gemm_grouped": (C.c_int, [C.POINTER(GemmDesc), _i32, _vp]),
+    "mtt_sum_partials": (C.c_int, [_vp, _i32, _i64, _i32, _i64, _vp, _vp, _i64, _vp]),
     "mtt_set_gemm_variant": (None, [C.c_int]),
     "mtt_attention": (C.c_int, [C.POINTER(AttnDesc), _vp]),
     "mtt_set_attention_variant": (None, [C.c_int]),

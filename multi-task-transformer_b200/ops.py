@@ -85,7 +85,7 @@ def layernorm(x, gamma, beta, eps, out_f32=None, out_split=None):
 
 def gemm(a, w, *, M=None, N=None, K=None, bias=None, act=ACT_NONE, residual=None, res_row_mod=0,
          out_f32=None, out_split=None, out_col_offset=0, regroup=None, conv=None, a_row_offset=0,
-         a_gather=None, w_col_offset=0):
+         a_gather=None, w_col_offset=0, a_col_offset=0):
     """D = act(A @ W^T + bias) + residual on the tcgen05 GEMM.
 
     a: Split [M, K] (or NHWC activation [B*H*W, C] when ``conv=(B, H, W, ksize, dil)``);
@@ -94,7 +94,7 @@ def gemm(a, w, *, M=None, N=None, K=None, bias=None, act=ACT_NONE, residual=None
     group_stride) gathers A rows in groups (M must be given); w_col_offset selects a K-slice of a wider packed W."""
     d = _L.GemmDesc()
     _fill_gemm_desc(d, a, w, M, N, K, bias, act, residual, res_row_mod, out_f32, out_split, out_col_offset, regroup, conv,
-                    a_row_offset, a_gather, w_col_offset)
+                    a_row_offset, a_gather, w_col_offset, a_col_offset)
     rc = _L.load().mtt_gemm(C.byref(d), _stream())
     _L.check(rc, "mtt_gemm")
 
@@ -105,17 +105,35 @@ def gemm_grouped(calls):
     arr = (_L.GemmDesc * len(calls))()
     for d, (a, w, kw) in zip(arr, calls):
         k = dict(M=None, N=None, K=None, bias=None, act=ACT_NONE, residual=None, res_row_mod=0, out_f32=None,
-                 out_split=None, out_col_offset=0, regroup=None, conv=None, a_row_offset=0, a_gather=None, w_col_offset=0)
+                 out_split=None, out_col_offset=0, regroup=None, conv=None, a_row_offset=0, a_gather=None, w_col_offset=0,
+                 a_col_offset=0)
         k.update(kw)
         _fill_gemm_desc(d, a, w, **k)
     rc = _L.load().mtt_gemm_grouped(arr, len(calls), _stream())
     _L.check(rc, "mtt_gemm_grouped")
 
 
+def gemm_splitk(a, w, partial, out_f32, *, K, bias=None, chunks):
+    """out = A @ W^T + bias for a skinny A with a very long K: `chunks` K-slices run as the problems of ONE grouped
+    launch into partial [chunks, M, N] (fp32), then a fixed-order reduction adds them and the bias. K-slices are
+    multiples of 64 (the GEMM's K block)."""
+    M, N = a.rows, w.rows
+    step = round_up(-(-K // chunks), 64)
+    calls, k0 = [], 0
+    while k0 < K:
+        kk = min(step, K - k0)
+        calls.append((a, w, dict(M=M, N=N, K=kk, out_f32=partial[len(calls)], a_col_offset=k0, w_col_offset=k0)))
+        k0 += kk
+    gemm_grouped(calls) if len({c[2]["K"] for c in calls}) == 1 else [gemm(c[0], c[1], **c[2]) for c in calls]
+    rc = _L.load().mtt_sum_partials(_ptr(partial), len(calls), M, N, partial.stride(-2), _ptr(bias), _ptr(out_f32),
+                                    out_f32.stride(-2), _stream())
+    _L.check(rc, "mtt_sum_partials")
+
+
 def _fill_gemm_desc(d, a, w, M, N, K, bias, act, residual, res_row_mod, out_f32, out_split, out_col_offset, regroup, conv,
-                    a_row_offset, a_gather, w_col_offset):
+                    a_row_offset, a_gather, w_col_offset, a_col_offset=0):
     nsplit = min(a.nsplit, w.nsplit)
-    aoff = 2 * a_row_offset * a.ld
+    aoff = 2 * (a_row_offset * a.ld + a_col_offset)
     d.a_hi, d.a_lo, d.lda = a.hi.data_ptr() + aoff, (a.lo.data_ptr() + aoff if nsplit == 2 else 0), a.ld
     woff = 2 * w_col_offset
     d.b_hi, d.b_lo, d.ldb = w.hi.data_ptr() + woff, (w.lo.data_ptr() + woff if nsplit == 2 else 0), w.ld

@@ -332,6 +332,11 @@ class _SwinPlan:
                 s.q32 = z(B * T, ce)
                 s.xat = S(B * C, L, zero=True)
                 s.kv32 = z(B * C, 2 * ce)
+                # chan_kv is Linear(H*W -> 2 ce) over B*C rows: few output tiles, very long K. Split K so that about one
+                # wave of 148 CTAs is busy (K chunks are multiples of 64, at least 512 columns each)
+                tiles = -(-(B * C) // 128) * -(-(2 * ce) // 128)
+                s.kchunks = max(1, min(32, 148 // tiles, L // 512))
+                s.kv_part = z(s.kchunks, B * C, 2 * ce) if s.kchunks > 1 else None
                 s.co32, s.cos = z(B * T, ce), S(B * T, ce)
                 s.t1 = S(B * T, ce)
                 s.rc = z(B, T, C, self.nh, self.nw)
@@ -417,7 +422,10 @@ class _SwinPlan:
         # channel attention between the prompts and the channels of the attention output (:372-396)
         ops.gemm(s.chan_ps, w.cq, bias=w.cq_b, out_f32=s.q32)
         ops.transpose_split(s.xa32, s.xat, B=B, L=s.L, Cdim=C)
-        ops.gemm(s.xat, w.ckv, K=s.L, bias=w.ckv_b, out_f32=s.kv32)
+        if s.kchunks > 1:   # C rows x (H*W) columns: a handful of M tiles with thousands of K blocks -> split K
+            ops.gemm_splitk(s.xat, w.ckv, s.kv_part, s.kv32, K=s.L, bias=w.ckv_b, chunks=s.kchunks)
+        else:
+            ops.gemm(s.xat, w.ckv, K=s.L, bias=w.ckv_b, out_f32=s.kv32)
         ops.swin_chan_attention(s.q32, s.kv32, s.co32, s.cos, s.rc, B=B, T=T, Cdim=C, ce=ce, nh=self.nh, nw=self.nw)
         ops.ln_mlp_residual(s.x, w.n2w, w.n2b, w.eps, w.fc1, w.fc1_b, w.fc2, w.fc2_b, s.ws_mlp)    # :400
         if not w.last:

@@ -105,11 +105,11 @@ def window_attention(sd, pre, xw, prompts_n, heads, ws, mask):
     q, k, v = qkv[0], qkv[1], qkv[2]
     raw = q @ k.transpose(-2, -1)                                       # :189, consumed un-scaled downstream
     logits = raw * dh ** -0.5
-    bias = sd[pre + "relative_position_bias_table"].to(xw.dtype)[relative_position_index(ws).reshape(-1)]
+    bias = sd[pre + "relative_position_bias_table"].to(xw.dtype)[relative_position_index(ws).reshape(-1).to(xw.device)]
     bias = bias.reshape(L, L, heads).permute(2, 0, 1)                   # [heads, L, L]
     extra = bias[None]
     if mask is not None:                                                # window w of every image gets mask[w]
-        extra = extra + mask.to(xw.dtype).repeat(B, 1, 1)[:, None]
+        extra = extra + mask.to(xw).repeat(B, 1, 1)[:, None]          # device and dtype of the activations
     patch_part = logits[:, :, T:, T:] + extra                           # :196 / :201: only patch x patch entries
     logits = torch.cat([logits[:, :, :T, :],
                         torch.cat([logits[:, :, T:, :T], patch_part], dim=-1)], dim=2)

@@ -37,7 +37,7 @@ for cta in range(2):
     s = sm_[1:]
     m = mm_[1:]
     nblk = 0
-    while 4 * nblk + 3 < len(s) and s[4 * nblk + 3] != 0:
+    while 4 * nblk + 3 < 956 and s[4 * nblk + 3] != 0:
         nblk += 1
     t0 = s[0]
     d = lambda a, b: int((b - a) & 0xFFFFFFFF)
@@ -51,5 +51,9 @@ for cta in range(2):
               + ("   <- item boundary" if (k + 1) % nkv == 0 else ""))
         tot["wait"] += d(a, b); tot["comp"] += d(b, c_); tot["pub"] += d(c_, dd); tot["gap"] += gap
     span = d(t0, s[4 * nblk - 1])
+    ep = sm_[960:960 + 60].reshape(20, 3)
+    for it in range(20):
+        if ep[it, 2]:
+            print(f"  item {it}: epilogue waits PV_last {d(ep[it, 0], ep[it, 1])} cycles, O/l + stores {d(ep[it, 1], ep[it, 2])}")
     print(f"blocks {nblk}, span {span} cycles = {span / max(nblk, 1):.0f} / block; softmax warp 0: wait_S {tot['wait']} "
           f"compute {tot['comp']} publish {tot['pub']} between-block {tot['gap']}")

@@ -58,15 +58,15 @@ def install(mp):
 
     def gemm(a, w, *, M=None, N=None, K=None, bias=None, act=0, residual=None, res_row_mod=0, out_f32=None,
              out_split=None, out_col_offset=0, regroup=None, conv=None, a_row_offset=0, a_gather=None,
-             w_col_offset=0):
+             w_col_offset=0, a_col_offset=0):
         M = a.rows if M is None else M
         N = w.rows if N is None else N
         K = a.cols if K is None else K
         if a_gather is not None:
             r_ = torch.arange(M)
-            A = _rsplit(a, K)[a_row_offset + (r_ // a_gather[0]) * a_gather[1] + r_ % a_gather[0]]
+            A = _rsplit(a, a_col_offset + K)[a_row_offset + (r_ // a_gather[0]) * a_gather[1] + r_ % a_gather[0], a_col_offset:]
         else:
-            A = _rsplit(a, K)[a_row_offset:a_row_offset + M]
+            A = _rsplit(a, a_col_offset + K)[a_row_offset:a_row_offset + M, a_col_offset:]
         if conv is None:
             Wm = _rsplit(w, w_col_offset + K)[:N, w_col_offset:]
             y = A @ Wm.t()
@@ -94,6 +94,9 @@ def install(mp):
             out_split.buf[0, ro, out_col_offset:out_col_offset + N] = hi
             if out_split.nsplit == 2:
                 out_split.buf[1, ro, out_col_offset:out_col_offset + N] = (y - hi.float()).bfloat16()
+
+    def gemm_splitk(a, w, partial, out_f32, *, K, bias=None, chunks):
+        ops.gemm(a, w, K=K, bias=bias, out_f32=out_f32)       # the same function; the K split is a scheduling detail
 
     def gemm_grouped(calls):
         for a, w, kw in calls:

@@ -86,6 +86,23 @@ def test_gate_split(both, cuda_dev):
             assert relerr(got_s, eys.float()) < 2e-5 and relerr(got_c, eyc.float()) < 2e-5
 
 
+def test_gemm_splitk(both, cuda_dev):
+    """Skinny M with a long K (Swin chan_kv): K chunks as one grouped launch + fixed-order reduction == one GEMM."""
+    ops, emu = both
+    torch.manual_seed(13)
+    for (M, N, K, chunks) in [(96, 64, 4608, 9), (256, 96, 2304, 4), (64, 40, 1000, 3)]:   # last: unequal chunks
+        a, w = ops.split_f32(rnd(M, K, dev=cuda_dev)), ops.pack_weight(rnd(N, K, dev=cuda_dev, scale=0.05), 2)
+        bias = rnd(N, dev=cuda_dev)
+        ref = torch.zeros(M, N, device=cuda_dev)
+        ops.gemm(a, w, bias=bias, out_f32=ref)
+        part, out = torch.zeros(chunks, M, N, device=cuda_dev), torch.zeros(M, N, device=cuda_dev)
+        ops.gemm_splitk(a, w, part, out, K=K, bias=bias, chunks=chunks)
+        torch.cuda.synchronize()
+        assert relerr(out, ref) < 2e-6
+        want = a.float().double() @ w.float()[:, :K].double().t() + bias.double()
+        assert relerr(out, want) < 2e-5
+
+
 def test_gemm_grouped_equals_separate_launches(both, cuda_dev):
     """mtt_gemm_grouped == the same problems launched one by one, bit for bit (linear and 3x3 conv, ragged N)."""
     ops, emu = both
