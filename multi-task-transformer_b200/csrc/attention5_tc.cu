@@ -168,6 +168,7 @@ template <int NSPLIT, bool TRACE, int MODE>
 __global__ void __launch_bounds__(kA5Threads, 2)
 attention5_kernel(const __grid_constant__ CUtensorMap tmq_hi, const __grid_constant__ CUtensorMap tmq_lo,
                   const __grid_constant__ CUtensorMap tmk_hi, const __grid_constant__ CUtensorMap tmk_lo,
+                  const __grid_constant__ CUtensorMap tmo_hi, const __grid_constant__ CUtensorMap tmo_lo,
                   const Attn5Params p) {
   constexpr bool FAST = MODE > 0;
   constexpr bool RN_LO = MODE == 2;
@@ -188,7 +189,8 @@ attention5_kernel(const __grid_constant__ CUtensorMap tmq_hi, const __grid_const
   uint64_t* p_ready = s_ready + 2;           // [2] P_j published by the 4 softmax warps
   uint64_t* pv_done = p_ready + 2;           // [2] O += P_j V_j retired (two barriers: a softmax warp may be two
                                              //     PVs behind, which one parity bit cannot tell apart)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
+  uint64_t* o_staged = pv_done + 2;          // the item's normalised output tile sits in sQ (MODE > 0), count 4
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_staged + 1);
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -219,6 +221,7 @@ attention5_kernel(const __grid_constant__ CUtensorMap tmq_hi, const __grid_const
       mbar_init(&p_ready[s], 4);
       mbar_init(&pv_done[s], 1);
     }
+    mbar_init(o_staged, 4);
     fence_barrier_init();
   }
   __syncwarp();
@@ -273,19 +276,51 @@ attention5_kernel(const __grid_constant__ CUtensorMap tmq_hi, const __grid_const
           if (NSPLIT == 2) tma_load_3d(dv + kA5KVTile, &tmk_lo, &v_full[vs], 2 * C + h * 64, j * 64, b);
         }
         __syncwarp();
-        if (j == 0 && item + (int)gridDim.x < total) {
-          // this item's Q sits in TMEM by now (or soon): sQ can take the next item's query tile
-          mbar_wait(q_ready, qi & 1);
-          if (elect_one()) {
-            int qt2, h2, b2;
-            item_coords(item + gridDim.x, qt2, h2, b2);
-            mbar_arrive_expect_tx(q_full, NSPLIT * kA5QTile);
-            tma_load_3d(sQ, &tmq_hi, q_full, h2 * 64, qt2 * 128, b2);
-            if (NSPLIT == 2) tma_load_3d(sQ + kA5QTile, &tmq_lo, q_full, h2 * 64, qt2 * 128, b2);
+        // MODE > 0: the softmax warps stage an item's normalised O tile in sQ (free between the copy of the next Q into
+        // TMEM and the next Q prefetch) and this warp writes it out with a TMA store, so the global-memory burst of the
+        // item boundary (all CTAs finish an item together: 9.5 MB) drains behind the next item's blocks instead of in
+        // front of them. The store of item qi - 1 is issued here, at block jq of item qi; only then may the Q tile of
+        // item qi + 1 be prefetched into sQ (MODE 0 prefetches at block 0).
+        const int jq = (MODE > 0) ? (nkv - 1 < 2 ? nkv - 1 : 2) : 0;
+        if (j == jq) {
+          if (MODE > 0 && qi >= 1) {
+            mbar_wait(o_staged, (qi - 1) & 1);
+            if (elect_one()) {
+              int qt0, h0, b0;
+              item_coords(item - (int)gridDim.x, qt0, h0, b0);
+              tma_store_3d(&tmo_hi, sQ, h0 * 64, qt0 * 128, b0);
+              if (NSPLIT == 2) tma_store_3d(&tmo_lo, sQ + kA5QTile, h0 * 64, qt0 * 128, b0);
+              tma_store_commit();
+              tma_store_wait_read();
+            }
+            __syncwarp();
           }
-          __syncwarp();
+          if (item + (int)gridDim.x < total) {
+            // this item's Q sits in TMEM by now (or soon): sQ can take the next item's query tile
+            mbar_wait(q_ready, qi & 1);
+            if (elect_one()) {
+              int qt2, h2, b2;
+              item_coords(item + gridDim.x, qt2, h2, b2);
+              mbar_arrive_expect_tx(q_full, NSPLIT * kA5QTile);
+              tma_load_3d(sQ, &tmq_hi, q_full, h2 * 64, qt2 * 128, b2);
+              if (NSPLIT == 2) tma_load_3d(sQ + kA5QTile, &tmq_lo, q_full, h2 * 64, qt2 * 128, b2);
+            }
+            __syncwarp();
+          }
         }
       }
+    }
+    if (MODE > 0 && qi >= 1) {   // the last item's output tile
+      mbar_wait(o_staged, (qi - 1) & 1);
+      if (elect_one()) {
+        int qt0, h0, b0;
+        item_coords((int)blockIdx.x + (int)(qi - 1) * (int)gridDim.x, qt0, h0, b0);
+        tma_store_3d(&tmo_hi, sQ, h0 * 64, qt0 * 128, b0);
+        if (NSPLIT == 2) tma_store_3d(&tmo_lo, sQ + kA5QTile, h0 * 64, qt0 * 128, b0);
+        tma_store_commit();
+        tma_store_wait_all();
+      }
+      __syncwarp();
     }
   } else if (warp == 4) {
     // ------------------------------------------------------------------ MMA warp (elected lane issues)
@@ -480,7 +515,27 @@ attention5_kernel(const __grid_constant__ CUtensorMap tmq_hi, const __grid_const
         uint32_t o[32];
         tmem_ld32(tO + lane_addr + c * 32, o);
         tmem_ld_wait();
-        if (q_row < p.N) {
+        if (MODE > 0) {
+          // stage this thread's row of the normalised tile in sQ (this thread copied ITS row of the next Q to TMEM
+          // before it got here, nobody else touches the row) in the 128-byte-swizzled layout of the output tensor map:
+          // 16-byte chunk k of row r lives at chunk k ^ (r & 7); the TMA warp stores the tile (rows >= N are clipped)
+#pragma unroll
+          for (int i = 0; i < 32; i += 16) {
+            U32x8 hv, lv;
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              split_pack2(__uint_as_float(o[i + 2 * k]) * inv, __uint_as_float(o[i + 2 * k + 1]) * inv, hv.v[k], lv.v[k]);
+            const int ch = (c * 32 + i) >> 3;   // first of the two 16-byte chunks of these 16 columns
+            uint8_t* rowp = sQ + row * 128;
+            *reinterpret_cast<uint4*>(rowp + (((ch) ^ (row & 7)) << 4)) = make_uint4(hv.v[0], hv.v[1], hv.v[2], hv.v[3]);
+            *reinterpret_cast<uint4*>(rowp + (((ch + 1) ^ (row & 7)) << 4)) = make_uint4(hv.v[4], hv.v[5], hv.v[6], hv.v[7]);
+            if (NSPLIT == 2) {
+              *reinterpret_cast<uint4*>(rowp + kA5QTile + (((ch) ^ (row & 7)) << 4)) = make_uint4(lv.v[0], lv.v[1], lv.v[2], lv.v[3]);
+              *reinterpret_cast<uint4*>(rowp + kA5QTile + (((ch + 1) ^ (row & 7)) << 4)) =
+                  make_uint4(lv.v[4], lv.v[5], lv.v[6], lv.v[7]);
+            }
+          }
+        } else if (q_row < p.N) {
 #pragma unroll
           for (int i = 0; i < 32; i += 16) {
             U32x8 hv, lv;
@@ -500,6 +555,12 @@ attention5_kernel(const __grid_constant__ CUtensorMap tmq_hi, const __grid_const
             }
           }
         }
+      }
+      if (MODE > 0) {
+        fence_proxy_async();   // the generic-proxy writes above must be visible to the TMA (async proxy) store
+        __syncwarp();
+        if (elect_one()) mbar_arrive(o_staged);
+        __syncwarp();
       }
       tc_fence_before();
       stamp_e(2);
@@ -529,8 +590,8 @@ static int launch_attn5(const CUtensorMap* maps, const Attn5Params& p, cudaStrea
   }
   const int total = ((p.N + 127) / 128) * p.H * p.B;
   const int slots = 2 * sm_count();
-  attention5_kernel<NSPLIT, TRACE, MODE><<<total < slots ? total : slots, kA5Threads, smem, stream>>>(maps[0], maps[1], maps[2],
-                                                                                       maps[3], p);
+  attention5_kernel<NSPLIT, TRACE, MODE><<<total < slots ? total : slots, kA5Threads, smem, stream>>>(
+      maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], p);
   return check_launch("mtt_attention(variant 5)");
 }
 
@@ -538,7 +599,7 @@ extern unsigned int* g_attn_trace;  // attention_tc.cu (mtt_set_attention_trace)
 
 int launch_attention5(const mtt_attn_desc* d, int mode, cudaStream_t stream) {
   const int C = d->H * 64;
-  CUtensorMap maps[4];
+  CUtensorMap maps[6];   // q hi/lo (128-row box), k|v hi/lo (64-row box), out hi/lo (128-row box, TMA store)
   const uint64_t dims[3] = {(uint64_t)3 * C, (uint64_t)d->N, (uint64_t)d->B};
   const uint64_t str[2] = {(uint64_t)3 * C * 2, (uint64_t)d->N * 3 * C * 2};
   const uint32_t qbox[3] = {64, 128, 1};
@@ -552,6 +613,16 @@ int launch_attention5(const mtt_attn_desc* d, int mode, cudaStream_t stream) {
   } else {
     maps[1] = maps[0];
     maps[3] = maps[2];
+  }
+  {
+    const uint64_t odims[3] = {(uint64_t)C, (uint64_t)d->N, (uint64_t)d->B};
+    const uint64_t ostr[2] = {(uint64_t)C * 2, (uint64_t)d->N * C * 2};
+    if ((rc = make_tmap_bf16(&maps[4], d->out_hi, 3, odims, ostr, qbox))) return rc;
+    if (d->nsplit == 2) {
+      if ((rc = make_tmap_bf16(&maps[5], d->out_lo, 3, odims, ostr, qbox))) return rc;
+    } else {
+      maps[5] = maps[4];
+    }
   }
   Attn5Params p;
   p.B = d->B;

@@ -88,11 +88,13 @@ swin_attn_kernel(const __nv_bfloat16* __restrict__ q_hi, const __nv_bfloat16* __
   }
   __syncthreads();
   for (int i = threadIdx.x; i < N; i += blockDim.x) {
-    float q[DH], o[DH];
+    // q and the output accumulator as packed fp32 pairs: FFMA2 halves the FMA-pipe instruction count of the two dot
+    // products (sm_100 packed fp32); the accumulator is rescaled only when the running maximum moves
+    float2 q[DH / 2], o[DH / 2];
 #pragma unroll
-    for (int d = 0; d < DH; ++d) {
-      q[d] = ld_f(row0 + i, h * DH + d);
-      o[d] = 0.f;
+    for (int d = 0; d < DH / 2; ++d) {
+      q[d] = make_float2(ld_f(row0 + i, h * DH + 2 * d), ld_f(row0 + i, h * DH + 2 * d + 1));
+      o[d] = make_float2(0.f, 0.f);
     }
     float m = -INFINITY, l = 0.f;
     const bool patch_q = i >= T;
@@ -100,31 +102,41 @@ swin_attn_kernel(const __nv_bfloat16* __restrict__ q_hi, const __nv_bfloat16* __
     const float* mcol = (patch_q && maskT) ? maskT + ((long long)(bw % nW) * L) * L + (i - T) : nullptr;
     float* rrow = (!patch_q && raw) ? raw + (((long long)bw * heads + h) * T + i) * L : nullptr;
     for (int j = 0; j < N; ++j) {
-      float s = 0.f;
+      const float2* kj = reinterpret_cast<const float2*>(sK + j * DH);
+      float2 acc = make_float2(0.f, 0.f);
 #pragma unroll
-      for (int d = 0; d < DH; ++d) s = fmaf(q[d], sK[j * DH + d], s);
+      for (int d = 0; d < DH / 2; ++d) acc = ffma2(q[d], kj[d], acc);
+      float s = acc.x + acc.y;
       if (rrow && j >= T) rrow[j - T] = s;
       s *= scale;
       if (patch_q && j >= T) {
         s += bcol[(long long)(j - T) * L];
         if (mcol) s += mcol[(long long)(j - T) * L];
       }
-      const float mn = fmaxf(m, s);
-      const float a = __expf(m - mn), p = __expf(s - mn);
-      l = l * a + p;
+      if (s > m) {                                   // new running maximum: rescale what has been accumulated
+        const float a = __expf(m - s);
+        l *= a;
+        const float2 a2 = make_float2(a, a);
 #pragma unroll
-      for (int d = 0; d < DH; ++d) o[d] = fmaf(p, sV[j * DH + d], o[d] * a);
-      m = mn;
+        for (int d = 0; d < DH / 2; ++d) o[d] = make_float2(o[d].x * a2.x, o[d].y * a2.y);
+        m = s;
+      }
+      const float p = __expf(s - m);
+      l += p;
+      const float2 p2 = make_float2(p, p);
+      const float2* vj = reinterpret_cast<const float2*>(sV + j * DH);
+#pragma unroll
+      for (int d = 0; d < DH / 2; ++d) o[d] = ffma2(p2, vj[d], o[d]);
     }
     const float inv = 1.f / l;
     __nv_bfloat16* dh = o_hi + (row0 + i) * ldo + h * DH;
     __nv_bfloat16* dl = o_lo ? o_lo + (row0 + i) * ldo + h * DH : nullptr;
 #pragma unroll
-    for (int d = 0; d < DH; d += 2) {
+    for (int d = 0; d < DH / 2; ++d) {
       uint32_t hh, ll;
-      split_pack2(o[d] * inv, o[d + 1] * inv, hh, ll);
-      *reinterpret_cast<uint32_t*>(dh + d) = hh;
-      if (dl) *reinterpret_cast<uint32_t*>(dl + d) = ll;
+      split_pack2(o[d].x * inv, o[d].y * inv, hh, ll);
+      *reinterpret_cast<uint32_t*>(dh + 2 * d) = hh;
+      if (dl) *reinterpret_cast<uint32_t*>(dl + 2 * d) = ll;
     }
   }
 }
@@ -148,15 +160,21 @@ swin_scatter_kernel(const float* __restrict__ o, long long ldo, WinGeom g, float
   }
 }
 
-// p[b, t, :] += mean over the windows of the prompt rows of the attention output (TP:210)
+// p[b, t, :] += mean over the windows of the prompt rows of the attention output (TP:210). Grid (B*T, C / 64): 64
+// channels x 4 window groups per block, fixed-order reduction in shared memory.
 __global__ void __launch_bounds__(256)
 swin_prompt_mean_kernel(const float* __restrict__ o, long long ldo, WinGeom g, float* __restrict__ p, long long ldp) {
+  __shared__ float part[4][64];
   const int bt = blockIdx.x, b = bt / g.T, t = bt % g.T;
-  for (int c = threadIdx.x; c < g.C; c += blockDim.x) {
-    float acc = 0.f;
-    for (int w = 0; w < g.nW; ++w) acc += o[(((long long)b * g.nW + w) * (g.T + g.wl) + t) * ldo + c];
-    p[(long long)bt * ldp + c] += acc / (float)g.nW;
-  }
+  const int cl = threadIdx.x & 63, grp = threadIdx.x >> 6;
+  const int c = blockIdx.y * 64 + cl;
+  float acc = 0.f;
+  if (c < g.C)
+    for (int w = grp; w < g.nW; w += 4) acc += o[(((long long)b * g.nW + w) * (g.T + g.wl) + t) * ldo + c];
+  part[grp][cl] = acc;
+  __syncthreads();
+  if (grp == 0 && c < g.C)
+    p[(long long)bt * ldp + c] += (part[0][cl] + part[1][cl] + part[2][cl] + part[3][cl]) / (float)g.nW;
 }
 
 // raw [B*nW, heads, T, wl] -> logits [B, heads, T, T + H*W] at column T + pixel
@@ -194,8 +212,11 @@ transpose_split_kernel(const float* __restrict__ in, long long ld_in, int L, int
 }
 
 // ---- channel attention (TP:383-396) ------------------------------------------------------------------------------------
-// One CTA per (b, window g of the sqrt(ce) x sqrt(ce) embedding grid, task t): logits over the C channels, softmax,
-// mixing of the value rows. kv [B*C, 2 ce] fp32 (k | v), q [B*T, ce]; the ce axis is (nh, wh, nw, ww).
+// Grid (b, window g of the sqrt(ce) x sqrt(ce) embedding grid, task t) x chunks of 32 embedding columns. Every block
+// computes the logits of its prompt against all C channels (warp per channel, lanes over the window's embedding
+// entries: coalesced), the softmax statistics, and then ITS 32 output columns (8 channel groups x 32 columns, reduced in
+// shared memory in a fixed order). Block y == 0 also writes raw_chan. kv [B*C, 2 ce] fp32 (k | v), q [B*T, ce]; the ce
+// axis is (nh, wh, nw, ww).
 __global__ void __launch_bounds__(256)
 swin_chan_attn_kernel(const float* __restrict__ q, long long ldq, const float* __restrict__ kv, long long ldkv, int T, int C,
                       int ce, int nh, int nw, float scale, float* __restrict__ co, long long ldco,
@@ -209,19 +230,24 @@ swin_chan_attn_kernel(const float* __restrict__ q, long long ldq, const float* _
   __shared__ float red[256];
   const int t = blockIdx.x % T, g = (blockIdx.x / T) % (nh * nw), b = blockIdx.x / (T * nh * nw);
   const int ga = g / nw, gb = g % nw;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   auto eidx = [&](int e) { return ((ga * wh + e / ww) * nw + gb) * ww + e % ww; };
   for (int e = threadIdx.x; e < we; e += blockDim.x) sq[e] = q[((long long)b * T + t) * ldq + eidx(e)];
   __syncthreads();
-  float mx = -INFINITY;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+  for (int c = warp; c < C; c += 8) {                      // logits: warp per channel
     const float* kr = kv + ((long long)b * C + c) * ldkv;
     float s = 0.f;
-    for (int e = 0; e < we; ++e) s = fmaf(sq[e], kr[eidx(e)], s);
-    rc[(((long long)b * T + t) * C + c) * (nh * nw) + g] = s;               // raw_chan [B, T, C, nh, nw] (TP:391)
-    s *= scale;
-    sp[c] = s;
-    mx = fmaxf(mx, s);
+    for (int e = lane; e < we; e += 32) s = fmaf(sq[e], kr[eidx(e)], s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) {
+      if (blockIdx.y == 0) rc[(((long long)b * T + t) * C + c) * (nh * nw) + g] = s;   // raw_chan [B,T,C,nh,nw] (TP:391)
+      sp[c] = s * scale;
+    }
   }
+  __syncthreads();
+  float mx = -INFINITY;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) mx = fmaxf(mx, sp[c]);
   red[threadIdx.x] = mx;
   __syncthreads();
   for (int s = blockDim.x >> 1; s > 0; s >>= 1) {
@@ -243,15 +269,26 @@ swin_chan_attn_kernel(const float* __restrict__ q, long long ldq, const float* _
     __syncthreads();
   }
   const float inv = 1.f / red[0];
-  for (int e = threadIdx.x; e < we; e += blockDim.x) {
-    const int col = eidx(e);
-    float acc = 0.f;
-    for (int c = 0; c < C; ++c) acc = fmaf(sp[c], kv[((long long)b * C + c) * ldkv + ce + col], acc);
-    acc *= inv;
+  __syncthreads();
+  // outputs: this block's 32 embedding columns, 8 channel groups
+  const int e = blockIdx.y * 32 + lane;
+  float acc = 0.f;
+  int col = 0;
+  if (e < we) {
+    col = eidx(e);
+    for (int c = warp; c < C; c += 8) acc = fmaf(sp[c], kv[((long long)b * C + c) * ldkv + ce + col], acc);
+  }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  if (warp == 0 && e < we) {
+    float tot = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) tot += red[k * 32 + lane];
+    tot *= inv;
     const long long orow = (long long)b * T + t;
-    co[orow * ldco + col] = acc;
+    co[orow * ldco + col] = tot;
     __nv_bfloat16 h, l;
-    split_bf16(acc, h, l);
+    split_bf16(tot, h, l);
     cs_hi[orow * ldcs + col] = h;
     if (cs_lo) cs_lo[orow * ldcs + col] = l;
   }
@@ -412,7 +449,7 @@ int mtt_swin_window_scatter(const float* o, int64_t ldo, const float* raw, int32
   swin_scatter_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, STREAM>>>(o, ldo, g, xa, ldxa, x, ldx);
   if ((rc = check_launch("mtt_swin_window_scatter(map)"))) return rc;
   if (update_prompts && T > 0) {
-    swin_prompt_mean_kernel<<<B * T, 256, 0, STREAM>>>(o, ldo, g, prompts, ldp);
+    swin_prompt_mean_kernel<<<dim3(B * T, (C + 63) / 64), 256, 0, STREAM>>>(o, ldo, g, prompts, ldp);
     if ((rc = check_launch("mtt_swin_window_scatter(prompts)"))) return rc;
   }
   if (T > 0) {
@@ -443,7 +480,8 @@ int mtt_swin_chan_attention(const float* q, int64_t ldq, const float* kv, int64_
     return set_error(MTT_ERR_BAD_SHAPE, "mtt_swin_chan_attention: bad arguments (ce=%d nh=%d nw=%d)", ce, nh, nw);
   const size_t smem = ((size_t)(r / nh) * (r / nw) + C) * sizeof(float);
   if (smem > 48 * 1024) return set_error(MTT_ERR_BAD_SHAPE, "mtt_swin_chan_attention: C=%d too large", C);
-  swin_chan_attn_kernel<<<B * nh * nw * T, 256, smem, STREAM>>>(
+  const int we = (r / nh) * (r / nw);
+  swin_chan_attn_kernel<<<dim3(B * nh * nw * T, (we + 31) / 32), 256, smem, STREAM>>>(
       q, ldq, kv, ldkv, T, C, ce, nh, nw, 1.0f / sqrtf((float)ce), chan_out, ldco, static_cast<__nv_bfloat16*>(cs_hi),
       static_cast<__nv_bfloat16*>(cs_lo), ldcs, raw_chan);
   return check_launch("mtt_swin_chan_attention");

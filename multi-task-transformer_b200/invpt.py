@@ -466,7 +466,8 @@ class _Plan:
             else:
                 self.back0 = z(B * 16 * h0 * w0, dims[2])
                 self.back1 = z(B * 4 * h0 * w0, dims[1])
-            self.cat = [S(B * h0 * w0, E + n, zero=True) for n in self.n_out]
+            cat_ld = ops.round_up(E + max(self.n_out), 8)     # one row stride for all tasks (grouped launches)
+            self.cat = [S(B * h0 * w0, E + n, zero=True, ld=cat_ld) for n in self.n_out]
             self.inter = [z(B * h0 * w0, ops.round_up(n, 4)) for n in self.n_out]
             self.st = []
             for i in range(3):

@@ -98,7 +98,7 @@ def test_gemm_splitk(both, cuda_dev):
         part, out = torch.zeros(chunks, M, N, device=cuda_dev), torch.zeros(M, N, device=cuda_dev)
         ops.gemm_splitk(a, w, part, out, K=K, bias=bias, chunks=chunks)
         torch.cuda.synchronize()
-        assert relerr(out, ref) < 2e-6
+        assert relerr(out, ref) < 1e-5          # same products, different fp32 summation order
         want = a.float().double() @ w.float()[:, :K].double().t() + bias.double()
         assert relerr(out, want) < 2e-5
 
