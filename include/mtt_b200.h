@@ -283,28 +283,15 @@ int mtt_dwconv3x3_s2(const float* in, int64_t ld_in, int32_t B, int32_t T, int32
 int mtt_avgpool(const float* in, int64_t ld_in, int32_t BT, int32_t h, int32_t w, int32_t C, int32_t s,
                 void* out_hi, void* out_lo, int64_t ld_out, mtt_stream_t stream);
 
-/* InvPT cross-task attention with cross-scale score fusion (IP invpt.py:204-236), 2 heads.
- * q fp32 [B,Lq,C] (ldq), k/v fp32 [B,Tk,C] (ldk), scale = C^-1/2. prev_score (optional) fp32
- * [B,2,T*(qh/2)*(qw/2),Tk] is bilinearly up-sampled x2 per task over the query grid and mixed with the
- * current scores by the 1x1 conv fuse_w [2,4], fuse_b [2]. score_out (optional) fp32 [B,2,Lq,Tk] gets
- * the fused pre-softmax scores; out = softmax . v as split [B*Lq, C]. */
-typedef struct {
-  const float* q;
-  const float* k;
-  const float* v;
-  int64_t ldq, ldk;
-  int32_t B, Lq, Tk, C;
-  float scale;
-  const float* prev_score;
-  int32_t T, qh, qw;
-  const float* fuse_w;
-  const float* fuse_b;
-  float* score_out;
-  void* out_hi;
-  void* out_lo;
-  int64_t ldo;
-} mtt_invpt_attn_desc;
-int mtt_invpt_attention(const mtt_invpt_attn_desc* d, mtt_stream_t stream);
+/* InvPT cross-task attention with cross-scale score fusion (IP invpt.py:204-236), 2 heads: the two contractions
+ * (S = Q_h K_h^T, O_h = P_h V_h) are grouped mtt_gemm launches over (batch, head); this is the step between them.
+ * raw fp32 [B,2,Lq,Tk] = un-scaled q_h . k_h; scale = C^-1/2. prev_score (optional) fp32 [B,2,T*(qh/2)*(qw/2),Tk] is
+ * bilinearly up-sampled x2 per task over the query grid and mixed with the current scores by the 1x1 conv fuse_w [2,4],
+ * fuse_b [2] (fuse_attn, :116,:229). score_out (optional, may alias raw) receives the fused pre-softmax scores (:230);
+ * P = softmax over the Tk keys is written as split rows [(b*2 + h)*Lq + l, ldp]: the A operand of the second GEMM. */
+int mtt_invpt_fuse_softmax(const float* raw, int32_t B, int32_t Lq, int32_t Tk, float scale, const float* prev_score,
+                           int32_t T, int32_t qh, int32_t qw, const float* fuse_w, const float* fuse_b, float* score_out,
+                           void* p_hi, void* p_lo, int64_t ldp, mtt_stream_t stream);
 
 /* ---- the named operators of SURVEY.md section 8(b) -----------------------------------------------------------
  * Each replaces one eager-op group of the reference block / decoder with a fixed launch sequence; intermediates
@@ -313,7 +300,8 @@ int mtt_invpt_attention(const mtt_invpt_attn_desc* d, mtt_stream_t stream);
  *
  * DEVIATIONS from the entry-point list SURVEY.md 8(b) sketched (all deliberate, same ownership / error / stream
  * rules): (1) attn_fwd, chan_prompt_logits, bilinear_up, invpt_attn, layernorm are the single-kernel entries above
- * (mtt_attention, mtt_chan_logits, mtt_bilinear, mtt_invpt_attention, mtt_layernorm) under their round-1 names;
+ * (mtt_attention, mtt_chan_logits, mtt_bilinear, mtt_invpt_fuse_softmax between two mtt_gemm_grouped launches,
+ * mtt_layernorm) under their own names;
  * (2) shapes travel in mtt_shape and weights in mtt_weight (pre-packed planes) instead of a flat argument list;
  * (3) LayerNorm is a kernel of the sequence, not a prologue inside the GEMM: the normalised rows are written once as
  * split planes (8.4 us per 16.8 MB at cfg4) and read back from L2 by the TMA producer. */

@@ -180,15 +180,13 @@ avgpool_kernel(const float* __restrict__ in, long long ld_in, int h, int w, int 
 }
 
 // ------------------------------------------------------------------------------------------------
-// InvPT cross-task attention (invpt.py:204-236), 2 heads, Tk <= 512 keys shared by all tasks:
-//   s[h]     = (q_h . k_h) * C^-1/2
+// InvPT cross-task attention (invpt.py:204-236), 2 heads, Tk keys shared by all tasks. The two contractions run on
+// the tcgen05 GEMM as grouped launches over (batch, head) -- S = Q_h K_h^T and O_h = P_h V_h -- and this kernel is
+// what sits between them, one warp per (batch, query):
+//   s[h]     = raw[h] * C^-1/2                               (raw = q_h . k_h from the first GEMM)
 //   prev_up  = bilinear x2 (per task, over the query grid) of the previous stage's fused score
-//   f[o]     = Wf[o,0] s[0] + Wf[o,1] s[1] + Wf[o,2] prev_up[0] + Wf[o,3] prev_up[1] + bf[o]
-//   score_out = f (pre-softmax, consumed by the next stage);  out = softmax(f) v
-constexpr int kQT = 16;       // queries per block
-constexpr int kIAThreads = 256;
-constexpr int kMaxTk = 512;
-
+//   f[o]     = Wf[o,0] s[0] + Wf[o,1] s[1] + Wf[o,2] prev_up[0] + Wf[o,3] prev_up[1] + bf[o]     (fuse_attn, :116,:229)
+//   score_out = f (pre-softmax, consumed by the next stage, :230);  P = softmax(f) as split rows [(b*2+h)*Lq + l, Tk]
 __device__ __forceinline__ void up2_coord(int d, int in_size, int& i0, int& i1, float& l1) {
   float s = 0.5f * (d + 0.5f) - 0.5f;
   if (s < 0.f) s = 0.f;
@@ -198,130 +196,87 @@ __device__ __forceinline__ void up2_coord(int d, int in_size, int& i0, int& i1, 
   l1 = s - (float)i0;
 }
 
-__global__ void __launch_bounds__(kIAThreads)
-invpt_attn_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
-                  long long ldq, long long ldk, int Lq, int Tk, int C, float scale,
-                  const float* __restrict__ prev, int T, int qh, int qw, const float* __restrict__ wf,
-                  const float* __restrict__ bf, float* __restrict__ score_out,
-                  __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo, long long ldo) {
-  extern __shared__ float sm[];
-  float* qs = sm;                      // [kQT][C]
-  float* ks = qs + kQT * C;            // [Tk][33]
-  float* sc = ks + (size_t)Tk * 33;    // [2][kQT][Tk]
-  const int b = blockIdx.y;
-  const int l0 = blockIdx.x * kQT;
-  const int nq = min(kQT, Lq - l0);
-  const int d = C / 2;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+constexpr int kFuseMaxPerLane = 16;   // Tk <= 512 keys
 
-  for (int i = tid; i < kQT * C; i += kIAThreads) {
-    const int qi = i / C, c = i % C;
-    qs[i] = qi < nq ? q[((long long)b * Lq + l0 + qi) * ldq + c] : 0.f;
+__global__ void __launch_bounds__(256)
+invpt_fuse_softmax_kernel(const float* __restrict__ raw, int B, int Lq, int Tk, float scale, const float* __restrict__ prev,
+                          int T, int qh, int qw, const float* __restrict__ wf, const float* __restrict__ bf,
+                          float* __restrict__ score_out, __nv_bfloat16* __restrict__ p_hi, __nv_bfloat16* __restrict__ p_lo,
+                          long long ldp) {
+  const long long wid = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);   // b * Lq + l
+  if (wid >= (long long)B * Lq) return;
+  const int lane = threadIdx.x & 31;
+  const int b = (int)(wid / Lq), l = (int)(wid % Lq);
+  const float* r0 = raw + (((long long)b * 2 + 0) * Lq + l) * Tk;
+  const float* r1 = raw + (((long long)b * 2 + 1) * Lq + l) * Tk;
+  float f0[kFuseMaxPerLane], f1[kFuseMaxPerLane];
+  int y0 = 0, y1 = 0, x0 = 0, x1 = 0, task = 0, sh = 0, sw = 0;
+  float ly = 0.f, lx = 0.f;
+  if (prev) {
+    sh = qh / 2;
+    sw = qw / 2;
+    task = l / (qh * qw);
+    const int r = l % (qh * qw);
+    up2_coord(r / qw, sh, y0, y1, ly);
+    up2_coord(r % qw, sw, x0, x1, lx);
   }
-  // ---- raw scores, one head at a time; thread owns keys t = tid, tid + 256
-  for (int hd = 0; hd < 2; ++hd) {
-    float acc[2][kQT];
+  float m0 = -INFINITY, m1 = -INFINITY;
 #pragma unroll
-    for (int u = 0; u < 2; ++u)
+  for (int k = 0; k < kFuseMaxPerLane; ++k) {
+    const int t = lane + 32 * k;
+    f0[k] = f1[k] = -INFINITY;
+    if (t < Tk) {
+      float s0 = r0[t] * scale, s1 = r1[t] * scale;
+      if (prev) {
+        float pu[2];
 #pragma unroll
-      for (int qi = 0; qi < kQT; ++qi) acc[u][qi] = 0.f;
-    for (int c0 = hd * d; c0 < (hd + 1) * d; c0 += 32) {
-      const int cw = min(32, (hd + 1) * d - c0);
-      __syncthreads();
-      for (int t = warp; t < Tk; t += kIAThreads / 32)
-        ks[t * 33 + lane] = lane < cw ? k[((long long)b * Tk + t) * ldk + c0 + lane] : 0.f;
-      __syncthreads();
-#pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const int t = tid + u * kIAThreads;
-        if (t < Tk) {
-          for (int j = 0; j < cw; ++j) {
-            const float kv = ks[t * 33 + j];
-#pragma unroll
-            for (int qi = 0; qi < kQT; ++qi) acc[u][qi] = fmaf(qs[qi * C + c0 + j], kv, acc[u][qi]);
-          }
+        for (int hd = 0; hd < 2; ++hd) {
+          const float* pb = prev + (((long long)b * 2 + hd) * ((long long)T * sh * sw) + (long long)task * sh * sw) * Tk + t;
+          const float p00 = pb[(long long)(y0 * sw + x0) * Tk], p01 = pb[(long long)(y0 * sw + x1) * Tk];
+          const float p10 = pb[(long long)(y1 * sw + x0) * Tk], p11 = pb[(long long)(y1 * sw + x1) * Tk];
+          pu[hd] = (1.f - ly) * ((1.f - lx) * p00 + lx * p01) + ly * ((1.f - lx) * p10 + lx * p11);
         }
+        const float a0 = wf[0] * s0 + wf[1] * s1 + wf[2] * pu[0] + wf[3] * pu[1] + bf[0];
+        const float a1 = wf[4] * s0 + wf[5] * s1 + wf[6] * pu[0] + wf[7] * pu[1] + bf[1];
+        s0 = a0;
+        s1 = a1;
       }
-    }
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const int t = tid + u * kIAThreads;
-      if (t < Tk)
-#pragma unroll
-        for (int qi = 0; qi < kQT; ++qi) sc[(hd * kQT + qi) * Tk + t] = acc[u][qi] * scale;
-    }
-  }
-  __syncthreads();
-  // ---- cross-scale fusion (1x1 conv over [cur h0, cur h1, prev h0, prev h1]) and score export
-  if (prev != nullptr) {
-    const int sh = qh / 2, sw = qw / 2;
-    const int Lp = T * sh * sw;
-    for (int i = tid; i < nq * Tk; i += kIAThreads) {
-      const int qi = i / Tk, t = i % Tk;
-      const int l = l0 + qi;
-      const int task = l / (qh * qw), r = l % (qh * qw);
-      int y0, y1, x0, x1;
-      float ly, lx;
-      up2_coord(r / qw, sh, y0, y1, ly);
-      up2_coord(r % qw, sw, x0, x1, lx);
-      float pu[2];
-#pragma unroll
-      for (int hd = 0; hd < 2; ++hd) {
-        const float* pb = prev + (((long long)b * 2 + hd) * Lp + (long long)task * sh * sw) * Tk + t;
-        const float p00 = pb[(long long)(y0 * sw + x0) * Tk], p01 = pb[(long long)(y0 * sw + x1) * Tk];
-        const float p10 = pb[(long long)(y1 * sw + x0) * Tk], p11 = pb[(long long)(y1 * sw + x1) * Tk];
-        pu[hd] = (1.f - ly) * ((1.f - lx) * p00 + lx * p01) + ly * ((1.f - lx) * p10 + lx * p11);
+      f0[k] = s0;
+      f1[k] = s1;
+      if (score_out) {
+        score_out[(((long long)b * 2 + 0) * Lq + l) * Tk + t] = s0;
+        score_out[(((long long)b * 2 + 1) * Lq + l) * Tk + t] = s1;
       }
-      const float s0 = sc[(0 * kQT + qi) * Tk + t], s1 = sc[(1 * kQT + qi) * Tk + t];
-      const float f0 = wf[0] * s0 + wf[1] * s1 + wf[2] * pu[0] + wf[3] * pu[1] + bf[0];
-      const float f1 = wf[4] * s0 + wf[5] * s1 + wf[6] * pu[0] + wf[7] * pu[1] + bf[1];
-      sc[(0 * kQT + qi) * Tk + t] = f0;
-      sc[(1 * kQT + qi) * Tk + t] = f1;
-    }
-    __syncthreads();
-  }
-  if (score_out != nullptr) {
-    for (int i = tid; i < 2 * nq * Tk; i += kIAThreads) {
-      const int hd = i / (nq * Tk), r = i % (nq * Tk);
-      const int qi = r / Tk, t = r % Tk;
-      score_out[(((long long)b * 2 + hd) * Lq + l0 + qi) * Tk + t] = sc[(hd * kQT + qi) * Tk + t];
+      m0 = fmaxf(m0, s0);
+      m1 = fmaxf(m1, s1);
     }
   }
-  // ---- softmax over keys, one warp per (head, query) row
-  for (int rowi = warp; rowi < 2 * kQT; rowi += kIAThreads / 32) {
-    float* row = sc + (long long)rowi * Tk;
-    float mx = -INFINITY;
-    for (int t = lane; t < Tk; t += 32) mx = fmaxf(mx, row[t]);
-    mx = warp_max_f(mx);
-    float sum = 0.f;
-    for (int t = lane; t < Tk; t += 32) {
-      const float e = expf(row[t] - mx);
-      row[t] = e;
-      sum += e;
-    }
-    const float inv = 1.0f / warp_sum_f(sum);
-    for (int t = lane; t < Tk; t += 32) row[t] *= inv;
-  }
-  __syncthreads();
-  // ---- out[qi, c] = sum_t p[head(c)][qi][t] * v[t, c]; thread owns channels
-  for (int c = tid; c < C; c += kIAThreads) {
-    const int hd = c / d;
-    float acc[kQT];
+  m0 = warp_max_f(m0);
+  m1 = warp_max_f(m1);
+  float z0 = 0.f, z1 = 0.f;
 #pragma unroll
-    for (int qi = 0; qi < kQT; ++qi) acc[qi] = 0.f;
-    const float* vb = v + (long long)b * Tk * ldk + c;
-    const float* pr = sc + (long long)hd * kQT * Tk;
-    for (int t = 0; t < Tk; ++t) {
-      const float vv = vb[(long long)t * ldk];
-#pragma unroll
-      for (int qi = 0; qi < kQT; ++qi) acc[qi] = fmaf(pr[qi * Tk + t], vv, acc[qi]);
+  for (int k = 0; k < kFuseMaxPerLane; ++k) {
+    if (lane + 32 * k < Tk) {
+      f0[k] = expf(f0[k] - m0);
+      f1[k] = expf(f1[k] - m1);
+      z0 += f0[k];
+      z1 += f1[k];
     }
-    for (int qi = 0; qi < nq; ++qi) {
+  }
+  const float i0 = 1.0f / warp_sum_f(z0), i1 = 1.0f / warp_sum_f(z1);
+  __nv_bfloat16* h0 = p_hi + (((long long)b * 2 + 0) * Lq + l) * ldp;
+  __nv_bfloat16* h1 = p_hi + (((long long)b * 2 + 1) * Lq + l) * ldp;
+#pragma unroll
+  for (int k = 0; k < kFuseMaxPerLane; ++k) {
+    const int t = lane + 32 * k;
+    if (t < Tk) {
       __nv_bfloat16 hh, ll;
-      split_bf16(acc[qi], hh, ll);
-      const long long orow = (long long)b * Lq + l0 + qi;
-      out_hi[orow * ldo + c] = hh;
-      if (out_lo) out_lo[orow * ldo + c] = ll;
+      split_bf16(f0[k] * i0, hh, ll);
+      h0[t] = hh;
+      if (p_lo) p_lo[(h0 - p_hi) + t] = ll;
+      split_bf16(f1[k] * i1, hh, ll);
+      h1[t] = hh;
+      if (p_lo) p_lo[(h1 - p_hi) + t] = ll;
     }
   }
 }
@@ -392,26 +347,17 @@ extern "C" int mtt_avgpool(const float* in, int64_t ld_in, int32_t BT, int32_t h
   return check_launch("mtt_avgpool");
 }
 
-extern "C" int mtt_invpt_attention(const mtt_invpt_attn_desc* d, mtt_stream_t stream) {
-  if (!d || !d->q || !d->k || !d->v || !d->out_hi || d->B <= 0 || d->Lq <= 0 || d->Tk <= 0 ||
-      d->Tk > kMaxTk || d->C <= 0 || (d->C & 1))
-    return set_error(MTT_ERR_BAD_SHAPE, "mtt_invpt_attention: bad arguments (Tk=%d C=%d)", d ? d->Tk : -1,
-                     d ? d->C : -1);
-  if (d->prev_score && (d->T <= 0 || d->qh <= 0 || d->qw <= 0 || (d->qh & 1) || (d->qw & 1) ||
-                        d->T * d->qh * d->qw != d->Lq || !d->fuse_w || !d->fuse_b))
-    return set_error(MTT_ERR_BAD_SHAPE, "mtt_invpt_attention: bad fusion geometry");
-  const size_t smem = ((size_t)kQT * d->C + (size_t)d->Tk * 33 + (size_t)2 * kQT * d->Tk) * sizeof(float);
-  if (smem > 220 * 1024) return set_error(MTT_ERR_BAD_SHAPE, "mtt_invpt_attention: shared memory %zu", smem);
-  static bool attr[kMaxDevices] = {};  // per device
-  const int dev_ = current_device();
-  if (!attr[dev_]) {
-    cudaFuncSetAttribute(invpt_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-    attr[dev_] = true;
-  }
-  dim3 grid((d->Lq + kQT - 1) / kQT, d->B);
-  invpt_attn_kernel<<<grid, kIAThreads, smem, STREAM>>>(
-      d->q, d->k, d->v, d->ldq, d->ldk, d->Lq, d->Tk, d->C, d->scale, d->prev_score, d->T, d->qh, d->qw,
-      d->fuse_w, d->fuse_b, d->score_out, static_cast<__nv_bfloat16*>(d->out_hi),
-      static_cast<__nv_bfloat16*>(d->out_lo), d->ldo);
-  return check_launch("mtt_invpt_attention");
+extern "C" int mtt_invpt_fuse_softmax(const float* raw, int32_t B, int32_t Lq, int32_t Tk, float scale,
+                                      const float* prev_score, int32_t T, int32_t qh, int32_t qw, const float* fuse_w,
+                                      const float* fuse_b, float* score_out, void* p_hi, void* p_lo, int64_t ldp,
+                                      mtt_stream_t stream) {
+  if (!raw || !p_hi || B <= 0 || Lq <= 0 || Tk <= 0 || Tk > 32 * kFuseMaxPerLane || ldp < Tk)
+    return set_error(MTT_ERR_BAD_SHAPE, "mtt_invpt_fuse_softmax: bad arguments (Tk=%d, at most %d)", Tk, 32 * kFuseMaxPerLane);
+  if (prev_score && (T <= 0 || qh <= 0 || qw <= 0 || (qh & 1) || (qw & 1) || T * qh * qw != Lq || !fuse_w || !fuse_b))
+    return set_error(MTT_ERR_BAD_SHAPE, "mtt_invpt_fuse_softmax: bad fusion geometry");
+  const long long rows = (long long)B * Lq;
+  invpt_fuse_softmax_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, STREAM>>>(
+      raw, B, Lq, Tk, scale, prev_score, T, qh, qw, fuse_w, fuse_b, score_out, static_cast<__nv_bfloat16*>(p_hi),
+      static_cast<__nv_bfloat16*>(p_lo), ldp);
+  return check_launch("mtt_invpt_fuse_softmax");
 }

@@ -482,8 +482,12 @@ class _Plan:
                 s.xn32 = z(B * T * h * w, Ci)
                 s.qin = S(B * s.Lq, Ci)
                 s.kvin = S(B * s.Tk, Ci)
-                s.q32, s.k32, s.v32 = z(B * s.Lq, Ci), z(B * s.Tk, Ci), z(B * s.Tk, Ci)
-                s.score = z(B, 2, s.Lq, s.Tk) if i < 2 else None
+                # cross-task attention (2 heads of dim Ci / 2): q, k as split operands of S = Q_h K_h^T, v transposed per image
+                # for O_h = P_h V_h; both contractions are grouped launches over (batch, head)
+                s.qs, s.ks, s.v32 = S(B * s.Lq, Ci), S(B * s.Tk, Ci), z(B * s.Tk, Ci)
+                s.vt = S(B * Ci, s.Tk, zero=True)
+                s.score = z(B, 2, s.Lq, s.Tk)          # raw scores, then (in place) the fused pre-softmax scores
+                s.P = S(B * 2 * s.Lq, s.Tk, zero=True)
                 s.ao = S(B * s.Lq, Ci)
                 s.a32 = z(B * s.Lq, Ci)
                 s.ws_mlp = ops.workspace(ops.workspace_bytes(ops._L.OP_LN_MLP_RESIDUAL, rows=B * T * h * w, Cdim=Ci,
@@ -614,13 +618,21 @@ class _Plan:
         ops.layernorm(s.xj, sw.n1w, sw.n1b, sw.eps, out_f32=s.xn32)                                    # :298
         ops.dwconv3x3_s2(s.xn32, sw.dw_w, sw.dw_b, s.qin, B=B, T=T, h=h, w=w, Cdim=Ci)                 # :171-173
         ops.avgpool(s.xn32, s.kvin, BT=B * T, h=h, w=w, Cdim=Ci, s=s.kvs)                              # :175-187
-        ops.gemm(s.qin, sw.proj_q, bias=sw.proj_q_b, out_f32=s.q32)                                    # :200
-        ops.gemm(s.kvin, sw.proj_k, bias=sw.proj_k_b, out_f32=s.k32)                                   # :201
+        ops.gemm(s.qin, sw.proj_q, bias=sw.proj_q_b, out_split=s.qs)                                   # :200
+        ops.gemm(s.kvin, sw.proj_k, bias=sw.proj_k_b, out_split=s.ks)                                  # :201
         ops.gemm(s.kvin, sw.proj_v, bias=sw.proj_v_b, out_f32=s.v32)                                   # :202
+        ops.transpose_split(s.v32, s.vt, B=B, L=s.Tk, Cdim=Ci)
+        dh = Ci // 2
+        ops.gemm_grouped([(s.qs, s.ks, dict(M=s.Lq, N=s.Tk, K=dh, a_row_offset=b * s.Lq, a_col_offset=hd * dh,
+                                            w_row_offset=b * s.Tk, w_col_offset=hd * dh, out_f32=s.score[b, hd]))
+                          for b in range(B) for hd in range(2)])                                       # :204 q k^T
         prev = self.st[i - 1].score if i > 0 else None
-        ops.invpt_attention(s.q32, s.k32, s.v32, s.ao, B=B, Lq=s.Lq, Tk=s.Tk, Cdim=Ci, scale=Ci ** -0.5,
-                            prev_score=prev, T=T, qh=h // 2, qw=w // 2, fuse_w=sw.fuse_w, fuse_b=sw.fuse_b,
-                            score_out=s.score)                                                          # :204-236
+        ops.invpt_fuse_softmax(s.score, s.P, B=B, Lq=s.Lq, Tk=s.Tk, scale=Ci ** -0.5, prev_score=prev, T=T, qh=h // 2,
+                               qw=w // 2, fuse_w=sw.fuse_w, fuse_b=sw.fuse_b,
+                               score_out=s.score if i < 2 else None)                                   # :205-232
+        ops.gemm_grouped([(s.P, s.vt, dict(M=s.Lq, N=dh, K=s.Tk, a_row_offset=(b * 2 + hd) * s.Lq,
+                                           w_row_offset=b * Ci + hd * dh, out_split=s.ao, out_row_offset=b * s.Lq,
+                                           out_col_offset=hd * dh)) for b in range(B) for hd in range(2)])   # :234 attn v
         ops.gemm(s.ao, sw.proj, bias=sw.proj_b, out_f32=s.a32)                                         # :238
         qhw = (h // 2) * (w // 2)
         self._par(lambda k: ops.bilinear(                                                              # :299-306

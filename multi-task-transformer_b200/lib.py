@@ -66,16 +66,6 @@ class BilinearSrc(C.Structure):
                 ("batch_rows", C.c_int64), ("row_offset", C.c_int64)]
 
 
-class InvptAttnDesc(C.Structure):
-    _fields_ = [
-        ("q", C.c_void_p), ("k", C.c_void_p), ("v", C.c_void_p), ("ldq", C.c_int64), ("ldk", C.c_int64),
-        ("B", C.c_int32), ("Lq", C.c_int32), ("Tk", C.c_int32), ("C", C.c_int32), ("scale", C.c_float),
-        ("prev_score", C.c_void_p), ("T", C.c_int32), ("qh", C.c_int32), ("qw", C.c_int32),
-        ("fuse_w", C.c_void_p), ("fuse_b", C.c_void_p), ("score_out", C.c_void_p),
-        ("out_hi", C.c_void_p), ("out_lo", C.c_void_p), ("ldo", C.c_int64),
-    ]
-
-
 # name -> (restype, argtypes); every symbol include/mtt_b200.h declares
 _i64, _i32, _f32, _vp = C.c_int64, C.c_int32, C.c_float, C.c_void_p
 SYMBOLS = {
@@ -114,7 +104,8 @@ SYMBOLS = {
     "mtt_zero_insert": (C.c_int, [_vp, _i64, _i64, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _i64, _vp]),
     "mtt_dwconv3x3_s2": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i64, _vp]),
     "mtt_avgpool": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _i64, _vp]),
-    "mtt_invpt_attention": (C.c_int, [C.POINTER(InvptAttnDesc), _vp]),
+    "mtt_invpt_fuse_softmax": (C.c_int, [_vp, _i32, _i32, _i32, _f32, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _i64,
+                                         _vp]),
     "mtt_workspace_bytes": (C.c_size_t, [_i32, C.POINTER(Shape)]),
     "mtt_ln_qkv": (C.c_int, [_vp, _i64, _vp, _vp, _f32, C.POINTER(Weight), _vp, _vp, _vp, _i64, C.POINTER(Shape), _vp,
                              C.c_size_t, _vp]),

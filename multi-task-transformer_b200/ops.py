@@ -85,7 +85,7 @@ def layernorm(x, gamma, beta, eps, out_f32=None, out_split=None):
 
 def gemm(a, w, *, M=None, N=None, K=None, bias=None, act=ACT_NONE, residual=None, res_row_mod=0,
          out_f32=None, out_split=None, out_col_offset=0, regroup=None, conv=None, a_row_offset=0,
-         a_gather=None, w_col_offset=0, a_col_offset=0):
+         a_gather=None, w_col_offset=0, a_col_offset=0, w_row_offset=0, out_row_offset=0):
     """D = act(A @ W^T + bias) + residual on the tcgen05 GEMM.
 
     a: Split [M, K] (or NHWC activation [B*H*W, C] when ``conv=(B, H, W, ksize, dil)``);
@@ -94,7 +94,7 @@ def gemm(a, w, *, M=None, N=None, K=None, bias=None, act=ACT_NONE, residual=None
     group_stride) gathers A rows in groups (M must be given); w_col_offset selects a K-slice of a wider packed W."""
     d = _L.GemmDesc()
     _fill_gemm_desc(d, a, w, M, N, K, bias, act, residual, res_row_mod, out_f32, out_split, out_col_offset, regroup, conv,
-                    a_row_offset, a_gather, w_col_offset, a_col_offset)
+                    a_row_offset, a_gather, w_col_offset, a_col_offset, w_row_offset, out_row_offset)
     rc = _L.load().mtt_gemm(C.byref(d), _stream())
     _L.check(rc, "mtt_gemm")
 
@@ -106,7 +106,7 @@ def gemm_grouped(calls):
     for d, (a, w, kw) in zip(arr, calls):
         k = dict(M=None, N=None, K=None, bias=None, act=ACT_NONE, residual=None, res_row_mod=0, out_f32=None,
                  out_split=None, out_col_offset=0, regroup=None, conv=None, a_row_offset=0, a_gather=None, w_col_offset=0,
-                 a_col_offset=0)
+                 a_col_offset=0, w_row_offset=0, out_row_offset=0)
         k.update(kw)
         _fill_gemm_desc(d, a, w, **k)
     rc = _L.load().mtt_gemm_grouped(arr, len(calls), _stream())
@@ -131,11 +131,13 @@ def gemm_splitk(a, w, partial, out_f32, *, K, bias=None, chunks):
 
 
 def _fill_gemm_desc(d, a, w, M, N, K, bias, act, residual, res_row_mod, out_f32, out_split, out_col_offset, regroup, conv,
-                    a_row_offset, a_gather, w_col_offset, a_col_offset=0):
+                    a_row_offset, a_gather, w_col_offset, a_col_offset=0, w_row_offset=0, out_row_offset=0):
+    """w_row_offset / out_row_offset: first row of the B operand / of the split output (pointer offsets): lets one
+    buffer hold the operands of several (batch, head) problems of a grouped launch."""
     nsplit = min(a.nsplit, w.nsplit)
     aoff = 2 * (a_row_offset * a.ld + a_col_offset)
     d.a_hi, d.a_lo, d.lda = a.hi.data_ptr() + aoff, (a.lo.data_ptr() + aoff if nsplit == 2 else 0), a.ld
-    woff = 2 * w_col_offset
+    woff = 2 * (w_row_offset * w.ld + w_col_offset)
     d.b_hi, d.b_lo, d.ldb = w.hi.data_ptr() + woff, (w.lo.data_ptr() + woff if nsplit == 2 else 0), w.ld
     d.M = a.rows if M is None else M
     d.N = w.rows if N is None else N
@@ -156,8 +158,9 @@ def _fill_gemm_desc(d, a, w, M, N, K, bias, act, residual, res_row_mod, out_f32,
         assert out_f32.dtype == torch.float32 and out_f32.stride(-1) == 1
         d.out_f32, d.ldo_f32 = out_f32.data_ptr(), out_f32.stride(-2)
     if out_split is not None:
-        d.out_hi = out_split.hi.data_ptr() + 2 * out_col_offset
-        d.out_lo = (out_split.lo.data_ptr() + 2 * out_col_offset) if out_split.nsplit == 2 else 0
+        ooff = 2 * (out_row_offset * out_split.ld + out_col_offset)
+        d.out_hi = out_split.hi.data_ptr() + ooff
+        d.out_lo = (out_split.lo.data_ptr() + ooff) if out_split.nsplit == 2 else 0
         d.ldo_bf = out_split.ld
         if nsplit == 2 and out_split.nsplit != 2:
             raise ValueError("nsplit=2 GEMM needs a 2-plane split output")
@@ -368,24 +371,18 @@ def avgpool(x, out, *, BT, h, w, Cdim, s):
     _L.check(rc, "mtt_avgpool")
 
 
-def invpt_attention(q, k, v, out, *, B, Lq, Tk, Cdim, scale, prev_score=None, T=0, qh=0, qw=0, fuse_w=None,
-                    fuse_b=None, score_out=None):
-    d = _L.InvptAttnDesc()
-    for t in (q, k, v):
-        assert t.dtype == torch.float32 and t.stride(-1) == 1
-    assert k.stride(-2) == v.stride(-2)
-    d.q, d.k, d.v, d.ldq, d.ldk = q.data_ptr(), k.data_ptr(), v.data_ptr(), q.stride(-2), k.stride(-2)
-    d.B, d.Lq, d.Tk, d.C, d.scale = B, Lq, Tk, Cdim, float(scale)
+def invpt_fuse_softmax(raw, P, *, B, Lq, Tk, scale, prev_score=None, T=0, qh=0, qw=0, fuse_w=None, fuse_b=None,
+                       score_out=None):
+    """The step between the two GEMMs of InvPT's cross-task attention (invpt.py:204-236): scale, cross-scale fusion with
+    the up-sampled previous score, score export, softmax -> P Split [B*2*Lq, Tk]."""
+    assert raw.is_contiguous() and raw.dtype == torch.float32
     if prev_score is not None:
         assert prev_score.is_contiguous() and fuse_w.is_contiguous()
-        d.prev_score, d.T, d.qh, d.qw = prev_score.data_ptr(), T, qh, qw
-        d.fuse_w, d.fuse_b = fuse_w.data_ptr(), fuse_b.data_ptr()
     if score_out is not None:
         assert score_out.is_contiguous()
-        d.score_out = score_out.data_ptr()
-    d.out_hi, d.out_lo, d.ldo = out.hi.data_ptr(), (out.lo.data_ptr() if out.nsplit == 2 else 0), out.ld
-    rc = _L.load().mtt_invpt_attention(C.byref(d), _stream())
-    _L.check(rc, "mtt_invpt_attention")
+    rc = _L.load().mtt_invpt_fuse_softmax(_ptr(raw), B, Lq, Tk, float(scale), _ptr(prev_score), T, qh, qw, _ptr(fuse_w),
+                                          _ptr(fuse_b), _ptr(score_out), _ptr(P.hi), _ptr(P.lo), P.ld, _stream())
+    _L.check(rc, "mtt_invpt_fuse_softmax")
 
 
 # ------------------------------------------------------------------------------------------------

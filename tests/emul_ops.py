@@ -58,7 +58,7 @@ def install(mp):
 
     def gemm(a, w, *, M=None, N=None, K=None, bias=None, act=0, residual=None, res_row_mod=0, out_f32=None,
              out_split=None, out_col_offset=0, regroup=None, conv=None, a_row_offset=0, a_gather=None,
-             w_col_offset=0, a_col_offset=0):
+             w_col_offset=0, a_col_offset=0, w_row_offset=0, out_row_offset=0):
         M = a.rows if M is None else M
         N = w.rows if N is None else N
         K = a.cols if K is None else K
@@ -68,7 +68,7 @@ def install(mp):
         else:
             A = _rsplit(a, a_col_offset + K)[a_row_offset:a_row_offset + M, a_col_offset:]
         if conv is None:
-            Wm = _rsplit(w, w_col_offset + K)[:N, w_col_offset:]
+            Wm = _rsplit(w, w_col_offset + K)[w_row_offset:w_row_offset + N, w_col_offset:]
             y = A @ Wm.t()
         else:
             B, H, Wd, ks, dil = conv
@@ -91,9 +91,9 @@ def install(mp):
             out_f32[ro, :N] = y
         if out_split is not None:
             hi = y.bfloat16()
-            out_split.buf[0, ro, out_col_offset:out_col_offset + N] = hi
+            out_split.buf[0, ro + out_row_offset, out_col_offset:out_col_offset + N] = hi
             if out_split.nsplit == 2:
-                out_split.buf[1, ro, out_col_offset:out_col_offset + N] = (y - hi.float()).bfloat16()
+                out_split.buf[1, ro + out_row_offset, out_col_offset:out_col_offset + N] = (y - hi.float()).bfloat16()
 
     def gemm_splitk(a, w, partial, out_f32, *, K, bias=None, chunks):
         ops.gemm(a, w, K=K, bias=bias, out_f32=out_f32)       # the same function; the K split is a scheduling detail
@@ -241,12 +241,9 @@ def install(mp):
         y = F.avg_pool2d(xm, s, s, 0, ceil_mode=True)
         _wsplit(out, y.flatten(2).transpose(1, 2).reshape(-1, Cdim))
 
-    def invpt_attention(q, k, v, out, *, B, Lq, Tk, Cdim, scale, prev_score=None, T=0, qh=0, qw=0, fuse_w=None,
-                        fuse_b=None, score_out=None):
-        d = Cdim // 2
-        sp = lambda t, L: t[:, :Cdim].reshape(B, L, 2, d).transpose(1, 2)
-        Q, K, V = sp(q, Lq), sp(k, Tk), sp(v, Tk)
-        score = (Q @ K.transpose(-2, -1)) * scale
+    def invpt_fuse_softmax(raw, P, *, B, Lq, Tk, scale, prev_score=None, T=0, qh=0, qw=0, fuse_w=None, fuse_b=None,
+                           score_out=None):
+        score = raw * scale                                                   # [B, 2, Lq, Tk]
         if prev_score is not None:
             sh, sw = qh // 2, qw // 2
             ups = []
@@ -258,8 +255,7 @@ def install(mp):
             score = F.conv2d(both, fuse_w.reshape(2, 4, 1, 1), fuse_b)
         if score_out is not None:
             score_out.copy_(score)
-        o = (score.softmax(-1) @ V).transpose(1, 2).reshape(B * Lq, Cdim)
-        _wsplit(out, o)
+        _wsplit(P, score.softmax(-1).reshape(B * 2 * Lq, Tk))
 
     # ---- the named operators of block_ops.cu, written like their C bodies: the same primitive sequence over the
     # ---- same workspace layout (so a wrong workspace offset or size fails here)
