@@ -484,7 +484,10 @@ class _Plan:
                 s.kvin = S(B * s.Tk, Ci)
                 # cross-task attention (2 heads of dim Ci / 2): q, k as split operands of S = Q_h K_h^T, v transposed per image
                 # for O_h = P_h V_h; both contractions are grouped launches over (batch, head)
-                s.qs, s.ks, s.v32 = S(B * s.Lq, Ci), S(B * s.Tk, Ci), z(B * s.Tk, Ci)
+                # (each head's columns start at a multiple of 8 elements: TMA base pointers are 16-byte aligned)
+                s.dh = Ci // 2
+                s.dhp = ops.round_up(s.dh, 8)
+                s.qs, s.ks, s.v32 = S(B * s.Lq, 2 * s.dhp, zero=True), S(B * s.Tk, 2 * s.dhp, zero=True), z(B * s.Tk, Ci)
                 s.vt = S(B * Ci, s.Tk, zero=True)
                 s.score = z(B, 2, s.Lq, s.Tk)          # raw scores, then (in place) the fused pre-softmax scores
                 s.P = S(B * 2 * s.Lq, s.Tk, zero=True)
@@ -618,13 +621,17 @@ class _Plan:
         ops.layernorm(s.xj, sw.n1w, sw.n1b, sw.eps, out_f32=s.xn32)                                    # :298
         ops.dwconv3x3_s2(s.xn32, sw.dw_w, sw.dw_b, s.qin, B=B, T=T, h=h, w=w, Cdim=Ci)                 # :171-173
         ops.avgpool(s.xn32, s.kvin, BT=B * T, h=h, w=w, Cdim=Ci, s=s.kvs)                              # :175-187
-        ops.gemm(s.qin, sw.proj_q, bias=sw.proj_q_b, out_split=s.qs)                                   # :200
-        ops.gemm(s.kvin, sw.proj_k, bias=sw.proj_k_b, out_split=s.ks)                                  # :201
+        dh, dhp = s.dh, s.dhp
+        for src, wq, bq, dst in ((s.qin, sw.proj_q, sw.proj_q_b, s.qs), (s.kvin, sw.proj_k, sw.proj_k_b, s.ks)):   # :200-201
+            if dh == dhp:
+                ops.gemm(src, wq, bias=bq, out_split=dst)
+            else:           # one launch per head so that each head's columns land on an aligned offset
+                for hd in range(2):
+                    ops.gemm(src, wq, N=dh, bias=bq[hd * dh:], w_row_offset=hd * dh, out_split=dst, out_col_offset=hd * dhp)
         ops.gemm(s.kvin, sw.proj_v, bias=sw.proj_v_b, out_f32=s.v32)                                   # :202
         ops.transpose_split(s.v32, s.vt, B=B, L=s.Tk, Cdim=Ci)
-        dh = Ci // 2
-        ops.gemm_grouped([(s.qs, s.ks, dict(M=s.Lq, N=s.Tk, K=dh, a_row_offset=b * s.Lq, a_col_offset=hd * dh,
-                                            w_row_offset=b * s.Tk, w_col_offset=hd * dh, out_f32=s.score[b, hd]))
+        ops.gemm_grouped([(s.qs, s.ks, dict(M=s.Lq, N=s.Tk, K=dh, a_row_offset=b * s.Lq, a_col_offset=hd * dhp,
+                                            w_row_offset=b * s.Tk, w_col_offset=hd * dhp, out_f32=s.score[b, hd]))
                           for b in range(B) for hd in range(2)])                                       # :204 q k^T
         prev = self.st[i - 1].score if i > 0 else None
         ops.invpt_fuse_softmax(s.score, s.P, B=B, Lq=s.Lq, Tk=s.Tk, scale=Ci ** -0.5, prev_score=prev, T=T, qh=h // 2,

@@ -295,7 +295,7 @@ class _SwinPlan:
         self.img = bb.full_img_size
         self.ds_img = tuple(bb.patch_embed.img_size)
         self.graph, self.static_in = None, None
-        self.streams = _Streams(device, max(T, 1))
+        self.streams = _Streams(device, max(T, 2))
         ns = nsplit
         S = lambda r, c, **kw: ops.Split(r, c, device, ns, **kw)
         z = lambda *s: torch.zeros(*s, device=device, dtype=torch.float32)
@@ -419,19 +419,24 @@ class _SwinPlan:
         ops.gemm(s.ao, w.proj, bias=w.proj_b, out_f32=s.o32)                                       # :207
         ops.swin_window_scatter(s.o32, s.raw, s.xa32, s.x, s.p, s.logits, B=B, H=s.H, W=s.W, Cdim=C, T=T, ws=s.ws,
                                 shift=shift, heads=s.heads, last=w.last)                            # :210, :343-360, :399
-        # channel attention between the prompts and the channels of the attention output (:372-396)
-        ops.gemm(s.chan_ps, w.cq, bias=w.cq_b, out_f32=s.q32)
-        ops.transpose_split(s.xa32, s.xat, B=B, L=s.L, Cdim=C)
-        if s.kchunks > 1:   # C rows x (H*W) columns: a handful of M tiles with thousands of K blocks -> split K
-            ops.gemm_splitk(s.xat, w.ckv, s.kv_part, s.kv32, K=s.L, bias=w.ckv_b, chunks=s.kchunks)
-        else:
-            ops.gemm(s.xat, w.ckv, K=s.L, bias=w.ckv_b, out_f32=s.kv32)
-        ops.swin_chan_attention(s.q32, s.kv32, s.co32, s.cos, s.rc, B=B, T=T, Cdim=C, ce=ce, nh=self.nh, nw=self.nw)
-        ops.ln_mlp_residual(s.x, w.n2w, w.n2b, w.eps, w.fc1, w.fc1_b, w.fc2, w.fc2_b, s.ws_mlp)    # :400
-        if not w.last:
-            ops.gemm(s.cos, w.cp, bias=w.cp_b, out_split=s.t1)                                     # chan_proj
-            ops.gemm(s.t1, w.tt1, bias=w.tt1_b, residual=s.p, out_f32=s.p)                         # token_trans1; :403
-            ops.ln_mlp_residual(s.p, w.n2w, w.n2b, w.eps, w.fc1, w.fc1_b, w.fc2, w.fc2_b, s.ws_mlp_p)   # :404
+        # The prompt path -- channel attention between the prompts and the channels of the attention output (:372-396),
+        # then the prompt update and the prompts' own MLP (:403-404) -- is a chain of small launches on B*T rows that
+        # only needs xa: it runs on a side stream next to the MLP of the B*H*W patch rows (:400) and joins at the end.
+        def prompt_path():
+            ops.gemm(s.chan_ps, w.cq, bias=w.cq_b, out_f32=s.q32)
+            ops.transpose_split(s.xa32, s.xat, B=B, L=s.L, Cdim=C)
+            if s.kchunks > 1:   # C rows x (H*W) columns: a handful of M tiles with thousands of K blocks -> split K
+                ops.gemm_splitk(s.xat, w.ckv, s.kv_part, s.kv32, K=s.L, bias=w.ckv_b, chunks=s.kchunks)
+            else:
+                ops.gemm(s.xat, w.ckv, K=s.L, bias=w.ckv_b, out_f32=s.kv32)
+            ops.swin_chan_attention(s.q32, s.kv32, s.co32, s.cos, s.rc, B=B, T=T, Cdim=C, ce=ce, nh=self.nh, nw=self.nw)
+            if not w.last:
+                ops.gemm(s.cos, w.cp, bias=w.cp_b, out_split=s.t1)                                 # chan_proj
+                ops.gemm(s.t1, w.tt1, bias=w.tt1_b, residual=s.p, out_f32=s.p)                     # token_trans1; :403
+                ops.ln_mlp_residual(s.p, w.n2w, w.n2b, w.eps, w.fc1, w.fc1_b, w.fc2, w.fc2_b, s.ws_mlp_p)   # :404
+
+        self.streams.par([prompt_path,
+                          lambda: ops.ln_mlp_residual(s.x, w.n2w, w.n2b, w.eps, w.fc1, w.fc1_b, w.fc2, w.fc2_b, s.ws_mlp)])
 
     def _merge(self, i):
         """PatchMerging (TP:430-472): stage i -> the inputs of stage i + 1 and of decoder level i."""
