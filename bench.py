@@ -299,7 +299,7 @@ def gemm_roofline(model, plan, x_dev, peaks, peak_src):
         traffic = tj["gemm_family"]["bytes_per_launch"]
         traffic_src = ("dram__bytes_read.sum + dram__bytes_write.sum averaged over the %d GEMM / conv launches of one "
                        "tp_cfg4 bs 4 forward (profiles/dram_traffic.json <- %s)" % (tj["gemm_family"]["launches"],
-                                                                                    "profiles/r1j_dram_launches.csv"))
+                                                                                    tj.get("source", "").rsplit(", ", 1)[-1]))
     bb = bb_fl / (bb_ms * 1e-3) / 1e12 if bb_ms > 0 else None
     at_ms = sum(s.elapsed_time(e) for s, e, _ in arecs)
     at = sum(f for _, _, f in arecs) / (at_ms * 1e-3) / 1e12 if at_ms > 0 else None
