@@ -25,11 +25,18 @@ struct Gemm2Cfg {
   static constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 + 256;
 };
 
-template <int NSPLIT, int BN2>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
-gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
-                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
-                const GemmParams p) {
+// Ragged last N tile: the pair issues a NARROWER MMA (N rounded up to 16) instead of multiplying zero-filled weight
+// rows. With N = n the two CTAs contribute n / 2 weight rows each, so CTA r loads the rows starting at
+// tile_start + r * n / 2 (not r * BN2 / 2): accumulator column c is then output column tile_start + c for c < n.
+// (350 -> 350 convs on 256-wide tiles: the second tile is 96 wide instead of 256 = 31 % fewer MMAs.)
+__device__ __forceinline__ int pair_tile_n(const GemmParams& p, int nt, int bn2) {
+  const int left = p.N - nt * bn2;
+  return left >= bn2 ? bn2 : ((left + 15) & ~15);
+}
+
+// The kernel body, shared by the single-problem kernel (GROUPED = false) and the grouped one (tile -> (problem, tile)).
+template <int NSPLIT, int BN2, bool GROUPED>
+__device__ __forceinline__ void gemm2_tc_body(const CUtensorMap (*maps)[4], const GemmParams& p, const GemmGroup* grp) {
   using Cfg = Gemm2Cfg<NSPLIT>;
   constexpr int ST = Cfg::kStages;
   constexpr int BNH = BN2 / 2;                       // weight rows held by each CTA
@@ -51,15 +58,16 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
   const int pair = blockIdx.x >> 1;
   const int num_pairs = gridDim.x >> 1;
   const int pairs_m = (p.tiles_m + 1) >> 1;
-  const int num_tiles = pairs_m * p.tiles_n;
+  const int tpp = pairs_m * p.tiles_n;                        // pair tiles per problem
+  const int num_tiles = GROUPED ? tpp * grp->count : tpp;
   const int k_iters = p.taps * p.num_kb;
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmA_hi);
-    tma_prefetch_desc(&tmB_hi);
+    tma_prefetch_desc(&maps[0][0]);
+    tma_prefetch_desc(&maps[0][2]);
     if (NSPLIT == 2) {
-      tma_prefetch_desc(&tmA_lo);
-      tma_prefetch_desc(&tmB_lo);
+      tma_prefetch_desc(&maps[0][1]);
+      tma_prefetch_desc(&maps[0][3]);
     }
     for (int s = 0; s < ST; ++s) {
       mbar_init(&full_bar[s], 1);
@@ -86,9 +94,15 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
       uint32_t phase = 0;
       const uint32_t stage_tx = 2 * NSPLIT * (p.a_box_bytes + kBTile);  // both CTAs' bytes
       for (int tile = pair; tile < num_tiles; tile += num_pairs) {
-        const int ms = (tile % pairs_m) * 2 + (int)rank;
-        const int nt = tile / pairs_m;
-        const int nrow = nt * BN2 + (int)rank * BNH;
+        const int g = GROUPED ? tile / tpp : 0;
+        const int tl = GROUPED ? tile - g * tpp : tile;
+        const int ms = (tl % pairs_m) * 2 + (int)rank;
+        const int nt = tl / pairs_m;
+        const int nrow = nt * BN2 + (int)rank * (pair_tile_n(p, nt, BN2) >> 1);
+        const CUtensorMap* tmA_hi = &maps[g][0];
+        const CUtensorMap* tmA_lo = &maps[g][1];
+        const CUtensorMap* tmB_hi = &maps[g][2];
+        const CUtensorMap* tmB_lo = &maps[g][3];
         for (int ki = 0; ki < k_iters; ++ki) {
           const int tap = ki / p.num_kb, kb = ki - tap * p.num_kb;
           const int dy = (tap / p.ksize - p.ksize / 2) * p.dil;
@@ -101,10 +115,10 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
               if (leader) mbar_arrive(&full_bar[stage]);
             } else {
               if (leader) mbar_arrive_expect_tx(&full_bar[stage], stage_tx);
-              load_a_tile<NSPLIT, 1>(p, &tmA_hi, &tmA_lo, sa, &full_bar[stage], ms, kb, dy, dx);
+              load_a_tile<NSPLIT, 1>(p, tmA_hi, tmA_lo, sa, &full_bar[stage], ms, kb, dy, dx);
               const int kcoord = tap * p.cin_pad + kb * BK;
-              tma_load_2d_cg2(sb, &tmB_hi, &full_bar[stage], kcoord, nrow);
-              if (NSPLIT == 2) tma_load_2d_cg2(sb + kBTile, &tmB_lo, &full_bar[stage], kcoord, nrow);
+              tma_load_2d_cg2(sb, tmB_hi, &full_bar[stage], kcoord, nrow);
+              if (NSPLIT == 2) tma_load_2d_cg2(sb + kBTile, tmB_lo, &full_bar[stage], kcoord, nrow);
             }
           }
           __syncwarp();
@@ -118,7 +132,6 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (leader CTA only; elected lane)
     if (leader) {
-      constexpr uint32_t idesc = umma_idesc_bf16(256, BN2, 0);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -128,6 +141,7 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
         mbar_wait(&tempty_bar[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t tacc = tmem_base + as * BN2;
+        const uint32_t idesc = umma_idesc_bf16(256, pair_tile_n(p, (GROUPED ? tile % tpp : tile) / pairs_m, BN2), 0);
         uint32_t accum = 0;
         int kb = 0;
         for (int ki = 0; ki < k_iters; ++ki) {
@@ -174,9 +188,20 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
     for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
-      const int ms = (tile % pairs_m) * 2 + (int)rank;
-      const int nt = tile / pairs_m;
+      const int g = GROUPED ? tile / tpp : 0;
+      const int tl = GROUPED ? tile - g * tpp : tile;
+      const int ms = (tl % pairs_m) * 2 + (int)rank;
+      const int nt = tl / pairs_m;
       const RowInfo ri = row_info(p, ms, row);
+      GemmParams pq = p;                      // grouped: this problem's pointers over the shared geometry
+      if (GROUPED) {
+        const GroupProblem& gp = grp->prob[g];
+        pq.bias = gp.bias;
+        pq.residual = gp.residual;
+        pq.out_f32 = gp.out_f32;
+        pq.out_hi = gp.out_hi;
+        pq.out_lo = gp.out_lo;
+      }
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN2 + half * kColsPerWarp;
@@ -190,8 +215,8 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
         __syncwarp();
         if (lane == 0) mbar_arrive_leader(&tempty_bar[as]);
         if (ri.ok && !(p.debug & 2)) {
-          epilogue_store32(p, r0, nbase, ri);
-          epilogue_store32(p, r1, nbase + 32, ri);
+          epilogue_store32(pq, r0, nbase, ri);
+          epilogue_store32(pq, r1, nbase + 32, ri);
         }
       } else {
         // 128 columns per warp: two 64-column halves to keep the register footprint at 64 accumulators
@@ -207,8 +232,8 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
             if (lane == 0) mbar_arrive_leader(&tempty_bar[as]);
           }
           if (ri.ok && !(p.debug & 2)) {
-            epilogue_store32(p, r0, nbase + hh * 64, ri);
-            epilogue_store32(p, r1, nbase + hh * 64 + 32, ri);
+            epilogue_store32(pq, r0, nbase + hh * 64, ri);
+            epilogue_store32(pq, r1, nbase + hh * 64 + 32, ri);
           }
           __syncwarp();
         }
@@ -223,6 +248,23 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
     tc_fence_after();
     tmem_dealloc_cg2<kTmemCols>(tmem_base);
   }
+}
+
+struct Gemm2Maps1 {
+  CUtensorMap m[1][4];
+};
+
+template <int NSPLIT, int BN2>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+gemm2_tc_kernel(const __grid_constant__ Gemm2Maps1 maps, const GemmParams p) {
+  gemm2_tc_body<NSPLIT, BN2, false>(maps.m, p, nullptr);
+}
+
+template <int NSPLIT, int BN2>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+gemm2_tc_grouped_kernel(const __grid_constant__ GemmGroupMaps maps, const __grid_constant__ GemmGroup grp,
+                        const GemmParams p) {
+  gemm2_tc_body<NSPLIT, BN2, true>(maps.m, p, &grp);
 }
 
 template <int NSPLIT, int BN2>
@@ -241,9 +283,52 @@ static int launch_gemm2(const CUtensorMap* maps, const GemmParams& p, cudaStream
   const int tiles = pairs_m * p.tiles_n;
   const int max_pairs = sm_count() / 2;
   const int pairs = tiles < max_pairs ? tiles : max_pairs;
-  gemm2_tc_kernel<NSPLIT, BN2><<<pairs * 2, kGemmThreads, Cfg::kSmemBytes, stream>>>(maps[0], maps[1], maps[2],
-                                                                                    maps[3], p);
+  Gemm2Maps1 gm;
+  for (int i = 0; i < 4; ++i) gm.m[0][i] = maps[i];
+  gemm2_tc_kernel<NSPLIT, BN2><<<pairs * 2, kGemmThreads, Cfg::kSmemBytes, stream>>>(gm, p);
   return check_launch("mtt_gemm(cta pair)");
+}
+
+template <int NSPLIT>
+static int launch_gemm2_grouped(const GemmGroupMaps& gm, const GemmGroup& grp, const GemmParams& p, cudaStream_t stream) {
+  using Cfg = Gemm2Cfg<NSPLIT>;
+  static bool attr_set[kMaxDevices] = {};
+  const int dev_ = current_device();
+  if (!attr_set[dev_]) {
+    cudaError_t e = cudaFuncSetAttribute(gemm2_tc_grouped_kernel<NSPLIT, 256>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (e != cudaSuccess)
+      return set_error(MTT_ERR_LAUNCH, "gemm2(grouped): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr_set[dev_] = true;
+  }
+  const int tiles = grp.tiles_per_problem * grp.count;
+  const int max_pairs = sm_count() / 2;
+  const int pairs = tiles < max_pairs ? tiles : max_pairs;
+  gemm2_tc_grouped_kernel<NSPLIT, 256><<<pairs * 2, kGemmThreads, Cfg::kSmemBytes, stream>>>(gm, grp, p);
+  return check_launch("mtt_gemm_grouped(cta pair)");
+}
+
+// count problems of identical geometry on the CTA-pair kernel (256 x 256 tiles, ragged last N tile narrowed)
+int launch_gemm_2cta_grouped(const mtt_gemm_desc* d, int count, cudaStream_t stream) {
+  GemmParams p;
+  GemmGroupMaps gm;
+  GemmGroup grp;
+  grp.count = count;
+  for (int g = 0; g < count; ++g) {
+    GemmParams pg;
+    int rc = gemm_prepare(&d[g], 128, pg, gm.m[g]);
+    if (rc) return rc;
+    pg.tiles_n = (d[g].N + 255) / 256;
+    if (g == 0) {
+      p = pg;
+    } else {
+      p.vec_ok = p.vec_ok && pg.vec_ok;
+      p.vec32_ok = p.vec32_ok && pg.vec32_ok;
+    }
+    grp.prob[g] = GroupProblem{pg.bias, pg.residual, pg.out_f32, pg.out_hi, pg.out_lo};
+  }
+  grp.tiles_per_problem = ((p.tiles_m + 1) / 2) * p.tiles_n;
+  return d[0].nsplit == 2 ? launch_gemm2_grouped<2>(gm, grp, p, stream) : launch_gemm2_grouped<1>(gm, grp, p, stream);
 }
 
 int launch_gemm_2cta(const mtt_gemm_desc* d, int bn2, cudaStream_t stream) {

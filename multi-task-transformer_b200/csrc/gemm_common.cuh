@@ -253,6 +253,7 @@ __device__ __forceinline__ void epilogue_store32(const GemmParams& p, const uint
 // Entry points of the two kernels (defined in gemm_tc.cu / gemm2_tc.cu)
 int launch_gemm_1cta(const mtt_gemm_desc* d, cudaStream_t stream);
 int launch_gemm_1cta_grouped(const mtt_gemm_desc* d, int count, cudaStream_t stream);
+int launch_gemm_2cta_grouped(const mtt_gemm_desc* d, int count, cudaStream_t stream);
 int launch_gemm_2cta(const mtt_gemm_desc* d, int bn2, cudaStream_t stream);
 
 }  // namespace mtt

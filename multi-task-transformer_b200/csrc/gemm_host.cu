@@ -243,5 +243,18 @@ extern "C" int mtt_gemm_grouped(const mtt_gemm_desc* d, int32_t count, mtt_strea
   double fl = 0;
   for (int g = 0; g < count; ++g) fl += 2.0 * d[g].M * d[g].N * d[g].K * (d[g].mode == 1 ? d[g].ksize * d[g].ksize : 1);
   ProfileScope prof(stream, 0, fl, a.M * count, a.N, a.K * (a.mode == 1 ? a.ksize * a.ksize : 1));
-  return launch_gemm_1cta_grouped(d, count, stream);
+  if (g_variant < 0) {
+    const char* e = getenv("MTT_GEMM_VARIANT");
+    g_variant = e ? atoi(e) : 0;
+  }
+  int v = g_variant;
+  if (v == 0) {
+    // Grouping removes the reason single decoder-width problems stay on the 128 x 128 tile (too few pair tiles to fill
+    // 74 CTA pairs): with >= one wave of 256-row pair tiles the CTA pair wins, because it needs half the L2 -> SM
+    // operand bytes per MMA (the 1-CTA split tile is capped at ~49 % tensor pipe by the 42 B/clk/SM L2 path) and
+    // narrows the ragged last N tile. Gathered-A problems and tiny M stay on the 1-CTA kernel.
+    const long long pair_tiles = (long long)count * ((a.M + 255) / 256) * ((a.N + 255) / 256);
+    v = (a.a_group_rows == 0 && a.M >= 512 && a.N >= 64 && pair_tiles >= sm_count() / 2) ? 2 : 1;
+  }
+  return v == 1 ? launch_gemm_1cta_grouped(d, count, stream) : launch_gemm_2cta_grouped(d, count, stream);
 }

@@ -60,14 +60,14 @@ swin_gather_kernel(const float* __restrict__ xn, long long ldx, const float* __r
 }
 
 // ---- window attention (TP:183-206) ------------------------------------------------------------------------------------
-// One CTA per (window, head); a thread owns TWO query rows (i and i + ceil(N/2)) of the N = T + ws^2 tokens and runs an
-// online softmax over the keys. K and V of the window are staged in shared memory as fp32 and read as float4
-// broadcasts: every key row is loaded once per thread for both of its query rows (the first version -- one row per
-// thread, float2 reads -- was bound by the shared-memory pipe: 32 LDS per key per warp). The relative-position bias and
-// the shift mask apply to patch x patch entries only (TP:196, :201) and are read through their TRANSPOSES so that
-// consecutive threads read consecutive addresses. Prompt rows export their raw q . k (TP:189).
+// One CTA per (window, head); thread i owns query row i of the N = T + ws^2 tokens and runs an online softmax over the
+// keys. K and V of the window are staged in shared memory as fp32 and read as float4 broadcasts (every thread reads the
+// same key). The relative-position bias and the shift mask apply to patch x patch entries only (TP:196, :201) and are
+// read through their TRANSPOSES so that consecutive threads read consecutive addresses. Prompt rows export their raw
+// q . k (TP:189). Measured on Swin-B 1024x2048 (24 launches per forward): float2 reads 250 us per launch; two query
+// rows per thread (half the shared-memory reads, 168 registers, 96 threads) was SLOWER (forward 23.6 -> 25.1 ms).
 template <int DH>
-__global__ void __launch_bounds__(96)
+__global__ void __launch_bounds__(192)
 swin_attn_kernel(const __nv_bfloat16* __restrict__ q_hi, const __nv_bfloat16* __restrict__ q_lo, long long ldq, int C,
                  int heads, int T, int L, int nW, float scale, const float* __restrict__ biasT,
                  const float* __restrict__ maskT, __nv_bfloat16* __restrict__ o_hi, __nv_bfloat16* __restrict__ o_lo,
@@ -89,85 +89,63 @@ swin_attn_kernel(const __nv_bfloat16* __restrict__ q_hi, const __nv_bfloat16* __
     sV[i] = ld_f(row0 + r, 2 * C + h * DH + d);
   }
   __syncthreads();
-  const int half = (N + 1) >> 1;
-  for (int i0 = threadIdx.x; i0 < half; i0 += blockDim.x) {
-    const int rows[2] = {i0, i0 + half};
-    const bool live[2] = {true, i0 + half < N};
-    float2 q[2][DH / 2], o[2][DH / 2];
-    float m[2] = {-INFINITY, -INFINITY}, l[2] = {0.f, 0.f};
-    const float* bcol[2];
-    const float* mcol[2];
-    float* rrow[2];
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    // q and the output accumulator as packed fp32 pairs (FFMA2); the accumulator is rescaled only when the running
+    // maximum moves
+    float2 q[DH / 2], o[DH / 2];
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const int i = live[u] ? rows[u] : rows[0];
-#pragma unroll
-      for (int d = 0; d < DH / 2; ++d) {
-        q[u][d] = make_float2(ld_f(row0 + i, h * DH + 2 * d), ld_f(row0 + i, h * DH + 2 * d + 1));
-        o[u][d] = make_float2(0.f, 0.f);
-      }
-      const bool pq = i >= T;
-      bcol[u] = pq ? biasT + ((long long)h * L) * L + (i - T) : nullptr;                  // + (j - T) * L
-      mcol[u] = (pq && maskT) ? maskT + ((long long)(bw % nW) * L) * L + (i - T) : nullptr;
-      rrow[u] = (!pq && raw && live[u]) ? raw + (((long long)bw * heads + h) * T + i) * L : nullptr;
+    for (int d = 0; d < DH / 2; ++d) {
+      q[d] = make_float2(ld_f(row0 + i, h * DH + 2 * d), ld_f(row0 + i, h * DH + 2 * d + 1));
+      o[d] = make_float2(0.f, 0.f);
     }
+    float m = -INFINITY, l = 0.f;
+    const bool patch_q = i >= T;
+    const float* bcol = patch_q ? biasT + ((long long)h * L) * L + (i - T) : nullptr;                  // + (j - T) * L
+    const float* mcol = (patch_q && maskT) ? maskT + ((long long)(bw % nW) * L) * L + (i - T) : nullptr;
+    float* rrow = (!patch_q && raw) ? raw + (((long long)bw * heads + h) * T + i) * L : nullptr;
     for (int j = 0; j < N; ++j) {
       const float4* kj = reinterpret_cast<const float4*>(sK + j * DH);
-      float2 acc[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+      float2 acc = make_float2(0.f, 0.f);
 #pragma unroll
       for (int d = 0; d < DH / 4; ++d) {
         const float4 k4 = kj[d];
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          acc[u] = ffma2(q[u][2 * d], make_float2(k4.x, k4.y), acc[u]);
-          acc[u] = ffma2(q[u][2 * d + 1], make_float2(k4.z, k4.w), acc[u]);
-        }
+        acc = ffma2(q[2 * d], make_float2(k4.x, k4.y), acc);
+        acc = ffma2(q[2 * d + 1], make_float2(k4.z, k4.w), acc);
       }
-      float p[2];
-#pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        float s = acc[u].x + acc[u].y;
-        if (rrow[u] && j >= T) rrow[u][j - T] = s;
-        s *= scale;
-        if (bcol[u] && j >= T) {
-          s += bcol[u][(long long)(j - T) * L];
-          if (mcol[u]) s += mcol[u][(long long)(j - T) * L];
-        }
-        if (s > m[u]) {                              // new running maximum: rescale what has been accumulated
-          const float a = __expf(m[u] - s);
-          l[u] *= a;
-#pragma unroll
-          for (int d = 0; d < DH / 2; ++d) o[u][d] = make_float2(o[u][d].x * a, o[u][d].y * a);
-          m[u] = s;
-        }
-        p[u] = __expf(s - m[u]);
-        l[u] += p[u];
+      float s = acc.x + acc.y;
+      if (rrow && j >= T) rrow[j - T] = s;
+      s *= scale;
+      if (patch_q && j >= T) {
+        s += bcol[(long long)(j - T) * L];
+        if (mcol) s += mcol[(long long)(j - T) * L];
       }
+      if (s > m) {                                   // new running maximum: rescale what has been accumulated
+        const float a = __expf(m - s);
+        l *= a;
+#pragma unroll
+        for (int d = 0; d < DH / 2; ++d) o[d] = make_float2(o[d].x * a, o[d].y * a);
+        m = s;
+      }
+      const float p = __expf(s - m);
+      l += p;
+      const float2 p2 = make_float2(p, p);
       const float4* vj = reinterpret_cast<const float4*>(sV + j * DH);
 #pragma unroll
       for (int d = 0; d < DH / 4; ++d) {
         const float4 v4 = vj[d];
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const float2 p2 = make_float2(p[u], p[u]);
-          o[u][2 * d] = ffma2(p2, make_float2(v4.x, v4.y), o[u][2 * d]);
-          o[u][2 * d + 1] = ffma2(p2, make_float2(v4.z, v4.w), o[u][2 * d + 1]);
-        }
+        o[2 * d] = ffma2(p2, make_float2(v4.x, v4.y), o[2 * d]);
+        o[2 * d + 1] = ffma2(p2, make_float2(v4.z, v4.w), o[2 * d + 1]);
       }
     }
+    const float inv = 1.f / l;
+    __nv_bfloat16* dh = o_hi + (row0 + i) * ldo + h * DH;
+    __nv_bfloat16* dl = o_lo ? o_lo + (row0 + i) * ldo + h * DH : nullptr;
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      if (!live[u]) continue;
-      const float inv = 1.f / l[u];
-      __nv_bfloat16* dh = o_hi + (row0 + rows[u]) * ldo + h * DH;
-      __nv_bfloat16* dl = o_lo ? o_lo + (row0 + rows[u]) * ldo + h * DH : nullptr;
-#pragma unroll
-      for (int d = 0; d < DH / 2; ++d) {
-        uint32_t hh, ll;
-        split_pack2(o[u][d].x * inv, o[u][d].y * inv, hh, ll);
-        *reinterpret_cast<uint32_t*>(dh + 2 * d) = hh;
-        if (dl) *reinterpret_cast<uint32_t*>(dl + 2 * d) = ll;
-      }
+    for (int d = 0; d < DH / 2; ++d) {
+      uint32_t hh, ll;
+      split_pack2(o[d].x * inv, o[d].y * inv, hh, ll);
+      *reinterpret_cast<uint32_t*>(dh + 2 * d) = hh;
+      if (dl) *reinterpret_cast<uint32_t*>(dl + 2 * d) = ll;
     }
   }
 }
@@ -442,7 +420,7 @@ int mtt_swin_window_attention(const void* qkv_hi, const void* qkv_lo, int64_t ld
   const __nv_bfloat16* ql = static_cast<const __nv_bfloat16*>(qkv_lo);
   __nv_bfloat16* oh = static_cast<__nv_bfloat16*>(out_hi);
   __nv_bfloat16* ol = static_cast<__nv_bfloat16*>(out_lo);
-  const int threads = N <= 64 ? 32 : (N <= 128 ? 64 : 96);      // one thread per pair of query rows
+  const int threads = N <= 64 ? 64 : (N <= 128 ? 128 : 192);
   dim3 grid(BW, heads);
 #define MTT_SWIN_ATTN(DH)                                                                                        \
   case DH: {                                                                                                     \

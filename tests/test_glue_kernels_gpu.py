@@ -103,9 +103,19 @@ def test_gemm_splitk(both, cuda_dev):
         assert relerr(out, want) < 2e-5
 
 
-def test_gemm_grouped_equals_separate_launches(both, cuda_dev):
-    """mtt_gemm_grouped == the same problems launched one by one, bit for bit (linear and 3x3 conv, ragged N)."""
+@pytest.mark.parametrize("variant", [1, 2], ids=["1cta_128x128", "cta_pair_256x256"])
+def test_gemm_grouped_equals_separate_launches(both, cuda_dev, variant):
+    """mtt_gemm_grouped == the same problems launched one by one on the same kernel variant, bit for bit (linear and
+    3x3 conv, ragged N: the CTA pair narrows its last N tile), and both agree with float64."""
     ops, emu = both
+    ops.set_gemm_variant(variant)
+    try:
+        _grouped_case(ops, cuda_dev)
+    finally:
+        ops.set_gemm_variant(0)
+
+
+def _grouped_case(ops, cuda_dev):
     torch.manual_seed(12)
     G, M, N, K = 5, 4 * 96, 300, 200
     A = [ops.split_f32(rnd(M, K, dev=cuda_dev)) for _ in range(G)]
@@ -123,6 +133,9 @@ def test_gemm_grouped_equals_separate_launches(both, cuda_dev):
     torch.cuda.synchronize()
     for g in range(G):
         assert torch.equal(o1[g], o2[g]) and torch.equal(s1[g].buf, s2[g].buf)
+        want = torch.nn.functional.gelu(A[g].float().double() @ W[g].float()[:, :K].double().t() + bias[g].double()) \
+            + res[g][:, :N].double()
+        assert relerr(o2[g][:, :N], want) < 3e-5
     B, H, Wd, Cin, Cout = 2, 8, 12, 70, 44
     X = [ops.split_f32(rnd(B * H * Wd, Cin, dev=cuda_dev)) for _ in range(G)]
     Wc = [ops.pack_conv_weight(rnd(Cout, Cin, 3, 3, dev=cuda_dev, scale=0.05), rnd(Cout, dev=cuda_dev), None, 2) for _ in range(G)]
