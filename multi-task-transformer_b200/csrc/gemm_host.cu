@@ -248,6 +248,12 @@ extern "C" int mtt_gemm_grouped(const mtt_gemm_desc* d, int32_t count, mtt_strea
     g_variant = e ? atoi(e) : 0;
   }
   int v = g_variant;
+  static int g_grouped = -1;  // MTT_GEMM_GROUPED_VARIANT: A/B knob for grouped launches only (0 auto, 1, 2)
+  if (g_grouped < 0) {
+    const char* e = getenv("MTT_GEMM_GROUPED_VARIANT");
+    g_grouped = e ? atoi(e) : 0;
+  }
+  if (v == 0) v = g_grouped;
   if (v == 0) {
     // Grouping removes the reason single decoder-width problems stay on the 128 x 128 tile (too few pair tiles to fill
     // 74 CTA pairs): with >= one wave of 256-row pair tiles the CTA pair wins, because it needs half the L2 -> SM
