@@ -471,6 +471,93 @@ int mtt_nchw_to_nhwc_split(const float* in, int32_t B, int32_t C, int32_t H, int
 int mtt_nhwc_to_nchw(const float* in, int64_t ld_in, int32_t B, int32_t C, int32_t H, int32_t W, float* out,
                      mtt_stream_t stream);
 
+/* ---- training step: backward-pass and train-mode kernels ------------------------------------------
+ * The loop served is TaskPrompter/utils/train_utils.py:34-51 (forward, criterion, backward, clip_grad_norm_, Adam step)
+ * under main.py:92-94 (SyncBatchNorm + DDP). Contractions of the backward pass run on mtt_gemm / mtt_gemm_grouped: for
+ * Y = A W^T, dA = dY (W^T)^T and dW = dY^T (A^T)^T are K-major GEMMs once the operands are transposed
+ * (mtt_transpose_split for fp32 -> split, mtt_transpose_planes for split -> split). Everything here is fp32, row-major,
+ * [rows, cols] with a leading dimension in elements.
+ *
+ * mtt_colsum: out[c] (+)= sum_r x[row(r), c] (bias gradients; pos_embed / task_prompts gradients over the batch); with
+ *   in_group > 0 logical row r = (g, i), i < in_group, is physical row g*src_group + src_offset + i (as mtt_split_rows).
+ * mtt_layernorm_bwd: dx (+)= LN'(x) dy; dgamma[c] += sum_r dy xhat, dbeta[c] += sum_r dy (accumulated: zero them once per
+ *   step); stats_ws: 2*rows floats of scratch. (nn.LayerNorm eps 1e-6, TP taskprompter.py:262,266,329.)
+ * mtt_act_split / mtt_act_bwd: act(pre) -> split planes (the A operand of the next GEMM); dx = dy * act'(pre) (dx may be dy).
+ * mtt_axpy_rows: dst[r,:] = base[r,:] + row_scale[r] * src[r,:] (base / row_scale may be NULL): residual adds under
+ *   DropPath (TP taskprompter.py:273-277; timm 0.5.4 drop_path: per-sample mask / keep_prob) and their adjoints.
+ * mtt_transpose_planes: bf16 planes [B][R][C] (image b at row b*in_batch_rows) -> image b's [C, R] block at element offset
+ *   b*out_batch_stride of the output (0 = C*ld_out: blocks stacked by rows; R: side by side along the columns); exact.
+ * mtt_bn_stats / mtt_bn_finalize / mtt_bn_act: train-mode BatchNorm2d over NHWC rows: sums = (sum x, sum x^2) per channel
+ *   [2*cols] (all-reduce them across ranks for SyncBatchNorm, main.py:92), mean_rstd [2*cols] from sums / count with the
+ *   running statistics updated like nn.BatchNorm2d (momentum, unbiased running_var), then y = act(xhat*gamma + beta) as
+ *   fp32 and / or split planes. mtt_bn_bwd_reduce: sums = (sum dz, sum dz*xhat), dz = dy * act'(z) (= dbeta, dgamma; all-reduce
+ *   for SyncBatchNorm); mtt_bn_bwd_apply: dx = gamma*rstd*(dz - sums[0]/count - xhat*sums[1]/count).
+ * mtt_attn_softmax_bwd: per (batch*head) rows of raw scores S [BH, N, ld] and dP [BH, N, ld]: P = softmax(scale*S)
+ *   overwrites S, dS = scale*P*(dP - sum_j P dP) (+ d_raw [BH, T, N] on the first T rows: the gradient of the exported
+ *   prompt logits, TP taskprompter.py:204) overwrites dP and is also written as split rows.
+ * mtt_bilinear_bwd: adjoint of mtt_bilinear (align_corners = False): dy NHWC (nchw = 0) or NCHW [B,C,H2,W2] (nchw = 1,
+ *   lddy unused) -> dx NHWC [B,h,w,C] (+)=.
+ * mtt_gate_bwd: adjoint of mtt_gate_split for one task: dx (+)=, d_prompt_logits [B,H,T,N] (+)= at column T + pixel,
+ *   d_chan_logits [B,T,C,nh,nw] (+)=; dys / dyc fp32 [B*gh*gw, lddy].
+ * mtt_chan_logits_bwd: adjoint of mtt_chan_logits: dcp [B,T,P] (=) and dxn (+)= on the patch rows of the joint stream.
+ * mtt_ctr_bwd: adjoint of mtt_ctr_weights + the weights' use in mtt_ctr_mix: dnew, F fp32 [T, M, ld]; d_prompt_logits
+ *   (+)= on the prompt-prompt columns; dw0 [T,H,H], db0 [T,H], dw2 [T,H], db2 [T] (+)=. dw_ws: B*T*T floats. (The feature
+ *   gradients dF[j] = sum_t w[b,t,j] dnew[t] are mtt_ctr_mix with the transposed weights.)
+ * mtt_im2col3x3_t / mtt_im2col_patch_t: the transposed, split im2col operands of the convolution weight gradients:
+ *   rows (c, ky, kx) in nn.Conv2d.weight order, columns = output pixels (ldo >= B*H*W).
+ * mtt_sumsq + mtt_adam_step: clip_grad_norm_(max_norm, 2) and torch.optim.Adam on flat fp32 arenas (p, g, m, v of n
+ *   elements): g is scaled by grad_scale (1 / world size after a sum all-reduce) and by min(1, max_norm / (norm + 1e-6))
+ *   when gnorm_sq (device scalar, sum of squared gradients BEFORE grad_scale) is given; weight decay is Adam's L2 form. */
+int mtt_colsum(const float* x, int64_t ldx, int64_t rows, int32_t cols, int64_t in_group, int64_t src_group, int64_t src_offset,
+               float* out, int32_t accumulate, mtt_stream_t stream);
+int mtt_layernorm_bwd(const float* x, int64_t ldx, const float* dy, int64_t lddy, const float* gamma, float eps, int64_t rows,
+                      int32_t cols, float* dx, int64_t lddx, int32_t accumulate_dx, float* dgamma, float* dbeta,
+                      float* stats_ws, mtt_stream_t stream);
+int mtt_act_split(const float* pre, int64_t ld, int64_t rows, int32_t cols, int32_t act, void* out_hi, void* out_lo,
+                  int64_t ldo, mtt_stream_t stream);
+int mtt_act_bwd(const float* pre, int64_t ld, const float* dy, int64_t lddy, int64_t rows, int32_t cols, int32_t act,
+                float* dx, int64_t lddx, mtt_stream_t stream);
+int mtt_axpy_rows(const float* base, int64_t ldb, const float* src, int64_t lds, const float* row_scale, int64_t rows,
+                  int32_t cols, float* dst, int64_t ldd, mtt_stream_t stream);
+int mtt_transpose_planes(const void* in_hi, const void* in_lo, int64_t ld_in, int64_t in_batch_rows, int32_t B, int32_t R,
+                         int32_t C, void* out_hi, void* out_lo, int64_t ld_out, int64_t out_batch_stride,
+                         mtt_stream_t stream);
+int mtt_bn_stats(const float* x, int64_t ldx, int64_t rows, int32_t cols, float* sums, mtt_stream_t stream);
+int mtt_bn_finalize(const float* sums, float count, int32_t cols, float eps, float momentum, float* mean_rstd,
+                    float* running_mean, float* running_var, mtt_stream_t stream);
+int mtt_bn_act(const float* x, int64_t ldx, int64_t rows, int32_t cols, const float* mean_rstd, const float* gamma,
+               const float* beta, int32_t act, float* out_f32, int64_t ldo, void* out_hi, void* out_lo, int64_t ldbf,
+               mtt_stream_t stream);
+int mtt_bn_bwd_reduce(const float* x, int64_t ldx, const float* dy, int64_t lddy, int64_t rows, int32_t cols,
+                      const float* mean_rstd, const float* gamma, const float* beta, int32_t act, float* sums,
+                      mtt_stream_t stream);
+int mtt_bn_bwd_apply(const float* x, int64_t ldx, const float* dy, int64_t lddy, int64_t rows, int32_t cols,
+                     const float* mean_rstd, const float* gamma, const float* beta, int32_t act, const float* sums,
+                     float count, float* dx, int64_t lddx, mtt_stream_t stream);
+int mtt_attn_softmax_bwd(float* S, float* dP, int64_t ld, int32_t BH, int32_t N, float scale, const float* d_raw, int32_t T,
+                         void* ds_hi, void* ds_lo, int64_t ldbf, mtt_stream_t stream);
+int mtt_bilinear_bwd(const float* dy, int64_t lddy, int32_t nchw, int32_t B, int32_t h, int32_t w, int32_t C, int32_t H2,
+                     int32_t W2, float* dx, int64_t lddx, int32_t accumulate, mtt_stream_t stream);
+int mtt_gate_bwd(const float* x, int64_t ldx, int64_t x_group_rows, int64_t x_row_offset, const float* prompt_logits,
+                 const float* chan_logits, int32_t task, int32_t B, int32_t T, int32_t N, int32_t H, int32_t C, int32_t gh,
+                 int32_t gw, int32_t nh, int32_t nw, const float* dys, const float* dyc, int64_t lddy, float* dx,
+                 int64_t lddx, float* d_prompt_logits, float* d_chan_logits, mtt_stream_t stream);
+int mtt_chan_logits_bwd(const float* d_rc, const float* cp, const void* xn_hi, const void* xn_lo, int64_t ldx, int32_t B,
+                        int32_t N, int32_t T, int32_t C, int32_t gh, int32_t gw, int32_t nh, int32_t nw, float* dcp,
+                        float* dxn, int64_t lddx, mtt_stream_t stream);
+int mtt_ctr_bwd(const float* dnew, const float* F, int32_t T, int64_t M, int32_t C, int64_t ld, int32_t rows_per_batch,
+                const float* prompt_logits, int32_t B, int32_t H, int32_t N, const float* w0, const float* b0,
+                const float* w2, float* dw_ws, float* d_prompt_logits, float* dw0, float* db0, float* dw2, float* db2,
+                mtt_stream_t stream);
+int mtt_im2col3x3_t(const float* x, int64_t ldx, int32_t B, int32_t H, int32_t W, int32_t C, void* out_hi, void* out_lo,
+                    int64_t ldo, mtt_stream_t stream);
+int mtt_im2col_patch_t(const float* img, int32_t B, int32_t Cin, int32_t H, int32_t W, int32_t patch, void* out_hi,
+                       void* out_lo, int64_t ldo, mtt_stream_t stream);
+int mtt_sumsq(const float* g, int64_t n, float* out, int32_t accumulate, mtt_stream_t stream);
+int mtt_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+                  float weight_decay, int32_t step, const float* gnorm_sq, float max_norm, float grad_scale,
+                  mtt_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -143,6 +143,30 @@ SYMBOLS = {
     "mtt_swin_chan_up": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp]),
     "mtt_nchw_to_nhwc_split": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _i64, _vp]),
     "mtt_nhwc_to_nchw": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp]),
+    # training step (csrc/train_ops.cu)
+    "mtt_colsum": (C.c_int, [_vp, _i64, _i64, _i32, _i64, _i64, _i64, _vp, _i32, _vp]),
+    "mtt_layernorm_bwd": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _f32, _i64, _i32, _vp, _i64, _i32, _vp, _vp, _vp, _vp]),
+    "mtt_act_split": (C.c_int, [_vp, _i64, _i64, _i32, _i32, _vp, _vp, _i64, _vp]),
+    "mtt_act_bwd": (C.c_int, [_vp, _i64, _vp, _i64, _i64, _i32, _i32, _vp, _i64, _vp]),
+    "mtt_axpy_rows": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _i64, _i32, _vp, _i64, _vp]),
+    "mtt_transpose_planes": (C.c_int, [_vp, _vp, _i64, _i64, _i32, _i32, _i32, _vp, _vp, _i64, _i64, _vp]),
+    "mtt_bn_stats": (C.c_int, [_vp, _i64, _i64, _i32, _vp, _vp]),
+    "mtt_bn_finalize": (C.c_int, [_vp, _f32, _i32, _f32, _f32, _vp, _vp, _vp, _vp]),
+    "mtt_bn_act": (C.c_int, [_vp, _i64, _i64, _i32, _vp, _vp, _vp, _i32, _vp, _i64, _vp, _vp, _i64, _vp]),
+    "mtt_bn_bwd_reduce": (C.c_int, [_vp, _i64, _vp, _i64, _i64, _i32, _vp, _vp, _vp, _i32, _vp, _vp]),
+    "mtt_bn_bwd_apply": (C.c_int, [_vp, _i64, _vp, _i64, _i64, _i32, _vp, _vp, _vp, _i32, _vp, _f32, _vp, _i64, _vp]),
+    "mtt_attn_softmax_bwd": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _f32, _vp, _i32, _vp, _vp, _i64, _vp]),
+    "mtt_bilinear_bwd": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _i64, _i32, _vp]),
+    "mtt_gate_bwd": (C.c_int, [_vp, _i64, _i64, _i64, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32,
+                               _vp, _vp, _i64, _vp, _i64, _vp, _vp, _vp]),
+    "mtt_chan_logits_bwd": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp,
+                                      _i64, _vp]),
+    "mtt_ctr_bwd": (C.c_int, [_vp, _vp, _i32, _i64, _i32, _i64, _i32, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp,
+                              _vp, _vp, _vp, _vp]),
+    "mtt_im2col3x3_t": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _i64, _vp]),
+    "mtt_im2col_patch_t": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _i64, _vp]),
+    "mtt_sumsq": (C.c_int, [_vp, _i64, _vp, _i32, _vp]),
+    "mtt_adam_step": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _f32, _i32, _vp, _f32, _f32, _vp]),
 }
 
 _lib = None

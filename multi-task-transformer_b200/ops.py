@@ -589,3 +589,154 @@ def swin_chan_up(rc_in, w, out, *, BT, Cdim, nwin):
     assert rc_in.is_contiguous() and w.is_contiguous() and out.is_contiguous()
     rc = _L.load().mtt_swin_chan_up(_ptr(rc_in), _ptr(w), BT, Cdim, w.shape[0], nwin, _ptr(out), _stream())
     _L.check(rc, "mtt_swin_chan_up")
+
+
+# ---- training step (csrc/train_ops.cu): fp32 [rows, cols] tensors, last dim contiguous ----------------------------------
+def _ld(t):
+    assert t.dtype == torch.float32 and t.stride(-1) == 1
+    return t.stride(-2) if t.dim() >= 2 else t.shape[-1]
+
+
+def colsum(x, out, accumulate=False, *, rows=None, in_group=0, src_group=0, src_offset=0):
+    """out[c] (+)= sum_r x[row(r), c]; row mapping as split_rows (in_group = 0: the first `rows` rows)."""
+    rows = x.shape[0] if rows is None else rows
+    _L.check(_L.load().mtt_colsum(_ptr(x), _ld(x), rows, x.shape[1], in_group, src_group, src_offset, _ptr(out),
+                                  int(accumulate), _stream()), "mtt_colsum")
+
+
+def layernorm_bwd(x, dy, gamma, eps, dx, dgamma, dbeta, *, accumulate_dx=False):
+    """dx (+)= d LN(x) . dy; dgamma / dbeta are ACCUMULATED (None: skip the parameter gradients)."""
+    rows, cols = x.shape
+    ws = torch.empty(2 * rows, dtype=torch.float32, device=x.device)
+    _L.check(_L.load().mtt_layernorm_bwd(_ptr(x), _ld(x), _ptr(dy), _ld(dy), _ptr(gamma), float(eps), rows, cols, _ptr(dx),
+                                         _ld(dx), int(accumulate_dx), _ptr(dgamma), _ptr(dbeta), _ptr(ws), _stream()),
+             "mtt_layernorm_bwd")
+
+
+def act_split(pre, act, out=None, nsplit=2):
+    rows, cols = pre.shape
+    if out is None:
+        out = Split(rows, cols, pre.device, nsplit, zero=cols % 8 != 0)
+    _L.check(_L.load().mtt_act_split(_ptr(pre), _ld(pre), rows, cols, act, _ptr(out.hi), _ptr(out.lo), out.ld, _stream()),
+             "mtt_act_split")
+    return out
+
+
+def act_bwd(pre, dy, act, dx):
+    rows, cols = pre.shape
+    _L.check(_L.load().mtt_act_bwd(_ptr(pre), _ld(pre), _ptr(dy), _ld(dy), rows, cols, act, _ptr(dx), _ld(dx), _stream()),
+             "mtt_act_bwd")
+
+
+def axpy_rows(base, src, row_scale, dst):
+    """dst = base + row_scale[:, None] * src (base / row_scale may be None)."""
+    rows, cols = src.shape
+    _L.check(_L.load().mtt_axpy_rows(_ptr(base), _ld(base) if base is not None else 0, _ptr(src), _ld(src),
+                                     _ptr(row_scale), rows, cols, _ptr(dst), _ld(dst), _stream()), "mtt_axpy_rows")
+
+
+def transpose_planes(a, *, B=1, R=None, Ccols=None, in_batch_rows=None, out=None, side_by_side=False):
+    """Split [B*R(+), C] -> Split: image b (rows b*in_batch_rows ... + R of `a`) transposed to a [C, R] block; blocks are
+    stacked by rows ([B*C, ld >= R]) or, side_by_side, along the columns of one [C, B*R] matrix."""
+    R = a.rows // B if R is None else R
+    Ccols = a.cols if Ccols is None else Ccols
+    in_batch_rows = R if in_batch_rows is None else in_batch_rows
+    if out is None:
+        rows, cols = (Ccols, B * R) if side_by_side else (B * Ccols, R)
+        out = Split(rows, cols, a.hi.device, a.nsplit, zero=cols % 8 != 0)
+    _L.check(_L.load().mtt_transpose_planes(_ptr(a.hi), _ptr(a.lo), a.ld, in_batch_rows, B, R, Ccols, _ptr(out.hi),
+                                            _ptr(out.lo), out.ld, R if side_by_side else 0, _stream()),
+             "mtt_transpose_planes")
+    return out
+
+
+def bn_stats(x, sums):
+    _L.check(_L.load().mtt_bn_stats(_ptr(x), _ld(x), x.shape[0], x.shape[1], _ptr(sums), _stream()), "mtt_bn_stats")
+
+
+def bn_finalize(sums, count, eps, momentum, mean_rstd, running_mean=None, running_var=None):
+    _L.check(_L.load().mtt_bn_finalize(_ptr(sums), float(count), sums.numel() // 2, float(eps), float(momentum),
+                                       _ptr(mean_rstd), _ptr(running_mean), _ptr(running_var), _stream()), "mtt_bn_finalize")
+
+
+def bn_act(x, mean_rstd, gamma, beta, act, *, out_f32=None, out_split=None):
+    rows, cols = x.shape
+    _L.check(_L.load().mtt_bn_act(_ptr(x), _ld(x), rows, cols, _ptr(mean_rstd), _ptr(gamma), _ptr(beta), act,
+                                  _ptr(out_f32), _ld(out_f32) if out_f32 is not None else 0,
+                                  _ptr(out_split.hi) if out_split is not None else None,
+                                  _ptr(out_split.lo) if out_split is not None else None,
+                                  out_split.ld if out_split is not None else 0, _stream()), "mtt_bn_act")
+
+
+def bn_bwd_reduce(x, dy, mean_rstd, gamma, beta, act, sums):
+    rows, cols = x.shape
+    _L.check(_L.load().mtt_bn_bwd_reduce(_ptr(x), _ld(x), _ptr(dy), _ld(dy), rows, cols, _ptr(mean_rstd), _ptr(gamma),
+                                         _ptr(beta), act, _ptr(sums), _stream()), "mtt_bn_bwd_reduce")
+
+
+def bn_bwd_apply(x, dy, mean_rstd, gamma, beta, act, sums, count, dx):
+    rows, cols = x.shape
+    _L.check(_L.load().mtt_bn_bwd_apply(_ptr(x), _ld(x), _ptr(dy), _ld(dy), rows, cols, _ptr(mean_rstd), _ptr(gamma),
+                                        _ptr(beta), act, _ptr(sums), float(count), _ptr(dx), _ld(dx), _stream()),
+             "mtt_bn_bwd_apply")
+
+
+def attn_softmax_bwd(S, dP, *, BH, N, scale, d_raw, T, ds):
+    """S, dP fp32 [BH*N, ld]; P overwrites S, dS overwrites dP and is written to the Split `ds` [BH*N, >= N]."""
+    _L.check(_L.load().mtt_attn_softmax_bwd(_ptr(S), _ptr(dP), _ld(S), BH, N, float(scale), _ptr(d_raw), T, _ptr(ds.hi),
+                                            _ptr(ds.lo), ds.ld, _stream()), "mtt_attn_softmax_bwd")
+
+
+def bilinear_bwd(dy, *, nchw, B, h, w, Cdim, H2, W2, dx, accumulate=False):
+    _L.check(_L.load().mtt_bilinear_bwd(_ptr(dy), 0 if nchw else _ld(dy), int(nchw), B, h, w, Cdim, H2, W2, _ptr(dx),
+                                        _ld(dx), int(accumulate), _stream()), "mtt_bilinear_bwd")
+
+
+def gate_bwd(x, x_group_rows, x_row_offset, prompt_logits, chan_lg, task, dys, dyc, dx, d_prompt_logits, d_chan_lg, *, B,
+             T, N, H, Cdim, gh, gw, nh, nw):
+    _L.check(_L.load().mtt_gate_bwd(_ptr(x), _ld(x), x_group_rows, x_row_offset, _ptr(prompt_logits), _ptr(chan_lg), task,
+                                    B, T, N, H, Cdim, gh, gw, nh, nw, _ptr(dys), _ptr(dyc), _ld(dys), _ptr(dx), _ld(dx),
+                                    _ptr(d_prompt_logits), _ptr(d_chan_lg), _stream()), "mtt_gate_bwd")
+
+
+def chan_logits_bwd(d_rc, cp, xn, dcp, dxn, *, B, N, T, Cdim, gh, gw, nh, nw):
+    _L.check(_L.load().mtt_chan_logits_bwd(_ptr(d_rc), _ptr(cp), _ptr(xn.hi), _ptr(xn.lo), xn.ld, B, N, T, Cdim, gh, gw, nh,
+                                           nw, _ptr(dcp), _ptr(dxn), _ld(dxn), _stream()), "mtt_chan_logits_bwd")
+
+
+def ctr_bwd(dnew, F, prompt_logits, w0, b0, w2, d_prompt_logits, dw0, db0, dw2, db2, *, T, M, Cdim, ld, rows_per_batch, B,
+            H, N):
+    ws = torch.empty(B * T * T, dtype=torch.float32, device=dnew.device)
+    _L.check(_L.load().mtt_ctr_bwd(_ptr(dnew), _ptr(F), T, M, Cdim, ld, rows_per_batch, _ptr(prompt_logits), B, H, N,
+                                   _ptr(w0), _ptr(b0), _ptr(w2), _ptr(ws), _ptr(d_prompt_logits), _ptr(dw0), _ptr(db0),
+                                   _ptr(dw2), _ptr(db2), _stream()), "mtt_ctr_bwd")
+
+
+def im2col3x3_t(x, *, B, H, W, Cdim, nsplit=2):
+    """NHWC fp32 [B*H*W, C] -> Split [C*9, B*H*W]: rows (c, ky, kx)."""
+    P = B * H * W
+    out = Split(Cdim * 9, P, x.device, nsplit, zero=P % 8 != 0)
+    _L.check(_L.load().mtt_im2col3x3_t(_ptr(x), _ld(x), B, H, W, Cdim, _ptr(out.hi), _ptr(out.lo), out.ld, _stream()),
+             "mtt_im2col3x3_t")
+    return out
+
+
+def im2col_patch_t(img, patch, nsplit=2):
+    """NCHW fp32 image -> Split [Cin*patch*patch, B*gh*gw]."""
+    B, Cin, H, W = img.shape
+    cols = B * (H // patch) * (W // patch)
+    out = Split(Cin * patch * patch, cols, img.device, nsplit, zero=cols % 8 != 0)
+    _L.check(_L.load().mtt_im2col_patch_t(_ptr(img), B, Cin, H, W, patch, _ptr(out.hi), _ptr(out.lo), out.ld, _stream()),
+             "mtt_im2col_patch_t")
+    return out
+
+
+def sumsq(g, out, accumulate=False):
+    _L.check(_L.load().mtt_sumsq(_ptr(g), g.numel(), _ptr(out), int(accumulate), _stream()), "mtt_sumsq")
+
+
+def adam_step(p, g, m, v, *, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, step, gnorm_sq=None, max_norm=0.0,
+              grad_scale=1.0):
+    _L.check(_L.load().mtt_adam_step(_ptr(p), _ptr(g), _ptr(m), _ptr(v), p.numel(), float(lr), float(betas[0]),
+                                     float(betas[1]), float(eps), float(weight_decay), int(step), _ptr(gnorm_sq),
+                                     float(max_norm), float(grad_scale), _stream()), "mtt_adam_step")

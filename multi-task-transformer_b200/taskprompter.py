@@ -286,6 +286,7 @@ class TaskPrompter(nn.Module):
         self.embed_dim = self.num_features = embed_dim
         self.num_heads = num_heads
         self.depth = depth
+        self.drop_path_rate = float(drop_path_rate)     # stochastic depth acts in the training step only (train.py)
         self.patch_size = patch_size
         self.in_chans = in_chans
         self.patch_embed = PatchEmbed(img_size, patch_size, in_chans, embed_dim)
@@ -785,7 +786,7 @@ def build_from_config(cfg, nsplit=PARITY, use_graph=True):
         p.dd_label_map_size = tuple(cfg["dd_label_map_size"])
     bb = TaskPrompter(p, cfg["select"], img_size=tuple(cfg["img_size"]), patch_size=cfg["patch"],
                       embed_dim=cfg["C"], depth=cfg["depth"], num_heads=cfg["heads"],
-                      chan_nheads=cfg["chan_nheads"])
+                      chan_nheads=cfg["chan_nheads"], drop_path_rate=cfg.get("drop_path_rate", 0.15))   # common_config.py:22
     head_cls = DEConvHead if cfg.get("head", "conv") == "deconv" else ConvHead       # utils/common_config.py:64-70
     heads = nn.ModuleDict({t: head_cls(cfg["f"], cfg["num_output"][t]) for t in cfg["tasks"]})
     return TaskPrompterWrapper(p, bb, heads, nsplit=nsplit, use_graph=use_graph)
@@ -802,7 +803,8 @@ def accelerate(ref_model, nsplit=PARITY, use_graph=True):
     mine_bb = TaskPrompter(p, list(bb.select_list), img_size=tuple(bb.patch_embed.img_size),
                            patch_size=bb.patch_embed.patch_size[0], embed_dim=bb.embed_dim,
                            depth=len(bb.blocks), num_heads=bb.blocks[0].attn.num_heads,
-                           chan_nheads=bb.blocks[0].attn.chan_nheads)
+                           chan_nheads=bb.blocks[0].attn.chan_nheads,
+                           drop_path_rate=float(getattr(bb.blocks[-1].drop_path, "drop_prob", 0.0) or 0.0))
 
     def mirror(t, hd):   # ConvHead (:688-698) or DEConvHead (:700-715), told apart by the first layer
         if not hasattr(hd, "mt_proj") or not hasattr(hd, "linear_pred"):

@@ -262,6 +262,95 @@ def main_big(only=None):
         print(f"wrote {path} ({os.path.getsize(path) / 1024:.0f} KiB, {time.time() - t0:.0f} s)", flush=True)
 
 
+# ---------------------------------------------------------------------------------------------------------
+# Training step: the unmodified reference model in TRAIN mode (BatchNorm batch statistics, DropPath
+# 0.15) -> the reference criterion -> autograd -> clip_grad_norm_ -> torch.optim.Adam (train_utils.py:34-51 with the
+# yml's optimizer block). The fixture keeps the DropPath masks the reference drew (CPU generator; the product draws
+# them with the same calls on its own device), the train-mode outputs, the losses, every parameter gradient (small
+# models) or its norm / sum plus a few full ones (large models), the BatchNorm running statistics after the forward and
+# the parameters after the optimizer step (same selection).
+TRAIN_JOBS = [("tp_tiny", 21, 2, True), ("tp_tiny1", 22, 3, False), ("tp_cfg4_d4", 23, 2, False)]
+TRAIN_HYPER = dict(lr=2e-5, weight_decay=1e-6, max_norm=10.0)      # configs/pascal/pascal_vitLp16_taskprompter.yml:18-23
+
+
+def train_inputs(cfg, seed, batch):
+    """The synthetic image batch and labels of a training fixture (CPU generator: identical wherever it runs)."""
+    g = torch.Generator().manual_seed(seed + 500)
+    x = torch.randn(batch, 3, *cfg["img_size"], generator=g)
+    return x, synthetic_labels(cfg["tasks"], cfg["num_output"], batch, *cfg["img_size"], g)
+
+
+def make_train(name, seed, batch, full):
+    from oracle import taskprompter_ref as R
+
+    cfg = configs.taskprompter(name)
+    sd = R.init_state_dict(cfg, seed=seed)
+    model = ref_loader.build_taskprompter(cfg)
+    model.load_state_dict(sd, strict=True)
+    model.train()
+    from easydict import EasyDict
+    from utils.common_config import get_criterion
+    tasks = cfg["tasks"]
+    p = EasyDict(TASKS=EasyDict(NAMES=list(tasks)), edge_w=0.95, ignore_index=255, ignore_invalid_area_depth=True,
+                 loss_kwargs=EasyDict(loss_weights={t: LOSS_WEIGHTS[t] for t in tasks}))
+    crit = get_criterion(p)
+    x, lab = train_inputs(cfg, seed, batch)
+    masks, real_rand = [], torch.rand
+
+    def rand(*a, **k):
+        r = real_rand(*a, **k)
+        if tuple(r.shape) == (batch, 1, 1):
+            masks.append(r.clone())
+        return r
+    torch.manual_seed(seed + 900)
+    torch.rand = rand
+    try:
+        out = model(x)
+    finally:
+        torch.rand = real_rand
+    loss = crit(out, lab, tasks=tasks)
+    opt = torch.optim.Adam(model.parameters(), lr=TRAIN_HYPER["lr"], weight_decay=TRAIN_HYPER["weight_decay"])
+    opt.zero_grad()
+    loss["total"].backward()
+    grads = {k: v.grad.detach().clone() for k, v in model.named_parameters()}
+    total_norm = float(torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm=TRAIN_HYPER["max_norm"], norm_type=2))
+    opt.step()
+    after = {k: v.detach().clone() for k, v in model.named_parameters()}
+    few = {
+        "backbone.task_prompts", "backbone.patch_embed.proj.bias", "backbone.blocks.0.attn.qkv.bias",
+        "backbone.blocks.0.norm1.weight", "backbone.blocks.1.mlp.fc1.bias", "backbone.blocks.3.attn.token_trans1.bias",
+        "backbone.blocks.2.attn.token_trans.bias", "backbone.norm.weight", f"heads.{tasks[0]}.linear_pred.weight",
+        f"backbone.ctr_attn_conv.0.{tasks[1]}.0.weight", f"backbone.fea_fuse.1.{tasks[0]}.2.weight",
+        f"backbone.fea_fuse.2.{tasks[1]}.4.weight", f"backbone.fea_decode_spa.3.{tasks[2 % len(tasks)]}.0.weight",
+        f"heads.{tasks[-1]}.mt_proj.1.bias"} & set(grads)
+    keep = set(grads) if full else few
+    bn = {k: v.detach().clone() for k, v in model.state_dict().items() if "running_" in k}
+    lat = lambda v: v[..., ::8, ::8].clone() if not full else v.detach().clone()
+    # the input and the labels are regenerated by the test from the seed (train_inputs below); only checksums travel
+    sha = lambda t_: hashlib.sha256(t_.contiguous().numpy().tobytes()).hexdigest()
+    return {"family": "train", "cfg": name, "seed": seed, "batch": batch, "x_sha256": sha(x),
+            "labels_sha256": {k: sha(v) for k, v in lab.items()}, "masks": masks, "hyper": TRAIN_HYPER,
+            "out": {k: lat(v.detach()) for k, v in out.items()}, "out_stride": 1 if full else 8,
+            "losses": {k: float(v.detach()) for k, v in loss.items()}, "total_norm": total_norm,
+            "grad_norm": {k: float(v.norm()) for k, v in grads.items()},
+            "grad_sum": {k: float(v.double().sum()) for k, v in grads.items()},
+            "grad_full": {k: grads[k] for k in sorted(keep)}, "param_after": {k: after[k] for k in sorted(few) if after[k].numel() <= 70000},
+            "running": bn if full else {k: v for k, v in bn.items() if ".2.running" in k and ".0." in k},
+            "sd_sha256": sd_checksum(sd), "weights": LOSS_WEIGHTS, "torch": torch.__version__,
+            "made_by": "oracle/make_golden.py train: the unmodified reference model in train mode, the reference criterion, "
+                       "torch autograd, clip_grad_norm_ and torch.optim.Adam"}
+
+
+def main_train(only=None):
+    for name, seed, batch, full in TRAIN_JOBS:
+        if only and name not in only:
+            continue
+        fx = make_train(name, seed, batch, full)
+        path = os.path.join(GOLD, f"train_{name}.pt")
+        torch.save(fx, path)
+        print(f"wrote {path} ({os.path.getsize(path) / 1024:.0f} KiB)", flush=True)
+
+
 def main():
     if not ref_loader.available():
         raise SystemExit("reference not found (set MTT_REFERENCE or mount /root/reference)")
@@ -296,5 +385,9 @@ if __name__ == "__main__":
         if not ref_loader.available():
             raise SystemExit("reference not found (set MTT_REFERENCE or mount /root/reference)")
         main_big(set(sys.argv[2:]) or None)
+    elif len(sys.argv) > 1 and sys.argv[1] == "train":  # python -m oracle.make_golden train [config ...]
+        if not ref_loader.available():
+            raise SystemExit("reference not found (set MTT_REFERENCE or mount /root/reference)")
+        main_train(set(sys.argv[2:]) or None)
     else:
         main()

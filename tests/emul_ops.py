@@ -427,9 +427,198 @@ def install(mp):
         r = rc.reshape(BT, Cdim, nwin)
         out.copy_(torch.einsum("oc,bcw->bow", w, r).reshape(out.shape))
 
+    # ---- training step (csrc/train_ops.cu). The adjoints are taken by torch autograd of the forward emulations, so they
+    # ---- are independent of the hand-derived formulas in the kernels.
+    def _actf(z, act):
+        return F.gelu(z) if act == 1 else (F.relu(z) if act == 2 else z)
+
+    def colsum(x, out, accumulate=False, *, rows=None, in_group=0, src_group=0, src_offset=0):
+        rows = x.shape[0] if rows is None else rows
+        s_ = x[_rows(rows, in_group, src_group, src_offset)].sum(0)
+        out[:x.shape[1]] = out[:x.shape[1]] + s_ if accumulate else s_
+
+    def layernorm_bwd(x, dy, gamma, eps, dx, dgamma, dbeta, *, accumulate_dx=False):
+        xr = x.detach().clone().requires_grad_(True)
+        g = gamma.detach().clone().requires_grad_(True)
+        b = torch.zeros_like(gamma, requires_grad=True)
+        F.layer_norm(xr, (x.shape[1],), g, b, eps).backward(dy[:, :x.shape[1]].contiguous())
+        dx[:, :x.shape[1]] = dx[:, :x.shape[1]] + xr.grad if accumulate_dx else xr.grad
+        if dgamma is not None:
+            dgamma += g.grad
+            dbeta += b.grad
+
+    def act_split(pre, act, out=None, nsplit=2):
+        rows, cols = pre.shape
+        if out is None:
+            out = ops.Split(rows, cols, pre.device, nsplit, zero=True)
+        _wsplit(out, _actf(pre, act))
+        return out
+
+    def act_bwd(pre, dy, act, dx):
+        z = pre.detach().clone().requires_grad_(True)
+        _actf(z, act).backward(dy[:, :pre.shape[1]].clone())
+        dx[:, :pre.shape[1]] = z.grad
+
+    def axpy_rows(base, src, row_scale, dst):
+        v = src if row_scale is None else src * row_scale[:, None]
+        dst.copy_(v if base is None else base + v)
+
+    def transpose_planes(a, *, B=1, R=None, Ccols=None, in_batch_rows=None, out=None, side_by_side=False):
+        R = a.rows // B if R is None else R
+        Ccols = a.cols if Ccols is None else Ccols
+        in_batch_rows = R if in_batch_rows is None else in_batch_rows
+        if out is None:
+            rows, cols = (Ccols, B * R) if side_by_side else (B * Ccols, R)
+            out = ops.Split(rows, cols, a.hi.device, a.nsplit, zero=True)
+        for b in range(B):
+            blk = a.buf[:, b * in_batch_rows:b * in_batch_rows + R, :Ccols].transpose(1, 2)
+            if side_by_side:
+                out.buf[:, :Ccols, b * R:(b + 1) * R] = blk
+            else:
+                out.buf[:, b * Ccols:(b + 1) * Ccols, :R] = blk
+        return out
+
+    def bn_stats(x, sums):
+        C_ = x.shape[1]
+        sums[:C_] = x.sum(0)
+        sums[C_:2 * C_] = (x * x).sum(0)
+
+    def bn_finalize(sums, count, eps, momentum, mean_rstd, running_mean=None, running_var=None):
+        C_ = sums.numel() // 2
+        mean = sums[:C_] / count
+        var = (sums[C_:] / count - mean * mean).clamp(min=0)
+        mean_rstd[:C_] = mean
+        mean_rstd[C_:] = 1.0 / torch.sqrt(var + eps)
+        if running_mean is not None:
+            unb = var * count / (count - 1) if count > 1 else var
+            running_mean.mul_(1 - momentum).add_(momentum * mean)
+            running_var.mul_(1 - momentum).add_(momentum * unb)
+
+    def _bn_y(x, mean_rstd, gamma, beta, act):
+        C_ = x.shape[1]
+        return _actf((x - mean_rstd[:C_]) * mean_rstd[C_:] * gamma + beta, act)
+
+    def bn_act(x, mean_rstd, gamma, beta, act, *, out_f32=None, out_split=None):
+        y = _bn_y(x, mean_rstd, gamma, beta, act)
+        if out_f32 is not None:
+            out_f32[:, :x.shape[1]] = y
+        if out_split is not None:
+            _wsplit(out_split, y)
+
+    def _bn_dz(x, dy, mean_rstd, gamma, beta, act):
+        C_ = x.shape[1]
+        xh = (x - mean_rstd[:C_]) * mean_rstd[C_:]
+        z = (xh * gamma + beta).detach().clone().requires_grad_(True)
+        _actf(z, act).backward(dy[:, :C_].clone())
+        return z.grad, xh
+
+    def bn_bwd_reduce(x, dy, mean_rstd, gamma, beta, act, sums):
+        C_ = x.shape[1]
+        dz, xh = _bn_dz(x, dy, mean_rstd, gamma, beta, act)
+        sums[:C_] = dz.sum(0)
+        sums[C_:] = (dz * xh).sum(0)
+
+    def bn_bwd_apply(x, dy, mean_rstd, gamma, beta, act, sums, count, dx):
+        C_ = x.shape[1]
+        dz, xh = _bn_dz(x, dy, mean_rstd, gamma, beta, act)
+        dx[:, :C_] = gamma * mean_rstd[C_:] * (dz - sums[:C_] / count - xh * sums[C_:] / count)
+
+    def attn_softmax_bwd(S, dP, *, BH, N, scale, d_raw, T, ds):
+        s_ = S[:, :N].reshape(BH, N, N).detach().clone().requires_grad_(True)
+        P = (s_ * scale).softmax(-1)
+        P.backward(dP[:, :N].reshape(BH, N, N).clone())
+        g = s_.grad
+        if d_raw is not None:
+            g[:, :T, :] += d_raw.reshape(BH, T, N)
+        S[:, :N] = P.detach().reshape(BH * N, N)
+        dP[:, :N] = g.reshape(BH * N, N)
+        _wsplit(ds, g.reshape(BH * N, N))
+
+    def bilinear_bwd(dy, *, nchw, B, h, w, Cdim, H2, W2, dx, accumulate=False):
+        g = dy.reshape(B, Cdim, H2, W2) if nchw else dy[:, :Cdim].reshape(B, H2, W2, Cdim).permute(0, 3, 1, 2)
+        x_ = torch.zeros(B, Cdim, h, w, requires_grad=True)
+        F.interpolate(x_, size=(H2, W2), mode="bilinear", align_corners=False).backward(g.contiguous())
+        gx = x_.grad.permute(0, 2, 3, 1).reshape(B * h * w, Cdim)
+        dx[:, :Cdim] = dx[:, :Cdim] + gx if accumulate else gx
+
+    def gate_bwd(x, x_group_rows, x_row_offset, prompt_logits, chan_lg, task, dys, dyc, dx, d_prompt_logits, d_chan_lg, *,
+                 B, T, N, H, Cdim, gh, gw, nh, nw):
+        P = gh * gw
+        xs = x.reshape(B, x_group_rows, -1)[:, x_row_offset:x_row_offset + P, :Cdim].detach().clone().requires_grad_(True)
+        pl = prompt_logits.detach().clone().requires_grad_(True)
+        cl = chan_lg.detach().clone().requires_grad_(True)
+        g = pl[:, :, task, T:].permute(0, 2, 1).repeat_interleave(Cdim // H, dim=2)
+        gc = cl[:, task].reshape(B, Cdim, nh, 1, nw, 1).expand(B, Cdim, nh, gh // nh, nw, gw // nw).reshape(B, Cdim, P)
+        ys = (xs * (1 + g)).reshape(B * P, Cdim)
+        yc = (xs * (1 + gc.permute(0, 2, 1))).reshape(B * P, Cdim)
+        ((ys * dys[:, :Cdim]).sum() + (yc * dyc[:, :Cdim]).sum()).backward()
+        dx.reshape(B, x_group_rows, -1)[:, x_row_offset:x_row_offset + P, :Cdim] += xs.grad
+        d_prompt_logits += pl.grad
+        d_chan_lg += cl.grad
+
+    def chan_logits_bwd(d_rc, cp, xn, dcp, dxn, *, B, N, T, Cdim, gh, gw, nh, nw):
+        x_ = _rsplit(xn, Cdim).reshape(B, N, Cdim)[:, T:].detach().clone().requires_grad_(True)
+        c_ = cp.detach().clone().requires_grad_(True)
+        wh, ww = gh // nh, gw // nw
+        rc = torch.einsum("btihjw,bihjwc->btcij", c_.reshape(B, T, nh, wh, nw, ww), x_.reshape(B, nh, wh, nw, ww, Cdim))
+        rc.backward(d_rc.reshape(rc.shape))
+        dcp.copy_(c_.grad.reshape(dcp.shape))
+        dxn.reshape(B, N, -1)[:, T:, :Cdim] += x_.grad
+
+    def ctr_bwd(dnew, Fm, prompt_logits, w0, b0, w2, d_prompt_logits, dw0, db0, dw2, db2, *, T, M, Cdim, ld, rows_per_batch,
+                B, H, N):
+        pl = prompt_logits.detach().clone().requires_grad_(True)
+        ps = [t_.detach().clone().requires_grad_(True) for t_ in (w0, b0, w2, torch.zeros(T))]
+        a = pl[:, :, :, :T]
+        ws_ = []
+        for t in range(T):
+            hdn = F.gelu(torch.einsum("oh,bhj->boj", ps[0][t], a[:, :, t, :]) + ps[1][t][None, :, None])
+            ws_.append(torch.einsum("o,boj->bj", ps[2][t], hdn) + ps[3][t])
+        w = torch.stack(ws_, 1)                                              # [B,T,T]
+        bidx = torch.arange(M) // rows_per_batch
+        new = torch.einsum("mtj,jmc->tmc", w[bidx], Fm.reshape(T, M, -1)[:, :, :Cdim])
+        (new * dnew.reshape(T, M, -1)[:, :, :Cdim]).sum().backward()
+        d_prompt_logits += pl.grad
+        dw0 += ps[0].grad
+        db0 += ps[1].grad
+        dw2 += ps[2].grad
+        db2 += ps[3].grad
+
+    def im2col3x3_t(x, *, B, H, W, Cdim, nsplit=2):
+        P = B * H * W
+        out = ops.Split(Cdim * 9, P, x.device, nsplit, zero=True)
+        img = x[:, :Cdim].reshape(B, H, W, Cdim).permute(0, 3, 1, 2)
+        cols = F.unfold(img, 3, padding=1)                                   # [B, C*9, H*W], rows (c, ky, kx)
+        _wsplit(out, cols.permute(1, 0, 2).reshape(Cdim * 9, P))
+        return out
+
+    def im2col_patch_t(img, patch, nsplit=2):
+        B, Cin, H, W = img.shape
+        cols = F.unfold(img, patch, stride=patch)                            # [B, Cin*p*p, P]
+        n = B * cols.shape[2]
+        out = ops.Split(Cin * patch * patch, n, img.device, nsplit, zero=True)
+        _wsplit(out, cols.permute(1, 0, 2).reshape(-1, n))
+        return out
+
+    def sumsq(g, out, accumulate=False):
+        v = (g.double() ** 2).sum().float()
+        out.copy_(out + v if accumulate else v)
+
+    def adam_step(p, g, m, v, *, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, step, gnorm_sq=None, max_norm=0.0,
+                  grad_scale=1.0):
+        clip = grad_scale
+        if gnorm_sq is not None:
+            c = max_norm / (float(gnorm_sq.sqrt()) * grad_scale + 1e-6)
+            clip *= min(c, 1.0)
+        gi = g * clip + weight_decay * p
+        m.mul_(betas[0]).add_((1 - betas[0]) * gi)
+        v.mul_(betas[1]).add_((1 - betas[1]) * gi * gi)
+        bc1, bc2 = 1 - betas[0] ** step, 1 - betas[1] ** step
+        p.sub_(lr / bc1 * m / (v.sqrt() / math.sqrt(bc2) + eps))
+
     for name, fn in list(locals().items()):
         if callable(fn) and not name.startswith("_") and name not in ("mp",):
-            mp.setattr(ops, name, fn, raising=False)
+            mp.setattr(ops, name, torch.enable_grad()(fn), raising=False)
     mp.setattr(ops._L, "check", lambda rc, what: None)
 
     class _FakeLib:
