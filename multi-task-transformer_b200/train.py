@@ -77,6 +77,7 @@ class TrainStep:
             raise NotImplementedError("mtt_b200 TrainStep: head dim must be 64 (mtt_attention)")
         self.select = list(bb.select_list)
         self.e, self.f = bb.p.embed_dim, bb.p.final_embed_dim
+        self.f_ld = round_up(self.f, 8)              # row stride of the per-task feature maps (pad columns stay zero)
         self.nh = self.nw = int(round(math.sqrt(bb.chan_nheads)))
         self.use_ctr = bool(bb.p.use_ctr)
         self.target = model.target_size
@@ -255,7 +256,7 @@ class TrainStep:
                  res_row_mod=P, out_f32=X, regroup=(P, N, T))
         ops.broadcast_rows(self.P_(bbp + "task_prompts"), X, B, N)
         scales = self._drop_scales(B, iter(drop_rand) if drop_rand is not None else None)
-        acc = _z(T, B * P, self.f, device=dev)
+        acc = _z(T, B * P, self.f_ld, device=dev)
         logits = rc = None
         for i in range(self.depth):
             sel = (i + 1) in self.select
@@ -327,7 +328,7 @@ class TrainStep:
         Mp = B * P
         W = self.W
         bbp = "backbone."
-        F_ = _e(T, Mp, f, device=dev)
+        F_ = _z(T, Mp, self.f_ld, device=dev)
         per = []
         for ti, t in enumerate(self.tasks):
             ys, yc = Split(Mp, C, dev, ns), Split(Mp, C, dev, ns)
@@ -348,7 +349,7 @@ class TrainStep:
                      conv=(B, self.gh, self.gw, 3, 1))
             y2s = Split(Mp, f, dev, ns, zero=f % 8 != 0)
             mr, count = self._bn_fwd(y1, pf + "2", ACT_GELU, y2s)
-            ops.gemm(y2s, W[pf + "4.weight"], bias=self.P_(pf + "4.bias"), out_f32=F_[ti])
+            ops.gemm(y2s, W[pf + "4.weight"], bias=self.P_(pf + "4.bias"), out_f32=F_[ti][:, :f])
             per.append(dict(ys=ys, yc=yc, s_s=s_s, c_s=c_s, y0=y0, y1=y1, y2s=y2s, mr=mr, count=count))
         ctrw = None
         if self.use_ctr:
@@ -360,10 +361,10 @@ class TrainStep:
             c2b = torch.stack([self.P_(p + "2.bias").reshape(()) for p in pc])
             ctrw = _e(B, T, T, device=dev)
             ops.ctr_weights(logits, c0, c0b, c2, c2b, ctrw, B=B, H=H, T=T, N=N)
-            ops.ctr_mix(F_, ctrw, acc, T=T, M=Mp, Cdim=f, ld=f, rows_per_batch=P, accumulate=True)
+            ops.ctr_mix(F_, ctrw, acc, T=T, M=Mp, Cdim=self.f_ld, ld=self.f_ld, rows_per_batch=P, accumulate=True)
             per_ctr = (c0, c0b, c2)
         else:
-            ops.axpy_rows(acc.view(T * Mp, f), F_.view(T * Mp, f), None, acc.view(T * Mp, f))
+            ops.axpy_rows(acc.view(T * Mp, -1), F_.view(T * Mp, -1), None, acc.view(T * Mp, -1))
             per_ctr = None
         self.ctx["levels"].append(dict(il=il, Xsrc=Xsrc, blk=blk, F=F_, per=per, ctrw=ctrw, ctr=per_ctr))
 
@@ -374,7 +375,7 @@ class TrainStep:
         W = self.W
         up = _e(M4, f, device=dev)
         ups = Split(M4, f, dev, ns, zero=f % 8 != 0)
-        ops.bilinear(acc_t, f, B, self.gh, self.gw, f, h4, w4, out_f32=up, out_split=ups)
+        ops.bilinear(acc_t, self.f_ld, B, self.gh, self.gw, f, h4, w4, out_f32=up, out_split=ups)
         ph = f"heads.{t}."
         z = _e(M4, f, device=dev)
         ops.gemm(ups, W[ph + "mt_proj.0.weight"], N=f, K=f, bias=self.P_(ph + "mt_proj.0.bias"), out_f32=z,
@@ -395,9 +396,10 @@ class TrainStep:
         B = cx["B"]
         T, P, N, C, f = self.T, self.P, self.N, self.C, self.f
         M, Mp = B * N, B * P
-        dacc = _e(T, Mp, f, device=dev)
+        dacc = _z(T, Mp, self.f_ld, device=dev)
         for ti in reversed(range(T)):
-            self._head_bwd(ti, self.tasks[ti], grad_out[self.tasks[ti]].to(dev, torch.float32).contiguous(), dacc[ti], B)
+            self._head_bwd(ti, self.tasks[ti], grad_out[self.tasks[ti]].to(dev, torch.float32).contiguous(),
+                           dacc[ti][:, :f], B)
         self._bucket_ready("heads.")
         dX = _z(M, C, device=dev)
         # last level reads LN_final(x)
@@ -474,7 +476,7 @@ class TrainStep:
         if self.use_ctr:
             c0, c0b, c2 = lv["ctr"]
             g0, g0b, g2, g2b = torch.zeros_like(c0), torch.zeros_like(c0b), torch.zeros_like(c2), _z(T, device=dev)
-            ops.ctr_bwd(dacc, lv["F"], logits, c0, c0b, c2, d_logits, g0, g0b, g2, g2b, T=T, M=Mp, Cdim=f, ld=f,
+            ops.ctr_bwd(dacc, lv["F"], logits, c0, c0b, c2, d_logits, g0, g0b, g2, g2b, T=T, M=Mp, Cdim=f, ld=self.f_ld,
                         rows_per_batch=P, B=B, H=H, N=N)
             for ti, t in enumerate(self.tasks):
                 p = f"{bbp}ctr_attn_conv.{il}.{t}."
@@ -482,15 +484,15 @@ class TrainStep:
                                   (p + "2.bias", g2b[ti:ti + 1])):
                     gv = self.G_(name).view(1, -1)
                     ops.axpy_rows(gv, src.reshape(1, -1), None, gv)
-            dF = _e(T, Mp, f, device=dev)
-            ops.ctr_mix(dacc, lv["ctrw"].transpose(1, 2).contiguous(), dF, T=T, M=Mp, Cdim=f, ld=f, rows_per_batch=P,
-                        accumulate=False)
+            dF = _e(T, Mp, self.f_ld, device=dev)
+            ops.ctr_mix(dacc, lv["ctrw"].transpose(1, 2).contiguous(), dF, T=T, M=Mp, Cdim=self.f_ld, ld=self.f_ld,
+                        rows_per_batch=P, accumulate=False)
         else:
             dF = dacc
         for ti, t in enumerate(self.tasks):
             pc = lv["per"][ti]
             pf = f"{bbp}fea_fuse.{il}.{t}."
-            dy2 = self._lin_bwd(dF[ti], pc["y2s"], pf + "4.weight", M=Mp, N=f, K=f)
+            dy2 = self._lin_bwd(dF[ti][:, :f], pc["y2s"], pf + "4.weight", M=Mp, N=f, K=f)
             dy1 = self._bn_bwd(pc["y1"], dy2, pf + "2", ACT_GELU, pc["mr"], pc["count"])
             dy0 = self._conv3_bwd(dy1, pc["y0"], pf + "1", B, self.gh, self.gw, f, f)
             dy0s = self._S(dy0)

@@ -39,8 +39,42 @@ def _conv(x, sd, name, padding=0):
     return F.conv2d(x, sd[name + ".weight"].to(x.dtype), None if b is None else b.to(x.dtype), padding=padding)
 
 
+_TRAIN = None      # train_mode(): {"rand": iterator of uniform [B,1,1] draws or None} while restating model.train()
+
+
+class train_mode:
+    """Context: the restatement follows model.train() -- BatchNorm2d normalises with batch statistics (running statistics
+    are not tracked here) and DropPath (timm 0.5.4 drop_path, taskprompter.py:265,273-277; rates linspace(0, rate, depth),
+    :320) scales each residual branch by floor(keep + u) / keep per sample, u drawn from `rand` (an iterable of [B,1,1]
+    tensors replaying the reference's torch.rand calls) or from torch.rand."""
+
+    def __init__(self, drop_path_rate=0.15, rand=None):
+        self.state = {"rate": drop_path_rate, "rand": iter(rand) if rand is not None else None}
+
+    def __enter__(self):
+        global _TRAIN
+        _TRAIN = self.state
+
+    def __exit__(self, *a):
+        global _TRAIN
+        _TRAIN = None
+
+
+def _drop_path(x, idx, depth):
+    if _TRAIN is None:
+        return x
+    dp = float(torch.linspace(0, _TRAIN["rate"], depth)[idx])
+    if dp == 0.0:
+        return x
+    keep = 1 - dp
+    u = next(_TRAIN["rand"]).to(x) if _TRAIN["rand"] is not None else torch.rand((x.shape[0], 1, 1), dtype=x.dtype, device=x.device)
+    return x / keep * torch.floor(keep + u)
+
+
 def _bn(x, sd, name, eps=1e-5):
-    # eval-mode BatchNorm2d: running statistics (taskprompter.py:362 BatchNorm2d, :692)
+    # eval-mode BatchNorm2d: running statistics (taskprompter.py:362 BatchNorm2d, :692); batch statistics under train_mode
+    if _TRAIN is not None:
+        return F.batch_norm(x, None, None, sd[name + ".weight"].to(x.dtype), sd[name + ".bias"].to(x.dtype), True, 0.0, eps)
     return F.batch_norm(x, sd[name + ".running_mean"].to(x.dtype), sd[name + ".running_var"].to(x.dtype),
                         sd[name + ".weight"].to(x.dtype), sd[name + ".bias"].to(x.dtype), False, 0.0, eps)
 
@@ -49,7 +83,7 @@ def grid_of(cfg):
     return cfg["img_size"][0] // cfg["patch"], cfg["img_size"][1] // cfg["patch"]
 
 
-def block_forward(sd, pre, cfg, x, prompts, want_logits):
+def block_forward(sd, pre, cfg, x, prompts, want_logits, idx=0):
     """One TaskPrompter block (taskprompter.py:270-279 with Attention :195-254).
 
     x [B,P,C] patches, prompts [B,T,C]. Returns x, prompts and, if want_logits, the two tensors
@@ -82,10 +116,11 @@ def block_forward(sd, pre, cfg, x, prompts, want_logits):
         cpw = cp.reshape(B, T, nh, wh, nw, ww)
         xw = xn.reshape(B, nh, wh, nw, ww, C)
         Rc = torch.einsum("btihjw,bihjwc->btcij", cpw, xw)
-    x = x + o_x                                     # :273 (drop_path = identity in eval)
-    x = x + _mlp(sd, pre, _ln(x, sd, pre + "norm2"))        # :274
-    prompts = prompts + o_p                         # :276
-    prompts = prompts + _mlp(sd, pre, _ln(prompts, sd, pre + "norm2"))  # :277
+    D = cfg["depth"]
+    x = x + _drop_path(o_x, idx, D)                 # :273 (drop_path = identity in eval)
+    x = x + _drop_path(_mlp(sd, pre, _ln(x, sd, pre + "norm2")), idx, D)        # :274
+    prompts = prompts + _drop_path(o_p, idx, D)     # :276
+    prompts = prompts + _drop_path(_mlp(sd, pre, _ln(prompts, sd, pre + "norm2")), idx, D)  # :277
     return x, prompts, R_prompt, Rc
 
 
@@ -146,7 +181,7 @@ def backbone_forward(sd, cfg, img, taps=None):
     R_prompt = Rc = None
     for idx in range(cfg["depth"]):
         want = (idx + 1 in select) or (idx == cfg["depth"] - 1)
-        x, prompts, R_prompt_i, Rc_i = block_forward(sd, f"backbone.blocks.{idx}.", cfg, x, prompts, want)
+        x, prompts, R_prompt_i, Rc_i = block_forward(sd, f"backbone.blocks.{idx}.", cfg, x, prompts, want, idx)
         if want:
             R_prompt, Rc = R_prompt_i, Rc_i
         if taps is not None:

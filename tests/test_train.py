@@ -53,8 +53,9 @@ def _check_grads(fx, ts, tol):
         else:
             err = abs(g.norm().item() - want) / max(want, floor)
         errs.append((err, k))
-        # a scalar parameter (the bias of ctr_attn_conv's last 1x1 conv) is ONE sum of cancelling terms: 5x the tolerance
-        if not err < (5 * tol if g.numel() == 1 else tol):
+        # the few parameters of ctr_attn_conv (H*H + 2H + 1 values per task and level) are sums of cancelling terms over the
+        # whole feature map: 5x the tolerance
+        if not err < (5 * tol if ".ctr_attn_conv." in k else tol):
             bad.append((k, err))
     if os.environ.get("MTT_TRAIN_TEST_VERBOSE"):
         print("worst gradient errors:", [(f"{e:.2e}", k) for e, k in sorted(errs, reverse=True)[:10]])
@@ -102,3 +103,37 @@ def test_training_step_matches_reference_autograd_cpu_emulation(monkeypatch, nam
         # Adam's first step is lr * sign(g) wherever |g| >> eps: compare the steps, not the parameters
         close = (step_got - step_ref).abs() <= 1e-3 * step_ref.abs() + 2e-7
         assert close.float().mean() > 0.98, (k, close.float().mean().item())
+
+
+def _oracle_grads(fx, cfg, device, x, grad_out=None, labels=None):
+    """Train-mode restatement (oracle.taskprompter_ref.train_mode) + torch autograd: outputs, losses, parameter gradients."""
+    sd = {k: v.to(device) for k, v in TPR.init_state_dict(cfg, seed=fx["seed"]).items()}
+    params = {k: v.requires_grad_(True) for k, v in sd.items() if v.is_floating_point() and "running_" not in k}
+    sd.update(params)
+    with TPR.train_mode(0.15, rand=[m.to(device) for m in fx["masks"]]):
+        out = TPR.forward(sd, cfg, x.to(device))
+    loss = None
+    if grad_out is None:
+        loss = loss_ref.multi_task_loss(out, {k: v.to(device) for k, v in labels.items()}, cfg["tasks"], fx["weights"])
+        loss["total"].backward()
+    else:
+        torch.autograd.backward([out[t] for t in cfg["tasks"]], [grad_out[t] for t in cfg["tasks"]])
+    return out, loss, {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in params.items()}
+
+
+def test_train_mode_restatement_is_pinned_to_the_reference():
+    """oracle.taskprompter_ref under train_mode (batch-statistics BatchNorm, DropPath with the reference's draws) + torch
+    autograd reproduces the unmodified reference's train-mode outputs, losses and parameter gradients (tp_tiny fixture): the
+    restatement can then serve as the checker of the CUDA reverse pass at sizes no fixture can carry."""
+    fx = _fixture("tp_tiny")
+    cfg = configs.taskprompter("tp_tiny")
+    out, loss, grads = _oracle_grads(fx, cfg, torch.device("cpu"), fx["x"], labels=fx["labels"])
+    for t in cfg["tasks"]:
+        assert (out[t].detach() - fx["out"][t]).abs().max() <= 1e-5 * fx["out"][t].abs().max()
+    for k, want in fx["losses"].items():
+        assert abs(float(loss[k].detach()) - want) <= 1e-5 * max(1.0, abs(want))
+    floor = 1e-4 * fx["total_norm"]
+    for k, ref in fx["grad_full"].items():
+        err = (grads[k] - ref).norm().item() / max(ref.norm().item(), floor)
+        # fp32 summation order alone moves the cancelling sums of ctr_attn_conv by 1e-4 (two fp32 evaluations of the same graph)
+        assert err < (5e-4 if ".ctr_attn_conv." in k else 2e-5), (k, err)
