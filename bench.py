@@ -487,6 +487,272 @@ def run_ours(args):
     D.teardown(world)
 
 
+# ------------------------------------------------------------------------------------------------
+# --train: the training step (TaskPrompter/utils/train_utils.py:34-51). A separate line from the
+# contract's inference metric: same JSON shape, metric "train images/sec".
+def _train_criterion(cfg):
+    from mtt_b200 import losses
+    w = {"semseg": 1.0, "human_parts": 2.0, "sal": 5.0, "edge": 50.0, "normals": 10.0, "depth": 1.0}   # the ymls
+    p = dict(TASKS=dict(NAMES=list(cfg["tasks"])), edge_w=0.95, ignore_index=255, ignore_invalid_area_depth=True,
+             loss_kwargs=dict(loss_weights={t: w[t] for t in cfg["tasks"]}))
+    return losses.get_criterion(p), w
+
+
+def _train_labels(cfg, B, g):
+    """Synthetic labels of the shapes the reference's datasets produce (ignore regions included)."""
+    H, W = cfg["img_size"]
+    lab = {}
+    hole = lambda frac: torch.rand(B, 1, H, W, generator=g) < frac
+    for t in cfg["tasks"]:
+        if t in ("semseg", "human_parts"):
+            y = torch.randint(0, cfg["num_output"][t], (B, 1, H, W), generator=g).float()
+            y[hole(0.1)] = 255.0
+        elif t in ("sal", "edge"):
+            y = (torch.rand(B, 1, H, W, generator=g) < (0.3 if t == "sal" else 0.1)).float()
+            y[hole(0.05)] = 255.0
+        elif t == "normals":
+            y = torch.nn.functional.normalize(torch.randn(B, 3, H, W, generator=g), dim=1)
+            y = torch.where(hole(0.1).expand(-1, 3, -1, -1), torch.full_like(y, 255.0), y)
+        else:
+            y = torch.rand(B, 1, H, W, generator=g) * 9 + 0.5
+            y[hole(0.15)] = -1.0
+        lab[t] = y
+    return lab
+
+
+def train_eager_baseline(cfg_name, batch, dev, labels, steps=3, warmup=1):
+    """The training step of the reference algorithm in eager PyTorch on the same GPU: train-mode restatement (oracle,
+    pinned to the reference by tests/test_train.py) -> criterion restatement -> autograd -> clip_grad_norm_ -> Adam."""
+    import contextlib
+
+    from oracle import loss_ref
+    from oracle import taskprompter_ref as TPR
+    cfg, _, _ = family(cfg_name)
+    sd = {k: v.to(dev) for k, v in TPR.init_state_dict(cfg, seed=0).items()}
+    params = [v.requires_grad_(True) for k, v in sd.items() if v.is_floating_point() and "running_" not in k]
+    opt = torch.optim.Adam(params, lr=2e-5, weight_decay=1e-6)
+    x = torch.randn(batch, 3, *cfg["img_size"], device=dev)
+    w = _train_criterion(cfg)[1]
+    res = {"kind": "port", "batch": batch, "steps": steps, "warmup": warmup, "unit": "images/s",
+           "what": "eager PyTorch training step of the reference algorithm on this GPU (cuBLAS / cuDNN + autograd + Adam)"}
+    old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+
+    def one(ctx):
+        with ctx, TPR.train_mode(0.15):
+            out = TPR.forward(sd, cfg, x)
+        loss = loss_ref.multi_task_loss({t: o.float() for t, o in out.items()}, labels, cfg["tasks"], w)
+        opt.zero_grad()
+        loss["total"].backward()
+        torch.nn.utils.clip_grad_norm_(params, 10.0)
+        opt.step()
+
+    def timed(ctx):
+        for _ in range(warmup):
+            one(ctx)
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(steps):
+            one(ctx)
+        e.record()
+        torch.cuda.synchronize()
+        return batch * steps / (s.elapsed_time(e) * 1e-3)
+
+    try:
+        torch.backends.cuda.matmul.allow_tf32 = False
+        torch.backends.cudnn.allow_tf32 = False
+        res["fp32"] = timed(contextlib.nullcontext())
+        torch.backends.cuda.matmul.allow_tf32 = True
+        torch.backends.cudnn.allow_tf32 = True
+        res["tf32"] = timed(contextlib.nullcontext())
+        res["bf16_autocast"] = timed(torch.autocast("cuda", dtype=torch.bfloat16))
+    except Exception as ex:
+        res["error"] = f"{type(ex).__name__}: {ex}"[:200]
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+    return res
+
+
+def run_train(args):
+    import mtt_b200  # noqa: F401
+    from mtt_b200 import dist as D
+    from mtt_b200 import ops
+    from mtt_b200.train import TrainStep
+
+    rank, world, local = D.setup("nccl")
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    cfg, M, _ = family(args.config)
+    nsplit = 2 if args.mode == "parity" else 1
+    torch.manual_seed(0)
+    with torch.device(dev):
+        model = M.build_from_config(cfg, nsplit=nsplit, use_graph=False)
+    pg = torch.distributed.group.WORLD if world > 1 else None
+    ts = TrainStep(model, nsplit=nsplit, process_group=pg)
+    crit, _ = _train_criterion(cfg)
+    B = args.batch
+    g = torch.Generator().manual_seed(1 + rank)
+    n_rot = 2
+    host_x = [torch.randn(B, 3, *cfg["img_size"], generator=g).pin_memory() for _ in range(n_rot)]
+    host_y = [{t: v.pin_memory() for t, v in _train_labels(cfg, B, g).items()} for _ in range(n_rot)]
+    in_bytes = host_x[0].numel() * 4 + sum(v.numel() * 4 for v in host_y[0].values())
+
+    def step(i):
+        x = host_x[i % n_rot].to(dev, non_blocking=True)
+        y = {t: v.to(dev, non_blocking=True) for t, v in host_y[i % n_rot].items()}
+        with torch.no_grad():
+            return ts.step(x, y, crit)
+
+    for i in range(args.warmup):
+        loss = step(i)
+    torch.cuda.synchronize()
+    ops.launch_count(reset=True)
+    step(0)
+    torch.cuda.synchronize()
+    launches = ops.launch_count()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    regions, last = [], None
+    for _ in range(max(1, args.repeats)):
+        D.barrier(world)
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for i in range(args.steps):
+            loss = step(i)
+            last = float(loss["total"])                   # the step's result is read back (D2H) every step
+        e.record()
+        torch.cuda.synchronize()
+        D.barrier(world)
+        regions.append(D.max_over_ranks(s.elapsed_time(e), world, dev))
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = sorted(regions)[len(regions) // 2]
+    value = world * B * args.steps / (ms_total * 1e-3)
+    # phases of one step (events) and the tensor-core share (library profiling hook)
+    x = host_x[0].to(dev)
+    y = {t: v.to(dev) for t, v in host_y[0].items()}
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+    with torch.no_grad():
+        ts.zero_grad()
+        ev[0].record()
+        out = ts.forward(x)
+        ev[1].record()
+        leaves = {t: o.requires_grad_(True) for t, o in out.items()}
+        with torch.enable_grad():
+            ls = crit(leaves, y, tasks=cfg["tasks"])
+            gr = torch.autograd.grad(ls["total"], [leaves[t] for t in cfg["tasks"]])
+        ev[2].record()
+        ts.backward(dict(zip(cfg["tasks"], gr)))
+        ev[3].record()
+        ts.optimizer_step()
+        ev[4].record()
+    torch.cuda.synchronize()
+    phases = {k: ev[i].elapsed_time(ev[i + 1]) for i, k in enumerate(("forward_ms", "loss_ms", "backward_ms", "optimizer_ms"))}
+    ops.profile_begin()
+    step(0)
+    recs = ops.profile_end(max_recs=16384)
+    tc_ms = sum(r[4] for r in recs)
+    tc_flops = sum(r[5] for r in recs)
+    if rank != 0:
+        D.teardown(world)
+        return
+    peaks, peak_src = load_peaks()
+    peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
+    line = {
+        "metric": "train images/sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16x3 (split-bf16 operands, fp32 accumulate)" if nsplit == 2 else "bf16",
+        "data": "synthetic",
+        "config": {"workload": f"{WORKLOAD[args.config]}, {args.config}, TRAINING step (train-mode forward, criterion, "
+                               f"backward, gradient all-reduce, clip_grad_norm_ 10, Adam), bs {B}/GPU, DropPath 0.15",
+                   "global_batch": world * B,
+                   "parallelism": f"dp{world}: SyncBatchNorm statistics + bucketed NCCL all-reduce of the gradient arena "
+                                  "overlapped with the reverse pass" if world > 1 else "dp1",
+                   "precision_mode": args.mode, "l2": "activations and weights of a step are >> 126 MB L2"},
+        "clocks": clocks, "last_loss": last,
+        "repeats": {"n": len(regions), "steps_each": args.steps, "reported": "median region",
+                    "images_per_s": [world * B * args.steps / (r * 1e-3) for r in regions]},
+        "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": 4,
+                "note": "the timed step IS end to end: pinned-host images + labels -> H2D -> TrainStep.step -> loss scalar D2H"},
+        "gpu_launches": int(launches * args.steps), "launches_per_step": int(launches),
+        "phases": phases,
+        "roofline": {"bound": "tensor", "achieved": tc_flops / (tc_ms * 1e-3) / 1e12 if tc_ms else None, "peak": peak,
+                     "unit": "TFLOP/s", "frac": (tc_flops / (tc_ms * 1e-3) / 1e12 / peak) if tc_ms else None, "traffic": None,
+                     "peak_source": peak_src, "kernel": "mtt_gemm / mtt_gemm_grouped / mtt_attention launches of one step",
+                     "launches": len(recs), "tensor_ms_per_step": tc_ms, "algorithmic_gflop_per_step": tc_flops / 1e9,
+                     "share_of_step": tc_ms / (ms_total / args.steps)},
+    }
+    if world == 1 and not args.no_gpu_eager:
+        del ts, model
+        torch.cuda.empty_cache()
+        ge = train_eager_baseline(args.config, B, dev, y)
+        for k in ("fp32", "tf32", "bf16_autocast"):
+            if k in ge:
+                ge[f"ours_over_{k}"] = value / ge[k]
+        line["gpu_eager_baseline"] = ge
+    print(json.dumps(line), file=_OUT, flush=True)
+    D.teardown(world)
+
+
+def run_reference_train(args):
+    """--impl reference --train: the reference's training step on the host cores (rank 0 only): the unmodified reference
+    model + criterion where importable, else the train-mode restatement; autograd, clip_grad_norm_, Adam."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import loss_ref, ref_loader
+    from oracle import taskprompter_ref as TPR
+    threads = pick_cpu_threads()
+    torch.set_num_threads(threads)
+    cfg, _, _ = family(args.config)
+    B = args.batch
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(B, 3, *cfg["img_size"], generator=g)
+    y = _train_labels(cfg, B, g)
+    w = {"semseg": 1.0, "human_parts": 2.0, "sal": 5.0, "edge": 50.0, "normals": 10.0, "depth": 1.0}
+    sd = TPR.init_state_dict(cfg, seed=0)
+    if ref_loader.available():
+        kind = "reference"
+        model = ref_loader.build_taskprompter(cfg).train()
+        model.load_state_dict(sd, strict=True)
+        params = list(model.parameters())
+        fwd = lambda: model(x)
+    else:
+        kind = "port"
+        params = [v.requires_grad_(True) for k, v in sd.items() if v.is_floating_point() and "running_" not in k]
+
+        def fwd():
+            with TPR.train_mode(0.15):
+                return TPR.forward(sd, cfg, x)
+    opt = torch.optim.Adam(params, lr=2e-5, weight_decay=1e-6)
+
+    def one():
+        loss = loss_ref.multi_task_loss(fwd(), y, cfg["tasks"], w)
+        opt.zero_grad()
+        loss["total"].backward()
+        torch.nn.utils.clip_grad_norm_(params, 10.0)
+        opt.step()
+    for _ in range(args.warmup):
+        one()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        one()
+    sec = (time.perf_counter() - t0) / max(args.steps, 1)
+    rate = B / sec
+    sample = (f"training step on batch {B} of {args.config} (fp32 eager CPU, "
+              f"{'the unmodified reference model' if kind == 'reference' else 'train-mode restatement (oracle/)'}, criterion "
+              f"restatement, autograd, clip, Adam), {args.warmup} warm-up + {args.steps} timed steps, {threads} host threads")
+    line = {"impl": "reference", "metric": "train images/sec", "value": rate, "unit": "images/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{WORKLOAD[args.config]}, {args.config}, TRAINING step, bs {B}", "global_batch": B,
+                       "parallelism": "one CPU process (rank 0)", "precision_mode": "fp32 eager CPU"},
+            "cpu_baseline": {"value": rate, "unit": "images/s", "cores": threads, "kind": kind, "sample": sample},
+            "e2e": {"value": rate, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), file=_OUT, flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -497,6 +763,7 @@ def main():
     ap.add_argument("--config", default="tp_cfg4")
     ap.add_argument("--batch", type=int, default=0, help="images per GPU per step (default: the config's)")
     ap.add_argument("--repeats", type=int, default=5, help="timed regions of --steps steps; the median is reported")
+    ap.add_argument("--train", action="store_true", help="time the TRAINING step (TaskPrompter ViT configs) instead of the forward")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-eager", action="store_true")
     args = ap.parse_args()
@@ -515,8 +782,12 @@ def main():
     sys.stdout.flush()
     _OUT = os.fdopen(os.dup(1), "w")
     os.dup2(2, 1)
+    if args.train and family(args.config)[2] != "oracle.taskprompter_ref":
+        ap.error("--train covers the ViT TaskPrompter configurations (tp_*)")
     if args.impl == "reference":
-        run_reference(args)
+        (run_reference_train if args.train else run_reference)(args)
+    elif args.train:
+        run_train(args)
     else:
         run_ours(args)
 

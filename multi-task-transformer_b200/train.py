@@ -645,9 +645,9 @@ class TrainStep:
         if not names:
             return
         self._done.update(names)
-        lo = min(self.grads.offsets[n][0] for n in names)
-        hi = max(self.grads.offsets[n][0] + round_up(max(self.grads.offsets[n][1], 1), 64) for n in names)
-        self._pending.append((lo, hi))
+        for n in names:                                  # per-parameter ranges; _flush merges the adjacent ones
+            o, cnt, _ = self.grads.offsets[n]
+            self._pending.append((o, o + round_up(max(cnt, 1), 64)))
         # merge into buckets of >= bucket_elems contiguous elements; flush when big enough or at the end
         if prefix is not None and sum(h - l for l, h in self._pending) < self.bucket_elems:
             return
