@@ -492,9 +492,11 @@ int mtt_nhwc_to_nchw(const float* in, int64_t ld_in, int32_t B, int32_t C, int32
  *   running statistics updated like nn.BatchNorm2d (momentum, unbiased running_var), then y = act(xhat*gamma + beta) as
  *   fp32 and / or split planes. mtt_bn_bwd_reduce: sums = (sum dz, sum dz*xhat), dz = dy * act'(z) (= dbeta, dgamma; all-reduce
  *   for SyncBatchNorm); mtt_bn_bwd_apply: dx = gamma*rstd*(dz - sums[0]/count - xhat*sums[1]/count).
- * mtt_attn_softmax_bwd: per (batch*head) rows of raw scores S [BH, N, ld] and dP [BH, N, ld]: P = softmax(scale*S)
- *   overwrites S, dS = scale*P*(dP - sum_j P dP) (+ d_raw [BH, T, N] on the first T rows: the gradient of the exported
- *   prompt logits, TP taskprompter.py:204) overwrites dP and is also written as split rows.
+ * mtt_attn_softmax_bwd: per (batch*head) rows of raw scores S [BH, N, ld] and dP [BH, N, ld] (fp32, read only):
+ *   P = softmax(scale*S) recomputed, dS = scale*P*(dP - sum_j P dP) (+ d_raw [BH, T, N] on the first T rows: the gradient of
+ *   the exported prompt logits, TP taskprompter.py:204). Outputs, all split planes with row stride ldbf: dS row-major
+ *   [BH*N queries, N] and (optional, NULL to skip) P^T and dS^T key-major [BH*N keys, N queries] -- the A operands of
+ *   dQ = dS k, dV = P^T dO and dK = dS^T q.
  * mtt_bilinear_bwd: adjoint of mtt_bilinear (align_corners = False): dy NHWC (nchw = 0) or NCHW [B,C,H2,W2] (nchw = 1,
  *   lddy unused) -> dx NHWC [B,h,w,C] (+)=.
  * mtt_gate_bwd: adjoint of mtt_gate_split for one task: dx (+)=, d_prompt_logits [B,H,T,N] (+)= at column T + pixel,
@@ -534,8 +536,9 @@ int mtt_bn_bwd_reduce(const float* x, int64_t ldx, const float* dy, int64_t lddy
 int mtt_bn_bwd_apply(const float* x, int64_t ldx, const float* dy, int64_t lddy, int64_t rows, int32_t cols,
                      const float* mean_rstd, const float* gamma, const float* beta, int32_t act, const float* sums,
                      float count, float* dx, int64_t lddx, mtt_stream_t stream);
-int mtt_attn_softmax_bwd(float* S, float* dP, int64_t ld, int32_t BH, int32_t N, float scale, const float* d_raw, int32_t T,
-                         void* ds_hi, void* ds_lo, int64_t ldbf, mtt_stream_t stream);
+int mtt_attn_softmax_bwd(const float* S, const float* dP, int64_t ld, int32_t BH, int32_t N, float scale, const float* d_raw,
+                         int32_t T, void* ds_hi, void* ds_lo, void* pt_hi, void* pt_lo, void* dst_hi, void* dst_lo, int64_t ldbf,
+                         mtt_stream_t stream);
 int mtt_bilinear_bwd(const float* dy, int64_t lddy, int32_t nchw, int32_t B, int32_t h, int32_t w, int32_t C, int32_t H2,
                      int32_t W2, float* dx, int64_t lddx, int32_t accumulate, mtt_stream_t stream);
 int mtt_gate_bwd(const float* x, int64_t ldx, int64_t x_group_rows, int64_t x_row_offset, const float* prompt_logits,

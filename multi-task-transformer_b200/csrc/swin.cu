@@ -201,22 +201,38 @@ swin_logits_kernel(const float* __restrict__ raw, WinGeom g, int heads, float* _
   }
 }
 
-// ---- [B, L, C] fp32 -> split [B*C, ld >= L] (the A operand of chan_kv, TP:379) ----------------------------------------
-__global__ void __launch_bounds__(1024)
+// ---- [B, L, C] fp32 -> split [B*C, ld >= L] (the A operand of chan_kv, TP:379; dY^T / P^T / dS^T of the training step) --
+// Tile = 64 rows (L) x 32 columns (C): 128-byte row reads, and every output row (one column of the input) is written as 64
+// consecutive bf16 = 128 bytes (one bf16x2 per lane).
+__global__ void __launch_bounds__(256)
 transpose_split_kernel(const float* __restrict__ in, long long ld_in, int L, int C, __nv_bfloat16* __restrict__ hi,
                        __nv_bfloat16* __restrict__ lo, long long ld) {
-  __shared__ float tile[32][33];
+  __shared__ float tile[64][33];
   const int b = blockIdx.z;
-  const int l0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
-  const int tx = threadIdx.x, ty = threadIdx.y;
-  if (l0 + ty < L && c0 + tx < C) tile[ty][tx] = in[((long long)b * L + l0 + ty) * ld_in + c0 + tx];
+  const int l0 = blockIdx.x * 64, c0 = blockIdx.y * 32;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float* src = in + (long long)b * L * ld_in;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int l = l0 + warp * 8 + k, c = c0 + lane;
+    tile[warp * 8 + k][lane] = (l < L && c < C) ? src[(long long)l * ld_in + c] : 0.f;
+  }
   __syncthreads();
-  if (c0 + ty < C && l0 + tx < L) {
-    __nv_bfloat16 h, l;
-    split_bf16(tile[tx][ty], h, l);
-    const long long o = ((long long)b * C + c0 + ty) * ld + l0 + tx;
-    hi[o] = h;
-    if (lo) lo[o] = l;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int c = c0 + warp * 4 + k;
+    const int l = l0 + 2 * lane;
+    if (c >= C || l >= L) continue;
+    uint32_t hh, ll;
+    split_pack2(tile[2 * lane][warp * 4 + k], tile[2 * lane + 1][warp * 4 + k], hh, ll);
+    const long long o = ((long long)b * C + c) * ld + l;
+    if (l + 1 < L) {
+      *reinterpret_cast<uint32_t*>(hi + o) = hh;
+      if (lo) *reinterpret_cast<uint32_t*>(lo + o) = ll;
+    } else {
+      hi[o] = __ushort_as_bfloat16((unsigned short)(hh & 0xFFFF));
+      if (lo) lo[o] = __ushort_as_bfloat16((unsigned short)(ll & 0xFFFF));
+    }
   }
 }
 
@@ -474,9 +490,11 @@ int mtt_transpose_split(const float* in, int64_t ld_in, int32_t B, int32_t L, in
                         int64_t ld_out, mtt_stream_t stream) {
   if (!in || !out_hi || B <= 0 || L <= 0 || C <= 0 || ld_out < L)
     return set_error(MTT_ERR_BAD_SHAPE, "mtt_transpose_split: bad arguments");
-  dim3 grid((L + 31) / 32, (C + 31) / 32, B);
-  transpose_split_kernel<<<grid, dim3(32, 32), 0, STREAM>>>(in, ld_in, L, C, static_cast<__nv_bfloat16*>(out_hi),
-                                                           static_cast<__nv_bfloat16*>(out_lo), ld_out);
+  if (ld_out % 2 || (reinterpret_cast<uintptr_t>(out_hi) & 3) || (reinterpret_cast<uintptr_t>(out_lo) & 3))
+    return set_error(MTT_ERR_MISALIGNED, "mtt_transpose_split: output planes must be 4-byte aligned with an even ld");
+  dim3 grid((L + 63) / 64, (C + 31) / 32, B);
+  transpose_split_kernel<<<grid, 256, 0, STREAM>>>(in, ld_in, L, C, static_cast<__nv_bfloat16*>(out_hi),
+                                                  static_cast<__nv_bfloat16*>(out_lo), ld_out);
   return check_launch("mtt_transpose_split");
 }
 

@@ -191,23 +191,50 @@ axpy_rows_kernel(const float* __restrict__ base, long long ldb, const float* __r
 }
 
 // ---- bf16 plane transpose [B][R][C] -> [B][C][ld_out >= R] -------------------------------------------------------------
+// 64 x 64 tiles, bf16x2 loads along C and bf16x2 stores along R (128-byte rows both ways); blockIdx.z = (plane, image).
 __global__ void __launch_bounds__(256)
-transpose_planes_kernel(const __nv_bfloat16* __restrict__ in, long long ld_in, long long in_batch, int R, int C,
-                        __nv_bfloat16* __restrict__ out, long long ld_out, long long out_batch) {
-  __shared__ __nv_bfloat16 tile[32][34];
-  const int b = blockIdx.z;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const __nv_bfloat16* ib = in + (long long)b * in_batch;
-  __nv_bfloat16* ob = out + (long long)b * out_batch;
-  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
-  for (int k = ty; k < 32; k += 8) {
-    const int r = r0 + k, c = c0 + tx;
-    tile[k][tx] = (r < R && c < C) ? ib[(long long)r * ld_in + c] : __float2bfloat16(0.f);
+transpose_planes_kernel(const __nv_bfloat16* __restrict__ in_hi, const __nv_bfloat16* __restrict__ in_lo, long long ld_in,
+                        long long in_batch, int R, int C, __nv_bfloat16* __restrict__ out_hi,
+                        __nv_bfloat16* __restrict__ out_lo, long long ld_out, long long out_batch, int B) {
+  __shared__ unsigned short tile[64][66];
+  const int plane = blockIdx.z / B, b = blockIdx.z % B;
+  const unsigned short* ib = reinterpret_cast<const unsigned short*>(plane ? in_lo : in_hi) + (long long)b * in_batch;
+  unsigned short* ob = reinterpret_cast<unsigned short*>(plane ? out_lo : out_hi) + (long long)b * out_batch;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int r0 = blockIdx.y * 64, c0 = blockIdx.x * 64;
+  const bool vec_in = ((ld_in & 1) == 0) && ((reinterpret_cast<uintptr_t>(ib) & 3) == 0);
+  const bool vec_out = ((ld_out & 1) == 0) && ((reinterpret_cast<uintptr_t>(ob) & 3) == 0);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int r = r0 + warp * 8 + k, c = c0 + 2 * lane;
+    unsigned short v0 = 0, v1 = 0;
+    if (r < R && c < C) {
+      const unsigned short* p = ib + (long long)r * ld_in + c;
+      if (vec_in && c + 1 < C) {
+        const uint32_t u = *reinterpret_cast<const uint32_t*>(p);
+        v0 = (unsigned short)(u & 0xFFFF);
+        v1 = (unsigned short)(u >> 16);
+      } else {
+        v0 = p[0];
+        if (c + 1 < C) v1 = p[1];
+      }
+    }
+    tile[warp * 8 + k][2 * lane] = v0;
+    tile[warp * 8 + k][2 * lane + 1] = v1;
   }
   __syncthreads();
-  for (int k = ty; k < 32; k += 8) {
-    const int c = c0 + k, r = r0 + tx;
-    if (c < C && r < R) ob[(long long)c * ld_out + r] = tile[tx][k];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int c = c0 + warp * 8 + k, r = r0 + 2 * lane;
+    if (c >= C || r >= R) continue;
+    const unsigned short v0 = tile[2 * lane][warp * 8 + k], v1 = tile[2 * lane + 1][warp * 8 + k];
+    unsigned short* p = ob + (long long)c * ld_out + r;
+    if (vec_out && r + 1 < R) {
+      *reinterpret_cast<uint32_t*>(p) = (uint32_t)v0 | ((uint32_t)v1 << 16);
+    } else {
+      p[0] = v0;
+      if (r + 1 < R) p[1] = v1;
+    }
   }
 }
 
@@ -267,42 +294,113 @@ bn_bwd_apply_kernel(const float* __restrict__ x, long long ldx, const float* __r
 }
 
 // ---- attention backward: softmax ---------------------------------------------------------------------------------------
-// One warp per query row of one (batch, head): P = softmax(scale * S) recomputed from the raw scores S, then
-// dS = scale * P * (dP - sum_j P dP) + d_raw for the first T rows (the prompt rows whose raw q.k are an output of the
-// block, taskprompter.py:204). P overwrites S and dS overwrites dP (fp32); dS is also written as split rows.
+// P = softmax(scale * S) recomputed from the raw scores S, dS = scale * P * (dP - sum_j P dP) + d_raw on the first T rows (the
+// prompt rows whose raw q.k are an output of the block, taskprompter.py:204). One block per (64 query rows, batch*head):
+// phase 1 = per-row statistics (warp per row), phase 2 = 64 x 64 tiles: dS is written row-major (the A operand of dQ = dS k)
+// and, through a shared-memory transpose, P^T and dS^T key-major (the A operands of dV = P^T dO and dK = dS^T q) -- all as
+// split planes; nothing of size N^2 is written in fp32.
 __global__ void __launch_bounds__(256)
-attn_softmax_bwd_kernel(float* __restrict__ S, float* __restrict__ dP, long long ld, int BH, int N, float scale,
+attn_softmax_bwd_kernel(const float* __restrict__ S, const float* __restrict__ dP, long long ld, int N, float scale,
                         const float* __restrict__ d_raw, int T, __nv_bfloat16* __restrict__ ds_hi,
-                        __nv_bfloat16* __restrict__ ds_lo, long long ldbf) {
-  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);   // bh * N + i
-  if (row >= (long long)BH * N) return;
-  const int lane = threadIdx.x & 31;
-  const int i = (int)(row % N);
-  const long long bh = row / N;
-  float* s = S + row * ld;
-  float* g = dP + row * ld;
-  float m = -INFINITY;
-  for (int j = lane; j < N; j += 32) m = fmaxf(m, s[j]);
-  m = wmax(m) * scale;
-  float l = 0.f;
-  for (int j = lane; j < N; j += 32) l += __expf(s[j] * scale - m);
-  const float inv = 1.f / wsum(l);
-  float dot = 0.f;
-  for (int j = lane; j < N; j += 32) {
-    const float p = __expf(s[j] * scale - m) * inv;
-    s[j] = p;
-    dot += p * g[j];
+                        __nv_bfloat16* __restrict__ ds_lo, __nv_bfloat16* __restrict__ pt_hi, __nv_bfloat16* __restrict__ pt_lo,
+                        __nv_bfloat16* __restrict__ dst_hi, __nv_bfloat16* __restrict__ dst_lo, long long ldbf) {
+  __shared__ float stat[64][3];
+  __shared__ float tp[64][65], td[64][65];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long bh = blockIdx.y;
+  const int q0 = blockIdx.x * 64;
+  const float* Sb = S + bh * N * ld;
+  const float* Gb = dP + bh * N * ld;
+  for (int k = 0; k < 8; ++k) {
+    const int q = q0 + warp * 8 + k;
+    if (q >= N) break;
+    const float* s = Sb + (long long)q * ld;
+    const float* g = Gb + (long long)q * ld;
+    float m = -INFINITY;
+    for (int j = lane; j < N; j += 32) m = fmaxf(m, s[j]);
+    m = wmax(m) * scale;
+    float l = 0.f;
+    for (int j = lane; j < N; j += 32) l += __expf(s[j] * scale - m);
+    const float inv = 1.f / wsum(l);
+    float dot = 0.f;
+    for (int j = lane; j < N; j += 32) dot += __expf(s[j] * scale - m) * inv * g[j];
+    dot = wsum(dot);
+    if (lane == 0) {
+      stat[warp * 8 + k][0] = m;
+      stat[warp * 8 + k][1] = inv;
+      stat[warp * 8 + k][2] = dot;
+    }
   }
-  dot = wsum(dot);
-  const float* dr = (d_raw && i < T) ? d_raw + (bh * T + i) * (long long)N : nullptr;
-  for (int j = lane; j < N; j += 32) {
-    float v = scale * s[j] * (g[j] - dot);
-    if (dr) v += dr[j];
-    g[j] = v;
-    __nv_bfloat16 h, lo;
-    split_bf16(v, h, lo);
-    ds_hi[row * ldbf + j] = h;
-    if (ds_lo) ds_lo[row * ldbf + j] = lo;
+  __syncthreads();
+  for (int k0 = 0; k0 < N; k0 += 64) {
+    const int kk = k0 + 2 * lane;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int ql = warp * 8 + k, q = q0 + ql;
+      float p0 = 0.f, p1 = 0.f, d0 = 0.f, d1 = 0.f;
+      if (q < N && kk < N) {
+        const float m = stat[ql][0], inv = stat[ql][1], dot = stat[ql][2];
+        const bool two = kk + 1 < N;
+        const float2 sv = two ? *reinterpret_cast<const float2*>(Sb + (long long)q * ld + kk)
+                              : make_float2(Sb[(long long)q * ld + kk], 0.f);
+        const float2 gv = two ? *reinterpret_cast<const float2*>(Gb + (long long)q * ld + kk)
+                              : make_float2(Gb[(long long)q * ld + kk], 0.f);
+        p0 = __expf(sv.x * scale - m) * inv;
+        d0 = scale * p0 * (gv.x - dot);
+        if (two) {
+          p1 = __expf(sv.y * scale - m) * inv;
+          d1 = scale * p1 * (gv.y - dot);
+        }
+        if (d_raw && q < T) {
+          const float* dr = d_raw + (bh * T + q) * (long long)N + kk;
+          d0 += dr[0];
+          if (two) d1 += dr[1];
+        }
+        uint32_t hh, ll;
+        split_pack2(d0, d1, hh, ll);
+        const long long o = (bh * N + q) * ldbf + kk;
+        if (two) {
+          *reinterpret_cast<uint32_t*>(ds_hi + o) = hh;
+          if (ds_lo) *reinterpret_cast<uint32_t*>(ds_lo + o) = ll;
+        } else {
+          ds_hi[o] = __ushort_as_bfloat16((unsigned short)(hh & 0xFFFF));
+          if (ds_lo) ds_lo[o] = __ushort_as_bfloat16((unsigned short)(ll & 0xFFFF));
+        }
+      }
+      tp[ql][2 * lane] = p0;
+      tp[ql][2 * lane + 1] = p1;
+      td[ql][2 * lane] = d0;
+      td[ql][2 * lane + 1] = d1;
+    }
+    __syncthreads();
+    if (pt_hi) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int kl = warp * 8 + k, key = k0 + kl;
+        const int q = q0 + 2 * lane;
+        if (key >= N || q >= N) continue;
+        const bool two = q + 1 < N;
+        const long long o = (bh * N + key) * ldbf + q;
+        uint32_t hh, ll;
+        split_pack2(tp[2 * lane][kl], tp[2 * lane + 1][kl], hh, ll);
+        if (two) {
+          *reinterpret_cast<uint32_t*>(pt_hi + o) = hh;
+          if (pt_lo) *reinterpret_cast<uint32_t*>(pt_lo + o) = ll;
+        } else {
+          pt_hi[o] = __ushort_as_bfloat16((unsigned short)(hh & 0xFFFF));
+          if (pt_lo) pt_lo[o] = __ushort_as_bfloat16((unsigned short)(ll & 0xFFFF));
+        }
+        split_pack2(td[2 * lane][kl], td[2 * lane + 1][kl], hh, ll);
+        if (two) {
+          *reinterpret_cast<uint32_t*>(dst_hi + o) = hh;
+          if (dst_lo) *reinterpret_cast<uint32_t*>(dst_lo + o) = ll;
+        } else {
+          dst_hi[o] = __ushort_as_bfloat16((unsigned short)(hh & 0xFFFF));
+          if (dst_lo) dst_lo[o] = __ushort_as_bfloat16((unsigned short)(ll & 0xFFFF));
+        }
+      }
+    }
+    __syncthreads();
   }
 }
 
@@ -663,16 +761,14 @@ extern "C" int mtt_transpose_planes(const void* in_hi, const void* in_lo, int64_
                                     int64_t out_batch_stride, mtt_stream_t stream) {
   if (!in_hi || !out_hi || B <= 0 || R <= 0 || C <= 0 || ld_out < R)
     return set_error(MTT_ERR_BAD_SHAPE, "mtt_transpose_planes: bad arguments");
-  const dim3 grid((C + 31) / 32, (R + 31) / 32, B);
+  const int planes = (in_lo && out_lo) ? 2 : 1;
+  const dim3 grid((C + 63) / 64, (R + 63) / 64, B * planes);
   const long long ib = in_batch_rows * ld_in, ob = out_batch_stride > 0 ? out_batch_stride : (long long)C * ld_out;
-  transpose_planes_kernel<<<grid, 256, 0, ST>>>(static_cast<const __nv_bfloat16*>(in_hi), ld_in, ib, R, C,
-                                               static_cast<__nv_bfloat16*>(out_hi), ld_out, ob);
+  transpose_planes_kernel<<<grid, 256, 0, ST>>>(static_cast<const __nv_bfloat16*>(in_hi),
+                                               static_cast<const __nv_bfloat16*>(in_lo), ld_in, ib, R, C,
+                                               static_cast<__nv_bfloat16*>(out_hi), static_cast<__nv_bfloat16*>(out_lo),
+                                               ld_out, ob, B);
   count_launch();
-  if (in_lo && out_lo) {
-    transpose_planes_kernel<<<grid, 256, 0, ST>>>(static_cast<const __nv_bfloat16*>(in_lo), ld_in, ib, R, C,
-                                                 static_cast<__nv_bfloat16*>(out_lo), ld_out, ob);
-    count_launch();
-  }
   return check_launch("mtt_transpose_planes");
 }
 
@@ -724,13 +820,17 @@ extern "C" int mtt_bn_bwd_apply(const float* x, int64_t ldx, const float* dy, in
   return check_launch("mtt_bn_bwd_apply");
 }
 
-extern "C" int mtt_attn_softmax_bwd(float* S, float* dP, int64_t ld, int32_t BH, int32_t N, float scale,
-                                    const float* d_raw, int32_t T, void* ds_hi, void* ds_lo, int64_t ldbf,
-                                    mtt_stream_t stream) {
-  if (!S || !dP || !ds_hi || BH <= 0 || N <= 0 || ld < N || ldbf < N)
+extern "C" int mtt_attn_softmax_bwd(const float* S, const float* dP, int64_t ld, int32_t BH, int32_t N, float scale,
+                                    const float* d_raw, int32_t T, void* ds_hi, void* ds_lo, void* pt_hi, void* pt_lo,
+                                    void* dst_hi, void* dst_lo, int64_t ldbf, mtt_stream_t stream) {
+  if (!S || !dP || !ds_hi || BH <= 0 || N <= 0 || ld < N || ldbf < N || ld % 2 || ldbf % 2 || (pt_hi && !dst_hi))
     return set_error(MTT_ERR_BAD_SHAPE, "mtt_attn_softmax_bwd: bad arguments");
-  attn_softmax_bwd_kernel<<<row_blocks((long long)BH * N), 256, 0, ST>>>(
-      S, dP, ld, BH, N, scale, d_raw, T, static_cast<__nv_bfloat16*>(ds_hi), static_cast<__nv_bfloat16*>(ds_lo), ldbf);
+  if ((reinterpret_cast<uintptr_t>(S) & 7) || (reinterpret_cast<uintptr_t>(dP) & 7))
+    return set_error(MTT_ERR_MISALIGNED, "mtt_attn_softmax_bwd: S / dP must be 8-byte aligned");
+  attn_softmax_bwd_kernel<<<dim3((N + 63) / 64, BH), 256, 0, ST>>>(
+      S, dP, ld, N, scale, d_raw, T, static_cast<__nv_bfloat16*>(ds_hi), static_cast<__nv_bfloat16*>(ds_lo),
+      static_cast<__nv_bfloat16*>(pt_hi), static_cast<__nv_bfloat16*>(pt_lo), static_cast<__nv_bfloat16*>(dst_hi),
+      static_cast<__nv_bfloat16*>(dst_lo), ldbf);
   count_launch();
   return check_launch("mtt_attn_softmax_bwd");
 }

@@ -616,7 +616,7 @@ def layernorm_bwd(x, dy, gamma, eps, dx, dgamma, dbeta, *, accumulate_dx=False):
 def act_split(pre, act, out=None, nsplit=2):
     rows, cols = pre.shape
     if out is None:
-        out = Split(rows, cols, pre.device, nsplit, zero=cols % 8 != 0)
+        out = Split(rows, cols, pre.device, nsplit)
     _L.check(_L.load().mtt_act_split(_ptr(pre), _ld(pre), rows, cols, act, _ptr(out.hi), _ptr(out.lo), out.ld, _stream()),
              "mtt_act_split")
     return out
@@ -643,7 +643,7 @@ def transpose_planes(a, *, B=1, R=None, Ccols=None, in_batch_rows=None, out=None
     in_batch_rows = R if in_batch_rows is None else in_batch_rows
     if out is None:
         rows, cols = (Ccols, B * R) if side_by_side else (B * Ccols, R)
-        out = Split(rows, cols, a.hi.device, a.nsplit, zero=cols % 8 != 0)
+        out = Split(rows, cols, a.hi.device, a.nsplit)     # pad columns are never read (TMA bounds)
     _L.check(_L.load().mtt_transpose_planes(_ptr(a.hi), _ptr(a.lo), a.ld, in_batch_rows, B, R, Ccols, _ptr(out.hi),
                                             _ptr(out.lo), out.ld, R if side_by_side else 0, _stream()),
              "mtt_transpose_planes")
@@ -681,10 +681,16 @@ def bn_bwd_apply(x, dy, mean_rstd, gamma, beta, act, sums, count, dx):
              "mtt_bn_bwd_apply")
 
 
-def attn_softmax_bwd(S, dP, *, BH, N, scale, d_raw, T, ds):
-    """S, dP fp32 [BH*N, ld]; P overwrites S, dS overwrites dP and is written to the Split `ds` [BH*N, >= N]."""
+def attn_softmax_bwd(S, dP, *, BH, N, scale, d_raw, T, ds, pt=None, dst=None):
+    """S, dP fp32 [BH*N, ld] (read only) -> Splits ds [BH*N queries, >= N], and optionally pt = P^T, dst = dS^T
+    [BH*N keys, >= N queries] (same ld as ds)."""
+    assert (pt is None) == (dst is None) and (pt is None or pt.ld == dst.ld == ds.ld)
     _L.check(_L.load().mtt_attn_softmax_bwd(_ptr(S), _ptr(dP), _ld(S), BH, N, float(scale), _ptr(d_raw), T, _ptr(ds.hi),
-                                            _ptr(ds.lo), ds.ld, _stream()), "mtt_attn_softmax_bwd")
+                                            _ptr(ds.lo), _ptr(pt.hi) if pt is not None else None,
+                                            _ptr(pt.lo) if pt is not None else None,
+                                            _ptr(dst.hi) if dst is not None else None,
+                                            _ptr(dst.lo) if dst is not None else None, ds.ld, _stream()),
+             "mtt_attn_softmax_bwd")
 
 
 def bilinear_bwd(dy, *, nchw, B, h, w, Cdim, H2, W2, dx, accumulate=False):
@@ -715,7 +721,7 @@ def ctr_bwd(dnew, F, prompt_logits, w0, b0, w2, d_prompt_logits, dw0, db0, dw2, 
 def im2col3x3_t(x, *, B, H, W, Cdim, nsplit=2):
     """NHWC fp32 [B*H*W, C] -> Split [C*9, B*H*W]: rows (c, ky, kx)."""
     P = B * H * W
-    out = Split(Cdim * 9, P, x.device, nsplit, zero=P % 8 != 0)
+    out = Split(Cdim * 9, P, x.device, nsplit)
     _L.check(_L.load().mtt_im2col3x3_t(_ptr(x), _ld(x), B, H, W, Cdim, _ptr(out.hi), _ptr(out.lo), out.ld, _stream()),
              "mtt_im2col3x3_t")
     return out
@@ -725,7 +731,7 @@ def im2col_patch_t(img, patch, nsplit=2):
     """NCHW fp32 image -> Split [Cin*patch*patch, B*gh*gw]."""
     B, Cin, H, W = img.shape
     cols = B * (H // patch) * (W // patch)
-    out = Split(Cin * patch * patch, cols, img.device, nsplit, zero=cols % 8 != 0)
+    out = Split(Cin * patch * patch, cols, img.device, nsplit)
     _L.check(_L.load().mtt_im2col_patch_t(_ptr(img), B, Cin, H, W, patch, _ptr(out.hi), _ptr(out.lo), out.ld, _stream()),
              "mtt_im2col_patch_t")
     return out

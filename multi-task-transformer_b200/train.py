@@ -58,7 +58,7 @@ class TrainStep:
     views of `self.grads.flat`."""
 
     def __init__(self, model, *, lr=2e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-6, max_norm=10.0, nsplit=2,
-                 process_group=None, bucket_mb=64):
+                 process_group=None, bucket_mb=64, use_graph=False):
         from .taskprompter import ConvHead, TaskPrompter, TaskPrompterWrapper
         if not isinstance(model, TaskPrompterWrapper) or not isinstance(model.backbone, TaskPrompter):
             raise NotImplementedError("mtt_b200 TrainStep: only the ViT TaskPrompter is covered (SURVEY.md 8f N1)")
@@ -107,6 +107,10 @@ class TrainStep:
         self.bucket_elems = int(bucket_mb * (1 << 20) // 4)
         self._pending = []
         self.ctx = None
+        # use_graph: step() captures forward + criterion + reverse pass (about 5000 launches) into ONE CUDA graph per input
+        # shape and replays it; clip + Adam stay outside (their bias-correction scalars change every step)
+        self.use_graph = bool(use_graph) and self.pg is None and self.dev.type == "cuda"
+        self._graph = None
 
     # ---- small helpers -------------------------------------------------------------------------------------------------
     def P_(self, name):
@@ -167,7 +171,7 @@ class TrainStep:
         """Y [M,N] = A [M,K] W^T + b. dy fp32 [M,N]; a_s Split [M,K]. Accumulates dW, db; returns dA (fp32 [M,K])."""
         wkey = name if wkey is None else wkey
         gW = self.G_(name).reshape(N, -1) if gW is None else gW
-        dyT = Split(N, M, self.dev, self.ns, zero=M % 8 != 0)
+        dyT = Split(N, M, self.dev, self.ns)
         ops.transpose_split(dy, dyT, B=1, L=M, Cdim=N)
         aT = ops.transpose_planes(a_s, R=M, Ccols=K)
         ops.gemm(dyT, aT, M=N, N=K, K=M, residual=gW, out_f32=gW)                       # dW += dY^T A
@@ -222,7 +226,7 @@ class TrainStep:
         ops.bn_act(x, mr, self.P_(prefix + ".weight"), self.P_(prefix + ".bias"), act, out_split=out_split)
         return mr, count
 
-    def _bn_bwd(self, x, dy, prefix, act, mr, count):
+    def _bn_bwd(self, x, dy, prefix, act, mr, count, dx=None):
         C_ = x.shape[1]
         sums = _e(2 * C_, device=self.dev)
         g, b = self.P_(prefix + ".weight"), self.P_(prefix + ".bias")
@@ -232,7 +236,8 @@ class TrainStep:
                       self.G_(prefix + ".weight").view(1, -1))
         if self.pg is not None:
             torch.distributed.all_reduce(sums, group=self.pg)
-        dx = _e(x.shape[0], C_, device=self.dev)
+        if dx is None:
+            dx = _e(x.shape[0], C_, device=self.dev)
         ops.bn_bwd_apply(x, dy, mr, g, b, act, sums, count, dx)
         return dx
 
@@ -271,12 +276,9 @@ class TrainStep:
         ops.layernorm(X, self.P_(bbp + "norm.weight"), self.P_(bbp + "norm.bias"), self.bb.norm.eps, out_f32=xfin)
         cx["final"] = (X, xfin)
         self._level_fwd(3, xfin, logits, rc, acc, B, self.depth - 1)
-        out = {}
         oh, ow = self.target if self.target is not None else img.shape[-2:]
-        for ti, t in enumerate(self.tasks):
-            out[t] = self._head_fwd(ti, t, acc[ti], B, oh, ow)
         cx["out_hw"] = (oh, ow)
-        return out
+        return self._heads_fwd(acc, B, oh, ow)
 
     def _block_fwd(self, i, X, B, want, scales):
         dev, ns = self.dev, self.ns
@@ -295,7 +297,7 @@ class TrainStep:
         o = self._mm(ao, W[b + "attn.proj.weight"], bias=self.P_(b + "attn.proj.bias"))
         # channel-prompt path on the prompt rows (taskprompter.py:217-250)
         cp = _e(B * T, P, device=dev)
-        cps = Split(B * T, P, dev, ns, zero=P % 8 != 0)
+        cps = Split(B * T, P, dev, ns)
         bstep = max(1, 128 // T)
         for b0 in range(0, B, bstep):
             nb = min(bstep, B - b0)
@@ -323,35 +325,42 @@ class TrainStep:
         return X2, logits, rc
 
     def _level_fwd(self, il, Xsrc, logits, rc, acc, B, blk):
+        """cal_task_feature (taskprompter.py:424-487) in train mode. The T tasks' buffers are stacked by rows ([T*B*P, .]) so
+        that their identically shaped GEMMs / convolutions run as ONE grouped launch each and the row-wise kernels as one
+        batched launch."""
         dev, ns = self.dev, self.ns
         T, P, N, C, H, e, f = self.T, self.P, self.N, self.C, self.H, self.e, self.f
         Mp = B * P
         W = self.W
         bbp = "backbone."
+        pf = [f"{bbp}fea_fuse.{il}.{t}." for t in self.tasks]
+        ps = [f"{bbp}fea_decode_spa.{il}.{t}.0." for t in self.tasks]
+        pcn = [f"{bbp}fea_decode_chan.{il}.{t}.0." for t in self.tasks]
+        rows = lambda t: dict(a_row_offset=t * Mp)
+        ys, yc = Split(T * Mp, C, dev, ns), Split(T * Mp, C, dev, ns)
+        for t in range(T):
+            ops.gate_split(Xsrc, N, T, logits, rc, t, _rows_view(ys, t * Mp, Mp), _rows_view(yc, t * Mp, Mp), B=B, T=T, N=N,
+                           H=H, Cdim=C, gh=self.gh, gw=self.gw, nh=self.nh, nw=self.nw)
+        s_s, c_s = Split(T * Mp, e, dev, ns), Split(T * Mp, e, dev, ns)
+        _grouped([(ys, W[ps[t] + "weight"], dict(M=Mp, bias=self.P_(ps[t] + "bias"), out_split=s_s, out_row_offset=t * Mp,
+                                                 **rows(t))) for t in range(T)] +
+                 [(yc, W[pcn[t] + "weight"], dict(M=Mp, bias=self.P_(pcn[t] + "bias"), out_split=c_s, out_row_offset=t * Mp,
+                                                  **rows(t))) for t in range(T)])
+        y0 = _e(T, Mp, f, device=dev)
+        y0s = Split(T * Mp, f, dev, ns)
+        _grouped([(s_s, W[pf[t] + "0.weight#s"], dict(M=Mp, K=e, bias=self.P_(pf[t] + "0.bias"), out_f32=y0[t], **rows(t)))
+                  for t in range(T)])
+        _grouped([(c_s, W[pf[t] + "0.weight#c"], dict(M=Mp, K=e, residual=y0[t], out_f32=y0[t], out_split=y0s,
+                                                      out_row_offset=t * Mp, **rows(t))) for t in range(T)])
+        y1 = _e(T, Mp, f, device=dev)
+        _grouped([(y0s, W[pf[t] + "1.weight"], dict(M=Mp, N=f, K=f, bias=self.P_(pf[t] + "1.bias"), out_f32=y1[t],
+                                                    conv=(B, self.gh, self.gw, 3, 1), **rows(t))) for t in range(T)])
+        y2s = Split(T * Mp, f, dev, ns)
+        bn = [self._bn_fwd(y1[t], pf[t] + "2", ACT_GELU, _rows_view(y2s, t * Mp, Mp)) for t in range(T)]
         F_ = _z(T, Mp, self.f_ld, device=dev)
-        per = []
-        for ti, t in enumerate(self.tasks):
-            ys, yc = Split(Mp, C, dev, ns), Split(Mp, C, dev, ns)
-            ops.gate_split(Xsrc, N, T, logits, rc, ti, ys, yc, B=B, T=T, N=N, H=H, Cdim=C, gh=self.gh, gw=self.gw,
-                           nh=self.nh, nw=self.nw)
-            ns_, nc_ = f"{bbp}fea_decode_spa.{il}.{t}.0.", f"{bbp}fea_decode_chan.{il}.{t}.0."
-            s_s = Split(Mp, e, dev, ns, zero=e % 8 != 0)
-            c_s = Split(Mp, e, dev, ns, zero=e % 8 != 0)
-            ops.gemm(ys, W[ns_ + "weight"], bias=self.P_(ns_ + "bias"), out_split=s_s)
-            ops.gemm(yc, W[nc_ + "weight"], bias=self.P_(nc_ + "bias"), out_split=c_s)
-            pf = f"{bbp}fea_fuse.{il}.{t}."
-            y0 = _e(Mp, f, device=dev)
-            ops.gemm(s_s, W[pf + "0.weight#s"], K=e, bias=self.P_(pf + "0.bias"), out_f32=y0)
-            y0s = Split(Mp, f, dev, ns, zero=f % 8 != 0)
-            ops.gemm(c_s, W[pf + "0.weight#c"], K=e, residual=y0, out_f32=y0, out_split=y0s)
-            y1 = _e(Mp, f, device=dev)
-            ops.gemm(y0s, W[pf + "1.weight"], N=f, K=f, bias=self.P_(pf + "1.bias"), out_f32=y1,
-                     conv=(B, self.gh, self.gw, 3, 1))
-            y2s = Split(Mp, f, dev, ns, zero=f % 8 != 0)
-            mr, count = self._bn_fwd(y1, pf + "2", ACT_GELU, y2s)
-            ops.gemm(y2s, W[pf + "4.weight"], bias=self.P_(pf + "4.bias"), out_f32=F_[ti][:, :f])
-            per.append(dict(ys=ys, yc=yc, s_s=s_s, c_s=c_s, y0=y0, y1=y1, y2s=y2s, mr=mr, count=count))
-        ctrw = None
+        _grouped([(y2s, W[pf[t] + "4.weight"], dict(M=Mp, bias=self.P_(pf[t] + "4.bias"), out_f32=F_[t][:, :f], **rows(t)))
+                  for t in range(T)])
+        ctrw = per_ctr = None
         if self.use_ctr:
             pc = [f"{bbp}ctr_attn_conv.{il}.{t}." for t in self.tasks]
             # the T tasks' tiny conv parameters side by side: [T,H,H], [T,H], [T,H], [T]
@@ -365,28 +374,36 @@ class TrainStep:
             per_ctr = (c0, c0b, c2)
         else:
             ops.axpy_rows(acc.view(T * Mp, -1), F_.view(T * Mp, -1), None, acc.view(T * Mp, -1))
-            per_ctr = None
-        self.ctx["levels"].append(dict(il=il, Xsrc=Xsrc, blk=blk, F=F_, per=per, ctrw=ctrw, ctr=per_ctr))
+        self.ctx["levels"].append(dict(il=il, Xsrc=Xsrc, blk=blk, F=F_, ys=ys, yc=yc, s_s=s_s, c_s=c_s, y0=y0, y1=y1, y2s=y2s,
+                                       bn=bn, ctrw=ctrw, ctr=per_ctr))
 
-    def _head_fwd(self, ti, t, acc_t, B, oh, ow):
-        dev, ns, f = self.dev, self.ns, self.f
+    def _heads_fwd(self, acc, B, oh, ow):
+        """ConvHead of every task (taskprompter.py:688-698) on its x4 up-sampled feature map, then the resize to the label
+        size (taskprompter_wrapper.py:35); the T 3x3 convolutions are one grouped launch."""
+        dev, ns, f, T = self.dev, self.ns, self.f, self.T
         h4, w4 = 4 * self.gh, 4 * self.gw
         M4 = B * h4 * w4
         W = self.W
-        up = _e(M4, f, device=dev)
-        ups = Split(M4, f, dev, ns, zero=f % 8 != 0)
-        ops.bilinear(acc_t, self.f_ld, B, self.gh, self.gw, f, h4, w4, out_f32=up, out_split=ups)
-        ph = f"heads.{t}."
-        z = _e(M4, f, device=dev)
-        ops.gemm(ups, W[ph + "mt_proj.0.weight"], N=f, K=f, bias=self.P_(ph + "mt_proj.0.bias"), out_f32=z,
-                 conv=(B, h4, w4, 3, 1))
-        z2s = Split(M4, f, dev, ns, zero=f % 8 != 0)
-        mr, count = self._bn_fwd(z, ph + "mt_proj.1", ACT_GELU, z2s)
-        n_out = self.P_(ph + "linear_pred.weight").shape[0]
-        y = self._mm(z2s, W[ph + "linear_pred.weight"], bias=self.P_(ph + "linear_pred.bias"))
-        out = _e(B, n_out, oh, ow, device=dev)
-        ops.bilinear(y, n_out, B, h4, w4, n_out, oh, ow, out_nchw=out)
-        self.ctx["heads"].append(dict(up=up, z=z, z2s=z2s, mr=mr, count=count, n_out=n_out))
+        up = _e(T, M4, f, device=dev)
+        ups = Split(T * M4, f, dev, ns)
+        for t in range(T):
+            ops.bilinear(acc[t], self.f_ld, B, self.gh, self.gw, f, h4, w4, out_f32=up[t], out_split=_rows_view(ups, t * M4, M4))
+        ph = [f"heads.{t}." for t in self.tasks]
+        z = _e(T, M4, f, device=dev)
+        _grouped([(ups, W[ph[t] + "mt_proj.0.weight"], dict(M=M4, N=f, K=f, bias=self.P_(ph[t] + "mt_proj.0.bias"), out_f32=z[t],
+                                                            conv=(B, h4, w4, 3, 1), a_row_offset=t * M4)) for t in range(T)])
+        z2s = Split(T * M4, f, dev, ns)
+        bn = [self._bn_fwd(z[t], ph[t] + "mt_proj.1", ACT_GELU, _rows_view(z2s, t * M4, M4)) for t in range(T)]
+        out, n_outs = {}, []
+        for t, name in enumerate(self.tasks):
+            n_out = self.P_(ph[t] + "linear_pred.weight").shape[0]
+            y = _e(M4, n_out, device=dev)
+            ops.gemm(z2s, W[ph[t] + "linear_pred.weight"], M=M4, bias=self.P_(ph[t] + "linear_pred.bias"), out_f32=y,
+                     a_row_offset=t * M4)
+            out[name] = _e(B, n_out, oh, ow, device=dev)
+            ops.bilinear(y, n_out, B, h4, w4, n_out, oh, ow, out_nchw=out[name])
+            n_outs.append(n_out)
+        self.ctx["heads"] = dict(up=up, z=z, z2s=z2s, bn=bn, n_out=n_outs)
         return out
 
     # ---- backward ------------------------------------------------------------------------------------------------------
@@ -397,9 +414,7 @@ class TrainStep:
         T, P, N, C, f = self.T, self.P, self.N, self.C, self.f
         M, Mp = B * N, B * P
         dacc = _z(T, Mp, self.f_ld, device=dev)
-        for ti in reversed(range(T)):
-            self._head_bwd(ti, self.tasks[ti], grad_out[self.tasks[ti]].to(dev, torch.float32).contiguous(),
-                           dacc[ti][:, :f], B)
+        self._heads_bwd(grad_out, dacc, B)
         self._bucket_ready("heads.")
         dX = _z(M, C, device=dev)
         # last level reads LN_final(x)
@@ -431,36 +446,76 @@ class TrainStep:
         self._bucket_ready(None)
         self.ctx = None
 
-    def _head_bwd(self, ti, t, g, dacc_t, B):
-        dev, f = self.dev, self.f
-        hc = self.ctx["heads"][ti]
+    def _heads_bwd(self, grad_out, dacc, B):
+        dev, f, T, ns = self.dev, self.f, self.T, self.ns
+        hc = self.ctx["heads"]
         h4, w4 = 4 * self.gh, 4 * self.gw
         M4 = B * h4 * w4
-        n_out = hc["n_out"]
         oh, ow = self.ctx["out_hw"]
-        ph = f"heads.{t}."
-        dy = _e(M4, n_out, device=dev)
-        ops.bilinear_bwd(g, nchw=True, B=B, h=h4, w=w4, Cdim=n_out, H2=oh, W2=ow, dx=dy)
-        dz2 = self._lin_bwd(dy, hc["z2s"], ph + "linear_pred.weight", M=M4, N=n_out, K=f)
-        dz = self._bn_bwd(hc["z"], dz2, ph + "mt_proj.1", ACT_GELU, hc["mr"], hc["count"])
-        dup = self._conv3_bwd(dz, hc["up"], ph + "mt_proj.0", B, h4, w4, f, f)
-        ops.bilinear_bwd(dup, nchw=False, B=B, h=self.gh, w=self.gw, Cdim=f, H2=h4, W2=w4, dx=dacc_t)
+        ph = [f"heads.{t}." for t in self.tasks]
+        dz2 = _e(T, M4, f, device=dev)
+        for t, name in enumerate(self.tasks):
+            n_out = hc["n_out"][t]
+            g = grad_out[name].to(dev, torch.float32).contiguous()
+            dy = _e(M4, n_out, device=dev)
+            ops.bilinear_bwd(g, nchw=True, B=B, h=h4, w=w4, Cdim=n_out, H2=oh, W2=ow, dx=dy)
+            self._lin_bwd(dy, _rows_view(hc["z2s"], t * M4, M4), ph[t] + "linear_pred.weight", M=M4, N=n_out, K=f,
+                          dx_out=dz2[t])
+        dz = _e(T, M4, f, device=dev)
+        for t in range(T):
+            self._bn_bwd(hc["z"][t], dz2[t], ph[t] + "mt_proj.1", ACT_GELU, *hc["bn"][t], dx=dz[t])
+        dup = self._conv3_bwd_group(dz.view(T * M4, f), hc["up"].view(T * M4, f), [p + "mt_proj.0" for p in ph], B, h4, w4, f, f)
+        for t in range(T):
+            ops.bilinear_bwd(dup[t * M4:(t + 1) * M4], nchw=False, B=B, h=self.gh, w=self.gw, Cdim=f, H2=h4, W2=w4,
+                             dx=dacc[t][:, :f])
 
-    def _conv3_bwd(self, dy, x32, prefix, B, h, w, Cin, Cout):
-        """3x3 conv (pad 1): dy fp32 [B*h*w, Cout], input x32 fp32 [B*h*w, Cin] -> dx; accumulates dW, db."""
-        Mx = B * h * w
-        dyT = Split(Cout, Mx, self.dev, self.ns, zero=Mx % 8 != 0)
-        ops.transpose_split(dy, dyT, B=1, L=Mx, Cdim=Cout)
-        x9T = ops.im2col3x3_t(x32, B=B, H=h, W=w, Cdim=Cin, nsplit=self.ns)
-        gW = self.G_(prefix + ".weight").reshape(Cout, Cin * 9)
-        ops.gemm(dyT, x9T, M=Cout, N=Cin * 9, K=Mx, residual=gW, out_f32=gW)
-        ops.colsum(dy, self.G_(prefix + ".bias"), accumulate=True)
-        dx = _e(Mx, Cin, device=self.dev)
-        ops.gemm(self._S(dy), self.WT[prefix + ".weight"], N=Cin, K=Cout, out_f32=dx, conv=(B, h, w, 3, 1))
+    def _conv3_bwd_group(self, dy, x32, prefixes, B, h, w, Cin, Cout):
+        """3x3 convs (pad 1) of len(prefixes) tasks stacked by rows: dy fp32 [T*Mx, Cout], inputs x32 fp32 [T*Mx, Cin] ->
+        dx fp32 [T*Mx, Cin]; dW (one grouped GEMM over the transposed im2col operand), db."""
+        Tn, Mx, dev, ns = len(prefixes), B * h * w, self.dev, self.ns
+        dyT = Split(Tn * Cout, Mx, dev, ns)
+        ops.transpose_split(dy, dyT, B=Tn, L=Mx, Cdim=Cout)
+        x9T = ops.im2col3x3_t(x32, B=Tn * B, H=h, W=w, Cdim=Cin, nsplit=ns)              # [Cin*9, Tn*Mx]: task t = columns t*Mx ..
+        gWs = [self.G_(p + ".weight").reshape(Cout, Cin * 9) for p in prefixes]
+        if Mx % 8 == 0:
+            _grouped([(dyT, x9T, dict(M=Cout, N=Cin * 9, K=Mx, a_row_offset=t * Cout, w_col_offset=t * Mx, residual=gWs[t],
+                                      out_f32=gWs[t])) for t in range(Tn)])
+        else:                                             # column offsets must stay 16-byte aligned for TMA
+            for t in range(Tn):
+                xt = ops.im2col3x3_t(x32[t * Mx:(t + 1) * Mx], B=B, H=h, W=w, Cdim=Cin, nsplit=ns)
+                ops.gemm(dyT, xt, M=Cout, N=Cin * 9, K=Mx, a_row_offset=t * Cout, residual=gWs[t], out_f32=gWs[t])
+        for t, p in enumerate(prefixes):
+            ops.colsum(dy, self.G_(p + ".bias"), accumulate=True, rows=Mx, in_group=Mx, src_group=Mx, src_offset=t * Mx)
+        dys = self._S(dy)
+        dx = _e(Tn * Mx, Cin, device=dev)
+        _grouped([(dys, self.WT[p + ".weight"], dict(M=Mx, N=Cin, K=Cout, out_f32=dx[t * Mx:(t + 1) * Mx],
+                                                     conv=(B, h, w, 3, 1), a_row_offset=t * Mx)) for t, p in enumerate(prefixes)])
         return dx
 
+    def _lin_bwd_group(self, dy, a_s, items, *, M, N, K, dyT=None, dy_s=None, need_dx=True):
+        """T problems Y_t = A_t W_t^T + b_t stacked by rows: dy fp32 [T*M, N] (any row stride), a_s Split [T*M, K];
+        items[t] = (gW view [N, K], bias-gradient view or None, key of W_t in self.WT). dW / db accumulate; returns
+        (dA fp32 [T*M, K] or None, dyT, dy_s) -- the transposed / split dY can be shared by a second call on the same dY."""
+        Tn, dev, ns = len(items), self.dev, self.ns
+        if dyT is None:
+            dyT = Split(Tn * N, M, dev, ns)
+            ops.transpose_split(dy, dyT, B=Tn, L=M, Cdim=N)
+        aT = ops.transpose_planes(a_s, B=Tn, R=M, Ccols=K)
+        _grouped([(dyT, aT, dict(M=N, N=K, K=M, a_row_offset=t * N, w_row_offset=t * K, residual=it[0], out_f32=it[0]))
+                  for t, it in enumerate(items)])
+        for t, it in enumerate(items):
+            if it[1] is not None:
+                ops.colsum(dy, it[1], accumulate=True, rows=M, in_group=M, src_group=M, src_offset=t * M)
+        dx = None
+        if need_dx:
+            dy_s = self._S(dy) if dy_s is None else dy_s
+            dx = _e(Tn * M, K, device=dev)
+            _grouped([(dy_s, self.WT[it[2]], dict(M=M, N=K, K=N, a_row_offset=t * M, out_f32=dx[t * M:(t + 1) * M]))
+                      for t, it in enumerate(items)])
+        return dx, dyT, dy_s
+
     def _level_bwd(self, lv, dacc, dXsrc, B):
-        """Adjoint of _level_fwd: dacc [T, B*P, f] (the same for every level: acc is their sum) -> dXsrc (+=), the logit
+        """Adjoint of _level_fwd: dacc [T, B*P, f_ld] (the same for every level: acc is their sum) -> dXsrc (+=), the logit
         gradients of the block that exported them, parameter gradients."""
         dev = self.dev
         T, P, N, C, H, e, f = self.T, self.P, self.N, self.C, self.H, self.e, self.f
@@ -489,22 +544,29 @@ class TrainStep:
                         rows_per_batch=P, accumulate=False)
         else:
             dF = dacc
-        for ti, t in enumerate(self.tasks):
-            pc = lv["per"][ti]
-            pf = f"{bbp}fea_fuse.{il}.{t}."
-            dy2 = self._lin_bwd(dF[ti][:, :f], pc["y2s"], pf + "4.weight", M=Mp, N=f, K=f)
-            dy1 = self._bn_bwd(pc["y1"], dy2, pf + "2", ACT_GELU, pc["mr"], pc["count"])
-            dy0 = self._conv3_bwd(dy1, pc["y0"], pf + "1", B, self.gh, self.gw, f, f)
-            dy0s = self._S(dy0)
-            g0 = self.G_(pf + "0.weight").reshape(f, 2 * e)
-            ds = self._lin_bwd(dy0, pc["s_s"], pf + "0.weight", M=Mp, N=f, K=e, wkey=pf + "0.weight#s", gW=g0[:, :e],
-                               dy_s=dy0s)
-            dc = self._lin_bwd(dy0, pc["c_s"], pf + "0.weight", M=Mp, N=f, K=e, wkey=pf + "0.weight#c", gW=g0[:, e:],
-                               bias_name=None, dy_s=dy0s)
-            dys = self._lin_bwd(ds, pc["ys"], f"{bbp}fea_decode_spa.{il}.{t}.0.weight", M=Mp, N=e, K=C)
-            dyc = self._lin_bwd(dc, pc["yc"], f"{bbp}fea_decode_chan.{il}.{t}.0.weight", M=Mp, N=e, K=C)
-            ops.gate_bwd(lv["Xsrc"], N, T, logits, rc, ti, dys, dyc, dXsrc, d_logits, d_rc, B=B, T=T, N=N, H=H, Cdim=C,
-                         gh=self.gh, gw=self.gw, nh=self.nh, nw=self.nw)
+        pf = [f"{bbp}fea_fuse.{il}.{t}." for t in self.tasks]
+        G, Pb = self.G_, (lambda n: self.G_(n))
+        dFv = dF.view(T * Mp, self.f_ld)[:, :f]
+        dy2, _, _ = self._lin_bwd_group(dFv, lv["y2s"], [(G(p + "4.weight").reshape(f, f), G(p + "4.bias"), p + "4.weight") for p in pf],
+                                        M=Mp, N=f, K=f)
+        dy1 = _e(T, Mp, f, device=dev)
+        for t in range(T):
+            self._bn_bwd(lv["y1"][t], dy2[t * Mp:(t + 1) * Mp], pf[t] + "2", ACT_GELU, *lv["bn"][t], dx=dy1[t])
+        dy0 = self._conv3_bwd_group(dy1.view(T * Mp, f), lv["y0"].view(T * Mp, f), [p + "1" for p in pf], B, self.gh, self.gw, f, f)
+        g0 = [G(p + "0.weight").reshape(f, 2 * e) for p in pf]
+        ds, dyT, dy0s = self._lin_bwd_group(dy0, lv["s_s"], [(g0[t][:, :e], G(pf[t] + "0.bias"), pf[t] + "0.weight#s")
+                                                             for t in range(T)], M=Mp, N=f, K=e)
+        dc, _, _ = self._lin_bwd_group(dy0, lv["c_s"], [(g0[t][:, e:], None, pf[t] + "0.weight#c") for t in range(T)],
+                                       M=Mp, N=f, K=e, dyT=dyT, dy_s=dy0s)
+        ps = [f"{bbp}fea_decode_spa.{il}.{t}.0." for t in self.tasks]
+        pcn = [f"{bbp}fea_decode_chan.{il}.{t}.0." for t in self.tasks]
+        dys, _, _ = self._lin_bwd_group(ds, lv["ys"], [(G(p + "weight").reshape(e, C), G(p + "bias"), p + "weight") for p in ps],
+                                        M=Mp, N=e, K=C)
+        dyc, _, _ = self._lin_bwd_group(dc, lv["yc"], [(G(p + "weight").reshape(e, C), G(p + "bias"), p + "weight") for p in pcn],
+                                        M=Mp, N=e, K=C)
+        for t in range(T):
+            ops.gate_bwd(lv["Xsrc"], N, T, logits, rc, t, dys[t * Mp:(t + 1) * Mp], dyc[t * Mp:(t + 1) * Mp], dXsrc, d_logits,
+                         d_rc, B=B, T=T, N=N, H=H, Cdim=C, gh=self.gh, gw=self.gw, nh=self.nh, nw=self.nw)
 
     def _block_bwd(self, i, dX2, B):
         dev, ns = self.dev, self.ns
@@ -604,17 +666,13 @@ class TrainStep:
                                                  out_f32=dP[r0:r0 + N])))
         _grouped(calls_s)
         _grouped(calls_p)
-        dS = Split(BH * N, Np, dev, ns, zero=Np != N)
-        ops.attn_softmax_bwd(S, dP, BH=BH, N=N, scale=64 ** -0.5, d_raw=bc["d_logits"], T=T, ds=dS)
-        PT = Split(BH * N, Np, dev, ns, zero=Np != N)
-        ops.transpose_split(S, PT, B=BH, L=N, Cdim=N)            # P^T per (b, h): [N keys, N queries]
-        dST = Split(BH * N, Np, dev, ns, zero=Np != N)
-        ops.transpose_split(dP, dST, B=BH, L=N, Cdim=N)
+        dS, PT, dST = Split(BH * N, Np, dev, ns), Split(BH * N, Np, dev, ns), Split(BH * N, Np, dev, ns)
+        ops.attn_softmax_bwd(S, dP, BH=BH, N=N, scale=64 ** -0.5, d_raw=bc["d_logits"], T=T, ds=dS, pt=PT, dst=dST)
         del S, dP
         # operands transposed per image: [B][3C][Np] (q^T | k^T | v^T rows) and [B][C][Np] (dO^T)
-        qkvT = Split(B * 3 * C, Np, dev, ns, zero=Np != N)
+        qkvT = Split(B * 3 * C, Np, dev, ns)
         ops.transpose_planes(qkv, B=B, R=N, Ccols=3 * C, in_batch_rows=N, out=qkvT)
-        daoT = Split(B * C, Np, dev, ns, zero=Np != N)
+        daoT = Split(B * C, Np, dev, ns)
         ops.transpose_planes(dao_s, B=B, R=N, Ccols=C, in_batch_rows=N, out=daoT)
         cq, ck, cv = [], [], []
         for b_ in range(B):
@@ -694,6 +752,14 @@ class TrainStep:
     def step(self, images, targets, criterion, tasks=None):
         """One iteration of train_utils.py:34-51 with `criterion` = mtt_b200.losses.MultiTaskLoss (device kernels):
         returns the loss dict (device scalars)."""
+        if self.use_graph:
+            loss = self._graph_fwd_bwd(images, targets, criterion, tasks)
+        else:
+            loss = self._fwd_bwd(images, targets, criterion, tasks)
+        self.optimizer_step()
+        return loss
+
+    def _fwd_bwd(self, images, targets, criterion, tasks):
         self.zero_grad()
         out = self.forward(images)
         leaves = {t: o.requires_grad_(True) for t, o in out.items()}
@@ -701,8 +767,35 @@ class TrainStep:
             loss = criterion(leaves, targets, tasks=tasks or self.tasks)
             grads = torch.autograd.grad(loss["total"], [leaves[t] for t in self.tasks])
         self.backward({t: g for t, g in zip(self.tasks, grads)})
-        self.optimizer_step()
         return {k: v.detach() for k, v in loss.items()}
+
+    def _graph_fwd_bwd(self, images, targets, criterion, tasks):
+        key = (tuple(images.shape), tuple(sorted((t, tuple(v.shape)) for t, v in targets.items())))
+        if self._graph is None or self._graph[0] != key:
+            gx = images.to(self.dev, torch.float32).clone()
+            gy = {t: v.to(self.dev).clone() for t, v in targets.items()}
+            # one eager pass on a side stream before capture (allocator warm-up); it must not count as a training step:
+            # the BatchNorm running statistics it touches are restored
+            bufs = [b for b in self.model.buffers()]
+            keep = [b.clone() for b in bufs]
+            side = torch.cuda.Stream(device=self.dev)
+            side.wait_stream(torch.cuda.current_stream(self.dev))
+            with torch.cuda.stream(side):
+                self._fwd_bwd(gx, gy, criterion, tasks)
+            torch.cuda.current_stream(self.dev).wait_stream(side)
+            with torch.no_grad():
+                for b, k in zip(bufs, keep):
+                    b.copy_(k)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                loss = self._fwd_bwd(gx, gy, criterion, tasks)
+            self._graph = (key, g, gx, gy, loss)
+        _, g, gx, gy, loss = self._graph
+        gx.copy_(images, non_blocking=True)
+        for t, v in targets.items():
+            gy[t].copy_(v, non_blocking=True)
+        g.replay()
+        return loss
 
     def apply(self, images):
         """Torch-facing forward: {task: prediction} attached to autograd; .backward() of any loss built on them runs the
@@ -711,6 +804,13 @@ class TrainStep:
         params = [p for _, p in self.model.named_parameters()]
         outs = _StepFn.apply(self, images, *params)
         return {t: o for t, o in zip(self.tasks, outs)}
+
+
+def _rows_view(sp, r0, n):
+    """Rows [r0, r0 + n) of a Split as a Split (shares storage)."""
+    v = Split.__new__(Split)
+    v.buf, v.rows, v.cols, v.ld, v.nsplit = sp.buf[:, r0:r0 + n], n, sp.cols, sp.ld, sp.nsplit
+    return v
 
 
 def _grouped(calls, limit=32):

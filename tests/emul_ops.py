@@ -523,16 +523,17 @@ def install(mp):
         dz, xh = _bn_dz(x, dy, mean_rstd, gamma, beta, act)
         dx[:, :C_] = gamma * mean_rstd[C_:] * (dz - sums[:C_] / count - xh * sums[C_:] / count)
 
-    def attn_softmax_bwd(S, dP, *, BH, N, scale, d_raw, T, ds):
+    def attn_softmax_bwd(S, dP, *, BH, N, scale, d_raw, T, ds, pt=None, dst=None):
         s_ = S[:, :N].reshape(BH, N, N).detach().clone().requires_grad_(True)
         P = (s_ * scale).softmax(-1)
         P.backward(dP[:, :N].reshape(BH, N, N).clone())
         g = s_.grad
         if d_raw is not None:
             g[:, :T, :] += d_raw.reshape(BH, T, N)
-        S[:, :N] = P.detach().reshape(BH * N, N)
-        dP[:, :N] = g.reshape(BH * N, N)
         _wsplit(ds, g.reshape(BH * N, N))
+        if pt is not None:
+            _wsplit(pt, P.detach().transpose(1, 2).reshape(BH * N, N))
+            _wsplit(dst, g.transpose(1, 2).reshape(BH * N, N))
 
     def bilinear_bwd(dy, *, nchw, B, h, w, Cdim, H2, W2, dx, accumulate=False):
         g = dy.reshape(B, Cdim, H2, W2) if nchw else dy[:, :Cdim].reshape(B, H2, W2, Cdim).permute(0, 3, 1, 2)

@@ -165,15 +165,17 @@ def test_batchnorm_train(both, cuda_dev, act):
 def test_attn_softmax_bwd(both, cuda_dev):
     ops, emu = both
     torch.manual_seed(6)
-    BH, N, T = 6, 45, 3
-    ld = 48
+    BH, N, T = 6, 77, 3          # two query tiles, the second ragged; odd N
+    ld = 80
     S, dP, dr = torch.randn(BH * N, ld) * 3, torch.randn(BH * N, ld), torch.randn(BH, T, N)
     res = []
     for dev, real in ((cuda_dev, True), ("cpu", False)):
         s, d = S.clone().to(dev), dP.clone().to(dev)
-        ds = ops.Split(BH * N, ld, dev, 2, zero=True)
-        (ops.attn_softmax_bwd if real else emu["attn_softmax_bwd"])(s, d, BH=BH, N=N, scale=0.125, d_raw=dr.to(dev), T=T, ds=ds)
-        res.append((s[:, :N], d[:, :N], ds.float()[:, :N]))
+        ds, pt, dst = (ops.Split(BH * N, ld, dev, 2, zero=True) for _ in range(3))
+        (ops.attn_softmax_bwd if real else emu["attn_softmax_bwd"])(s, d, BH=BH, N=N, scale=0.125, d_raw=dr.to(dev), T=T, ds=ds,
+                                                                    pt=pt, dst=dst)
+        assert torch.equal(s.cpu(), S) and torch.equal(d.cpu(), dP)          # inputs are read only
+        res.append((ds.float()[:, :N], pt.float()[:, :N], dst.float()[:, :N]))
     for a, b in zip(*res):
         assert relerr(a, b) < 2e-5
 
@@ -396,3 +398,43 @@ def test_torch_facing_step_delivers_the_same_gradients(cuda_dev):
     assert nz >= len(got) - 2, f"only {nz} of {len(got)} parameters received a gradient"
     total = torch.sqrt(sum((g.double() ** 2).sum() for g in got.values()))
     assert 0.2 * fx["total_norm"] < float(total) < 5 * fx["total_norm"]      # DropPath masks differ from the fixture's
+
+
+def test_graph_replay_equals_eager_steps(cuda_dev):
+    """TrainStep(use_graph=True) captures forward + criterion + reverse pass once and replays it: after three steps on
+    changing batches the parameters equal those of the eagerly launched steps (DropPath off: both draw nothing)."""
+    import mtt_b200  # noqa: F401
+    from mtt_b200 import losses, taskprompter as TP
+    from mtt_b200.train import TrainStep
+    from oracle.make_golden import synthetic_labels
+
+    cfg = configs.taskprompter("tp_tiny1")
+    cfg["drop_path_rate"] = 0.0
+    sd = TPR.init_state_dict(cfg, seed=5)
+    p = dict(TASKS=dict(NAMES=list(cfg["tasks"])), edge_w=0.95, ignore_index=255, ignore_invalid_area_depth=True,
+             loss_kwargs=dict(loss_weights={"semseg": 1.0, "edge": 50.0}))
+    crit = losses.get_criterion(p)
+    g = torch.Generator().manual_seed(9)
+    batches = [(torch.randn(2, 3, *cfg["img_size"], generator=g), synthetic_labels(cfg["tasks"], cfg["num_output"], 2,
+                                                                                  *cfg["img_size"], g)) for _ in range(3)]
+    res = []
+    for use_graph in (False, True):
+        model = TP.build_from_config(cfg, use_graph=False)
+        model.load_state_dict(sd)
+        model.to(cuda_dev)
+        ts = TrainStep(model, lr=1e-3, use_graph=use_graph)
+        losses_seen = []
+        with torch.no_grad():
+            for x, y in batches:
+                out = ts.step(x.to(cuda_dev), {t: v.to(cuda_dev) for t, v in y.items()}, crit)
+                losses_seen.append(float(out["total"]))
+        torch.cuda.synchronize()
+        res.append((ts.grads.flat.clone(), losses_seen, {k: v.clone() for k, v in model.state_dict().items() if "running_" in k}))
+    (pe, le, be), (pg, lg, bg) = res
+    assert all(abs(a - b) <= 1e-4 * max(1.0, abs(a)) for a, b in zip(le, lg)), (le, lg)
+    assert le[0] != le[1]                                        # the replays really saw different batches
+    # the gradients of the third step (parameters themselves are not compared: a bias in front of a BatchNorm has a zero
+    # gradient up to atomics-order noise, and Adam turns that noise into +-lr steps)
+    assert relerr(pg, pe) < 1e-3
+    for k in be:
+        assert torch.allclose(be[k], bg[k], rtol=1e-5, atol=1e-6), k
