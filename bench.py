@@ -659,6 +659,14 @@ def run_train(args):
     recs = ops.profile_end(max_recs=16384)
     tc_ms = sum(r[4] for r in recs)
     tc_flops = sum(r[5] for r in recs)
+    ts._graph = None                 # the captured step (and the NCCL work inside it) goes before the process group does
+    torch.cuda.synchronize()
+    D.barrier(world)
+    if world > 1:                    # a process group that has been captured into CUDA graphs can block in its destructor:
+        import threading             # the result is already measured, so do not let the tear-down hang the job
+        w = threading.Timer(30.0, lambda: os._exit(0))
+        w.daemon = True
+        w.start()
     shapes = {}
     for kind, M_, N_, K_, ms, fl in recs:
         a = shapes.setdefault((kind, M_, N_, K_), [0, 0.0, 0.0])

@@ -493,7 +493,8 @@ int mtt_nhwc_to_nchw(const float* in, int64_t ld_in, int32_t B, int32_t C, int32
  *   fp32 and / or split planes. mtt_bn_bwd_reduce: sums = (sum dz, sum dz*xhat), dz = dy * act'(z) (= dbeta, dgamma; all-reduce
  *   for SyncBatchNorm); mtt_bn_bwd_apply: dx = gamma*rstd*(dz - sums[0]/count - xhat*sums[1]/count).
  * mtt_attn_softmax_bwd: per (batch*head) rows of raw scores S [BH, N, ld] and dP [BH, N, ld] (fp32, read only):
- *   P = softmax(scale*S) recomputed, dS = scale*P*(dP - sum_j P dP) (+ d_raw [BH, T, N] on the first T rows: the gradient of
+ *   P = softmax(scale*S) recomputed, dS = scale*P*(dP - delta) with delta [BH, N] = sum_j P dP = rowdot(dO, O) from
+ *   mtt_attn_delta (dO fp32 [B*N, H*head_dim], O = the forward's split output) (+ d_raw [BH, T, N] on the first T rows: the gradient of
  *   the exported prompt logits, TP taskprompter.py:204). Outputs, all split planes with row stride ldbf: dS row-major
  *   [BH*N queries, N] and (optional, NULL to skip) P^T and dS^T key-major [BH*N keys, N queries] -- the A operands of
  *   dQ = dS k, dV = P^T dO and dK = dS^T q.
@@ -536,9 +537,11 @@ int mtt_bn_bwd_reduce(const float* x, int64_t ldx, const float* dy, int64_t lddy
 int mtt_bn_bwd_apply(const float* x, int64_t ldx, const float* dy, int64_t lddy, int64_t rows, int32_t cols,
                      const float* mean_rstd, const float* gamma, const float* beta, int32_t act, const float* sums,
                      float count, float* dx, int64_t lddx, mtt_stream_t stream);
-int mtt_attn_softmax_bwd(const float* S, const float* dP, int64_t ld, int32_t BH, int32_t N, float scale, const float* d_raw,
-                         int32_t T, void* ds_hi, void* ds_lo, void* pt_hi, void* pt_lo, void* dst_hi, void* dst_lo, int64_t ldbf,
-                         mtt_stream_t stream);
+int mtt_attn_delta(const float* dO, int64_t lddo, const void* o_hi, const void* o_lo, int64_t ldo, int32_t B, int32_t N,
+                   int32_t H, int32_t head_dim, float* delta, mtt_stream_t stream);
+int mtt_attn_softmax_bwd(const float* S, const float* dP, const float* delta, int64_t ld, int32_t BH, int32_t N, float scale,
+                         const float* d_raw, int32_t T, void* ds_hi, void* ds_lo, void* pt_hi, void* pt_lo, void* dst_hi,
+                         void* dst_lo, int64_t ldbf, mtt_stream_t stream);
 int mtt_bilinear_bwd(const float* dy, int64_t lddy, int32_t nchw, int32_t B, int32_t h, int32_t w, int32_t C, int32_t H2,
                      int32_t W2, float* dx, int64_t lddx, int32_t accumulate, mtt_stream_t stream);
 int mtt_gate_bwd(const float* x, int64_t ldx, int64_t x_group_rows, int64_t x_row_offset, const float* prompt_logits,

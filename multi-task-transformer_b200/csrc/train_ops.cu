@@ -296,12 +296,14 @@ bn_bwd_apply_kernel(const float* __restrict__ x, long long ldx, const float* __r
 // ---- attention backward: softmax ---------------------------------------------------------------------------------------
 // P = softmax(scale * S) recomputed from the raw scores S, dS = scale * P * (dP - sum_j P dP) + d_raw on the first T rows (the
 // prompt rows whose raw q.k are an output of the block, taskprompter.py:204). One block per (64 query rows, batch*head):
-// phase 1 = per-row statistics (warp per row), phase 2 = 64 x 64 tiles: dS is written row-major (the A operand of dQ = dS k)
+// phase 1 = row maximum and sum in ONE pass (warp per row; sum_j P dP comes precomputed as delta = rowdot(dO, O), the
+// identity sum_j P_ij (dO_i . v_j) = dO_i . O_i), phase 2 = 64 x 64 tiles: dS is written row-major (the A operand of dQ = dS k)
 // and, through a shared-memory transpose, P^T and dS^T key-major (the A operands of dV = P^T dO and dK = dS^T q) -- all as
 // split planes; nothing of size N^2 is written in fp32.
 __global__ void __launch_bounds__(256)
-attn_softmax_bwd_kernel(const float* __restrict__ S, const float* __restrict__ dP, long long ld, int N, float scale,
-                        const float* __restrict__ d_raw, int T, __nv_bfloat16* __restrict__ ds_hi,
+attn_softmax_bwd_kernel(const float* __restrict__ S, const float* __restrict__ dP, const float* __restrict__ delta,
+                        long long ld, int N, float scale, const float* __restrict__ d_raw, int T,
+                        __nv_bfloat16* __restrict__ ds_hi,
                         __nv_bfloat16* __restrict__ ds_lo, __nv_bfloat16* __restrict__ pt_hi, __nv_bfloat16* __restrict__ pt_lo,
                         __nv_bfloat16* __restrict__ dst_hi, __nv_bfloat16* __restrict__ dst_lo, long long ldbf) {
   __shared__ float stat[64][3];
@@ -315,20 +317,23 @@ attn_softmax_bwd_kernel(const float* __restrict__ S, const float* __restrict__ d
     const int q = q0 + warp * 8 + k;
     if (q >= N) break;
     const float* s = Sb + (long long)q * ld;
-    const float* g = Gb + (long long)q * ld;
-    float m = -INFINITY;
-    for (int j = lane; j < N; j += 32) m = fmaxf(m, s[j]);
-    m = wmax(m) * scale;
-    float l = 0.f;
-    for (int j = lane; j < N; j += 32) l += __expf(s[j] * scale - m);
-    const float inv = 1.f / wsum(l);
-    float dot = 0.f;
-    for (int j = lane; j < N; j += 32) dot += __expf(s[j] * scale - m) * inv * g[j];
-    dot = wsum(dot);
+    // one pass over the row: running maximum and rescaled sum per lane, merged across the warp
+    float m = -INFINITY, l = 0.f;
+    for (int j = lane; j < N; j += 32) {
+      const float v = s[j] * scale;
+      if (v > m) {
+        l = l * __expf(m - v) + 1.f;
+        m = v;
+      } else {
+        l += __expf(v - m);
+      }
+    }
+    const float mw = wmax(m);
+    l = wsum(l * __expf(m - mw));
     if (lane == 0) {
-      stat[warp * 8 + k][0] = m;
-      stat[warp * 8 + k][1] = inv;
-      stat[warp * 8 + k][2] = dot;
+      stat[warp * 8 + k][0] = mw;
+      stat[warp * 8 + k][1] = 1.f / l;
+      stat[warp * 8 + k][2] = delta[bh * N + q];
     }
   }
   __syncthreads();
@@ -401,6 +406,28 @@ attn_softmax_bwd_kernel(const float* __restrict__ S, const float* __restrict__ d
       }
     }
     __syncthreads();
+  }
+}
+
+// delta[(b*H + h)*N + i] = sum_d dO[b*N + i, h*dh + d] * O[b*N + i, h*dh + d]; O given as split planes. One warp per token row.
+__global__ void __launch_bounds__(256)
+attn_delta_kernel(const float* __restrict__ dO, long long lddo, const __nv_bfloat16* __restrict__ o_hi,
+                  const __nv_bfloat16* __restrict__ o_lo, long long ldo, int B, int N, int H, int dh,
+                  float* __restrict__ delta) {
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= (long long)B * N) return;
+  const int lane = threadIdx.x & 31;
+  const int b = (int)(row / N), i = (int)(row % N);
+  for (int h = 0; h < H; ++h) {
+    float acc = 0.f;
+    for (int d = lane; d < dh; d += 32) {
+      const long long c = (long long)h * dh + d;
+      float o = __bfloat162float(o_hi[row * ldo + c]);
+      if (o_lo) o += __bfloat162float(o_lo[row * ldo + c]);
+      acc += dO[row * lddo + c] * o;
+    }
+    acc = wsum(acc);
+    if (lane == 0) delta[((long long)b * H + h) * N + i] = acc;
   }
 }
 
@@ -820,15 +847,26 @@ extern "C" int mtt_bn_bwd_apply(const float* x, int64_t ldx, const float* dy, in
   return check_launch("mtt_bn_bwd_apply");
 }
 
-extern "C" int mtt_attn_softmax_bwd(const float* S, const float* dP, int64_t ld, int32_t BH, int32_t N, float scale,
-                                    const float* d_raw, int32_t T, void* ds_hi, void* ds_lo, void* pt_hi, void* pt_lo,
-                                    void* dst_hi, void* dst_lo, int64_t ldbf, mtt_stream_t stream) {
-  if (!S || !dP || !ds_hi || BH <= 0 || N <= 0 || ld < N || ldbf < N || ld % 2 || ldbf % 2 || (pt_hi && !dst_hi))
+extern "C" int mtt_attn_delta(const float* dO, int64_t lddo, const void* o_hi, const void* o_lo, int64_t ldo, int32_t B,
+                              int32_t N, int32_t H, int32_t head_dim, float* delta, mtt_stream_t stream) {
+  if (!dO || !o_hi || !delta || B <= 0 || N <= 0 || H <= 0 || head_dim <= 0)
+    return set_error(MTT_ERR_BAD_SHAPE, "mtt_attn_delta: bad arguments");
+  attn_delta_kernel<<<row_blocks((long long)B * N), 256, 0, ST>>>(dO, lddo, static_cast<const __nv_bfloat16*>(o_hi),
+                                                                static_cast<const __nv_bfloat16*>(o_lo), ldo, B, N, H,
+                                                                head_dim, delta);
+  count_launch();
+  return check_launch("mtt_attn_delta");
+}
+
+extern "C" int mtt_attn_softmax_bwd(const float* S, const float* dP, const float* delta, int64_t ld, int32_t BH, int32_t N,
+                                    float scale, const float* d_raw, int32_t T, void* ds_hi, void* ds_lo, void* pt_hi,
+                                    void* pt_lo, void* dst_hi, void* dst_lo, int64_t ldbf, mtt_stream_t stream) {
+  if (!S || !dP || !delta || !ds_hi || BH <= 0 || N <= 0 || ld < N || ldbf < N || ld % 2 || ldbf % 2 || (pt_hi && !dst_hi))
     return set_error(MTT_ERR_BAD_SHAPE, "mtt_attn_softmax_bwd: bad arguments");
   if ((reinterpret_cast<uintptr_t>(S) & 7) || (reinterpret_cast<uintptr_t>(dP) & 7))
     return set_error(MTT_ERR_MISALIGNED, "mtt_attn_softmax_bwd: S / dP must be 8-byte aligned");
   attn_softmax_bwd_kernel<<<dim3((N + 63) / 64, BH), 256, 0, ST>>>(
-      S, dP, ld, N, scale, d_raw, T, static_cast<__nv_bfloat16*>(ds_hi), static_cast<__nv_bfloat16*>(ds_lo),
+      S, dP, delta, ld, N, scale, d_raw, T, static_cast<__nv_bfloat16*>(ds_hi), static_cast<__nv_bfloat16*>(ds_lo),
       static_cast<__nv_bfloat16*>(pt_hi), static_cast<__nv_bfloat16*>(pt_lo), static_cast<__nv_bfloat16*>(dst_hi),
       static_cast<__nv_bfloat16*>(dst_lo), ldbf);
   count_launch();

@@ -155,7 +155,8 @@ SYMBOLS = {
     "mtt_bn_act": (C.c_int, [_vp, _i64, _i64, _i32, _vp, _vp, _vp, _i32, _vp, _i64, _vp, _vp, _i64, _vp]),
     "mtt_bn_bwd_reduce": (C.c_int, [_vp, _i64, _vp, _i64, _i64, _i32, _vp, _vp, _vp, _i32, _vp, _vp]),
     "mtt_bn_bwd_apply": (C.c_int, [_vp, _i64, _vp, _i64, _i64, _i32, _vp, _vp, _vp, _i32, _vp, _f32, _vp, _i64, _vp]),
-    "mtt_attn_softmax_bwd": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _f32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
+    "mtt_attn_delta": (C.c_int, [_vp, _i64, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "mtt_attn_softmax_bwd": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _f32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
     "mtt_bilinear_bwd": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _i64, _i32, _vp]),
     "mtt_gate_bwd": (C.c_int, [_vp, _i64, _i64, _i64, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32,
                                _vp, _vp, _i64, _vp, _i64, _vp, _vp, _vp]),

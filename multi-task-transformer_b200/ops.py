@@ -681,11 +681,17 @@ def bn_bwd_apply(x, dy, mean_rstd, gamma, beta, act, sums, count, dx):
              "mtt_bn_bwd_apply")
 
 
-def attn_softmax_bwd(S, dP, *, BH, N, scale, d_raw, T, ds, pt=None, dst=None):
-    """S, dP fp32 [BH*N, ld] (read only) -> Splits ds [BH*N queries, >= N], and optionally pt = P^T, dst = dS^T
-    [BH*N keys, >= N queries] (same ld as ds)."""
+def attn_delta(dO, o, delta, *, B, N, H, head_dim):
+    """delta [B*H*N] = rowdot(dO, O) per head: dO fp32 [B*N, H*head_dim], o = the forward's attention output (Split)."""
+    _L.check(_L.load().mtt_attn_delta(_ptr(dO), _ld(dO), _ptr(o.hi), _ptr(o.lo), o.ld, B, N, H, head_dim, _ptr(delta),
+                                      _stream()), "mtt_attn_delta")
+
+
+def attn_softmax_bwd(S, dP, delta, *, BH, N, scale, d_raw, T, ds, pt=None, dst=None):
+    """S, dP fp32 [BH*N, ld] (read only), delta fp32 [BH*N] -> Splits ds [BH*N queries, >= N], and optionally pt = P^T,
+    dst = dS^T [BH*N keys, >= N queries] (same ld as ds)."""
     assert (pt is None) == (dst is None) and (pt is None or pt.ld == dst.ld == ds.ld)
-    _L.check(_L.load().mtt_attn_softmax_bwd(_ptr(S), _ptr(dP), _ld(S), BH, N, float(scale), _ptr(d_raw), T, _ptr(ds.hi),
+    _L.check(_L.load().mtt_attn_softmax_bwd(_ptr(S), _ptr(dP), _ptr(delta), _ld(S), BH, N, float(scale), _ptr(d_raw), T, _ptr(ds.hi),
                                             _ptr(ds.lo), _ptr(pt.hi) if pt is not None else None,
                                             _ptr(pt.lo) if pt is not None else None,
                                             _ptr(dst.hi) if dst is not None else None,

@@ -109,7 +109,7 @@ class TrainStep:
         self.ctx = None
         # use_graph: step() captures forward + criterion + reverse pass (about 5000 launches) into ONE CUDA graph per input
         # shape and replays it; clip + Adam stay outside (their bias-correction scalars change every step)
-        self.use_graph = bool(use_graph) and self.pg is None and self.dev.type == "cuda"
+        self.use_graph = bool(use_graph) and self.dev.type == "cuda"      # with a process group the NCCL calls are captured too
         self._graph = None
 
     # ---- small helpers -------------------------------------------------------------------------------------------------
@@ -444,6 +444,8 @@ class TrainStep:
         ops.colsum(dX, self.G_(bbp + "patch_embed.proj.bias"), accumulate=True, rows=Mp, in_group=P, src_group=N,
                    src_offset=T)
         self._bucket_ready(None)
+        if self.comm is not None:                       # the communication stream rejoins (required when the step is captured)
+            torch.cuda.current_stream(self.dev).wait_stream(self.comm)
         self.ctx = None
 
     def _heads_bwd(self, grad_out, dacc, B):
@@ -667,7 +669,9 @@ class TrainStep:
         _grouped(calls_s)
         _grouped(calls_p)
         dS, PT, dST = Split(BH * N, Np, dev, ns), Split(BH * N, Np, dev, ns), Split(BH * N, Np, dev, ns)
-        ops.attn_softmax_bwd(S, dP, BH=BH, N=N, scale=64 ** -0.5, d_raw=bc["d_logits"], T=T, ds=dS, pt=PT, dst=dST)
+        delta = _e(BH * N, device=dev)
+        ops.attn_delta(dao, bc["ao"], delta, B=B, N=N, H=H, head_dim=64)
+        ops.attn_softmax_bwd(S, dP, delta, BH=BH, N=N, scale=64 ** -0.5, d_raw=bc["d_logits"], T=T, ds=dS, pt=PT, dst=dST)
         del S, dP
         # operands transposed per image: [B][3C][Np] (q^T | k^T | v^T rows) and [B][C][Np] (dO^T)
         qkvT = Split(B * 3 * C, Np, dev, ns)

@@ -523,11 +523,16 @@ def install(mp):
         dz, xh = _bn_dz(x, dy, mean_rstd, gamma, beta, act)
         dx[:, :C_] = gamma * mean_rstd[C_:] * (dz - sums[:C_] / count - xh * sums[C_:] / count)
 
-    def attn_softmax_bwd(S, dP, *, BH, N, scale, d_raw, T, ds, pt=None, dst=None):
-        s_ = S[:, :N].reshape(BH, N, N).detach().clone().requires_grad_(True)
-        P = (s_ * scale).softmax(-1)
-        P.backward(dP[:, :N].reshape(BH, N, N).clone())
-        g = s_.grad
+    def attn_delta(dO, o, delta, *, B, N, H, head_dim):
+        Cd = H * head_dim
+        prod = (dO[:, :Cd] * _rsplit(o, Cd)).reshape(B, N, H, head_dim).sum(-1)         # [B, N, H]
+        delta.copy_(prod.permute(0, 2, 1).reshape(-1))
+
+    def attn_softmax_bwd(S, dP, delta, *, BH, N, scale, d_raw, T, ds, pt=None, dst=None):
+        # written from the kernel's contract: dS = scale * P * (dP - delta) with the GIVEN delta (the whole-step tests check
+        # that delta = rowdot(dO, O) makes this the softmax adjoint)
+        P = (S[:, :N].reshape(BH, N, N) * scale).softmax(-1)
+        g = scale * P * (dP[:, :N].reshape(BH, N, N) - delta.reshape(BH, N, 1))
         if d_raw is not None:
             g[:, :T, :] += d_raw.reshape(BH, T, N)
         _wsplit(ds, g.reshape(BH * N, N))

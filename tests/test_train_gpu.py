@@ -165,19 +165,34 @@ def test_batchnorm_train(both, cuda_dev, act):
 def test_attn_softmax_bwd(both, cuda_dev):
     ops, emu = both
     torch.manual_seed(6)
-    BH, N, T = 6, 77, 3          # two query tiles, the second ragged; odd N
-    ld = 80
+    B, H, N, T = 3, 2, 77, 3          # two query tiles, the second ragged; odd N
+    BH, ld = B * H, 80
     S, dP, dr = torch.randn(BH * N, ld) * 3, torch.randn(BH * N, ld), torch.randn(BH, T, N)
+    # delta from its definition rowdot(dO, O) with O = P V, dP = dO V^T (so the kernel output must equal the softmax adjoint)
+    V, dO = torch.randn(BH, N, 64), torch.randn(BH, N, 64)
+    P = (S[:, :N].reshape(BH, N, N) * 0.125).softmax(-1)
+    dP[:, :N] = (dO @ V.transpose(1, 2)).reshape(BH * N, N)
+    O = (P @ V).reshape(B, H, N, 64).permute(0, 2, 1, 3).reshape(B * N, H * 64)
+    dOf = dO.reshape(B, H, N, 64).permute(0, 2, 1, 3).reshape(B * N, H * 64).contiguous()
+    o_s = cpu_split(emu, O)
     res = []
     for dev, real in ((cuda_dev, True), ("cpu", False)):
+        f = (lambda n: getattr(ops, n)) if real else (lambda n: emu[n])
         s, d = S.clone().to(dev), dP.clone().to(dev)
+        delta = torch.empty(BH * N, device=dev)
+        f("attn_delta")(dOf.to(dev), to_dev(ops, o_s, dev), delta, B=B, N=N, H=H, head_dim=64)
         ds, pt, dst = (ops.Split(BH * N, ld, dev, 2, zero=True) for _ in range(3))
-        (ops.attn_softmax_bwd if real else emu["attn_softmax_bwd"])(s, d, BH=BH, N=N, scale=0.125, d_raw=dr.to(dev), T=T, ds=ds,
-                                                                    pt=pt, dst=dst)
+        f("attn_softmax_bwd")(s, d, delta, BH=BH, N=N, scale=0.125, d_raw=dr.to(dev), T=T, ds=ds, pt=pt, dst=dst)
         assert torch.equal(s.cpu(), S) and torch.equal(d.cpu(), dP)          # inputs are read only
-        res.append((ds.float()[:, :N], pt.float()[:, :N], dst.float()[:, :N]))
+        res.append((delta, ds.float()[:, :N], pt.float()[:, :N], dst.float()[:, :N]))
     for a, b in zip(*res):
-        assert relerr(a, b) < 2e-5
+        assert relerr(a, b) < 3e-5
+    # against torch autograd of softmax
+    s_ = S[:, :N].reshape(BH, N, N).clone().requires_grad_(True)
+    (s_ * 0.125).softmax(-1).backward(dP[:, :N].reshape(BH, N, N))
+    want = s_.grad.clone()
+    want[:, :T] += dr
+    assert relerr(res[0][1], want.reshape(BH * N, N)) < 1e-4
 
 
 @pytest.mark.parametrize("nchw", [True, False])
@@ -437,4 +452,4 @@ def test_graph_replay_equals_eager_steps(cuda_dev):
     # gradient up to atomics-order noise, and Adam turns that noise into +-lr steps)
     assert relerr(pg, pe) < 1e-3
     for k in be:
-        assert torch.allclose(be[k], bg[k], rtol=1e-5, atol=1e-6), k
+        assert torch.allclose(be[k], bg[k], rtol=2e-3, atol=1e-5), k      # three momentum updates of sums made with atomics
