@@ -452,4 +452,6 @@ def test_graph_replay_equals_eager_steps(cuda_dev):
     # gradient up to atomics-order noise, and Adam turns that noise into +-lr steps)
     assert relerr(pg, pe) < 1e-3
     for k in be:
-        assert torch.allclose(be[k], bg[k], rtol=2e-3, atol=1e-5), k      # three momentum updates of sums made with atomics
+        # the running MEAN in front of a BatchNorm contains the conv bias, whose zero gradient is noise that Adam turns into
+        # +-lr steps (lr = 1e-3 here, 2 steps before the last forward)
+        assert torch.allclose(be[k], bg[k], rtol=2e-3, atol=5e-3), k
