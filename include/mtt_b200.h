@@ -121,6 +121,13 @@ typedef struct {
    * [B,H,W] map land on the (dy,dx) phase of the [B,2H,2W] map: ConvTranspose2d(k2,s2) as four GEMMs
    * (TP taskprompter.py:704, DEConvHead). 0 / 1 = dense. */
   int32_t out_row_stride;
+  /* Optional stream-K workspace (NULL = off), mtt_gemm_streamk_bytes() bytes, 256-byte aligned, zero-filled ONCE before
+   * its first use (every launch leaves its flag words zero again) and not shared by launches that may run
+   * concurrently. With it, a problem that mtt_gemm puts on the CTA-pair 256x256 kernel splits the tiles of its ragged
+   * last round along K over all SM pairs instead of leaving most of them idle (204 qkv tiles on 74 pairs: 2.76 rounds
+   * of work in 2.8 instead of 3); the partial sums are added in a fixed order, so results are reproducible. */
+  void* sk_ws;
+  int64_t sk_ws_bytes;
 } mtt_gemm_desc;
 
 int mtt_gemm(const mtt_gemm_desc* d, mtt_stream_t stream);
@@ -137,6 +144,18 @@ int mtt_sum_partials(const float* partial, int32_t S, int64_t M, int32_t N, int6
  * 128x128 tiles, 2 = CTA pair (tcgen05 cta_group::2) 256x256 tiles, 3 = CTA pair 256x128 tiles.
  * All variants compute the same function; this is a tuning / testing knob. */
 void mtt_set_gemm_variant(int variant);
+/* Bytes of the stream-K workspace mtt_gemm_desc.sk_ws needs on the current device (flags + one fp32 256x256 partial
+ * tile per SM pair, ~19 MB on a B200); mtt_workspace_bytes already includes it for the operators that use it. */
+size_t mtt_gemm_streamk_bytes(void);
+/* 0 switches the stream-K schedule off (sk_ws is then ignored), anything else on (the default; also env
+ * MTT_GEMM_STREAMK). Tuning / testing knob: both settings compute the same function. */
+void mtt_set_gemm_streamk(int on);
+/* Test hook (no GPU needed): the work list of CTA pair `pair` of `pairs` for a problem of `tiles` 256x256 tiles that
+ * are `k_iters` k-blocks deep, computed by the code the kernel runs. pieces receives up to max_pieces triples
+ * (tile, first k-block, end k-block); returns the number of pieces of that pair. A piece that does not start at
+ * k-block 0 is a stream-K contribution to the pair that holds the tile's first k-block. */
+int mtt_debug_streamk_schedule(int32_t tiles, int32_t k_iters, int32_t pairs, int32_t pair, int32_t* pieces,
+                               int32_t max_pieces);
 
 /* ---- fused multi-head attention over the joint [prompts; patches] sequence ----------------
  * Replaces TP taskprompter.py:204-210 (raw = q k^T, softmax(raw*scale), attn @ v) and IP
@@ -296,7 +315,9 @@ int mtt_invpt_fuse_softmax(const float* raw, int32_t B, int32_t Lq, int32_t Tk, 
 /* ---- the named operators of SURVEY.md section 8(b) -----------------------------------------------------------
  * Each replaces one eager-op group of the reference block / decoder with a fixed launch sequence; intermediates
  * live in the caller's workspace (size from mtt_workspace_bytes, 256-byte aligned), so nothing is allocated and
- * the whole forward stays capturable in one CUDA graph.
+ * the whole forward stays capturable in one CUDA graph. A workspace is zero-filled ONCE by the caller when it is
+ * allocated (the LayerNorm-fronted operators keep their GEMMs' stream-K flag words in it: mtt_gemm_desc.sk_ws) and
+ * must not be shared by calls that can run concurrently on different streams.
  *
  * DEVIATIONS from the entry-point list SURVEY.md 8(b) sketched (all deliberate, same ownership / error / stream
  * rules): (1) attn_fwd, chan_prompt_logits, bilinear_up, invpt_attn, layernorm are the single-kernel entries above

@@ -160,10 +160,11 @@ size_t mtt_workspace_bytes(int32_t op, const mtt_shape* s) {
   if (!s) return 0;
   const int ns = s->nsplit == 1 ? 1 : 2;
   switch (op) {
-    case MTT_OP_LN_QKV:  // LN1 output, split [ns][rows][pad8(C)]
-      return align256(planes_bytes(ns, s->rows, pad8(s->C)));
-    case MTT_OP_LN_MLP_RESIDUAL:  // LN2 output + hidden activations
-      return align256(planes_bytes(ns, s->rows, pad8(s->C))) + align256(planes_bytes(ns, s->rows, pad8(s->hidden)));
+    case MTT_OP_LN_QKV:  // LN1 output, split [ns][rows][pad8(C)], then the GEMM's stream-K workspace
+      return align256(planes_bytes(ns, s->rows, pad8(s->C))) + align256(mtt_gemm_streamk_bytes());
+    case MTT_OP_LN_MLP_RESIDUAL:  // LN2 output + hidden activations, then the stream-K workspace of fc1 / fc2
+      return align256(planes_bytes(ns, s->rows, pad8(s->C))) + align256(planes_bytes(ns, s->rows, pad8(s->hidden))) +
+             align256(mtt_gemm_streamk_bytes());
     case MTT_OP_GATED_CONV1X1:  // two gated copies of the patch map per task: [task][spatial | channel][plane][rows][ld]
       return (size_t)(s->T > 0 ? s->T : 1) * 2 * align256(planes_bytes(ns, s->rows, pad8(s->C)));
     case MTT_OP_CONV3X3_BN_ACT:  // hidden map between the 3x3 and a fused 1x1 head
@@ -220,6 +221,8 @@ int mtt_ln_qkv(const float* x, int64_t ldx, const float* gamma, const float* bet
   g.out_hi = qkv_hi;
   g.out_lo = qkv_lo;
   g.ldo_bf = ldq;
+  g.sk_ws = static_cast<uint8_t*>(ws) + align256(planes_bytes(ns, s->rows, ldn));
+  g.sk_ws_bytes = (int64_t)mtt_gemm_streamk_bytes();
   return mtt_gemm(&g, stream);
 }
 
@@ -272,6 +275,9 @@ int mtt_ln_mlp_residual(float* x, int64_t ldx, const float* gamma, const float* 
   g.out_hi = h_hi;
   g.out_lo = h_lo;
   g.ldo_bf = ldh;
+  void* sk_ws = base + align256(planes_bytes(ns, s->rows, ldn)) + align256(planes_bytes(ns, s->rows, ldh));
+  g.sk_ws = sk_ws;
+  g.sk_ws_bytes = (int64_t)mtt_gemm_streamk_bytes();
   if ((rc = mtt_gemm(&g, stream))) return rc;
   mtt_gemm_desc g2 = {};
   g2.a_hi = h_hi;
@@ -287,6 +293,8 @@ int mtt_ln_mlp_residual(float* x, int64_t ldx, const float* gamma, const float* 
   g2.ldr = ldx;
   g2.out_f32 = x;
   g2.ldo_f32 = ldx;
+  g2.sk_ws = sk_ws;   // fc2 follows fc1 on the same stream: the flags are zero again when it starts
+  g2.sk_ws_bytes = (int64_t)mtt_gemm_streamk_bytes();
   return mtt_gemm(&g2, stream);
 }
 

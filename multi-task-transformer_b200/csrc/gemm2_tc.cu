@@ -14,6 +14,8 @@
 //     the smem-empty and accumulator-full barriers fire in BOTH CTAs;
 //   * each CTA's 8 epilogue warps drain their own TMEM slice and arrive on the LEADER's
 //     accumulator-empty barrier (16 arrivals).
+#include <stdlib.h>
+
 #include "gemm_common.cuh"
 
 namespace mtt {
@@ -34,9 +36,81 @@ __device__ __forceinline__ int pair_tile_n(const GemmParams& p, int nt, int bn2)
   return left >= bn2 ? bn2 : ((left + 15) & ~15);
 }
 
+// ---- stream-K tail (SK = true, single-problem kernel with 256-wide tiles) ------------------------------------------------
+// With T tiles on P pairs the plain persistent schedule runs ceil(T / P) rounds: 204 qkv tiles on 74 pairs are 3 rounds
+// for 2.76 rounds of work (fc1: 4 for 3.68, fc2: 1 for 0.92). Here the R = T mod P tiles that would form the ragged last
+// round (tile indices [0, R)) are split along K instead: their R * k_iters k-blocks are dealt out evenly, pair p taking
+// the contiguous range [p W / P, (p + 1) W / P) of W = R * k_iters, which touches at most two tiles. The remaining
+// T - R tiles run one pair per tile as before (tile R + p + j P). Every pair does its stream-K range FIRST.
+//   * a range piece that starts inside a tile (k0 > 0) is a CONTRIBUTION: the epilogue warps dump the raw fp32
+//     accumulator to this pair's slot of p.sk_part and publish it per warp (release store to p.sk_flags);
+//   * the piece that holds a tile's first k-block OWNS the tile: its epilogue warps wait for the warps of the following
+//     pairs whose ranges end the tile (a contribution is always a pair's first piece, so it never waits on anything),
+//     add their partials in pair order (a fixed order: results are reproducible run to run) and run the fused epilogue.
+//     The owner resets each flag it consumed, so the flag array is all-zero again when the launch retires.
+// All pairs are co-resident (grid <= number of SM pairs, one CTA per SM), so the owner's spin cannot starve a contributor.
+struct SkSched {
+  int n_sk;                  // 0..2 stream-K pieces of this pair
+  int tile0, k0_0, k1_0;     // first piece (may start inside its tile)
+  int k1_1;                  // second piece: tile0 + 1, k-blocks [0, k1_1)
+  int dp_first, dp_step;     // whole tiles: dp_first + j * dp_step < num_tiles
+  int n_seg;
+  long long W;               // total stream-K k-blocks
+};
+template <bool SK>
+__host__ __device__ __forceinline__ SkSched sk_schedule(const GemmParams& p, int pair, int num_pairs, int num_tiles, int k_iters) {
+  SkSched s;
+  s.n_sk = 0;
+  s.tile0 = s.k0_0 = s.k1_0 = s.k1_1 = 0;
+  s.W = 0;
+  s.dp_first = pair;
+  s.dp_step = num_pairs;
+  if (SK && p.sk_tiles > 0) {
+    s.W = (long long)p.sk_tiles * k_iters;
+    const long long b = (long long)pair * s.W / num_pairs, e = (long long)(pair + 1) * s.W / num_pairs;
+    if (e > b) {
+      const int t0 = (int)(b / k_iters);
+      const long long t0_end = (long long)(t0 + 1) * k_iters;
+      s.tile0 = t0;
+      s.k0_0 = (int)(b - (long long)t0 * k_iters);
+      s.k1_0 = (int)((e < t0_end ? e : t0_end) - (long long)t0 * k_iters);
+      s.n_sk = 1;
+      if (e > t0_end) {
+        s.k1_1 = (int)(e - t0_end);
+        s.n_sk = 2;
+      }
+    }
+    s.dp_first = p.sk_tiles + pair;
+  }
+  const int left = num_tiles - s.dp_first;
+  s.n_seg = s.n_sk + (left > 0 ? (left + s.dp_step - 1) / s.dp_step : 0);
+  return s;
+}
+// piece `si` of a pair's schedule: tile index and k-block range [k0, k1)
+__host__ __device__ __forceinline__ void sk_piece(const SkSched& s, int si, int k_iters, int& tile, int& k0, int& k1) {
+  if (si < s.n_sk) {
+    tile = s.tile0 + si;
+    k0 = si == 0 ? s.k0_0 : 0;
+    k1 = si == 0 ? s.k1_0 : s.k1_1;
+  } else {
+    tile = s.dp_first + (si - s.n_sk) * s.dp_step;
+    k0 = 0;
+    k1 = k_iters;
+  }
+}
+__device__ __forceinline__ void sk_flag_publish(unsigned int* f) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(f), "r"(1u) : "memory");
+}
+__device__ __forceinline__ unsigned int sk_flag_peek(const unsigned int* f) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+  return v;
+}
+
 // The kernel body, shared by the single-problem kernel (GROUPED = false) and the grouped one (tile -> (problem, tile)).
-template <int NSPLIT, int BN2, bool GROUPED>
+template <int NSPLIT, int BN2, bool GROUPED, bool SK>
 __device__ __forceinline__ void gemm2_tc_body(const CUtensorMap (*maps)[4], const GemmParams& p, const GemmGroup* grp) {
+  static_assert(!SK || (BN2 == 256 && !GROUPED), "stream-K: single-problem kernel with 256-wide tiles only");
   using Cfg = Gemm2Cfg<NSPLIT>;
   constexpr int ST = Cfg::kStages;
   constexpr int BNH = BN2 / 2;                       // weight rows held by each CTA
@@ -61,6 +135,7 @@ __device__ __forceinline__ void gemm2_tc_body(const CUtensorMap (*maps)[4], cons
   const int tpp = pairs_m * p.tiles_n;                        // pair tiles per problem
   const int num_tiles = GROUPED ? tpp * grp->count : tpp;
   const int k_iters = p.taps * p.num_kb;
+  const SkSched sched = sk_schedule<SK>(p, pair, num_pairs, num_tiles, k_iters);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&maps[0][0]);
@@ -93,7 +168,9 @@ __device__ __forceinline__ void gemm2_tc_body(const CUtensorMap (*maps)[4], cons
       int stage = 0;
       uint32_t phase = 0;
       const uint32_t stage_tx = 2 * NSPLIT * (p.a_box_bytes + kBTile);  // both CTAs' bytes
-      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+      for (int si = 0; si < sched.n_seg; ++si) {
+        int tile, kbeg, kend;
+        sk_piece(sched, si, k_iters, tile, kbeg, kend);
         const int g = GROUPED ? tile / tpp : 0;
         const int tl = GROUPED ? tile - g * tpp : tile;
         const int ms = (tl % pairs_m) * 2 + (int)rank;
@@ -103,7 +180,7 @@ __device__ __forceinline__ void gemm2_tc_body(const CUtensorMap (*maps)[4], cons
         const CUtensorMap* tmA_lo = &maps[g][1];
         const CUtensorMap* tmB_hi = &maps[g][2];
         const CUtensorMap* tmB_lo = &maps[g][3];
-        for (int ki = 0; ki < k_iters; ++ki) {
+        for (int ki = kbeg; ki < kend; ++ki) {
           const int tap = ki / p.num_kb, kb = ki - tap * p.num_kb;
           const int dy = (tap / p.ksize - p.ksize / 2) * p.dil;
           const int dx = (tap % p.ksize - p.ksize / 2) * p.dil;
@@ -134,8 +211,9 @@ __device__ __forceinline__ void gemm2_tc_body(const CUtensorMap (*maps)[4], cons
     if (leader) {
       int stage = 0;
       uint32_t phase = 0;
-      int it = 0;
-      for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
+      for (int it = 0; it < sched.n_seg; ++it) {
+        int tile, kbeg, kend;
+        sk_piece(sched, it, k_iters, tile, kbeg, kend);
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
         mbar_wait(&tempty_bar[as], aphase ^ 1);
@@ -143,8 +221,8 @@ __device__ __forceinline__ void gemm2_tc_body(const CUtensorMap (*maps)[4], cons
         const uint32_t tacc = tmem_base + as * BN2;
         const uint32_t idesc = umma_idesc_bf16(256, pair_tile_n(p, (GROUPED ? tile % tpp : tile) / pairs_m, BN2), 0);
         uint32_t accum = 0;
-        int kb = 0;
-        for (int ki = 0; ki < k_iters; ++ki) {
+        int kb = kbeg % p.num_kb;
+        for (int ki = kbeg; ki < kend; ++ki) {
           const int nks = (++kb == p.num_kb) ? p.k_last_steps : BK / 16;  // zero-padded tail of K: no MMAs
           if (kb == p.num_kb) kb = 0;
           mbar_wait(&full_bar[stage], phase);
@@ -184,8 +262,9 @@ __device__ __forceinline__ void gemm2_tc_body(const CUtensorMap (*maps)[4], cons
     const int half = (warp - 2) >> 2;
     const int row = q * 32 + lane;
     constexpr int kColsPerWarp = BN2 / 2;  // 128 or 64 columns per epilogue warp
-    int it = 0;
-    for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
+    for (int it = 0; it < sched.n_seg; ++it) {
+      int tile, kbeg, kend;
+      sk_piece(sched, it, k_iters, tile, kbeg, kend);
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       const int g = GROUPED ? tile / tpp : 0;
@@ -219,6 +298,11 @@ __device__ __forceinline__ void gemm2_tc_body(const CUtensorMap (*maps)[4], cons
           epilogue_store32(pq, r1, nbase + 32, ri);
         }
       } else {
+        // stream-K roles of this piece: a contribution starts inside its tile; the owner holds the tile's first
+        // k-block and, unless it holds all of them, adds the partials of the pairs that follow it
+        const bool sk_contrib = SK && kbeg > 0;
+        const bool sk_owner = SK && kbeg == 0 && kend < k_iters;
+        const long long tile_kend = (long long)(tile + 1) * k_iters;
         // 128 columns per warp: two 64-column halves to keep the register footprint at 64 accumulators
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
@@ -231,11 +315,66 @@ __device__ __forceinline__ void gemm2_tc_body(const CUtensorMap (*maps)[4], cons
             __syncwarp();
             if (lane == 0) mbar_arrive_leader(&tempty_bar[as]);
           }
-          if (ri.ok && !(p.debug & 2)) {
-            epilogue_store32(pq, r0, nbase + hh * 64, ri);
-            epilogue_store32(pq, r1, nbase + hh * 64 + 32, ri);
+          if (SK && sk_contrib) {
+            if (ri.ok) {
+              float* dst = p.sk_part + ((size_t)(pair * 2 + (int)rank) * BM + row) * 256 + half * kColsPerWarp + hh * 64;
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                U32x8 a, b;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  a.v[j] = r0[c * 8 + j];
+                  b.v[j] = r1[c * 8 + j];
+                }
+                st_global_v8(dst + c * 8, a);
+                st_global_v8(dst + 32 + c * 8, b);
+              }
+            }
+          } else {
+            if (SK && sk_owner) {
+              for (int pp = pair + 1; pp < num_pairs && (long long)pp * sched.W / num_pairs < tile_kend; ++pp) {
+                unsigned int* flag = p.sk_flags + (pp * 2 + (int)rank) * kEpiWarps + (warp - 2);
+                if (hh == 0) {
+                  if (lane == 0) {
+                    while (sk_flag_peek(flag) == 0) {
+                    }
+                  }
+                  __syncwarp();
+                  __threadfence();
+                }
+                if (ri.ok) {
+                  const float4* src = reinterpret_cast<const float4*>(
+                      p.sk_part + ((size_t)(pp * 2 + (int)rank) * BM + row) * 256 + half * kColsPerWarp + hh * 64);
+#pragma unroll
+                  for (int c = 0; c < 8; ++c) {
+                    const float4 a = __ldcg(src + c), b = __ldcg(src + 8 + c);
+                    r0[c * 4 + 0] = __float_as_uint(__uint_as_float(r0[c * 4 + 0]) + a.x);
+                    r0[c * 4 + 1] = __float_as_uint(__uint_as_float(r0[c * 4 + 1]) + a.y);
+                    r0[c * 4 + 2] = __float_as_uint(__uint_as_float(r0[c * 4 + 2]) + a.z);
+                    r0[c * 4 + 3] = __float_as_uint(__uint_as_float(r0[c * 4 + 3]) + a.w);
+                    r1[c * 4 + 0] = __float_as_uint(__uint_as_float(r1[c * 4 + 0]) + b.x);
+                    r1[c * 4 + 1] = __float_as_uint(__uint_as_float(r1[c * 4 + 1]) + b.y);
+                    r1[c * 4 + 2] = __float_as_uint(__uint_as_float(r1[c * 4 + 2]) + b.z);
+                    r1[c * 4 + 3] = __float_as_uint(__uint_as_float(r1[c * 4 + 3]) + b.w);
+                  }
+                }
+                if (hh == 1) {   // both halves read: hand the flag back as zero for the next launch
+                  __syncwarp();
+                  if (lane == 0) *reinterpret_cast<volatile unsigned int*>(flag) = 0u;
+                }
+              }
+            }
+            if (ri.ok && !(p.debug & 2)) {
+              epilogue_store32(pq, r0, nbase + hh * 64, ri);
+              epilogue_store32(pq, r1, nbase + hh * 64 + 32, ri);
+            }
           }
           __syncwarp();
+        }
+        if (SK && sk_contrib) {   // this warp's 32 rows x 128 columns of the partial are written: publish them
+          __threadfence();
+          __syncwarp();
+          if (lane == 0) sk_flag_publish(p.sk_flags + (pair * 2 + (int)rank) * kEpiWarps + (warp - 2));
         }
       }
       __syncwarp();
@@ -257,14 +396,21 @@ struct Gemm2Maps1 {
 template <int NSPLIT, int BN2>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 gemm2_tc_kernel(const __grid_constant__ Gemm2Maps1 maps, const GemmParams p) {
-  gemm2_tc_body<NSPLIT, BN2, false>(maps.m, p, nullptr);
+  gemm2_tc_body<NSPLIT, BN2, false, false>(maps.m, p, nullptr);
+}
+
+// the same kernel with the stream-K tail (separate instantiation: the plain kernel keeps its register budget)
+template <int NSPLIT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+gemm2_tc_streamk_kernel(const __grid_constant__ Gemm2Maps1 maps, const GemmParams p) {
+  gemm2_tc_body<NSPLIT, 256, false, true>(maps.m, p, nullptr);
 }
 
 template <int NSPLIT, int BN2>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 gemm2_tc_grouped_kernel(const __grid_constant__ GemmGroupMaps maps, const __grid_constant__ GemmGroup grp,
                         const GemmParams p) {
-  gemm2_tc_body<NSPLIT, BN2, true>(maps.m, p, &grp);
+  gemm2_tc_body<NSPLIT, BN2, true, false>(maps.m, p, &grp);
 }
 
 template <int NSPLIT, int BN2>
@@ -287,6 +433,53 @@ static int launch_gemm2(const CUtensorMap* maps, const GemmParams& p, cudaStream
   for (int i = 0; i < 4; ++i) gm.m[0][i] = maps[i];
   gemm2_tc_kernel<NSPLIT, BN2><<<pairs * 2, kGemmThreads, Cfg::kSmemBytes, stream>>>(gm, p);
   return check_launch("mtt_gemm(cta pair)");
+}
+
+// Stream-K launch: all SM pairs, the ragged last round (p.sk_tiles tiles) split along K (see sk_schedule above).
+template <int NSPLIT>
+static int launch_gemm2_streamk(const CUtensorMap* maps, const GemmParams& p, int pairs, cudaStream_t stream) {
+  using Cfg = Gemm2Cfg<NSPLIT>;
+  static bool attr_set[kMaxDevices] = {};
+  const int dev_ = current_device();
+  if (!attr_set[dev_]) {
+    cudaError_t e = cudaFuncSetAttribute(gemm2_tc_streamk_kernel<NSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::kSmemBytes);
+    if (e != cudaSuccess)
+      return set_error(MTT_ERR_LAUNCH, "gemm2(stream-K): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr_set[dev_] = true;
+  }
+  Gemm2Maps1 gm;
+  for (int i = 0; i < 4; ++i) gm.m[0][i] = maps[i];
+  gemm2_tc_streamk_kernel<NSPLIT><<<pairs * 2, kGemmThreads, Cfg::kSmemBytes, stream>>>(gm, p);
+  return check_launch("mtt_gemm(cta pair, stream-K)");
+}
+
+static int g_streamk = -1;  // -1: read MTT_GEMM_STREAMK once (default on); 0 = off
+void set_gemm_streamk(int on) { g_streamk = on ? 1 : 0; }
+
+// How many tiles of a `tiles`-tile, k_iters-deep problem go to the stream-K schedule on `pairs` CTA pairs (0 = none):
+// the ragged last round, when splitting it saves at least 1/16 of a round and leaves every pair >= 4 k-blocks.
+int streamk_tiles(int tiles, int k_iters, int pairs) {
+  if (g_streamk < 0) {
+    const char* e = getenv("MTT_GEMM_STREAMK");
+    g_streamk = e ? (atoi(e) != 0) : 1;
+  }
+  if (!g_streamk || pairs < 2 || pairs * 2 * kEpiWarps * 4 > (int)kSkFlagBytes) return 0;
+  const int r = tiles % pairs;
+  if (r == 0 || (pairs - r) * 16 < pairs || (long long)r * k_iters / pairs < 4) return 0;
+  return r;
+}
+
+// Test hook (mtt_debug_streamk_schedule): the pieces pair `pair` of `pairs` runs, from the same code the kernel uses.
+int streamk_schedule_host(int tiles, int k_iters, int pairs, int pair, int* out, int max_pieces) {
+  GemmParams p = {};
+  p.sk_tiles = streamk_tiles(tiles, k_iters, pairs);
+  const int num_pairs = p.sk_tiles > 0 ? pairs : (tiles < pairs ? tiles : pairs);
+  if (pair >= num_pairs) return 0;
+  const SkSched s = sk_schedule<true>(p, pair, num_pairs, tiles, k_iters);
+  int n = 0;
+  for (int si = 0; si < s.n_seg && n < max_pieces; ++si, ++n) sk_piece(s, si, k_iters, out[3 * n], out[3 * n + 1], out[3 * n + 2]);
+  return s.n_seg;
 }
 
 template <int NSPLIT>
@@ -337,6 +530,21 @@ int launch_gemm_2cta(const mtt_gemm_desc* d, int bn2, cudaStream_t stream) {
   int rc = gemm_prepare(d, bn2 / 2, p, maps);
   if (rc) return rc;
   p.tiles_n = (d->N + bn2 - 1) / bn2;
+  if (bn2 == 256 && d->sk_ws) {
+    // the caller lent a stream-K workspace (mtt_gemm_streamk_bytes): split the ragged last round of tiles along K
+    const int pairs = sm_count() / 2;
+    const int tiles = ((p.tiles_m + 1) / 2) * p.tiles_n;
+    const int r = streamk_tiles(tiles, p.taps * p.num_kb, pairs);
+    if (r > 0) {
+      if ((size_t)d->sk_ws_bytes < sk_workspace_bytes(pairs) || (reinterpret_cast<uintptr_t>(d->sk_ws) & 255))
+        return set_error(MTT_ERR_BAD_SHAPE, "mtt_gemm: sk_ws of %lld bytes (256-byte aligned) < required %zu "
+                         "(mtt_gemm_streamk_bytes)", (long long)d->sk_ws_bytes, sk_workspace_bytes(pairs));
+      p.sk_tiles = r;
+      p.sk_flags = static_cast<unsigned int*>(d->sk_ws);
+      p.sk_part = reinterpret_cast<float*>(static_cast<uint8_t*>(d->sk_ws) + kSkFlagBytes);
+      return d->nsplit == 2 ? launch_gemm2_streamk<2>(maps, p, pairs, stream) : launch_gemm2_streamk<1>(maps, p, pairs, stream);
+    }
+  }
   if (bn2 == 256)
     return d->nsplit == 2 ? launch_gemm2<2, 256>(maps, p, stream) : launch_gemm2<1, 256>(maps, p, stream);
   return d->nsplit == 2 ? launch_gemm2<2, 128>(maps, p, stream) : launch_gemm2<1, 128>(maps, p, stream);

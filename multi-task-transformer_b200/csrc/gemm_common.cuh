@@ -37,7 +37,16 @@ struct GemmParams {
   int vec32_ok;  // every epilogue pointer / stride allows 32-byte accesses
   int a_groups_per_tile;  // >0: A rows are gathered in groups through a rank-3 tensor map
   int debug;              // profiling aid (env MTT_GEMM_DEBUG): bit0 = skip TMA loads, bit1 = skip global stores
+  // stream-K tail of the CTA-pair kernel (gemm2_tc.cu): the first sk_tiles tiles are split along K over ALL pairs
+  int sk_tiles;           // 0: every tile is computed by one pair
+  float* sk_part;         // [pair][cta rank][128 rows][256 columns] fp32 partial accumulators
+  unsigned int* sk_flags; // [pair][cta rank][epilogue warp]: 1 = that warp's slice of the partial is published
 };
+
+// Stream-K workspace of the CTA-pair kernel for `pairs` CTA pairs: flags first (zero before the first launch and
+// left zero by every launch), then one 256 x 256 fp32 partial tile per pair.
+constexpr size_t kSkFlagBytes = 16384;  // up to 256 pairs x 2 CTAs x 8 warps x 4 bytes
+constexpr size_t sk_workspace_bytes(int pairs) { return kSkFlagBytes + (size_t)pairs * 256 * 256 * 4; }
 
 // Grouped launch (mtt_gemm_grouped): up to kMaxGroup problems of IDENTICAL geometry (M, N, K, mode, conv shape, nsplit,
 // activation, row regrouping) that differ only in their operand / bias / residual / output pointers run as ONE
@@ -255,5 +264,8 @@ int launch_gemm_1cta(const mtt_gemm_desc* d, cudaStream_t stream);
 int launch_gemm_1cta_grouped(const mtt_gemm_desc* d, int count, cudaStream_t stream);
 int launch_gemm_2cta_grouped(const mtt_gemm_desc* d, int count, cudaStream_t stream);
 int launch_gemm_2cta(const mtt_gemm_desc* d, int bn2, cudaStream_t stream);
+void set_gemm_streamk(int on);
+int streamk_tiles(int tiles, int k_iters, int pairs);
+int streamk_schedule_host(int tiles, int k_iters, int pairs, int pair, int* out, int max_pieces);
 
 }  // namespace mtt

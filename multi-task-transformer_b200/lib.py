@@ -25,6 +25,7 @@ class GemmDesc(C.Structure):
         ("in_group", C.c_int32), ("out_group", C.c_int32), ("out_offset", C.c_int32),
         ("a_group_rows", C.c_int32), ("a_group_stride", C.c_int64),
         ("out_row_stride", C.c_int32),
+        ("sk_ws", C.c_void_p), ("sk_ws_bytes", C.c_int64),
     ]
 
 
@@ -82,6 +83,9 @@ SYMBOLS = {
     "mtt_gemm_grouped": (C.c_int, [C.POINTER(GemmDesc), _i32, _vp]),
     "mtt_sum_partials": (C.c_int, [_vp, _i32, _i64, _i32, _i64, _vp, _vp, _i64, _vp]),
     "mtt_set_gemm_variant": (None, [C.c_int]),
+    "mtt_gemm_streamk_bytes": (C.c_size_t, []),
+    "mtt_set_gemm_streamk": (None, [C.c_int]),
+    "mtt_debug_streamk_schedule": (C.c_int, [_i32, _i32, _i32, _i32, C.POINTER(C.c_int32), _i32]),
     "mtt_attention": (C.c_int, [C.POINTER(AttnDesc), _vp]),
     "mtt_set_attention_variant": (None, [C.c_int]),
     "mtt_set_attention_trace": (None, [C.c_void_p]),

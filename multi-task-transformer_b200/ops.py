@@ -85,16 +85,19 @@ def layernorm(x, gamma, beta, eps, out_f32=None, out_split=None):
 
 def gemm(a, w, *, M=None, N=None, K=None, bias=None, act=ACT_NONE, residual=None, res_row_mod=0,
          out_f32=None, out_split=None, out_col_offset=0, regroup=None, conv=None, a_row_offset=0,
-         a_gather=None, w_col_offset=0, a_col_offset=0, w_row_offset=0, out_row_offset=0):
+         a_gather=None, w_col_offset=0, a_col_offset=0, w_row_offset=0, out_row_offset=0, sk_ws=None):
     """D = act(A @ W^T + bias) + residual on the tcgen05 GEMM.
 
     a: Split [M, K] (or NHWC activation [B*H*W, C] when ``conv=(B, H, W, ksize, dil)``);
     w: Split [N, K] (conv: [N, ksize*ksize*cin_pad]); outputs: fp32 tensor and/or Split.
     regroup=(in_group, out_group, out_offset[, row_stride]) scatters output rows; a_gather=(group_rows,
-    group_stride) gathers A rows in groups (M must be given); w_col_offset selects a K-slice of a wider packed W."""
+    group_stride) gathers A rows in groups (M must be given); w_col_offset selects a K-slice of a wider packed W.
+    sk_ws: optional stream-K workspace (streamk_workspace(device)); see mtt_gemm_desc.sk_ws."""
     d = _L.GemmDesc()
     _fill_gemm_desc(d, a, w, M, N, K, bias, act, residual, res_row_mod, out_f32, out_split, out_col_offset, regroup, conv,
                     a_row_offset, a_gather, w_col_offset, a_col_offset, w_row_offset, out_row_offset)
+    if sk_ws is not None:
+        d.sk_ws, d.sk_ws_bytes = sk_ws.data_ptr(), sk_ws.numel()
     rc = _L.load().mtt_gemm(C.byref(d), _stream())
     _L.check(rc, "mtt_gemm")
 
@@ -186,6 +189,17 @@ def attention(qkv, out, *, B, N, H, scale, prompt_logits=None, T=0):
     d.B, d.N, d.H, d.T, d.nsplit, d.scale = B, N, H, T, nsplit, float(scale)
     rc = _L.load().mtt_attention(C.byref(d), _stream())
     _L.check(rc, "mtt_attention")
+
+
+def streamk_workspace(device):
+    """A zero-filled stream-K workspace for gemm(sk_ws=...): one per stream that issues such launches."""
+    with torch.cuda.device(device):
+        return workspace(_L.load().mtt_gemm_streamk_bytes(), device)
+
+
+def set_gemm_streamk(on):
+    """False switches the stream-K schedule of the CTA-pair GEMM off (tuning / testing knob; env MTT_GEMM_STREAMK)."""
+    _L.load().mtt_set_gemm_streamk(int(bool(on)))
 
 
 def set_gemm_variant(v):
@@ -405,8 +419,9 @@ def workspace_bytes(op, **shape):
 
 
 def workspace(nbytes, device):
-    """A 256-byte aligned byte buffer (torch's caching allocator aligns to 512)."""
-    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+    """A 256-byte aligned, ZERO-FILLED byte buffer (torch's caching allocator aligns to 512). Zero because the stream-K
+    flag words inside the LayerNorm-fronted operators' workspaces must start at zero (include/mtt_b200.h, sk_ws)."""
+    return torch.zeros(max(int(nbytes), 256), dtype=torch.uint8, device=device)
 
 
 def ws_split_view(ws, byte_offset, rows, cols, nsplit):

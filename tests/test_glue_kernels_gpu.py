@@ -12,6 +12,7 @@ Tolerance: split outputs carry 16 significant bits (2^-17 relative), fp32 output
 import pytest
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
 
 pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600)]
 
@@ -200,6 +201,28 @@ def test_bilinear_forms(both, cuda_dev, h, w, H2, W2):
     emu["bilinear"](x.cpu(), x.stride(0), B, h, w, C, H2, W2, out_f32=racc, **kw2)
     torch.cuda.synchronize()
     assert relerr(acc, racc) < 1e-5
+
+
+@pytest.mark.parametrize("h,w,H2,W2,C,pad", [(32, 32, 128, 128, 350, 2), (9, 7, 18, 37, 21, 0), (16, 24, 40, 50, 130, 3),
+                                             (20, 33, 10, 17, 66, 0)])
+def test_bilinear_runs(both, cuda_dev, h, w, H2, W2, C, pad):
+    """The NHWC form walks runs of 16 output pixels per warp with the corner columns kept in registers: several 64-channel
+    chunks (C = 350: the last one partial), odd C (a single-channel lane), odd row strides (scalar loads), rows that are
+    not a multiple of the run length, x2 / x4 / fractional up-sampling and down-sampling."""
+    ops, emu = both
+    torch.manual_seed(5)
+    B = 2
+    x = rnd(B * h * w, C + pad, dev=cuda_dev)
+    o32 = torch.zeros(B * H2 * W2, C + 1, device=cuda_dev)
+    osp = ops.Split(B * H2 * W2, C, cuda_dev, zero=True)
+    ops.bilinear(x, x.stride(0), B, h, w, C, H2, W2, out_f32=o32, out_split=osp)
+    r32, rsp = torch.zeros(B * H2 * W2, C + 1), cpu_split(ops, osp)
+    emu["bilinear"](x.cpu(), x.stride(0), B, h, w, C, H2, W2, out_f32=r32, out_split=rsp)
+    torch.cuda.synchronize()
+    ref = F.interpolate(x[:, :C].reshape(B, h, w, C).permute(0, 3, 1, 2).double().cpu(), size=(H2, W2), mode="bilinear",
+                        align_corners=False).permute(0, 2, 3, 1).reshape(B * H2 * W2, C)
+    assert relerr(o32[:, :C], ref) < 1e-5 and (o32[:, C:] == 0).all()
+    assert relerr(o32, r32) < 1e-5 and relerr(osp.float(), rsp.float()) < 2e-5
 
 
 @pytest.mark.parametrize("kind,C", [(0, 7), (1, 1), (2, 2), (3, 3), (4, 1)])

@@ -133,6 +133,55 @@ def test_gemm_block_shapes(cuda_dev, nsplit, gemm_variant):
     _gemm_case(cuda_dev, 1029, 1024, 4096, nsplit, True, ops.ACT_NONE, True)
 
 
+@pytest.mark.parametrize("nsplit", [2, 1])
+@pytest.mark.parametrize("M,N,K,act,residual", [(4116, 3072, 1024, 0, False), (4116, 4096, 1024, 1, False),
+                                                (4116, 1024, 4096, 0, True), (2058, 3072, 1024, 0, False),
+                                                (1029, 1024, 4096, 0, True), (700, 1000, 2368, 2, True)],
+                         ids=["qkv_bs4", "fc1_bs4", "fc2_bs4", "qkv_bs2", "fc2_bs1", "ragged"])
+def test_gemm_streamk(cuda_dev, nsplit, M, N, K, act, residual):
+    """The stream-K schedule of the CTA-pair kernel (mtt_gemm_desc.sk_ws) against fp64 and against the plain schedule:
+    same function, reproducible bit for bit from launch to launch, flag words handed back as zero."""
+    import ctypes as C
+
+    from mtt_b200 import lib, ops
+
+    dev = cuda_dev
+    L = lib.load()
+    pairs = torch.cuda.get_device_properties(dev).multi_processor_count // 2
+    tiles = ((M + 255) // 256) * ((N + 255) // 256)
+    buf = (C.c_int32 * 96)()
+    pieces = [L.mtt_debug_streamk_schedule(tiles, (K + 63) // 64, pairs, p, buf, 32) for p in range(pairs)]
+    assert max(pieces) >= 1
+    torch.manual_seed(M + N + K)
+    a = torch.randn(M, K, device=dev)
+    w = torch.randn(N, K, device=dev) * 0.05
+    bs = torch.randn(N, device=dev)
+    res = torch.randn(M, N, device=dev) if residual else None
+    A, Wp = ops.split_f32(a, nsplit), ops.split_f32(w, nsplit)
+    ws = ops.streamk_workspace(dev)
+    ops.set_gemm_variant(2)
+    try:
+        outs = []
+        for use_sk in (True, True, False):
+            of = torch.full((M, N), float("nan"), device=dev)
+            osp = ops.Split(M, N, dev, nsplit, zero=True)
+            ops.gemm(A, Wp, bias=bs, act=act, residual=res, out_f32=of, out_split=osp, sk_ws=ws if use_sk else None)
+            torch.cuda.synchronize()
+            outs.append((of, osp.buf.clone()))
+            assert int(ws[:16384].view(torch.int32).abs().sum()) == 0, "stream-K flags must be zero after a launch"
+    finally:
+        ops.set_gemm_variant(0)
+    ref = a.double().cpu() @ w.double().cpu().t() + bs.double().cpu()
+    ref = F.gelu(ref) if act == 1 else F.relu(ref) if act == 2 else ref
+    if residual:
+        ref = ref + res.double().cpu()
+    for of, _ in outs:
+        assert relerr(of, ref) < TOL[nsplit]
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1]), "stream-K must be reproducible"
+    # against the one-pair-per-tile schedule: only the fp32 summation order of the split tiles differs
+    assert relerr(outs[0][0], outs[2][0].double()) < 1e-5
+
+
 def test_gemm_regroup_and_rowmod(cuda_dev, gemm_variant):
     from mtt_b200 import ops
 
