@@ -432,58 +432,87 @@ def run_ours(args):
     e2e_ms = max_over_ranks(max(s2.elapsed_time(e2), 0.0), world, dev)
     e2e_value = world * B * args.steps / (e2e_ms * 1e-3)
 
-    if rank != 0:
-        D.teardown(world)
-        return
-
-    peaks, peak_src = load_peaks()
-    roof = gemm_roofline(model, plan, dev_in[0], peaks, peak_src)
-    gflop_img = GFLOP_PER_IMAGE.get(args.config)
-    tot_gflop = gflop_img * B if gflop_img else None
-    line = {
-        "metric": "images/sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "bf16x3 (split-bf16 operands, fp32 accumulate)" if nsplit == 2 else "bf16",
-        "data": "synthetic",
-        "config": {
-            "workload": f"{WORKLOAD[args.config]}, {args.config}, bs {B}/GPU, random-init weights, eval",
-            "global_batch": world * B, "parallelism": f"dp{world} (batch-sharded forward, no collective)",
-            "precision_mode": args.mode,
-            "l2": "no explicit flush: each step streams 1.6 GB of packed weights plus ~1 GB of activations "
-                  "(>> 126 MB L2) and the input rotates over 4 buffers",
-        },
-        "clocks": clocks,
-        "repeats": {"n": len(regions), "steps_each": args.steps, "reported": "median region",
-                    "images_per_s": [world * B * args.steps / (r * 1e-3) for r in regions]},
-        "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": in_bytes,
-                "d2h_bytes_per_step": out_bytes, "ms_per_step": e2e_ms / args.steps, "wall_ms_per_step": wall_ms / args.steps,
-                "note": "pinned-host input -> H2D -> model(x) -> all task logits D2H (overlapped with the next step)"},
-        "gpu_launches": int(launches_per_fwd * args.steps),
-        "launches_per_step": int(launches_per_fwd),
-        "roofline": roof,
-    }
-    if gflop_img:
-        line["model_tflops_algorithmic"] = value * gflop_img / 1e3 / world
-        peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
-        line["whole_step"] = {"gflop_per_step_algorithmic": tot_gflop, "tflops_algorithmic": value * gflop_img / 1e3 / world,
-                              "frac_of_sustained_bf16_peak": value * gflop_img / 1e3 / world / peak,
-                              "note": "every FLOP of the reference forward (SURVEY.md 8d) over the whole step time"}
-    if world == 1 and not args.no_gpu_eager:
-        del model, plan
-        torch.cuda.empty_cache()
+    want_train = (not args.no_train_leg and family(args.config)[2] == "oracle.taskprompter_ref"
+                  and not args.config.startswith("tp_cfg5"))
+    line = None
+    if rank == 0:
+        peaks, peak_src = load_peaks()
+        roof = gemm_roofline(model, plan, dev_in[0], peaks, peak_src)
+        gflop_img = GFLOP_PER_IMAGE.get(args.config)
+        tot_gflop = gflop_img * B if gflop_img else None
+        line = {
+            "metric": "images/sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16x3 (split-bf16 operands, fp32 accumulate)" if nsplit == 2 else "bf16",
+            "data": "synthetic",
+            "config": {
+                "workload": f"{WORKLOAD[args.config]}, {args.config}, bs {B}/GPU, random-init weights, eval",
+                "global_batch": world * B, "parallelism": f"dp{world} (batch-sharded forward, no collective)",
+                "precision_mode": args.mode,
+                "l2": "no explicit flush: each step streams 1.6 GB of packed weights plus ~1 GB of activations "
+                      "(>> 126 MB L2) and the input rotates over 4 buffers",
+            },
+            "clocks": clocks,
+            "repeats": {"n": len(regions), "steps_each": args.steps, "reported": "median region",
+                        "images_per_s": [world * B * args.steps / (r * 1e-3) for r in regions]},
+            "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": in_bytes,
+                    "d2h_bytes_per_step": out_bytes, "ms_per_step": e2e_ms / args.steps, "wall_ms_per_step": wall_ms / args.steps,
+                    "note": "pinned-host input -> H2D -> model(x) -> all task logits D2H (overlapped with the next step)"},
+            "gpu_launches": int(launches_per_fwd * args.steps),
+            "launches_per_step": int(launches_per_fwd),
+            "roofline": roof,
+        }
+        if gflop_img:
+            line["model_tflops_algorithmic"] = value * gflop_img / 1e3 / world
+            peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
+            line["whole_step"] = {"gflop_per_step_algorithmic": tot_gflop, "tflops_algorithmic": value * gflop_img / 1e3 / world,
+                                  "frac_of_sustained_bf16_peak": value * gflop_img / 1e3 / world / peak,
+                                  "note": "every FLOP of the reference forward (SURVEY.md 8d) over the whole step time"}
+    del model, plan, out, stage, dev_in
+    torch.cuda.empty_cache()
+    if rank == 0 and world == 1 and not args.no_gpu_eager:
         ge = gpu_eager_baseline(args.config, B, dev)
         for k in ("fp32", "tf32", "bf16_autocast"):
             if k in ge:
                 ge[f"ours_over_{k}"] = value / ge[k]
         line["gpu_eager_baseline"] = ge
-    if world == 1 and not args.no_cpu_baseline:
+        torch.cuda.empty_cache()
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = pick_cpu_threads()
         n_fwd = 1 if args.config in ("tp_cfg5", "tps_swinB") else 3
         rate, sec, kind = cpu_oracle_rate(args.config, n_fwd, 1, threads)
         line["cpu_baseline"] = {"value": rate, "unit": "images/s", "cores": threads, "kind": kind,
                                 "sample": f"{n_fwd} forward(s) of batch 1 of {args.config} (fp32 eager, eval, "
                                           f"{threads} of {os.cpu_count()} host threads = fastest setting)"}
-    print(json.dumps(line), file=_OUT, flush=True)
+
+    # ---------------- the training step on the same ranks (`train_step`): the part of the job with a real collective.
+    # The inference line above is complete before this starts and is printed whatever happens here: a watchdog prints it
+    # (rank 0) and ends the process if the leg does not come back, an exception is recorded in the block.
+    def emit():
+        if rank == 0:
+            print(json.dumps(line), file=_OUT, flush=True)
+
+    if want_train:
+        def give_up():
+            if rank == 0:
+                line["train_step"] = {"error": f"no result within {args.train_leg_timeout} s (watchdog)"}
+                emit()
+            os._exit(0)
+        dog = threading.Timer(args.train_leg_timeout, give_up)
+        dog.daemon = True
+        dog.start()
+        try:
+            block = train_leg(args, rank, world, dev)
+        except Exception as ex:  # noqa: BLE001 -- the inference line must survive a failure of the extra leg
+            block = {"error": f"{type(ex).__name__}: {ex}"[:300]}
+        dog.cancel()
+        if rank == 0:
+            line["train_step"] = block
+    emit()
+    if world > 1:                    # a process group that has been captured into CUDA graphs can block in its destructor:
+        w = threading.Timer(30.0, lambda: os._exit(0))   # the line is out, so do not let the tear-down hang the job
+        w.daemon = True
+        w.start()
     D.teardown(world)
 
 
@@ -571,6 +600,67 @@ def train_eager_baseline(cfg_name, batch, dev, labels, steps=3, warmup=1):
     finally:
         torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
     return res
+
+
+def train_leg(args, rank, world, dev, steps=10, warmup=3, repeats=3):
+    """The TRAINING step of the same workload on the same ranks, appended to the inference line as `train_step`: the
+    forward shards over the batch without any exchange, so the scaling run would otherwise never exercise a collective.
+    Here every step all-reduces the SyncBatchNorm statistics and the whole gradient arena over NCCL (captured with the
+    step in one CUDA graph). Same step and timing rules as `bench.py --train` (barrier + synchronize around each timed
+    region, max over ranks, median region); every rank takes part, rank 0 gets the numbers back."""
+    from mtt_b200 import dist as D
+    from mtt_b200.train import TrainStep
+
+    cfg, M, _ = family(args.config)
+    nsplit = 2 if args.mode == "parity" else 1
+    torch.manual_seed(0)
+    with torch.device(dev):
+        model = M.build_from_config(cfg, nsplit=nsplit, use_graph=False)
+    pg = torch.distributed.group.WORLD if world > 1 else None
+    ts = TrainStep(model, nsplit=nsplit, process_group=pg, use_graph=True)
+    crit, _ = _train_criterion(cfg)
+    B = args.batch
+    g = torch.Generator().manual_seed(11 + rank)
+    n_rot = 2
+    host_x = [torch.randn(B, 3, *cfg["img_size"], generator=g).pin_memory() for _ in range(n_rot)]
+    host_y = [{t: v.pin_memory() for t, v in _train_labels(cfg, B, g).items()} for _ in range(n_rot)]
+    in_bytes = host_x[0].numel() * 4 + sum(v.numel() * 4 for v in host_y[0].values())
+    last = None
+    with torch.no_grad():
+        for i in range(warmup):                       # the first call warms the allocator and captures the step
+            ts.step(host_x[i % n_rot], host_y[i % n_rot], crit)
+        torch.cuda.synchronize()
+        regions = []
+        for _ in range(repeats):
+            D.barrier(world)
+            torch.cuda.synchronize()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            for i in range(steps):
+                loss = ts.step(host_x[i % n_rot], host_y[i % n_rot], crit)
+                last = float(loss["total"])           # the step's result is read back (D2H) every step
+            e.record()
+            torch.cuda.synchronize()
+            D.barrier(world)
+            regions.append(D.max_over_ranks(s.elapsed_time(e), world, dev))
+    ms_total = sorted(regions)[len(regions) // 2]
+    grad_bytes = ts.grads.flat.numel() * 4
+    ts._graph = None                                  # the captured step (and the NCCL work in it) goes before the group does
+    del ts, model
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+    return {
+        "metric": "train images/sec", "value": world * B * steps / (ms_total * 1e-3), "unit": "images/s",
+        "ms_per_step": ms_total / steps, "steps": steps, "warmup": warmup, "global_batch": world * B,
+        "repeats": [world * B * steps / (r * 1e-3) for r in regions], "last_loss": last,
+        "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": 4,
+        "what": ("pinned-host images + labels -> H2D -> train-mode forward (DropPath 0.15, batch-statistics BatchNorm) -> "
+                 "criterion -> reverse pass -> clip_grad_norm_ 10 -> Adam -> loss scalar D2H, one CUDA-graph replay per step; "
+                 "the line `python bench.py --train` prints, measured here on the ranks of this run"),
+        "parallelism": (f"dp{world}: SyncBatchNorm statistics + bucketed NCCL all-reduce of the {grad_bytes / 1e6:.0f} MB fp32 "
+                        "gradient arena on a communication stream behind the reverse pass") if world > 1 else "dp1 (no collective)",
+        "allreduce_bytes_per_step": grad_bytes if world > 1 else 0,
+    }
 
 
 def run_train(args):
@@ -789,6 +879,9 @@ def main():
     ap.add_argument("--train", action="store_true", help="time the TRAINING step (TaskPrompter ViT configs) instead of the forward")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-eager", action="store_true")
+    ap.add_argument("--no-train-leg", action="store_true",
+                    help="skip the `train_step` block (the training step timed on the same ranks after the forward)")
+    ap.add_argument("--train-leg-timeout", type=float, default=300.0)
     args = ap.parse_args()
     if args.config not in WORKLOAD:       # any named configuration of mtt_b200/configs.py (tiny ones: contract tests)
         try:

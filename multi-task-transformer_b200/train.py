@@ -111,6 +111,8 @@ class TrainStep:
         # shape and replays it; clip + Adam stay outside (their bias-correction scalars change every step)
         self.use_graph = bool(use_graph) and self.dev.type == "cuda"      # with a process group the NCCL calls are captured too
         self._graph = None
+        # stream-K workspace of the step's GEMMs (one: every kernel of the step runs on one compute stream)
+        self.sk_ws = ops.streamk_workspace(self.dev) if self.dev.type == "cuda" else None
 
     # ---- small helpers -------------------------------------------------------------------------------------------------
     def P_(self, name):
@@ -158,12 +160,18 @@ class TrainStep:
     def _S(self, x, cols=None):
         return ops.split_f32(x, self.ns, cols_pad=round_up(x.shape[1] if cols is None else cols, 8))
 
+    def _gemm(self, a, w, **kw):
+        """ops.gemm on the step's (single) compute stream, with the step's stream-K workspace: the weight-gradient GEMMs
+        dW = dY^T A have 48 .. 64 tiles of 256 x 256 for 74 SM pairs and a reduction over all B*N rows, exactly the shape
+        whose idle pairs the stream-K schedule puts to work (include/mtt_b200.h, mtt_gemm_desc.sk_ws)."""
+        ops.gemm(a, w, sk_ws=self.sk_ws, **kw)
+
     def _mm(self, a, w, *, M=None, N=None, K=None, bias=None, out=None, **kw):
         M = a.rows if M is None else M
         N = w.rows if N is None else N
         if out is None:
             out = _e(M, N, device=self.dev)
-        ops.gemm(a, w, M=M, N=N, K=K, bias=bias, out_f32=out, **kw)
+        self._gemm(a, w, M=M, N=N, K=K, bias=bias, out_f32=out, **kw)
         return out
 
     def _lin_bwd(self, dy, a_s, name, *, M, N, K, need_dx=True, dx_residual=None, dx_out=None, wkey=None, gW=None,
@@ -174,7 +182,7 @@ class TrainStep:
         dyT = Split(N, M, self.dev, self.ns)
         ops.transpose_split(dy, dyT, B=1, L=M, Cdim=N)
         aT = ops.transpose_planes(a_s, R=M, Ccols=K)
-        ops.gemm(dyT, aT, M=N, N=K, K=M, residual=gW, out_f32=gW)                       # dW += dY^T A
+        self._gemm(dyT, aT, M=N, N=K, K=M, residual=gW, out_f32=gW)                       # dW += dY^T A
         if bias_name == "auto":
             bias_name = name[:-len("weight")] + "bias"
         if bias_name is not None:
@@ -184,7 +192,7 @@ class TrainStep:
         dy_s = self._S(dy) if dy_s is None else dy_s
         if dx_out is None:
             dx_out = _e(M, K, device=self.dev)
-        ops.gemm(dy_s, self.WT[wkey], M=M, N=K, K=N, residual=dx_residual, out_f32=dx_out)  # dA = dY W
+        self._gemm(dy_s, self.WT[wkey], M=M, N=K, K=N, residual=dx_residual, out_f32=dx_out)  # dA = dY W
         return dx_out
 
     # ---- forward -------------------------------------------------------------------------------------------------------
@@ -257,7 +265,7 @@ class TrainStep:
         ops.im2col_patch(img, self.patch, cols)
         X = _e(M, C, device=dev)
         pos = self.P_(bbp + "pos_embed")[0, 1:]
-        ops.gemm(cols, W[bbp + "patch_embed.proj.weight"], bias=self.P_(bbp + "patch_embed.proj.bias"), residual=pos,
+        self._gemm(cols, W[bbp + "patch_embed.proj.weight"], bias=self.P_(bbp + "patch_embed.proj.bias"), residual=pos,
                  res_row_mod=P, out_f32=X, regroup=(P, N, T))
         ops.broadcast_rows(self.P_(bbp + "task_prompts"), X, B, N)
         scales = self._drop_scales(B, iter(drop_rand) if drop_rand is not None else None)
@@ -290,7 +298,7 @@ class TrainStep:
         xn = Split(M, C, dev, ns)
         ops.layernorm(X, self.P_(b + "norm1.weight"), self.P_(b + "norm1.bias"), eps, out_split=xn)
         qkv = Split(M, 3 * C, dev, ns)
-        ops.gemm(xn, W[b + "attn.qkv.weight"], bias=self.P_(b + "attn.qkv.bias"), out_split=qkv)
+        self._gemm(xn, W[b + "attn.qkv.weight"], bias=self.P_(b + "attn.qkv.bias"), out_split=qkv)
         ao = Split(M, C, dev, ns)
         logits = _e(B, H, T, N, device=dev) if want else None
         ops.attention(qkv, ao, B=B, N=N, H=H, scale=64 ** -0.5, prompt_logits=logits, T=T)
@@ -301,7 +309,7 @@ class TrainStep:
         bstep = max(1, 128 // T)
         for b0 in range(0, B, bstep):
             nb = min(bstep, B - b0)
-            ops.gemm(xn, W[b + "attn.token_trans.weight"], M=nb * T, bias=self.P_(b + "attn.token_trans.bias"),
+            self._gemm(xn, W[b + "attn.token_trans.weight"], M=nb * T, bias=self.P_(b + "attn.token_trans.bias"),
                      a_gather=(T, N), a_row_offset=b0 * N, out_f32=cp, out_split=cps, regroup=(nb * T, nb * T, b0 * T))
         rc = None
         if want:
@@ -309,7 +317,7 @@ class TrainStep:
             ops.chan_logits(cp, xn, rc, B=B, N=N, T=T, Cdim=C, gh=self.gh, gw=self.gw, nh=self.nh, nw=self.nw)
         for b0 in range(0, B, bstep):
             nb = min(bstep, B - b0)
-            ops.gemm(cps, W[b + "attn.token_trans1.weight"], M=nb * T, bias=self.P_(b + "attn.token_trans1.bias"),
+            self._gemm(cps, W[b + "attn.token_trans1.weight"], M=nb * T, bias=self.P_(b + "attn.token_trans1.bias"),
                      a_row_offset=b0 * T, residual=o, out_f32=o, regroup=(T, N, b0 * N))
         X1 = _e(M, C, device=dev)
         ops.axpy_rows(X, o, scales[0], X1)
@@ -398,7 +406,7 @@ class TrainStep:
         for t, name in enumerate(self.tasks):
             n_out = self.P_(ph[t] + "linear_pred.weight").shape[0]
             y = _e(M4, n_out, device=dev)
-            ops.gemm(z2s, W[ph[t] + "linear_pred.weight"], M=M4, bias=self.P_(ph[t] + "linear_pred.bias"), out_f32=y,
+            self._gemm(z2s, W[ph[t] + "linear_pred.weight"], M=M4, bias=self.P_(ph[t] + "linear_pred.bias"), out_f32=y,
                      a_row_offset=t * M4)
             out[name] = _e(B, n_out, oh, ow, device=dev)
             ops.bilinear(y, n_out, B, h4, w4, n_out, oh, ow, out_nchw=out[name])
@@ -440,7 +448,7 @@ class TrainStep:
         dXpT = ops.transpose_planes(dXp, R=Mp, Ccols=C)
         colsT = ops.im2col_patch_t(cx["img"], self.patch, self.ns)
         gW = self.G_(bbp + "patch_embed.proj.weight").reshape(C, -1)
-        ops.gemm(dXpT, colsT, M=C, N=gW.shape[1], K=Mp, residual=gW, out_f32=gW)
+        self._gemm(dXpT, colsT, M=C, N=gW.shape[1], K=Mp, residual=gW, out_f32=gW)
         ops.colsum(dX, self.G_(bbp + "patch_embed.proj.bias"), accumulate=True, rows=Mp, in_group=P, src_group=N,
                    src_offset=T)
         self._bucket_ready(None)
@@ -485,7 +493,7 @@ class TrainStep:
         else:                                             # column offsets must stay 16-byte aligned for TMA
             for t in range(Tn):
                 xt = ops.im2col3x3_t(x32[t * Mx:(t + 1) * Mx], B=B, H=h, W=w, Cdim=Cin, nsplit=ns)
-                ops.gemm(dyT, xt, M=Cout, N=Cin * 9, K=Mx, a_row_offset=t * Cout, residual=gWs[t], out_f32=gWs[t])
+                self._gemm(dyT, xt, M=Cout, N=Cin * 9, K=Mx, a_row_offset=t * Cout, residual=gWs[t], out_f32=gWs[t])
         for t, p in enumerate(prefixes):
             ops.colsum(dy, self.G_(p + ".bias"), accumulate=True, rows=Mx, in_group=Mx, src_group=Mx, src_offset=t * Mx)
         dys = self._S(dy)
@@ -607,11 +615,11 @@ class TrainStep:
         dopT = ops.transpose_planes(dop, R=B * T, Ccols=C)
         cpT = ops.transpose_planes(bc["cps"], R=B * T, Ccols=P)
         g1 = self.G_(n1)
-        ops.gemm(dopT, cpT, M=C, N=P, K=B * T, residual=g1, out_f32=g1)
+        self._gemm(dopT, cpT, M=C, N=P, K=B * T, residual=g1, out_f32=g1)
         ops.colsum(do, self.G_(b + "attn.token_trans1.bias"), accumulate=True, rows=B * T, in_group=T, src_group=N,
                    src_offset=0)
         dcp = _e(B * T, P, device=dev)
-        ops.gemm(dop, self.WT[n1], M=B * T, N=P, K=C, out_f32=dcp)
+        self._gemm(dop, self.WT[n1], M=B * T, N=P, K=C, out_f32=dcp)
         # raw channel logits
         if bc["d_rc"] is not None:
             dcp2 = _e(B * T, P, device=dev)
@@ -625,12 +633,12 @@ class TrainStep:
         ops.transpose_split(dcp, dcpT, B=1, L=B * T, Cdim=P)
         pnT = ops.transpose_planes(bc["xn"], B=B, R=T, Ccols=C, in_batch_rows=N, side_by_side=True)   # [C, B*T]
         g0 = self.G_(n0)
-        ops.gemm(dcpT, pnT, M=P, N=C, K=B * T, residual=g0, out_f32=g0)
+        self._gemm(dcpT, pnT, M=P, N=C, K=B * T, residual=g0, out_f32=g0)
         ops.colsum(dcp, self.G_(b + "attn.token_trans.bias"), accumulate=True)
         bstep = max(1, 128 // T)
         for b0 in range(0, B, bstep):
             nb = min(bstep, B - b0)
-            ops.gemm(dcps, self.WT[n0], M=nb * T, N=C, K=P, a_row_offset=b0 * T, residual=dxn, out_f32=dxn,
+            self._gemm(dcps, self.WT[n0], M=nb * T, N=C, K=P, a_row_offset=b0 * T, residual=dxn, out_f32=dxn,
                      regroup=(T, N, b0 * N))
         # proj
         dao = self._lin_bwd(do, bc["ao"], b + "attn.proj.weight", M=M, N=C, K=C)

@@ -58,7 +58,7 @@ def install(mp):
 
     def gemm(a, w, *, M=None, N=None, K=None, bias=None, act=0, residual=None, res_row_mod=0, out_f32=None,
              out_split=None, out_col_offset=0, regroup=None, conv=None, a_row_offset=0, a_gather=None,
-             w_col_offset=0, a_col_offset=0, w_row_offset=0, out_row_offset=0):
+             w_col_offset=0, a_col_offset=0, w_row_offset=0, out_row_offset=0, sk_ws=None):
         M = a.rows if M is None else M
         N = w.rows if N is None else N
         K = a.cols if K is None else K

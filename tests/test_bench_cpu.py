@@ -54,3 +54,7 @@ def test_bench_line_contract_live(cuda_dev):
     assert c["kind"] in ("reference", "port") and c["cores"] >= 1 and c["value"] > 0 and c["unit"] == j["unit"] and c["sample"]
     g = j["gpu_eager_baseline"]
     assert g["fp32"] > 0 and g["tf32"] > 0 and g["bf16_autocast"] > 0
+    t = j["train_step"]          # the training step of the same workload on the same ranks (the leg with the collective)
+    assert "error" not in t, t
+    assert t["metric"] == "train images/sec" and t["value"] > 0 and t["global_batch"] == B
+    assert abs(t["value"] - B * 1e3 / t["ms_per_step"]) < 1e-6 * t["value"] and t["last_loss"] == t["last_loss"]
