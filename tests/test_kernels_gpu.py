@@ -316,3 +316,26 @@ def test_bilinear_sum3(cuda_dev):
     ref = up(s0[k * B * 6:(k + 1) * B * 6], 2, 3) + up(s1.contiguous(), 4, 6) + up(s2, 8, 12)
     got = out.float()[:, :C].reshape(B, H2, W2, C).permute(0, 3, 1, 2)
     assert relerr(got, ref) < 3e-5
+
+
+@pytest.mark.parametrize("nsrc,C,W2,odd_ld", [(3, 130, 37, False), (2, 64, 50, True), (1, 200, 16, False)])
+def test_bilinear_sum3_runs(cuda_dev, nsrc, C, W2, odd_ld):
+    """Rows longer than one 16-pixel run and not a multiple of it, several 64-channel chunks (the last one partial),
+    1 / 2 / 3 sources, and a source whose row stride is odd (scalar-load instantiation)."""
+    from mtt_b200 import ops
+
+    torch.manual_seed(9)
+    B, H2 = 2, 12
+    dims = [(3, 5), (6, 19), (12, W2)][:nsrc]
+    srcs, ref = [], 0
+    for i, (h, w) in enumerate(dims):
+        ld = C + (3 if (odd_ld and i == 1) else 2 * i)
+        t = torch.randn(B * h * w, ld, device=cuda_dev)[:, :C]
+        srcs.append((t, h, w, 0, 0))
+        img = t.double().cpu().reshape(B, h, w, C).permute(0, 3, 1, 2)
+        ref = ref + F.interpolate(img, size=(H2, W2), mode="bilinear", align_corners=False)
+    out = ops.Split(B * H2 * W2, C, cuda_dev, zero=True)
+    ops.bilinear_sum3(srcs, out, B=B, Cdim=C, H2=H2, W2=W2)
+    torch.cuda.synchronize()
+    got = out.float()[:, :C].reshape(B, H2, W2, C).permute(0, 3, 1, 2)
+    assert relerr(got, ref) < 3e-5
