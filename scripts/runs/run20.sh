@@ -2,7 +2,7 @@ set -u
 O=gpurun_out/r3a; mkdir -p $O
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.limit --format=csv,noheader
 # 1. the new schedule / kernels against their references
-timeout 900 python -m pytest tests/test_kernels_gpu.py -m gpu -q -x -k "gemm" > $O/pytest_gemm.log 2>&1; echo "gemm tests rc=$?"; tail -3 $O/pytest_gemm.log | cut -c1-400
+timeout 900 python -m pytest tests/test_kernels_gpu.py -m gpu -q -x -k "gemm or bilinear" > $O/pytest_gemm.log 2>&1; echo "gemm tests rc=$?"; tail -3 $O/pytest_gemm.log | cut -c1-400
 timeout 600 python -m pytest tests/test_glue_kernels_gpu.py -m gpu -q > $O/pytest_glue.log 2>&1; echo "glue tests rc=$?"; tail -3 $O/pytest_glue.log | cut -c1-400
 timeout 900 python -m pytest tests/test_big_goldens_gpu.py -m gpu -q -k "cfg4_b4 or ip_cfg3" > $O/pytest_big.log 2>&1; echo "big goldens rc=$?"; tail -3 $O/pytest_big.log | cut -c1-400
 timeout 900 python -m pytest tests/test_train_gpu.py -m gpu -q -k "training_step or graph_replay" > $O/pytest_train.log 2>&1; echo "train tests rc=$?"; tail -3 $O/pytest_train.log | cut -c1-400
