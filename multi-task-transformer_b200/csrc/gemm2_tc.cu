@@ -454,19 +454,25 @@ static int launch_gemm2_streamk(const CUtensorMap* maps, const GemmParams& p, in
   return check_launch("mtt_gemm(cta pair, stream-K)");
 }
 
-static int g_streamk = -1;  // -1: read MTT_GEMM_STREAMK once (default on); 0 = off
-void set_gemm_streamk(int on) { g_streamk = on ? 1 : 0; }
+static int g_streamk = -1;  // -1: read MTT_GEMM_STREAMK once. 0 = off, 1 = automatic (default), 2 = whenever legal
+void set_gemm_streamk(int mode) { g_streamk = mode < 0 ? 0 : (mode > 2 ? 2 : mode); }
 
-// How many tiles of a `tiles`-tile, k_iters-deep problem go to the stream-K schedule on `pairs` CTA pairs (0 = none):
-// the ragged last round, when splitting it saves at least 1/16 of a round and leaves every pair >= 4 k-blocks.
+// How many tiles of a `tiles`-tile, k_iters-deep problem go to the stream-K schedule on `pairs` CTA pairs (0 = none).
+// Legal: a ragged last round whose split leaves every pair >= 4 k-blocks (the owner's wait assumes no pair is empty).
+// Automatic: only a SINGLE partial round (tiles < pairs) that leaves >= 1/4 of the pairs idle and is >= 32 k-blocks
+// deep. Measured (profiles/r3_streamk.md): every split tile costs a 256 KB fp32 partial written and read back plus two
+// extra epilogue passes, ~10 us per launch; on the multi-round backbone GEMMs (qkv 204 tiles x 16 k-blocks: 2.76
+// rounds instead of 3) that is more than the 5 us the balance saves -- cfg4 forward 328 -> 308 images/s with the split
+// forced on -- while a 48-tile weight-gradient GEMM over 65 k-blocks leaves 35 % of the SMs idle for 80 us.
 int streamk_tiles(int tiles, int k_iters, int pairs) {
   if (g_streamk < 0) {
     const char* e = getenv("MTT_GEMM_STREAMK");
-    g_streamk = e ? (atoi(e) != 0) : 1;
+    set_gemm_streamk(e ? atoi(e) : 1);
   }
   if (!g_streamk || pairs < 2 || pairs * 2 * kEpiWarps * 4 > (int)kSkFlagBytes) return 0;
   const int r = tiles % pairs;
   if (r == 0 || (pairs - r) * 16 < pairs || (long long)r * k_iters / pairs < 4) return 0;
+  if (g_streamk == 1 && (tiles >= pairs || (pairs - r) * 4 < pairs || k_iters < 32)) return 0;
   return r;
 }
 

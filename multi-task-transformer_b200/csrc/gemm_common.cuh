@@ -264,7 +264,7 @@ int launch_gemm_1cta(const mtt_gemm_desc* d, cudaStream_t stream);
 int launch_gemm_1cta_grouped(const mtt_gemm_desc* d, int count, cudaStream_t stream);
 int launch_gemm_2cta_grouped(const mtt_gemm_desc* d, int count, cudaStream_t stream);
 int launch_gemm_2cta(const mtt_gemm_desc* d, int bn2, cudaStream_t stream);
-void set_gemm_streamk(int on);
+void set_gemm_streamk(int mode);
 int streamk_tiles(int tiles, int k_iters, int pairs);
 int streamk_schedule_host(int tiles, int k_iters, int pairs, int pair, int* out, int max_pieces);
 

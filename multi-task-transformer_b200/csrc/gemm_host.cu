@@ -184,7 +184,7 @@ static int g_variant = -1;  // -1: read MTT_GEMM_VARIANT once; 0 auto, 1 = 1-CTA
 }  // namespace mtt
 
 extern "C" void mtt_set_gemm_variant(int v) { mtt::g_variant = v; }
-extern "C" void mtt_set_gemm_streamk(int on) { mtt::set_gemm_streamk(on); }
+extern "C" void mtt_set_gemm_streamk(int mode) { mtt::set_gemm_streamk(mode); }
 extern "C" int mtt_debug_streamk_schedule(int32_t tiles, int32_t k_iters, int32_t pairs, int32_t pair, int32_t* pieces,
                                           int32_t max_pieces) {
   return mtt::streamk_schedule_host(tiles, k_iters, pairs, pair, pieces, max_pieces);

@@ -197,9 +197,10 @@ def streamk_workspace(device):
         return workspace(_L.load().mtt_gemm_streamk_bytes(), device)
 
 
-def set_gemm_streamk(on):
-    """False switches the stream-K schedule of the CTA-pair GEMM off (tuning / testing knob; env MTT_GEMM_STREAMK)."""
-    _L.load().mtt_set_gemm_streamk(int(bool(on)))
+def set_gemm_streamk(mode):
+    """Stream-K policy of the CTA-pair GEMM: 0 off, 1 automatic (default), 2 whenever legal (tuning / testing knob; env
+    MTT_GEMM_STREAMK)."""
+    _L.load().mtt_set_gemm_streamk(int(mode))
 
 
 def set_gemm_variant(v):

@@ -8,7 +8,15 @@ import ctypes as C
 import pytest
 
 
-def _schedule(L, tiles, k_iters, pairs):
+def _schedule(L, tiles, k_iters, pairs, policy=2):
+    L.mtt_set_gemm_streamk(policy)          # 2 = split whenever legal (the schedule under test); 1 = automatic (default)
+    try:
+        return _pieces(L, tiles, k_iters, pairs)
+    finally:
+        L.mtt_set_gemm_streamk(1)
+
+
+def _pieces(L, tiles, k_iters, pairs):
     out = []
     for p in range(pairs):
         buf = (C.c_int32 * (3 * 512))()
@@ -61,3 +69,19 @@ def test_streamk_schedule_backbone_shapes_are_balanced():
     for tiles, k_iters, plain in [(204, 16, 48), (272, 16, 64), (68, 64, 64)]:
         load = [sum(k1 - k0 for _, k0, k1 in pieces) for pieces in _schedule(L, tiles, k_iters, 74)]
         assert max(load) <= tiles * k_iters / 74 + 1 < plain
+
+
+def test_streamk_automatic_policy():
+    """Default policy: only single-partial-round, long-K problems are split (profiles/r3_streamk.md): the weight-gradient
+    GEMM of qkv (48 tiles x 65 k-blocks) and fc2 at batch 1 (20 x 64) are, the multi-round backbone GEMMs of cfg4 bs 4 and
+    the 68-tile fc2 (8 % idle) are not."""
+    import mtt_b200  # noqa: F401
+    from mtt_b200 import lib
+
+    L = lib.load()
+
+    def split(tiles, k_iters):
+        return any((k0, k1) != (0, k_iters) for pieces in _schedule(L, tiles, k_iters, 74, policy=1) for _, k0, k1 in pieces)
+
+    assert split(48, 65) and split(20, 64) and split(12, 37)
+    assert not split(204, 16) and not split(272, 16) and not split(68, 64) and not split(64, 65) and not split(20, 16)
