@@ -124,9 +124,9 @@ typedef struct {
   /* Optional stream-K workspace (NULL = off), mtt_gemm_streamk_bytes() bytes, 256-byte aligned, zero-filled ONCE before
    * its first use (every launch leaves its flag words zero again) and not shared by launches that may run
    * concurrently. With it, a problem that mtt_gemm puts on the CTA-pair 256x256 kernel may split the tiles of its ragged
-   * last round along K over all SM pairs instead of leaving most of them idle (policy: mtt_set_gemm_streamk; e.g. the
-   * 48-tile, 65-k-block weight-gradient GEMMs of the training step, or fc2 at batch 1: 20 tiles of 64 k-blocks on 74
-   * pairs); the partial sums are added in a fixed order, so results are reproducible. */
+   * last round along K over all SM pairs instead of leaving most of them idle (policy: mtt_set_gemm_streamk; e.g. fc2
+   * at batch 1: 20 tiles of 64 k-blocks on 74 pairs, or the 16-tile weight-gradient GEMM of proj in the training step);
+   * the partial sums are added in a fixed order, so results are reproducible. */
   void* sk_ws;
   int64_t sk_ws_bytes;
 } mtt_gemm_desc;
@@ -149,7 +149,7 @@ void mtt_set_gemm_variant(int variant);
  * tile per SM pair, ~19 MB on a B200); mtt_workspace_bytes already includes it for the operators that use it. */
 size_t mtt_gemm_streamk_bytes(void);
 /* Stream-K policy (also env MTT_GEMM_STREAMK): 0 = off (sk_ws is ignored), 1 = automatic (default: problems of a
- * single partial round -- fewer tiles than SM pairs, >= 1/4 of the pairs idle, >= 32 k-blocks deep -- where the split
+ * single partial round -- fewer tiles than SM pairs, >= 1/2 of the pairs idle, >= 32 k-blocks deep -- where the split
  * pays for its partial sums), 2 = whenever the split is legal. Tuning / testing knob: all settings compute the same
  * function. */
 void mtt_set_gemm_streamk(int mode);

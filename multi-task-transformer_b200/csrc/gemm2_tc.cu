@@ -459,11 +459,12 @@ void set_gemm_streamk(int mode) { g_streamk = mode < 0 ? 0 : (mode > 2 ? 2 : mod
 
 // How many tiles of a `tiles`-tile, k_iters-deep problem go to the stream-K schedule on `pairs` CTA pairs (0 = none).
 // Legal: a ragged last round whose split leaves every pair >= 4 k-blocks (the owner's wait assumes no pair is empty).
-// Automatic: only a SINGLE partial round (tiles < pairs) that leaves >= 1/4 of the pairs idle and is >= 32 k-blocks
-// deep. Measured (profiles/r3_streamk.md): every split tile costs a 256 KB fp32 partial written and read back plus two
-// extra epilogue passes, ~10 us per launch; on the multi-round backbone GEMMs (qkv 204 tiles x 16 k-blocks: 2.76
-// rounds instead of 3) that is more than the 5 us the balance saves -- cfg4 forward 328 -> 308 images/s with the split
-// forced on -- while a 48-tile weight-gradient GEMM over 65 k-blocks leaves 35 % of the SMs idle for 80 us.
+// Automatic: only a SINGLE partial round (tiles < pairs) that leaves >= 1/2 of the pairs idle and is >= 32 k-blocks
+// deep. Measured per shape (profiles/r3_streamk.md, split / plain launch time): fc2 at batch 1 (20 tiles x 64 k-blocks)
+// 0.91, dW of proj (16 x 65) 0.91 -- but dW of qkv (48 x 65) 1.05, fc2 at batch 4 (68 x 64) 1.21, qkv (204 x 16) 1.17:
+// with all 148 SMs streaming operands the k-block rate drops (the pair kernel already sits at the L2 -> SM operand
+// rate) and every split tile adds a 256 KB partial written and read back plus two epilogue passes; cfg4 bs 4 forward
+// 328 -> 308 images/s with the split forced on, bs 1 forward 159.4 -> 161.9 images/s with this policy.
 int streamk_tiles(int tiles, int k_iters, int pairs) {
   if (g_streamk < 0) {
     const char* e = getenv("MTT_GEMM_STREAMK");
@@ -472,7 +473,7 @@ int streamk_tiles(int tiles, int k_iters, int pairs) {
   if (!g_streamk || pairs < 2 || pairs * 2 * kEpiWarps * 4 > (int)kSkFlagBytes) return 0;
   const int r = tiles % pairs;
   if (r == 0 || (pairs - r) * 16 < pairs || (long long)r * k_iters / pairs < 4) return 0;
-  if (g_streamk == 1 && (tiles >= pairs || (pairs - r) * 4 < pairs || k_iters < 32)) return 0;
+  if (g_streamk == 1 && (tiles >= pairs || (pairs - r) * 2 < pairs || k_iters < 32)) return 0;
   return r;
 }
 

@@ -215,20 +215,25 @@ __device__ __forceinline__ void bilin_coord(int d, float scale, int in_size, int
   l1 = s - (float)i0;
 }
 
-// One warp per (run of kBilinRun consecutive output pixels of one output row, 64-channel chunk); a lane owns two
+// One warp per (run of up to kBilinRun consecutive output pixels of one output row, 64-channel chunk); a lane owns two
 // channels and walks the run keeping the four corner values in registers: when the left source column advances by one the
 // old right column becomes the new left one, so an x4 up-sampling (taskprompter.py:420: 32x32 -> 128x128, 350 channels)
 // reads ~0.75 source values per output value from L2 instead of 4 (one warp per output pixel moved 367 MB L2 -> SM to
 // write 92 MB: 59 us, 24 % of the HBM copy rate). The arithmetic and its order are those of the one-pixel form
 // (bit-identical results); down-sampling ratios simply reload both columns at every pixel.
-constexpr int kBilinRun = 16;
+constexpr int kBilinRun = 16;   // longest run; short rows / small maps get shorter runs so that the launch still fills the SMs
+static int bilin_run_len(long long rows, int W2, int chunks) {
+  int run = kBilinRun;
+  while (run > 1 && rows * ((W2 + run - 1) / run) * chunks < 148LL * 48) run >>= 1;
+  return run;
+}
 template <bool VEC>
 __global__ void __launch_bounds__(256)
 bilinear_nhwc_kernel(const float* __restrict__ in, long long ld_in, long long in_brows, long long in_off, int B,
                      int h, int w, int C, int H2, int W2, float sy, float sx, float* __restrict__ out_f32,
                      long long ld_f32, __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo,
-                     long long ld_bf, long long out_brows, long long out_off, int accumulate, int runs_per_row,
-                     int chunks) {
+                     long long ld_bf, long long out_brows, long long out_off, int accumulate, int run_len,
+                     int runs_per_row, int chunks) {
   long long wid = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (wid >= (long long)B * H2 * runs_per_row * chunks) return;
   const int lane = threadIdx.x & 31;
@@ -255,8 +260,8 @@ bilinear_nhwc_kernel(const float* __restrict__ in, long long ld_in, long long in
   int cx0 = -1, cx1 = -1;
   float2 t0 = make_float2(0.f, 0.f), t1 = t0, b0 = t0, b1 = t0;   // top / bottom source rows at columns cx0, cx1
   const long long orow = (long long)b * out_brows + out_off + (long long)y * W2;
-  const int xbeg = run * kBilinRun;
-  const int xend = xbeg + kBilinRun < W2 ? xbeg + kBilinRun : W2;
+  const int xbeg = run * run_len;
+  const int xend = xbeg + run_len < W2 ? xbeg + run_len : W2;
   for (int x = xbeg; x < xend; ++x) {
     int x0, x1;
     float lx;
@@ -344,7 +349,7 @@ template <int NSRC, bool VEC>
 __global__ void __launch_bounds__(256)
 bilinear_sum3_kernel(BilinSrc s0, BilinSrc s1, BilinSrc s2, int B, int C, int H2, int W2,
                      __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo, long long ld_bf,
-                     int runs_per_row, int chunks) {
+                     int run_len, int runs_per_row, int chunks) {
   long long wid = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (wid >= (long long)B * H2 * runs_per_row * chunks) return;
   const int lane = threadIdx.x & 31;
@@ -382,8 +387,8 @@ bilinear_sum3_kernel(BilinSrc s0, BilinSrc s1, BilinSrc s2, int B, int C, int H2
     return make_float2(q[0], q[1]);
   };
   const long long orow = ((long long)b * H2 + y) * W2;
-  const int xbeg = run * kBilinRun;
-  const int xend = xbeg + kBilinRun < W2 ? xbeg + kBilinRun : W2;
+  const int xbeg = run * run_len;
+  const int xend = xbeg + run_len < W2 ? xbeg + run_len : W2;
   for (int x = xbeg; x < xend; ++x) {
     float v0 = 0.f, v1 = 0.f;
 #pragma unroll
@@ -587,14 +592,16 @@ extern "C" int mtt_bilinear(const float* in, int64_t ld_in, int32_t B, int32_t h
   if (out_f32 || out_hi) {
     if (out_hi && (ld_bf % 2))
       return set_error(MTT_ERR_MISALIGNED, "mtt_bilinear: ld_bf must be even");
-    const int runs = (W2 + kBilinRun - 1) / kBilinRun, chunks = (C + 63) / 64;
+    const int chunks = (C + 63) / 64;
+    const int run_len = bilin_run_len((long long)B * H2, W2, chunks);
+    const int runs = (W2 + run_len - 1) / run_len;
     const long long warps = (long long)B * H2 * runs * chunks;
     const unsigned blocks = (unsigned)((warps + 7) / 8);
     const bool vec = (ld_in % 2 == 0) && (reinterpret_cast<uintptr_t>(in) % 8 == 0);
     auto kern = vec ? bilinear_nhwc_kernel<true> : bilinear_nhwc_kernel<false>;
     kern<<<blocks, 256, 0, STREAM>>>(in, ld_in, in_batch_rows, in_row_offset, B, h, w, C, H2, W2, sy, sx, out_f32, ld_f32,
                                      static_cast<__nv_bfloat16*>(out_hi), static_cast<__nv_bfloat16*>(out_lo), ld_bf,
-                                     out_batch_rows, out_row_offset, accumulate, runs, chunks);
+                                     out_batch_rows, out_row_offset, accumulate, run_len, runs, chunks);
     return check_launch("mtt_bilinear(nhwc)");
   }
   return MTT_OK;
@@ -631,13 +638,15 @@ extern "C" int mtt_bilinear_sum3(const mtt_bilinear_src* srcs, int32_t nsrc, int
   }
   bool vec = true;
   for (int i = 0; i < nsrc; ++i) vec = vec && (s[i].ld % 2 == 0) && (reinterpret_cast<uintptr_t>(s[i].p) % 8 == 0);
-  const int runs = (W2 + kBilinRun - 1) / kBilinRun, chunks = (C + 63) / 64;
+  const int chunks = (C + 63) / 64;
+  const int run_len = bilin_run_len((long long)B * H2, W2, chunks);
+  const int runs = (W2 + run_len - 1) / run_len;
   const long long warps = (long long)B * H2 * runs * chunks;
   const unsigned blocks = (unsigned)((warps + 7) / 8);
   auto hi = static_cast<__nv_bfloat16*>(out_hi);
   auto lo = static_cast<__nv_bfloat16*>(out_lo);
 #define MTT_SUM3(NS, V) \
-  bilinear_sum3_kernel<NS, V><<<blocks, 256, 0, STREAM>>>(s[0], s[1], s[2], B, C, H2, W2, hi, lo, ld_bf, runs, chunks)
+  bilinear_sum3_kernel<NS, V><<<blocks, 256, 0, STREAM>>>(s[0], s[1], s[2], B, C, H2, W2, hi, lo, ld_bf, run_len, runs, chunks)
   if (nsrc == 1) { if (vec) MTT_SUM3(1, true); else MTT_SUM3(1, false); }
   else if (nsrc == 2) { if (vec) MTT_SUM3(2, true); else MTT_SUM3(2, false); }
   else { if (vec) MTT_SUM3(3, true); else MTT_SUM3(3, false); }
