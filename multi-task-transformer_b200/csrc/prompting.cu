@@ -215,19 +215,24 @@ __device__ __forceinline__ void bilin_coord(int d, float scale, int in_size, int
   l1 = s - (float)i0;
 }
 
-// One warp per (run of up to kBilinRun consecutive output pixels of one output row, 64-channel chunk); a lane owns two
-// channels and walks the run keeping the four corner values in registers: when the left source column advances by one the
-// old right column becomes the new left one, so an x4 up-sampling (taskprompter.py:420: 32x32 -> 128x128, 350 channels)
-// reads ~0.75 source values per output value from L2 instead of 4 (one warp per output pixel moved 367 MB L2 -> SM to
-// write 92 MB: 59 us, 24 % of the HBM copy rate). The arithmetic and its order are those of the one-pixel form
-// (bit-identical results); down-sampling ratios simply reload both columns at every pixel.
+// One warp per (run of up to kBilinRun consecutive output pixels of one output row, chunk of 64 * NCH channels). A lane
+// owns NCH channel pairs (c, c + 64, ...) and walks the run keeping the four corner values of each pair in registers:
+// when the left source column advances by one the old right column becomes the new left one, so an x4 up-sampling
+// (taskprompter.py:420: 32x32 -> 128x128, 350 channels) reads ~0.75 source values per output value from L2 instead of 4.
+// History (profiles/r3_bilinear.md): one warp per output pixel was 59 us for 92 MB of output (1.6 TB/s; a plain fill of
+// the same bytes takes 18 us); the run walk with one pair per lane 49 us and, by its ncu capture, ISSUE-bound (85 % issue
+// active, 120 instructions per lane per pixel, most of them 64-bit index arithmetic and the coordinate / cache logic) --
+// hence several pairs per lane behind ONE coordinate computation and output pointers that advance by a stride.
+// The interpolation expression and its order are those of the one-pixel form: bit-identical results.
 constexpr int kBilinRun = 16;   // longest run; short rows / small maps get shorter runs so that the launch still fills the SMs
 static int bilin_run_len(long long rows, int W2, int chunks) {
   int run = kBilinRun;
   while (run > 1 && rows * ((W2 + run - 1) / run) * chunks < 148LL * 48) run >>= 1;
   return run;
 }
-template <bool VEC>
+static int bilin_pairs_per_lane(int C) { return C > 128 ? 4 : (C > 64 ? 2 : 1); }
+
+template <int NCH, bool VEC>
 __global__ void __launch_bounds__(256)
 bilinear_nhwc_kernel(const float* __restrict__ in, long long ld_in, long long in_brows, long long in_off, int B,
                      int h, int w, int C, int H2, int W2, float sy, float sx, float* __restrict__ out_f32,
@@ -242,9 +247,14 @@ bilinear_nhwc_kernel(const float* __restrict__ in, long long ld_in, long long in
   const int run = (int)(wid % runs_per_row);
   wid /= runs_per_row;
   const int y = (int)(wid % H2), b = (int)(wid / H2);
-  const int c = chunk * 64 + lane * 2;
+  const int c = chunk * (64 * NCH) + lane * 2;   // this lane's pairs start at c + 64 j
   if (c >= C) return;
-  const bool two = c + 1 < C;
+  bool ok[NCH], two[NCH];
+#pragma unroll
+  for (int j = 0; j < NCH; ++j) {
+    ok[j] = c + 64 * j < C;
+    two[j] = c + 64 * j + 1 < C;
+  }
   int y0, y1;
   float ly;
   bilin_coord(y, sy, h, y0, y1, ly);
@@ -252,62 +262,87 @@ bilinear_nhwc_kernel(const float* __restrict__ in, long long ld_in, long long in
   const float* ib = in + ((long long)b * in_brows + in_off) * ld_in + c;
   const float* row0 = ib + (long long)y0 * w * ld_in;
   const float* row1 = ib + (long long)y1 * w * ld_in;
-  auto ld2 = [&](const float* rowp, int xx) -> float2 {
-    const float* q = rowp + (long long)xx * ld_in;
-    if (VEC && two) return *reinterpret_cast<const float2*>(q);
-    return make_float2(q[0], two ? q[1] : 0.f);
+  float2 t0[NCH], t1[NCH], b0[NCH], b1[NCH];   // top / bottom source rows at the cached columns cx0, cx1
+#pragma unroll
+  for (int j = 0; j < NCH; ++j) t0[j] = t1[j] = b0[j] = b1[j] = make_float2(0.f, 0.f);
+  auto load_col = [&](int xx, float2 (&tt)[NCH], float2 (&bb)[NCH]) {
+    const float* q0 = row0 + (long long)xx * ld_in;
+    const float* q1 = row1 + (long long)xx * ld_in;
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) {
+      if (!ok[j]) continue;
+      if (VEC && two[j]) {
+        tt[j] = *reinterpret_cast<const float2*>(q0 + 64 * j);
+        bb[j] = *reinterpret_cast<const float2*>(q1 + 64 * j);
+      } else {
+        tt[j] = make_float2(q0[64 * j], two[j] ? q0[64 * j + 1] : 0.f);
+        bb[j] = make_float2(q1[64 * j], two[j] ? q1[64 * j + 1] : 0.f);
+      }
+    }
   };
   int cx0 = -1, cx1 = -1;
-  float2 t0 = make_float2(0.f, 0.f), t1 = t0, b0 = t0, b1 = t0;   // top / bottom source rows at columns cx0, cx1
-  const long long orow = (long long)b * out_brows + out_off + (long long)y * W2;
   const int xbeg = run * run_len;
   const int xend = xbeg + run_len < W2 ? xbeg + run_len : W2;
+  const long long opix0 = (long long)b * out_brows + out_off + (long long)y * W2 + xbeg;
+  float* of = out_f32 ? out_f32 + opix0 * ld_f32 + c : nullptr;
+  __nv_bfloat16* ohi = out_hi ? out_hi + opix0 * ld_bf + c : nullptr;
+  __nv_bfloat16* olo = (out_hi && out_lo) ? out_lo + opix0 * ld_bf + c : nullptr;
   for (int x = xbeg; x < xend; ++x) {
     int x0, x1;
     float lx;
     bilin_coord(x, sx, w, x0, x1, lx);
     if (x0 != cx0 || x1 != cx1) {
       if (x0 == cx1) {
-        t0 = t1;
-        b0 = b1;
+#pragma unroll
+        for (int j = 0; j < NCH; ++j) {
+          t0[j] = t1[j];
+          b0[j] = b1[j];
+        }
       } else if (x0 != cx0) {
-        t0 = ld2(row0, x0);
-        b0 = ld2(row1, x0);
+        load_col(x0, t0, b0);
       }
       if (x1 == x0) {
-        t1 = t0;
-        b1 = b0;
+#pragma unroll
+        for (int j = 0; j < NCH; ++j) {
+          t1[j] = t0[j];
+          b1[j] = b0[j];
+        }
       } else {
-        t1 = ld2(row0, x1);
-        b1 = ld2(row1, x1);
+        load_col(x1, t1, b1);
       }
       cx0 = x0;
       cx1 = x1;
     }
     const float hx = 1.f - lx;
-    float v0 = hy * (hx * t0.x + lx * t1.x) + ly * (hx * b0.x + lx * b1.x);
-    float v1 = two ? hy * (hx * t0.y + lx * t1.y) + ly * (hx * b0.y + lx * b1.y) : 0.f;
-    const long long opix = orow + x;
-    if (out_f32) {
-      float* o = out_f32 + opix * ld_f32 + c;
-      if (accumulate) {
-        v0 += o[0];
-        if (two) v1 += o[1];
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) {
+      if (!ok[j]) continue;
+      float v0 = hy * (hx * t0[j].x + lx * t1[j].x) + ly * (hx * b0[j].x + lx * b1[j].x);
+      float v1 = two[j] ? hy * (hx * t0[j].y + lx * t1[j].y) + ly * (hx * b0[j].y + lx * b1[j].y) : 0.f;
+      if (of) {
+        float* o = of + 64 * j;
+        if (accumulate) {
+          v0 += o[0];
+          if (two[j]) v1 += o[1];
+        }
+        o[0] = v0;
+        if (two[j]) o[1] = v1;
       }
-      o[0] = v0;
-      if (two) o[1] = v1;
-    }
-    if (out_hi) {
-      uint32_t hh, ll;
-      split_pack2(v0, v1, hh, ll);
-      if (two) {
-        *reinterpret_cast<uint32_t*>(out_hi + opix * ld_bf + c) = hh;
-        if (out_lo) *reinterpret_cast<uint32_t*>(out_lo + opix * ld_bf + c) = ll;
-      } else {
-        out_hi[opix * ld_bf + c] = __ushort_as_bfloat16((unsigned short)(hh & 0xFFFF));
-        if (out_lo) out_lo[opix * ld_bf + c] = __ushort_as_bfloat16((unsigned short)(ll & 0xFFFF));
+      if (ohi) {
+        uint32_t hh, ll;
+        split_pack2(v0, v1, hh, ll);
+        if (two[j]) {
+          *reinterpret_cast<uint32_t*>(ohi + 64 * j) = hh;
+          if (olo) *reinterpret_cast<uint32_t*>(olo + 64 * j) = ll;
+        } else {
+          ohi[64 * j] = __ushort_as_bfloat16((unsigned short)(hh & 0xFFFF));
+          if (olo) olo[64 * j] = __ushort_as_bfloat16((unsigned short)(ll & 0xFFFF));
+        }
       }
     }
+    if (of) of += ld_f32;
+    if (ohi) ohi += ld_bf;
+    if (olo) olo += ld_bf;
   }
 }
 
@@ -342,10 +377,11 @@ struct BilinSrc {
   long long ld, batch_rows, row_off;
   int h, w;
 };
-// Same run walk as bilinear_nhwc_kernel: a warp owns kBilinRun consecutive output pixels of one row for a 64-channel
-// chunk and keeps each source's four corner values in registers (round 2 read 12 corner rows per output pixel from L2:
-// 173 us per launch at InvPT cfg3). Per output value the sources are added in the same order with the same expression.
-template <int NSRC, bool VEC>
+// Same run walk as bilinear_nhwc_kernel: a warp owns a run of consecutive output pixels of one row for a chunk of
+// 64 * NCH channels, a lane NCH channel pairs, and each source's four corner values per pair stay in registers (round 2
+// read 12 corner rows per output pixel from L2: 173 us per launch at InvPT cfg3). Per output value the sources are added
+// in the same order with the same expression.
+template <int NSRC, int NCH, bool VEC>
 __global__ void __launch_bounds__(256)
 bilinear_sum3_kernel(BilinSrc s0, BilinSrc s1, BilinSrc s2, int B, int C, int H2, int W2,
                      __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo, long long ld_bf,
@@ -358,15 +394,18 @@ bilinear_sum3_kernel(BilinSrc s0, BilinSrc s1, BilinSrc s2, int B, int C, int H2
   const int run = (int)(wid % runs_per_row);
   wid /= runs_per_row;
   const int y = (int)(wid % H2), b = (int)(wid / H2);
-  const int c = chunk * 64 + lane * 2;   // C is even: a lane always owns a full channel pair
+  const int c = chunk * (64 * NCH) + lane * 2;   // C is even: a lane always owns full channel pairs c + 64 j
   if (c >= C) return;
+  bool ok[NCH];
+#pragma unroll
+  for (int j = 0; j < NCH; ++j) ok[j] = c + 64 * j < C;
   const BilinSrc* ss[3] = {&s0, &s1, &s2};
   const float* row0[NSRC];
   const float* row1[NSRC];
   float hy[NSRC], ly[NSRC], sx[NSRC];
   long long ld[NSRC];
   int w[NSRC], cx0[NSRC], cx1[NSRC];
-  float2 t0[NSRC], t1[NSRC], b0[NSRC], b1[NSRC];
+  float2 t0[NSRC][NCH], t1[NSRC][NCH], b0[NSRC][NCH], b1[NSRC][NCH];
 #pragma unroll
   for (int i = 0; i < NSRC; ++i) {
     const BilinSrc& s = *ss[i];
@@ -380,17 +419,31 @@ bilinear_sum3_kernel(BilinSrc s0, BilinSrc s1, BilinSrc s2, int B, int C, int H2
     row0[i] = ib + (long long)y0 * s.w * s.ld;
     row1[i] = ib + (long long)y1 * s.w * s.ld;
     cx0[i] = cx1[i] = -1;
-    t0[i] = t1[i] = b0[i] = b1[i] = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) t0[i][j] = t1[i][j] = b0[i][j] = b1[i][j] = make_float2(0.f, 0.f);
   }
-  auto ld2 = [&](const float* q) -> float2 {
-    if (VEC) return *reinterpret_cast<const float2*>(q);
-    return make_float2(q[0], q[1]);
+  auto load_col = [&](const float* q0, const float* q1, float2 (&tt)[NCH], float2 (&bb)[NCH]) {
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) {
+      if (!ok[j]) continue;
+      if (VEC) {
+        tt[j] = *reinterpret_cast<const float2*>(q0 + 64 * j);
+        bb[j] = *reinterpret_cast<const float2*>(q1 + 64 * j);
+      } else {
+        tt[j] = make_float2(q0[64 * j], q0[64 * j + 1]);
+        bb[j] = make_float2(q1[64 * j], q1[64 * j + 1]);
+      }
+    }
   };
-  const long long orow = ((long long)b * H2 + y) * W2;
   const int xbeg = run * run_len;
   const int xend = xbeg + run_len < W2 ? xbeg + run_len : W2;
+  const long long opix0 = ((long long)b * H2 + y) * W2 + xbeg;
+  __nv_bfloat16* ohi = out_hi + opix0 * ld_bf + c;
+  __nv_bfloat16* olo = out_lo ? out_lo + opix0 * ld_bf + c : nullptr;
   for (int x = xbeg; x < xend; ++x) {
-    float v0 = 0.f, v1 = 0.f;
+    float v0[NCH], v1[NCH];
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) v0[j] = v1[j] = 0.f;
 #pragma unroll
     for (int i = 0; i < NSRC; ++i) {
       int x0, x1;
@@ -398,30 +451,43 @@ bilinear_sum3_kernel(BilinSrc s0, BilinSrc s1, BilinSrc s2, int B, int C, int H2
       bilin_coord(x, sx[i], w[i], x0, x1, lx);
       if (x0 != cx0[i] || x1 != cx1[i]) {
         if (x0 == cx1[i]) {
-          t0[i] = t1[i];
-          b0[i] = b1[i];
+#pragma unroll
+          for (int j = 0; j < NCH; ++j) {
+            t0[i][j] = t1[i][j];
+            b0[i][j] = b1[i][j];
+          }
         } else if (x0 != cx0[i]) {
-          t0[i] = ld2(row0[i] + (long long)x0 * ld[i]);
-          b0[i] = ld2(row1[i] + (long long)x0 * ld[i]);
+          load_col(row0[i] + (long long)x0 * ld[i], row1[i] + (long long)x0 * ld[i], t0[i], b0[i]);
         }
         if (x1 == x0) {
-          t1[i] = t0[i];
-          b1[i] = b0[i];
+#pragma unroll
+          for (int j = 0; j < NCH; ++j) {
+            t1[i][j] = t0[i][j];
+            b1[i][j] = b0[i][j];
+          }
         } else {
-          t1[i] = ld2(row0[i] + (long long)x1 * ld[i]);
-          b1[i] = ld2(row1[i] + (long long)x1 * ld[i]);
+          load_col(row0[i] + (long long)x1 * ld[i], row1[i] + (long long)x1 * ld[i], t1[i], b1[i]);
         }
         cx0[i] = x0;
         cx1[i] = x1;
       }
       const float hx = 1.f - lx;
-      v0 += hy[i] * (hx * t0[i].x + lx * t1[i].x) + ly[i] * (hx * b0[i].x + lx * b1[i].x);
-      v1 += hy[i] * (hx * t0[i].y + lx * t1[i].y) + ly[i] * (hx * b0[i].y + lx * b1[i].y);
+#pragma unroll
+      for (int j = 0; j < NCH; ++j) {
+        v0[j] += hy[i] * (hx * t0[i][j].x + lx * t1[i][j].x) + ly[i] * (hx * b0[i][j].x + lx * b1[i][j].x);
+        v1[j] += hy[i] * (hx * t0[i][j].y + lx * t1[i][j].y) + ly[i] * (hx * b0[i][j].y + lx * b1[i][j].y);
+      }
     }
-    uint32_t hh, ll;
-    split_pack2(v0, v1, hh, ll);
-    *reinterpret_cast<uint32_t*>(out_hi + (orow + x) * ld_bf + c) = hh;
-    if (out_lo) *reinterpret_cast<uint32_t*>(out_lo + (orow + x) * ld_bf + c) = ll;
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) {
+      if (!ok[j]) continue;
+      uint32_t hh, ll;
+      split_pack2(v0[j], v1[j], hh, ll);
+      *reinterpret_cast<uint32_t*>(ohi + 64 * j) = hh;
+      if (olo) *reinterpret_cast<uint32_t*>(olo + 64 * j) = ll;
+    }
+    ohi += ld_bf;
+    if (olo) olo += ld_bf;
   }
 }
 
@@ -592,16 +658,22 @@ extern "C" int mtt_bilinear(const float* in, int64_t ld_in, int32_t B, int32_t h
   if (out_f32 || out_hi) {
     if (out_hi && (ld_bf % 2))
       return set_error(MTT_ERR_MISALIGNED, "mtt_bilinear: ld_bf must be even");
-    const int chunks = (C + 63) / 64;
+    const int nch = bilin_pairs_per_lane(C);
+    const int chunks = (C + 64 * nch - 1) / (64 * nch);
     const int run_len = bilin_run_len((long long)B * H2, W2, chunks);
     const int runs = (W2 + run_len - 1) / run_len;
     const long long warps = (long long)B * H2 * runs * chunks;
     const unsigned blocks = (unsigned)((warps + 7) / 8);
     const bool vec = (ld_in % 2 == 0) && (reinterpret_cast<uintptr_t>(in) % 8 == 0);
-    auto kern = vec ? bilinear_nhwc_kernel<true> : bilinear_nhwc_kernel<false>;
-    kern<<<blocks, 256, 0, STREAM>>>(in, ld_in, in_batch_rows, in_row_offset, B, h, w, C, H2, W2, sy, sx, out_f32, ld_f32,
-                                     static_cast<__nv_bfloat16*>(out_hi), static_cast<__nv_bfloat16*>(out_lo), ld_bf,
-                                     out_batch_rows, out_row_offset, accumulate, run_len, runs, chunks);
+#define MTT_BILIN(NCH, V)                                                                                                \
+  bilinear_nhwc_kernel<NCH, V><<<blocks, 256, 0, STREAM>>>(                                                               \
+      in, ld_in, in_batch_rows, in_row_offset, B, h, w, C, H2, W2, sy, sx, out_f32, ld_f32,                               \
+      static_cast<__nv_bfloat16*>(out_hi), static_cast<__nv_bfloat16*>(out_lo), ld_bf, out_batch_rows, out_row_offset,   \
+      accumulate, run_len, runs, chunks)
+    if (nch == 4) { if (vec) MTT_BILIN(4, true); else MTT_BILIN(4, false); }
+    else if (nch == 2) { if (vec) MTT_BILIN(2, true); else MTT_BILIN(2, false); }
+    else { if (vec) MTT_BILIN(1, true); else MTT_BILIN(1, false); }
+#undef MTT_BILIN
     return check_launch("mtt_bilinear(nhwc)");
   }
   return MTT_OK;
@@ -638,18 +710,23 @@ extern "C" int mtt_bilinear_sum3(const mtt_bilinear_src* srcs, int32_t nsrc, int
   }
   bool vec = true;
   for (int i = 0; i < nsrc; ++i) vec = vec && (s[i].ld % 2 == 0) && (reinterpret_cast<uintptr_t>(s[i].p) % 8 == 0);
-  const int chunks = (C + 63) / 64;
+  const int nch = C > 64 ? 2 : 1;
+  const int chunks = (C + 64 * nch - 1) / (64 * nch);
   const int run_len = bilin_run_len((long long)B * H2, W2, chunks);
   const int runs = (W2 + run_len - 1) / run_len;
   const long long warps = (long long)B * H2 * runs * chunks;
   const unsigned blocks = (unsigned)((warps + 7) / 8);
   auto hi = static_cast<__nv_bfloat16*>(out_hi);
   auto lo = static_cast<__nv_bfloat16*>(out_lo);
-#define MTT_SUM3(NS, V) \
-  bilinear_sum3_kernel<NS, V><<<blocks, 256, 0, STREAM>>>(s[0], s[1], s[2], B, C, H2, W2, hi, lo, ld_bf, run_len, runs, chunks)
-  if (nsrc == 1) { if (vec) MTT_SUM3(1, true); else MTT_SUM3(1, false); }
-  else if (nsrc == 2) { if (vec) MTT_SUM3(2, true); else MTT_SUM3(2, false); }
-  else { if (vec) MTT_SUM3(3, true); else MTT_SUM3(3, false); }
+#define MTT_SUM3(NS, NC, V) \
+  bilinear_sum3_kernel<NS, NC, V><<<blocks, 256, 0, STREAM>>>(s[0], s[1], s[2], B, C, H2, W2, hi, lo, ld_bf, run_len, runs, chunks)
+#define MTT_SUM3_V(NS, NC) do { if (vec) MTT_SUM3(NS, NC, true); else MTT_SUM3(NS, NC, false); } while (0)
+  if (nch == 2) {
+    if (nsrc == 1) MTT_SUM3_V(1, 2); else if (nsrc == 2) MTT_SUM3_V(2, 2); else MTT_SUM3_V(3, 2);
+  } else {
+    if (nsrc == 1) MTT_SUM3_V(1, 1); else if (nsrc == 2) MTT_SUM3_V(2, 1); else MTT_SUM3_V(3, 1);
+  }
+#undef MTT_SUM3_V
 #undef MTT_SUM3
   return check_launch("mtt_bilinear_sum3");
 }
