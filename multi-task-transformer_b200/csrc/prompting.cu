@@ -3,6 +3,8 @@
 // bilinear resampling.  All are coalesced along the channel (innermost NHWC / token-major) axis,
 // float4 / bf16x2 vectorised where the layout allows, with grids sized by the data (>= several
 // waves of 148 SMs at the benchmark shapes).
+#include <stdlib.h>
+
 #include "host_common.h"
 #include "ptx.cuh"
 
@@ -232,7 +234,7 @@ static int bilin_run_len(long long rows, int W2, int chunks) {
 }
 static int bilin_pairs_per_lane(int C) { return C > 128 ? 4 : (C > 64 ? 2 : 1); }
 
-template <int NCH, bool VEC>
+template <int NCH, bool VEC, bool FAST>   // FAST: even C, both split planes, no fp32 output (the decoder's hot form)
 __global__ void __launch_bounds__(256)
 bilinear_nhwc_kernel(const float* __restrict__ in, long long ld_in, long long in_brows, long long in_off, int B,
                      int h, int w, int C, int H2, int W2, float sy, float sx, float* __restrict__ out_f32,
@@ -253,7 +255,7 @@ bilinear_nhwc_kernel(const float* __restrict__ in, long long ld_in, long long in
 #pragma unroll
   for (int j = 0; j < NCH; ++j) {
     ok[j] = c + 64 * j < C;
-    two[j] = c + 64 * j + 1 < C;
+    two[j] = FAST || c + 64 * j + 1 < C;
   }
   int y0, y1;
   float ly;
@@ -284,9 +286,9 @@ bilinear_nhwc_kernel(const float* __restrict__ in, long long ld_in, long long in
   const int xbeg = run * run_len;
   const int xend = xbeg + run_len < W2 ? xbeg + run_len : W2;
   const long long opix0 = (long long)b * out_brows + out_off + (long long)y * W2 + xbeg;
-  float* of = out_f32 ? out_f32 + opix0 * ld_f32 + c : nullptr;
-  __nv_bfloat16* ohi = out_hi ? out_hi + opix0 * ld_bf + c : nullptr;
-  __nv_bfloat16* olo = (out_hi && out_lo) ? out_lo + opix0 * ld_bf + c : nullptr;
+  float* of = (!FAST && out_f32) ? out_f32 + opix0 * ld_f32 + c : nullptr;
+  __nv_bfloat16* ohi = (FAST || out_hi) ? out_hi + opix0 * ld_bf + c : nullptr;
+  __nv_bfloat16* olo = (FAST || (out_hi && out_lo)) ? out_lo + opix0 * ld_bf + c : nullptr;
   for (int x = xbeg; x < xend; ++x) {
     int x0, x1;
     float lx;
@@ -319,7 +321,7 @@ bilinear_nhwc_kernel(const float* __restrict__ in, long long ld_in, long long in
       if (!ok[j]) continue;
       float v0 = hy * (hx * t0[j].x + lx * t1[j].x) + ly * (hx * b0[j].x + lx * b1[j].x);
       float v1 = two[j] ? hy * (hx * t0[j].y + lx * t1[j].y) + ly * (hx * b0[j].y + lx * b1[j].y) : 0.f;
-      if (of) {
+      if (!FAST && of) {
         float* o = of + 64 * j;
         if (accumulate) {
           v0 += o[0];
@@ -328,7 +330,12 @@ bilinear_nhwc_kernel(const float* __restrict__ in, long long ld_in, long long in
         o[0] = v0;
         if (two[j]) o[1] = v1;
       }
-      if (ohi) {
+      if (FAST) {
+        uint32_t hh, ll;
+        split_pack2(v0, v1, hh, ll);
+        *reinterpret_cast<uint32_t*>(ohi + 64 * j) = hh;
+        *reinterpret_cast<uint32_t*>(olo + 64 * j) = ll;
+      } else if (ohi) {
         uint32_t hh, ll;
         split_pack2(v0, v1, hh, ll);
         if (two[j]) {
@@ -340,9 +347,9 @@ bilinear_nhwc_kernel(const float* __restrict__ in, long long ld_in, long long in
         }
       }
     }
-    if (of) of += ld_f32;
-    if (ohi) ohi += ld_bf;
-    if (olo) olo += ld_bf;
+    if (!FAST && of) of += ld_f32;
+    if (FAST || ohi) ohi += ld_bf;
+    if (FAST || olo) olo += ld_bf;
   }
 }
 
@@ -658,21 +665,28 @@ extern "C" int mtt_bilinear(const float* in, int64_t ld_in, int32_t B, int32_t h
   if (out_f32 || out_hi) {
     if (out_hi && (ld_bf % 2))
       return set_error(MTT_ERR_MISALIGNED, "mtt_bilinear: ld_bf must be even");
-    const int nch = bilin_pairs_per_lane(C);
+    static int force_nch = -1;   // MTT_BILINEAR_PAIRS: 1 / 2 / 4 channel pairs per lane (tuning aid); 0 = by channel count
+    if (force_nch < 0) {
+      const char* e = getenv("MTT_BILINEAR_PAIRS");
+      force_nch = e ? atoi(e) : 0;
+    }
+    const int nch = (force_nch == 1 || force_nch == 2 || force_nch == 4) ? force_nch : bilin_pairs_per_lane(C);
     const int chunks = (C + 64 * nch - 1) / (64 * nch);
     const int run_len = bilin_run_len((long long)B * H2, W2, chunks);
     const int runs = (W2 + run_len - 1) / run_len;
     const long long warps = (long long)B * H2 * runs * chunks;
     const unsigned blocks = (unsigned)((warps + 7) / 8);
     const bool vec = (ld_in % 2 == 0) && (reinterpret_cast<uintptr_t>(in) % 8 == 0);
-#define MTT_BILIN(NCH, V)                                                                                                \
-  bilinear_nhwc_kernel<NCH, V><<<blocks, 256, 0, STREAM>>>(                                                               \
+    const bool fast = vec && (C % 2 == 0) && out_hi && out_lo && !out_f32;
+#define MTT_BILIN(NCH, V, F)                                                                                             \
+  bilinear_nhwc_kernel<NCH, V, F><<<blocks, 256, 0, STREAM>>>(                                                            \
       in, ld_in, in_batch_rows, in_row_offset, B, h, w, C, H2, W2, sy, sx, out_f32, ld_f32,                               \
       static_cast<__nv_bfloat16*>(out_hi), static_cast<__nv_bfloat16*>(out_lo), ld_bf, out_batch_rows, out_row_offset,   \
       accumulate, run_len, runs, chunks)
-    if (nch == 4) { if (vec) MTT_BILIN(4, true); else MTT_BILIN(4, false); }
-    else if (nch == 2) { if (vec) MTT_BILIN(2, true); else MTT_BILIN(2, false); }
-    else { if (vec) MTT_BILIN(1, true); else MTT_BILIN(1, false); }
+#define MTT_BILIN_N(NCH) do { if (fast) MTT_BILIN(NCH, true, true); else if (vec) MTT_BILIN(NCH, true, false); \
+                              else MTT_BILIN(NCH, false, false); } while (0)
+    if (nch == 4) MTT_BILIN_N(4); else if (nch == 2) MTT_BILIN_N(2); else MTT_BILIN_N(1);
+#undef MTT_BILIN_N
 #undef MTT_BILIN
     return check_launch("mtt_bilinear(nhwc)");
   }
