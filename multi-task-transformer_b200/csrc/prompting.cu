@@ -223,8 +223,9 @@ __device__ __forceinline__ void bilin_coord(int d, float scale, int in_size, int
 // (taskprompter.py:420: 32x32 -> 128x128, 350 channels) reads ~0.75 source values per output value from L2 instead of 4.
 // History (profiles/r3_bilinear.md): one warp per output pixel was 59 us for 92 MB of output (1.6 TB/s; a plain fill of
 // the same bytes takes 18 us); the run walk with one pair per lane 49 us and, by its ncu capture, ISSUE-bound (85 % issue
-// active, 120 instructions per lane per pixel, most of them 64-bit index arithmetic and the coordinate / cache logic) --
-// hence several pairs per lane behind ONE coordinate computation and output pointers that advance by a stride.
+// active, 120 instructions per lane per pixel, most of them 64-bit index arithmetic and the output-form / odd-channel
+// branches) -- hence the FAST instantiation for the decoder's form (about 50 instructions per pixel), output pointers
+// that advance by a stride, and two pairs per lane behind one coordinate computation: 36.9 us (2.5 TB/s).
 // The interpolation expression and its order are those of the one-pixel form: bit-identical results.
 constexpr int kBilinRun = 16;   // longest run; short rows / small maps get shorter runs so that the launch still fills the SMs
 static int bilin_run_len(long long rows, int W2, int chunks) {
@@ -232,7 +233,8 @@ static int bilin_run_len(long long rows, int W2, int chunks) {
   while (run > 1 && rows * ((W2 + run - 1) / run) * chunks < 148LL * 48) run >>= 1;
   return run;
 }
-static int bilin_pairs_per_lane(int C) { return C > 128 ? 4 : (C > 64 ? 2 : 1); }
+// measured on the x4 decoder resize (profiles/r3_bilinear.md): 1 pair 41.0 us, 2 pairs 36.9 us, 4 pairs 45.1 us (84 registers)
+static int bilin_pairs_per_lane(int C) { return C > 64 ? 2 : 1; }
 
 template <int NCH, bool VEC, bool FAST>   // FAST: even C, both split planes, no fp32 output (the decoder's hot form)
 __global__ void __launch_bounds__(256)
