@@ -635,37 +635,65 @@ __global__ void ctr_weights_bwd_kernel(const float* __restrict__ plog, int B, in
 // ---- weight-gradient operands of the convolutions ----------------------------------------------------------------------
 // 3x3 (pad 1) im2col, transposed and split: out[(c*9 + ky*3 + kx), p] = x[b, y+ky-1, x+kx-1, c] (0 outside), p = pixel
 // index over [B,H,W]; rows in nn.Conv2d's weight order so that dW = dY^T . out^T is [Cout, Cin*9] = weight.view(Cout,-1).
+// One block = 64 consecutive pixels x 32 channels, all nine taps: per tap the shifted [64 x 32] slab goes through a
+// shared-memory tile (loads coalesced along channels, neighbouring taps hit L1 / L2) and leaves as 128-byte rows of 64
+// pixels (one bf16x2 per lane). The first version ran one 32 x 32 tile of ONE tap per block with 2-byte stores: 202 752
+// blocks of four elements per thread, 1.11 ms for the 825 MB operand of a 350-channel 128 x 128 map at batch 4
+// (0.75 TB/s; profiles/r2p_train_launch_shares.md), a sixth of the plain fill rate.
 __global__ void __launch_bounds__(256)
 im2col3x3_t_kernel(const float* __restrict__ x, long long ldx, int B, int H, int W, int C, __nv_bfloat16* __restrict__ hi,
-                   __nv_bfloat16* __restrict__ lo, long long ldo) {
-  __shared__ float tile[32][33];
-  const int tap = blockIdx.z;
-  const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+                   __nv_bfloat16* __restrict__ lo, long long ldo, int vec_out) {
+  __shared__ float tile[64][33];
   const long long Ptot = (long long)B * H * W;
-  const long long p0 = (long long)blockIdx.x * 32;
+  const long long p0 = (long long)blockIdx.x * 64;
   const int c0 = blockIdx.y * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  for (int k = ty; k < 32; k += 8) {
-    const long long p = p0 + k;
-    float v = 0.f;
-    const int c = c0 + tx;
-    if (p < Ptot && c < C) {
-      const int xx = (int)(p % W), yy = (int)((p / W) % H);
-      const int sy = yy + dy, sx = xx + dx;
-      if (sy >= 0 && sy < H && sx >= 0 && sx < W) v = x[(p + (long long)dy * W + dx) * ldx + c];
+  // the eight pixels this thread loads (rows ty*8 .. ty*8+7 of the tile), channel c0 + tx
+  int px[8], py[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const long long p = p0 + ty * 8 + k;
+    if (p < Ptot) {
+      px[k] = (int)(p % W);
+      py[k] = (int)((p / W) % H);
+    } else {
+      px[k] = py[k] = -1000000;   // never in bounds
     }
-    tile[k][tx] = v;
   }
-  __syncthreads();
-  for (int k = ty; k < 32; k += 8) {
-    const int c = c0 + k;
-    const long long p = p0 + tx;
-    if (c < C && p < Ptot) {
-      __nv_bfloat16 h, l;
-      split_bf16(tile[tx][k], h, l);
-      hi[((long long)c * 9 + tap) * ldo + p] = h;
-      if (lo) lo[((long long)c * 9 + tap) * ldo + p] = l;
+  const bool c_ok = c0 + tx < C;
+  const float* xc = x + c0 + tx;
+  for (int tap = 0; tap < 9; ++tap) {
+    const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int sy = py[k] + dy, sx = px[k] + dx;
+      float v = 0.f;
+      if (c_ok && sy >= 0 && sy < H && sx >= 0 && sx < W) v = xc[(p0 + ty * 8 + k + (long long)dy * W + dx) * ldx];
+      tile[ty * 8 + k][tx] = v;
     }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int c = c0 + ty * 4 + k;
+      const long long p = p0 + 2 * tx;
+      if (c < C && p < Ptot) {
+        uint32_t hh, ll;
+        split_pack2(tile[2 * tx][ty * 4 + k], tile[2 * tx + 1][ty * 4 + k], hh, ll);
+        const long long o = ((long long)c * 9 + tap) * ldo + p;
+        if (vec_out && p + 1 < Ptot) {
+          *reinterpret_cast<uint32_t*>(hi + o) = hh;
+          if (lo) *reinterpret_cast<uint32_t*>(lo + o) = ll;
+        } else {
+          hi[o] = __ushort_as_bfloat16((unsigned short)(hh & 0xFFFF));
+          if (lo) lo[o] = __ushort_as_bfloat16((unsigned short)(ll & 0xFFFF));
+          if (p + 1 < Ptot) {
+            hi[o + 1] = __ushort_as_bfloat16((unsigned short)(hh >> 16));
+            if (lo) lo[o + 1] = __ushort_as_bfloat16((unsigned short)(ll >> 16));
+          }
+        }
+      }
+    }
+    __syncthreads();
   }
 }
 
@@ -938,8 +966,10 @@ extern "C" int mtt_im2col3x3_t(const float* x, int64_t ldx, int32_t B, int32_t H
   const long long P = (long long)B * H * W;
   if (!x || !out_hi || P <= 0 || C <= 0 || ldo < P) return set_error(MTT_ERR_BAD_SHAPE, "mtt_im2col3x3_t: bad arguments");
   const int cb = (C + 31) / 32;
-  im2col3x3_t_kernel<<<dim3((unsigned)((P + 31) / 32), cb, 9), 256, 0, ST>>>(
-      x, ldx, B, H, W, C, static_cast<__nv_bfloat16*>(out_hi), static_cast<__nv_bfloat16*>(out_lo), ldo);
+  const int vec_out = (ldo % 2 == 0) && (reinterpret_cast<uintptr_t>(out_hi) % 4 == 0) &&
+                      (!out_lo || reinterpret_cast<uintptr_t>(out_lo) % 4 == 0);
+  im2col3x3_t_kernel<<<dim3((unsigned)((P + 63) / 64), cb), 256, 0, ST>>>(
+      x, ldx, B, H, W, C, static_cast<__nv_bfloat16*>(out_hi), static_cast<__nv_bfloat16*>(out_lo), ldo, vec_out);
   count_launch();
   return check_launch("mtt_im2col3x3_t");
 }
