@@ -89,6 +89,8 @@ class TrainStep:
         self.max_norm = max_norm
         self.step_no = 0
         self.drop_path = [float(x) for x in torch.linspace(0, float(getattr(bb, "drop_path_rate", 0.0)), self.depth)]
+        self._dp_keep = torch.tensor([1.0 - d for d in self.drop_path if d > 0.0] or [1.0],
+                                     dtype=torch.float32).to(self.dev).view(-1, 1, 1)
         # arenas: parameters in the order the reverse pass finishes them LAST -> FIRST is not needed; buckets are cut by
         # layer group below, so keep module order
         named = [(n, p) for n, p in model.named_parameters()]
@@ -199,6 +201,8 @@ class TrainStep:
     def _drop_scales(self, B, rand=None):
         """Per block the two row-scale vectors [B*N] of the joint stream (attention / MLP residual), or None. `rand`:
         optional iterator of the uniform [B,1,1] draws to use instead of torch.rand (tests replay the reference's)."""
+        if rand is None:
+            return self._drop_scales_batched(B)
         out = []
         for i in range(self.depth):
             dp = self.drop_path[i]
@@ -206,8 +210,7 @@ class TrainStep:
                 out.append((None, None))
                 continue
             keep = 1.0 - dp
-            draw = (lambda: next(rand).to(self.dev, torch.float32)) if rand is not None else \
-                (lambda: torch.rand((B, 1, 1), dtype=torch.float32, device=self.dev))
+            draw = lambda: next(rand).to(self.dev, torch.float32)
             # reference call order (taskprompter.py:273,274,276,277): x attn, x mlp, prompts attn, prompts mlp
             r = [torch.floor(keep + draw()) / keep for _ in range(4)]
             sa = torch.empty(B, self.N, dtype=torch.float32, device=self.dev)
@@ -215,6 +218,23 @@ class TrainStep:
             sa[:, self.T:], sa[:, :self.T] = r[0].view(B, 1), r[2].view(B, 1)
             sm[:, self.T:], sm[:, :self.T] = r[1].view(B, 1), r[3].view(B, 1)
             out.append((sa.view(-1), sm.view(-1)))
+        return out
+
+    def _drop_scales_batched(self, B):
+        """The same per-sample masks (timm DropPath: floor(keep + U[0,1)) / keep per sample and residual branch) for ALL
+        blocks from one torch.rand call: ~8 launches per step instead of ~20 per block (1.2 ms of launch time at depth 24)."""
+        act = [i for i in range(self.depth) if self.drop_path[i] > 0.0]
+        out = [(None, None)] * self.depth
+        if not act:
+            return out
+        keep = self._dp_keep        # device tensor made at construction: nothing here may copy from the host (graph capture)
+        u = torch.rand((len(act), 4, B), dtype=torch.float32, device=self.dev)   # (block, [x attn, x mlp, prompts attn, prompts mlp], sample)
+        r = torch.floor(keep + u) / keep
+        s = torch.empty(len(act), 2, B, self.N, dtype=torch.float32, device=self.dev)    # (block, [attn, mlp], sample, token)
+        s[:, :, :, self.T:] = r[:, 0:2, :, None]
+        s[:, :, :, :self.T] = r[:, 2:4, :, None]
+        for j, i in enumerate(act):
+            out[i] = (s[j, 0].reshape(-1), s[j, 1].reshape(-1))
         return out
 
     def _bn_fwd(self, x, prefix, act, out_split):
