@@ -881,7 +881,8 @@ def main():
     ap.add_argument("--no-gpu-eager", action="store_true")
     ap.add_argument("--no-train-leg", action="store_true",
                     help="skip the `train_step` block (the training step timed on the same ranks after the forward)")
-    ap.add_argument("--train-leg-timeout", type=float, default=300.0)
+    ap.add_argument("--train-leg-timeout", type=float, default=150.0,
+                    help="seconds after which the watchdog prints the finished inference line without the train_step block")
     args = ap.parse_args()
     if args.config not in WORKLOAD:       # any named configuration of mtt_b200/configs.py (tiny ones: contract tests)
         try:

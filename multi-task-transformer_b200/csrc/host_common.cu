@@ -1,3 +1,5 @@
+#include <string.h>
+
 #include "host_common.h"
 
 #include <cudaTypedefs.h>
@@ -52,6 +54,41 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
     if (strides_bytes[i] % 16 != 0)
       return set_error(MTT_ERR_MISALIGNED, "TMA stride %d = %llu bytes is not a multiple of 16", i,
                        (unsigned long long)strides_bytes[i]);
+  // The descriptor is a pure function of (base, rank, dims, strides, box): a small per-thread direct-mapped cache keeps
+  // the eager (non-graph) launch path and batch-1 latency from paying four driver encodes per GEMM / attention call
+  // (inside a CUDA graph the maps are baked into the kernel parameters at capture and none of this runs on replay).
+  struct Key {
+    const void* base;
+    int rank;
+    uint64_t dims[5], strides[4];
+    uint32_t box[5];
+  };
+  struct Slot {
+    bool used;
+    Key key;
+    CUtensorMap map;
+  };
+  constexpr int kSlots = 512;
+  static thread_local Slot* cache = nullptr;   // heap, not a 120 KB TLS block in a dlopen'ed library
+  if (!cache) cache = new Slot[kSlots]();
+  Key k;
+  memset(&k, 0, sizeof(k));
+  k.base = base;
+  k.rank = rank;
+  uint64_t h = reinterpret_cast<uintptr_t>(base) * 0x9E3779B97F4A7C15ull + (uint64_t)rank;
+  for (int i = 0; i < rank; ++i) {
+    k.dims[i] = dims[i];
+    k.box[i] = box[i];
+    if (i + 1 < rank) k.strides[i] = strides_bytes[i];
+    h = (h ^ dims[i]) * 0x9E3779B97F4A7C15ull;
+    h = (h ^ box[i]) * 0x9E3779B97F4A7C15ull;
+    if (i + 1 < rank) h = (h ^ strides_bytes[i]) * 0x9E3779B97F4A7C15ull;
+  }
+  Slot& slot = cache[(h >> 32) % kSlots];
+  if (slot.used && memcmp(&slot.key, &k, sizeof(k)) == 0) {
+    *out = slot.map;
+    return MTT_OK;
+  }
   cuuint64_t gdim[5];
   cuuint64_t gstr[4];
   cuuint32_t bx[5], estr[5];
@@ -75,6 +112,9 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
                      (unsigned long long)(rank > 4 ? dims[4] : 0), box[0], rank > 1 ? box[1] : 0,
                      rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0, rank > 4 ? box[4] : 0);
   }
+  slot.used = true;
+  slot.key = k;
+  slot.map = *out;
   return MTT_OK;
 }
 
