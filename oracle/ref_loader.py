@@ -14,8 +14,13 @@ _SHIM = os.path.join(os.path.dirname(os.path.abspath(__file__)), "shim")
 _COLLIDING = ("models", "utils", "data", "evaluation", "losses", "configs", "detection_toolbox")
 
 
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
 def reference_root():
-    for cand in (os.environ.get("MTT_REFERENCE"), "/root/reference"):
+    """$MTT_REFERENCE, /root/reference (the build container), then <repo>/baseline/_ref (a copy of the reference tree
+    that travels to the GPU box when someone puts one there; the reference has no installable package)."""
+    for cand in (os.environ.get("MTT_REFERENCE"), "/root/reference", os.path.join(_REPO, "baseline", "_ref")):
         if cand and os.path.isdir(os.path.join(cand, "TaskPrompter")):
             return cand
     return None
