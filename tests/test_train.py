@@ -138,3 +138,44 @@ def test_train_mode_restatement_is_pinned_to_the_reference():
         # fp32 summation order alone moves the cancelling sums of ctr_attn_conv by 1e-4 (two fp32 evaluations of the same graph)
         # ... and a bias in front of a BatchNorm holds nothing but such noise (its gradient is zero)
         assert err < (1e-3 if (".ctr_attn_conv." in k or ref.norm().item() < floor) else 1e-4), (k, err)
+
+
+def test_batched_drop_path_scales_follow_timm_droppath():
+    """TrainStep._drop_scales_batched (all blocks from ONE torch.rand call) against timm 0.5.4 drop_path semantics
+    (taskprompter.py:273-277): per block i with rate d_i > 0 every sample gets floor(keep + U) / keep in {0, 1 / keep}
+    independently for the four residual branches (x attn, x mlp, prompts attn, prompts mlp); the value is constant over
+    the patch rows / over the prompt rows of that sample; blocks with rate 0 get (None, None)."""
+    import types
+
+    import mtt_b200  # noqa: F401
+    from mtt_b200.train import TrainStep
+
+    depth, B, T, N = 6, 64, 3, 11
+    rates = [float(x) for x in torch.linspace(0, 0.5, depth)]
+    ts = types.SimpleNamespace(depth=depth, drop_path=rates, dev=torch.device("cpu"), T=T, N=N,
+                               _dp_keep=torch.tensor([1.0 - d for d in rates if d > 0.0]).view(-1, 1, 1))
+    torch.manual_seed(0)
+    out = TrainStep._drop_scales_batched(ts, B)
+    assert len(out) == depth and out[0] == (None, None)
+    seen_zero = seen_keep = False
+    for i in range(1, depth):
+        keep = 1.0 - rates[i]
+        for vec in out[i]:
+            assert vec.shape == (B * N,) and vec.dtype == torch.float32
+            m = vec.view(B, N)
+            for part in (m[:, :T], m[:, T:]):                       # constant within the prompt rows / the patch rows
+                assert torch.equal(part, part[:, :1].expand_as(part))
+            vals = m[:, [0, T]]
+            ok = (vals == 0) | ((vals - 1.0 / keep).abs() < 1e-6)
+            assert ok.all()
+            seen_zero |= bool((vals == 0).any())
+            seen_keep |= bool((vals != 0).any())
+        # the four branches are drawn independently: attn / mlp and prompt / patch columns are not copies of each other
+        a, m_ = out[i][0].view(B, N), out[i][1].view(B, N)
+        if rates[i] >= 0.3:
+            assert not torch.equal(a[:, 0], a[:, T]) or not torch.equal(a[:, T], m_[:, T])
+    assert seen_zero and seen_keep
+    # expected keep fraction of the last block (rate 0.5) over 4 * B draws
+    last = torch.stack([out[-1][0].view(B, N)[:, 0], out[-1][0].view(B, N)[:, T], out[-1][1].view(B, N)[:, 0],
+                        out[-1][1].view(B, N)[:, T]])
+    assert 0.3 < float((last != 0).float().mean()) < 0.7
