@@ -417,7 +417,9 @@ class _Plan:
             if bb is not None:
                 self.C = C = bb.embed_dim
                 self.H = bb.num_heads
-                assert C // self.H == 64, "attention kernel is built for head_dim 64"
+                if C // self.H != 64 or C % self.H:
+                    raise ValueError(f"InvPT: embed_dim / num_heads = {C} / {self.H} must be 64 (mtt_attention is built for "
+                                     "head dim 64: ViT-B 768 / 12, ViT-L 1024 / 16)")
                 self.gh, self.gw = bb.patch_embed.grid_size
                 self.patch = bb.patch_size
                 self.img = (self.gh * self.patch, self.gw * self.patch)
@@ -426,6 +428,13 @@ class _Plan:
             elif mode == "decoder":
                 self.C = C = p.backbone_channels[-1]
                 self.gh, self.gw = p.spatial_dim[-1]
+            if mode in ("full", "postproc", "decoder") and (self.gh % 4 or self.gw % 4):
+                # the decoder concatenates x2 / x4 / x8 up-sampled maps with stride-2-reduced ones (IP invpt.py:125-147,
+                # :524-539, transformer_decoder.py:63-98): they only line up when the token grid is a multiple of 4 x 4.
+                # The reference fails for other sizes too (torch.cat size mismatch); say so before any kernel is launched.
+                raise ValueError(f"InvPT: token grid {self.gh} x {self.gw} must be a multiple of 4 x 4 (image height and "
+                                 f"width multiples of {4 * (self.patch if bb is not None else 16)}); the reference "
+                                 "rejects this size as well")
             self.P = P = self.gh * self.gw if mode != "invpt" else 0
             self.N = N = 1 + P
             # ---- backbone workspace

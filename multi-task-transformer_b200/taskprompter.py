@@ -307,7 +307,11 @@ class TaskPrompter(nn.Module):
         self.task_prompts = nn.Parameter(torch.ones(self.prompts_len, embed_dim))
         self.chan_nheads = chan_nheads
         nh = int(round(math.sqrt(chan_nheads)))
-        assert nh * nh == chan_nheads and self.resolution[0] % nh == 0 and self.resolution[1] % nh == 0
+        if nh * nh != chan_nheads or self.resolution[0] % nh or self.resolution[1] % nh:
+            # taskprompter.py:233 takes nh = nw = int(sqrt(chan_nheads)) windows per axis and rearranges the token grid
+            # "(nh h nw w)" (:236): the reference's configurations use 1, 4 and 16, and an indivisible grid fails there too
+            raise ValueError(f"TaskPrompter: chan_nheads={chan_nheads} must be a perfect square whose root divides the "
+                             f"token grid {self.resolution[0]} x {self.resolution[1]}")
         e, f = p.embed_dim, p.final_embed_dim
         prompt_dim = num_heads * p.prompt_len
         self.fea_fuse = nn.ModuleList()
@@ -583,7 +587,9 @@ class _Plan:
         self.T = T = len(self.tasks)
         self.C = C = bb.embed_dim
         self.H = bb.num_heads
-        assert C // self.H == 64, "attention kernel is built for head_dim 64"
+        if C // self.H != 64 or C % self.H:
+            raise ValueError(f"TaskPrompter: embed_dim / num_heads = {C} / {self.H} must be 64 (mtt_attention is built for "
+                             "head dim 64: ViT-B 768 / 12, ViT-L 1024 / 16)")
         self.gh, self.gw = bb.resolution
         self.P = P = self.gh * self.gw
         self.N = N = T + P

@@ -1,0 +1,196 @@
+"""CPU: randomly drawn TaskPrompter geometries -- task subsets, image shapes, widths, depths, tapped blocks, decoder
+widths, 1 or 4 channel-attention windows, with / without cross-task reweighting, ConvHead / DEConvHead, batch 1..3 --
+through (a) the oracle restatement against the UNMODIFIED reference (where its tree is present) and (b) the product's
+launch plan, kernels emulated by tests/emul_ops.py, against the oracle. The named configurations pin particular shapes;
+this pins the bookkeeping (offsets, paddings of e / f to multiples of 8, level selection, per-task slices) in general."""
+import random
+
+import pytest
+import torch
+
+from oracle import ref_loader
+from oracle import taskprompter_ref as TPR
+
+N_OUT = {"semseg": None, "human_parts": None, "sal": 2, "normals": 3, "edge": 1, "depth": 1}
+
+
+def draw(seed):
+    rng = random.Random(seed)
+    tasks = rng.sample(list(N_OUT), rng.randint(1, 5))
+    cn = rng.choice([1, 1, 4])
+    step = 32 if cn == 4 else 16                         # the token grid must split into sqrt(cn) x sqrt(cn) windows
+    C = rng.choice([64, 128, 192])
+    depth = rng.choice([4, 5, 6])
+    cfg = dict(tasks=tasks, num_output={t: (N_OUT[t] or rng.randint(2, 9)) for t in tasks},
+               img_size=(step * rng.randint(1, 3) + (16 if cn == 1 else 0), step * rng.randint(1, 3) + (16 if cn == 1 else 0)),
+               patch=16, C=C, depth=depth, heads=C // 64, select=sorted(rng.sample(range(1, depth), 3)),
+               e=rng.choice([12, 20, 24, 30, 36]), f=rng.choice([16, 28, 32, 44]), chan_nheads=cn,
+               use_ctr=rng.random() < 0.5, name=f"random{seed}", prompt_len=1, head=rng.choice(["conv", "conv", "deconv"]))
+    return cfg, rng.choice([1, 2, 3])
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="reference tree not present")
+@pytest.mark.parametrize("seed", range(6))
+def test_oracle_vs_reference_on_random_geometries(seed):
+    cfg, B = draw(seed)
+    torch.manual_seed(seed)
+    model = ref_loader.build_taskprompter(cfg).eval()     # the reference's own modules and initialisation
+    for m in model.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.running_mean.normal_(0, 0.1)
+            m.running_var.uniform_(0.8, 1.2)
+    x = torch.randn(B, 3, *cfg["img_size"])
+    with torch.no_grad():
+        ref = model(x)
+        out = TPR.forward(model.state_dict(), cfg, x)
+    for t in cfg["tasks"]:
+        assert out[t].shape == ref[t].shape
+        assert (out[t] - ref[t]).abs().max() <= 3e-6 * ref[t].abs().max().clamp_min(1.0), (cfg, t)
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_launch_plan_vs_oracle_on_random_geometries(monkeypatch, seed):
+    import mtt_b200  # noqa: F401
+    from mtt_b200 import taskprompter as TP
+    import emul_ops
+
+    emul_ops.install(monkeypatch)
+    cfg, B = draw(seed)
+    sd = TPR.init_state_dict(cfg, seed=seed)
+    model = TP.build_from_config(cfg, nsplit=2, use_graph=False).eval()
+    model.load_state_dict(sd, strict=True)
+    torch.manual_seed(seed)
+    x = torch.randn(B, 3, *cfg["img_size"])
+    with torch.no_grad():
+        ref = TPR.forward(sd, cfg, x)
+        got = model.plan(B, torch.device("cpu")).run(x, graph=False)
+    for t in cfg["tasks"]:
+        assert got[t].shape == ref[t].shape
+        err = float((got[t] - ref[t]).norm() / ref[t].norm())
+        assert err < 2e-4, (cfg, t, err)
+
+
+# ---- InvPT -----------------------------------------------------------------------------------------------------------------
+def draw_invpt(seed):
+    rng = random.Random(1000 + seed)
+    tasks = rng.sample(list(N_OUT), rng.randint(1, 4))
+    C = rng.choice([128, 192])
+    depth = rng.choice([4, 5, 6])
+    cfg = dict(tasks=tasks, num_output={t: (N_OUT[t] or rng.randint(2, 9)) for t in tasks},
+               img_size=(64 * rng.randint(1, 2), 64 * rng.randint(1, 2)), patch=16, C=C, depth=depth, heads=C // 64,
+               select=sorted(rng.sample(range(1, depth), 3)), embed_dim=rng.choice([32, 48, 64]),
+               pred_const=rng.choice([8, 16]), down=2, name=f"random_ip{seed}")
+    return cfg, rng.choice([1, 2])
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_invpt_launch_plan_and_oracle_on_random_geometries(monkeypatch, seed):
+    """InvPT (IP transformer_net.py:22-38): launch plan (kernels emulated) against the oracle, and the oracle against the
+    unmodified reference where its tree is present."""
+    import mtt_b200  # noqa: F401
+    from mtt_b200 import invpt as IP
+    from oracle import invpt_ref as IPR
+    import emul_ops
+
+    emul_ops.install(monkeypatch)
+    cfg, B = draw_invpt(seed)
+    sd = IPR.init_state_dict(cfg, seed=seed)
+    model = IP.build_from_config(cfg, nsplit=2, use_graph=False).eval()
+    model.load_state_dict(sd, strict=True)
+    torch.manual_seed(seed)
+    x = torch.randn(B, 3, *cfg["img_size"])
+    with torch.no_grad():
+        ref = IPR.forward(sd, cfg, x)
+        got = model.plan(B, torch.device("cpu")).run(x, graph=False)
+    for t in cfg["tasks"]:
+        assert got[t].shape == ref[t].shape
+        assert float((got[t] - ref[t]).norm() / ref[t].norm()) < 2e-4, (cfg, t)
+        ri, gi = ref["inter_preds"][t], got["inter_preds"][t]
+        assert float((gi - ri).norm() / ri.norm()) < 2e-4, (cfg, t, "inter_preds")
+    if ref_loader.available():
+        torch.manual_seed(seed)
+        m = ref_loader.build_invpt(cfg).eval()
+        with torch.no_grad():
+            r2, o2 = m(x), IPR.forward(m.state_dict(), cfg, x)
+        for t in cfg["tasks"]:
+            assert (o2[t] - r2[t]).abs().max() <= 5e-6 * r2[t].abs().max().clamp_min(1.0), (cfg, t)
+
+
+def test_invpt_rejects_the_sizes_the_reference_rejects(monkeypatch):
+    """A 6 x 6 token grid (96 x 96 image): the reference's decoder concatenates maps of different sizes and raises; the
+    oracle restates that; the product says so explicitly before it launches anything."""
+    import mtt_b200  # noqa: F401
+    from mtt_b200 import invpt as IP
+    from oracle import invpt_ref as IPR
+    import emul_ops
+
+    emul_ops.install(monkeypatch)
+    cfg = dict(tasks=["edge", "semseg"], num_output={"edge": 1, "semseg": 5}, img_size=(96, 96), patch=16, C=128, depth=4,
+               heads=2, select=[1, 2, 3], embed_dim=32, pred_const=16, down=2, name="ip_6x6")
+    x = torch.randn(1, 3, 96, 96)
+    sd = IPR.init_state_dict(cfg, seed=0)
+    with pytest.raises(RuntimeError), torch.no_grad():
+        IPR.forward(sd, cfg, x)
+    if ref_loader.available():
+        with pytest.raises(RuntimeError), torch.no_grad():
+            ref_loader.build_invpt(cfg).eval()(x)
+    model = IP.build_from_config(cfg, nsplit=2, use_graph=False).eval()
+    with pytest.raises(ValueError, match="multiple of 4 x 4"):
+        model.plan(1, torch.device("cpu"))
+
+
+# ---- error behaviour and odd-but-legal arguments -----------------------------------------------------------------------
+_TP_BASE = dict(tasks=["semseg", "depth"], num_output={"semseg": 5, "depth": 1}, img_size=(64, 64), patch=16, C=128, depth=4,
+                heads=2, select=[1, 2, 3], e=24, f=32, use_ctr=True, chan_nheads=1, name="edge", prompt_len=1, head="conv")
+
+
+@pytest.mark.parametrize("change,match", [(dict(img_size=(48, 80), chan_nheads=4), "chan_nheads=4 must be a perfect square"),
+                                          (dict(chan_nheads=2), "chan_nheads=2 must be a perfect square"),
+                                          (dict(C=96, heads=2), "must be 64")])
+def test_taskprompter_says_what_it_does_not_support(monkeypatch, change, match):
+    """Geometries the kernels are not built for (or that fail inside the reference's rearrange, taskprompter.py:236) are
+    refused when the model is built / planned, with the reason -- never by a kernel reading out of bounds."""
+    import mtt_b200  # noqa: F401
+    from mtt_b200 import taskprompter as TP
+    import emul_ops
+
+    emul_ops.install(monkeypatch)
+    cfg = dict(_TP_BASE, **change)
+    with pytest.raises(ValueError, match=match):
+        TP.build_from_config(cfg, nsplit=2, use_graph=False).eval().plan(1, torch.device("cpu"))
+
+
+def test_taskprompter_refuses_inputs_of_another_size(monkeypatch):
+    import mtt_b200  # noqa: F401
+    from mtt_b200 import taskprompter as TP
+    import emul_ops
+
+    emul_ops.install(monkeypatch)
+    model = TP.build_from_config(dict(_TP_BASE), nsplit=2, use_graph=False).eval()
+    for shape in ((1, 3, 64, 96), (1, 3, 50, 64)):          # the reference asserts on these in PatchEmbed (timm)
+        with pytest.raises(ValueError, match="expected fp32 input"):
+            model.plan(1, torch.device("cpu")).run(torch.randn(*shape), graph=False)
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="reference tree not present")
+@pytest.mark.parametrize("select", [[1, 2, 4], [0, 2, 3], [2, 2, 3], [3, 2, 1]])
+def test_unusual_select_lists_follow_the_reference(monkeypatch, select):
+    """select_list entries past the depth, repeated, zero or out of order: the reference taps a level when
+    `idx + 1 in select_list` (taskprompter.py:404-411), so such lists simply tap fewer / other blocks. Same here."""
+    import mtt_b200  # noqa: F401
+    from mtt_b200 import taskprompter as TP
+    import emul_ops
+
+    emul_ops.install(monkeypatch)
+    cfg = dict(_TP_BASE, select=select)
+    torch.manual_seed(0)
+    ref_model = ref_loader.build_taskprompter(cfg).eval()
+    sd = ref_model.state_dict()
+    x = torch.randn(2, 3, 64, 64)
+    model = TP.build_from_config(cfg, nsplit=2, use_graph=False).eval()
+    model.load_state_dict(sd, strict=True)
+    with torch.no_grad():
+        ref = ref_model(x)
+        got = model.plan(2, torch.device("cpu")).run(x, graph=False)
+    for t in cfg["tasks"]:
+        assert float((got[t] - ref[t]).norm() / ref[t].norm()) < 2e-4, t
