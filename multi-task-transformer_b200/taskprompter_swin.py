@@ -166,6 +166,18 @@ class TaskPrompterSwin(nn.Module):
         ds_size = [int(s * self.img_ds_ratio) for s in img_size]                         # TP:590
         self.patch_embed = SwinPatchEmbed(ds_size, patch_size, in_chans, embed_dim)
         self.patch_grid = self.patch_embed.grid_size
+        for i in range(self.num_layers - 1):              # PatchMerging halves each map (TP taskprompter_swin.py:438
+            gh, gw = self.patch_grid[0] // 2 ** i, self.patch_grid[1] // 2 ** i     # asserts "x size (H*W) are not even")
+            if gh % 2 or gw % 2:
+                raise ValueError(f"TaskPrompterSwin: the stage-{i} token map {gh} x {gw} (image {tuple(img_size)} x ratio "
+                                 f"{self.img_ds_ratio} / patch {patch_size}) must be even on both axes for PatchMerging; the "
+                                 "reference asserts the same")
+        cnh = int(round(math.sqrt(p.chan_nheads)))
+        for i in range(self.num_layers):                  # the channel gate of level i is a cnh x cnh grid of windows over its map
+            gh, gw = self.patch_grid[0] // 2 ** i, self.patch_grid[1] // 2 ** i     # (TP taskprompter_swin.py:738-763)
+            if cnh * cnh != p.chan_nheads or gh % cnh or gw % cnh:
+                raise ValueError(f"TaskPrompterSwin: chan_nheads={p.chan_nheads} must be a perfect square whose root divides "
+                                 f"every level's token map (level {i}: {gh} x {gw}); the reference fails on such sizes too")
         assert p.prompt_len == 1, "prompt_len != 1 is unsupported (as in the reference's channel branch)"
         self.prompts_len = len(tasks) * p.prompt_len
         self.task_prompts = nn.Parameter(torch.ones(self.prompts_len, embed_dim))

@@ -194,3 +194,81 @@ def test_unusual_select_lists_follow_the_reference(monkeypatch, select):
         got = model.plan(2, torch.device("cpu")).run(x, graph=False)
     for t in cfg["tasks"]:
         assert float((got[t] - ref[t]).norm() / ref[t].norm()) < 2e-4, t
+
+
+# ---- Swin TaskPrompter ------------------------------------------------------------------------------------------------------
+def draw_swin(seed):
+    rng = random.Random(2000 + seed)
+    tasks = rng.sample(["semseg", "sal", "normals", "edge", "depth"], rng.randint(1, 3))
+    ed = rng.choice([16, 32])
+    hd = rng.choice([16, ed])                               # head dim 16 or 32 (the two window-attention instantiations)
+    cn = rng.choice([1, 1, 4])
+    cnh = 2 if cn == 4 else 1
+    ratio = rng.choice([1.0, 1.0, 0.75])
+    # token maps (image x ratio / 4) must stay even through three PatchMergings and split into cnh x cnh windows at every level:
+    # image multiples of 32 cnh at ratio 1, of 128 cnh at ratio 0.75 (x 0.75 -> multiples of 96 = 4 * 8 * 3)
+    if ratio == 1.0:
+        img = (32 * cnh * rng.randint(1, 3), 32 * cnh * rng.randint(1, 4))
+    else:
+        img = (128 * cnh * rng.randint(1, 2), 128 * cnh * rng.randint(1, 2))
+    cfg = dict(tasks=tasks, num_output={t: (N_OUT[t] or rng.randint(2, 7)) for t in tasks}, img_size=img, patch=4,
+               embed_dim=ed, depths=(2, 2, rng.choice([2, 4]), 2), heads=tuple(max(1, (ed * 2 ** i) // hd) for i in range(4)),
+               window=rng.choice([4, 6, 8]), img_ds_ratio=ratio, level_embed_dim=rng.choice([10, 12, 16]),
+               f=rng.choice([20, 24]), chan_embed_dim=16, chan_nheads=cn, head=rng.choice(["conv", "deconv"]),
+               name=f"random_swin{seed}", prompt_len=1)
+    return cfg, rng.choice([1, 2])
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_swin_launch_plan_and_oracle_on_random_geometries(monkeypatch, seed):
+    """Swin TaskPrompter (TP taskprompter_swin.py:542-774): shifted windows clipped / padded to the map, 0.75 input
+    down-scaling, 1 or 4 channel windows, both head types. Plan (kernels emulated) against the oracle; the oracle against the
+    unmodified reference where its tree is present."""
+    import mtt_b200  # noqa: F401
+    from mtt_b200 import taskprompter_swin as TS
+    from oracle import taskprompter_swin_ref as TSR
+    import emul_ops
+
+    emul_ops.install(monkeypatch)
+    cfg, B = draw_swin(seed)
+    sd = TSR.init_state_dict(cfg, seed=seed)
+    torch.manual_seed(seed)
+    x = torch.randn(B, 3, *cfg["img_size"])
+    model = TS.build_from_config(cfg, nsplit=2, use_graph=False).eval()
+    model.load_state_dict(sd, strict=False)              # index / mask buffers are derived, not parameters
+    with torch.no_grad():
+        ref = TSR.forward(sd, cfg, x)
+        got = model.plan(B, torch.device("cpu")).run(x, graph=False)
+    for t in cfg["tasks"]:
+        assert got[t].shape == ref[t].shape
+        assert float((got[t] - ref[t]).norm() / ref[t].norm()) < 2e-4, (cfg, t)
+    if ref_loader.available():
+        torch.manual_seed(seed)
+        m = ref_loader.build_taskprompter_swin(cfg).eval()
+        with torch.no_grad():
+            r2, o2 = m(x), TSR.forward(m.state_dict(), cfg, x)
+        for t in cfg["tasks"]:
+            assert (o2[t] - r2[t]).abs().max() <= 5e-6 * r2[t].abs().max().clamp_min(1.0), (cfg, t)
+
+
+@pytest.mark.parametrize("change,match", [(dict(img_size=(128, 96), img_ds_ratio=0.75), "must be even on both axes"),
+                                          (dict(img_size=(96, 64), chan_nheads=4), "chan_nheads=4 must be a perfect square")])
+def test_swin_rejects_the_sizes_the_reference_rejects(change, match):
+    """PatchMerging asserts even maps (TP taskprompter_swin.py:438) and the channel gate needs every level's map to split into
+    sqrt(chan_nheads)^2 windows (the reference's torch.cat fails at :763 otherwise): refused when the model is built."""
+    import mtt_b200  # noqa: F401
+    from mtt_b200 import taskprompter_swin as TS
+    from oracle import taskprompter_swin_ref as TSR
+
+    cfg = dict(tasks=["depth"], num_output={"depth": 1}, img_size=(64, 96), patch=4, embed_dim=16, depths=(2, 2, 2, 2),
+               heads=(1, 2, 4, 8), window=4, img_ds_ratio=1.0, level_embed_dim=12, f=24, chan_embed_dim=16, chan_nheads=1,
+               head="conv", name="swin_bad", prompt_len=1)
+    cfg.update(change)
+    with pytest.raises(ValueError, match=match):
+        TS.build_from_config(cfg, nsplit=2, use_graph=False)
+    x = torch.randn(1, 3, *cfg["img_size"])
+    with pytest.raises((RuntimeError, AssertionError)), torch.no_grad():
+        TSR.forward(TSR.init_state_dict(cfg, seed=0), cfg, x)
+    if ref_loader.available():
+        with pytest.raises((RuntimeError, AssertionError)), torch.no_grad():
+            ref_loader.build_taskprompter_swin(cfg).eval()(x)
