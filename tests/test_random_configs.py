@@ -272,3 +272,59 @@ def test_swin_rejects_the_sizes_the_reference_rejects(change, match):
     if ref_loader.available():
         with pytest.raises((RuntimeError, AssertionError)), torch.no_grad():
             ref_loader.build_taskprompter_swin(cfg).eval()(x)
+
+
+# ---- the training step ---------------------------------------------------------------------------------------------------
+def draw_train(seed):
+    rng = random.Random(3000 + seed)
+    tasks = rng.sample(list(N_OUT), rng.randint(1, 4))
+    cn = rng.choice([1, 1, 4])
+    step = 32 if cn == 4 else 16
+    C = rng.choice([64, 128])
+    depth = rng.choice([4, 5])
+    cfg = dict(tasks=tasks, num_output={t: (N_OUT[t] or rng.randint(2, 7)) for t in tasks},
+               img_size=(step * rng.randint(1, 2) + (16 if cn == 1 else 0), step * rng.randint(1, 2) + (16 if cn == 1 else 0)),
+               patch=16, C=C, depth=depth, heads=C // 64, select=sorted(rng.sample(range(1, depth), 3)),
+               e=rng.choice([12, 20, 24]), f=rng.choice([16, 28, 36]), chan_nheads=cn, use_ctr=rng.random() < 0.5,
+               name=f"random_train{seed}", prompt_len=1, head="conv", drop_path_rate=0.2)
+    return cfg, rng.choice([2, 3])
+
+
+@pytest.mark.parametrize("seed", [0, 4, 6, 7])
+def test_training_step_on_random_geometries(monkeypatch, seed):
+    """TrainStep (train-mode forward with replayed DropPath draws, hand-scheduled reverse pass; kernels emulated) against
+    torch autograd of the oracle's train-mode restatement, for the same upstream gradient: forward 2e-4, every parameter
+    gradient 5e-3 of max(|g|, 1e-4 |all gradients|)."""
+    import mtt_b200  # noqa: F401
+    from mtt_b200 import taskprompter as TP
+    from mtt_b200.train import TrainStep
+    import emul_ops
+
+    emul_ops.install(monkeypatch)
+    cfg, B = draw_train(seed)
+    sd = TPR.init_state_dict(cfg, seed=seed)
+    model = TP.build_from_config(cfg, use_graph=False)
+    model.load_state_dict(sd, strict=True)
+    ts = TrainStep(model, lr=1e-4)
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, 3, *cfg["img_size"], generator=g)
+    masks = [torch.rand(B, 1, 1, generator=g) for _ in range(4 * cfg["depth"])]
+    ts.zero_grad()
+    with torch.no_grad():
+        out = ts.forward(x, drop_rand=masks)
+    gout = {t: torch.randn(out[t].shape, generator=g) for t in cfg["tasks"]}
+    with torch.no_grad():
+        ts.backward(gout)
+    sdo = {k: v.clone() for k, v in sd.items()}
+    params = {k: v.requires_grad_(True) for k, v in sdo.items() if v.is_floating_point() and "running_" not in k}
+    sdo.update(params)
+    with TPR.train_mode(0.2, rand=masks):
+        ref = TPR.forward(sdo, cfg, x)
+    for t in cfg["tasks"]:
+        assert float((out[t] - ref[t].detach()).norm() / ref[t].detach().norm()) < 2e-4, (cfg, t)
+    torch.autograd.backward([ref[t] for t in cfg["tasks"]], [gout[t] for t in cfg["tasks"]])
+    total = float(torch.sqrt(sum((v.grad ** 2).sum() for v in params.values() if v.grad is not None)))
+    for k, v in params.items():
+        want = v.grad if v.grad is not None else torch.zeros_like(v)
+        err = float((ts.G_(k).detach().cpu() - want).norm()) / max(float(want.norm()), 1e-4 * total)
+        assert err < 5e-3, (cfg, k, err)
