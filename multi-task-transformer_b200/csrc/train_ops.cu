@@ -107,7 +107,6 @@ int launch_colreduce(Op op, long long rows, int cols, float* out1, float* out2, 
   if (rb > cap) rb = cap;
   if (rb < 1) rb = 1;
   colreduce_kernel<Op><<<dim3(cb, (unsigned)rb), 256, 0, st>>>(op, rows, cols, out1, out2);
-  count_launch();
   return check_launch(what);
 }
 
@@ -780,7 +779,6 @@ extern "C" int mtt_layernorm_bwd(const float* x, int64_t ldx, const float* dy, i
     return set_error(MTT_ERR_BAD_SHAPE, "mtt_layernorm_bwd: bad arguments");
   ln_bwd_rows_kernel<<<row_blocks(rows), 256, 0, ST>>>(x, ldx, dy, lddy, gamma, eps, rows, cols, dx, lddx, accumulate_dx,
                                                        stats_ws);
-  count_launch();
   int rc = check_launch("mtt_layernorm_bwd(rows)");
   if (rc || !dgamma) return rc;
   return launch_colreduce(LnBwdOp{x, ldx, dy, lddy, stats_ws}, rows, cols, dbeta, dgamma, ST, "mtt_layernorm_bwd(cols)");
@@ -791,7 +789,6 @@ extern "C" int mtt_act_split(const float* pre, int64_t ld, int64_t rows, int32_t
   if (!pre || !out_hi || rows <= 0 || cols <= 0) return set_error(MTT_ERR_BAD_SHAPE, "mtt_act_split: bad arguments");
   act_split_kernel<<<row_blocks(rows), 256, 0, ST>>>(pre, ld, rows, cols, act, static_cast<__nv_bfloat16*>(out_hi),
                                                      static_cast<__nv_bfloat16*>(out_lo), ldo);
-  count_launch();
   return check_launch("mtt_act_split");
 }
 
@@ -799,7 +796,6 @@ extern "C" int mtt_act_bwd(const float* pre, int64_t ld, const float* dy, int64_
                            int32_t act, float* dx, int64_t lddx, mtt_stream_t stream) {
   if (!pre || !dy || !dx || rows <= 0 || cols <= 0) return set_error(MTT_ERR_BAD_SHAPE, "mtt_act_bwd: bad arguments");
   act_bwd_kernel<<<row_blocks(rows), 256, 0, ST>>>(pre, ld, dy, lddy, rows, cols, act, dx, lddx);
-  count_launch();
   return check_launch("mtt_act_bwd");
 }
 
@@ -807,7 +803,6 @@ extern "C" int mtt_axpy_rows(const float* base, int64_t ldb, const float* src, i
                              int64_t rows, int32_t cols, float* dst, int64_t ldd, mtt_stream_t stream) {
   if (!src || !dst || rows <= 0 || cols <= 0) return set_error(MTT_ERR_BAD_SHAPE, "mtt_axpy_rows: bad arguments");
   axpy_rows_kernel<<<row_blocks(rows), 256, 0, ST>>>(base, ldb, src, lds, row_scale, rows, cols, dst, ldd);
-  count_launch();
   return check_launch("mtt_axpy_rows");
 }
 
@@ -823,7 +818,6 @@ extern "C" int mtt_transpose_planes(const void* in_hi, const void* in_lo, int64_
                                                static_cast<const __nv_bfloat16*>(in_lo), ld_in, ib, R, C,
                                                static_cast<__nv_bfloat16*>(out_hi), static_cast<__nv_bfloat16*>(out_lo),
                                                ld_out, ob, B);
-  count_launch();
   return check_launch("mtt_transpose_planes");
 }
 
@@ -838,7 +832,6 @@ extern "C" int mtt_bn_finalize(const float* sums, float count, int32_t cols, flo
   if (!sums || !mean_rstd || cols <= 0 || count <= 0.f) return set_error(MTT_ERR_BAD_SHAPE, "mtt_bn_finalize: bad arguments");
   bn_finalize_kernel<<<(cols + 127) / 128, 128, 0, ST>>>(sums, count, cols, eps, momentum, mean_rstd, running_mean,
                                                          running_var);
-  count_launch();
   return check_launch("mtt_bn_finalize");
 }
 
@@ -850,7 +843,6 @@ extern "C" int mtt_bn_act(const float* x, int64_t ldx, int64_t rows, int32_t col
   bn_act_kernel<<<row_blocks(rows), 256, 0, ST>>>(x, ldx, rows, cols, mean_rstd, gamma, beta, act, out_f32, ldo,
                                                   static_cast<__nv_bfloat16*>(out_hi), static_cast<__nv_bfloat16*>(out_lo),
                                                   ldbf);
-  count_launch();
   return check_launch("mtt_bn_act");
 }
 
@@ -871,7 +863,6 @@ extern "C" int mtt_bn_bwd_apply(const float* x, int64_t ldx, const float* dy, in
     return set_error(MTT_ERR_BAD_SHAPE, "mtt_bn_bwd_apply: bad arguments");
   bn_bwd_apply_kernel<<<row_blocks(rows), 256, 0, ST>>>(x, ldx, dy, lddy, rows, cols, mean_rstd, gamma, beta, act, sums,
                                                         count, dx, lddx);
-  count_launch();
   return check_launch("mtt_bn_bwd_apply");
 }
 
@@ -882,7 +873,6 @@ extern "C" int mtt_attn_delta(const float* dO, int64_t lddo, const void* o_hi, c
   attn_delta_kernel<<<row_blocks((long long)B * N), 256, 0, ST>>>(dO, lddo, static_cast<const __nv_bfloat16*>(o_hi),
                                                                 static_cast<const __nv_bfloat16*>(o_lo), ldo, B, N, H,
                                                                 head_dim, delta);
-  count_launch();
   return check_launch("mtt_attn_delta");
 }
 
@@ -897,7 +887,6 @@ extern "C" int mtt_attn_softmax_bwd(const float* S, const float* dP, const float
       S, dP, delta, ld, N, scale, d_raw, T, static_cast<__nv_bfloat16*>(ds_hi), static_cast<__nv_bfloat16*>(ds_lo),
       static_cast<__nv_bfloat16*>(pt_hi), static_cast<__nv_bfloat16*>(pt_lo), static_cast<__nv_bfloat16*>(dst_hi),
       static_cast<__nv_bfloat16*>(dst_lo), ldbf);
-  count_launch();
   return check_launch("mtt_attn_softmax_bwd");
 }
 
@@ -909,7 +898,6 @@ extern "C" int mtt_bilinear_bwd(const float* dy, int64_t lddy, int32_t nchw, int
   const long long total = (long long)B * H2 * W2;
   const unsigned blocks = nchw ? (unsigned)((total + 255) / 256) : row_blocks(total);
   bilinear_bwd_kernel<<<blocks, 256, 0, ST>>>(dy, lddy, nchw, B, h, w, C, H2, W2, (float)h / H2, (float)w / W2, dx, lddx);
-  count_launch();
   return check_launch("mtt_bilinear_bwd");
 }
 
@@ -924,10 +912,8 @@ extern "C" int mtt_gate_bwd(const float* x, int64_t ldx, int64_t x_group_rows, i
   gate_bwd_kernel<<<row_blocks((long long)B * gh * gw), 256, 0, ST>>>(x, ldx, x_group_rows, x_row_offset, prompt_logits,
                                                                     chan_logits, task, B, T, N, H, C, gh, gw, nh, nw, dys,
                                                                     dyc, lddy, dx, lddx, d_prompt_logits);
-  count_launch();
   gate_chan_bwd_kernel<<<dim3((C + 31) / 32, B * nh * nw), 256, 0, ST>>>(x, ldx, x_group_rows, x_row_offset, task, T, C, gh,
                                                                         gw, nh, nw, dyc, lddy, d_chan_logits);
-  count_launch();
   return check_launch("mtt_gate_bwd");
 }
 
@@ -939,7 +925,6 @@ extern "C" int mtt_chan_logits_bwd(const float* d_rc, const float* cp, const voi
   chan_logits_bwd_kernel<<<row_blocks((long long)B * gh * gw), 256, 0, ST>>>(
       d_rc, cp, static_cast<const __nv_bfloat16*>(xn_hi), static_cast<const __nv_bfloat16*>(xn_lo), ldx, B, N, T, C, gh, gw,
       nh, nw, dcp, dxn, lddx);
-  count_launch();
   return check_launch("mtt_chan_logits_bwd");
 }
 
@@ -954,10 +939,8 @@ extern "C" int mtt_ctr_bwd(const float* dnew, const float* F, int32_t T, int64_t
   int chunks = (rows_per_batch + 63) / 64;
   if (chunks > 32) chunks = 32;
   ctr_dw_kernel<<<dim3(T * T, B, chunks), 256, 0, ST>>>(dnew, F, T, M, C, ld, rows_per_batch, dw_ws);
-  count_launch();
   ctr_weights_bwd_kernel<<<(B * T * T + 63) / 64, 64, 0, ST>>>(prompt_logits, B, H, T, N, w0, b0, w2, dw_ws,
                                                                d_prompt_logits, dw0, db0, dw2, db2);
-  count_launch();
   return check_launch("mtt_ctr_bwd");
 }
 
@@ -970,7 +953,6 @@ extern "C" int mtt_im2col3x3_t(const float* x, int64_t ldx, int32_t B, int32_t H
                       (!out_lo || reinterpret_cast<uintptr_t>(out_lo) % 4 == 0);
   im2col3x3_t_kernel<<<dim3((unsigned)((P + 63) / 64), cb), 256, 0, ST>>>(
       x, ldx, B, H, W, C, static_cast<__nv_bfloat16*>(out_hi), static_cast<__nv_bfloat16*>(out_lo), ldo, vec_out);
-  count_launch();
   return check_launch("mtt_im2col3x3_t");
 }
 
@@ -981,7 +963,6 @@ extern "C" int mtt_im2col_patch_t(const float* img, int32_t B, int32_t Cin, int3
   const long long total = (long long)Cin * patch * patch * B * (H / patch) * (W / patch);
   im2col_patch_t_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ST>>>(
       img, B, Cin, H, W, patch, static_cast<__nv_bfloat16*>(out_hi), static_cast<__nv_bfloat16*>(out_lo), ldo);
-  count_launch();
   return check_launch("mtt_im2col_patch_t");
 }
 
@@ -992,7 +973,6 @@ extern "C" int mtt_sumsq(const float* g, int64_t n, float* out, int32_t accumula
   const long long cap = (long long)sm_count() * 8;
   if (blocks > cap) blocks = cap;
   sumsq_kernel<<<(unsigned)blocks, 256, 0, ST>>>(g, n, out);
-  count_launch();
   return check_launch("mtt_sumsq");
 }
 
@@ -1006,6 +986,5 @@ extern "C" int mtt_adam_step(float* p, const float* g, float* m, float* v, int64
   const float bc1 = 1.f - powf(beta1, (float)step), bc2 = 1.f - powf(beta2, (float)step);
   adam_kernel<<<(unsigned)blocks, 256, 0, ST>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2, gnorm_sq,
                                                 max_norm, grad_scale);
-  count_launch();
   return check_launch("mtt_adam_step");
 }
