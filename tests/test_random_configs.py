@@ -328,3 +328,45 @@ def test_training_step_on_random_geometries(monkeypatch, seed):
         want = v.grad if v.grad is not None else torch.zeros_like(v)
         err = float((ts.G_(k).detach().cpu() - want).norm()) / max(float(want.norm()), 1e-4 * total)
         assert err < 5e-3, (cfg, k, err)
+
+
+# ---- accelerate(live reference model) end to end -----------------------------------------------------------------------
+@pytest.mark.skipif(not ref_loader.available(), reason="reference tree not present")
+@pytest.mark.parametrize("family,name", [("tp", "tp_tiny"), ("tp", "tp_tiny_de"), ("ip", "ip_tiny")])
+def test_accelerate_runs_a_live_reference_model_end_to_end(monkeypatch, family, name):
+    """accelerate(ref_model) on an instance of the UNMODIFIED reference (its own random initialisation, BatchNorm statistics
+    perturbed): the accelerated model's forward (launch plan, kernels emulated) reproduces the reference model's own
+    forward on the same input -- the drop-in claim of INTEGRATION.md section 1, not only equal state dicts."""
+    import mtt_b200  # noqa: F401
+    from mtt_b200 import configs
+    import emul_ops
+
+    emul_ops.install(monkeypatch)
+    if family == "tp":
+        from mtt_b200 import taskprompter as M
+        cfg = configs.taskprompter(name)
+        ref = ref_loader.build_taskprompter(cfg)
+    else:
+        from mtt_b200 import invpt as M
+        cfg = configs.invpt(name)
+        ref = ref_loader.build_invpt(cfg)
+    torch.manual_seed(5)
+    for m in ref.modules():
+        if isinstance(m, (torch.nn.BatchNorm2d, torch.nn.SyncBatchNorm)):
+            m.running_mean.normal_(0, 0.1)
+            m.running_var.uniform_(0.8, 1.2)
+    ref.eval()
+    mine = M.accelerate(ref, use_graph=False).eval()
+    x = torch.randn(2, 3, *cfg["img_size"])
+    with torch.no_grad():
+        want = ref(x)
+        got = {t: v.clone() for t, v in mine.plan(2, torch.device("cpu")).run(x, graph=False).items() if t in cfg["tasks"]}
+    for t in cfg["tasks"]:
+        assert got[t].shape == want[t].shape
+        assert float((got[t] - want[t]).norm() / want[t].norm()) < 2e-4, t
+    # accelerate() COPIES the parameters (DESIGN.md section 1): a later in-place update of the reference is not seen ...
+    with torch.no_grad():
+        next(ref.parameters()).add_(1.0)
+        again = mine.plan(2, torch.device("cpu")).run(x, graph=False)
+    for t in cfg["tasks"]:
+        assert torch.equal(again[t], got[t])
