@@ -86,3 +86,39 @@ def test_streamk_automatic_policy():
     assert split(16, 65) and split(20, 64) and split(12, 37)
     assert not split(204, 16) and not split(272, 16) and not split(68, 64) and not split(64, 65) and not split(48, 65)
     assert not split(20, 16)
+
+
+def test_streamk_schedule_invariants_on_random_problems():
+    """300 random (tiles, k-blocks, pairs) triples under the split-whenever-legal policy: exact cover, contributions only as
+    first pieces, no empty pair in a split launch, per-pair load within one k-block of the ideal share for the split part."""
+    import random
+
+    import mtt_b200  # noqa: F401
+    from mtt_b200 import lib
+
+    L = lib.load()
+    rng = random.Random(7)
+    n_split = 0
+    for _ in range(300):
+        pairs = rng.choice([74, 74, 66, 72, 33, 8])
+        tiles = rng.randint(1, 6 * pairs)
+        k_iters = rng.choice([1, 2, 4, 9, 16, 37, 48, 64, 65, 144])
+        sched = _schedule(L, tiles, k_iters, pairs)
+        cover, split = set(), False
+        for p, pieces in enumerate(sched):
+            for i, (t, k0, k1) in enumerate(pieces):
+                assert 0 <= t < tiles and 0 <= k0 < k1 <= k_iters
+                assert k0 == 0 or i == 0
+                split |= (k0, k1) != (0, k_iters)
+                for k in range(k0, k1):
+                    assert (t, k) not in cover
+                    cover.add((t, k))
+        assert len(cover) == tiles * k_iters
+        if split:
+            n_split += 1
+            assert all(sched)
+            r = tiles % pairs
+            whole = tiles // pairs                      # whole tiles every pair runs after its stream-K range
+            load = [sum(k1 - k0 for _, k0, k1 in pieces) for pieces in sched]
+            assert max(load) <= whole * k_iters + -(-r * k_iters // pairs), (tiles, k_iters, pairs)
+    assert n_split > 50
